@@ -1,0 +1,142 @@
+/*
+ * plb200.h — C ABI of libplb200.so: the B200 (sm_100a) descriptor linear-algebra hot path of
+ * PotentialLearning.jl (reference v0.2.7, citations are relative to /root/reference).
+ *
+ * This is the drop-in boundary. The reference has no FFI of its own (it is pure Julia and the
+ * boundary is multiple dispatch on exported generics), so every entry point below names the
+ * reference method body it replaces; INTEGRATION.md shows the Julia `ccall` stub per entry.
+ *
+ * Conventions
+ *  - all arithmetic is IEEE fp64; every function returns 0 on success, a PL_E* code otherwise;
+ *    the message of the last failure on the calling thread is pl_last_error().
+ *  - "host" entry points take HOST pointers owned by the caller. They copy in, launch, copy out and
+ *    are synchronous; no host pointer is retained after return (Julia only roots arrays for the
+ *    duration of a ccall).
+ *  - "_dev" entry points take DEVICE pointers (16-byte aligned, leading dimension even) plus a
+ *    cudaStream_t passed as void*; they only enqueue work on that stream (no sync) and are what
+ *    the multi-GPU host code and the benchmarks use.
+ *  - Matrices of descriptors are ROW-MAJOR n x d with leading dimension ld (elements). This is
+ *    byte-identical to Julia's column-major d x n produced by reduce(hcat, F).
+ *  - There is NO CPU fallback: without an sm_100 device pl_init fails and every entry errors.
+ */
+#ifndef PLB200_H
+#define PLB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* error codes */
+#define PL_OK 0
+#define PL_EINVAL 1   /* bad argument (shape, stride, alignment, enum) */
+#define PL_ECUDA 2    /* CUDA runtime / driver error (message has the CUDA string) */
+#define PL_ENODEV 3   /* no sm_100 device / library not initialised */
+#define PL_ENOMEM 4   /* device allocation failed */
+
+/* kernel ids (src/Kernels/kernels.jl) */
+#define PL_KERNEL_LINEAR 0 /* plain Gram X1*X2' (no epilogue); building block, e.g. X*Cinv      */
+#define PL_KERNEL_DOT 1    /* DotProduct: (a.b / sqrt((a.a)(b.b)))^alpha      kernels.jl:21-36  */
+#define PL_KERNEL_RBF 2    /* RBF(Euclidean): beta*exp(-0.5*d2/ell^2)         kernels.jl:51-75  */
+
+/* Euclidean Cinv kinds (src/Kernels/distances.jl:39-51) */
+#define PL_CINV_IDENTITY 0 /* Euclidean(dim): 1.0*I(dim)                      distances.jl:43-45 */
+#define PL_CINV_DIAGONAL 1 /* Diagonal{T}: cinv = d doubles                                      */
+#define PL_CINV_FULL 2     /* Symmetric{T}: cinv = d x d (symmetric, so row/col-major agree)     */
+
+/* which triangle(s) of a symmetric result are written. Bits refer to the ROW-MAJOR view out[i*ld+j]:
+ * PL_FILL_RM_UPPER writes j>=i, PL_FILL_RM_LOWER writes j<=i. Julia's Symmetric(K) (uplo=:U, column-major,
+ * kernels.jl:222) is PL_FILL_RM_LOWER of the same bytes; the unused triangle of the storage is written as 0,
+ * exactly as the reference leaves it (zeros(n,n), kernels.jl:216). */
+#define PL_FILL_RM_UPPER 1
+#define PL_FILL_RM_LOWER 2
+#define PL_FILL_FULL 3
+#define PL_FILL_JULIA_U PL_FILL_RM_LOWER
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+/* Bind the library to one CUDA device (-1: the current device). One process drives one GPU; multi-GPU jobs run
+ * one process per GPU and combine partials with one all-reduce. Fails with PL_ENODEV unless the
+ * device is compute capability 10.x. Idempotent. */
+int pl_init(int device);
+void pl_finalize(void);
+const char* pl_last_error(void);
+/* milliseconds spent by the last host entry point: kernels (CUDA events), H2D and D2H copies. */
+int pl_last_timing(double* kernel_ms, double* h2d_ms, double* d2h_ms);
+/* number of plb200 CUDA kernels launched by this process so far (benchmarks report it as gpu_launches). */
+int64_t pl_launch_count(void);
+/* bytes of device workspace currently held by the library. */
+int64_t pl_workspace_bytes(void);
+
+/* ---- Gram / kernel matrices: replaces KernelMatrix(F,k) kernels.jl:211-223 and (F1,F2,k) :229-244 ------ */
+
+/* Symmetric DotProduct kernel matrix of n features of length d.
+ *   K[i,j] = (x_i.x_j / sqrt((x_i.x_i)(x_j.x_j)))^alpha        (kernels.jl:35; alpha is the Int power)
+ * K: n x n, leading dimension ldk, triangles per `fill`. */
+int pl_gram_dot(const double* X, int64_t n, int64_t d, int64_t ldx, int alpha, double* K, int64_t ldk, int fill);
+
+/* Symmetric RBF(Euclidean) kernel matrix.
+ *   d2 = (x_i-x_j)' Cinv (x_i-x_j)  (distances.jl:58-60);  K[i,j] = beta*exp(-0.5*d2/ell^2) (kernels.jl:73-74).
+ * RBF.alpha is NOT applied (the reference never applies it); K[i,i] == beta exactly.
+ * cinv: NULL for PL_CINV_IDENTITY, d doubles for DIAGONAL, d*d doubles for FULL. */
+int pl_gram_rbf(const double* X, int64_t n, int64_t d, int64_t ldx, int cinv_kind, const double* cinv, double ell,
+                double beta, double* K, int64_t ldk, int fill);
+
+/* Rectangular kernel matrix KernelMatrix(F1,F2,k) (kernels.jl:229-244), written ROW-MAJOR n1 x n2:
+ *   K[i*ldk + j] = k(X1_i, X2_j).   (Julia column-major m x n: pass F2 as X1 and F1 as X2.)
+ * kernel_id: PL_KERNEL_LINEAR / DOT / RBF; alpha used by DOT; cinv_kind, cinv, ell, beta by RBF. */
+int pl_gram_cross(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, const double* X2, int64_t n2, int64_t ldx2,
+                  int64_t d, int alpha, int cinv_kind, const double* cinv, double ell, double beta, double* K,
+                  int64_t ldk);
+
+/* ---- weighted normal equations: replaces every A'WA / A'Wb site of src/Learning/linear-learn.jl ------- */
+/* A: row-major R x Kf (rows = [n_energy_rows energy rows ; force rows], linear-learn.jl:232-245).
+ * Row weights: w != NULL -> w[r] (ooc_learn! per-configuration weights, linear-learn.jl:341-352);
+ *              w == NULL -> r < n_energy_rows ? w_e : w_f      (Q = Diagonal([ws1*1_N; ws2*1_M]), :246-249).
+ * b: R right-hand sides or NULL (then AtWb is not touched).
+ * add_intercept != 0 prepends the column [1_N ; 0_M] (linear-learn.jl:239-241): outputs have order Kf+1 and the
+ * intercept is row/column 0. lambda is added to EVERY diagonal entry, intercept included (:253).
+ * AtWA: (Kf+ic) x (Kf+ic) full symmetric (exactly symmetric), AtWb: Kf+ic. */
+int pl_normal_eq(const double* A, int64_t R, int64_t Kf, int64_t lda, const double* w, int64_t n_energy_rows, double w_e,
+                 double w_f, const double* b, int add_intercept, double lambda, double* AtWA, double* AtWb);
+
+/* ---- covariance / second moment: replaces compute_eigen's Q (dimension_reduction.jl:11-12) and the
+ *      mean/centre of fit!(ds, ::PCAState) (pca_state.jl:34-37) ------------------------------------------ */
+/* X: row-major n x Kf.  center == 0: C = (1/n) sum_r x_r x_r'   (PCA / ActiveSubspace, pca.jl:28, as.jl:25).
+ * center != 0: if mean_given == 0, mean_inout <- sum_r x_r / n (pca_state.jl:35), else mean_inout is used as is
+ * (pca.m persists, pca_state.jl:34); C = (1/n) sum_r (x_r-m)(x_r-m)'. C: Kf x Kf full, exactly symmetric. */
+int pl_cov(const double* X, int64_t n, int64_t Kf, int64_t ldx, double* mean_inout, int mean_given, int center, double* C);
+
+/* ---- device-resident entry points (enqueue only; `stream` is a cudaStream_t) ---------------------------- */
+
+/* Kernel matrix on device data. dX2 == NULL -> symmetric (n2/ldx2 ignored, `fill` applies); otherwise rectangular
+ * row-major n1 x n2 (fill ignored). part/nparts shard the 128x128 output tiles round-robin (tile t is computed iff
+ * t % nparts == part); with packed != 0 the computed tiles are stored contiguously (tile-packed, 128*128 doubles
+ * each, in the order given by pl_gram_tile_coords) instead of densely in an n1 x n2 matrix with leading dim ldo. */
+int pl_gram_dev(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, const double* dX2, int64_t n2, int64_t ldx2,
+                int64_t d, int alpha, int cinv_kind, const double* dcinv, double ell, double beta, double* dOut,
+                int64_t ldo, int fill, int part, int nparts, int packed, void* stream);
+/* number of tiles part `part` of `nparts` owns for an n1 x n2 (n2 = 0: symmetric n1 x n1) kernel matrix */
+int64_t pl_gram_tile_count(int64_t n1, int64_t n2, int part, int nparts);
+/* tile-row / tile-column (units of 128) of the k-th tile owned by `part`; returns 0 or PL_EINVAL */
+int pl_gram_tile_coords(int64_t n1, int64_t n2, int part, int nparts, int64_t k, int64_t* ti, int64_t* tj);
+
+/* Partial weighted SYRK of a row shard: S = sum_r w_r (a_r-m)(a_r-m)' and, if db or n_energy_rows>0 requested,
+ * v = sum_r w_r b_r a_r, c = sum_{r<n_energy_rows} w_r a_r, s = [sum_{r<ne} w_r, sum_{r<ne} w_r b_r].
+ * dmean == NULL -> no centring. Outputs are UNSCALED sums so shards can be all-reduced:
+ *   dS  : Kf x Kf full symmetric, leading dim Kf
+ *   dvec: 2*Kf + 2 doubles = [v (Kf) ; c (Kf) ; s (2)]  (may be NULL if neither b nor the intercept is wanted) */
+int pl_syrk_dev(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dw, int64_t n_energy_rows, double w_e,
+                double w_f, const double* db, const double* dmean, double* dS, double* dvec, void* stream);
+/* Assemble (AtWA, AtWb) of order Kf+ic from (all-reduced) S / vec as pl_normal_eq defines them. */
+int pl_normal_eq_finish_dev(const double* dS, const double* dvec, int64_t Kf, int add_intercept, double lambda,
+                            double* dAtWA, double* dAtWb, void* stream);
+/* column sums of a row shard: dsum[k] = sum_r A[r,k] (deterministic two-stage reduction) */
+int pl_colsum_dev(const double* dA, int64_t R, int64_t Kf, int64_t lda, double* dsum, void* stream);
+/* dOut[i] = dIn[i] / denom, i < count (covariance 1/n and mean 1/n after the all-reduce) */
+int pl_scale_div_dev(const double* dIn, double denom, int64_t count, double* dOut, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLB200_H */

@@ -1,0 +1,434 @@
+"""oracle.py — CPU restatement (numpy / pure Python) of the reference algorithms on the hot path of
+PotentialLearning.jl v0.2.7. Citations are into /root/reference.
+
+TEST INFRASTRUCTURE ONLY. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product (potentiallearning.jl_b200/) never does and has no CPU fallback.
+
+PARITY UNPINNED: the reference is pure Julia; Julia is not installed here nor on the GPU box, and the reference's
+tests carry no golden values for this path (only properties and types). The functions below
+follow the reference line by line in its own operation order; tests/golden/make_golden.py cross-checks them against an
+independent extended-precision evaluation of the same formulas, and tests/test_oracle.py re-states every property
+the reference's tests assert (test/kernels/kernel_tests.jl, test/learning/linear_tests.jl,
+test/dimension_reduction/dimension_reduction_tests.jl).
+
+The C half (oracle/pl_oracle.c -> oracle/_build/libploracle.so) holds the same loops for sizes where Python is too slow.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libploracle.so")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# C half
+# ----------------------------------------------------------------------------------------------------------------
+def build_c(force: bool = False) -> str:
+    """gcc-compile oracle/pl_oracle.c (strict fp64, no fast-math, no FMA contraction)."""
+    src = os.path.join(_HERE, "pl_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(_LIB_PATH), exist_ok=True)
+        subprocess.check_call(
+            ["gcc", "-O2", "-fPIC", "-shared", "-fno-fast-math", "-ffp-contract=off", "-o", _LIB_PATH, src, "-lm"]
+        )
+    return _LIB_PATH
+
+
+_clib = None
+
+
+def clib():
+    global _clib
+    if _clib is None:
+        build_c()
+        L = ctypes.CDLL(_LIB_PATH)
+        dp = ctypes.POINTER(ctypes.c_double)
+        i64 = ctypes.c_int64
+        L.orc_kernel_matrix_sym.argtypes = [ctypes.c_int, dp, i64, i64, i64, ctypes.c_int, ctypes.c_int, dp, ctypes.c_double,
+                                            ctypes.c_double, dp, i64, i64, i64]
+        L.orc_kernel_matrix_cross.argtypes = [ctypes.c_int, dp, i64, i64, dp, i64, i64, i64, ctypes.c_int, ctypes.c_int, dp,
+                                              ctypes.c_double, ctypes.c_double, dp, i64]
+        L.orc_outer_sum.argtypes = [dp, i64, i64, i64, dp, dp, dp, dp, dp]
+        L.orc_atqa.argtypes = [dp, i64, i64, i64, dp, dp, dp, dp]
+        L.orc_atqa_blocked.argtypes = [dp, i64, i64, i64, dp, dp]
+        for f in (L.orc_kernel_matrix_sym, L.orc_kernel_matrix_cross, L.orc_outer_sum, L.orc_atqa, L.orc_atqa_blocked):
+            f.restype = ctypes.c_int
+        _clib = L
+    return _clib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _c64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Kernels: features, distances, kernels (src/Kernels)
+# ----------------------------------------------------------------------------------------------------------------
+def global_mean(local_descriptors) -> np.ndarray:
+    """compute_feature(B::LocalDescriptors, ::GlobalMean) = mean(get_values(B))  (features.jl:32-34):
+    sequential sum of the per-atom vectors, divided by natoms."""
+    vals = [np.asarray(v, dtype=np.float64) for v in local_descriptors]
+    s = vals[0].copy()
+    for v in vals[1:]:
+        s = s + v
+    return s / len(vals)
+
+
+def global_sum(local_descriptors) -> np.ndarray:
+    """sum(get_values(B)) (features.jl:19-21; linear-learning-problem.jl:75; pca_state.jl:23)."""
+    vals = [np.asarray(v, dtype=np.float64) for v in local_descriptors]
+    s = vals[0].copy()
+    for v in vals[1:]:
+        s = s + v
+    return s
+
+
+@dataclass
+class Euclidean:
+    """Euclidean(dim) / Euclidean(Cinv) (distances.jl:39-51). cinv: None (identity), 1-D (Diagonal) or 2-D (Symmetric)."""
+    dim: int
+    cinv: np.ndarray | None = None
+
+    @property
+    def kind(self) -> int:
+        return 0 if self.cinv is None else (1 if np.ndim(self.cinv) == 1 else 2)
+
+
+@dataclass
+class DotProduct:
+    alpha: int = 2  # kernels.jl:21-26
+
+
+@dataclass
+class RBF:
+    d: Euclidean
+    alpha: float = 1e-8  # stored, never applied (kernels.jl:73-74)
+    ell: float = 1.0
+    beta: float = 1.0
+
+
+def compute_distance(b1, b2, e: Euclidean) -> float:
+    """(B1 - B2)' * e.Cinv * (B1 - B2)  (distances.jl:58-60)."""
+    v = np.asarray(b1, dtype=np.float64) - np.asarray(b2, dtype=np.float64)
+    if e.cinv is None:
+        c = 1.0 * v  # 1.0*I(dim)
+    elif np.ndim(e.cinv) == 1:
+        c = np.asarray(e.cinv) * v
+    else:
+        return float((v @ np.asarray(e.cinv)) @ v)
+    return float(np.dot(v, c))
+
+
+def compute_kernel(a, b, k) -> float:
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if isinstance(k, DotProduct):
+        # (dot(A,B) / sqrt(dot(A,A)*dot(B,B)))^α   (kernels.jl:35)
+        return float((np.dot(a, b) / np.sqrt(np.dot(a, a) * np.dot(b, b))) ** int(k.alpha))
+    if isinstance(k, RBF):
+        d2 = compute_distance(a, b, k.d)
+        return float(k.beta * np.exp(-0.5 * d2 / k.ell ** 2))  # kernels.jl:73-74
+    raise TypeError(k)
+
+
+def kernel_matrix(F, k, use_c: bool | None = None) -> np.ndarray:
+    """KernelMatrix(F,k) (kernels.jl:211-223). Returns the n x n array whose [i, j] entry for i <= j is k(F_i, F_j) and
+    whose strict lower triangle is 0 — i.e. `K.data` of the reference's Symmetric(K) (uplo = :U)."""
+    X = np.ascontiguousarray(np.asarray(F, dtype=np.float64))
+    n, d = X.shape
+    if use_c is None:
+        use_c = n > 64
+    K = np.zeros((n, n))
+    if use_c:
+        kid, alpha, kind, cinv, ell, beta = _kernel_args(k)
+        # C writes Julia column-major K[i + j*ld] for j >= i; viewed row-major that is KT = K.T
+        KT = np.zeros((n, n))
+        rc = clib().orc_kernel_matrix_sym(kid, _p(X), n, d, d, alpha, kind, _p(cinv), ell, beta, _p(KT), n, 0, n)
+        assert rc == 0
+        return np.ascontiguousarray(KT.T)
+    for i in range(n):
+        for j in range(i, n):
+            K[i, j] = compute_kernel(X[i], X[j], k)
+    return K
+
+
+def symmetric(Kdata: np.ndarray) -> np.ndarray:
+    """Symmetric(K) with uplo=:U (kernels.jl:222): mirror the upper triangle."""
+    return np.triu(Kdata) + np.triu(Kdata, 1).T
+
+
+def kernel_matrix_cross(F1, F2, k, use_c: bool | None = None) -> np.ndarray:
+    """KernelMatrix(F1,F2,k) (kernels.jl:229-244): m x n."""
+    X1 = np.ascontiguousarray(np.asarray(F1, dtype=np.float64))
+    X2 = np.ascontiguousarray(np.asarray(F2, dtype=np.float64))
+    m, d = X1.shape
+    n = X2.shape[0]
+    if use_c is None:
+        use_c = m * n > 4096
+    if use_c:
+        kid, alpha, kind, cinv, ell, beta = _kernel_args(k)
+        KT = np.zeros((n, m))  # column-major m x n
+        rc = clib().orc_kernel_matrix_cross(kid, _p(X1), m, d, _p(X2), n, d, d, alpha, kind, _p(cinv), ell, beta, _p(KT), m)
+        assert rc == 0
+        return np.ascontiguousarray(KT.T)
+    K = np.zeros((m, n))
+    for i in range(m):
+        for j in range(n):
+            K[i, j] = compute_kernel(X1[i], X2[j], k)
+    return K
+
+
+def _kernel_args(k):
+    if isinstance(k, DotProduct):
+        return 1, int(k.alpha), 0, None, 1.0, 1.0
+    if isinstance(k, RBF):
+        cinv = None if k.d.cinv is None else _c64(k.d.cinv)
+        return 2, 0, k.d.kind, cinv, float(k.ell), float(k.beta)
+    raise TypeError(k)
+
+
+def kernel_matrix_rows(F, k, row_begin: int, row_end: int) -> int:
+    """Bounded sample of the reference pair loop: rows [row_begin, row_end) of the upper triangle (kernels.jl:217-221).
+    Returns the number of kernel evaluations done (used by bench.py to time the CPU baseline)."""
+    X = np.ascontiguousarray(np.asarray(F, dtype=np.float64))
+    n, d = X.shape
+    kid, alpha, kind, cinv, ell, beta = _kernel_args(k)
+    strip = np.zeros((n, row_end))  # column-major row_end x n: K[i + j*row_end], i < row_end
+    rc = clib().orc_kernel_matrix_sym(kid, _p(X), n, d, d, alpha, kind, _p(cinv), ell, beta, _p(strip), row_end, row_begin, row_end)
+    assert rc == 0
+    return sum(n - i for i in range(row_begin, row_end))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Learning: LinearProblem layout and normal-equation assembly (src/Learning)
+# ----------------------------------------------------------------------------------------------------------------
+@dataclass
+class UnivariateLinearProblem:
+    iv_data: list
+    dv_data: list
+    beta: np.ndarray
+    beta0: np.ndarray
+    sigma: np.ndarray = field(default_factory=lambda: np.array([1.0]))
+
+
+@dataclass
+class CovariateLinearProblem:
+    e: list
+    f: list
+    B: list
+    dB: list
+    beta: np.ndarray
+    beta0: np.ndarray
+
+
+def linear_problem(local_descriptors=None, energies=None, force_descriptors=None, forces=None):
+    """LinearProblem(ds) (linear-learning-problem.jl:71-145) on plain nested lists:
+    local_descriptors[c][atom] -> K-vector; force_descriptors[c][atom][xyz] -> K-vector; forces[c][atom] -> 3-vector."""
+    d_flag = local_descriptors is not None and energies is not None
+    fd_flag = force_descriptors is not None and forces is not None
+    if d_flag:
+        descriptors = [global_sum(ld) for ld in local_descriptors]  # :75 sum.(get_values.(...))
+    if fd_flag:
+        fdesc = [[np.asarray(comp, dtype=np.float64) for atom in cfg for comp in atom] for cfg in force_descriptors]  # :81 reduce(vcat, ...)
+        fvals = [np.concatenate([np.asarray(fa, dtype=np.float64) for fa in cfg]) for cfg in forces]  # :126 reduce(vcat, fi)
+        dB = [np.stack(fi, axis=1) for fi in fdesc]  # :127 reduce(hcat, fi): K x 3natoms
+    if d_flag and not fd_flag:
+        dim = len(descriptors[0])
+        return UnivariateLinearProblem(descriptors, list(energies), np.zeros(dim), np.zeros(1))
+    if fd_flag and not d_flag:
+        dim = dB[0].shape[0]
+        return UnivariateLinearProblem(dB, fvals, np.zeros(dim), np.zeros(1))
+    if d_flag and fd_flag:
+        dim = len(descriptors[0])
+        if dim != dB[0].shape[0]:
+            raise ValueError("Descriptors and Force Descriptors have different dimension!")
+        return CovariateLinearProblem(list(energies), fvals, descriptors, dB, np.zeros(dim), np.zeros(1))
+    raise ValueError("Either no (Energy, Descriptors) or (Forces, Force Descriptors) in DataSet")
+
+
+def wls_matrices(lp, ws, intercept: bool):
+    """A, b, q of learn!(lp, ws, int) (linear-learn.jl:183-197 univariate, :232-249 covariate)."""
+    if isinstance(lp, UnivariateLinearProblem):
+        iv = lp.iv_data
+        if np.ndim(iv[0]) == 1:
+            B_train = np.stack(iv, axis=0)  # reduce(hcat, iv)'
+            b = np.asarray(lp.dv_data, dtype=np.float64)
+        else:  # force-only: iv[i] is K x 3natoms
+            B_train = np.concatenate([m.T for m in iv], axis=0)
+            b = np.concatenate(lp.dv_data)
+        A = np.hstack([np.ones((B_train.shape[0], 1)), B_train]) if intercept else B_train
+        q = ws[0] * np.ones(len(b))
+        return A, b, q
+    B_train = np.stack(lp.B, axis=0)
+    dB_train = np.concatenate([m.T for m in lp.dB], axis=0)
+    e_train = np.asarray(lp.e, dtype=np.float64)
+    f_train = np.concatenate(lp.f)
+    A = np.vstack([B_train, dB_train])
+    if intercept:
+        int_col = np.concatenate([np.ones(B_train.shape[0]), np.zeros(dB_train.shape[0])])  # :240
+        A = np.hstack([int_col[:, None], A])
+    b = np.concatenate([e_train, f_train])
+    q = np.concatenate([ws[0] * np.ones(len(e_train)), ws[1] * np.ones(len(f_train))])
+    return A, b, q
+
+
+def normal_equations(A, b, q, lam: float = 0.0, use_c: bool = False):
+    """(A'*Q*A + λ*I, A'*Q*b)  (linear-learn.jl:200, :253)."""
+    A = _c64(A)
+    q = _c64(q)
+    b = _c64(b)
+    n = A.shape[1]
+    if use_c:
+        M = np.zeros((n, n))
+        v = np.zeros(n)
+        rc = clib().orc_atqa(_p(A), A.shape[0], n, n, _p(q), _p(b), _p(M), _p(v))
+        assert rc == 0
+    else:
+        QA = q[:, None] * A
+        M = A.T @ QA
+        v = A.T @ (q * b)
+    return M + lam * np.eye(n), v
+
+
+def learn_wls(lp, ws, intercept: bool, lam: float = 0.0):
+    """learn!(lp, ws, int; λ) (linear-learn.jl:178-215, 226-268): solve and update lp.β / lp.β0 in place."""
+    A, b, q = wls_matrices(lp, ws, intercept)
+    M, v = normal_equations(A, b, q, lam if isinstance(lp, CovariateLinearProblem) else 0.0)
+    try:
+        bs = np.linalg.solve(M, v)
+    except np.linalg.LinAlgError:
+        bs = np.linalg.pinv(M) @ v
+    if intercept:
+        lp.beta0[:] = bs[0]
+        lp.beta[:] = bs[1:]
+    else:
+        lp.beta[:] = bs
+    return M, v
+
+
+def ols_sums(iv_data, dv_data):
+    """AtA = sum(v*v' for v in iv), Atb = sum(v*b ...) (linear-learn.jl:16-17; also :45-49 per block).
+    v is a K-vector (b scalar) or a K x m matrix (b an m-vector)."""
+    K = np.asarray(iv_data[0]).shape[0]
+    AtA = np.zeros((K, K))
+    Atb = np.zeros(K)
+    for v, b in zip(iv_data, dv_data):
+        v = np.asarray(v, dtype=np.float64)
+        if v.ndim == 1:
+            AtA = AtA + np.outer(v, v)
+            Atb = Atb + v * b
+        else:
+            AtA = AtA + v @ v.T
+            Atb = Atb + v @ np.asarray(b, dtype=np.float64)
+    return AtA, Atb
+
+
+def ooc_accumulate(configs, ws=(30.0, 1.0), eweight_normalized="squared"):
+    """AtWA .+= A'*W*A; AtWb .+= A'*W*b per configuration (linear-learn.jl:328-357).
+    configs: iterable of (global_descr K, force_descrs 3natoms x K, ref_energy, ref_forces 3natoms)."""
+    AtWA = None
+    for gd, fdm, e, f in configs:
+        gd = np.asarray(gd, dtype=np.float64)
+        fdm = np.asarray(fdm, dtype=np.float64)
+        A = np.vstack([gd[None, :], fdm])
+        b = np.concatenate([[e], np.asarray(f, dtype=np.float64)])
+        natoms = fdm.shape[0] // 3
+        if eweight_normalized is None:
+            we = 1.0
+        elif eweight_normalized == "standard":
+            we = 1 / natoms
+        elif eweight_normalized == "squared":
+            we = 1 / natoms ** 2
+        else:
+            raise ValueError("eweight_normalized can only be nothing, :standard, or :squared")
+        w = np.concatenate([[we * ws[0]], ws[1] * np.ones(len(f))])
+        if AtWA is None:
+            AtWA = np.zeros((A.shape[1], A.shape[1]))
+            AtWb = np.zeros(A.shape[1])
+        AtWA += A.T @ (w[:, None] * A)
+        AtWb += A.T @ (w * b)
+    return AtWA, AtWb
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# DimensionReduction (src/DimensionReduction)
+# ----------------------------------------------------------------------------------------------------------------
+def second_moment(rows, use_c: bool | None = None) -> np.ndarray:
+    """Q = mean(di*di' for di in d) (dimension_reduction.jl:12): sequential sum of outer products, divided by n."""
+    X = np.ascontiguousarray(np.asarray(rows, dtype=np.float64))
+    n, K = X.shape
+    if use_c is None:
+        use_c = n * K * K > 2_000_000
+    if use_c:
+        S = np.zeros((K, K))
+        rc = clib().orc_outer_sum(_p(X), n, K, K, None, None, None, _p(S), None)
+        assert rc == 0
+    else:
+        S = np.zeros((K, K))
+        for r in range(n):
+            S = S + np.outer(X[r], X[r])
+    return S / n
+
+
+def compute_eigen(rows):
+    """eigen(Symmetric(Q)) (dimension_reduction.jl:11-14): ascending eigenvalues, eigenvectors in columns."""
+    Q = second_moment(rows)
+    lam, phi = np.linalg.eigh(symmetric(Q))
+    return lam, phi
+
+
+def select_eigendirections(rows, tol):
+    """dimension_reduction.jl:15-28."""
+    lam, phi = compute_eigen(rows)
+    lam, phi = lam[::-1], phi[:, ::-1]
+    if isinstance(tol, (int, np.integer)) and not isinstance(tol, bool):
+        W = phi[:, :tol]
+    else:
+        resid = 1.0 - np.cumsum(lam) / np.sum(lam)
+        W = phi[:, resid > tol]
+    return lam, W
+
+
+@dataclass
+class PCAState:
+    tol: float | int = 0.01
+    lam: np.ndarray | None = None
+    W: np.ndarray | None = None
+    m: np.ndarray | None = None  # [] in the reference
+
+
+def pcastate_fit(local_descriptors, pca: PCAState, force_descriptor_rows=None):
+    """fit!(ds, pca::PCAState) (pca_state.jl:20-40). As written in the reference the force-descriptor branch always throws
+    (undefined `fd`, pca_state.jl:29) and is swallowed, so only the global-sum descriptors are used; pass
+    force_descriptor_rows to opt into the intended stacked-rows mode (BASELINE config 4)."""
+    d = [global_sum(ld) for ld in local_descriptors]  # :23
+    if force_descriptor_rows is not None:
+        d = d + [np.asarray(r, dtype=np.float64) for r in force_descriptor_rows]
+    if pca.m is None:
+        s = d[0].copy()
+        for v in d[1:]:
+            s = s + v
+        pca.m = s / len(d)  # :35
+    dm = [di - pca.m for di in d]  # :37
+    pca.lam, pca.W = select_eigendirections(dm, pca.tol)
+    return pca
+
+
+def centered_cov(X, mean=None):
+    """(mean, (1/n) sum (x-m)(x-m)') with m = sum(x)/n when not supplied; vectorised (used at larger sizes)."""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    if mean is None:
+        mean = X.sum(axis=0) / n
+    Xc = X - mean
+    return mean, (Xc.T @ Xc) / n

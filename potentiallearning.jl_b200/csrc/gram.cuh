@@ -1,0 +1,259 @@
+// gram.cuh — kernel-matrix (Gram) kernel: out[i][j] = epilogue( sum_k A[i][k] * B[j][k] ).
+//
+// Replaces the scalar pair loops of KernelMatrix (reference src/Kernels/kernels.jl:211-223 symmetric, :229-244
+// rectangular) for compute_kernel(::DotProduct) (:30-36) and compute_kernel(::RBF) over Euclidean (:68-75,
+// distances.jl:58-60). Both operands are K-major (row-major n x d, contraction index contiguous) — "NT" geometry.
+//
+// Design (B200 / sm_100a):
+//   * persistent CTAs (one per SM), 128 x 128 output tile, BK = 16 doubles (= one 128-byte swizzle row) per stage,
+//     PL_GRAM_STAGES-deep TMA -> shared-memory ring guarded by full/empty mbarriers;
+//   * warps 8..11 form the TMA producer warpgroup (one elected lane works; the group hands its registers to the
+//     consumers with setmaxnreg), warps 0..7 are DMMA consumers laid out 4 (m) x 2 (n),
+//     each owning a 32 x 64 warp tile = 4 x 8 DMMA.8x8x4 tiles = 64 fp64 accumulators per thread;
+//   * fragments are read with 128-bit LDS: one load yields the k-pair (2c, 2c+1) of one row, feeding two DMMAs
+//     (the contraction index may be permuted freely as long as A and B agree). Bank conflicts are removed by a row
+//     permutation inside each 8-row group (fragment row g <-> tile row perm(g) = ((g&1)<<2)|(g>>1)) so that every
+//     quarter-warp touches 8 distinct 16-byte chunks of the 128B-swizzled tile; the permutation is undone in the
+//     epilogue index math (free);
+//   * symmetric mode computes only tiles tj >= ti, mirrors them on store (exact symmetry by construction), and on
+//     diagonal tiles loads the operand tile once;
+//   * the epilogue (normalise+power, or distance+exp) is fused; nothing but the final kernel matrix touches HBM.
+#pragma once
+#include "ptx.cuh"
+
+namespace plb {
+
+constexpr int GRAM_BM = 128;
+constexpr int GRAM_BN = 128;
+constexpr int GRAM_BK = 16;  // doubles per stage row: 128 bytes, the TMA 128B-swizzle span
+constexpr int GRAM_STAGES = 5;
+constexpr int GRAM_CONSUMER_WARPS = 8;
+constexpr int GRAM_THREADS = (GRAM_CONSUMER_WARPS + 4) * 32;  // 2 DMMA warpgroups + 1 producer warpgroup (setmaxnreg needs whole warpgroups)
+constexpr int PRODUCER_REGS = 24;
+constexpr int CONSUMER_REGS = 240;  // per SMSP: 2 x 240 + 24 = 504 <= 512 registers per lane
+constexpr int GRAM_TILE_BYTES = GRAM_BM * GRAM_BK * 8;  // 16 KB per operand per stage
+constexpr int GRAM_SMEM_BYTES = GRAM_STAGES * 2 * GRAM_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum { EPI_LINEAR = 0, EPI_DOT = 1, EPI_RBF = 2 };
+
+struct GramParams {
+  int64_t n1, n2;       // output rows (A operand rows) / cols (B operand rows); symmetric: n2 == n1
+  int64_t d;            // contraction length
+  double* out;          // dense: row-major, leading dim ldo ; packed: tile-packed (128*128 doubles per tile)
+  int64_t ldo;
+  const double* ra;     // per-row statistics of the A operand rows (DOT: 1/sqrt(x.x); RBF: quadratic form q_i)
+  const double* rb;     // same for B operand rows
+  int symmetric;        // only tiles tj >= ti, mirrored per `fill`
+  int same_operand;     // symmetric and A == B matrix: diagonal tiles load one operand tile
+  int fill;             // PL_FILL_* bits (symmetric only)
+  int packed;           // tile-packed output
+  int alpha;            // DOT power
+  double s;             // RBF: -0.5 / ell^2
+  double beta;          // RBF scale
+  int T1, T2;           // tile rows / tile cols
+  int64_t ntiles_total; // linear tile slots (symmetric: folded enumeration incl. a few invalid slots)
+  int part, nparts;     // tile sharding across GPUs: slot l is ours iff l % nparts == part
+};
+
+// Folded enumeration of the upper triangle of a T x T tile grid: tile row p is paired with row T-1-p so that every
+// pair has T+1 slots. Slot l -> (ti, tj); returns false for the (few) unused slots when T is odd.
+__host__ __device__ __forceinline__ bool gram_slot_to_tile(const int T1, const int T2, const int symmetric, int64_t l, int& ti, int& tj) {
+  if (!symmetric) {
+    ti = (int)(l / T2);
+    tj = (int)(l % T2);
+    return ti < T1;
+  }
+  const int T = T1;
+  const int p = (int)(l / (T + 1));
+  const int q = (int)(l % (T + 1));
+  if (q < T - p) {
+    ti = p;
+    tj = p + q;
+    return true;
+  }
+  const int p2 = T - 1 - p;
+  if (p2 <= p) return false;  // middle row of an odd T is not paired
+  ti = p2;
+  tj = p2 + (q - (T - p));
+  return true;
+}
+__host__ __device__ __forceinline__ int64_t gram_num_slots(int T1, int T2, int symmetric) {
+  if (!symmetric) return (int64_t)T1 * T2;
+  return (int64_t)((T1 + 1) / 2) * (T1 + 1);
+}
+
+__device__ __forceinline__ double ipow(double x, int a) {
+  // integer power by squaring (DotProduct alpha; Julia's x^n for Int n is accurate to <1 ulp, this is within a few)
+  if (a == 2) return x * x;
+  if (a == 1) return x;
+  bool neg = a < 0;
+  unsigned e = neg ? (unsigned)(-a) : (unsigned)a;
+  double r = 1.0, b = x;
+  while (e) {
+    if (e & 1u) r *= b;
+    b *= b;
+    e >>= 1;
+  }
+  return neg ? 1.0 / r : r;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
+gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GramParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle needs 1024-byte aligned tiles
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + GRAM_STAGES * 2 * GRAM_TILE_BYTES;  // full[S] then empty[S], 8 bytes each
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (GRAM_STAGES + s); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GRAM_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), GRAM_CONSUMER_WARPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int KT = (int)((p.d + GRAM_BK - 1) / GRAM_BK);
+  const int64_t slot0 = (int64_t)blockIdx.x * p.nparts + p.part;
+  const int64_t slot_stride = (int64_t)gridDim.x * p.nparts;
+
+  if (warp >= GRAM_CONSUMER_WARPS) {
+    // ------------------------------ TMA producer warpgroup (one elected lane works) ------------------------------
+    setmaxnreg_dec<PRODUCER_REGS>();
+    if (warp == GRAM_CONSUMER_WARPS && lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      uint32_t it = 0;
+      for (int64_t l = slot0; l < p.ntiles_total; l += slot_stride) {
+        int ti, tj;
+        if (!gram_slot_to_tile(p.T1, p.T2, p.symmetric, l, ti, tj)) continue;
+        const bool one_tile = p.same_operand && (ti == tj);
+        const uint32_t bytes = one_tile ? GRAM_TILE_BYTES : 2 * GRAM_TILE_BYTES;
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+          const int s = it % GRAM_STAGES;
+          const uint32_t ph = (it / GRAM_STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), bytes);
+          const uint32_t dstA = smem_base + s * 2 * GRAM_TILE_BYTES;
+          tma_load_2d(dstA, &tmA, full_bar(s), kt * GRAM_BK, ti * GRAM_BM);
+          if (!one_tile) tma_load_2d(dstA + GRAM_TILE_BYTES, &tmB, full_bar(s), kt * GRAM_BK, tj * GRAM_BN);
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------ DMMA consumers ------------------------------
+  setmaxnreg_inc<CONSUMER_REGS>();
+  const int wm = warp >> 1;  // 0..3 : 32-row slab
+  const int wn = warp & 1;   // 0..1 : 64-col slab
+  const int g = lane >> 2;
+  const int t = lane & 3;
+  const int pg = ((g & 1) << 2) | (g >> 1);  // tile row (within an 8-row group) served by fragment row g
+  // byte offset of this thread's 16B chunk inside a 128B row for k-half 0; k-half 1 is the same ^ 64
+  const uint32_t xo = (uint32_t)((t ^ pg) << 4);
+  const uint32_t offA0 = (uint32_t)((32 * wm + pg) * 128) + xo;  // + mt * 1024
+  const uint32_t offB0 = (uint32_t)((64 * wn + pg) * 128) + xo;  // + nt * 1024
+
+  uint32_t it = 0;
+  for (int64_t l = slot0; l < p.ntiles_total; l += slot_stride) {
+    int ti, tj;
+    if (!gram_slot_to_tile(p.T1, p.T2, p.symmetric, l, ti, tj)) continue;
+    const bool one_tile = p.same_operand && (ti == tj);
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt, ++it) {
+      const int s = it % GRAM_STAGES;
+      const uint32_t ph = (it / GRAM_STAGES) & 1u;
+      mbar_wait(full_bar(s), ph);
+      const uint32_t sA = smem_base + s * 2 * GRAM_TILE_BYTES;
+      const uint32_t sB = one_tile ? sA : sA + GRAM_TILE_BYTES;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double2 a[4], b[8];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) a[mt] = lds128(sA + ((offA0 + mt * 1024) ^ (uint32_t)(h << 6)));
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) b[nt] = lds128(sB + ((offB0 + nt * 1024) ^ (uint32_t)(h << 6)));
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(s));
+    }
+
+    // ------------------------------ fused epilogue ------------------------------
+    // accumulator (mt, nt, c) of lane (g, t) is element
+    //   i = 128*ti + 32*wm + 8*mt + perm(g),   j = 128*tj + 64*wn + 8*nt + perm(2t + c) = ... + t + 4c
+    const int64_t i_base = (int64_t)ti * GRAM_BM + 32 * wm + pg;  // + 8*mt
+    const int64_t j_base = (int64_t)tj * GRAM_BN + 64 * wn + t;   // + 8*nt + 4*c
+    const bool diag_tile = p.symmetric && (ti == tj);
+    double rbj[8][2];
+    if (EPI != EPI_LINEAR) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int64_t j = j_base + 8 * nt + 4 * c;
+          rbj[nt][c] = (j < p.n2) ? __ldg(p.rb + j) : 0.0;
+        }
+    }
+    // tile-packed output: tile k = (l - part) / nparts of this part, 128 x 128 row-major
+    double* const tile_out = p.out + ((l - p.part) / p.nparts) * (int64_t)(GRAM_BM * GRAM_BN);
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const int64_t i = i_base + 8 * mt;
+      const bool iok = i < p.n1;
+      double rai = 0.0;
+      if (EPI != EPI_LINEAR && iok) rai = __ldg(p.ra + i);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int64_t j = j_base + 8 * nt + 4 * c;
+          if (!iok || j >= p.n2) continue;
+          double v = acc[mt][nt][c];
+          if (EPI == EPI_DOT) {
+            v = ipow(v * rai * rbj[nt][c], p.alpha);
+            if (p.same_operand && i == j) v = 1.0;  // n/sqrt(n*n): the reference diagonal (kernels.jl:35)
+          } else if (EPI == EPI_RBF) {
+            double d2 = rai + rbj[nt][c] - 2.0 * v;
+            d2 = d2 < 0.0 ? 0.0 : d2;
+            v = p.beta * exp(p.s * d2);
+            if (p.symmetric && i == j) v = p.beta;  // d2(x,x) == 0 exactly in the reference
+          }
+          if (p.packed) {
+            tile_out[(i - (int64_t)ti * GRAM_BM) * GRAM_BN + (j - (int64_t)tj * GRAM_BN)] = v;
+          } else if (!p.symmetric) {
+            p.out[i * p.ldo + j] = v;
+          } else if (i == j) {
+            p.out[i * p.ldo + i] = v;
+          } else if (!(diag_tile && j < i)) {  // lower half of a diagonal tile is produced by mirroring
+            // unused triangle inside diagonal tiles is written as 0 (reference storage is zeros(n,n))
+            if (p.fill & 1) p.out[i * p.ldo + j] = v; else if (diag_tile) p.out[i * p.ldo + j] = 0.0;
+            if (p.fill & 2) p.out[j * p.ldo + i] = v; else if (diag_tile) p.out[j * p.ldo + i] = 0.0;
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace plb

@@ -1,0 +1,761 @@
+// plb200_api.cu — the C ABI of libplb200.so (include/plb200.h): context, workspaces, TMA descriptors, launches.
+// Everything here is plumbing around the three kernel families in gram.cuh / syrk.cuh / prelude.cuh.
+// There is deliberately no CPU code path: every entry point needs an sm_100 device.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/plb200.h"
+#include "gram.cuh"
+#include "prelude.cuh"
+#include "syrk.cuh"
+
+using namespace plb;
+
+namespace {
+
+thread_local char g_err[1024] = "";
+std::mutex g_mu;
+std::atomic<int64_t> g_launches{0};
+
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      cudaGetLastError();                                                                               \
+      return set_err(_e == cudaErrorMemoryAllocation ? PL_ENOMEM : PL_ECUDA, "%s failed: %s (%s:%d)", #expr, \
+                     cudaGetErrorString(_e), __FILE__, __LINE__);                                       \
+    }                                                                                                   \
+  } while (0)
+#define PL_TRY(expr)         \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != PL_OK) return _r; \
+  } while (0)
+#define LAUNCH_CHECK()                  \
+  do {                                  \
+    g_launches.fetch_add(1);            \
+    CUDA_TRY(cudaGetLastError());       \
+  } while (0)
+
+enum WsSlot {
+  WS_COLSUM_PARTIAL = 0,
+  WS_MEAN,
+  WS_XC1,
+  WS_XC2,
+  WS_Y1,
+  WS_Y2,
+  WS_STAT1,
+  WS_STAT2,
+  WS_PAD1,
+  WS_PAD2,
+  WS_PADC,
+  WS_SYRK_TILES,
+  WS_SYRK_VEC,
+  WS_H_IN1,
+  WS_H_IN2,
+  WS_H_IN3,
+  WS_H_IN4,
+  WS_H_OUT1,
+  WS_H_OUT2,
+  WS_H_S,
+  WS_H_VEC,
+  WS_NSLOTS
+};
+
+struct Ctx {
+  bool ready = false;
+  int device = -1;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  PFN_cuTensorMapEncodeTiled encode = nullptr;
+  void* ws[WS_NSLOTS] = {};
+  size_t ws_bytes[WS_NSLOTS] = {};
+  double t_kernel = 0, t_h2d = 0, t_d2h = 0;
+} g;
+
+int ws_get(int slot, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 16;
+  if (g.ws_bytes[slot] < bytes) {
+    if (g.ws[slot]) {
+      CUDA_TRY(cudaFree(g.ws[slot]));
+      g.ws[slot] = nullptr;
+      g.ws_bytes[slot] = 0;
+    }
+    // grow with 12.5% slack, 256-byte granularity
+    size_t want = (bytes + bytes / 8 + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&g.ws[slot], want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      want = (bytes + 255) & ~(size_t)255;
+      e = cudaMalloc(&g.ws[slot], want);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      g.ws[slot] = nullptr;
+      return set_err(PL_ENOMEM, "device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+    }
+    g.ws_bytes[slot] = want;
+  }
+  *out = g.ws[slot];
+  return PL_OK;
+}
+
+int need_ready() {
+  if (!g.ready) return set_err(PL_ENODEV, "plb200 is not initialised: call pl_init (needs an sm_100 GPU; there is no CPU fallback)");
+  return PL_OK;
+}
+
+int make_tmap_2d(CUtensorMap* tm, const double* ptr, int64_t dim0, int64_t dim1, int64_t ld, uint32_t box0, uint32_t box1) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || (ld & 1)) return set_err(PL_EINVAL, "TMA operand must be 16-byte aligned with an even leading dimension");
+  cuuint64_t gdim[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g.encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(PL_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (dims %lld x %lld, ld %lld)", (int)r, (long long)dim0, (long long)dim1, (long long)ld);
+  return PL_OK;
+}
+
+__global__ void pad_copy_kernel(const double* __restrict__ src, int64_t rows, int64_t cols, int64_t lds, double* __restrict__ dst, int64_t ldd) {
+  const int64_t total = rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / cols, c = e % cols;
+    dst[r * ldd + c] = src[r * lds + c];
+  }
+}
+
+// returns an operand that TMA / 128-bit loads can read: the original if aligned with even ld, else a padded copy
+int tma_operand(const double* src, int64_t rows, int64_t cols, int64_t ld, int slot, cudaStream_t st, const double** out, int64_t* ldout) {
+  if (!(reinterpret_cast<uintptr_t>(src) & 15u) && !(ld & 1)) {
+    *out = src;
+    *ldout = ld;
+    return PL_OK;
+  }
+  const int64_t ldp = (cols + 1) & ~(int64_t)1;
+  void* buf;
+  PL_TRY(ws_get(slot, (size_t)rows * ldp * 8, &buf));
+  const int64_t total = rows * cols;
+  int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  if (blocks < 1) blocks = 1;
+  pad_copy_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, ld, (double*)buf, ldp);
+  LAUNCH_CHECK();
+  *out = (const double*)buf;
+  *ldout = ldp;
+  return PL_OK;
+}
+
+int colsum(const double* dA, int64_t R, int64_t Kf, int64_t lda, double denom, double* dout, cudaStream_t st) {
+  const int64_t nblk = (R + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK;
+  void* part;
+  PL_TRY(ws_get(WS_COLSUM_PARTIAL, (size_t)(nblk > 0 ? nblk : 1) * Kf * 8, &part));
+  if (nblk > 0) {
+    const int64_t pairs = (Kf + 1) / 2;
+    dim3 grid((unsigned)((pairs + 127) / 128), (unsigned)nblk);
+    colsum_partial_kernel<<<grid, 128, 0, st>>>(dA, R, Kf, lda, (double*)part);
+    LAUNCH_CHECK();
+  }
+  colsum_final_kernel<<<(unsigned)((Kf + 127) / 128), 128, 0, st>>>((const double*)part, nblk, Kf, denom, dout);
+  LAUNCH_CHECK();
+  return PL_OK;
+}
+
+struct GramLaunch {
+  int epi;
+  const double *A, *B;
+  int64_t nA, ldA, nB, ldB, d;
+  const double *ra, *rb;
+  double* out;
+  int64_t ldo;
+  int symmetric, same_operand, fill, packed, part, nparts, alpha;
+  double s, beta;
+};
+
+int launch_gram(const GramLaunch& L, cudaStream_t st) {
+  if (L.nA == 0 || L.nB == 0) return PL_OK;
+  CUtensorMap tmA, tmB;
+  PL_TRY(make_tmap_2d(&tmA, L.A, L.d, L.nA, L.ldA, GRAM_BK, GRAM_BM));
+  PL_TRY(make_tmap_2d(&tmB, L.B, L.d, L.nB, L.ldB, GRAM_BK, GRAM_BN));
+  GramParams p;
+  p.n1 = L.nA;
+  p.n2 = L.nB;
+  p.d = L.d;
+  p.out = L.out;
+  p.ldo = L.ldo;
+  p.ra = L.ra;
+  p.rb = L.rb;
+  p.symmetric = L.symmetric;
+  p.same_operand = L.same_operand;
+  p.fill = L.fill;
+  p.packed = L.packed;
+  p.alpha = L.alpha;
+  p.s = L.s;
+  p.beta = L.beta;
+  p.T1 = (int)((L.nA + GRAM_BM - 1) / GRAM_BM);
+  p.T2 = (int)((L.nB + GRAM_BN - 1) / GRAM_BN);
+  p.ntiles_total = gram_num_slots(p.T1, p.T2, p.symmetric);
+  p.part = L.part;
+  p.nparts = L.nparts;
+  const int64_t mine = (p.ntiles_total - L.part + L.nparts - 1) / L.nparts;
+  if (mine <= 0) return PL_OK;
+  const int grid = (int)(mine < g.num_sms ? mine : g.num_sms);
+  switch (L.epi) {
+    case EPI_LINEAR: gram_kernel<EPI_LINEAR><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
+    case EPI_DOT: gram_kernel<EPI_DOT><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
+    case EPI_RBF: gram_kernel<EPI_RBF><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
+    default: return set_err(PL_EINVAL, "unknown epilogue %d", L.epi);
+  }
+  LAUNCH_CHECK();
+  return PL_OK;
+}
+
+template <int MODE>
+int launch_prep(const double* X, int64_t n, int64_t d, int64_t ldx, const double* mean, const double* cdiag, double* Xc, double* Y, int64_t ldc,
+                double* stat, cudaStream_t st) {
+  if (n == 0) return PL_OK;
+  const int64_t threads = n * 32;
+  prep_rows_kernel<MODE><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(X, n, d, ldx, mean, cdiag, Xc, Y, ldc, stat);
+  LAUNCH_CHECK();
+  return PL_OK;
+}
+
+int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, const double* dX2, int64_t n2, int64_t ldx2, int64_t d, int alpha,
+                  int cinv_kind, const double* dcinv, double ell, double beta, double* dOut, int64_t ldo, int fill, int part, int nparts, int packed,
+                  cudaStream_t st) {
+  PL_TRY(need_ready());
+  const bool sym = (dX2 == nullptr);
+  if (n1 < 0 || d <= 0 || (!sym && n2 < 0)) return set_err(PL_EINVAL, "bad shape n1=%lld n2=%lld d=%lld", (long long)n1, (long long)n2, (long long)d);
+  if (!dX1 || !dOut) return set_err(PL_EINVAL, "null pointer");
+  if (ldx1 < d || (!sym && ldx2 < d)) return set_err(PL_EINVAL, "leading dimension smaller than d");
+  if (nparts < 1 || part < 0 || part >= nparts) return set_err(PL_EINVAL, "bad part %d of %d", part, nparts);
+  if (sym) {
+    n2 = n1;
+    if (!packed && (fill < 1 || fill > 3)) return set_err(PL_EINVAL, "fill must be PL_FILL_RM_UPPER, PL_FILL_RM_LOWER or PL_FILL_FULL");
+  }
+  if (!packed && ldo < n2) return set_err(PL_EINVAL, "ldo smaller than the number of columns");
+  if (n1 == 0 || n2 == 0) return PL_OK;
+
+  const double *X1, *X2 = nullptr;
+  int64_t l1, l2 = 0;
+  PL_TRY(tma_operand(dX1, n1, d, ldx1, WS_PAD1, st, &X1, &l1));
+  if (!sym) PL_TRY(tma_operand(dX2, n2, d, ldx2, WS_PAD2, st, &X2, &l2));
+
+  GramLaunch L{};
+  L.d = d;
+  L.out = dOut;
+  L.ldo = ldo;
+  L.symmetric = sym;
+  L.fill = fill;
+  L.packed = packed;
+  L.part = part;
+  L.nparts = nparts;
+  L.alpha = alpha;
+  L.nA = n1;
+  L.nB = n2;
+
+  if (kernel_id == PL_KERNEL_LINEAR) {
+    L.epi = EPI_LINEAR;
+    L.A = X1; L.ldA = l1;
+    L.B = sym ? X1 : X2; L.ldB = sym ? l1 : l2;
+    L.same_operand = sym;
+    return launch_gram(L, st);
+  }
+  if (kernel_id == PL_KERNEL_DOT) {
+    void *s1, *s2 = nullptr;
+    PL_TRY(ws_get(WS_STAT1, (size_t)n1 * 8, &s1));
+    PL_TRY(launch_prep<PREP_DOT>(X1, n1, d, l1, nullptr, nullptr, nullptr, nullptr, 0, (double*)s1, st));
+    if (!sym) {
+      PL_TRY(ws_get(WS_STAT2, (size_t)n2 * 8, &s2));
+      PL_TRY(launch_prep<PREP_DOT>(X2, n2, d, l2, nullptr, nullptr, nullptr, nullptr, 0, (double*)s2, st));
+    }
+    L.epi = EPI_DOT;
+    L.A = X1; L.ldA = l1;
+    L.B = sym ? X1 : X2; L.ldB = sym ? l1 : l2;
+    L.ra = (double*)s1;
+    L.rb = sym ? (double*)s1 : (double*)s2;
+    L.same_operand = sym;
+    return launch_gram(L, st);
+  }
+  if (kernel_id != PL_KERNEL_RBF) return set_err(PL_EINVAL, "unknown kernel id %d", kernel_id);
+  if (!(ell != 0.0)) return set_err(PL_EINVAL, "RBF length scale must be non-zero");
+  if (cinv_kind != PL_CINV_IDENTITY && cinv_kind != PL_CINV_DIAGONAL && cinv_kind != PL_CINV_FULL) return set_err(PL_EINVAL, "unknown cinv_kind %d", cinv_kind);
+  if (cinv_kind != PL_CINV_IDENTITY && !dcinv) return set_err(PL_EINVAL, "cinv is NULL");
+
+  // The distance is translation invariant: shift by the column mean of X1 so that the Gram form
+  // q_i + q_j - 2 G_ij does not cancel against |mean|^2 (parity at 1e-10).
+  void *mean, *xc1, *xc2 = nullptr, *y1 = nullptr, *y2 = nullptr, *s1, *s2 = nullptr;
+  const int64_t ldc = (d + 1) & ~(int64_t)1;
+  PL_TRY(ws_get(WS_MEAN, (size_t)ldc * 8, &mean));
+  PL_TRY(colsum(X1, n1, d, l1, (double)n1, (double*)mean, st));
+  PL_TRY(ws_get(WS_XC1, (size_t)n1 * ldc * 8, &xc1));
+  PL_TRY(ws_get(WS_STAT1, (size_t)n1 * 8, &s1));
+  if (!sym) {
+    PL_TRY(ws_get(WS_XC2, (size_t)n2 * ldc * 8, &xc2));
+    PL_TRY(ws_get(WS_STAT2, (size_t)n2 * 8, &s2));
+  }
+  L.epi = EPI_RBF;
+  L.s = -0.5 / (ell * ell);
+  L.beta = beta;
+  L.ra = (double*)s1;
+  L.rb = sym ? (double*)s1 : (double*)s2;
+  if (cinv_kind == PL_CINV_IDENTITY) {
+    PL_TRY(launch_prep<PREP_RBF_ID>(X1, n1, d, l1, (double*)mean, nullptr, (double*)xc1, nullptr, ldc, (double*)s1, st));
+    if (!sym) PL_TRY(launch_prep<PREP_RBF_ID>(X2, n2, d, l2, (double*)mean, nullptr, (double*)xc2, nullptr, ldc, (double*)s2, st));
+    L.A = (double*)xc1; L.ldA = ldc;
+    L.B = sym ? (double*)xc1 : (double*)xc2; L.ldB = ldc;
+    L.same_operand = sym;
+    return launch_gram(L, st);
+  }
+  PL_TRY(ws_get(WS_Y1, (size_t)n1 * ldc * 8, &y1));
+  if (!sym) PL_TRY(ws_get(WS_Y2, (size_t)n2 * ldc * 8, &y2));
+  if (cinv_kind == PL_CINV_DIAGONAL) {
+    const double* cd;
+    int64_t ldcd;
+    PL_TRY(tma_operand(dcinv, 1, d, ldc, WS_PADC, st, &cd, &ldcd));
+    PL_TRY(launch_prep<PREP_RBF_DIAG>(X1, n1, d, l1, (double*)mean, cd, (double*)xc1, (double*)y1, ldc, (double*)s1, st));
+    if (!sym) PL_TRY(launch_prep<PREP_RBF_DIAG>(X2, n2, d, l2, (double*)mean, cd, (double*)xc2, (double*)y2, ldc, (double*)s2, st));
+  } else {
+    // Y = Xc * Cinv through the same DMMA Gram engine (Cinv symmetric: rows of Cinv are its columns)
+    const double* cf;
+    int64_t ldcf;
+    PL_TRY(tma_operand(dcinv, d, d, d, WS_PADC, st, &cf, &ldcf));
+    PL_TRY(launch_prep<PREP_CENTER_ONLY>(X1, n1, d, l1, (double*)mean, nullptr, (double*)xc1, nullptr, ldc, nullptr, st));
+    GramLaunch Ly{};
+    Ly.epi = EPI_LINEAR;
+    Ly.A = (double*)xc1; Ly.nA = n1; Ly.ldA = ldc;
+    Ly.B = cf; Ly.nB = d; Ly.ldB = ldcf;
+    Ly.d = d;
+    Ly.out = (double*)y1; Ly.ldo = ldc;
+    Ly.nparts = 1;
+    PL_TRY(launch_gram(Ly, st));
+    rowdot_kernel<<<(unsigned)((n1 * 32 + 255) / 256), 256, 0, st>>>((double*)y1, (double*)xc1, n1, d, ldc, (double*)s1);
+    LAUNCH_CHECK();
+    if (!sym) {
+      PL_TRY(launch_prep<PREP_CENTER_ONLY>(X2, n2, d, l2, (double*)mean, nullptr, (double*)xc2, nullptr, ldc, nullptr, st));
+      Ly.A = (double*)xc2; Ly.nA = n2;
+      Ly.out = (double*)y2;
+      PL_TRY(launch_gram(Ly, st));
+      rowdot_kernel<<<(unsigned)((n2 * 32 + 255) / 256), 256, 0, st>>>((double*)y2, (double*)xc2, n2, d, ldc, (double*)s2);
+      LAUNCH_CHECK();
+    }
+  }
+  L.A = (double*)y1; L.ldA = ldc;
+  L.B = sym ? (double*)xc1 : (double*)xc2; L.ldB = ldc;
+  L.same_operand = 0;
+  return launch_gram(L, st);
+}
+
+void choose_splits(int64_t R, int ntiles, int* splits, int64_t* rows_per_split) {
+  // one CTA per (tile, split). Pick the number of waves (<= 6) whose last wave is fullest, keep >= 256 rows per CTA.
+  int best = 1;
+  double best_eff = 0.0;
+  for (int w = 1; w <= 6; ++w) {
+    const int s = (g.num_sms * w) / ntiles;
+    if (s < 1) continue;
+    const double eff = (double)(ntiles * s) / (double)(g.num_sms * w);
+    if (eff > best_eff + 0.02 || (best_eff == 0.0)) {
+      best_eff = eff;
+      best = s;
+    }
+  }
+  int64_t max_by_rows = R / 256;
+  if (max_by_rows < 1) max_by_rows = 1;
+  int64_t s = best < max_by_rows ? best : max_by_rows;
+  int64_t rps = (R + s - 1) / s;
+  rps = (rps + SYRK_BK - 1) / SYRK_BK * SYRK_BK;
+  if (rps < SYRK_BK) rps = SYRK_BK;
+  s = (R + rps - 1) / rps;
+  if (s < 1) s = 1;
+  *splits = (int)s;
+  *rows_per_split = rps;
+}
+
+int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dw, int64_t ne, double w_e, double w_f, const double* db,
+                  const double* dmean, double* dS, double* dvec, cudaStream_t st) {
+  PL_TRY(need_ready());
+  if (R < 0 || Kf <= 0 || lda < Kf) return set_err(PL_EINVAL, "bad shape R=%lld Kf=%lld lda=%lld", (long long)R, (long long)Kf, (long long)lda);
+  if (!dA || !dS) return set_err(PL_EINVAL, "null pointer");
+  if (ne < 0) ne = 0;
+  if (ne > R) ne = R;
+  if (dmean && dvec) return set_err(PL_EINVAL, "centred SYRK does not produce moment vectors");
+  const double* A;
+  int64_t ld;
+  PL_TRY(tma_operand(dA, R, Kf, lda, WS_PAD1, st, &A, &ld));
+
+  SyrkParams p;
+  p.R = R;
+  p.Kf = Kf;
+  p.w = dw;
+  p.ne = ne;
+  p.w_e = w_e;
+  p.w_f = w_f;
+  p.b = db;
+  p.mean = dmean;
+  p.want_vec = dvec ? 1 : 0;
+  p.T = (int)((Kf + SYRK_BT - 1) / SYRK_BT);
+  p.ntiles = p.T * (p.T + 1) / 2;
+  choose_splits(R, p.ntiles, &p.splits, &p.rows_per_split);
+  void *wst, *wsv = nullptr;
+  PL_TRY(ws_get(WS_SYRK_TILES, (size_t)p.splits * p.ntiles * SYRK_TILE_ELEMS * 8, &wst));
+  if (p.want_vec) PL_TRY(ws_get(WS_SYRK_VEC, (size_t)p.splits * 2 * p.T * SYRK_BT * 8, &wsv));
+  p.ws_tiles = (double*)wst;
+  p.ws_vec = (double*)wsv;
+
+  CUtensorMap tm;
+  // R == 0: the kernel loads nothing (KT = 0) but the descriptor still needs a non-zero extent
+  PL_TRY(make_tmap_2d(&tm, A, Kf, R > 0 ? R : 1, ld, 16, SYRK_BK));
+  dim3 grid((unsigned)p.ntiles, (unsigned)p.splits);
+  if (dmean)
+    syrk_kernel<true, false><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, p);
+  else if (p.want_vec)
+    syrk_kernel<false, true><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, p);
+  else
+    syrk_kernel<false, false><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, p);
+  LAUNCH_CHECK();
+  syrk_reduce_kernel<<<dim3((unsigned)p.ntiles, 8), 256, 0, st>>>(p.ws_tiles, p.ws_vec, p.T, p.ntiles, p.splits, Kf, dS, dvec, p.want_vec);
+  LAUNCH_CHECK();
+  if (p.want_vec) {
+    syrk_scalar_kernel<<<1, 1024, 0, st>>>(dw, db, ne, w_e, dvec + 2 * Kf);
+    LAUNCH_CHECK();
+  }
+  return PL_OK;
+}
+
+int finish_dev_impl(const double* dS, const double* dvec, int64_t Kf, int ic, double lambda, double* dAtWA, double* dAtWb, cudaStream_t st) {
+  PL_TRY(need_ready());
+  if (Kf <= 0 || !dS || !dAtWA) return set_err(PL_EINVAL, "bad arguments");
+  if ((ic || dAtWb) && !dvec) return set_err(PL_EINVAL, "intercept / AtWb need the moment vectors");
+  ic = ic ? 1 : 0;
+  const int64_t n = Kf + ic;
+  int blocks = (int)((n * n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  normal_eq_finish_kernel<<<blocks, 256, 0, st>>>(dS, dvec, Kf, ic, lambda, dAtWA, dAtWb);
+  LAUNCH_CHECK();
+  return PL_OK;
+}
+
+// host <-> device helpers for the host-pointer entry points
+int h2d_matrix(const double* h, int64_t rows, int64_t cols, int64_t ldh, int slot, double** dptr, int64_t* ldd) {
+  const int64_t ldp = (cols + 1) & ~(int64_t)1;
+  void* buf;
+  PL_TRY(ws_get(slot, (size_t)(rows > 0 ? rows : 1) * ldp * 8, &buf));
+  if (rows > 0) CUDA_TRY(cudaMemcpy2DAsync(buf, (size_t)ldp * 8, h, (size_t)ldh * 8, (size_t)cols * 8, (size_t)rows, cudaMemcpyHostToDevice, g.stream));
+  *dptr = (double*)buf;
+  *ldd = ldp;
+  return PL_OK;
+}
+int h2d_vector(const double* h, int64_t count, int slot, double** dptr) {
+  void* buf;
+  PL_TRY(ws_get(slot, (size_t)(count > 0 ? count : 1) * 8, &buf));
+  if (count > 0) CUDA_TRY(cudaMemcpyAsync(buf, h, (size_t)count * 8, cudaMemcpyHostToDevice, g.stream));
+  *dptr = (double*)buf;
+  return PL_OK;
+}
+
+int finish_timing() {
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  float a = 0, b = 0, c = 0;
+  CUDA_TRY(cudaEventElapsedTime(&a, g.ev[0], g.ev[1]));
+  CUDA_TRY(cudaEventElapsedTime(&b, g.ev[1], g.ev[2]));
+  CUDA_TRY(cudaEventElapsedTime(&c, g.ev[2], g.ev[3]));
+  g.t_h2d = a;
+  g.t_kernel = b;
+  g.t_d2h = c;
+  return PL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pl_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g.ready) return PL_OK;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return set_err(PL_ENODEV, "no CUDA device available (%s); plb200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  if (device >= count) return set_err(PL_EINVAL, "device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return set_err(PL_ENODEV, "device %d is sm_%d%d; libplb200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  CUDA_TRY(cudaSetDevice(device));
+  g.device = device;
+  g.num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return set_err(PL_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  g.encode = (PFN_cuTensorMapEncodeTiled)fn;
+  CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  for (auto& ev : g.ev) CUDA_TRY(cudaEventCreate(&ev));
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
+  g.ready = true;
+  return PL_OK;
+}
+
+void pl_finalize(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g.ready) return;
+  cudaSetDevice(g.device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < WS_NSLOTS; ++i) {
+    if (g.ws[i]) cudaFree(g.ws[i]);
+    g.ws[i] = nullptr;
+    g.ws_bytes[i] = 0;
+  }
+  for (auto& ev : g.ev) {
+    if (ev) cudaEventDestroy(ev);
+    ev = nullptr;
+  }
+  if (g.stream) cudaStreamDestroy(g.stream);
+  g.stream = nullptr;
+  g.ready = false;
+}
+
+const char* pl_last_error(void) { return g_err; }
+
+int pl_last_timing(double* kernel_ms, double* h2d_ms, double* d2h_ms) {
+  if (kernel_ms) *kernel_ms = g.t_kernel;
+  if (h2d_ms) *h2d_ms = g.t_h2d;
+  if (d2h_ms) *d2h_ms = g.t_d2h;
+  return PL_OK;
+}
+
+int64_t pl_launch_count(void) { return g_launches.load(); }
+
+int64_t pl_workspace_bytes(void) {
+  int64_t tot = 0;
+  for (int i = 0; i < WS_NSLOTS; ++i) tot += (int64_t)g.ws_bytes[i];
+  return tot;
+}
+
+int pl_gram_dev(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, const double* dX2, int64_t n2, int64_t ldx2, int64_t d, int alpha,
+                int cinv_kind, const double* dcinv, double ell, double beta, double* dOut, int64_t ldo, int fill, int part, int nparts, int packed,
+                void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return gram_dev_impl(kernel_id, dX1, n1, ldx1, dX2, n2, ldx2, d, alpha, cinv_kind, dcinv, ell, beta, dOut, ldo, fill, part, nparts, packed,
+                       (cudaStream_t)stream);
+}
+
+int64_t pl_gram_tile_count(int64_t n1, int64_t n2, int part, int nparts) {
+  if (nparts < 1 || part < 0 || part >= nparts || n1 <= 0) return 0;
+  const int sym = (n2 <= 0);
+  const int T1 = (int)((n1 + GRAM_BM - 1) / GRAM_BM);
+  const int T2 = sym ? T1 : (int)((n2 + GRAM_BN - 1) / GRAM_BN);
+  const int64_t slots = gram_num_slots(T1, T2, sym);
+  const int64_t mine = (slots - part + nparts - 1) / nparts;
+  return mine > 0 ? mine : 0;
+}
+
+int pl_gram_tile_coords(int64_t n1, int64_t n2, int part, int nparts, int64_t k, int64_t* ti, int64_t* tj) {
+  const int64_t cnt = pl_gram_tile_count(n1, n2, part, nparts);
+  if (k < 0 || k >= cnt) return set_err(PL_EINVAL, "tile index %lld out of range (%lld)", (long long)k, (long long)cnt);
+  const int sym = (n2 <= 0);
+  const int T1 = (int)((n1 + GRAM_BM - 1) / GRAM_BM);
+  const int T2 = sym ? T1 : (int)((n2 + GRAM_BN - 1) / GRAM_BN);
+  int a = -1, b = -1;
+  // slots of the folded enumeration that hold no tile (odd T only) report (-1, -1)
+  if (!gram_slot_to_tile(T1, T2, sym, k * nparts + part, a, b)) a = b = -1;
+  if (ti) *ti = a;
+  if (tj) *tj = b;
+  return PL_OK;
+}
+
+int pl_syrk_dev(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dw, int64_t n_energy_rows, double w_e, double w_f,
+                const double* db, const double* dmean, double* dS, double* dvec, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return syrk_dev_impl(dA, R, Kf, lda, dw, n_energy_rows, w_e, w_f, db, dmean, dS, dvec, (cudaStream_t)stream);
+}
+
+int pl_normal_eq_finish_dev(const double* dS, const double* dvec, int64_t Kf, int add_intercept, double lambda, double* dAtWA, double* dAtWb,
+                            void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return finish_dev_impl(dS, dvec, Kf, add_intercept, lambda, dAtWA, dAtWb, (cudaStream_t)stream);
+}
+
+int pl_colsum_dev(const double* dA, int64_t R, int64_t Kf, int64_t lda, double* dsum, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (R < 0 || Kf <= 0 || lda < Kf || !dA || !dsum) return set_err(PL_EINVAL, "bad arguments");
+  const double* A;
+  int64_t ld;
+  PL_TRY(tma_operand(dA, R, Kf, lda, WS_PAD1, (cudaStream_t)stream, &A, &ld));
+  return colsum(A, R, Kf, ld, 0.0, dsum, (cudaStream_t)stream);
+}
+
+int pl_scale_div_dev(const double* dIn, double denom, int64_t count, double* dOut, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (count < 0 || !dIn || !dOut) return set_err(PL_EINVAL, "bad arguments");
+  if (count == 0) return PL_OK;
+  int blocks = (int)((count + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  scale_div_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dIn, denom, count, dOut);
+  LAUNCH_CHECK();
+  return PL_OK;
+}
+
+// ------------------------------------------------ host-pointer entry points ------------------------------------------------
+
+static int gram_host(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, const double* X2, int64_t n2, int64_t ldx2, int64_t d, int alpha,
+                     int cinv_kind, const double* cinv, double ell, double beta, double* K, int64_t ldk, int fill) {
+  PL_TRY(need_ready());
+  const bool sym = (X2 == nullptr);
+  if (!X1 || !K || n1 < 0 || d <= 0 || ldx1 < d || (!sym && (n2 < 0 || ldx2 < d))) return set_err(PL_EINVAL, "bad arguments");
+  if (sym) n2 = n1;
+  if (ldk < n2) return set_err(PL_EINVAL, "ldk smaller than the number of columns");
+  if (sym && (fill < 1 || fill > 3)) return set_err(PL_EINVAL, "bad fill");
+  if (n1 == 0 || n2 == 0) return PL_OK;
+  CUDA_TRY(cudaSetDevice(g.device));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  double *d1, *d2 = nullptr, *dc = nullptr, *dK;
+  int64_t l1, l2 = 0;
+  PL_TRY(h2d_matrix(X1, n1, d, ldx1, WS_H_IN1, &d1, &l1));
+  if (!sym) PL_TRY(h2d_matrix(X2, n2, d, ldx2, WS_H_IN2, &d2, &l2));
+  if (kernel_id == PL_KERNEL_RBF && cinv_kind == PL_CINV_DIAGONAL) {
+    if (!cinv) return set_err(PL_EINVAL, "cinv is NULL");
+    PL_TRY(h2d_vector(cinv, d, WS_H_IN3, &dc));
+  } else if (kernel_id == PL_KERNEL_RBF && cinv_kind == PL_CINV_FULL) {
+    if (!cinv) return set_err(PL_EINVAL, "cinv is NULL");
+    PL_TRY(h2d_vector(cinv, d * d, WS_H_IN3, &dc));  // dense d x d; gram_dev_impl pads it if d is odd
+  }
+  const int64_t ldo = (n2 + 1) & ~(int64_t)1;
+  void* outbuf;
+  PL_TRY(ws_get(WS_H_OUT1, (size_t)n1 * ldo * 8, &outbuf));
+  dK = (double*)outbuf;
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  PL_TRY(gram_dev_impl(kernel_id, d1, n1, l1, d2, n2, l2, d, alpha, cinv_kind, dc, ell, beta, dK, ldo, fill, 0, 1, 0, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  if (!sym || fill == PL_FILL_FULL) {
+    CUDA_TRY(cudaMemcpy2DAsync(K, (size_t)ldk * 8, dK, (size_t)ldo * 8, (size_t)n2 * 8, (size_t)n1, cudaMemcpyDeviceToHost, g.stream));
+  } else {
+    // one triangle only: copy the staircase of 128-row blocks (half the PCIe traffic). Inside diagonal tiles the
+    // unused half was written as zeros by the kernel, matching the reference's zeros(n,n) storage.
+    for (int64_t r0 = 0; r0 < n1; r0 += GRAM_BM) {
+      const int64_t r1 = r0 + GRAM_BM < n1 ? r0 + GRAM_BM : n1;
+      if (fill == PL_FILL_RM_LOWER) {
+        CUDA_TRY(cudaMemcpy2DAsync(K + r0 * ldk, (size_t)ldk * 8, dK + r0 * ldo, (size_t)ldo * 8, (size_t)r1 * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, g.stream));
+      } else {
+        CUDA_TRY(cudaMemcpy2DAsync(K + r0 * ldk + r0, (size_t)ldk * 8, dK + r0 * ldo + r0, (size_t)ldo * 8, (size_t)(n2 - r0) * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, g.stream));
+      }
+    }
+  }
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();
+}
+
+int pl_gram_dot(const double* X, int64_t n, int64_t d, int64_t ldx, int alpha, double* K, int64_t ldk, int fill) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return gram_host(PL_KERNEL_DOT, X, n, ldx, nullptr, 0, 0, d, alpha, 0, nullptr, 1.0, 1.0, K, ldk, fill);
+}
+
+int pl_gram_rbf(const double* X, int64_t n, int64_t d, int64_t ldx, int cinv_kind, const double* cinv, double ell, double beta, double* K,
+                int64_t ldk, int fill) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return gram_host(PL_KERNEL_RBF, X, n, ldx, nullptr, 0, 0, d, 0, cinv_kind, cinv, ell, beta, K, ldk, fill);
+}
+
+int pl_gram_cross(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, const double* X2, int64_t n2, int64_t ldx2, int64_t d, int alpha,
+                  int cinv_kind, const double* cinv, double ell, double beta, double* K, int64_t ldk) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!X2) return set_err(PL_EINVAL, "X2 is NULL (use pl_gram_dot / pl_gram_rbf for the symmetric form)");
+  return gram_host(kernel_id, X1, n1, ldx1, X2, n2, ldx2, d, alpha, cinv_kind, cinv, ell, beta, K, ldk, PL_FILL_FULL);
+}
+
+int pl_normal_eq(const double* A, int64_t R, int64_t Kf, int64_t lda, const double* w, int64_t n_energy_rows, double w_e, double w_f,
+                 const double* b, int add_intercept, double lambda, double* AtWA, double* AtWb) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!A || !AtWA || R < 0 || Kf <= 0 || lda < Kf) return set_err(PL_EINVAL, "bad arguments");
+  if (AtWb && !b) return set_err(PL_EINVAL, "AtWb requested without b");
+  CUDA_TRY(cudaSetDevice(g.device));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  double *dA, *dw = nullptr, *db = nullptr;
+  int64_t ld;
+  PL_TRY(h2d_matrix(A, R, Kf, lda, WS_H_IN1, &dA, &ld));
+  if (w) PL_TRY(h2d_vector(w, R, WS_H_IN2, &dw));
+  if (b) PL_TRY(h2d_vector(b, R, WS_H_IN3, &db));
+  const int ic = add_intercept ? 1 : 0;
+  const int64_t n = Kf + ic;
+  const bool want_vec = ic || b;
+  void *dS, *dvec = nullptr, *dM, *dv = nullptr;
+  PL_TRY(ws_get(WS_H_S, (size_t)Kf * Kf * 8, &dS));
+  if (want_vec) PL_TRY(ws_get(WS_H_VEC, (size_t)(2 * Kf + 2) * 8, &dvec));
+  PL_TRY(ws_get(WS_H_OUT1, (size_t)n * n * 8, &dM));
+  if (AtWb) PL_TRY(ws_get(WS_H_OUT2, (size_t)n * 8, &dv));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  PL_TRY(syrk_dev_impl(dA, R, Kf, ld, dw, n_energy_rows, w_e, w_f, db, nullptr, (double*)dS, (double*)dvec, g.stream));
+  PL_TRY(finish_dev_impl((double*)dS, (double*)dvec, Kf, ic, lambda, (double*)dM, (double*)dv, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaMemcpyAsync(AtWA, dM, (size_t)n * n * 8, cudaMemcpyDeviceToHost, g.stream));
+  if (AtWb) CUDA_TRY(cudaMemcpyAsync(AtWb, dv, (size_t)n * 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();
+}
+
+int pl_cov(const double* X, int64_t n, int64_t Kf, int64_t ldx, double* mean_inout, int mean_given, int center, double* C) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!X || !C || n <= 0 || Kf <= 0 || ldx < Kf) return set_err(PL_EINVAL, "bad arguments");
+  if (center && !mean_inout) return set_err(PL_EINVAL, "centred covariance needs mean_inout");
+  CUDA_TRY(cudaSetDevice(g.device));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  double* dX;
+  int64_t ld;
+  PL_TRY(h2d_matrix(X, n, Kf, ldx, WS_H_IN1, &dX, &ld));
+  double* dmean = nullptr;
+  if (center) {
+    if (mean_given) {
+      PL_TRY(h2d_vector(mean_inout, Kf, WS_H_IN2, &dmean));
+    } else {
+      void* m;
+      PL_TRY(ws_get(WS_H_IN2, (size_t)Kf * 8, &m));
+      dmean = (double*)m;
+    }
+  }
+  void *dS, *dC;
+  PL_TRY(ws_get(WS_H_S, (size_t)Kf * Kf * 8, &dS));
+  PL_TRY(ws_get(WS_H_OUT1, (size_t)Kf * Kf * 8, &dC));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  if (center && !mean_given) PL_TRY(colsum(dX, n, Kf, ld, (double)n, dmean, g.stream));  // pca.m = sum(d)/length(d)
+  PL_TRY(syrk_dev_impl(dX, n, Kf, ld, nullptr, 0, 1.0, 1.0, nullptr, dmean, (double*)dS, nullptr, g.stream));
+  {
+    const int64_t count = Kf * Kf;
+    int blocks = (int)((count + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    scale_div_kernel<<<blocks, 256, 0, g.stream>>>((double*)dS, (double)n, count, (double*)dC);  // mean(di*di'): sum / n
+    LAUNCH_CHECK();
+  }
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaMemcpyAsync(C, dC, (size_t)Kf * Kf * 8, cudaMemcpyDeviceToHost, g.stream));
+  if (center && !mean_given) CUDA_TRY(cudaMemcpyAsync(mean_inout, dmean, (size_t)Kf * 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();
+}
+
+}  // extern "C"

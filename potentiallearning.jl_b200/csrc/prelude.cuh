@@ -1,0 +1,150 @@
+// prelude.cuh — HBM-bound preludes of the contractions: column sums / means, row norms, centring and the
+// Cinv transform of Euclidean. Coalesced 128-bit loads; row reductions finish with warp shuffles; column
+// reductions are two-stage with a fixed summation order (bitwise reproducible run to run).
+//
+// Reference sites: dot(A,A), dot(B,B) recomputed per pair (src/Kernels/kernels.jl:35); (B1-B2)'*Cinv*(B1-B2)
+// (src/Kernels/distances.jl:58-60); pca.m = sum(d)/length(d) (src/DimensionReduction/pca_state.jl:35).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace plb {
+
+constexpr int COLSUM_ROWS_PER_BLOCK = 512;
+
+// partial[blockIdx.y][col] = sum of rows [blockIdx.y*RPB, ...) of column col. blockDim.x threads x 2 columns each.
+__global__ void colsum_partial_kernel(const double* __restrict__ A, int64_t R, int64_t Kf, int64_t lda, double* __restrict__ partial) {
+  const int64_t c0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (c0 >= Kf) return;
+  const int64_t r0 = (int64_t)blockIdx.y * COLSUM_ROWS_PER_BLOCK;
+  int64_t r1 = r0 + COLSUM_ROWS_PER_BLOCK;
+  if (r1 > R) r1 = R;
+  const bool pair = (c0 + 1 < Kf);
+  double s0 = 0.0, s1 = 0.0;
+  const double* ptr = A + r0 * lda + c0;
+  int64_t r = r0;
+  if (pair) {
+    // lda even and base 16B aligned (checked by the caller): 128-bit loads, 4 rows in flight
+    for (; r + 4 <= r1; r += 4) {
+      const double2 v0 = __ldg(reinterpret_cast<const double2*>(ptr));
+      const double2 v1 = __ldg(reinterpret_cast<const double2*>(ptr + lda));
+      const double2 v2 = __ldg(reinterpret_cast<const double2*>(ptr + 2 * lda));
+      const double2 v3 = __ldg(reinterpret_cast<const double2*>(ptr + 3 * lda));
+      s0 += v0.x; s1 += v0.y;
+      s0 += v1.x; s1 += v1.y;
+      s0 += v2.x; s1 += v2.y;
+      s0 += v3.x; s1 += v3.y;
+      ptr += 4 * lda;
+    }
+    for (; r < r1; ++r) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(ptr));
+      s0 += v.x; s1 += v.y;
+      ptr += lda;
+    }
+  } else {
+    for (; r < r1; ++r) {
+      s0 += __ldg(ptr);
+      ptr += lda;
+    }
+  }
+  partial[(int64_t)blockIdx.y * Kf + c0] = s0;
+  if (pair) partial[(int64_t)blockIdx.y * Kf + c0 + 1] = s1;
+}
+
+// out[col] = (sum_b partial[b][col]) (/ denom if denom != 0), fixed order over b; 8 independent chains for latency
+__global__ void colsum_final_kernel(const double* __restrict__ partial, int64_t nblocks, int64_t Kf, double denom, double* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Kf) return;
+  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t b = 0;
+  for (; b + 8 <= nblocks; b += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s[u] += partial[(b + u) * Kf + c];
+  }
+  for (int u = 0; b < nblocks; ++b, ++u) s[u] += partial[b * Kf + c];
+  double tot = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  if (denom != 0.0) tot = tot / denom;
+  out[c] = tot;
+}
+
+enum { PREP_DOT = 0, PREP_RBF_ID = 1, PREP_RBF_DIAG = 2, PREP_CENTER_ONLY = 3 };
+
+// One warp per row.
+//   PREP_DOT:         stat[i] = 1/sqrt(sum_k x^2)                                  (kernels.jl:35)
+//   PREP_RBF_ID:      xc = x - mean -> Xc ; stat[i] = sum_k xc^2                   (distances.jl:59, Cinv = I)
+//   PREP_RBF_DIAG:    xc = x - mean -> Xc ; y = xc * cinv -> Y ; stat[i] = sum_k y*xc
+//   PREP_CENTER_ONLY: xc = x - mean -> Xc                                          (then Y = Xc*Cinv by GEMM)
+// ldc is the leading dimension of Xc and Y.
+template <int MODE>
+__global__ void prep_rows_kernel(const double* __restrict__ X, int64_t n, int64_t d, int64_t ldx, const double* __restrict__ mean,
+                                 const double* __restrict__ cdiag, double* __restrict__ Xc, double* __restrict__ Y, int64_t ldc,
+                                 double* __restrict__ stat) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const double* x = X + row * ldx;
+  double acc = 0.0;
+  const int64_t dpair = d & ~(int64_t)1;
+  for (int64_t k = 2 * lane; k < dpair; k += 64) {
+    double2 v = __ldg(reinterpret_cast<const double2*>(x + k));
+    if (MODE == PREP_DOT) {
+      acc = fma(v.x, v.x, acc);
+      acc = fma(v.y, v.y, acc);
+    } else {
+      const double2 m = __ldg(reinterpret_cast<const double2*>(mean + k));
+      v.x -= m.x;
+      v.y -= m.y;
+      *reinterpret_cast<double2*>(Xc + row * ldc + k) = v;
+      if (MODE == PREP_RBF_ID) {
+        acc = fma(v.x, v.x, acc);
+        acc = fma(v.y, v.y, acc);
+      } else if (MODE == PREP_RBF_DIAG) {
+        const double2 c = __ldg(reinterpret_cast<const double2*>(cdiag + k));
+        double2 y;
+        y.x = v.x * c.x;
+        y.y = v.y * c.y;
+        *reinterpret_cast<double2*>(Y + row * ldc + k) = y;
+        acc = fma(y.x, v.x, acc);
+        acc = fma(y.y, v.y, acc);
+      }
+    }
+  }
+  if ((d & 1) && lane == 0) {
+    const int64_t k = d - 1;
+    double v = __ldg(x + k);
+    if (MODE == PREP_DOT) {
+      acc = fma(v, v, acc);
+    } else {
+      v -= mean[k];
+      Xc[row * ldc + k] = v;
+      if (MODE == PREP_RBF_ID) acc = fma(v, v, acc);
+      else if (MODE == PREP_RBF_DIAG) {
+        const double y = v * cdiag[k];
+        Y[row * ldc + k] = y;
+        acc = fma(y, v, acc);
+      }
+    }
+  }
+  if (MODE == PREP_CENTER_ONLY) return;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) stat[row] = (MODE == PREP_DOT) ? 1.0 / sqrt(acc) : acc;
+}
+
+// stat[i] = sum_k Y[i][k] * Xc[i][k]  (quadratic form x' Cinv x with Y = Xc Cinv); one warp per row
+__global__ void rowdot_kernel(const double* __restrict__ Y, const double* __restrict__ Xc, int64_t n, int64_t d, int64_t ld, double* __restrict__ stat) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  double acc = 0.0;
+  for (int64_t k = lane; k < d; k += 32) acc = fma(Y[row * ld + k], Xc[row * ld + k], acc);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) stat[row] = acc;
+}
+
+__global__ void scale_div_kernel(const double* __restrict__ in, double denom, int64_t count, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i] / denom;
+}
+
+}  // namespace plb

@@ -1,0 +1,361 @@
+// syrk.cuh — weighted, optionally mean-centred SYRK over rows:  S = sum_r w_r (a_r - m)(a_r - m)'   (Kf x Kf)
+// plus, fused on the diagonal tiles, the moment vectors  v = sum_r w_r b_r (a_r - m)  and  c = sum_{r<ne} w_r a_r.
+//
+// Replaces every normal-equation assembly site of the reference (src/Learning/linear-learn.jl:16-17, 45-49, 94-95,
+// 139-143, 157-158, 200, 253, 355-356) and the per-row outer-product mean of compute_eigen
+// (src/DimensionReduction/dimension_reduction.jl:12) with the centring of fit!(::PCAState) (pca_state.jl:34-37).
+//
+// Geometry: the contraction runs over ROWS of one row-major R x Kf matrix, so both MMA operands are "MN-major"
+// (the output index is contiguous in memory) — the transpose of the Gram kernel's geometry:
+//   * CTA (tile, split): 128 x 128 output tile (upper-triangle tile pairs only) x a contiguous row range; partial
+//     tiles go to a workspace in fragment order (perfectly coalesced) and a deterministic second-stage kernel sums
+//     the splits in fixed order, mirrors, and applies scale / ridge / intercept layout;
+//   * stage = 16 rows x 128 columns per operand, brought in as 8 TMA boxes of 16 rows x 16 columns (128 bytes wide,
+//     128B swizzle); diagonal tiles load one operand only;
+//   * fragment loads are 128-bit: lane (g,t) reads columns (2g, 2g+1) of row 2t+par(+8h) of a box — two m-tiles of
+//     one k4-step. The contraction index is permuted (MMA k <-> stage row 2t+par), which together with the 128B
+//     swizzle makes every quarter-warp hit 8 distinct 16-byte chunks (conflict-free);
+//   * the per-row weight (and the mean subtraction) is applied to the A fragment in registers: the weighted /
+//     centred matrix never exists in memory.
+#pragma once
+#include "ptx.cuh"
+
+namespace plb {
+
+constexpr int SYRK_BT = 128;      // output tile edge
+constexpr int SYRK_BK = 16;       // rows per stage
+constexpr int SYRK_STAGES = 5;
+constexpr int SYRK_CONSUMER_WARPS = 8;
+constexpr int SYRK_THREADS = (SYRK_CONSUMER_WARPS + 4) * 32;  // 2 DMMA warpgroups + 1 producer warpgroup
+constexpr int SYRK_BOX_BYTES = SYRK_BK * 16 * 8;        // 2 KB: 16 rows x 16 cols
+constexpr int SYRK_OP_BYTES = 8 * SYRK_BOX_BYTES;       // 16 KB per operand per stage
+constexpr int SYRK_SMEM_BYTES = SYRK_STAGES * 2 * SYRK_OP_BYTES + 1024 + 256;
+constexpr int SYRK_TILE_ELEMS = SYRK_BT * SYRK_BT;      // 16384 accumulators per partial tile
+
+struct SyrkParams {
+  int64_t R, Kf;
+  const double* w;        // per-row weights or NULL
+  int64_t ne;             // rows < ne are "energy rows": weight w_e and member of the intercept column
+  double w_e, w_f;
+  const double* b;        // right-hand side or NULL
+  const double* mean;     // column means (centred mode) or NULL
+  int want_vec;           // accumulate v / c on diagonal tiles
+  int T;                  // tile rows = ceil(Kf / 128)
+  int ntiles;             // T (T+1) / 2
+  int splits;             // row splits
+  int64_t rows_per_split; // multiple of SYRK_BK
+  double* ws_tiles;       // [split][tile][64 acc][256 threads]
+  double* ws_vec;         // [split][2][T*128]   (v then c), only if want_vec
+};
+
+// linear upper-triangle tile index -> (ti, tj), tj >= ti (row-major over the triangle)
+__host__ __device__ __forceinline__ void syrk_tile_coords(int T, int idx, int& ti, int& tj) {
+  int row = 0;
+  int rem = idx;
+  while (rem >= T - row) {
+    rem -= T - row;
+    ++row;
+  }
+  ti = row;
+  tj = row + rem;
+}
+
+template <bool CENTER, bool VEC>
+__global__ void __launch_bounds__(SYRK_THREADS, 1)
+syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + SYRK_STAGES * 2 * SYRK_OP_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (SYRK_STAGES + s); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int split = blockIdx.y;
+  int ti, tj;
+  syrk_tile_coords(p.T, tile, ti, tj);
+  const bool diag = (ti == tj);
+  const int64_t r_begin = (int64_t)split * p.rows_per_split;
+  int64_t r_end = r_begin + p.rows_per_split;
+  if (r_end > p.R) r_end = p.R;
+  const int KT = r_end > r_begin ? (int)((r_end - r_begin + SYRK_BK - 1) / SYRK_BK) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SYRK_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), SYRK_CONSUMER_WARPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp >= SYRK_CONSUMER_WARPS) {
+    setmaxnreg_dec<24>();
+    if (warp == SYRK_CONSUMER_WARPS && lane == 0) {
+      tma_prefetch_desc(&tm);
+      const uint32_t bytes = diag ? SYRK_OP_BYTES : 2 * SYRK_OP_BYTES;
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % SYRK_STAGES;
+        const uint32_t ph = (kt / SYRK_STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_arrive_expect_tx(full_bar(s), bytes);
+        const uint32_t dst = smem_base + s * 2 * SYRK_OP_BYTES;
+        const int r0 = (int)(r_begin + (int64_t)kt * SYRK_BK);
+        // NOTE: the last stage of a split may read rows of the next split (r >= r_end); they are zero-weighted below.
+#pragma unroll
+        for (int bx = 0; bx < 8; ++bx) tma_load_2d(dst + bx * SYRK_BOX_BYTES, &tm, full_bar(s), ti * SYRK_BT + 16 * bx, r0);
+        if (!diag) {
+#pragma unroll
+          for (int bx = 0; bx < 8; ++bx)
+            tma_load_2d(dst + SYRK_OP_BYTES + bx * SYRK_BOX_BYTES, &tm, full_bar(s), tj * SYRK_BT + 16 * bx, r0);
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------ consumers ------------------------------
+  setmaxnreg_inc<240>();
+  const int wm = warp >> 1;  // 32-column slab of the i (row of S) index
+  const int wn = warp & 1;   // 64-column slab of the j index
+  const int g = lane >> 2;
+  const int t = lane & 3;
+
+  double acc[4][8][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+  // moment vectors (diagonal tiles, wn == 0 warps): columns i = 128 ti + 32 wm + 16 bx + 2g + e
+  double vb[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  double vc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  const bool do_vec = VEC && diag && (wn == 0);
+
+  // column means of this thread's fragment columns
+  double mi[2][2], mj[4][2];
+  if (CENTER) {
+#pragma unroll
+    for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int64_t col = (int64_t)ti * SYRK_BT + 32 * wm + 16 * bx + 2 * g + e;
+        mi[bx][e] = col < p.Kf ? __ldg(p.mean + col) : 0.0;
+      }
+#pragma unroll
+    for (int bx = 0; bx < 4; ++bx)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int64_t col = (int64_t)tj * SYRK_BT + 64 * wn + 16 * bx + 2 * g + e;
+        mj[bx][e] = col < p.Kf ? __ldg(p.mean + col) : 0.0;
+      }
+  }
+
+  // byte offset of lane's chunk for step (h, par): row rho = 8h + 2t + par, chunk g ^ (rho & 7)
+  // rho & 7 = 2t + par  ->  (g ^ (2t+par)) << 4 ;  row offset rho * 128
+  for (int kt = 0; kt < KT; ++kt) {
+    const int s = kt % SYRK_STAGES;
+    const uint32_t ph = (kt / SYRK_STAGES) & 1u;
+    const int64_t r0 = r_begin + (int64_t)kt * SYRK_BK;
+
+    // per-row weights / rhs of the 4 stage rows this lane contracts over (independent of the TMA data)
+    double wv[2][2], bv[2][2], cv[2][2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        const int64_t r = r0 + 8 * h + 2 * t + par;
+        const bool ok = r < r_end;
+        double w = 0.0;
+        if (ok) w = p.w ? __ldg(p.w + r) : (r < p.ne ? p.w_e : p.w_f);
+        wv[h][par] = w;
+        if (VEC) {
+          bv[h][par] = (ok && p.b) ? __ldg(p.b + r) : 0.0;
+          cv[h][par] = (ok && r < p.ne) ? 1.0 : 0.0;
+        }
+      }
+
+    mbar_wait(full_bar(s), ph);
+    const uint32_t sA = smem_base + s * 2 * SYRK_OP_BYTES + (2 * wm) * SYRK_BOX_BYTES;
+    const uint32_t sB = smem_base + s * 2 * SYRK_OP_BYTES + (diag ? 0 : SYRK_OP_BYTES) + (4 * wn) * SYRK_BOX_BYTES;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        const uint32_t off = (uint32_t)((8 * h + 2 * t + par) * 128 + ((g ^ (2 * t + par)) << 4));
+        double2 a[2], b[4];
+#pragma unroll
+        for (int bx = 0; bx < 2; ++bx) a[bx] = lds128(sA + bx * SYRK_BOX_BYTES + off);
+#pragma unroll
+        for (int bx = 0; bx < 4; ++bx) b[bx] = lds128(sB + bx * SYRK_BOX_BYTES + off);
+        const double w = wv[h][par];
+        if (CENTER) {
+#pragma unroll
+          for (int bx = 0; bx < 2; ++bx) {
+            a[bx].x -= mi[bx][0];
+            a[bx].y -= mi[bx][1];
+          }
+#pragma unroll
+          for (int bx = 0; bx < 4; ++bx) {
+            b[bx].x -= mj[bx][0];
+            b[bx].y -= mj[bx][1];
+          }
+        }
+#pragma unroll
+        for (int bx = 0; bx < 2; ++bx) {
+          a[bx].x *= w;
+          a[bx].y *= w;
+        }
+        if (VEC) {
+          if (do_vec) {
+            const double bb = bv[h][par], cc = cv[h][par];
+#pragma unroll
+            for (int bx = 0; bx < 2; ++bx) {
+              vb[bx][0] = fma(a[bx].x, bb, vb[bx][0]);
+              vb[bx][1] = fma(a[bx].y, bb, vb[bx][1]);
+              vc[bx][0] = fma(a[bx].x, cc, vc[bx][0]);
+              vc[bx][1] = fma(a[bx].y, cc, vc[bx][1]);
+            }
+          }
+        }
+        // m-tile (bx, e) = columns 16 bx + 2g + e ; n-tile (bx', e') likewise: 4 x 8 DMMA tiles per k4-step
+#pragma unroll
+        for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+          for (int by = 0; by < 4; ++by) {
+            dmma884(acc[2 * bx + 0][2 * by + 0][0], acc[2 * bx + 0][2 * by + 0][1], a[bx].x, b[by].x);
+            dmma884(acc[2 * bx + 0][2 * by + 1][0], acc[2 * bx + 0][2 * by + 1][1], a[bx].x, b[by].y);
+            dmma884(acc[2 * bx + 1][2 * by + 0][0], acc[2 * bx + 1][2 * by + 0][1], a[bx].y, b[by].x);
+            dmma884(acc[2 * bx + 1][2 * by + 1][0], acc[2 * bx + 1][2 * by + 1][1], a[bx].y, b[by].y);
+          }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar(s));
+  }
+
+  // ---- partial tile to the workspace in fragment order: [acc index][consumer thread] (coalesced) ----
+  double* wst = p.ws_tiles + ((int64_t)split * p.ntiles + tile) * SYRK_TILE_ELEMS;
+  const int ctid = threadIdx.x;  // 0..255
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) wst[((mt * 8 + nt) * 2 + c) * 256 + ctid] = acc[mt][nt][c];
+
+  if (VEC) {
+    if (do_vec) {
+      // reduce over the 4 lanes t = 0..3 that share g (they hold disjoint stage rows)
+#pragma unroll
+      for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double x = vb[bx][e], y = vc[bx][e];
+          x += __shfl_xor_sync(0xffffffffu, x, 1);
+          x += __shfl_xor_sync(0xffffffffu, x, 2);
+          y += __shfl_xor_sync(0xffffffffu, y, 1);
+          y += __shfl_xor_sync(0xffffffffu, y, 2);
+          if (t == 0) {
+            const int col = ti * SYRK_BT + 32 * wm + 16 * bx + 2 * g + e;
+            double* wv2 = p.ws_vec + (int64_t)split * 2 * p.T * SYRK_BT;
+            wv2[col] = x;
+            wv2[p.T * SYRK_BT + col] = y;
+          }
+        }
+    }
+  }
+}
+
+// Second stage: S[i][j] = S[j][i] = sum over splits (fixed order) of the partial tiles; v, c likewise.
+// Element (acc index a, consumer thread tid) of tile (ti, tj):
+//   warp = tid>>5, wm = warp>>1, wn = warp&1, g = (tid&31)>>2, t = tid&3, mt = a>>4, nt = (a>>1)&7, c = a&1
+//   i = 128 ti + 32 wm + 16 (mt>>1) + 2 g + (mt&1)
+//   j = 128 tj + 64 wn + 16 (nt>>1) + 4 t + 2 c + (nt&1)
+__global__ void syrk_reduce_kernel(const double* __restrict__ ws_tiles, const double* __restrict__ ws_vec, int T, int ntiles,
+                                   int splits, int64_t Kf, double* __restrict__ S, double* __restrict__ vec, int want_vec) {
+  const int tile = blockIdx.x;
+  int ti, tj;
+  syrk_tile_coords(T, tile, ti, tj);
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < SYRK_TILE_ELEMS; e += gridDim.y * blockDim.x) {
+    const int a = e >> 8;
+    const int tid = e & 255;
+    const int warp = tid >> 5, wm = warp >> 1, wn = warp & 1, g = (tid & 31) >> 2, t = tid & 3;
+    const int mt = a >> 4, nt = (a >> 1) & 7, c = a & 1;
+    const int64_t i = (int64_t)ti * SYRK_BT + 32 * wm + 16 * (mt >> 1) + 2 * g + (mt & 1);
+    const int64_t j = (int64_t)tj * SYRK_BT + 64 * wn + 16 * (nt >> 1) + 4 * t + 2 * c + (nt & 1);
+    if (i >= Kf || j >= Kf) continue;
+    if (ti == tj && j < i) continue;  // diagonal tiles: keep j >= i, mirror (weights are applied to one operand only)
+    double sum = 0.0;
+    for (int sp = 0; sp < splits; ++sp) sum += ws_tiles[((int64_t)sp * ntiles + tile) * SYRK_TILE_ELEMS + e];
+    S[i * Kf + j] = sum;
+    S[j * Kf + i] = sum;
+  }
+  if (want_vec && ti == tj && blockIdx.y == 0) {
+    for (int cidx = threadIdx.x; cidx < SYRK_BT; cidx += blockDim.x) {
+      const int64_t col = (int64_t)ti * SYRK_BT + cidx;
+      if (col >= Kf) continue;
+      double sv = 0.0, sc = 0.0;
+      for (int sp = 0; sp < splits; ++sp) {
+        const double* wv2 = ws_vec + (int64_t)sp * 2 * T * SYRK_BT;
+        sv += wv2[col];
+        sc += wv2[(int64_t)T * SYRK_BT + col];
+      }
+      vec[col] = sv;
+      vec[Kf + col] = sc;
+    }
+  }
+}
+
+// s[0] = sum_{r<ne} w_r, s[1] = sum_{r<ne} w_r b_r  (one block, fixed-order tree: deterministic)
+__global__ void syrk_scalar_kernel(const double* __restrict__ w, const double* __restrict__ b, int64_t ne, double w_e, double* __restrict__ s) {
+  __shared__ double sh0[1024], sh1[1024];
+  double a0 = 0.0, a1 = 0.0;
+  for (int64_t r = threadIdx.x; r < ne; r += blockDim.x) {
+    const double wr = w ? w[r] : w_e;
+    a0 += wr;
+    if (b) a1 = fma(wr, b[r], a1);
+  }
+  sh0[threadIdx.x] = a0;
+  sh1[threadIdx.x] = a1;
+  __syncthreads();
+  for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      sh0[threadIdx.x] += sh0[threadIdx.x + off];
+      sh1[threadIdx.x] += sh1[threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    s[0] = sh0[0];
+    s[1] = sh1[0];
+  }
+}
+
+// (AtWA, AtWb) of order Kf + ic from S, vec = [v ; c ; s]: intercept is row/column 0 (linear-learn.jl:239-241),
+// lambda on every diagonal entry (linear-learn.jl:253).
+__global__ void normal_eq_finish_kernel(const double* __restrict__ S, const double* __restrict__ vec, int64_t Kf, int ic, double lambda,
+                                        double* __restrict__ AtWA, double* __restrict__ AtWb) {
+  const int64_t n = Kf + ic;
+  const int64_t total = n * n;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / n, j = e % n;
+    double v;
+    if (ic && (i == 0 || j == 0)) {
+      if (i == 0 && j == 0) v = vec[2 * Kf];
+      else v = vec[Kf + (i == 0 ? j - 1 : i - 1)];
+    } else {
+      v = S[(i - ic) * Kf + (j - ic)];
+    }
+    if (i == j) v += lambda;
+    AtWA[e] = v;
+  }
+  if (AtWb && vec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      AtWb[i] = (ic && i == 0) ? vec[2 * Kf + 1] : vec[i - ic];
+    }
+  }
+}
+
+}  // namespace plb

@@ -1,0 +1,19 @@
+"""plb200 — B200-native descriptor linear algebra for PotentialLearning.jl's hot path (host mirror of the Julia API).
+
+Layout: csrc/ (sm_100a CUDA + C ABI -> plb200/libplb200.so), plb200/ (this package: ctypes binding + the reference's
+operator interface for the path), julia/ (the ccall shim a Julia deployment loads). See DESIGN.md / INTEGRATION.md.
+"""
+from . import _lib
+from ._lib import PLB200Error, finalize, init, last_timing, launch_count
+from .data import (Configuration, DataSet, Energy, ForceDescriptors, Forces, LocalDescriptors, get_energy, get_force_descriptors,
+                   get_forces, get_local_descriptors, get_values)
+from .dimred import PCA, ActiveSubspace, DimensionReducer, PCAState, compute_eigen, covariance, fit, fit_, select_eigendirections, transform_
+from .dpp import (EllEnsemble, SubsetSelector, get_dpp_mode, get_inclusion_prob, get_random_subset, greedy_subset, inclusion_prob, kDPP,
+                  rescale_, sample)
+from .kernels import (RBF, Diagonal, Distance, DotProduct, Euclidean, Feature, GlobalMean, GlobalSum, Kernel, KernelMatrix, Symmetric,
+                      compute_distance, compute_feature, compute_features, compute_kernel, get_parameters, gram_tile_coords,
+                      kernel_matrix_dev)
+from .learning import (CovariateLinearProblem, LinearProblem, UnivariateLinearProblem, assemble_matrices, learn_, normal_equations,
+                       ols_sums, ooc_learn_, pack_rhs, pack_rows)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

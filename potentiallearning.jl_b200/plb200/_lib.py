@@ -1,0 +1,124 @@
+"""ctypes binding of libplb200.so — the same C ABI a Julia `ccall` binds (include/plb200.h).
+
+The library is the product: if it is missing, or no sm_100 GPU is present, every call raises. There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("PLB200_LIB", os.path.join(_HERE, "libplb200.so"))
+
+PL_KERNEL_LINEAR, PL_KERNEL_DOT, PL_KERNEL_RBF = 0, 1, 2
+PL_CINV_IDENTITY, PL_CINV_DIAGONAL, PL_CINV_FULL = 0, 1, 2
+PL_FILL_RM_UPPER, PL_FILL_RM_LOWER, PL_FILL_FULL = 1, 2, 3
+PL_FILL_JULIA_U = PL_FILL_RM_LOWER
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_dbl = ctypes.c_double
+_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/plb200.h one to one (tests/test_abi.py checks the header against this)
+PROTOTYPES = {
+    "pl_init": (_int, [_int]),
+    "pl_finalize": (None, []),
+    "pl_last_error": (ctypes.c_char_p, []),
+    "pl_last_timing": (_int, [_dp, _dp, _dp]),
+    "pl_launch_count": (_i64, []),
+    "pl_workspace_bytes": (_i64, []),
+    "pl_gram_dot": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _i64, _int]),
+    "pl_gram_rbf": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _dbl, _dbl, _dp, _i64, _int]),
+    "pl_gram_cross": (_int, [_int, _dp, _i64, _i64, _dp, _i64, _i64, _i64, _int, _int, _dp, _dbl, _dbl, _dp, _i64]),
+    "pl_normal_eq": (_int, [_dp, _i64, _i64, _i64, _dp, _i64, _dbl, _dbl, _dp, _int, _dbl, _dp, _dp]),
+    "pl_cov": (_int, [_dp, _i64, _i64, _i64, _dp, _int, _int, _dp]),
+    "pl_gram_dev": (_int, [_int, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _int, _vp, _dbl, _dbl, _vp, _i64, _int, _int, _int, _int, _vp]),
+    "pl_gram_tile_count": (_i64, [_i64, _i64, _int, _int]),
+    "pl_gram_tile_coords": (_int, [_i64, _i64, _int, _int, _i64, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "pl_syrk_dev": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp]),
+    "pl_normal_eq_finish_dev": (_int, [_vp, _vp, _i64, _int, _dbl, _vp, _vp, _vp]),
+    "pl_colsum_dev": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "pl_scale_div_dev": (_int, [_vp, _dbl, _i64, _vp, _vp]),
+}
+
+
+class PLB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+_inited = False
+
+
+def load():
+    """dlopen libplb200.so and attach prototypes. Raises if the library has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PLB200Error(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). plb200 has no CPU fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export what the header declares
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().pl_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise PLB200Error(f"{what} failed (code {rc}): {last_error()}")
+
+
+def init(device: int = -1):
+    """pl_init: bind to one B200. Raises PLB200Error when there is no sm_100 device."""
+    global _inited
+    lib = load()
+    if not _inited:
+        check(lib.pl_init(int(device)), "pl_init")
+        _inited = True
+    return lib
+
+
+def lib():
+    return init()
+
+
+def finalize():
+    global _inited
+    if _lib is not None and _inited:
+        _lib.pl_finalize()
+        _inited = False
+
+
+def last_timing():
+    k, h, d = _dbl(), _dbl(), _dbl()
+    load().pl_last_timing(ctypes.byref(k), ctypes.byref(h), ctypes.byref(d))
+    return {"kernel_ms": k.value, "h2d_ms": h.value, "d2h_ms": d.value}
+
+
+def launch_count() -> int:
+    return int(load().pl_launch_count())
+
+
+def dptr(a: np.ndarray | None):
+    """host pointer of a C-contiguous float64 numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(_dp)
+
+
+def as_f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)

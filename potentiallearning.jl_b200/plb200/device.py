@@ -1,0 +1,70 @@
+"""Device-resident entry points on CUDA float64 torch tensors (torch is plumbing: device memory and streams only).
+Every function enqueues on torch's current stream through the `_dev` C ABI of libplb200.so and does not synchronise."""
+from __future__ import annotations
+
+from . import _lib
+
+
+def _stream(t):
+    import torch
+
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _check_mat(t, name):
+    import torch
+
+    if not (t.is_cuda and t.dtype == torch.float64 and t.dim() == 2 and t.stride(1) == 1):
+        raise ValueError(f"{name} must be a CUDA float64 row-major matrix")
+
+
+class DeviceEngine:
+    """The B200 compute engine used by plb200.distributed (and directly by the benchmarks)."""
+
+    name = "b200"
+
+    def syrk_partial(self, A, w=None, n_energy_rows=0, w_e=1.0, w_f=1.0, b=None, mean=None, want_vec=False):
+        """Unscaled partial sums of a row shard (pl_syrk_dev): S (K x K) and, if want_vec, vec = [v ; c ; s] (2K+2)."""
+        import torch
+
+        _check_mat(A, "A")
+        R, K = A.shape
+        S = torch.empty((K, K), device=A.device, dtype=torch.float64)
+        vec = torch.empty(2 * K + 2, device=A.device, dtype=torch.float64) if want_vec else None
+        _lib.check(
+            _lib.lib().pl_syrk_dev(A.data_ptr(), R, K, A.stride(0), None if w is None else w.data_ptr(), int(n_energy_rows), float(w_e),
+                                   float(w_f), None if b is None else b.data_ptr(), None if mean is None else mean.data_ptr(), S.data_ptr(),
+                                   None if vec is None else vec.data_ptr(), _stream(A)),
+            "pl_syrk_dev",
+        )
+        return S, vec
+
+    def normal_eq_finish(self, S, vec, intercept=False, lam=0.0, want_rhs=True):
+        import torch
+
+        K = S.shape[0]
+        n = K + (1 if intercept else 0)
+        M = torch.empty((n, n), device=S.device, dtype=torch.float64)
+        v = torch.empty(n, device=S.device, dtype=torch.float64) if (want_rhs and vec is not None) else None
+        _lib.check(
+            _lib.lib().pl_normal_eq_finish_dev(S.data_ptr(), None if vec is None else vec.data_ptr(), K, 1 if intercept else 0, float(lam),
+                                               M.data_ptr(), None if v is None else v.data_ptr(), _stream(S)),
+            "pl_normal_eq_finish_dev",
+        )
+        return M, v
+
+    def colsum(self, A):
+        import torch
+
+        _check_mat(A, "A")
+        R, K = A.shape
+        s = torch.empty(K, device=A.device, dtype=torch.float64)
+        _lib.check(_lib.lib().pl_colsum_dev(A.data_ptr(), R, K, A.stride(0), s.data_ptr(), _stream(A)), "pl_colsum_dev")
+        return s
+
+    def scale_div(self, x, denom):
+        import torch
+
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().pl_scale_div_dev(x.data_ptr(), float(denom), x.numel(), out.data_ptr(), _stream(x)), "pl_scale_div_dev")
+        return out

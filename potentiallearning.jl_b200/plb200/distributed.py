@@ -1,0 +1,67 @@
+"""Multi-GPU host logic: one process per GPU, torch.distributed (NCCL over NVLink) for the ONE exchange step each
+contraction has. The reference has no distributed code at all; sharding follows section 8(e):
+
+  * normal equations / covariance: shard ROWS (whole configurations per rank), each rank produces unscaled partial
+    sums with the fused SYRK kernel, ONE all-reduce of K*K (+2K+2) doubles, then the tiny finish kernel;
+    the centred covariance needs one earlier all-reduce of the K column sums (two-pass, required for 1e-10).
+  * Gram matrices: tiles are dealt round-robin to ranks; X is replicated; NO collective on the result (tile-packed
+    shards stay on their GPU).
+
+`engine` is the compute backend: DeviceEngine (libplb200.so on a B200) in production — there is no CPU engine in
+the product. The gloo/CPU tests inject a checker engine built on the oracle to exercise this file's logic only.
+"""
+from __future__ import annotations
+
+from .device import DeviceEngine
+
+
+def shard_rows(n_rows: int, rank: int, world: int, align: int = 1):
+    """Contiguous, balanced row range of `rank`; boundaries are multiples of `align` (e.g. rows per configuration)."""
+    units = (n_rows + align - 1) // align
+    base, rem = divmod(units, world)
+    lo_u = rank * base + min(rank, rem)
+    hi_u = lo_u + base + (1 if rank < rem else 0)
+    return min(lo_u * align, n_rows), min(hi_u * align, n_rows)
+
+
+def _all_reduce(t, group):
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def normal_equations_sharded(A_local, b_local=None, w_local=None, n_energy_rows_local=0, w_e=1.0, w_f=1.0, intercept=False, lam=0.0,
+                             group=None, engine=None):
+    """(A'WA + λI, A'Wb) of the row-wise concatenation of every rank's shard. Each rank's shard is laid out
+    [its energy rows ; its force rows]. Returns identical (M, v) on every rank."""
+    import torch
+
+    engine = engine or DeviceEngine()
+    want_vec = intercept or (b_local is not None)
+    S, vec = engine.syrk_partial(A_local, w_local, n_energy_rows_local, w_e, w_f, b_local, None, want_vec)
+    if vec is not None:
+        flat = torch.cat([S.reshape(-1), vec])  # one bucket -> one all-reduce
+        _all_reduce(flat, group)
+        K = S.shape[0]
+        S, vec = flat[: K * K].view(K, K), flat[K * K:]
+    else:
+        _all_reduce(S, group)
+    return engine.normal_eq_finish(S, vec, intercept, lam, want_rhs=b_local is not None)
+
+
+def covariance_sharded(X_local, n_total: int, mean=None, center=True, group=None, engine=None):
+    """(Q, m) with Q = (1/n) sum_r (x_r - m)(x_r - m)' over all ranks' rows (compute_eigen's Q + PCAState centring)."""
+    engine = engine or DeviceEngine()
+    m = None
+    if center:
+        if mean is None:
+            s = engine.colsum(X_local)
+            _all_reduce(s, group)
+            m = engine.scale_div(s, float(n_total))  # pca.m = sum(d) / length(d)
+        else:
+            m = mean
+    S, _ = engine.syrk_partial(X_local, None, 0, 1.0, 1.0, None, m, False)
+    _all_reduce(S, group)
+    return engine.scale_div(S, float(n_total)), m

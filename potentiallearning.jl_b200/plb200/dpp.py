@@ -1,0 +1,164 @@
+"""Host mirror of reference src/SubsetSelection/dpp.jl: kDPP over an L-ensemble whose kernel matrix is built on the GPU.
+
+The ONLY hot-path piece is `K = KernelMatrix(...)` inside the constructors (dpp.jl:25, :40). Everything after it is
+Determinantal.jl in the reference ([external], version unpinned — Project.toml has no compat bound, Manifest is
+git-ignored): EllEnsemble (dense symmetric eigendecomposition), rescale!, sample, greedy_subset, inclusion_prob.
+In a Julia deployment those calls stay in Determinantal.jl and see the GPU-built Symmetric K.
+So that a Python user of this mirror still gets a working selector, the published algorithms are restated here
+(Kulesza & Taskar, "Determinantal point processes for machine learning", 2012: Alg. 1 spectral sampling, Alg. 7/8
+k-DPP eigenvector selection via elementary symmetric polynomials; greedy MAP by Schur-complement updates).
+PARITY UNPINNED for these host routines: they use numpy's RNG, not Julia's, so indices are not comparable draw-for-draw.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .data import DataSet, LocalDescriptors
+from .kernels import Feature, Kernel, KernelMatrix, Symmetric
+
+
+class SubsetSelector:
+    pass
+
+
+class EllEnsemble:
+    """L-ensemble: L = U diag(λ) U', scaled by α (Determinantal.jl EllEnsemble + rescale!)."""
+
+    def __init__(self, K):
+        self.L = np.asarray(K) if isinstance(K, Symmetric) else np.asarray(K, dtype=np.float64)
+        if self.L.shape[0] != self.L.shape[1]:
+            raise ValueError("EllEnsemble needs a square kernel matrix")
+        lam, U = np.linalg.eigh(self.L)
+        self.λ = np.maximum(lam, 0.0)  # clip round-off negatives of a PSD kernel
+        self.U = U
+        self.α = 1.0
+
+    @property
+    def nitems(self):
+        return self.L.shape[0]
+
+
+def rescale_(ell: EllEnsemble, k: int):
+    """rescale!(L, k): pick α so that the expected cardinality sum(αλ/(1+αλ)) equals k (bisection in log α)."""
+    lam = ell.λ
+    rank = int(np.sum(lam > lam.max() * 1e-14))
+    if not (0 < k <= rank):
+        raise ValueError(f"cannot rescale an L-ensemble of numerical rank {rank} to expected size {k}")
+    if k == rank:
+        ell.α = 1e12 / max(lam.max(), 1e-300)
+        return ell
+    f = lambda la: np.sum(np.exp(la) * lam / (1.0 + np.exp(la) * lam)) - k
+    lo, hi = -60.0, 60.0
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        if f(mid) > 0:
+            hi = mid
+        else:
+            lo = mid
+    ell.α = float(np.exp(0.5 * (lo + hi)))
+    return ell
+
+
+def _esp(lam, k):
+    """E[l, n] = e_l(λ_1..λ_n), elementary symmetric polynomials (Kulesza & Taskar Alg. 7)."""
+    N = len(lam)
+    E = np.zeros((k + 1, N + 1))
+    E[0, :] = 1.0
+    for l in range(1, k + 1):
+        for n in range(1, N + 1):
+            E[l, n] = E[l, n - 1] + lam[n - 1] * E[l - 1, n - 1]
+    return E
+
+
+def sample(ell: EllEnsemble, k: int, rng=None):
+    """Determinantal.sample(L, k): exact k-DPP sample (Kulesza & Taskar Alg. 8 + Alg. 1). Returns sorted 0-based indices."""
+    rng = np.random.default_rng() if rng is None else rng
+    lam = ell.α * ell.λ
+    lam = lam / lam.max()  # e_k ratios are scale-invariant after normalising; avoids overflow
+    N = len(lam)
+    E = _esp(lam, k)
+    J = []
+    l = k
+    for n in range(N, 0, -1):
+        if l == 0:
+            break
+        if rng.random() < lam[n - 1] * E[l - 1, n - 1] / E[l, n]:
+            J.append(n - 1)
+            l -= 1
+    V = ell.U[:, J].copy()
+    items = []
+    for _ in range(len(J)):
+        p = np.sum(V * V, axis=1)
+        p = np.maximum(p, 0.0)
+        i = int(rng.choice(N, p=p / p.sum()))
+        items.append(i)
+        j = int(np.argmax(np.abs(V[i, :])))  # eliminate e_i from span(V)
+        Vj = V[:, j].copy()
+        V = np.delete(V, j, axis=1)
+        if V.shape[1] == 0:
+            break
+        V = V - np.outer(Vj, V[i, :] / Vj[i])
+        V, _ = np.linalg.qr(V)
+    return sorted(items)
+
+
+def greedy_subset(ell: EllEnsemble, k: int):
+    """greedy_subset(L, k): greedy MAP (largest conditional variance first, Cholesky-style updates)."""
+    L = ell.L
+    N = L.shape[0]
+    d = np.diag(L).astype(np.float64).copy()
+    C = np.zeros((k, N))
+    chosen = []
+    for t in range(k):
+        i = int(np.argmax(d))
+        chosen.append(i)
+        if d[i] <= 0:
+            break
+        e = (L[i, :] - C[:t, i] @ C[:t, :]) / np.sqrt(d[i])
+        C[t, :] = e
+        d = d - e * e
+        d[chosen] = -np.inf
+    return chosen
+
+
+def inclusion_prob(ell: EllEnsemble):
+    """Determinantal.inclusion_prob(L): diagonal of the marginal kernel U diag(αλ/(1+αλ)) U'."""
+    g = ell.α * ell.λ
+    g = g / (1.0 + g)
+    return np.sum(ell.U * ell.U * g[None, :], axis=1)
+
+
+class kDPP(SubsetSelector):
+    """kDPP(ds, f, k; batch_size = length(ds) ÷ 2, dt) and kDPP(features, k; batch_size) (dpp.jl:9-44).
+    `K` is the (rescaled) EllEnsemble as in the reference; `dpp.K.L` is the GPU-built kernel matrix."""
+
+    def __init__(self, *args, batch_size=None, dt=LocalDescriptors):
+        if len(args) == 3 and isinstance(args[0], DataSet) and isinstance(args[1], Feature) and isinstance(args[2], Kernel):
+            ds, f, k = args
+            n = len(ds)
+            Kmat = KernelMatrix(ds, f, k, dt=dt)  # dpp.jl:25  <- the hot path
+        elif len(args) == 2 and isinstance(args[1], Kernel):
+            features, k = args
+            n = len(features)
+            Kmat = KernelMatrix(features, k)  # dpp.jl:40
+        else:
+            raise TypeError("kDPP(ds, f, k; batch_size, dt) | kDPP(features, k; batch_size)")
+        self.batch_size = n // 2 if batch_size is None else int(batch_size)
+        ell = EllEnsemble(Kmat)
+        rescale_(ell, self.batch_size)
+        self.K = ell
+
+
+def get_random_subset(dpp: kDPP, batch_size: int | None = None, rng=None):
+    """get_random_subset(dpp; batch_size) (dpp.jl:50-53)."""
+    return sample(dpp.K, dpp.batch_size if batch_size is None else batch_size, rng)
+
+
+def get_dpp_mode(dpp: kDPP, batch_size: int | None = None):
+    """get_dpp_mode(dpp; batch_size) (dpp.jl:59-62)."""
+    return greedy_subset(dpp.K, dpp.batch_size if batch_size is None else batch_size)
+
+
+def get_inclusion_prob(dpp: kDPP):
+    """get_inclusion_prob(dpp) (dpp.jl:68-70)."""
+    return np.asarray(inclusion_prob(dpp.K)).reshape(-1)

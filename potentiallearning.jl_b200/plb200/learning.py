@@ -1,0 +1,240 @@
+"""Host mirror of reference src/Learning (linear-learning-problem.jl, linear-learn.jl) for the hot path:
+LinearProblem construction (which defines the packed row layout) and every normal-equation assembly site; the
+assembly runs on the GPU (pl_normal_eq), the small K x K solves stay on the host exactly as in the reference.
+
+Julia `learn!` is spelled `learn_` here (trailing underscore = mutates its first argument).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .data import DataSet, get_energy, get_force_descriptors, get_forces, get_local_descriptors, get_values
+
+
+class LinearProblem:
+    """abstract type LinearProblem (linear-learning-problem.jl:8)."""
+
+    def __new__(cls, ds: DataSet = None):
+        if cls is LinearProblem:
+            return _linear_problem(ds)
+        return super().__new__(cls)
+
+
+class UnivariateLinearProblem(LinearProblem):
+    """linear-learning-problem.jl:22-29."""
+
+    def __init__(self, iv_data, dv_data, beta, beta0, sigma, Sigma):
+        self.iv_data, self.dv_data = iv_data, dv_data
+        self.β, self.β0, self.σ, self.Σ = beta, beta0, sigma, Sigma
+
+    def __repr__(self):
+        return f"UnivariateLinearProblem{{T, {self.β}, {self.σ}}}"
+
+
+class CovariateLinearProblem(LinearProblem):
+    """linear-learning-problem.jl:48-58."""
+
+    def __init__(self, e, f, B, dB, beta, beta0, sigma_e, sigma_f, Sigma):
+        self.e, self.f, self.B, self.dB = e, f, B, dB
+        self.β, self.β0, self.σe, self.σf, self.Σ = beta, beta0, sigma_e, sigma_f, Sigma
+
+    def __repr__(self):
+        return f"CovariateLinearProblem{{T, {self.β}, {self.σe}, {self.σf}}}"
+
+
+def _linear_problem(ds: DataSet):
+    """LinearProblem(ds) (linear-learning-problem.jl:71-145): detect (energy, descriptors) / (forces, force descriptors)."""
+    try:
+        descriptors = [np.add.reduce(get_values(get_local_descriptors(c)), axis=0) for c in ds]  # :75 sum.(...)
+        energies = [get_values(get_energy(c)) for c in ds]
+        d_flag = True
+    except KeyError:
+        d_flag, descriptors, energies = False, None, None
+    try:
+        # :81 reduce(vcat, get_values(fd)) -> 3natoms vectors (atom-major, xyz inner); :127 reduce(hcat, fi) -> K x 3natoms.
+        # Stored transposed (3natoms x K, row-major) — byte-identical to Julia's column-major K x 3natoms.
+        force_descriptors = [get_values(get_force_descriptors(c)).reshape(-1, get_values(get_force_descriptors(c)).shape[2]) for c in ds]
+        forces = [get_values(get_forces(c)).reshape(-1) for c in ds]  # :126 reduce(vcat, fi)
+        fd_flag = True
+    except KeyError:
+        fd_flag, force_descriptors, forces = False, None, None
+    if d_flag and not fd_flag:
+        dim = len(descriptors[0])
+        return UnivariateLinearProblem(descriptors, energies, np.zeros(dim), np.zeros(1), np.array([1.0]), np.zeros((dim, dim)))
+    if fd_flag and not d_flag:
+        dim = force_descriptors[0].shape[1]
+        return UnivariateLinearProblem([m.T for m in force_descriptors], forces, np.zeros(dim), np.zeros(1), np.array([1.0]), np.zeros((dim, dim)))
+    if d_flag and fd_flag:
+        dim_d, dim_fd = len(descriptors[0]), force_descriptors[0].shape[1]
+        if dim_d != dim_fd:
+            raise ValueError("Descriptors and Force Descriptors have different dimension!")
+        dim = dim_d
+        return CovariateLinearProblem(energies, forces, descriptors, [m.T for m in force_descriptors], np.zeros(dim), np.zeros(1),
+                                      np.array([1.0]), np.array([1.0]), np.zeros((dim, dim)))
+    raise ValueError("Either no (Energy, Descriptors) or (Forces, Force Descriptors) in DataSet")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# packing: nested reference containers -> one row-major R x K buffer (the device layout), zero transposition
+# ----------------------------------------------------------------------------------------------------------------
+def _rows_of(iv):
+    """rows contributed by one iv_data / B / dB entry: a K-vector is one row; a K x m matrix is m rows (its columns)."""
+    iv = np.asarray(iv, dtype=np.float64)
+    return iv[None, :] if iv.ndim == 1 else iv.T
+
+
+def pack_rows(blocks) -> np.ndarray:
+    return np.ascontiguousarray(np.concatenate([_rows_of(b) for b in blocks], axis=0))
+
+
+def pack_rhs(vals) -> np.ndarray:
+    return np.ascontiguousarray(np.concatenate([np.atleast_1d(np.asarray(v, dtype=np.float64)) for v in vals]))
+
+
+def normal_equations(A, b=None, w=None, n_energy_rows=0, w_e=1.0, w_f=1.0, intercept=False, lam=0.0):
+    """GPU assembly of (A'WA + λI, A'Wb) through pl_normal_eq. A: R x K rows; see include/plb200.h for the weights."""
+    A = _lib.as_f64(A)
+    R, K = A.shape
+    n = K + (1 if intercept else 0)
+    b = None if b is None else _lib.as_f64(b)
+    w = None if w is None else _lib.as_f64(w)
+    M = np.empty((n, n))
+    v = np.empty(n) if b is not None else None
+    _lib.check(
+        _lib.lib().pl_normal_eq(_lib.dptr(A), R, K, K, _lib.dptr(w), int(n_energy_rows), float(w_e), float(w_f), _lib.dptr(b),
+                                1 if intercept else 0, float(lam), _lib.dptr(M), _lib.dptr(v)),
+        "pl_normal_eq",
+    )
+    return M, v
+
+
+def _solve(M, v):
+    """βs = M \\ v, falling back to pinv(M)*v on a singular system (linear-learn.jl:199-205, 252-258)."""
+    try:
+        return np.linalg.solve(M, v)
+    except np.linalg.LinAlgError as e:
+        print(e)
+        print("Linear system will be solved using pinv.")
+        return np.linalg.pinv(M) @ v
+
+
+def assemble_matrices(lp: CovariateLinearProblem, ws):
+    """assemble_matrices(lp, ws) (linear-learn.jl:286-299): (A, W, b) with W returned as its diagonal."""
+    A = np.concatenate([pack_rows(lp.B), pack_rows(lp.dB)], axis=0)
+    b = np.concatenate([pack_rhs(lp.e), pack_rhs(lp.f)])
+    W = np.concatenate([ws[0] * np.ones(len(lp.e)), ws[1] * np.ones(A.shape[0] - len(lp.e))])
+    return A, W, b
+
+
+def learn_(lp: LinearProblem, *args, **kw):
+    """learn!(lp, ...) dispatch (linear-learn.jl):
+    learn_(lp)                    default WLS, ws = ones, int = false          (:278-284)
+    learn_(lp, ws::list, int)     weighted least squares [; λ for covariate]   (:178-215, :226-268)
+    learn_(lp, α::Real)           OLS / MLE assembly                            (:11-23, :37-69)
+    """
+    if len(args) == 0:
+        n = 1 if isinstance(lp, UnivariateLinearProblem) else 2
+        return learn_(lp, [1.0] * n, False)
+    if len(args) == 2 and isinstance(args[1], (bool, np.bool_)):
+        return _learn_wls(lp, list(args[0]), bool(args[1]), **kw)
+    if len(args) == 1 and np.isscalar(args[0]):
+        return _learn_ols(lp, float(args[0]))
+    raise TypeError("learn_(lp) | learn_(lp, ws, int; λ) | learn_(lp, α); the minibatch/Adam variants stay in PotentialLearning.jl")
+
+
+def _learn_wls(lp, ws, intercept: bool, λ: float = 0.0, lam: float | None = None):
+    if lam is not None:
+        λ = lam
+    if isinstance(lp, UnivariateLinearProblem):
+        if λ != 0.0:
+            raise TypeError("learn!(::UnivariateLinearProblem, ws, int) has no λ keyword (linear-learn.jl:178-182)")
+        A = pack_rows(lp.iv_data)
+        b = pack_rhs(lp.dv_data)
+        # Q = Diagonal(ws[1] * ones(length(e_train))) (:196); the intercept column is all ones (:189-190)
+        M, v = normal_equations(A, b, None, A.shape[0], ws[0], ws[0], intercept, 0.0)
+    else:
+        A, _, b = assemble_matrices(lp, ws)
+        M, v = normal_equations(A, b, None, len(lp.e), ws[0], ws[1], intercept, λ)
+    βs = _solve(M, v)
+    if intercept:
+        lp.β0[:] = βs[0]
+        lp.β[:] = βs[1:]
+    else:
+        lp.β[:] = βs
+    return lp
+
+
+def ols_sums(iv_data, dv_data):
+    """AtA = sum(v*v' for v in iv), Atb = sum(v*b for (v,b) in zip(iv,dv)) (linear-learn.jl:16-17, 45-49, 94-95, 139-143)."""
+    A = pack_rows(iv_data)
+    b = pack_rhs(dv_data)
+    return normal_equations(A, b)
+
+
+def _learn_ols(lp, α: float):
+    if isinstance(lp, UnivariateLinearProblem):
+        AtA, Atb = ols_sums(lp.iv_data, lp.dv_data)  # :16-17 on the GPU
+        Q = np.linalg.pinv(AtA, rcond=0.0, hermitian=False) if α == 0 else _pinv_atol(AtA, α)  # pinv(AtA, α): atol
+        lp.β[:] = Q @ Atb
+        lp.σ[:] = np.std(Atb - AtA @ lp.β, ddof=1)
+        lp.Σ[:, :] = lp.σ[0] ** 2 * Q
+        return lp
+    # covariate MLE (:37-69): only the four sums are on the hot path; the Adam/MvNormal optimisation stays in Julia
+    AtAe, Atbe = ols_sums(lp.B, lp.e)
+    AtAf, Atbf = ols_sums(lp.dB, lp.f)
+    return AtAe, Atbe, AtAf, Atbf
+
+
+def _pinv_atol(M, atol):
+    """Julia pinv(M, atol): singular values <= atol are dropped (linear-learn.jl:19)."""
+    U, s, Vt = np.linalg.svd(M)
+    sinv = np.where(s > atol, 1.0 / np.where(s > atol, s, 1.0), 0.0)
+    return (Vt.T * sinv) @ U.T
+
+
+def ooc_learn_(lb_beta: np.ndarray, configs, ws=(30.0, 1.0), symmetrize=True, λ=0.01, reg_style="default", AtWA=None, AtWb=None,
+               eweight_normalized="squared"):
+    """ooc_learn!(lb, ds_train; ...) (linear-learn.jl:301-391) with the per-configuration accumulation
+    AtWA .+= A'*W*A; AtWb .+= A'*W*b (:355-356) done in ONE GPU pass over the stacked rows with per-row weights
+    (the energy weight ws[1]*{1, 1/natoms, 1/natoms^2} differs per configuration, :341-352).
+    configs: iterable of (global_descr K, force_descrs 3natoms x K, ref_energy, ref_forces 3natoms); descriptor evaluation
+    itself (InteratomicPotentials) is upstream of the hot path. Returns (AtWA, AtWb) like the reference."""
+    if AtWA is None or AtWb is None:
+        rows, rhs, wts = [], [], []
+        for gd, fdm, e, f in configs:
+            fdm = np.asarray(fdm, dtype=np.float64)
+            natoms = fdm.shape[0] // 3
+            if eweight_normalized is None:
+                we_norm = 1.0
+            elif eweight_normalized == "standard":
+                we_norm = 1 / natoms
+            elif eweight_normalized == "squared":
+                we_norm = 1 / natoms ** 2
+            else:
+                raise ValueError("eweight_normalized can only be nothing, :standard, or :squared")
+            rows.append(np.asarray(gd, dtype=np.float64)[None, :])
+            rows.append(fdm)
+            rhs.append(np.atleast_1d(np.float64(e)))
+            rhs.append(np.asarray(f, dtype=np.float64))
+            wts.append(np.array([we_norm * ws[0]]))
+            wts.append(ws[1] * np.ones(fdm.shape[0]))
+        A = np.ascontiguousarray(np.concatenate(rows, axis=0))
+        AtWA, AtWb = normal_equations(A, np.concatenate(rhs), np.concatenate(wts))
+    else:
+        AtWA, AtWb = np.array(AtWA, copy=True), np.array(AtWb, copy=True)
+    if symmetrize:
+        AtWA = np.triu(AtWA) + np.triu(AtWA, 1).T  # Symmetric(AtWA)
+    if λ is not None:
+        if reg_style == "default":
+            AtWA = AtWA + λ * np.eye(AtWA.shape[0])
+        if reg_style in ("scale_thresh", "scale"):
+            for i in range(AtWA.shape[0]):
+                reg_elem = AtWA[i, i] * (1 + λ)
+                if reg_style == "scale_thresh":
+                    reg_elem = max(reg_elem, λ)
+                AtWA[i, i] = reg_elem
+    β = np.linalg.solve(AtWA, AtWb)
+    print(f"condition number of AtWA: {np.linalg.cond(AtWA)}")
+    lb_beta[:] = β
+    return AtWA, AtWb
