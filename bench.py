@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 hot path (driver contract in the task statement).
+
+Workload (BASELINE.json configs[1]): KernelMatrix(F, RBF(Euclidean(300))) for N = 20 000 GlobalMean descriptors of
+length d = 300, fp64, synthetic (mu + N(0, 1/96)). One "step" = one full symmetric kernel matrix.
+
+  value     : Gram GFLOP/s with the descriptors already resident in HBM; algorithmic flops N(N+1)d (symmetric-half
+              convention, the reference itself only loops j >= i, kernels.jl:217-218) / device time of the step
+              (CUDA events on the launching stream; the step = column-mean + row-norm preludes + the fused DMMA kernel).
+  e2e       : the same metric through the host C ABI (pl_gram_rbf / pl_gram_part) with PINNED HOST buffers: H2D of the
+              descriptors and D2H of the result inside the timed region.
+  roofline  : the fused Gram kernel alone (events inside libplb200 around that launch) against the fp64 tensor (DMMA)
+              peak, taken as cuBLAS DGEMM 8192^3 measured in this same process (MEASURED_PEAKS.json has no fp64 figure).
+  N > 1     : one process per GPU; the 128x128 tiles of the upper triangle are dealt round-robin to ranks (no data-path
+              collective), strong scaling of the one matrix; time = max over ranks.
+  --impl reference : the reference's own algorithm (single-threaded scalar pair loop, kernels.jl:211-223) as restated in
+              oracle/pl_oracle.c, timed on a bounded sample of rows of the same workload on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "potentiallearning.jl_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+N_CFG, D_CFG = 20000, 300
+ELL, BETA = 1.0, 1.0
+SEED = 1002
+METRIC = "gram_rbf_fp64_gflops"
+UNIT = "GFLOP/s"
+
+
+def make_features_host(n=N_CFG, d=D_CFG, seed=SEED):
+    rng = np.random.default_rng(seed)
+    mu = 2.0 * rng.standard_normal(d)
+    return mu + rng.standard_normal((n, d)) / np.sqrt(96.0)
+
+
+def workload_config(extra=None):
+    cfg = {"workload": f"KernelMatrix RBF(Euclidean({D_CFG})) N={N_CFG} d={D_CFG} (BASELINE configs[1])", "flop_convention": "N(N+1)d",
+           "l2": "output 3.2 GB >> 126 MB L2; 256 MiB L2 flush written between timed steps"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def cpu_reference_rate(X, seconds_target, oracle):
+    """Time the restated reference pair loop on the first rows of the upper triangle; returns (GFLOP/s, pairs, seconds, rows)."""
+    k = oracle.RBF(oracle.Euclidean(X.shape[1]), ell=ELL, beta=BETA)
+    n, d = X.shape
+    t0 = time.perf_counter()
+    pairs = oracle.kernel_matrix_rows(X, k, 0, 8)  # calibrate
+    dt = time.perf_counter() - t0
+    rows = int(max(8, min(n, 8 * seconds_target / max(dt, 1e-6))))
+    t0 = time.perf_counter()
+    pairs = oracle.kernel_matrix_rows(X, k, 0, rows)
+    dt = time.perf_counter() - t0
+    return pairs * 2.0 * d / dt / 1e9, pairs, dt, rows
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle
+
+    oracle.build_c()
+    X = make_features_host()
+    rates = []
+    for _ in range(args.warmup):
+        cpu_reference_rate(X, 1.0, oracle)
+    t_total = 0.0
+    sample = None
+    for _ in range(args.steps):
+        r, pairs, dt, rows = cpu_reference_rate(X, 3.0, oracle)
+        rates.append(r)
+        t_total += dt
+        sample = f"rows 0..{rows} of the upper-triangle pair loop ({pairs} kernel evaluations of {N_CFG * (N_CFG + 1) // 2}) per step"
+    value = float(np.mean(rates))
+    full_ms = N_CFG * (N_CFG + 1) * D_CFG / (value * 1e9) * 1e3
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": full_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config({"ms_per_step_note": "extrapolated from the sampled rows to the full matrix"}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": sample + "; the reference loop is single-threaded Julia (kernels.jl:217-221), restated in C (oracle/pl_oracle.c)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import plb200
+    from plb200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    plb200.init(local_rank)
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- inputs resident in HBM ----------------
+    Xh = make_features_host()
+    X = torch.as_tensor(Xh, device=dev)
+    kern = plb200.RBF(plb200.Euclidean(D_CFG), ell=ELL, beta=BETA)
+    packed = world > 1
+    if packed:
+        ntiles_mine = int(_lib.load().pl_gram_tile_count(N_CFG, 0, rank, world))
+        out = torch.empty((ntiles_mine, 128, 128), device=dev, dtype=torch.float64)
+    else:
+        out = torch.empty((N_CFG, N_CFG), device=dev, dtype=torch.float64)
+    flush = torch.empty(256 * 1024 * 1024 // 8, device=dev, dtype=torch.float64)
+
+    def step():
+        plb200.kernel_matrix_dev(X, kern, out=out, fill=_lib.PL_FILL_FULL, part=rank, nparts=world, packed=packed)
+
+    flops = float(N_CFG) * (N_CFG + 1) * D_CFG
+    for _ in range(W):
+        step()
+    barrier()
+    launches0 = plb200.launch_count()
+    _lib.set_profiling(True)
+    step_ms, main_ms = [], []
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for _ in range(K):
+            flush.fill_(1.0)  # L2 flush, outside the per-step events
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            e1.synchronize()
+            step_ms.append(e0.elapsed_time(e1))
+            main_ms.append(_lib.last_main_kernel_ms())
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    _lib.set_profiling(False)
+    launches = plb200.launch_count() - launches0
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+    main_total = torch.tensor([sum(main_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(main_total, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / K
+    main_ms_per_step = float(main_total.item()) / K
+    value = flops / (ms_per_step * 1e-3) / 1e9
+
+    # ---------------- end to end through the host C ABI, pinned host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        Xp = torch.as_tensor(Xh).pin_memory()
+        lib = _lib.lib()
+        if packed:
+            Kp = torch.empty((ntiles_mine, 128, 128), dtype=torch.float64).pin_memory()
+            d2h = Kp.numel() * 8
+
+            def e2e_step():
+                _lib.check(lib.pl_gram_part(_lib.PL_KERNEL_RBF, _lib.dptr(Xp.numpy()), N_CFG, D_CFG, D_CFG, 0, 0, None, ELL, BETA, rank, world,
+                                            _lib.dptr(Kp.numpy().reshape(-1))), "pl_gram_part")
+        else:
+            Kp = torch.zeros((N_CFG, N_CFG), dtype=torch.float64).pin_memory()  # zeros(n,n) (kernels.jl:216)
+            d2h = sum(min(r0 + 128, N_CFG) * (min(r0 + 128, N_CFG) - r0) * 8 for r0 in range(0, N_CFG, 128))
+
+            def e2e_step():
+                # Symmetric(K) storage contract of the reference: uplo = :U triangle only (kernels.jl:217-222)
+                _lib.check(lib.pl_gram_rbf(_lib.dptr(Xp.numpy()), N_CFG, D_CFG, D_CFG, 0, None, ELL, BETA, _lib.dptr(Kp.numpy().reshape(-1)), N_CFG,
+                                           _lib.PL_FILL_JULIA_U), "pl_gram_rbf")
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        n_e2e = max(3, min(K, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()  # synchronous: returns after the D2H has completed
+        barrier()
+        t_e2e = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        tm = _lib.last_timing()
+        e2e = {"value": flops / float(t_e2e.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": N_CFG * D_CFG * 8, "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": float(t_e2e.item()) * 1e3, "steps": n_e2e, "last_call_ms": tm,
+               "api": "pl_gram_part (tile-packed shard)" if packed else "pl_gram_rbf fill=PL_FILL_JULIA_U (Symmetric uplo=:U storage)"}
+        del Kp
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline denominator: fp64 tensor peak = cuBLAS DGEMM measured here ----------------
+    del out
+    torch.cuda.empty_cache()
+    a = torch.randn((8192, 8192), device=dev, dtype=torch.float64)
+    b = torch.randn((8192, 8192), device=dev, dtype=torch.float64)
+    c = torch.empty((8192, 8192), device=dev, dtype=torch.float64)
+    for _ in range(2):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    peak_tflops = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    del a, b, c
+    flops_launch = flops / world  # tiles are dealt evenly; per-launch algorithmic flops of this rank
+    achieved = flops_launch / (main_ms_per_step * 1e-3) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_gram_rbf_ncu_summary.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic,
+                "kernel": "plb::gram_kernel<EPI_RBF>", "kernel_ms": main_ms_per_step,
+                "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; MEASURED_PEAKS.json has no fp64 figure; nominal 37 TFLOP/s (HGX B200)",
+                "algorithmic_flops_per_launch": flops_launch}
+
+    # ---------------- CPU baseline on the box's host cores (rank 0, N = 1 only, bounded sample) ----------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+
+        oracle.build_c()
+        r, pairs, dt, rows = cpu_reference_rate(Xh, 12.0, oracle)
+        cpu = {"value": r, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"rows 0..{rows} of the reference pair loop ({pairs} of {N_CFG * (N_CFG + 1) // 2} kernel evaluations, {dt:.1f} s); "
+                         "single thread because the reference loop is serial Julia (kernels.jl:217-221)", "host_cores_available": os.cpu_count()}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config({"parallelism": f"tiles round-robin over {world} GPU(s), no collective", "output": "tile-packed shards" if packed else "dense N x N, both triangles"}),
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
+            "wall_s_timed_region": t_wall}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -67,6 +67,10 @@ int pl_last_timing(double* kernel_ms, double* h2d_ms, double* d2h_ms);
 int64_t pl_launch_count(void);
 /* bytes of device workspace currently held by the library. */
 int64_t pl_workspace_bytes(void);
+/* on != 0: the dominant DMMA kernel (Gram or SYRK) of every following operation is bracketed by CUDA events on the
+ * stream it is launched on; pl_last_main_kernel_ms waits for it and returns its duration (roofline measurements). */
+int pl_set_profiling(int on);
+int pl_last_main_kernel_ms(double* ms);
 
 /* ---- Gram / kernel matrices: replaces KernelMatrix(F,k) kernels.jl:211-223 and (F1,F2,k) :229-244 ------ */
 
@@ -88,6 +92,13 @@ int pl_gram_rbf(const double* X, int64_t n, int64_t d, int64_t ldx, int cinv_kin
 int pl_gram_cross(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, const double* X2, int64_t n2, int64_t ldx2,
                   int64_t d, int alpha, int cinv_kind, const double* cinv, double ell, double beta, double* K,
                   int64_t ldk);
+
+/* Multi-GPU form of the symmetric kernel matrix for one process per GPU: this call computes only the 128x128 tiles
+ * t with t % nparts == part of the upper triangle (no collective: tiles are independent, kernels.jl:217-221 loops
+ * j >= i only) and returns them tile-packed, 128*128 doubles each, in pl_gram_tile_coords order.
+ * tiles: pl_gram_tile_count(n, 0, part, nparts) * 16384 doubles. */
+int pl_gram_part(int kernel_id, const double* X, int64_t n, int64_t d, int64_t ldx, int alpha, int cinv_kind, const double* cinv,
+                 double ell, double beta, int part, int nparts, double* tiles);
 
 /* ---- weighted normal equations: replaces every A'WA / A'Wb site of src/Learning/linear-learn.jl ------- */
 /* A: row-major R x Kf (rows = [n_energy_rows energy rows ; force rows], linear-learn.jl:232-245).

@@ -82,11 +82,9 @@ __host__ __device__ __forceinline__ int64_t gram_num_slots(int T1, int T2, int s
   return (int64_t)((T1 + 1) / 2) * (T1 + 1);
 }
 
-__device__ __forceinline__ double ipow(double x, int a) {
-  // integer power by squaring (DotProduct alpha; Julia's x^n for Int n is accurate to <1 ulp, this is within a few)
-  if (a == 2) return x * x;
-  if (a == 1) return x;
-  bool neg = a < 0;
+// Integer power by squaring for a general DotProduct alpha (kernels.jl:35 `^d.α`); alpha = 1, 2 are inlined in the epilogue.
+__device__ __noinline__ double ipow_general(double x, int a) {
+  const bool neg = a < 0;
   unsigned e = neg ? (unsigned)(-a) : (unsigned)a;
   double r = 1.0, b = x;
   while (e) {
@@ -95,6 +93,100 @@ __device__ __forceinline__ double ipow(double x, int a) {
     e >>= 1;
   }
   return neg ? 1.0 / r : r;
+}
+
+// exp(x) for x in [-708, 709]: n = rint(x/ln2) by the magic-number add, Cody-Waite two-constant reduction, degree-13
+// Taylor polynomial on |r| <= ln2/2 (truncation 4e-18), 2^n applied to the exponent field. Branch-free, 19 fp64
+// instructions; measured max relative error 1.4e-16 (1.2 ulp) against long double over 2e7 points in [-708, 0]
+// (tests/test_fast_exp.py re-states it). The library exp() costs ~370 SASS instructions per call site once its slow
+// paths are inlined, which made the fused RBF epilogue instruction-cache bound (profiles/r01 notes).
+// coefficients live in the constant bank so that every DFMA takes its constant as a c[][] operand (no UMOV pairs)
+__constant__ double EXP_C[18] = {
+    6755399441055744.0 /*1.5*2^52*/, 1.4426950408889634 /*log2 e*/, -6.93147180369123816490e-01 /*-ln2 hi*/,
+    -1.90821492927058770002e-10 /*-ln2 lo*/, 1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0,
+    1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+__device__ __forceinline__ double exp_fast(double x) {
+  const double t = fma(x, EXP_C[1], EXP_C[0]);
+  const int n = __double2loint(t);
+  const double nd = t - EXP_C[0];
+  double r = fma(nd, EXP_C[2], x);
+  r = fma(nd, EXP_C[3], r);
+  double p = EXP_C[4];
+#pragma unroll
+  for (int k = 5; k < 18; ++k) p = fma(p, r, EXP_C[k]);
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+// arguments outside the fast range (results below 3e-308 or overflow): the library routine, kept out of line
+__device__ __noinline__ double exp_slow(double x) { return exp(x); }
+
+// Fused epilogue of one warp tile. GENERAL = false: interior, off-diagonal tile (97% of the tiles of a large matrix):
+// no bounds or triangle logic, ~30 instructions per element. GENERAL = true: edge and diagonal tiles.
+//   rel0: (j - i) of accumulator (0,0,0) for diagonal tiles (elements with j < i are produced by mirroring, j == i is the
+//         kernel diagonal), 4096 otherwise. w1 / w2: write the direct / mirrored position; in diagonal tiles both
+//         positions are always written and hold 0 when their triangle was not requested (zeros(n,n) storage).
+template <int EPI, bool GENERAL>
+__device__ __forceinline__ void gram_epilogue(const double (&acc)[4][8][2], const GramParams& p, int64_t i0, int64_t j0, int rel0, bool w1, bool w2,
+                                              double* __restrict__ prow, double* __restrict__ pcol, int64_t ldo) {
+  unsigned imask = 0xfu, jmask = 0xffffu;
+  double sa[4], sb[8][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    bool ok = true;
+    if (GENERAL) {
+      ok = i0 + 8 * mt < p.n1;
+      if (!ok) imask &= ~(1u << mt);
+    }
+    double r = (EPI != EPI_LINEAR && ok) ? __ldg(p.ra + i0 + 8 * mt) : 0.0;
+    sa[mt] = (EPI == EPI_RBF) ? p.s * r : r;
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      bool ok = true;
+      if (GENERAL) {
+        ok = j0 + 8 * nt + 4 * c < p.n2;
+        if (!ok) jmask &= ~(1u << (2 * nt + c));
+      }
+      double r = (EPI != EPI_LINEAR && ok) ? __ldg(p.rb + j0 + 8 * nt + 4 * c) : 0.0;
+      sb[nt][c] = (EPI == EPI_RBF) ? p.s * r : r;
+    }
+  const double m2s = -2.0 * p.s;
+  const double diagval = (EPI == EPI_RBF) ? p.beta : 1.0;
+  const bool fill1 = p.packed || !p.symmetric || (p.fill & 1);
+  const bool fill2 = p.packed || (p.fill & 2);
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    double* const pr = prow + (int64_t)(8 * mt) * ldo;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        double v = acc[mt][nt][c];
+        if (EPI == EPI_DOT) {
+          v = v * sa[mt] * sb[nt][c];
+          if (p.alpha == 2) v = v * v;
+          else if (p.alpha != 1) v = ipow_general(v, p.alpha);
+        } else if (EPI == EPI_RBF) {
+          // x = s*(q_i + q_j - 2 G_ij) = -0.5 d2 / ell^2  (kernels.jl:73-74 with distances.jl:59 expanded)
+          const double x = fma(v, m2s, sa[mt] + sb[nt][c]);
+          v = (x >= -708.0 && x <= 709.0) ? exp_fast(x) : exp_slow(x);
+          v *= p.beta;
+        }
+        if (!GENERAL) {
+          if (w1) pr[8 * nt + 4 * c] = v;
+          if (w2) pcol[(int64_t)(8 * nt + 4 * c) * ldo + 8 * mt] = v;
+        } else {
+          const bool ok = ((imask >> mt) & (jmask >> (2 * nt + c)) & 1u) != 0;
+          const int rel = rel0 + (8 * nt + 4 * c - 8 * mt);
+          const bool dg = rel0 != 4096;
+          if (EPI != EPI_LINEAR && rel == 0) v = diagval;  // k(x,x): beta (d2 == 0), resp. n/sqrt(n*n) = 1 in the reference
+          if (ok && w1 && rel >= 0) pr[8 * nt + 4 * c] = (!dg || fill1 || rel == 0) ? v : 0.0;
+          if (ok && w2 && rel > 0) pcol[(int64_t)(8 * nt + 4 * c) * ldo + 8 * mt] = (!dg || fill2) ? v : 0.0;
+        }
+      }
+    }
+  }
 }
 
 template <int EPI>
@@ -202,57 +294,33 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------ fused epilogue ------------------------------
     // accumulator (mt, nt, c) of lane (g, t) is element
     //   i = 128*ti + 32*wm + 8*mt + perm(g),   j = 128*tj + 64*wn + 8*nt + perm(2t + c) = ... + t + 4c
-    const int64_t i_base = (int64_t)ti * GRAM_BM + 32 * wm + pg;  // + 8*mt
-    const int64_t j_base = (int64_t)tj * GRAM_BN + 64 * wn + t;   // + 8*nt + 4*c
+    const int il0 = 32 * wm + pg;  // local row of mt = 0
+    const int jl0 = 64 * wn + t;   // local col of (nt = 0, c = 0)
+    const int64_t i0 = (int64_t)ti * GRAM_BM + il0;
+    const int64_t j0 = (int64_t)tj * GRAM_BN + jl0;
     const bool diag_tile = p.symmetric && (ti == tj);
-    double rbj[8][2];
-    if (EPI != EPI_LINEAR) {
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int64_t j = j_base + 8 * nt + 4 * c;
-          rbj[nt][c] = (j < p.n2) ? __ldg(p.rb + j) : 0.0;
-        }
+    const bool f1 = p.packed || !p.symmetric || (p.fill & 1);            // write [i][j]
+    const bool f2 = !p.packed && p.symmetric && (p.fill & 2);            // write [j][i] (off-diagonal tiles)
+    double* base;
+    int64_t ldo, ib, jb;
+    if (p.packed) {  // tile k = (l - part) / nparts of this part, 128 x 128 row-major
+      base = p.out + ((l - p.part) / p.nparts) * (int64_t)(GRAM_BM * GRAM_BN);
+      ldo = GRAM_BN;
+      ib = il0;
+      jb = jl0;
+    } else {
+      base = p.out;
+      ldo = p.ldo;
+      ib = i0;
+      jb = j0;
     }
-    // tile-packed output: tile k = (l - part) / nparts of this part, 128 x 128 row-major
-    double* const tile_out = p.out + ((l - p.part) / p.nparts) * (int64_t)(GRAM_BM * GRAM_BN);
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-      const int64_t i = i_base + 8 * mt;
-      const bool iok = i < p.n1;
-      double rai = 0.0;
-      if (EPI != EPI_LINEAR && iok) rai = __ldg(p.ra + i);
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int64_t j = j_base + 8 * nt + 4 * c;
-          if (!iok || j >= p.n2) continue;
-          double v = acc[mt][nt][c];
-          if (EPI == EPI_DOT) {
-            v = ipow(v * rai * rbj[nt][c], p.alpha);
-            if (p.same_operand && i == j) v = 1.0;  // n/sqrt(n*n): the reference diagonal (kernels.jl:35)
-          } else if (EPI == EPI_RBF) {
-            double d2 = rai + rbj[nt][c] - 2.0 * v;
-            d2 = d2 < 0.0 ? 0.0 : d2;
-            v = p.beta * exp(p.s * d2);
-            if (p.symmetric && i == j) v = p.beta;  // d2(x,x) == 0 exactly in the reference
-          }
-          if (p.packed) {
-            tile_out[(i - (int64_t)ti * GRAM_BM) * GRAM_BN + (j - (int64_t)tj * GRAM_BN)] = v;
-          } else if (!p.symmetric) {
-            p.out[i * p.ldo + j] = v;
-          } else if (i == j) {
-            p.out[i * p.ldo + i] = v;
-          } else if (!(diag_tile && j < i)) {  // lower half of a diagonal tile is produced by mirroring
-            // unused triangle inside diagonal tiles is written as 0 (reference storage is zeros(n,n))
-            if (p.fill & 1) p.out[i * p.ldo + j] = v; else if (diag_tile) p.out[i * p.ldo + j] = 0.0;
-            if (p.fill & 2) p.out[j * p.ldo + i] = v; else if (diag_tile) p.out[j * p.ldo + i] = 0.0;
-          }
-        }
-      }
-    }
+    double* const prow = base + ib * ldo + jb;  // direct:  prow[8*mt*ldo + 8*nt + 4*c]
+    double* const pcol = base + jb * ldo + ib;  // mirror:  pcol[(8*nt + 4*c)*ldo + 8*mt]
+    const bool interior = ((int64_t)(ti + 1) * GRAM_BM <= p.n1) && ((int64_t)(tj + 1) * GRAM_BN <= p.n2);
+    if (interior && !diag_tile)
+      gram_epilogue<EPI, false>(acc, p, i0, j0, 0, f1, f2, prow, pcol, ldo);
+    else
+      gram_epilogue<EPI, true>(acc, p, i0, j0, diag_tile ? (jl0 - il0) : 4096, f1 || diag_tile, diag_tile ? true : f2, prow, pcol, ldo);
   }
 }
 

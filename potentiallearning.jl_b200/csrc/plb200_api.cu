@@ -87,7 +87,13 @@ struct Ctx {
   void* ws[WS_NSLOTS] = {};
   size_t ws_bytes[WS_NSLOTS] = {};
   double t_kernel = 0, t_h2d = 0, t_d2h = 0;
+  bool profiling = false;
+  bool main_timed = false;
 } g;
+
+// ev[4], ev[5] bracket the dominant (DMMA) kernel of the last operation when profiling is on
+#define MAIN_KERNEL_BEGIN(st) do { if (g.profiling) CUDA_TRY(cudaEventRecord(g.ev[4], st)); } while (0)
+#define MAIN_KERNEL_END(st) do { if (g.profiling) { CUDA_TRY(cudaEventRecord(g.ev[5], st)); g.main_timed = true; } } while (0)
 
 int ws_get(int slot, size_t bytes, void** out) {
   if (bytes == 0) bytes = 16;
@@ -215,6 +221,7 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   const int64_t mine = (p.ntiles_total - L.part + L.nparts - 1) / L.nparts;
   if (mine <= 0) return PL_OK;
   const int grid = (int)(mine < g.num_sms ? mine : g.num_sms);
+  if (L.epi != EPI_LINEAR || L.packed || L.symmetric) MAIN_KERNEL_BEGIN(st);
   switch (L.epi) {
     case EPI_LINEAR: gram_kernel<EPI_LINEAR><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
     case EPI_DOT: gram_kernel<EPI_DOT><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
@@ -222,6 +229,7 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
     default: return set_err(PL_EINVAL, "unknown epilogue %d", L.epi);
   }
   LAUNCH_CHECK();
+  if (L.epi != EPI_LINEAR || L.packed || L.symmetric) MAIN_KERNEL_END(st);
   return PL_OK;
 }
 
@@ -421,6 +429,7 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
   // R == 0: the kernel loads nothing (KT = 0) but the descriptor still needs a non-zero extent
   PL_TRY(make_tmap_2d(&tm, A, Kf, R > 0 ? R : 1, ld, 16, SYRK_BK));
   dim3 grid((unsigned)p.ntiles, (unsigned)p.splits);
+  MAIN_KERNEL_BEGIN(st);
   if (dmean)
     syrk_kernel<true, false><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, p);
   else if (p.want_vec)
@@ -428,6 +437,7 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
   else
     syrk_kernel<false, false><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, p);
   LAUNCH_CHECK();
+  MAIN_KERNEL_END(st);
   syrk_reduce_kernel<<<dim3((unsigned)p.ntiles, 8), 256, 0, st>>>(p.ws_tiles, p.ws_vec, p.T, p.ntiles, p.splits, Kf, dS, dvec, p.want_vec);
   LAUNCH_CHECK();
   if (p.want_vec) {
@@ -547,6 +557,24 @@ int pl_last_timing(double* kernel_ms, double* h2d_ms, double* d2h_ms) {
 }
 
 int64_t pl_launch_count(void) { return g_launches.load(); }
+
+int pl_set_profiling(int on) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g.profiling = on != 0;
+  g.main_timed = false;
+  return PL_OK;
+}
+
+int pl_last_main_kernel_ms(double* ms) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!g.main_timed) return set_err(PL_EINVAL, "no dominant kernel has been timed: call pl_set_profiling(1) first");
+  CUDA_TRY(cudaEventSynchronize(g.ev[5]));
+  float t = 0;
+  CUDA_TRY(cudaEventElapsedTime(&t, g.ev[4], g.ev[5]));
+  if (ms) *ms = t;
+  return PL_OK;
+}
 
 int64_t pl_workspace_bytes(void) {
   int64_t tot = 0;
@@ -685,6 +713,34 @@ int pl_gram_cross(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, con
   std::lock_guard<std::mutex> lk(g_mu);
   if (!X2) return set_err(PL_EINVAL, "X2 is NULL (use pl_gram_dot / pl_gram_rbf for the symmetric form)");
   return gram_host(kernel_id, X1, n1, ldx1, X2, n2, ldx2, d, alpha, cinv_kind, cinv, ell, beta, K, ldk, PL_FILL_FULL);
+}
+
+int pl_gram_part(int kernel_id, const double* X, int64_t n, int64_t d, int64_t ldx, int alpha, int cinv_kind, const double* cinv, double ell,
+                 double beta, int part, int nparts, double* tiles) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!X || !tiles || n < 0 || d <= 0 || ldx < d || nparts < 1 || part < 0 || part >= nparts) return set_err(PL_EINVAL, "bad arguments");
+  if (n == 0) return PL_OK;
+  CUDA_TRY(cudaSetDevice(g.device));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  double *dX, *dc = nullptr;
+  int64_t ld;
+  PL_TRY(h2d_matrix(X, n, d, ldx, WS_H_IN1, &dX, &ld));
+  if (kernel_id == PL_KERNEL_RBF && cinv_kind != PL_CINV_IDENTITY) {
+    if (!cinv) return set_err(PL_EINVAL, "cinv is NULL");
+    PL_TRY(h2d_vector(cinv, cinv_kind == PL_CINV_DIAGONAL ? d : d * d, WS_H_IN3, &dc));
+  }
+  const int T = (int)((n + GRAM_BM - 1) / GRAM_BM);
+  const int64_t slots = gram_num_slots(T, T, 1);
+  const int64_t mine = (slots - part + nparts - 1) / nparts;
+  void* outbuf;
+  PL_TRY(ws_get(WS_H_OUT1, (size_t)(mine > 0 ? mine : 1) * GRAM_BM * GRAM_BN * 8, &outbuf));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  PL_TRY(gram_dev_impl(kernel_id, dX, n, ld, nullptr, 0, 0, d, alpha, cinv_kind, dc, ell, beta, (double*)outbuf, GRAM_BN, PL_FILL_FULL, part, nparts, 1, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  if (mine > 0) CUDA_TRY(cudaMemcpyAsync(tiles, outbuf, (size_t)mine * GRAM_BM * GRAM_BN * 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();
 }
 
 int pl_normal_eq(const double* A, int64_t R, int64_t Kf, int64_t lda, const double* w, int64_t n_energy_rows, double w_e, double w_f,

@@ -31,6 +31,9 @@ PROTOTYPES = {
     "pl_last_timing": (_int, [_dp, _dp, _dp]),
     "pl_launch_count": (_i64, []),
     "pl_workspace_bytes": (_i64, []),
+    "pl_set_profiling": (_int, [_int]),
+    "pl_last_main_kernel_ms": (_int, [_dp]),
+    "pl_gram_part": (_int, [_int, _dp, _i64, _i64, _i64, _int, _int, _dp, _dbl, _dbl, _int, _int, _dp]),
     "pl_gram_dot": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _i64, _int]),
     "pl_gram_rbf": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _dbl, _dbl, _dp, _i64, _int]),
     "pl_gram_cross": (_int, [_int, _dp, _i64, _i64, _dp, _i64, _i64, _i64, _int, _int, _dp, _dbl, _dbl, _dp, _i64]),
@@ -106,6 +109,16 @@ def last_timing():
     k, h, d = _dbl(), _dbl(), _dbl()
     load().pl_last_timing(ctypes.byref(k), ctypes.byref(h), ctypes.byref(d))
     return {"kernel_ms": k.value, "h2d_ms": h.value, "d2h_ms": d.value}
+
+
+def set_profiling(on: bool):
+    check(load().pl_set_profiling(1 if on else 0), "pl_set_profiling")
+
+
+def last_main_kernel_ms() -> float:
+    ms = _dbl()
+    check(load().pl_last_main_kernel_ms(ctypes.byref(ms)), "pl_last_main_kernel_ms")
+    return ms.value
 
 
 def launch_count() -> int:

@@ -12,13 +12,15 @@ from . import _lib
 from .data import DataSet, get_energy, get_force_descriptors, get_forces, get_local_descriptors, get_values
 
 
-class LinearProblem:
-    """abstract type LinearProblem (linear-learning-problem.jl:8)."""
-
-    def __new__(cls, ds: DataSet = None):
+class _LinearProblemMeta(type):
+    def __call__(cls, *args, **kw):
         if cls is LinearProblem:
-            return _linear_problem(ds)
-        return super().__new__(cls)
+            return _linear_problem(*args, **kw)  # LinearProblem(ds) constructs the right concrete subtype
+        return super().__call__(*args, **kw)
+
+
+class LinearProblem(metaclass=_LinearProblemMeta):
+    """abstract type LinearProblem (linear-learning-problem.jl:8); LinearProblem(ds) is the constructor function (:71-145)."""
 
 
 class UnivariateLinearProblem(LinearProblem):

@@ -156,6 +156,20 @@ def test_rbf_mahalanobis(pl, orc, d):
     assert relerr(Kx, orc.kernel_matrix_cross(X[:20], X[20:75], orc.RBF(orc.Euclidean(d, C), ell=2.0))) < RTOL
 
 
+def test_rbf_extreme_arguments(pl, orc):
+    """exp argument outside the fast range (< -708: results below 3e-308) and the whole dynamic range in between."""
+    rng = np.random.default_rng(9)
+    n, d = 260, 10
+    X = rng.standard_normal((n, d))
+    for ell in (0.02, 0.05, 0.2, 5.0):
+        K = np.asarray(pl.KernelMatrix(X, pl.RBF(pl.Euclidean(d), ell=ell)))
+        ref = orc.symmetric(orc.kernel_matrix(X, orc.RBF(orc.Euclidean(d), ell=ell)))
+        big = ref > 1e-290
+        assert relerr(K[big], ref[big]) < 1e-10  # |x| up to ~700: the relative error of exp grows with |x| * eps
+        assert np.all(np.abs(K[~big] - ref[~big]) <= 1e-290)
+        assert np.all(np.isfinite(K))
+
+
 def test_gram_mean_heavy_descriptors_keep_1e10(pl, orc):
     """|x|^2 >> d2 (GlobalMean descriptors with a large common mean): the column-mean shift keeps the Gram-form distance exact."""
     rng = np.random.default_rng(5)
@@ -233,7 +247,11 @@ def test_reference_covariate_linear_tests(pl, orc):
         assert normerr(M, Mc) < RTOL and normerr(v, vc) < RTOL
         assert np.array_equal(M, M.T), "exactly symmetric"
         orc.learn_wls(o, ws, intercept, lam)
-        assert np.allclose(lpi.β, o.beta, rtol=1e-9, atol=1e-12) and np.allclose(lpi.β0, o.beta0, rtol=1e-9, atol=1e-12)
+        assert np.allclose(lpi.β, o.beta, rtol=1e-9, atol=1e-12)
+        if intercept:  # without an intercept β0 is left untouched (linear-learn.jl:261-266)
+            assert np.allclose(lpi.β0, o.beta0, rtol=1e-9, atol=1e-12)
+        else:
+            assert np.array_equal(lpi.β0, np.zeros(1))
     # default learn! == ws=[1,1], int=false (:104-109)
     lpa, lpb = pl.LinearProblem(ds), pl.LinearProblem(ds)
     pl.learn_(lpa)
