@@ -125,10 +125,11 @@ __global__ void prep_rows_kernel(const double* __restrict__ X, int64_t n, int64_
       }
     }
   }
-  if (MODE == PREP_CENTER_ONLY) return;
+  if (MODE != PREP_CENTER_ONLY) {
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (lane == 0) stat[row] = (MODE == PREP_DOT) ? 1.0 / sqrt(acc) : acc;
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) stat[row] = (MODE == PREP_DOT) ? 1.0 / sqrt(acc) : acc;
+  }
 }
 
 // stat[i] = sum_k Y[i][k] * Xc[i][k]  (quadratic form x' Cinv x with Y = Xc Cinv); one warp per row

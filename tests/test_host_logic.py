@@ -1,0 +1,133 @@
+"""Host-side logic of the reference-interface mirror that needs no GPU: containers, LinearProblem layout and packing,
+Symmetric storage semantics, row sharding, the restated k-DPP routines, eigen-direction selection."""
+import numpy as np
+import pytest
+
+import plb200 as pl
+from oracle import oracle as orc
+from plb200.dimred import _select
+from plb200.distributed import shard_rows
+
+
+def make_ds(rng, ncfg, nat, d, energies=True, forces=True):
+    cfgs = []
+    for _ in range(ncfg):
+        items = [pl.LocalDescriptors(rng.standard_normal((nat, d)))]
+        if energies:
+            items.append(pl.Energy(rng.random()))
+        if forces:
+            items += [pl.ForceDescriptors(rng.standard_normal((nat, 3, d))), pl.Forces(rng.standard_normal((nat, 3)))]
+        cfgs.append(pl.Configuration(*items))
+    return pl.DataSet(cfgs)
+
+
+def test_features_match_reference_definition():
+    rng = np.random.default_rng(0)
+    ds = make_ds(rng, 6, 20, 8, energies=False, forces=False)
+    gm, gs = pl.GlobalMean(), pl.GlobalSum()
+    for c in ds:
+        b = pl.get_values(pl.get_local_descriptors(c))
+        assert np.array_equal(pl.compute_feature(c, gm), orc.global_mean(list(b)))
+        assert np.array_equal(pl.compute_feature(c, gs), orc.global_sum(list(b)))
+        assert np.array_equal(pl.compute_feature(c, gm, dt=pl.ForceDescriptors), pl.compute_feature(c, gm))  # dt ignored (features.jl:59-61)
+    assert len(pl.compute_features(ds, gm)) == len(ds)
+    with pytest.raises(KeyError):
+        pl.get_energy(ds[0])
+
+
+def test_linear_problem_layout_matches_oracle():
+    rng = np.random.default_rng(1)
+    ds = make_ds(rng, 7, 5, 4)
+    lp = pl.LinearProblem(ds)
+    assert isinstance(lp, pl.CovariateLinearProblem) and isinstance(lp, pl.LinearProblem)
+    o = orc.linear_problem(
+        [list(pl.get_values(pl.get_local_descriptors(c))) for c in ds], [pl.get_values(pl.get_energy(c)) for c in ds],
+        [[list(a) for a in pl.get_values(pl.get_force_descriptors(c))] for c in ds], [list(pl.get_values(pl.get_forces(c))) for c in ds])
+    for a, b in zip(lp.B, o.B):
+        assert np.array_equal(a, b)
+    for a, b in zip(lp.dB, o.dB):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    for a, b in zip(lp.f, o.f):
+        assert np.array_equal(a, b)
+    A, W, b = pl.assemble_matrices(lp, [100.0, 1.0])
+    Ao, bo, qo = orc.wls_matrices(o, [100.0, 1.0], False)
+    assert np.array_equal(A, Ao) and np.array_equal(b, bo) and np.array_equal(W, qo)
+    assert A.flags.c_contiguous  # the device layout: row-major R x K, zero transposition from Julia's column-major blocks
+    # energies only / forces only -> Univariate
+    lpe = pl.LinearProblem(make_ds(rng, 4, 5, 4, forces=False))
+    assert isinstance(lpe, pl.UnivariateLinearProblem) and pl.pack_rows(lpe.iv_data).shape == (4, 4)
+    ds_f = pl.DataSet([pl.Configuration(pl.ForceDescriptors(rng.standard_normal((5, 3, 4))), pl.Forces(rng.standard_normal((5, 3)))) for _ in range(3)])
+    lpf = pl.LinearProblem(ds_f)
+    assert isinstance(lpf, pl.UnivariateLinearProblem) and lpf.iv_data[0].shape == (4, 15) and pl.pack_rows(lpf.iv_data).shape == (45, 4)
+    with pytest.raises(ValueError):
+        pl.LinearProblem(pl.DataSet([pl.Configuration(pl.Energy(1.0))]))
+    bad = pl.DataSet([pl.Configuration(pl.LocalDescriptors(np.ones((2, 3))), pl.Energy(1.0), pl.ForceDescriptors(np.ones((2, 3, 4))), pl.Forces(np.ones((2, 3))))])
+    with pytest.raises(ValueError, match="different dimension"):
+        pl.LinearProblem(bad)
+
+
+def test_symmetric_wrapper():
+    d = np.array([[1.0, 2.0, 3.0], [0.0, 4.0, 5.0], [0.0, 0.0, 6.0]])
+    S = pl.Symmetric(d)
+    assert np.array_equal(np.asarray(S), np.array([[1, 2, 3], [2, 4, 5], [3, 5, 6.0]]))
+    assert S[2, 0] == 3.0 and S[0, 2] == 3.0 and S.shape == (3, 3)
+    with pytest.raises(ValueError):
+        pl.Symmetric(np.ones((2, 3)))
+
+
+def test_kernel_argument_errors():
+    with pytest.raises(TypeError):
+        pl.RBF("forstner")
+    with pytest.raises(TypeError):
+        pl.DotProduct(2.0)
+    assert pl.get_parameters(pl.DotProduct(3)) == (3,)
+    assert pl.get_parameters(pl.RBF(pl.Euclidean(4), ell=2.0)) == (1e-8, 2.0, 1.0)
+    e = pl.Euclidean(pl.Symmetric(np.eye(3)))
+    assert e.dim == 3 and e.kind == 2
+    assert pl.Euclidean(pl.Diagonal([1.0, 2.0])).kind == 1
+
+
+def test_shard_rows_partitions_exactly():
+    for n, world, align in ((10, 3, 1), (2890000, 8, 289), (7, 8, 1), (1000, 4, 96)):
+        spans = [shard_rows(n, r, world, align) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+            assert a1 == b0 and a0 <= a1
+        assert all(lo % align == 0 for lo, _ in spans)
+        sizes = [(hi - lo + align - 1) // align for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_select_eigendirections_rules():
+    lam = np.array([0.1, 0.4, 1.5, 8.0])  # ascending, as eigen() returns
+    phi = np.eye(4)
+    l2, W = _select(lam, phi, 2)
+    assert np.array_equal(l2, lam[::-1]) and W.shape == (4, 2) and W[3, 0] == 1.0
+    l3, W = _select(lam, phi, 0.1)
+    resid = 1.0 - np.cumsum(lam[::-1]) / lam.sum()
+    assert W.shape[1] == int(np.sum(resid > 0.1))
+
+
+def test_kdpp_host_routines_on_oracle_kernel():
+    """The restated Determinantal.jl pieces (host-side, [external]) on a CPU-built L-ensemble."""
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((40, 6)) + 1.0
+    K = orc.symmetric(orc.kernel_matrix(X, orc.DotProduct()))
+    ell = pl.EllEnsemble(K)
+    pl.rescale_(ell, 5)
+    ip = pl.inclusion_prob(ell)
+    assert abs(ip.sum() - 5.0) < 1e-8 and np.all(ip > 0) and np.all(ip < 1)
+    s = pl.sample(ell, 5, rng=np.random.default_rng(0))
+    assert len(s) == 5 and len(set(s)) == 5 and all(0 <= i < 40 for i in s)
+    assert s == pl.sample(ell, 5, rng=np.random.default_rng(0)), "same seed + same eigendecomposition -> same indices"
+    g = pl.greedy_subset(ell, 5)
+    assert len(set(g)) == 5
+    # empirical inclusion frequencies of the k-DPP sampler are in the right ballpark of a k-DPP (sum to k)
+    cnt = np.zeros(40)
+    r = np.random.default_rng(1)
+    for _ in range(300):
+        for i in pl.sample(ell, 5, rng=r):
+            cnt[i] += 1
+    assert abs(cnt.sum() / 300 - 5.0) < 1e-12
+    with pytest.raises(ValueError):
+        pl.rescale_(ell, 30)  # a degree-2 polynomial kernel of 6-dim features has rank 21 < 30

@@ -1,0 +1,182 @@
+"""CPU tests of the oracle (oracle/oracle.py + oracle/pl_oracle.c): golden vectors, the properties the reference's own tests
+assert (test/kernels/kernel_tests.jl, test/learning/linear_tests.jl, test/dimension_reduction/dimension_reduction_tests.jl),
+numpy half vs C half, and the numerical facts the kernel design relies on."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "hotpath_golden.npz"))
+ULPS = 2e-14  # the oracle is plain fp64 in reference order; the golden truth is 80-bit extended
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+def normerr(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def test_golden_features_and_kernels():
+    ld = GOLD["kt_local"]
+    feats = [orc.global_mean(list(c)) for c in ld]
+    assert np.array_equal(np.stack(feats), GOLD["kt_feat"])  # mean(get_values(B)): sequential sum / natoms
+    Kd = orc.symmetric(orc.kernel_matrix(feats, orc.DotProduct(), use_c=False))
+    Kr = orc.symmetric(orc.kernel_matrix(feats, orc.RBF(orc.Euclidean(8)), use_c=False))
+    assert relerr(Kd, GOLD["kt_dot"]) < ULPS and relerr(Kr, GOLD["kt_rbf"]) < ULPS
+    F = GOLD["c1_feat"]
+    for use_c in (False, True):
+        assert relerr(orc.symmetric(orc.kernel_matrix(F, orc.DotProduct(3), use_c=use_c)), GOLD["c1_dot3"]) < ULPS
+        assert relerr(orc.symmetric(orc.kernel_matrix(F, orc.RBF(orc.Euclidean(26), ell=0.8, beta=2.0), use_c=use_c)), GOLD["c1_rbf"]) < 1e-13
+        assert relerr(orc.symmetric(orc.kernel_matrix(F, orc.RBF(orc.Euclidean(26, GOLD["c1_cdiag"]), ell=1.5), use_c=use_c)), GOLD["c1_rbf_diag"]) < 1e-13
+        assert relerr(orc.symmetric(orc.kernel_matrix(F, orc.RBF(orc.Euclidean(26, GOLD["c1_cfull"]), ell=2.0), use_c=use_c)), GOLD["c1_rbf_full"]) < 1e-13
+    Kx = orc.kernel_matrix_cross(F[:7], F[7:20], orc.RBF(orc.Euclidean(26), ell=0.8, beta=2.0), use_c=True)
+    assert relerr(Kx, GOLD["c1_rbf"][:7, 7:20]) < 1e-13
+
+
+def test_golden_normal_equations_and_cov():
+    A, b, q = GOLD["ne_A"], GOLD["ne_b"], GOLD["ne_q"]
+    for use_c in (False, True):
+        M, v = orc.normal_equations(A, b, q, 0.0, use_c=use_c)
+        assert normerr(M, GOLD["ne_M"]) < ULPS and normerr(v, GOLD["ne_v"]) < ULPS
+        Ai = np.hstack([np.concatenate([np.ones(12), np.zeros(A.shape[0] - 12)])[:, None], A])
+        M, v = orc.normal_equations(Ai, b, q, 0.01, use_c=use_c)
+        assert normerr(M, GOLD["ne_Mi"]) < ULPS and normerr(v, GOLD["ne_vi"]) < ULPS
+    X = GOLD["cov_X"]
+    m, C = orc.centered_cov(X)
+    assert relerr(m, GOLD["cov_mean"]) < ULPS and normerr(C, GOLD["cov_centered"]) < ULPS
+    assert normerr(orc.second_moment(X, use_c=False), GOLD["cov_raw"]) < ULPS
+    assert normerr(orc.second_moment(X, use_c=True), GOLD["cov_raw"]) < ULPS
+    st = orc.pcastate_fit([[r] for r in X], orc.PCAState(tol=3))  # one "atom" per configuration: global sum == the row
+    assert relerr(st.m, GOLD["cov_mean"]) < ULPS
+    lam = np.linalg.eigvalsh(GOLD["cov_centered"])[::-1]
+    assert np.allclose(st.lam, lam, rtol=1e-11) and st.W.shape == (8, 3)
+
+
+def test_reference_kernel_properties():
+    """test/kernels/kernel_tests.jl: K(x,x) ≈ 1, off-diagonal > 0, distance 0 on identical inputs, storage of Symmetric(K)."""
+    rng = np.random.default_rng(0)
+    ld = rng.standard_normal((10, 20, 8))
+    f = [orc.global_mean(list(c)) for c in ld]
+    e = orc.Euclidean(8)
+    assert orc.compute_distance(f[0], f[0], e) < np.finfo(float).eps  # :43
+    assert orc.compute_distance(f[0], f[1], e) > 0.0  # :44
+    dp, rbf = orc.DotProduct(), orc.RBF(e)
+    assert np.isclose(orc.compute_kernel(f[0], f[0], dp), 1.0) and np.isclose(orc.compute_kernel(f[0], f[0], rbf), 1.0)  # :66-67
+    assert orc.compute_kernel(f[0], f[1], dp) > 0 and orc.compute_kernel(f[0], f[1], rbf) > 0  # :72-73
+    K = orc.kernel_matrix(f, dp)
+    assert K.dtype == np.float64 and np.array_equal(np.tril(K, -1), np.zeros((10, 10)))  # zeros(n,n) + j >= i loop (:216-218)
+    S = orc.symmetric(K)
+    assert np.array_equal(S, S.T)
+    # RBF.alpha is stored but never applied: K[i,i] == beta exactly (kernels.jl:73-74)
+    Kr = orc.kernel_matrix(f, orc.RBF(e, alpha=0.5, beta=3.0))
+    assert np.all(np.diag(Kr) == 3.0)
+    # DotProduct: ONE sqrt of the product (kernels.jl:35), not the docstring formula
+    a, b = f[0], f[1]
+    assert orc.compute_kernel(a, b, orc.DotProduct(1)) == np.dot(a, b) / np.sqrt(np.dot(a, a) * np.dot(b, b))
+
+
+def test_reference_linear_problem_layout_and_learning():
+    """test/learning/linear_tests.jl: layout of lp.f / lp.B / lp.dB (:93-97), energies reproduced to 1e-4 (:50), intercept."""
+    rng = np.random.default_rng(0)
+    d, nat, ncfg = 8, 20, 8
+    ld = [list(rng.standard_normal((nat, d))) for _ in range(ncfg)]
+    e = list(rng.random(ncfg))
+    lp = orc.linear_problem(ld, e)
+    assert isinstance(lp, orc.UnivariateLinearProblem)
+    assert all(np.array_equal(a, orc.global_sum(l)) for a, l in zip(lp.iv_data, ld))  # :37
+    orc.learn_wls(lp, [1.0], False)
+    A = np.stack(lp.iv_data)
+    assert np.max(np.abs(A @ lp.beta - np.array(e))) < 1e-4  # :50
+    ncfg = 30
+    ld = [list(rng.standard_normal((nat, d))) for _ in range(ncfg)]
+    fd = [[[rng.standard_normal(d) for _ in range(3)] for _ in range(nat)] for _ in range(ncfg)]
+    e = list(rng.random(ncfg))
+    f = [[rng.standard_normal(3) for _ in range(nat)] for _ in range(ncfg)]
+    lp = orc.linear_problem(ld, e, fd, f)
+    assert isinstance(lp, orc.CovariateLinearProblem)
+    assert all(np.array_equal(a, np.concatenate(fi)) for a, fi in zip(lp.f, f))  # :94 reduce(vcat, fi)
+    for dB, fdi in zip(lp.dB, fd):  # :96-97 reduce(hcat, reduce(vcat, ...)): K x 3natoms, atom-major, xyz inner
+        assert dB.shape == (d, 3 * nat)
+        assert np.array_equal(dB[:, 4], fdi[1][1]) and np.array_equal(dB[:, 3 * 7 + 2], fdi[7][2])
+    A, b, q = orc.wls_matrices(lp, [100.0, 1.0], True)
+    assert A.shape == (ncfg + 3 * nat * ncfg, d + 1)
+    assert np.array_equal(A[:, 0], np.concatenate([np.ones(ncfg), np.zeros(3 * nat * ncfg)]))  # intercept column (:240)
+    assert np.array_equal(q[:ncfg], 100.0 * np.ones(ncfg)) and np.array_equal(q[ncfg:], np.ones(3 * nat * ncfg))
+    M0, _ = orc.normal_equations(A, b, q, 0.0)
+    M1, _ = orc.normal_equations(A, b, q, 0.25)
+    assert np.allclose(M1 - M0, 0.25 * np.eye(d + 1))  # λ*I regularises the intercept too (:253)
+    # OLS sums == weighted normal equations with unit weights (linear-learn.jl:16-17 vs :200)
+    AtA, Atb = orc.ols_sums(lp.B, lp.e)
+    Bm = np.stack(lp.B)
+    assert np.allclose(AtA, Bm.T @ Bm) and np.allclose(Atb, Bm.T @ np.array(lp.e))
+    AtAf, Atbf = orc.ols_sums(lp.dB, lp.f)
+    dBm = np.concatenate([m.T for m in lp.dB])
+    assert np.allclose(AtAf, dBm.T @ dBm) and np.allclose(Atbf, dBm.T @ np.concatenate(lp.f))
+
+
+def test_ooc_weights():
+    """ooc_learn! energy weight ws[1] * {1, 1/natoms, 1/natoms^2} (linear-learn.jl:341-349)."""
+    rng = np.random.default_rng(4)
+    K = 6
+    cfgs = [(rng.standard_normal(K), rng.standard_normal((3 * n, K)), rng.standard_normal(), rng.standard_normal(3 * n)) for n in (3, 5, 3)]
+    for norm, fn in ((None, lambda n: 1.0), ("standard", lambda n: 1 / n), ("squared", lambda n: 1 / n ** 2)):
+        M, v = orc.ooc_accumulate(cfgs, ws=(30.0, 1.0), eweight_normalized=norm)
+        Mr = sum(30.0 * fn(fd.shape[0] // 3) * np.outer(gd, gd) + fd.T @ fd for gd, fd, _, _ in cfgs)
+        assert np.allclose(M, Mr)
+    with pytest.raises(ValueError):
+        orc.ooc_accumulate(cfgs, eweight_normalized="bogus")
+
+
+def test_reference_dimension_reduction_properties():
+    """dimension_reduction_tests.jl: λ_as ≈ λ_pca (:41), W is d x tol (:32-33); Float64 tol keeps residual fraction > tol (:18-19)."""
+    rng = np.random.default_rng(0)
+    rows = [orc.global_sum(list(rng.standard_normal((20, 8)))) for _ in range(10)]
+    lam, W = orc.select_eigendirections(rows, 2)
+    assert lam.shape == (8,) and W.shape == (8, 2) and np.all(np.diff(lam) <= 0)
+    lam_f, W_f = orc.select_eigendirections(rows, 0.3)
+    resid = 1.0 - np.cumsum(lam_f) / np.sum(lam_f)
+    assert W_f.shape[1] == int(np.sum(resid > 0.3))
+    # the un-centred second moment is a MEAN (1/n), not 1/(n-1) (dimension_reduction.jl:12)
+    Q = orc.second_moment(rows)
+    assert np.allclose(Q, np.stack(rows).T @ np.stack(rows) / 10)
+    # PCAState: the mean is computed once and then persists (pca_state.jl:34)
+    st = orc.PCAState(tol=2)
+    ld = [list(rng.standard_normal((20, 8))) for _ in range(10)]
+    orc.pcastate_fit(ld, st)
+    m0 = st.m.copy()
+    orc.pcastate_fit(ld[:4], st)
+    assert np.array_equal(st.m, m0)
+
+
+def test_design_numerics_mean_shift_and_two_pass():
+    """The facts the GPU design relies on: the Gram-form distance needs the column-mean shift to hold
+    1e-10 on mean-heavy descriptors; one-pass covariance fails the bar, two-pass holds it."""
+    rng = np.random.default_rng(3)
+    n, d = 300, 300
+    X = 2.0 * rng.standard_normal(d) + rng.standard_normal((n, d)) / np.sqrt(96)
+    Xl = X.astype(np.longdouble)
+    D2 = ((Xl[:, None, :] - Xl[None, :, :]) ** 2).sum(-1).astype(np.float64)
+    off = ~np.eye(n, dtype=bool)
+
+    def gram_form(Y):
+        q = (Y * Y).sum(1)
+        return q[:, None] + q[None, :] - 2.0 * (Y @ Y.T)
+
+    err_raw = np.max(np.abs(gram_form(X) - D2)[off] / D2[off])
+    err_shift = np.max(np.abs(gram_form(X - X.mean(0)) - D2)[off] / D2[off])
+    assert err_shift < 1e-13 < err_raw
+    Xc = 50.0 + rng.standard_normal((4000, 16))
+    truth = np.cov(Xc.astype(np.longdouble).T, bias=True).astype(np.float64)
+    m = Xc.mean(0)
+    one_pass = Xc.T @ Xc / 4000 - np.outer(m, m)
+    _, two_pass = orc.centered_cov(Xc)
+    assert normerr(two_pass, truth) < 1e-13 < normerr(one_pass, truth)
+
+
+def test_pair_loop_sampler_counts_pairs():
+    X = np.random.default_rng(1).standard_normal((50, 6))
+    assert orc.kernel_matrix_rows(X, orc.RBF(orc.Euclidean(6)), 0, 4) == 50 + 49 + 48 + 47
