@@ -168,13 +168,17 @@ int tma_operand(const double* src, int64_t rows, int64_t cols, int64_t ld, int s
 }
 
 int colsum(const double* dA, int64_t R, int64_t Kf, int64_t lda, double denom, double* dout, cudaStream_t st) {
-  const int64_t nblk = (R + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK;
+  // rows per block: aim at >= 16 blocks per SM, between 32 and 512 rows each (fixed for a given shape: deterministic)
+  const int64_t colblocks = ((Kf + 1) / 2 + 127) / 128;
+  int64_t rpb = R * colblocks / ((int64_t)g.num_sms * 16);
+  rpb = rpb < 32 ? 32 : (rpb > COLSUM_MAX_ROWS_PER_BLOCK ? COLSUM_MAX_ROWS_PER_BLOCK : (rpb + 3) / 4 * 4);
+  const int64_t nblk = (R + rpb - 1) / rpb;
   void* part;
   PL_TRY(ws_get(WS_COLSUM_PARTIAL, (size_t)(nblk > 0 ? nblk : 1) * Kf * 8, &part));
   if (nblk > 0) {
     const int64_t pairs = (Kf + 1) / 2;
     dim3 grid((unsigned)((pairs + 127) / 128), (unsigned)nblk);
-    colsum_partial_kernel<<<grid, 128, 0, st>>>(dA, R, Kf, lda, (double*)part);
+    colsum_partial_kernel<<<grid, 128, 0, st>>>(dA, R, Kf, lda, (int)rpb, (double*)part);
     LAUNCH_CHECK();
   }
   colsum_final_kernel<<<(unsigned)((Kf + 127) / 128), 128, 0, st>>>((const double*)part, nblk, Kf, denom, dout);

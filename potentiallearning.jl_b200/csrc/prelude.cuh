@@ -10,14 +10,15 @@
 
 namespace plb {
 
-constexpr int COLSUM_ROWS_PER_BLOCK = 512;
+constexpr int COLSUM_MAX_ROWS_PER_BLOCK = 512;
 
-// partial[blockIdx.y][col] = sum of rows [blockIdx.y*RPB, ...) of column col. blockDim.x threads x 2 columns each.
-__global__ void colsum_partial_kernel(const double* __restrict__ A, int64_t R, int64_t Kf, int64_t lda, double* __restrict__ partial) {
+// partial[blockIdx.y][col] = sum of rows [blockIdx.y*rpb, ...) of column col. blockDim.x threads x 2 columns each.
+// rpb (rows per block) is chosen by the host so that small matrices still fill the machine.
+__global__ void colsum_partial_kernel(const double* __restrict__ A, int64_t R, int64_t Kf, int64_t lda, int rpb, double* __restrict__ partial) {
   const int64_t c0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (c0 >= Kf) return;
-  const int64_t r0 = (int64_t)blockIdx.y * COLSUM_ROWS_PER_BLOCK;
-  int64_t r1 = r0 + COLSUM_ROWS_PER_BLOCK;
+  const int64_t r0 = (int64_t)blockIdx.y * rpb;
+  int64_t r1 = r0 + rpb;
   if (r1 > R) r1 = R;
   const bool pair = (c0 + 1 < Kf);
   double s0 = 0.0, s1 = 0.0;

@@ -1,0 +1,142 @@
+# PotentialLearningB200.jl — the Julia side of the drop-in: `using PotentialLearning, PotentialLearningB200` re-points the hot
+# path of PotentialLearning.jl (v0.2.7) at libplb200.so (hand-written sm_100a CUDA, C ABI in include/plb200.h).
+#
+# It ONLY adds more specific methods for the signatures below; everything else of PotentialLearning stays as is:
+#   KernelMatrix(F::Vector{Vector{Float64}}, k::DotProduct)                    src/Kernels/kernels.jl:211-223
+#   KernelMatrix(F::Vector{Vector{Float64}}, k::RBF)   (k.d isa Euclidean)     src/Kernels/kernels.jl:211-223
+#   KernelMatrix(F1, F2, k)                                                    src/Kernels/kernels.jl:229-244
+#   learn!(lp::UnivariateLinearProblem, ws::Vector, int::Bool)                 src/Learning/linear-learn.jl:178-215
+#   learn!(lp::CovariateLinearProblem,  ws::Vector, int::Bool; λ)              src/Learning/linear-learn.jl:226-268
+#   learn!(lp::UnivariateLinearProblem, α::Real)   (assembly only)             src/Learning/linear-learn.jl:11-23
+#   compute_eigen(d::Vector{<:Vector{<:Real}})                                 src/DimensionReduction/dimension_reduction.jl:11-14
+#   fit!(ds::DataSet, pca::PCAState)                                           src/DimensionReduction/pca_state.jl:20-40
+# kDPP(ds, f, k) / kDPP(features, k) (src/SubsetSelection/dpp.jl:18-44) need no override: they call KernelMatrix and hand
+# the Symmetric result to Determinantal.jl exactly as before.
+#
+# NOTE: Julia is not installed in the build image nor on the benchmark box, so this file has never been executed there.
+# It is deliberately declarative (pack -> ccall -> wrap); all logic lives behind the C ABI, which the Python ctypes mirror
+# (plb200/_lib.py) exercises symbol for symbol in tests/. There is no CPU fallback: a nonzero status raises.
+module PotentialLearningB200
+
+using LinearAlgebra
+using PotentialLearning
+import PotentialLearning: KernelMatrix, learn!, fit!, compute_eigen, DotProduct, RBF, Euclidean, UnivariateLinearProblem,
+                          CovariateLinearProblem, PCAState, DataSet, get_values, get_local_descriptors, select_eigendirections
+
+const libplb200 = get(ENV, "PLB200_LIB", joinpath(@__DIR__, "..", "plb200", "libplb200.so"))
+
+const PL_KERNEL_DOT, PL_KERNEL_RBF = Cint(1), Cint(2)
+const PL_CINV_IDENTITY, PL_CINV_DIAGONAL, PL_CINV_FULL = Cint(0), Cint(1), Cint(2)
+const PL_FILL_JULIA_U = Cint(2)   # Symmetric(K) with uplo = :U over column-major storage
+
+function check(rc::Cint, what)
+    rc == 0 || error("$what failed (code $rc): ", unsafe_string(ccall((:pl_last_error, libplb200), Cstring, ())))
+    nothing
+end
+
+function __init__()
+    dev = parse(Cint, get(ENV, "PLB200_DEVICE", "-1"))
+    check(ccall((:pl_init, libplb200), Cint, (Cint,), dev), "pl_init")   # errors without an sm_100 GPU: no CPU path
+    atexit(() -> ccall((:pl_finalize, libplb200), Cvoid, ()))
+end
+
+# Vector{Vector{Float64}} -> d x n column-major == the library's row-major n x d (zero transposition)
+pack(F::Vector{Vector{Float64}}) = reduce(hcat, F)
+
+cinv_args(e::Euclidean) =
+    e.Cinv isa Diagonal ? (all(==(1.0), e.Cinv.diag) ? (PL_CINV_IDENTITY, C_NULL, nothing) : (PL_CINV_DIAGONAL, pointer(e.Cinv.diag), e.Cinv.diag)) :
+                          (let M = Matrix(e.Cinv); (PL_CINV_FULL, pointer(M), M) end)
+
+# ---- KernelMatrix(F, k) -> Symmetric{Float64,Matrix{Float64}} (kernels.jl:211-223) -------------------------------------------
+function KernelMatrix(F::Vector{Vector{Float64}}, k::DotProduct)
+    X = pack(F); d, n = size(X)
+    K = zeros(n, n)                                                                    # kernels.jl:216
+    check(ccall((:pl_gram_dot, libplb200), Cint, (Ptr{Cdouble}, Int64, Int64, Int64, Cint, Ptr{Cdouble}, Int64, Cint),
+                X, n, d, d, Cint(k.α), K, n, PL_FILL_JULIA_U), "pl_gram_dot")
+    Symmetric(K)                                                                       # kernels.jl:222
+end
+
+function KernelMatrix(F::Vector{Vector{Float64}}, k::RBF)
+    k.d isa Euclidean || return invoke(KernelMatrix, Tuple{Vector{Vector{Float64}},PotentialLearning.Kernel}, F, k)
+    X = pack(F); d, n = size(X)
+    kind, cptr, keep = cinv_args(k.d)
+    K = zeros(n, n)
+    GC.@preserve keep check(ccall((:pl_gram_rbf, libplb200), Cint,
+                (Ptr{Cdouble}, Int64, Int64, Int64, Cint, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cdouble}, Int64, Cint),
+                X, n, d, d, kind, cptr, Float64(k.ℓ), Float64(k.β), K, n, PL_FILL_JULIA_U), "pl_gram_rbf")
+    Symmetric(K)
+end
+
+# ---- KernelMatrix(F1, F2, k) -> Matrix m x n (kernels.jl:229-244). Column-major m x n == row-major n x m: pass F2 first. ------
+function KernelMatrix(F1::Vector{Vector{Float64}}, F2::Vector{Vector{Float64}}, k::Union{DotProduct,RBF})
+    (k isa RBF && !(k.d isa Euclidean)) && return invoke(KernelMatrix, Tuple{Vector{Vector{Float64}},Vector{Vector{Float64}},PotentialLearning.Kernel}, F1, F2, k)
+    X1 = pack(F1); X2 = pack(F2); d, m = size(X1); n = size(X2, 2)
+    K = zeros(m, n)
+    kid, α, kind, cptr, keep, ℓ, β = k isa DotProduct ? (PL_KERNEL_DOT, Cint(k.α), PL_CINV_IDENTITY, C_NULL, nothing, 1.0, 1.0) :
+                                                      (PL_KERNEL_RBF, Cint(0), cinv_args(k.d)..., Float64(k.ℓ), Float64(k.β))
+    GC.@preserve keep check(ccall((:pl_gram_cross, libplb200), Cint,
+                (Cint, Ptr{Cdouble}, Int64, Int64, Ptr{Cdouble}, Int64, Int64, Int64, Cint, Cint, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cdouble}, Int64),
+                kid, X2, n, d, X1, m, d, d, α, kind, cptr, ℓ, β, K, m), "pl_gram_cross")
+    K
+end
+
+# ---- normal equations ---------------------------------------------------------------------------------------------------------
+# rows of A as the library wants them: [B' ; dB'] row-major R x K == hcat of the K-vectors / K x m blocks, column-major K x R
+pack_rows(blocks) = reduce(hcat, blocks)
+
+function normal_eq(A::Matrix{Float64}, b::Vector{Float64}, ne::Integer, we, wf, int::Bool, λ; w = nothing)
+    K, R = size(A); n = K + (int ? 1 : 0)
+    AtWA = zeros(n, n); AtWb = zeros(n)
+    check(ccall((:pl_normal_eq, libplb200), Cint,
+                (Ptr{Cdouble}, Int64, Int64, Int64, Ptr{Cdouble}, Int64, Cdouble, Cdouble, Ptr{Cdouble}, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}),
+                A, R, K, K, w === nothing ? C_NULL : w, ne, we, wf, b, int, λ, AtWA, AtWb), "pl_normal_eq")
+    AtWA, AtWb
+end
+
+solve(M, v) = try M \ v catch e; println(e); println("Linear system will be solved using pinv."); pinv(M) * v end   # linear-learn.jl:199-205
+
+function learn!(lp::UnivariateLinearProblem, ws::Vector, int::Bool)                    # linear-learn.jl:178-215
+    A = pack_rows(lp.iv_data); b = Float64.(reduce(vcat, lp.dv_data))
+    M, v = normal_eq(A, b, size(A, 2), ws[1], ws[1], int, 0.0)
+    βs = solve(M, v)
+    if int; lp.β0 .= βs[1]; lp.β .= βs[2:end] else lp.β .= βs end
+end
+
+function learn!(lp::CovariateLinearProblem, ws::Vector, int::Bool; λ::Real = 0.0)      # linear-learn.jl:226-268
+    A = hcat(pack_rows(lp.B), pack_rows(lp.dB)); b = Float64.(vcat(lp.e, reduce(vcat, lp.f)))
+    M, v = normal_eq(A, b, length(lp.e), ws[1], ws[2], int, Float64(λ))
+    βs = solve(M, v)
+    if int; lp.β0 .= βs[1]; lp.β .= βs[2:end] else lp.β .= βs end
+end
+
+function learn!(lp::UnivariateLinearProblem, α::Real)                                  # linear-learn.jl:11-23
+    A = pack_rows(lp.iv_data); b = Float64.(reduce(vcat, lp.dv_data))
+    AtA, Atb = normal_eq(A, b, 0, 1.0, 1.0, false, 0.0)                                # sum(v*v'), sum(v*b) on the GPU (:16-17)
+    Q = pinv(AtA, α)
+    lp.β .= Q * Atb
+    lp.σ .= std(Atb - AtA * lp.β)
+    lp.Σ .= Symmetric(lp.σ[1]^2 * Q)
+end
+
+# ---- covariance ---------------------------------------------------------------------------------------------------------------
+function cov_gpu(d::Vector{<:Vector{<:Real}}; center = false, mean = Float64[])
+    X = reduce(hcat, d); K, n = size(X)
+    C = zeros(K, K); m = isempty(mean) ? zeros(K) : Float64.(mean)
+    check(ccall((:pl_cov, libplb200), Cint, (Ptr{Cdouble}, Int64, Int64, Int64, Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}),
+                Float64.(X), n, K, K, m, !isempty(mean), center, C), "pl_cov")
+    Symmetric(C), m
+end
+
+compute_eigen(d::Vector{T}) where {T<:Vector{<:Real}} = eigen(first(cov_gpu(d)))        # dimension_reduction.jl:11-14
+
+function fit!(ds::DataSet, pca::PCAState)                                              # pca_state.jl:20-40 (as written: descriptors only)
+    d = sum.(get_values.(get_local_descriptors.(ds)))
+    Q, m = cov_gpu(d; center = true, mean = pca.m == [] ? Float64[] : pca.m)            # mean persists (:34)
+    pca.m = m
+    λ, ϕ = eigen(Q); λ, ϕ = λ[end:-1:1], ϕ[:, end:-1:1]                                 # dimension_reduction.jl:16-17
+    Σ = 1.0 .- cumsum(λ) / sum(λ)
+    pca.λ, pca.W = λ, (pca.tol isa Int ? ϕ[:, 1:pca.tol] : ϕ[:, Σ .> pca.tol])
+    nothing
+end
+
+end # module
