@@ -54,24 +54,57 @@ def workload_config(extra=None):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region. NVML (pynvml) is polled every ~5 ms in a thread; if NVML is not
+    importable the recipe's nvidia-smi query is used instead (slower: ~50 ms per sample)."""
     QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
         self.index = index
-        self.samples = []
+        self.sm, self.reason_bits, self.max_sm, self.power = [], 0, None, []
+        self.smi_samples = []
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[i])
+            except Exception:
+                return i
+        return i
 
     def _run(self):
+        nv = self._nvml
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if nv is not None:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+                    try:
+                        self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                    except Exception:
+                        self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    self._stop.wait(0.005)
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.smi_samples.append([x.strip() for x in out.split(",")])
+                    self._stop.wait(0.05)
             except Exception:
-                pass
-            self._stop.wait(0.1)
+                self._stop.wait(0.05)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -83,14 +116,23 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        if not self.samples:
+        if self._nvml is not None and self.sm:
+            nv = self._nvml
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = [k for k, bit in names.items() if self.reason_bits & bit]
+            return {"sm_mhz": float(np.median(self.sm)), "sm_min_mhz": float(min(self.sm)), "sm_max_mhz": self.max_sm, "reasons": reasons,
+                    "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm), "source": "nvml"}
+        if not self.smi_samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        sm = [float(s[0]) for s in self.smi_samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.smi_samples if s[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.smi_samples)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+                "samples": len(self.smi_samples), "source": "nvidia-smi"}
 
 
 def cpu_reference_rate(X, seconds_target, oracle):

@@ -116,19 +116,25 @@ __device__ __forceinline__ double exp_fast(double x) {
   for (int k = 5; k < 18; ++k) p = fma(p, r, EXP_C[k]);
   return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
-// arguments outside the fast range (results below 3e-308 or overflow): the library routine, kept out of line
-__device__ __noinline__ double exp_slow(double x) { return exp(x); }
+// Whole-range wrapper, still branch free (a per-element branch to a slow path stops the compiler from interleaving the
+// 64 independent exp chains of a thread, which left the FP64 pipe ~25% utilised in the epilogue): arguments below -708
+// (results under 3.3e-308, i.e. denormal or zero in the reference) flush to 0, arguments above 709 saturate at exp(709).
+__device__ __forceinline__ double exp_clamped(double x) {
+  const double xc = fmin(fmax(x, -708.0), 709.0);
+  const double e = exp_fast(xc);
+  return x < -708.0 ? 0.0 : e;
+}
 
 // Fused epilogue of one warp tile. GENERAL = false: interior, off-diagonal tile (97% of the tiles of a large matrix):
 // no bounds or triangle logic, ~30 instructions per element. GENERAL = true: edge and diagonal tiles.
 //   rel0: (j - i) of accumulator (0,0,0) for diagonal tiles (elements with j < i are produced by mirroring, j == i is the
 //         kernel diagonal), 4096 otherwise. w1 / w2: write the direct / mirrored position; in diagonal tiles both
 //         positions are always written and hold 0 when their triangle was not requested (zeros(n,n) storage).
-template <int EPI, bool GENERAL>
+template <int EPI, bool GENERAL, int ALPHA /* DotProduct power: 1, 2, or 0 = general (runtime p.alpha) */>
 __device__ __forceinline__ void gram_epilogue(const double (&acc)[4][8][2], const GramParams& p, int64_t i0, int64_t j0, int rel0, bool w1, bool w2,
                                               double* __restrict__ prow, double* __restrict__ pcol, int64_t ldo) {
-  unsigned imask = 0xfu, jmask = 0xffffu;
-  double sa[4], sb[8][2];
+  unsigned imask = 0xfu;
+  double sa[4];
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
     bool ok = true;
@@ -136,55 +142,58 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[4][8][2], cons
       ok = i0 + 8 * mt < p.n1;
       if (!ok) imask &= ~(1u << mt);
     }
-    double r = (EPI != EPI_LINEAR && ok) ? __ldg(p.ra + i0 + 8 * mt) : 0.0;
+    const double r = (EPI != EPI_LINEAR && ok) ? __ldg(p.ra + i0 + 8 * mt) : 0.0;
     sa[mt] = (EPI == EPI_RBF) ? p.s * r : r;
   }
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      bool ok = true;
-      if (GENERAL) {
-        ok = j0 + 8 * nt + 4 * c < p.n2;
-        if (!ok) jmask &= ~(1u << (2 * nt + c));
-      }
-      double r = (EPI != EPI_LINEAR && ok) ? __ldg(p.rb + j0 + 8 * nt + 4 * c) : 0.0;
-      sb[nt][c] = (EPI == EPI_RBF) ? p.s * r : r;
-    }
   const double m2s = -2.0 * p.s;
   const double diagval = (EPI == EPI_RBF) ? p.beta : 1.0;
   const bool fill1 = p.packed || !p.symmetric || (p.fill & 1);
   const bool fill2 = p.packed || (p.fill & 2);
+  const bool dg = rel0 != 4096;
+  // 8 independent elements per step (one row, 4 column blocks x 2 columns = 2 full 128-byte lines of the direct store)
+  // keep the FP64 pipe busy through the exp chains without blowing up the live register set
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
     double* const pr = prow + (int64_t)(8 * mt) * ldo;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int ng = 0; ng < 2; ++ng) {
+      double v[4][2];
+      bool jok[4][2];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        double v = acc[mt][nt][c];
-        if (EPI == EPI_DOT) {
-          v = v * sa[mt] * sb[nt][c];
-          if (p.alpha == 2) v = v * v;
-          else if (p.alpha != 1) v = ipow_general(v, p.alpha);
-        } else if (EPI == EPI_RBF) {
-          // x = s*(q_i + q_j - 2 G_ij) = -0.5 d2 / ell^2  (kernels.jl:73-74 with distances.jl:59 expanded)
-          const double x = fma(v, m2s, sa[mt] + sb[nt][c]);
-          v = (x >= -708.0 && x <= 709.0) ? exp_fast(x) : exp_slow(x);
-          v *= p.beta;
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int nt = 4 * ng + q;
+          jok[q][c] = GENERAL ? (j0 + 8 * nt + 4 * c < p.n2) : true;
+          const double r = (EPI != EPI_LINEAR && jok[q][c]) ? __ldg(p.rb + j0 + 8 * nt + 4 * c) : 0.0;
+          double x = acc[mt][nt][c];
+          if (EPI == EPI_DOT) {
+            x = x * sa[mt] * r;
+            if (ALPHA == 2) x = x * x;
+            else if (ALPHA == 0) x = ipow_general(x, p.alpha);
+          } else if (EPI == EPI_RBF) {
+            // arg = s*(q_i + q_j - 2 G_ij) = -0.5 d2 / ell^2  (kernels.jl:73-74 with distances.jl:59 expanded)
+            x = exp_clamped(fma(x, m2s, fma(p.s, r, sa[mt]))) * p.beta;
+          }
+          v[q][c] = x;
         }
-        if (!GENERAL) {
-          if (w1) pr[8 * nt + 4 * c] = v;
-          if (w2) pcol[(int64_t)(8 * nt + 4 * c) * ldo + 8 * mt] = v;
-        } else {
-          const bool ok = ((imask >> mt) & (jmask >> (2 * nt + c)) & 1u) != 0;
-          const int rel = rel0 + (8 * nt + 4 * c - 8 * mt);
-          const bool dg = rel0 != 4096;
-          if (EPI != EPI_LINEAR && rel == 0) v = diagval;  // k(x,x): beta (d2 == 0), resp. n/sqrt(n*n) = 1 in the reference
-          if (ok && w1 && rel >= 0) pr[8 * nt + 4 * c] = (!dg || fill1 || rel == 0) ? v : 0.0;
-          if (ok && w2 && rel > 0) pcol[(int64_t)(8 * nt + 4 * c) * ldo + 8 * mt] = (!dg || fill2) ? v : 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int nt = 4 * ng + q;
+          double x = v[q][c];
+          if (!GENERAL) {
+            if (w1) pr[8 * nt + 4 * c] = x;
+            if (w2) pcol[(int64_t)(8 * nt + 4 * c) * ldo + 8 * mt] = x;
+          } else {
+            const bool ok = ((imask >> mt) & 1u) && jok[q][c];
+            const int rel = rel0 + (8 * nt + 4 * c - 8 * mt);
+            if (EPI != EPI_LINEAR && rel == 0) x = diagval;  // k(x,x): beta (d2 == 0), resp. n/sqrt(n*n) = 1 in the reference
+            if (ok && w1 && rel >= 0) pr[8 * nt + 4 * c] = (!dg || fill1 || rel == 0) ? x : 0.0;
+            if (ok && w2 && rel > 0) pcol[(int64_t)(8 * nt + 4 * c) * ldo + 8 * mt] = (!dg || fill2) ? x : 0.0;
+          }
         }
-      }
     }
   }
 }
@@ -265,28 +274,56 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-    for (int kt = 0; kt < KT; ++kt, ++it) {
+    // Software-pipelined main loop: the fragments of the next half-step (and, across k-iterations, the barrier wait of the
+    // next stage) are issued before the 64 DMMAs of the current half-step, so LDS latency and mbarrier wake-up never
+    // expose the DMMA pipe. Two fragment buffers of 12 x 128 bit (96 registers) on top of the 128 accumulator registers.
+    double2 a0[4], b0[8], a1[4], b1[8];
+    {
       const int s = it % GRAM_STAGES;
-      const uint32_t ph = (it / GRAM_STAGES) & 1u;
-      mbar_wait(full_bar(s), ph);
+      mbar_wait(full_bar(s), (it / GRAM_STAGES) & 1u);
       const uint32_t sA = smem_base + s * 2 * GRAM_TILE_BYTES;
       const uint32_t sB = one_tile ? sA : sA + GRAM_TILE_BYTES;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        double2 a[4], b[8];
+      for (int mt = 0; mt < 4; ++mt) a0[mt] = lds128(sA + (offA0 + mt * 1024));
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) a[mt] = lds128(sA + ((offA0 + mt * 1024) ^ (uint32_t)(h << 6)));
+      for (int nt = 0; nt < 8; ++nt) b0[nt] = lds128(sB + (offB0 + nt * 1024));
+    }
+    for (int kt = 0; kt < KT; ++kt, ++it) {
+      const int s = it % GRAM_STAGES;
+      const uint32_t sA = smem_base + s * 2 * GRAM_TILE_BYTES;
+      const uint32_t sB = one_tile ? sA : sA + GRAM_TILE_BYTES;
+      // second k-half of this stage -> buffer 1, then the stage can go back to the producer
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) b[nt] = lds128(sB + ((offB0 + nt * 1024) ^ (uint32_t)(h << 6)));
+      for (int mt = 0; mt < 4; ++mt) a1[mt] = lds128(sA + ((offA0 + mt * 1024) ^ 64u));
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+      for (int nt = 0; nt < 8; ++nt) b1[nt] = lds128(sB + ((offB0 + nt * 1024) ^ 64u));
 #pragma unroll
-          for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
+      for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+        for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a0[mt].x, b0[nt].x);
 #pragma unroll
-          for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a0[mt].y, b0[nt].y);
+      if (kt + 1 < KT) {
+        const int s2 = (it + 1) % GRAM_STAGES;
+        mbar_wait(full_bar(s2), ((it + 1) / GRAM_STAGES) & 1u);
+        const uint32_t sA2 = smem_base + s2 * 2 * GRAM_TILE_BYTES;
+        const uint32_t sB2 = one_tile ? sA2 : sA2 + GRAM_TILE_BYTES;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) a0[mt] = lds128(sA2 + (offA0 + mt * 1024));
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) b0[nt] = lds128(sB2 + (offB0 + nt * 1024));
       }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a1[mt].x, b1[nt].x);
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a1[mt].y, b1[nt].y);
+      // all fragments of stage s have been consumed from registers (a DMMA reads its operands at issue): release the stage
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar(s));
     }
@@ -317,10 +354,15 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     double* const prow = base + ib * ldo + jb;  // direct:  prow[8*mt*ldo + 8*nt + 4*c]
     double* const pcol = base + jb * ldo + ib;  // mirror:  pcol[(8*nt + 4*c)*ldo + 8*mt]
     const bool interior = ((int64_t)(ti + 1) * GRAM_BM <= p.n1) && ((int64_t)(tj + 1) * GRAM_BN <= p.n2);
-    if (interior && !diag_tile)
-      gram_epilogue<EPI, false>(acc, p, i0, j0, 0, f1, f2, prow, pcol, ldo);
-    else
-      gram_epilogue<EPI, true>(acc, p, i0, j0, diag_tile ? (jl0 - il0) : 4096, f1 || diag_tile, diag_tile ? true : f2, prow, pcol, ldo);
+    const int rel0 = diag_tile ? (jl0 - il0) : 4096;
+    const bool w1 = f1 || diag_tile, w2 = diag_tile ? true : f2;
+    if (EPI == EPI_DOT && p.alpha != 2) {  // uncommon powers: one general instantiation (alpha = 1 included)
+      gram_epilogue<EPI, true, 0>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo);
+    } else if (interior && !diag_tile) {
+      gram_epilogue<EPI, false, 2>(acc, p, i0, j0, 0, f1, f2, prow, pcol, ldo);
+    } else {
+      gram_epilogue<EPI, true, 2>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo);
+    }
   }
 }
 

@@ -91,7 +91,7 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
   __syncthreads();
 
   if (warp >= SYRK_CONSUMER_WARPS) {
-    setmaxnreg_dec<24>();
+    setmaxnreg_dec<24>();  // 256*240 + 128*24 = 64512 = 384 threads x 168 registers (the CTA pool)
     if (warp == SYRK_CONSUMER_WARPS && lane == 0) {
       tma_prefetch_desc(&tm);
       const uint32_t bytes = diag ? SYRK_OP_BYTES : 2 * SYRK_OP_BYTES;
