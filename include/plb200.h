@@ -146,6 +146,9 @@ int pl_normal_eq_finish_dev(const double* dS, const double* dvec, int64_t Kf, in
 int pl_colsum_dev(const double* dA, int64_t R, int64_t Kf, int64_t lda, double* dsum, void* stream);
 /* dOut[i] = dIn[i] / denom, i < count (covariance 1/n and mean 1/n after the all-reduce) */
 int pl_scale_div_dev(const double* dIn, double denom, int64_t count, double* dOut, void* stream);
+/* dOut[i][j] = dOut[j][i] = dIn[min(i,j)][max(i,j)] / denom for a K x K matrix: the covariance 1/n after the all-reduce, made
+ * EXACTLY symmetric again (a ring all-reduce sums S[i][j] and S[j][i] in different rank orders). */
+int pl_sym_scale_div_dev(const double* dIn, int64_t K, double denom, double* dOut, void* stream);
 
 #ifdef __cplusplus
 }

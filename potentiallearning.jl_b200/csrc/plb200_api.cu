@@ -652,6 +652,17 @@ int pl_scale_div_dev(const double* dIn, double denom, int64_t count, double* dOu
   return PL_OK;
 }
 
+int pl_sym_scale_div_dev(const double* dIn, int64_t K, double denom, double* dOut, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (K <= 0 || !dIn || !dOut) return set_err(PL_EINVAL, "bad arguments");
+  int blocks = (int)((K * K + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sym_scale_div_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dIn, K, denom, dOut);
+  LAUNCH_CHECK();
+  return PL_OK;
+}
+
 // ------------------------------------------------ host-pointer entry points ------------------------------------------------
 
 static int gram_host(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, const double* X2, int64_t n2, int64_t ldx2, int64_t d, int alpha,

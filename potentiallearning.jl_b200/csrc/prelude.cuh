@@ -149,4 +149,13 @@ __global__ void scale_div_kernel(const double* __restrict__ in, double denom, in
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i] / denom;
 }
 
+// out[i][j] = out[j][i] = in[min(i,j)][max(i,j)] / denom: exactly symmetric K x K result (covariance 1/n after the all-reduce)
+__global__ void sym_scale_div_kernel(const double* __restrict__ in, int64_t K, double denom, double* __restrict__ out) {
+  const int64_t total = K * K;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / K, j = e % K;
+    out[e] = (i <= j ? in[i * K + j] : in[j * K + i]) / denom;
+  }
+}
+
 }  // namespace plb

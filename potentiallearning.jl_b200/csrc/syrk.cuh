@@ -346,7 +346,10 @@ __global__ void normal_eq_finish_kernel(const double* __restrict__ S, const doub
       if (i == 0 && j == 0) v = vec[2 * Kf];
       else v = vec[Kf + (i == 0 ? j - 1 : i - 1)];
     } else {
-      v = S[(i - ic) * Kf + (j - ic)];
+      // read the j >= i triangle only: after a multi-rank all-reduce S[i][j] and S[j][i] may differ in the last bit
+      // (a ring reduces different chunks in different rank orders); the result must be EXACTLY symmetric
+      const int64_t a = i - ic, b = j - ic;
+      v = a <= b ? S[a * Kf + b] : S[b * Kf + a];
     }
     if (i == j) v += lambda;
     AtWA[e] = v;

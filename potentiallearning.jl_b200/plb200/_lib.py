@@ -46,6 +46,7 @@ PROTOTYPES = {
     "pl_normal_eq_finish_dev": (_int, [_vp, _vp, _i64, _int, _dbl, _vp, _vp, _vp]),
     "pl_colsum_dev": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "pl_scale_div_dev": (_int, [_vp, _dbl, _i64, _vp, _vp]),
+    "pl_sym_scale_div_dev": (_int, [_vp, _i64, _dbl, _vp, _vp]),
 }
 
 

@@ -68,3 +68,12 @@ class DeviceEngine:
         out = torch.empty_like(x)
         _lib.check(_lib.lib().pl_scale_div_dev(x.data_ptr(), float(denom), x.numel(), out.data_ptr(), _stream(x)), "pl_scale_div_dev")
         return out
+
+    def sym_scale_div(self, S, denom):
+        """out = sym(S) / denom from the j >= i triangle: exactly symmetric whatever order the all-reduce summed in."""
+        import torch
+
+        K = S.shape[0]
+        out = torch.empty_like(S)
+        _lib.check(_lib.lib().pl_sym_scale_div_dev(S.data_ptr(), K, float(denom), out.data_ptr(), _stream(S)), "pl_sym_scale_div_dev")
+        return out

@@ -64,4 +64,4 @@ def covariance_sharded(X_local, n_total: int, mean=None, center=True, group=None
             m = mean
     S, _ = engine.syrk_partial(X_local, None, 0, 1.0, 1.0, None, m, False)
     _all_reduce(S, group)
-    return engine.scale_div(S, float(n_total)), m
+    return engine.sym_scale_div(S, float(n_total)), m  # exactly symmetric even after a >2-rank ring all-reduce

@@ -125,7 +125,9 @@ if "c4" in cfgs:
     best, med = timed(lambda: covariance_sharded(X, n, engine=eng), reps=3, warm=1)
     out["c4_pca_cov"] = {"ms": best, "ms_median": med, "tflops": n * K * (K + 1) / best / 1e9, "rows_per_s": n / best * 1e3, "shape": [n, K],
                          "gb_this_rank": (r1 - r0) * K * 8 / 1e9}
-    m = eng.colsum(X)
+    C, _ = covariance_sharded(X, n, engine=eng)
+    out["c4_pca_cov"]["symmetric"] = bool(torch.equal(C, C.T))
+    del C
     best_c, _ = timed(lambda: eng.colsum(X), reps=3, warm=1)
     out["c4_pca_cov"]["colsum_ms"] = best_c
     out["c4_pca_cov"]["colsum_GBs"] = (r1 - r0) * K * 8 / best_c / 1e6

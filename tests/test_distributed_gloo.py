@@ -46,7 +46,7 @@ class CheckerEngine:
         else:
             M = Sn.copy()
             rhs = vec.numpy()[:K] if vec is not None else None
-        M = M + lam * np.eye(M.shape[0])
+        M = np.triu(M) + np.triu(M, 1).T + lam * np.eye(M.shape[0])  # j >= i triangle only, like normal_eq_finish_kernel
         return torch.from_numpy(M), (torch.from_numpy(rhs) if (want_rhs and rhs is not None) else None)
 
     def colsum(self, A):
@@ -54,6 +54,9 @@ class CheckerEngine:
 
     def scale_div(self, x, denom):
         return x / denom
+
+    def sym_scale_div(self, S, denom):
+        return (torch.triu(S) + torch.triu(S, 1).T) / denom
 
 
 def _free_port():
