@@ -373,15 +373,17 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
   return launch_gram(L, st);
 }
 
-void choose_splits(int64_t R, int ntiles, int* splits, int64_t* rows_per_split) {
-  // one CTA per (tile, split). Pick the number of waves (<= 6) whose last wave is fullest, keep >= 256 rows per CTA.
+void choose_splits(int64_t R, int nunits, int* splits, int64_t* rows_per_split) {
+  // one CTA per (work unit, row split), one CTA per SM at a time. Pick the number of waves (1..6) whose last wave is
+  // fullest; ties go to MORE waves (work units are not perfectly equal — e.g. blocks that also accumulate A'Wb — and the
+  // hardware block scheduler evens that out only when there is more than one wave). Keep >= 256 rows per CTA.
   int best = 1;
   double best_eff = 0.0;
   for (int w = 1; w <= 6; ++w) {
-    const int s = (g.num_sms * w) / ntiles;
+    const int s = (g.num_sms * w) / nunits;
     if (s < 1) continue;
-    const double eff = (double)(ntiles * s) / (double)(g.num_sms * w);
-    if (eff > best_eff + 0.02 || (best_eff == 0.0)) {
+    const double eff = (double)(nunits * s) / (double)(g.num_sms * w);
+    if (eff >= best_eff - 1e-9) {
       best_eff = eff;
       best = s;
     }
@@ -421,7 +423,7 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
   p.mean = dmean;
   p.want_vec = dvec ? 1 : 0;
   p.T = (int)((Kf + SYRK_BT - 1) / SYRK_BT);
-  p.ntiles = p.T * (p.T + 1) / 2;
+  p.ntiles = syrk_num_units(p.T);
   choose_splits(R, p.ntiles, &p.splits, &p.rows_per_split);
   void *wst, *wsv = nullptr;
   PL_TRY(ws_get(WS_SYRK_TILES, (size_t)p.splits * p.ntiles * SYRK_TILE_ELEMS * 8, &wst));

@@ -7,9 +7,13 @@
 //
 // Geometry: the contraction runs over ROWS of one row-major R x Kf matrix, so both MMA operands are "MN-major"
 // (the output index is contiguous in memory) — the transpose of the Gram kernel's geometry:
-//   * CTA (tile, split): 128 x 128 output tile (upper-triangle tile pairs only) x a contiguous row range; partial
-//     tiles go to a workspace in fragment order (perfectly coalesced) and a deterministic second-stage kernel sums
-//     the splits in fixed order, mirrors, and applies scale / ridge / intercept layout;
+//   * CTA (unit, split): a work unit is 8 warp blocks of 32 (i) x 64 (j) output elements x a contiguous row range.
+//     Off-diagonal 128 x 128 tiles are one unit each (4 x 2 warp blocks). A diagonal tile only needs 6 of its 8 warp
+//     blocks (the two below the diagonal are pure mirror images), so the diagonal blocks of ALL tiles are packed 8 per
+//     unit (a unit then spans at most two column blocks, the same shared-memory footprint as an off-diagonal tile):
+//     T(T-1)/2 + ceil(6T/8) units instead of T(T+1)/2 tiles, e.g. 9 instead of 10 at K = 500, and every warp of every
+//     unit does useful work. Partial blocks go to a workspace in fragment order (perfectly coalesced) and a
+//     deterministic second-stage kernel sums the splits in fixed order, mirrors, and applies scale / ridge / intercept;
 //   * stage = 16 rows x 128 columns per operand, brought in as 8 TMA boxes of 16 rows x 16 columns (128 bytes wide,
 //     128B swizzle); diagonal tiles load one operand only;
 //   * fragment loads are 128-bit: lane (g,t) reads columns (2g, 2g+1) of row 2t+par(+8h) of a box — two m-tiles of
@@ -40,24 +44,57 @@ struct SyrkParams {
   const double* b;        // right-hand side or NULL
   const double* mean;     // column means (centred mode) or NULL
   int want_vec;           // accumulate v / c on diagonal tiles
-  int T;                  // tile rows = ceil(Kf / 128)
-  int ntiles;             // T (T+1) / 2
+  int T;                  // column blocks = ceil(Kf / 128)
+  int ntiles;             // work units: T (T-1) / 2 off-diagonal tiles + ceil(6 T / 8) packs of diagonal warp blocks
   int splits;             // row splits
   int64_t rows_per_split; // multiple of SYRK_BK
   double* ws_tiles;       // [split][tile][64 acc][256 threads]
   double* ws_vec;         // [split][2][T*128]   (v then c), only if want_vec
 };
 
-// linear upper-triangle tile index -> (ti, tj), tj >= ti (row-major over the triangle)
-__host__ __device__ __forceinline__ void syrk_tile_coords(int T, int idx, int& ti, int& tj) {
-  int row = 0;
-  int rem = idx;
-  while (rem >= T - row) {
-    rem -= T - row;
-    ++row;
+// The 6 warp blocks (wm = 32-column slab of i, wn = 64-column slab of j) of a diagonal tile that touch j >= i.
+// Blocks 0, 2, 4, 5 — one per wm — also accumulate the moment vectors of their 32 i-columns.
+__host__ __device__ __forceinline__ int syrk_num_units(int T) { return T * (T - 1) / 2 + (6 * T + 7) / 8; }
+
+struct SyrkWarpBlock {
+  int cb_a, wm;   // i columns: 128 cb_a + 32 wm + [0, 32)
+  int cb_b, wn;   // j columns: 128 cb_b + 64 wn + [0, 64)
+  int src_a, src_b;  // which of the unit's two operand buffers holds that column block
+  bool valid, vec;
+};
+
+// work unit u, warp w -> its block. cb0 / cb1: the (at most two) column blocks the unit loads into buffers 0 / 1.
+__host__ __device__ __forceinline__ SyrkWarpBlock syrk_warp_block(int T, int u, int w, int& cb0, int& cb1) {
+  SyrkWarpBlock B;
+  const int noff = T * (T - 1) / 2;
+  if (u < noff) {  // off-diagonal tile (ti < tj), row-major over the strict upper triangle
+    int ti = 0, rem = u;
+    while (rem >= T - 1 - ti) {
+      rem -= T - 1 - ti;
+      ++ti;
+    }
+    cb0 = ti;
+    cb1 = ti + 1 + rem;
+    B.cb_a = cb0; B.wm = w >> 1; B.src_a = 0;
+    B.cb_b = cb1; B.wn = w & 1; B.src_b = 1;
+    B.valid = true;
+    B.vec = false;
+    return B;
   }
-  ti = row;
-  tj = row + rem;
+  const int q = u - noff;  // pack q holds diagonal warp blocks 8q .. 8q+7 of the list (tile t, k): index 6t + k
+  const int first = 8 * q, last = (8 * q + 7 < 6 * T - 1) ? 8 * q + 7 : 6 * T - 1;
+  cb0 = first / 6;
+  cb1 = last / 6;
+  const int idx = first + w;
+  B.valid = idx < 6 * T;
+  const int t = B.valid ? idx / 6 : cb0, k = B.valid ? idx % 6 : 0;
+  // k: 0 -> (0,0)  1 -> (0,1)  2 -> (1,0)  3 -> (1,1)  4 -> (2,1)  5 -> (3,1)
+  B.wm = k < 4 ? (k >> 1) : (k - 2);
+  B.wn = k < 4 ? (k & 1) : 1;
+  B.cb_a = B.cb_b = t;
+  B.src_a = B.src_b = (t == cb0) ? 0 : 1;
+  B.vec = B.valid && (k == 0 || k == 2 || k == 4 || k == 5);
+  return B;
 }
 
 template <bool CENTER, bool VEC>
@@ -71,11 +108,11 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
+  const int tile = blockIdx.x;  // work unit
   const int split = blockIdx.y;
-  int ti, tj;
-  syrk_tile_coords(p.T, tile, ti, tj);
-  const bool diag = (ti == tj);
+  int cb0, cb1;
+  const SyrkWarpBlock WB = syrk_warp_block(p.T, tile, warp < SYRK_CONSUMER_WARPS ? warp : 0, cb0, cb1);
+  const bool one_buf = (cb0 == cb1);
   const int64_t r_begin = (int64_t)split * p.rows_per_split;
   int64_t r_end = r_begin + p.rows_per_split;
   if (r_end > p.R) r_end = p.R;
@@ -94,7 +131,7 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
     setmaxnreg_dec<24>();  // 256*240 + 128*24 = 64512 = 384 threads x 168 registers (the CTA pool)
     if (warp == SYRK_CONSUMER_WARPS && lane == 0) {
       tma_prefetch_desc(&tm);
-      const uint32_t bytes = diag ? SYRK_OP_BYTES : 2 * SYRK_OP_BYTES;
+      const uint32_t bytes = one_buf ? SYRK_OP_BYTES : 2 * SYRK_OP_BYTES;
       for (int kt = 0; kt < KT; ++kt) {
         const int s = kt % SYRK_STAGES;
         const uint32_t ph = (kt / SYRK_STAGES) & 1u;
@@ -104,11 +141,11 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
         const int r0 = (int)(r_begin + (int64_t)kt * SYRK_BK);
         // NOTE: the last stage of a split may read rows of the next split (r >= r_end); they are zero-weighted below.
 #pragma unroll
-        for (int bx = 0; bx < 8; ++bx) tma_load_2d(dst + bx * SYRK_BOX_BYTES, &tm, full_bar(s), ti * SYRK_BT + 16 * bx, r0);
-        if (!diag) {
+        for (int bx = 0; bx < 8; ++bx) tma_load_2d(dst + bx * SYRK_BOX_BYTES, &tm, full_bar(s), cb0 * SYRK_BT + 16 * bx, r0);
+        if (!one_buf) {
 #pragma unroll
           for (int bx = 0; bx < 8; ++bx)
-            tma_load_2d(dst + SYRK_OP_BYTES + bx * SYRK_BOX_BYTES, &tm, full_bar(s), tj * SYRK_BT + 16 * bx, r0);
+            tma_load_2d(dst + SYRK_OP_BYTES + bx * SYRK_BOX_BYTES, &tm, full_bar(s), cb1 * SYRK_BT + 16 * bx, r0);
         }
       }
     }
@@ -117,8 +154,8 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
 
   // ------------------------------ consumers ------------------------------
   setmaxnreg_inc<240>();
-  const int wm = warp >> 1;  // 32-column slab of the i (row of S) index
-  const int wn = warp & 1;   // 64-column slab of the j index
+  const int wm = WB.wm;  // 32-column slab of the i (row of S) index inside column block WB.cb_a
+  const int wn = WB.wn;  // 64-column slab of the j index inside column block WB.cb_b
   const int g = lane >> 2;
   const int t = lane & 3;
 
@@ -128,10 +165,10 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-  // moment vectors (diagonal tiles, wn == 0 warps): columns i = 128 ti + 32 wm + 16 bx + 2g + e
+  // moment vectors (one diagonal warp block per 32-column slab): columns i = 128 cb_a + 32 wm + 16 bx + 2g + e
   double vb[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
   double vc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-  const bool do_vec = VEC && diag && (wn == 0);
+  const bool do_vec = VEC && WB.vec;
 
   // column means of this thread's fragment columns
   double mi[2][2], mj[4][2];
@@ -140,14 +177,14 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
     for (int bx = 0; bx < 2; ++bx)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int64_t col = (int64_t)ti * SYRK_BT + 32 * wm + 16 * bx + 2 * g + e;
+        const int64_t col = (int64_t)WB.cb_a * SYRK_BT + 32 * wm + 16 * bx + 2 * g + e;
         mi[bx][e] = col < p.Kf ? __ldg(p.mean + col) : 0.0;
       }
 #pragma unroll
     for (int bx = 0; bx < 4; ++bx)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int64_t col = (int64_t)tj * SYRK_BT + 64 * wn + 16 * bx + 2 * g + e;
+        const int64_t col = (int64_t)WB.cb_b * SYRK_BT + 64 * wn + 16 * bx + 2 * g + e;
         mj[bx][e] = col < p.Kf ? __ldg(p.mean + col) : 0.0;
       }
   }
@@ -177,8 +214,8 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
       }
 
     mbar_wait(full_bar(s), ph);
-    const uint32_t sA = smem_base + s * 2 * SYRK_OP_BYTES + (2 * wm) * SYRK_BOX_BYTES;
-    const uint32_t sB = smem_base + s * 2 * SYRK_OP_BYTES + (diag ? 0 : SYRK_OP_BYTES) + (4 * wn) * SYRK_BOX_BYTES;
+    const uint32_t sA = smem_base + s * 2 * SYRK_OP_BYTES + WB.src_a * SYRK_OP_BYTES + (2 * wm) * SYRK_BOX_BYTES;
+    const uint32_t sB = smem_base + s * 2 * SYRK_OP_BYTES + WB.src_b * SYRK_OP_BYTES + (4 * wn) * SYRK_BOX_BYTES;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -258,7 +295,7 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
           y += __shfl_xor_sync(0xffffffffu, y, 1);
           y += __shfl_xor_sync(0xffffffffu, y, 2);
           if (t == 0) {
-            const int col = ti * SYRK_BT + 32 * wm + 16 * bx + 2 * g + e;
+            const int col = WB.cb_a * SYRK_BT + 32 * wm + 16 * bx + 2 * g + e;
             double* wv2 = p.ws_vec + (int64_t)split * 2 * p.T * SYRK_BT;
             wv2[col] = x;
             wv2[p.T * SYRK_BT + col] = y;
@@ -268,34 +305,35 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
   }
 }
 
-// Second stage: S[i][j] = S[j][i] = sum over splits (fixed order) of the partial tiles; v, c likewise.
-// Element (acc index a, consumer thread tid) of tile (ti, tj):
-//   warp = tid>>5, wm = warp>>1, wn = warp&1, g = (tid&31)>>2, t = tid&3, mt = a>>4, nt = (a>>1)&7, c = a&1
-//   i = 128 ti + 32 wm + 16 (mt>>1) + 2 g + (mt&1)
-//   j = 128 tj + 64 wn + 16 (nt>>1) + 4 t + 2 c + (nt&1)
+// Second stage: S[i][j] = S[j][i] = sum over splits (fixed order) of the partial blocks; v, c likewise.
+// Element (acc index a, consumer thread tid) of work unit u:
+//   warp = tid>>5 -> block (cb_a, wm, cb_b, wn) = syrk_warp_block(T, u, warp); g = (tid&31)>>2, t = tid&3
+//   mt = a>>4, nt = (a>>1)&7, c = a&1
+//   i = 128 cb_a + 32 wm + 16 (mt>>1) + 2 g + (mt&1)
+//   j = 128 cb_b + 64 wn + 16 (nt>>1) + 4 t + 2 c + (nt&1)
 __global__ void syrk_reduce_kernel(const double* __restrict__ ws_tiles, const double* __restrict__ ws_vec, int T, int ntiles,
                                    int splits, int64_t Kf, double* __restrict__ S, double* __restrict__ vec, int want_vec) {
-  const int tile = blockIdx.x;
-  int ti, tj;
-  syrk_tile_coords(T, tile, ti, tj);
+  const int unit = blockIdx.x;
   for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < SYRK_TILE_ELEMS; e += gridDim.y * blockDim.x) {
     const int a = e >> 8;
     const int tid = e & 255;
-    const int warp = tid >> 5, wm = warp >> 1, wn = warp & 1, g = (tid & 31) >> 2, t = tid & 3;
+    const int warp = tid >> 5, g = (tid & 31) >> 2, t = tid & 3;
+    int cb0, cb1;
+    const SyrkWarpBlock WB = syrk_warp_block(T, unit, warp, cb0, cb1);
+    if (!WB.valid) continue;
     const int mt = a >> 4, nt = (a >> 1) & 7, c = a & 1;
-    const int64_t i = (int64_t)ti * SYRK_BT + 32 * wm + 16 * (mt >> 1) + 2 * g + (mt & 1);
-    const int64_t j = (int64_t)tj * SYRK_BT + 64 * wn + 16 * (nt >> 1) + 4 * t + 2 * c + (nt & 1);
+    const int64_t i = (int64_t)WB.cb_a * SYRK_BT + 32 * WB.wm + 16 * (mt >> 1) + 2 * g + (mt & 1);
+    const int64_t j = (int64_t)WB.cb_b * SYRK_BT + 64 * WB.wn + 16 * (nt >> 1) + 4 * t + 2 * c + (nt & 1);
     if (i >= Kf || j >= Kf) continue;
-    if (ti == tj && j < i) continue;  // diagonal tiles: keep j >= i, mirror (weights are applied to one operand only)
+    if (j < i) continue;  // diagonal blocks: keep j >= i, mirror (weights are applied to one operand only)
     double sum = 0.0;
-    for (int sp = 0; sp < splits; ++sp) sum += ws_tiles[((int64_t)sp * ntiles + tile) * SYRK_TILE_ELEMS + e];
+    for (int sp = 0; sp < splits; ++sp) sum += ws_tiles[((int64_t)sp * ntiles + unit) * SYRK_TILE_ELEMS + e];
     S[i * Kf + j] = sum;
     S[j * Kf + i] = sum;
   }
-  if (want_vec && ti == tj && blockIdx.y == 0) {
-    for (int cidx = threadIdx.x; cidx < SYRK_BT; cidx += blockDim.x) {
-      const int64_t col = (int64_t)ti * SYRK_BT + cidx;
-      if (col >= Kf) continue;
+  if (want_vec && blockIdx.y == 0) {
+    // every column block's moment vectors: handled by the first T units' blocks (any mapping works: one writer per column)
+    for (int64_t col = (int64_t)unit * blockDim.x + threadIdx.x; col < Kf; col += (int64_t)gridDim.x * blockDim.x) {
       double sv = 0.0, sc = 0.0;
       for (int sp = 0; sp < splits; ++sp) {
         const double* wv2 = ws_vec + (int64_t)sp * 2 * T * SYRK_BT;

@@ -134,6 +134,7 @@ if "c4" in cfgs:
     del X
 
 if "c5" in cfgs:
+    torch.cuda.empty_cache()
     N, d = args.c5_n, 500
     mu = 2.0 * torch.randn(d, device=dev, dtype=torch.float64, generator=gen_shared)
     X = mu + torch.randn((N, d), device=dev, dtype=torch.float64, generator=gen_shared) / np.sqrt(96.0)

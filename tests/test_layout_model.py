@@ -171,3 +171,49 @@ def test_folded_triangle_enumeration_covers_every_tile_once():
         tiles = [s for s in seen if s is not None]
         assert len(tiles) == len(set(tiles)) == T * (T + 1) // 2
         assert all(0 <= ti <= tj < T for ti, tj in tiles)
+
+
+def _syrk_warp_block(T, u, w):
+    """Python restatement of syrk_warp_block (csrc/syrk.cuh): work unit u, warp w -> (cb_a, wm, cb_b, wn, valid, vec, cb0, cb1)."""
+    noff = T * (T - 1) // 2
+    if u < noff:
+        ti, rem = 0, u
+        while rem >= T - 1 - ti:
+            rem -= T - 1 - ti
+            ti += 1
+        cb0, cb1 = ti, ti + 1 + rem
+        return cb0, w >> 1, cb1, w & 1, True, False, cb0, cb1
+    q = u - noff
+    first, last = 8 * q, min(8 * q + 7, 6 * T - 1)
+    cb0, cb1 = first // 6, last // 6
+    idx = first + w
+    valid = idx < 6 * T
+    t, k = (idx // 6, idx % 6) if valid else (cb0, 0)
+    wm = (k >> 1) if k < 4 else (k - 2)
+    wn = (k & 1) if k < 4 else 1
+    return t, wm, t, wn, valid, valid and k in (0, 2, 4, 5), cb0, cb1
+
+
+def test_syrk_work_units_cover_upper_triangle_once():
+    """Off-diagonal tiles + packed diagonal warp blocks: every (i, j), j >= i, of the K x K result is produced exactly once,
+    every 32-column slab has exactly one moment-vector writer, and a unit never needs more than two column blocks."""
+    for T in (1, 2, 3, 4, 8, 9):
+        K = 128 * T
+        units = T * (T - 1) // 2 + (6 * T + 7) // 8
+        cover = np.zeros((K, K), dtype=np.int32)
+        vec_writers = np.zeros(K, dtype=np.int32)
+        for u in range(units):
+            for w in range(8):
+                cb_a, wm, cb_b, wn, valid, vec, cb0, cb1 = _syrk_warp_block(T, u, w)
+                assert cb_a in (cb0, cb1) and cb_b in (cb0, cb1) and cb1 - cb0 >= 0
+                if not valid:
+                    continue
+                i0, j0 = 128 * cb_a + 32 * wm, 128 * cb_b + 64 * wn
+                ii, jj = np.meshgrid(np.arange(i0, i0 + 32), np.arange(j0, j0 + 64), indexing="ij")
+                keep = jj >= ii
+                cover[ii[keep], jj[keep]] += 1
+                if vec:
+                    vec_writers[i0:i0 + 32] += 1
+        assert np.array_equal(np.triu(cover), np.triu(np.ones((K, K), dtype=np.int32))), T
+        assert np.all(vec_writers == 1)
+    assert 4 * 3 // 2 + (6 * 4 + 7) // 8 == 9  # K = 500: 9 units instead of 10 tiles
