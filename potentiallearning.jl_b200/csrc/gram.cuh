@@ -53,6 +53,9 @@ struct GramParams {
   int T1, T2;           // tile rows / tile cols
   int64_t ntiles_total; // linear tile slots (symmetric: folded enumeration incl. a few invalid slots)
   int part, nparts;     // tile sharding across GPUs: slot l is ours iff l % nparts == part
+  int tcol_begin;       // >= 0: "column range" enumeration (symmetric only): tiles (ti <= tj) of tile columns
+  int tcol_end;         //       [tcol_begin, tcol_end), column by column — lets the host stream finished rows of the
+                        //       Symmetric(:U) storage to the host while later columns are still being computed
 };
 
 // Folded enumeration of the upper triangle of a T x T tile grid: tile row p is paired with row T-1-p so that every
@@ -76,6 +79,19 @@ __host__ __device__ __forceinline__ bool gram_slot_to_tile(const int T1, const i
   ti = p2;
   tj = p2 + (q - (T - p));
   return true;
+}
+// column-range enumeration: slot l (0-based inside the range) -> (ti, tj), tj in [c0, c1), ti <= tj, column-major over the
+// upper triangle: global index L = c0(c0+1)/2 + l, tj = floor((sqrt(8L+1)-1)/2), ti = L - tj(tj+1)/2
+__host__ __device__ __forceinline__ void gram_colrange_slot_to_tile(int c0, int64_t l, int& ti, int& tj) {
+  const int64_t L = (int64_t)c0 * (c0 + 1) / 2 + l;
+  int64_t t = (int64_t)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
+  while (t * (t + 1) / 2 > L) --t;
+  while ((t + 1) * (t + 2) / 2 <= L) ++t;
+  tj = (int)t;
+  ti = (int)(L - t * (t + 1) / 2);
+}
+__host__ __device__ __forceinline__ int64_t gram_colrange_num_slots(int c0, int c1) {
+  return (int64_t)c1 * (c1 + 1) / 2 - (int64_t)c0 * (c0 + 1) / 2;
 }
 __host__ __device__ __forceinline__ int64_t gram_num_slots(int T1, int T2, int symmetric) {
   if (!symmetric) return (int64_t)T1 * T2;
@@ -233,7 +249,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t it = 0;
       for (int64_t l = slot0; l < p.ntiles_total; l += slot_stride) {
         int ti, tj;
-        if (!gram_slot_to_tile(p.T1, p.T2, p.symmetric, l, ti, tj)) continue;
+        if (p.tcol_begin >= 0) gram_colrange_slot_to_tile(p.tcol_begin, l, ti, tj);
+        else if (!gram_slot_to_tile(p.T1, p.T2, p.symmetric, l, ti, tj)) continue;
         const bool one_tile = p.same_operand && (ti == tj);
         const uint32_t bytes = one_tile ? GRAM_TILE_BYTES : 2 * GRAM_TILE_BYTES;
         for (int kt = 0; kt < KT; ++kt, ++it) {
@@ -265,7 +282,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint32_t it = 0;
   for (int64_t l = slot0; l < p.ntiles_total; l += slot_stride) {
     int ti, tj;
-    if (!gram_slot_to_tile(p.T1, p.T2, p.symmetric, l, ti, tj)) continue;
+    if (p.tcol_begin >= 0) gram_colrange_slot_to_tile(p.tcol_begin, l, ti, tj);
+    else if (!gram_slot_to_tile(p.T1, p.T2, p.symmetric, l, ti, tj)) continue;
     const bool one_tile = p.same_operand && (ti == tj);
 
     double acc[4][8][2];

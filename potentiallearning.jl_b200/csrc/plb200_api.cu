@@ -82,6 +82,8 @@ struct Ctx {
   int device = -1;
   int num_sms = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // D2H of finished row blocks overlaps the remaining Gram launches
+  cudaEvent_t chunk_ev[16] = {};
   cudaEvent_t ev[6] = {};
   PFN_cuTensorMapEncodeTiled encode = nullptr;
   void* ws[WS_NSLOTS] = {};
@@ -195,6 +197,7 @@ struct GramLaunch {
   int64_t ldo;
   int symmetric, same_operand, fill, packed, part, nparts, alpha;
   double s, beta;
+  int tcol_begin = -1, tcol_end = -1;  // column-range enumeration (host streaming path)
 };
 
 int launch_gram(const GramLaunch& L, cudaStream_t st) {
@@ -219,7 +222,9 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   p.beta = L.beta;
   p.T1 = (int)((L.nA + GRAM_BM - 1) / GRAM_BM);
   p.T2 = (int)((L.nB + GRAM_BN - 1) / GRAM_BN);
-  p.ntiles_total = gram_num_slots(p.T1, p.T2, p.symmetric);
+  p.tcol_begin = L.tcol_begin;
+  p.tcol_end = L.tcol_end;
+  p.ntiles_total = L.tcol_begin >= 0 ? gram_colrange_num_slots(L.tcol_begin, L.tcol_end) : gram_num_slots(p.T1, p.T2, p.symmetric);
   p.part = L.part;
   p.nparts = L.nparts;
   const int64_t mine = (p.ntiles_total - L.part + L.nparts - 1) / L.nparts;
@@ -247,9 +252,11 @@ int launch_prep(const double* X, int64_t n, int64_t d, int64_t ldx, const double
   return PL_OK;
 }
 
+// prepared != NULL: run the preludes, fill *prepared with the main launch and return WITHOUT launching it (the host
+// streaming path launches it several times over tile-column ranges).
 int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, const double* dX2, int64_t n2, int64_t ldx2, int64_t d, int alpha,
                   int cinv_kind, const double* dcinv, double ell, double beta, double* dOut, int64_t ldo, int fill, int part, int nparts, int packed,
-                  cudaStream_t st) {
+                  cudaStream_t st, GramLaunch* prepared = nullptr) {
   PL_TRY(need_ready());
   const bool sym = (dX2 == nullptr);
   if (n1 < 0 || d <= 0 || (!sym && n2 < 0)) return set_err(PL_EINVAL, "bad shape n1=%lld n2=%lld d=%lld", (long long)n1, (long long)n2, (long long)d);
@@ -286,6 +293,7 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
     L.A = X1; L.ldA = l1;
     L.B = sym ? X1 : X2; L.ldB = sym ? l1 : l2;
     L.same_operand = sym;
+    if (prepared) { *prepared = L; return PL_OK; }
     return launch_gram(L, st);
   }
   if (kernel_id == PL_KERNEL_DOT) {
@@ -302,6 +310,7 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
     L.ra = (double*)s1;
     L.rb = sym ? (double*)s1 : (double*)s2;
     L.same_operand = sym;
+    if (prepared) { *prepared = L; return PL_OK; }
     return launch_gram(L, st);
   }
   if (kernel_id != PL_KERNEL_RBF) return set_err(PL_EINVAL, "unknown kernel id %d", kernel_id);
@@ -332,6 +341,7 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
     L.A = (double*)xc1; L.ldA = ldc;
     L.B = sym ? (double*)xc1 : (double*)xc2; L.ldB = ldc;
     L.same_operand = sym;
+    if (prepared) { *prepared = L; return PL_OK; }
     return launch_gram(L, st);
   }
   PL_TRY(ws_get(WS_Y1, (size_t)n1 * ldc * 8, &y1));
@@ -370,6 +380,7 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
   L.A = (double*)y1; L.ldA = ldc;
   L.B = sym ? (double*)xc1 : (double*)xc2; L.ldB = ldc;
   L.same_operand = 0;
+  if (prepared) { *prepared = L; return PL_OK; }
   return launch_gram(L, st);
 }
 
@@ -471,7 +482,12 @@ int h2d_matrix(const double* h, int64_t rows, int64_t cols, int64_t ldh, int slo
   const int64_t ldp = (cols + 1) & ~(int64_t)1;
   void* buf;
   PL_TRY(ws_get(slot, (size_t)(rows > 0 ? rows : 1) * ldp * 8, &buf));
-  if (rows > 0) CUDA_TRY(cudaMemcpy2DAsync(buf, (size_t)ldp * 8, h, (size_t)ldh * 8, (size_t)cols * 8, (size_t)rows, cudaMemcpyHostToDevice, g.stream));
+  if (rows > 0) {
+    if (ldp == ldh && ldh == cols)  // dense on both sides: one linear copy (faster than the pitched path)
+      CUDA_TRY(cudaMemcpyAsync(buf, h, (size_t)rows * cols * 8, cudaMemcpyHostToDevice, g.stream));
+    else
+      CUDA_TRY(cudaMemcpy2DAsync(buf, (size_t)ldp * 8, h, (size_t)ldh * 8, (size_t)cols * 8, (size_t)rows, cudaMemcpyHostToDevice, g.stream));
+  }
   *dptr = (double*)buf;
   *ldd = ldp;
   return PL_OK;
@@ -523,7 +539,9 @@ int pl_init(int device) {
   if (!fn || qres != cudaDriverEntryPointSuccess) return set_err(PL_ECUDA, "cuTensorMapEncodeTiled entry point not found");
   g.encode = (PFN_cuTensorMapEncodeTiled)fn;
   CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
   for (auto& ev : g.ev) CUDA_TRY(cudaEventCreate(&ev));
+  for (auto& ev : g.chunk_ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
@@ -548,8 +566,14 @@ void pl_finalize(void) {
     if (ev) cudaEventDestroy(ev);
     ev = nullptr;
   }
+  for (auto& ev : g.chunk_ev) {
+    if (ev) cudaEventDestroy(ev);
+    ev = nullptr;
+  }
   if (g.stream) cudaStreamDestroy(g.stream);
+  if (g.copy_stream) cudaStreamDestroy(g.copy_stream);
   g.stream = nullptr;
+  g.copy_stream = nullptr;
   g.ready = false;
 }
 
@@ -694,6 +718,39 @@ static int gram_host(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, 
   PL_TRY(ws_get(WS_H_OUT1, (size_t)n1 * ldo * 8, &outbuf));
   dK = (double*)outbuf;
   CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  const int T = (int)((n1 + GRAM_BM - 1) / GRAM_BM);
+  if (sym && fill == PL_FILL_RM_LOWER && T >= 16) {
+    // Symmetric(K) uplo = :U storage (kernels.jl:217-222): row block jb of the row-major view is complete as soon as tile
+    // column jb is. Launch the Gram kernel over NCHUNK tile-column ranges of equal work and stream each finished range
+    // to the host on a second stream while the next ranges compute: the PCIe copy (the e2e bottleneck) starts at once.
+    constexpr int NCHUNK = 8;
+    GramLaunch L;
+    PL_TRY(gram_dev_impl(kernel_id, d1, n1, l1, nullptr, n2, 0, d, alpha, cinv_kind, dc, ell, beta, dK, ldo, fill, 0, 1, 0, g.stream, &L));
+    int bounds[NCHUNK + 1];
+    for (int c = 0; c <= NCHUNK; ++c) bounds[c] = (int)(T * sqrt((double)c / NCHUNK) + 0.5);
+    bounds[0] = 0;
+    bounds[NCHUNK] = T;
+    for (int c = 0; c < NCHUNK; ++c) {
+      if (bounds[c + 1] > bounds[c]) {
+        L.tcol_begin = bounds[c];
+        L.tcol_end = bounds[c + 1];
+        PL_TRY(launch_gram(L, g.stream));
+      }
+      CUDA_TRY(cudaEventRecord(g.chunk_ev[c], g.stream));
+    }
+    CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+    for (int c = 0; c < NCHUNK; ++c) {
+      CUDA_TRY(cudaStreamWaitEvent(g.copy_stream, g.chunk_ev[c], 0));
+      for (int tb = bounds[c]; tb < bounds[c + 1]; ++tb) {
+        const int64_t r0 = (int64_t)tb * GRAM_BM;
+        const int64_t r1 = r0 + GRAM_BM < n1 ? r0 + GRAM_BM : n1;
+        CUDA_TRY(cudaMemcpy2DAsync(K + r0 * ldk, (size_t)ldk * 8, dK + r0 * ldo, (size_t)ldo * 8, (size_t)r1 * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, g.copy_stream));
+      }
+    }
+    CUDA_TRY(cudaEventRecord(g.ev[3], g.copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(g.copy_stream));
+    return finish_timing();
+  }
   PL_TRY(gram_dev_impl(kernel_id, d1, n1, l1, d2, n2, l2, d, alpha, cinv_kind, dc, ell, beta, dK, ldo, fill, 0, 1, 0, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
   if (!sym || fill == PL_FILL_FULL) {

@@ -104,6 +104,21 @@ def test_symmetric_storage_matches_reference(pl, orc):
         assert np.array_equal(np.triu(full), np.triu(S.data))
 
 
+def test_symmetric_storage_streamed_path(pl, orc):
+    """n >= 2048 with the :U storage contract takes the streamed host path (tile-column ranges + overlapped D2H)."""
+    rng = np.random.default_rng(18)
+    n, d = 2100, 20
+    X = rng.standard_normal((n, d)) * 0.3 + 1.0
+    for k, ko in ((pl.RBF(pl.Euclidean(d)), orc.RBF(orc.Euclidean(d))), (pl.DotProduct(), orc.DotProduct())):
+        S = pl.KernelMatrix(X, k, fill="U")
+        assert np.array_equal(np.tril(S.data, -1), np.zeros((n, n)))
+        ref = orc.kernel_matrix(X, ko)
+        iu = np.triu_indices(n)
+        assert relerr(S.data[iu], ref[iu]) < RTOL
+        full = np.asarray(pl.KernelMatrix(X, k))
+        assert np.array_equal(np.triu(full), S.data), "streamed and one-shot paths agree bit for bit"
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Gram kernels: shapes, ragged edges, parameters
 # ---------------------------------------------------------------------------------------------------------------
@@ -457,3 +472,68 @@ def test_config3_slice_properties(pl, orc):
     Mo, vo = orc.normal_equations(Ai, bh, q, 0.01)
     assert normerr(M.cpu().numpy(), Mo) < RTOL and normerr(v.cpu().numpy(), vo) < RTOL
     assert bool(torch.equal(M, M.T))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the raw C ABI (what a Julia ccall sees): layouts, fill modes, sharded host entry, error codes
+# ---------------------------------------------------------------------------------------------------------------
+def test_c_abi_layouts_and_errors(pl, orc):
+    import ctypes
+
+    from plb200 import _lib
+
+    lib = _lib.lib()
+    rng = np.random.default_rng(41)
+    n, d = 150, 9
+    X = rng.standard_normal((n, d)) + 0.5
+    ref = orc.symmetric(orc.kernel_matrix(X, orc.DotProduct()))
+    # Julia layout: column-major d x n features with a padded leading dimension, K with ldk > n, uplo = :U only
+    ldx, ldk = d + 3, n + 5
+    Xj = np.zeros((n, ldx))
+    Xj[:, :d] = X
+    Kj = np.full((n, ldk), -7.0)  # sentinel: untouched entries must keep it
+    _lib.check(lib.pl_gram_dot(_lib.dptr(Xj), n, d, ldx, 2, _lib.dptr(Kj), ldk, _lib.PL_FILL_JULIA_U), "pl_gram_dot")
+    # Julia K[i,j] (i <= j) lives at K[i + j*ldk] = row-major element [j][i]
+    got = Kj[:, :n]
+    il = np.tril_indices(n)
+    assert relerr(got[il], ref[il]) < RTOL
+    assert np.all(Kj[:, n:] == -7.0), "padding columns of the caller's buffer are not written"
+    iu = np.triu_indices(n, 1)
+    assert np.all((got[iu] == 0.0) | (got[iu] == -7.0)), "other triangle: zeros inside diagonal tiles, untouched elsewhere"
+    # rectangular: Julia column-major m x n == row-major n x m -> pass F2 first
+    F1, F2 = X[:40], X[40:150]
+    Kc = np.zeros((110, 40))
+    _lib.check(lib.pl_gram_cross(_lib.PL_KERNEL_RBF, _lib.dptr(np.ascontiguousarray(F2)), 110, d, _lib.dptr(np.ascontiguousarray(F1)), 40, d, d, 0,
+                                 0, None, 1.0, 1.0, _lib.dptr(Kc), 40), "pl_gram_cross")
+    assert relerr(Kc.T, orc.kernel_matrix_cross(F1, F2, orc.RBF(orc.Euclidean(d)))) < RTOL
+    # sharded host entry: union of the parts == the full matrix
+    nparts = 3
+    full = orc.symmetric(orc.kernel_matrix(X, orc.RBF(orc.Euclidean(d))))
+    seen = 0
+    for part in range(nparts):
+        cnt = int(lib.pl_gram_tile_count(n, 0, part, nparts))
+        tiles = np.zeros((cnt, 128, 128))
+        _lib.check(lib.pl_gram_part(_lib.PL_KERNEL_RBF, _lib.dptr(np.ascontiguousarray(X)), n, d, d, 0, 0, None, 1.0, 1.0, part, nparts,
+                                    _lib.dptr(tiles.reshape(-1))), "pl_gram_part")
+        for (ti, tj), tile in zip(pl.gram_tile_coords(n, 0, part, nparts), tiles):
+            if ti < 0:
+                continue
+            blk = full[128 * ti:128 * ti + 128, 128 * tj:128 * tj + 128]
+            assert relerr(tile[: blk.shape[0], : blk.shape[1]], blk) < RTOL
+            seen += 1
+    assert seen == 3  # T = 2 -> 3 upper-triangle tiles
+    # error behaviour: integer status + message, never an exception across the ABI, output untouched
+    K0 = np.zeros((4, 4))
+    assert lib.pl_gram_dot(_lib.dptr(X), 4, 0, 1, 2, _lib.dptr(K0), 4, 3) == 1 and b"bad" in lib.pl_last_error()  # PL_EINVAL
+    assert lib.pl_gram_dot(_lib.dptr(X), 4, d, d - 1, 2, _lib.dptr(K0), 4, 3) == 1
+    assert lib.pl_gram_dot(_lib.dptr(X), 4, d, d, 2, _lib.dptr(K0), 4, 7) == 1  # bad fill
+    assert lib.pl_gram_rbf(_lib.dptr(X), 4, d, d, 1, None, 1.0, 1.0, _lib.dptr(K0), 4, 3) == 1  # diagonal Cinv without data
+    assert lib.pl_gram_rbf(_lib.dptr(X), 4, d, d, 0, None, 0.0, 1.0, _lib.dptr(K0), 4, 3) == 1  # ell == 0
+    assert lib.pl_normal_eq(_lib.dptr(X), n, d, d, None, 0, 1.0, 1.0, None, 0, 0.0, _lib.dptr(K0), _lib.dptr(np.zeros(d))) == 1  # AtWb without b
+    assert np.all(K0 == 0.0)
+    with pytest.raises(ValueError, match="DimensionMismatch"):
+        pl.KernelMatrix(X, pl.RBF(pl.Euclidean(d + 1)))
+    # empty input is a no-op, not an error
+    assert lib.pl_gram_dot(_lib.dptr(X), 0, d, d, 2, _lib.dptr(K0), 4, 3) == 0
+    t = pl.last_timing()
+    assert set(t) == {"kernel_ms", "h2d_ms", "d2h_ms"} and pl.launch_count() > 0
