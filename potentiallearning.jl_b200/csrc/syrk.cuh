@@ -189,12 +189,28 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
       }
   }
 
+  // Uniform-weight fast path: when every row of this CTA's range carries the same weight (the two-segment form
+  // Q = Diagonal([ws1*1_N; ws2*1_M]) away from the segment boundary, or plain sums), the weight is factored out of the
+  // sum and applied once to the 64 accumulators at the end instead of to every A fragment: the FP64 multiplies would
+  // otherwise queue behind the DMMAs on the shared FP64 pipe inside the main loop.
+  bool uniform = (p.w == nullptr);
+  double wscale = 1.0;
+  if (uniform) {
+    if (r_end <= p.ne) wscale = p.w_e;
+    else if (r_begin >= p.ne) wscale = p.w_f;
+    else uniform = false;
+  }
+  // rows of the last stage beyond r_end are zero-filled by TMA (rows_per_split is a multiple of the stage height, so
+  // r_end < r_begin + rows_per_split only at the end of the matrix); only the centred mode has to mask them (0 - mean != 0)
+  const int64_t r_full_end = r_end - (r_end - r_begin) % SYRK_BK;  // stages starting at or after this row are ragged
+
   // byte offset of lane's chunk for step (h, par): row rho = 8h + 2t + par, chunk g ^ (rho & 7)
   // rho & 7 = 2t + par  ->  (g ^ (2t+par)) << 4 ;  row offset rho * 128
   for (int kt = 0; kt < KT; ++kt) {
     const int s = kt % SYRK_STAGES;
     const uint32_t ph = (kt / SYRK_STAGES) & 1u;
     const int64_t r0 = r_begin + (int64_t)kt * SYRK_BK;
+    const bool need_w = !uniform || (CENTER && r0 >= r_full_end);
 
     // per-row weights / rhs of the 4 stage rows this lane contracts over (independent of the TMA data)
     double wv[2][2], bv[2][2], cv[2][2];
@@ -205,7 +221,7 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
         const int64_t r = r0 + 8 * h + 2 * t + par;
         const bool ok = r < r_end;
         double w = 0.0;
-        if (ok) w = p.w ? __ldg(p.w + r) : (r < p.ne ? p.w_e : p.w_f);
+        if (ok) w = uniform ? 1.0 : (p.w ? __ldg(p.w + r) : (r < p.ne ? p.w_e : p.w_f));
         wv[h][par] = w;
         if (VEC) {
           bv[h][par] = (ok && p.b) ? __ldg(p.b + r) : 0.0;
@@ -226,7 +242,6 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
         for (int bx = 0; bx < 2; ++bx) a[bx] = lds128(sA + bx * SYRK_BOX_BYTES + off);
 #pragma unroll
         for (int bx = 0; bx < 4; ++bx) b[bx] = lds128(sB + bx * SYRK_BOX_BYTES + off);
-        const double w = wv[h][par];
         if (CENTER) {
 #pragma unroll
           for (int bx = 0; bx < 2; ++bx) {
@@ -239,10 +254,13 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
             b[bx].y -= mj[bx][1];
           }
         }
+        if (need_w) {
+          const double w = wv[h][par];
 #pragma unroll
-        for (int bx = 0; bx < 2; ++bx) {
-          a[bx].x *= w;
-          a[bx].y *= w;
+          for (int bx = 0; bx < 2; ++bx) {
+            a[bx].x *= w;
+            a[bx].y *= w;
+          }
         }
         if (VEC) {
           if (do_vec) {
@@ -270,6 +288,22 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar(s));
+  }
+  if (uniform && wscale != 1.0) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        acc[mt][nt][0] *= wscale;
+        acc[mt][nt][1] *= wscale;
+      }
+#pragma unroll
+    for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        vb[bx][e] *= wscale;
+        vc[bx][e] *= wscale;
+      }
   }
 
   // ---- partial tile to the workspace in fragment order: [acc index][consumer thread] (coalesced) ----
