@@ -183,7 +183,7 @@ int colsum(const double* dA, int64_t R, int64_t Kf, int64_t lda, double denom, d
     colsum_partial_kernel<<<grid, 128, 0, st>>>(dA, R, Kf, lda, (int)rpb, (double*)part);
     LAUNCH_CHECK();
   }
-  colsum_final_kernel<<<(unsigned)((Kf + 127) / 128), 128, 0, st>>>((const double*)part, nblk, Kf, denom, dout);
+  colsum_final_kernel<<<(unsigned)((Kf + 31) / 32), 256, 0, st>>>((const double*)part, nblk, Kf, denom, dout);
   LAUNCH_CHECK();
   return PL_OK;
 }

@@ -52,20 +52,31 @@ __global__ void colsum_partial_kernel(const double* __restrict__ A, int64_t R, i
   if (pair) partial[(int64_t)blockIdx.y * Kf + c0 + 1] = s1;
 }
 
-// out[col] = (sum_b partial[b][col]) (/ denom if denom != 0), fixed order over b; 8 independent chains for latency
+// out[col] = (sum_b partial[b][col]) (/ denom if denom != 0). Block = 32 columns x 8 row lanes: lane rl sums partial rows
+// rl, rl+8, ... (4 independent chains), then the 8 lane sums are added in fixed order: deterministic, and the pass stays
+// a few microseconds even with hundreds of partial rows (a one-thread-per-column loop took 181 us at config 2).
 __global__ void colsum_final_kernel(const double* __restrict__ partial, int64_t nblocks, int64_t Kf, double denom, double* __restrict__ out) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Kf) return;
-  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int64_t b = 0;
-  for (; b + 8 <= nblocks; b += 8) {
-#pragma unroll
-    for (int u = 0; u < 8; ++u) s[u] += partial[(b + u) * Kf + c];
+  __shared__ double sh[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + cl;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (c < Kf) {
+    int64_t b = rl;
+    for (; b + 24 < nblocks; b += 32) {
+      s0 += partial[b * Kf + c];
+      s1 += partial[(b + 8) * Kf + c];
+      s2 += partial[(b + 16) * Kf + c];
+      s3 += partial[(b + 24) * Kf + c];
+    }
+    for (; b < nblocks; b += 8) s0 += partial[b * Kf + c];
   }
-  for (int u = 0; b < nblocks; ++b, ++u) s[u] += partial[b * Kf + c];
-  double tot = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
-  if (denom != 0.0) tot = tot / denom;
-  out[c] = tot;
+  sh[rl][cl] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (rl == 0 && c < Kf) {
+    double tot = ((sh[0][cl] + sh[1][cl]) + (sh[2][cl] + sh[3][cl])) + ((sh[4][cl] + sh[5][cl]) + (sh[6][cl] + sh[7][cl]));
+    if (denom != 0.0) tot = tot / denom;
+    out[c] = tot;
+  }
 }
 
 enum { PREP_DOT = 0, PREP_RBF_ID = 1, PREP_RBF_DIAG = 2, PREP_CENTER_ONLY = 3 };
