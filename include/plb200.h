@@ -39,6 +39,8 @@ extern "C" {
 #define PL_KERNEL_LINEAR 0 /* plain Gram X1*X2' (no epilogue); building block, e.g. X*Cinv      */
 #define PL_KERNEL_DOT 1    /* DotProduct: (a.b / sqrt((a.a)(b.b)))^alpha      kernels.jl:21-36  */
 #define PL_KERNEL_RBF 2    /* RBF(Euclidean): beta*exp(-0.5*d2/ell^2)         kernels.jl:51-75  */
+#define PL_KERNEL_IMQ 3    /* InverseMultiquadric(Euclidean): (c2 + d2/ell^2)^(-1/2)  kernels.jl:139-164 ("next" row f4:
+                              same Gram engine, one more epilogue). In the generic entries `beta` carries c2.           */
 
 /* Euclidean Cinv kinds (src/Kernels/distances.jl:39-51) */
 #define PL_CINV_IDENTITY 0 /* Euclidean(dim): 1.0*I(dim)                      distances.jl:43-45 */
@@ -86,9 +88,13 @@ int pl_gram_dot(const double* X, int64_t n, int64_t d, int64_t ldx, int alpha, d
 int pl_gram_rbf(const double* X, int64_t n, int64_t d, int64_t ldx, int cinv_kind, const double* cinv, double ell,
                 double beta, double* K, int64_t ldk, int fill);
 
+/* Symmetric InverseMultiquadric(Euclidean) kernel matrix: K[i,j] = (c2 + d2/ell^2)^(-1/2) (kernels.jl:156-164), 0 < c2, 0 < ell. */
+int pl_gram_imq(const double* X, int64_t n, int64_t d, int64_t ldx, int cinv_kind, const double* cinv, double c2, double ell,
+                double* K, int64_t ldk, int fill);
+
 /* Rectangular kernel matrix KernelMatrix(F1,F2,k) (kernels.jl:229-244), written ROW-MAJOR n1 x n2:
  *   K[i*ldk + j] = k(X1_i, X2_j).   (Julia column-major m x n: pass F2 as X1 and F1 as X2.)
- * kernel_id: PL_KERNEL_LINEAR / DOT / RBF; alpha used by DOT; cinv_kind, cinv, ell, beta by RBF. */
+ * kernel_id: PL_KERNEL_LINEAR / DOT / RBF / IMQ; alpha used by DOT; cinv_kind, cinv, ell, beta by RBF (IMQ: beta = c2). */
 int pl_gram_cross(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, const double* X2, int64_t n2, int64_t ldx2,
                   int64_t d, int alpha, int cinv_kind, const double* cinv, double ell, double beta, double* K,
                   int64_t ldk);

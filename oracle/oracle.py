@@ -117,8 +117,28 @@ class RBF:
     beta: float = 1.0
 
 
+@dataclass
+class InverseMultiquadric:
+    d: Euclidean
+    c2: float = 1.0  # kernels.jl:139-152
+    ell: float = 1.0
+
+
+def correlation_matrix(local_descriptors) -> np.ndarray:
+    """compute_feature(B, ::CorrelationMatrix) = Symmetric(mean(Bi*Bi' for Bi in B)) (features.jl:48-50)."""
+    vals = [np.asarray(v, dtype=np.float64) for v in local_descriptors]
+    acc = np.zeros((len(vals[0]), len(vals[0])))
+    for v in vals:
+        acc = acc + np.outer(v, v)
+    return acc / len(vals)
+
+
 def compute_distance(b1, b2, e: Euclidean) -> float:
     """(B1 - B2)' * e.Cinv * (B1 - B2)  (distances.jl:58-60)."""
+    if np.ndim(b1) == 2:  # Symmetric features: tr(Csqrt*(C1-C2)'*Cinv*(C1-C2)*Csqrt) (distances.jl:62-68); identity Cinv here
+        assert e.cinv is None
+        D = np.asarray(b1, dtype=np.float64) - np.asarray(b2, dtype=np.float64)
+        return float(np.trace(D.T @ D))
     v = np.asarray(b1, dtype=np.float64) - np.asarray(b2, dtype=np.float64)
     if e.cinv is None:
         c = 1.0 * v  # 1.0*I(dim)
@@ -134,10 +154,15 @@ def compute_kernel(a, b, k) -> float:
     b = np.asarray(b, dtype=np.float64)
     if isinstance(k, DotProduct):
         # (dot(A,B) / sqrt(dot(A,A)*dot(B,B)))^α   (kernels.jl:35)
-        return float((np.dot(a, b) / np.sqrt(np.dot(a, a) * np.dot(b, b))) ** int(k.alpha))
+        # dot() of two matrices is the sum of elementwise products (LinearAlgebra.dot), so Symmetric features work unchanged
+        return float((np.sum(a * b) / np.sqrt(np.sum(a * a) * np.sum(b * b))) ** int(k.alpha)) if a.ndim == 2 else \
+            float((np.dot(a, b) / np.sqrt(np.dot(a, a) * np.dot(b, b))) ** int(k.alpha))
     if isinstance(k, RBF):
         d2 = compute_distance(a, b, k.d)
         return float(k.beta * np.exp(-0.5 * d2 / k.ell ** 2))  # kernels.jl:73-74
+    if isinstance(k, InverseMultiquadric):
+        d2 = compute_distance(a, b, k.d)
+        return float((k.c2 + d2 / k.ell ** 2) ** (-0.5))  # kernels.jl:162-163
     raise TypeError(k)
 
 
@@ -145,6 +170,13 @@ def kernel_matrix(F, k, use_c: bool | None = None) -> np.ndarray:
     """KernelMatrix(F,k) (kernels.jl:211-223). Returns the n x n array whose [i, j] entry for i <= j is k(F_i, F_j) and
     whose strict lower triangle is 0 — i.e. `K.data` of the reference's Symmetric(K) (uplo = :U)."""
     X = np.ascontiguousarray(np.asarray(F, dtype=np.float64))
+    if X.ndim == 3:  # Vector{Symmetric}: pure-Python pair loop on the matrices themselves
+        n = X.shape[0]
+        K = np.zeros((n, n))
+        for i in range(n):
+            for j in range(i, n):
+                K[i, j] = compute_kernel(X[i], X[j], k)
+        return K
     n, d = X.shape
     if use_c is None:
         use_c = n > 64
@@ -194,6 +226,9 @@ def _kernel_args(k):
     if isinstance(k, RBF):
         cinv = None if k.d.cinv is None else _c64(k.d.cinv)
         return 2, 0, k.d.kind, cinv, float(k.ell), float(k.beta)
+    if isinstance(k, InverseMultiquadric):
+        cinv = None if k.d.cinv is None else _c64(k.d.cinv)
+        return 3, 0, k.d.kind, cinv, float(k.ell), float(k.c2)
     raise TypeError(k)
 
 

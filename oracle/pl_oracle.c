@@ -68,9 +68,22 @@ double orc_kernel_rbf(const double* a, const double* b, int64_t d, int cinv_kind
   return beta * exp(-0.5 * d2 / (ell * ell));
 }
 
+/* compute_kernel(A,B,::InverseMultiquadric) src/Kernels/kernels.jl:156-164:  (c2 + d2 / ell^2)^(-0.5) */
+double orc_kernel_imq(const double* a, const double* b, int64_t d, int cinv_kind, const double* cinv, double ell, double c2, double* tmp) {
+  const double d2 = orc_distance_euclidean(a, b, d, cinv_kind, cinv, tmp);
+  return pow(c2 + d2 / (ell * ell), -0.5);
+}
+
+static double eval_kernel(int kernel_id, const double* a, const double* b, int64_t d, int alpha, int cinv_kind, const double* cinv, double ell,
+                          double beta, double* tmp) {
+  if (kernel_id == 1) return orc_kernel_dot(a, b, d, alpha);
+  if (kernel_id == 3) return orc_kernel_imq(a, b, d, cinv_kind, cinv, ell, beta, tmp); /* beta carries c2 */
+  return orc_kernel_rbf(a, b, d, cinv_kind, cinv, ell, beta, tmp);
+}
+
 /* KernelMatrix(F,k) src/Kernels/kernels.jl:211-223: K = zeros(n,n); for i=1:n, j=i:n K[i,j] = k(F_i,F_j); Symmetric(K).
  * X: row-major n x d. K: n x n, Julia column-major K[i + j*ldk] (== row-major element [j][i]); only j >= i is written,
- * the other triangle is left as the caller initialised it (zeros in the reference). kernel_id 1 = DotProduct, 2 = RBF.
+ * the other triangle is left as the caller initialised it (zeros in the reference). kernel_id 1 = DotProduct, 2 = RBF, 3 = InverseMultiquadric (beta carries c2).
  * Rows [row_begin, row_end) only: lets the benchmark time a bounded sample of the pair loop. */
 int orc_kernel_matrix_sym(int kernel_id, const double* X, int64_t n, int64_t d, int64_t ldx, int alpha, int cinv_kind, const double* cinv,
                           double ell, double beta, double* K, int64_t ldk, int64_t row_begin, int64_t row_end) {
@@ -80,7 +93,7 @@ int orc_kernel_matrix_sym(int kernel_id, const double* X, int64_t n, int64_t d, 
     for (int64_t j = i; j < n; ++j) {
       const double* a = X + i * ldx;
       const double* b = X + j * ldx;
-      K[i + j * ldk] = (kernel_id == 1) ? orc_kernel_dot(a, b, d, alpha) : orc_kernel_rbf(a, b, d, cinv_kind, cinv, ell, beta, tmp);
+      K[i + j * ldk] = eval_kernel(kernel_id, a, b, d, alpha, cinv_kind, cinv, ell, beta, tmp);
     }
   }
   free(tmp);
@@ -96,7 +109,7 @@ int orc_kernel_matrix_cross(int kernel_id, const double* X1, int64_t m, int64_t 
     for (int64_t j = 0; j < n; ++j) {
       const double* a = X1 + i * ldx1;
       const double* b = X2 + j * ldx2;
-      K[i + j * ldk] = (kernel_id == 1) ? orc_kernel_dot(a, b, d, alpha) : orc_kernel_rbf(a, b, d, cinv_kind, cinv, ell, beta, tmp);
+      K[i + j * ldk] = eval_kernel(kernel_id, a, b, d, alpha, cinv_kind, cinv, ell, beta, tmp);
     }
   free(tmp);
   return 0;

@@ -34,7 +34,7 @@ constexpr int CONSUMER_REGS = 240;  // per SMSP: 2 x 240 + 24 = 504 <= 512 regis
 constexpr int GRAM_TILE_BYTES = GRAM_BM * GRAM_BK * 8;  // 16 KB per operand per stage
 constexpr int GRAM_SMEM_BYTES = GRAM_STAGES * 2 * GRAM_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
-enum { EPI_LINEAR = 0, EPI_DOT = 1, EPI_RBF = 2 };
+enum { EPI_LINEAR = 0, EPI_DOT = 1, EPI_RBF = 2, EPI_IMQ = 3 };
 
 struct GramParams {
   int64_t n1, n2;       // output rows (A operand rows) / cols (B operand rows); symmetric: n2 == n1
@@ -48,8 +48,8 @@ struct GramParams {
   int fill;             // PL_FILL_* bits (symmetric only)
   int packed;           // tile-packed output
   int alpha;            // DOT power
-  double s;             // RBF: -0.5 / ell^2
-  double beta;          // RBF scale
+  double s;             // RBF: -0.5 / ell^2 ; IMQ: 1 / ell^2
+  double beta;          // RBF scale ; IMQ: c^2
   int T1, T2;           // tile rows / tile cols
   int64_t ntiles_total; // linear tile slots (symmetric: folded enumeration incl. a few invalid slots)
   int part, nparts;     // tile sharding across GPUs: slot l is ours iff l % nparts == part
@@ -159,10 +159,11 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[4][8][2], cons
       if (!ok) imask &= ~(1u << mt);
     }
     const double r = (EPI != EPI_LINEAR && ok) ? __ldg(p.ra + i0 + 8 * mt) : 0.0;
-    sa[mt] = (EPI == EPI_RBF) ? p.s * r : r;
+    sa[mt] = (EPI == EPI_RBF || EPI == EPI_IMQ) ? p.s * r : r;
   }
   const double m2s = -2.0 * p.s;
-  const double diagval = (EPI == EPI_RBF) ? p.beta : 1.0;
+  // k(x,x): beta for RBF (d2 == 0), c2^(-1/2) for IMQ, n/sqrt(n*n) = 1 for DotProduct
+  const double diagval = (EPI == EPI_RBF) ? p.beta : (EPI == EPI_IMQ ? rsqrt(p.beta) : 1.0);
   const bool fill1 = p.packed || !p.symmetric || (p.fill & 1);
   const bool fill2 = p.packed || (p.fill & 2);
   const bool dg = rel0 != 4096;
@@ -190,6 +191,9 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[4][8][2], cons
           } else if (EPI == EPI_RBF) {
             // arg = s*(q_i + q_j - 2 G_ij) = -0.5 d2 / ell^2  (kernels.jl:73-74 with distances.jl:59 expanded)
             x = exp_clamped(fma(x, m2s, fma(p.s, r, sa[mt]))) * p.beta;
+          } else if (EPI == EPI_IMQ) {
+            // (c2 + d2/ell^2)^(-1/2)  (kernels.jl:156-164): d2/ell^2 = s*(q_i + q_j - 2 G_ij) with s = 1/ell^2
+            x = rsqrt(p.beta + fma(x, m2s, fma(p.s, r, sa[mt])));
           }
           v[q][c] = x;
         }

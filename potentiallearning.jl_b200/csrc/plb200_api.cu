@@ -235,6 +235,7 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
     case EPI_LINEAR: gram_kernel<EPI_LINEAR><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
     case EPI_DOT: gram_kernel<EPI_DOT><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
     case EPI_RBF: gram_kernel<EPI_RBF><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
+    case EPI_IMQ: gram_kernel<EPI_IMQ><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
     default: return set_err(PL_EINVAL, "unknown epilogue %d", L.epi);
   }
   LAUNCH_CHECK();
@@ -313,8 +314,9 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
     if (prepared) { *prepared = L; return PL_OK; }
     return launch_gram(L, st);
   }
-  if (kernel_id != PL_KERNEL_RBF) return set_err(PL_EINVAL, "unknown kernel id %d", kernel_id);
-  if (!(ell != 0.0)) return set_err(PL_EINVAL, "RBF length scale must be non-zero");
+  if (kernel_id != PL_KERNEL_RBF && kernel_id != PL_KERNEL_IMQ) return set_err(PL_EINVAL, "unknown kernel id %d", kernel_id);
+  if (!(ell != 0.0)) return set_err(PL_EINVAL, "length scale must be non-zero");
+  if (kernel_id == PL_KERNEL_IMQ && !(beta > 0.0 && ell > 0.0)) return set_err(PL_EINVAL, "InverseMultiquadric needs 0 < c2 and 0 < ell (kernels.jl:143-146)");
   if (cinv_kind != PL_CINV_IDENTITY && cinv_kind != PL_CINV_DIAGONAL && cinv_kind != PL_CINV_FULL) return set_err(PL_EINVAL, "unknown cinv_kind %d", cinv_kind);
   if (cinv_kind != PL_CINV_IDENTITY && !dcinv) return set_err(PL_EINVAL, "cinv is NULL");
 
@@ -330,9 +332,9 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
     PL_TRY(ws_get(WS_XC2, (size_t)n2 * ldc * 8, &xc2));
     PL_TRY(ws_get(WS_STAT2, (size_t)n2 * 8, &s2));
   }
-  L.epi = EPI_RBF;
-  L.s = -0.5 / (ell * ell);
-  L.beta = beta;
+  L.epi = kernel_id == PL_KERNEL_IMQ ? EPI_IMQ : EPI_RBF;
+  L.s = kernel_id == PL_KERNEL_IMQ ? 1.0 / (ell * ell) : -0.5 / (ell * ell);
+  L.beta = beta;  // RBF: beta ; IMQ: c2
   L.ra = (double*)s1;
   L.rb = sym ? (double*)s1 : (double*)s2;
   if (cinv_kind == PL_CINV_IDENTITY) {
@@ -545,6 +547,7 @@ int pl_init(int device) {
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_IMQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
@@ -706,10 +709,11 @@ static int gram_host(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, 
   int64_t l1, l2 = 0;
   PL_TRY(h2d_matrix(X1, n1, d, ldx1, WS_H_IN1, &d1, &l1));
   if (!sym) PL_TRY(h2d_matrix(X2, n2, d, ldx2, WS_H_IN2, &d2, &l2));
-  if (kernel_id == PL_KERNEL_RBF && cinv_kind == PL_CINV_DIAGONAL) {
+  const bool dist_kernel = (kernel_id == PL_KERNEL_RBF || kernel_id == PL_KERNEL_IMQ);
+  if (dist_kernel && cinv_kind == PL_CINV_DIAGONAL) {
     if (!cinv) return set_err(PL_EINVAL, "cinv is NULL");
     PL_TRY(h2d_vector(cinv, d, WS_H_IN3, &dc));
-  } else if (kernel_id == PL_KERNEL_RBF && cinv_kind == PL_CINV_FULL) {
+  } else if (dist_kernel && cinv_kind == PL_CINV_FULL) {
     if (!cinv) return set_err(PL_EINVAL, "cinv is NULL");
     PL_TRY(h2d_vector(cinv, d * d, WS_H_IN3, &dc));  // dense d x d; gram_dev_impl pads it if d is odd
   }
@@ -782,6 +786,12 @@ int pl_gram_rbf(const double* X, int64_t n, int64_t d, int64_t ldx, int cinv_kin
   return gram_host(PL_KERNEL_RBF, X, n, ldx, nullptr, 0, 0, d, 0, cinv_kind, cinv, ell, beta, K, ldk, fill);
 }
 
+int pl_gram_imq(const double* X, int64_t n, int64_t d, int64_t ldx, int cinv_kind, const double* cinv, double c2, double ell, double* K,
+                int64_t ldk, int fill) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return gram_host(PL_KERNEL_IMQ, X, n, ldx, nullptr, 0, 0, d, 0, cinv_kind, cinv, ell, c2, K, ldk, fill);
+}
+
 int pl_gram_cross(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, const double* X2, int64_t n2, int64_t ldx2, int64_t d, int alpha,
                   int cinv_kind, const double* cinv, double ell, double beta, double* K, int64_t ldk) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -800,7 +810,7 @@ int pl_gram_part(int kernel_id, const double* X, int64_t n, int64_t d, int64_t l
   double *dX, *dc = nullptr;
   int64_t ld;
   PL_TRY(h2d_matrix(X, n, d, ldx, WS_H_IN1, &dX, &ld));
-  if (kernel_id == PL_KERNEL_RBF && cinv_kind != PL_CINV_IDENTITY) {
+  if ((kernel_id == PL_KERNEL_RBF || kernel_id == PL_KERNEL_IMQ) && cinv_kind != PL_CINV_IDENTITY) {
     if (!cinv) return set_err(PL_EINVAL, "cinv is NULL");
     PL_TRY(h2d_vector(cinv, cinv_kind == PL_CINV_DIAGONAL ? d : d * d, WS_H_IN3, &dc));
   }

@@ -10,7 +10,8 @@ from .data import (Configuration, DataSet, Energy, ForceDescriptors, Forces, Loc
 from .dimred import PCA, ActiveSubspace, DimensionReducer, PCAState, compute_eigen, covariance, fit, fit_, select_eigendirections, transform_
 from .dpp import (EllEnsemble, SubsetSelector, get_dpp_mode, get_inclusion_prob, get_random_subset, greedy_subset, inclusion_prob, kDPP,
                   rescale_, sample)
-from .kernels import (RBF, Diagonal, Distance, DotProduct, Euclidean, Feature, GlobalMean, GlobalSum, Kernel, KernelMatrix, Symmetric,
+from .kernels import (RBF, CorrelationMatrix, Diagonal, Distance, DotProduct, Euclidean, Feature, GlobalMean, GlobalSum, InverseMultiquadric, Kernel,
+                      KernelMatrix, Symmetric,
                       compute_distance, compute_feature, compute_features, compute_kernel, get_parameters, gram_tile_coords,
                       kernel_matrix_dev)
 from .learning import (CovariateLinearProblem, LinearProblem, UnivariateLinearProblem, assemble_matrices, learn_, normal_equations,

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PLB200_LIB", os.path.join(_HERE, "libplb200.so"))
 
-PL_KERNEL_LINEAR, PL_KERNEL_DOT, PL_KERNEL_RBF = 0, 1, 2
+PL_KERNEL_LINEAR, PL_KERNEL_DOT, PL_KERNEL_RBF, PL_KERNEL_IMQ = 0, 1, 2, 3
 PL_CINV_IDENTITY, PL_CINV_DIAGONAL, PL_CINV_FULL = 0, 1, 2
 PL_FILL_RM_UPPER, PL_FILL_RM_LOWER, PL_FILL_FULL = 1, 2, 3
 PL_FILL_JULIA_U = PL_FILL_RM_LOWER
@@ -36,6 +36,7 @@ PROTOTYPES = {
     "pl_gram_part": (_int, [_int, _dp, _i64, _i64, _i64, _int, _int, _dp, _dbl, _dbl, _int, _int, _dp]),
     "pl_gram_dot": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _i64, _int]),
     "pl_gram_rbf": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _dbl, _dbl, _dp, _i64, _int]),
+    "pl_gram_imq": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _dbl, _dbl, _dp, _i64, _int]),
     "pl_gram_cross": (_int, [_int, _dp, _i64, _i64, _dp, _i64, _i64, _i64, _int, _int, _dp, _dbl, _dbl, _dp, _i64]),
     "pl_normal_eq": (_int, [_dp, _i64, _i64, _i64, _dp, _i64, _dbl, _dbl, _dp, _int, _dbl, _dp, _dp]),
     "pl_cov": (_int, [_dp, _i64, _i64, _i64, _dp, _int, _int, _dp]),

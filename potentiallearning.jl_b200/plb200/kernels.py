@@ -2,7 +2,10 @@
 GlobalMean / GlobalSum features, Euclidean distance, DotProduct and RBF kernels, and the four KernelMatrix methods.
 Same names, argument meaning and error behaviour as the Julia API; the arithmetic runs in libplb200.so on the GPU.
 
-Out of scope (stay Julia): Forstner, CorrelationMatrix, InverseMultiquadric, kernel gradients, KernelSteinDiscrepancy.
+Widened beyond the north-star kernels on the same Gram engine: InverseMultiquadric(Euclidean) and
+CorrelationMatrix features (a Symmetric d x d feature is flattened: dot(A,B) and the identity-Cinv Euclidean distance of two
+Symmetric matrices are the dot product / squared distance of their d*d entries).
+Out of scope (stay Julia): Forstner, kernel gradients, KernelSteinDiscrepancy.
 """
 from __future__ import annotations
 
@@ -25,12 +28,21 @@ class GlobalMean(Feature):
     """GlobalMean (features.jl:28-34)."""
 
 
+class CorrelationMatrix(Feature):
+    """CorrelationMatrix (features.jl:37-50): Symmetric(mean(Bi*Bi' for Bi in B)), a d x d global descriptor."""
+
+
 def compute_feature(x, f: Feature, dt=LocalDescriptors) -> np.ndarray:
     """compute_feature(B::LocalDescriptors, gm) / compute_feature(c::Configuration, gm; dt) (features.jl:19-21, 32-34, 59-65).
     `dt` is accepted and ignored for GlobalMean/GlobalSum exactly as in the reference (features.jl:59-65)."""
     if isinstance(x, Configuration):
         x = get_local_descriptors(x)
     b = get_values(x) if isinstance(x, LocalDescriptors) else np.asarray(x, dtype=np.float64)
+    if isinstance(f, CorrelationMatrix):
+        acc = np.zeros((b.shape[1], b.shape[1]))
+        for bi in b:  # mean(Bi * Bi' ...): sequential sum of outer products / natoms (features.jl:49)
+            acc = acc + np.outer(bi, bi)
+        return Symmetric(acc / b.shape[0])
     s = np.add.reduce(b, axis=0)  # sequential row accumulation == Julia's sum over a Vector{Vector}
     if isinstance(f, GlobalMean):
         return s / b.shape[0]
@@ -127,10 +139,23 @@ class RBF(Kernel):
         self.d, self.alpha, self.ell, self.beta = d, alpha, ell, beta
 
 
+class InverseMultiquadric(Kernel):
+    """InverseMultiquadric(d; c2 = 1.0, ℓ = 1.0) (kernels.jl:139-152): (c2 + d2/ℓ²)^(-1/2); asserts 0 < c2, 0 < ℓ."""
+
+    def __init__(self, d: Distance, c2=1.0, ell=1.0):
+        if not isinstance(d, Euclidean):
+            raise TypeError("only InverseMultiquadric(Euclidean) is on the B200 Gram engine")
+        assert 0 < c2
+        assert 0 < ell
+        self.d, self.c2, self.ell = d, c2, ell
+
+
 def get_parameters(k: Kernel):
-    """get_parameters (kernels.jl:28, 61)."""
+    """get_parameters (kernels.jl:28, 61, 153)."""
     if isinstance(k, DotProduct):
         return (k.alpha,)
+    if isinstance(k, InverseMultiquadric):
+        return (k.c2, k.ell)
     return (k.alpha, k.ell, k.beta)
 
 
@@ -142,11 +167,20 @@ def _kargs(k: Kernel, d: int):
         if e.dim != d:
             raise ValueError(f"DimensionMismatch: Euclidean of dimension {e.dim} applied to features of length {d}")
         return _lib.PL_KERNEL_RBF, 0, e.kind, e.Cinv, float(k.ell), float(k.beta)
+    if isinstance(k, InverseMultiquadric):
+        e = k.d
+        if e.dim != d:
+            raise ValueError(f"DimensionMismatch: Euclidean of dimension {e.dim} applied to features of length {d}")
+        return _lib.PL_KERNEL_IMQ, 0, e.kind, e.Cinv, float(k.ell), float(k.c2)
     raise TypeError(f"kernel {type(k).__name__} is outside the B200 hot path")
 
 
 def _features_matrix(F) -> np.ndarray:
-    """Vector{Vector{T}} -> row-major n x d (== Julia's reduce(hcat, F), column-major d x n)."""
+    """Vector{Vector{T}} -> row-major n x d (== Julia's reduce(hcat, F), column-major d x n).
+    Vector{Symmetric} features (CorrelationMatrix) are flattened to their d*d entries: dot(A,B) of two matrices and the
+    identity-Cinv Euclidean distance tr((C1-C2)'(C1-C2)) (distances.jl:62-68) are exactly the vector forms of the entries."""
+    if len(F) > 0 and isinstance(F[0], Symmetric):
+        return np.ascontiguousarray(np.stack([np.asarray(f).reshape(-1) for f in F]))
     X = _lib.as_f64(F)
     if X.ndim != 2:
         raise ValueError("features must be n vectors of equal length")
@@ -171,7 +205,9 @@ class _Linear(Kernel):
 
 
 def compute_kernel(A, B, k: Kernel) -> float:
-    """compute_kernel(A, B, k) for two feature vectors (kernels.jl:30-36, 68-75)."""
+    """compute_kernel(A, B, k) for two features, vectors or Symmetric matrices (kernels.jl:30-36, 68-75, 156-164)."""
+    if isinstance(A, Symmetric):
+        return float(KernelMatrix([A], [B], k)[0, 0])
     return float(KernelMatrix([_lib.as_f64(A)], [_lib.as_f64(B)], k)[0, 0])
 
 
@@ -186,19 +222,31 @@ def KernelMatrix(*args, dt=LocalDescriptors, fill: str = "full"):
     """
     if len(args) == 2:
         F, k = args
-        return _kernel_matrix_sym(_features_matrix(F), k, fill)
+        X = _features_matrix(F)
+        return _kernel_matrix_sym(X, _for_flattened(k, F, X.shape[1]), fill)
     if len(args) == 3 and isinstance(args[0], DataSet):
         ds, f, k = args
-        return _kernel_matrix_sym(_features_matrix(compute_features(ds, f, dt=dt)), k, fill)
+        return KernelMatrix(compute_features(ds, f, dt=dt), k, fill=fill)
     if len(args) == 3:
         F1, F2, k = args
-        return _kernel_matrix_cross(_features_matrix(F1), _features_matrix(F2), k)
+        X1, X2 = _features_matrix(F1), _features_matrix(F2)
+        return _kernel_matrix_cross(X1, X2, _for_flattened(k, F1, X1.shape[1]))
     if len(args) == 4:
         ds1, ds2, f, k = args
-        F1 = _features_matrix(compute_features(ds1, f, dt=dt))
-        F2 = _features_matrix(compute_features(ds2, f, dt=dt))
-        return _kernel_matrix_cross(F1, F2, k)
+        return KernelMatrix(compute_features(ds1, f, dt=dt), compute_features(ds2, f, dt=dt), k)
     raise TypeError("KernelMatrix(F,k) | (F1,F2,k) | (ds,f,k) | (ds1,ds2,f,k)")
+
+
+def _for_flattened(k: Kernel, F, d_flat: int) -> Kernel:
+    """Kernel acting on flattened Symmetric features: the Euclidean dimension refers to the matrix order."""
+    if len(F) > 0 and isinstance(F[0], Symmetric) and isinstance(k, (RBF, InverseMultiquadric)):
+        if k.d.kind != _lib.PL_CINV_IDENTITY:
+            raise TypeError("Euclidean(Cinv) on Symmetric features needs tr(Csqrt*(C1-C2)'*Cinv*(C1-C2)*Csqrt): stays in PotentialLearning.jl")
+        if k.d.dim ** 2 != d_flat:
+            raise ValueError("DimensionMismatch: Euclidean dimension does not match the matrix features")
+        e = Euclidean(d_flat)
+        return RBF(e, k.alpha, k.ell, k.beta) if isinstance(k, RBF) else InverseMultiquadric(e, k.c2, k.ell)
+    return k
 
 
 def _kernel_matrix_sym(X: np.ndarray, k: Kernel, fill: str) -> Symmetric:
@@ -212,6 +260,8 @@ def _kernel_matrix_sym(X: np.ndarray, k: Kernel, fill: str) -> Symmetric:
     kid, alpha, kind, cinv, ell, beta = _kargs(k, d)
     if kid == _lib.PL_KERNEL_DOT:
         _lib.check(lib.pl_gram_dot(_lib.dptr(X), n, d, d, alpha, _lib.dptr(K), n, fl), "pl_gram_dot")
+    elif kid == _lib.PL_KERNEL_IMQ:
+        _lib.check(lib.pl_gram_imq(_lib.dptr(X), n, d, d, kind, _lib.dptr(cinv), beta, ell, _lib.dptr(K), n, fl), "pl_gram_imq")
     else:
         _lib.check(lib.pl_gram_rbf(_lib.dptr(X), n, d, d, kind, _lib.dptr(cinv), ell, beta, _lib.dptr(K), n, fl), "pl_gram_rbf")
     return Symmetric(K, "U")

@@ -46,7 +46,7 @@ def test_python_prototypes_match_header():
 
 def test_constants_match_header():
     txt = open(HEADER).read()
-    for cname in ("PL_KERNEL_LINEAR", "PL_KERNEL_DOT", "PL_KERNEL_RBF", "PL_CINV_IDENTITY", "PL_CINV_DIAGONAL", "PL_CINV_FULL",
+    for cname in ("PL_KERNEL_LINEAR", "PL_KERNEL_DOT", "PL_KERNEL_RBF", "PL_KERNEL_IMQ", "PL_CINV_IDENTITY", "PL_CINV_DIAGONAL", "PL_CINV_FULL",
                   "PL_FILL_RM_UPPER", "PL_FILL_RM_LOWER", "PL_FILL_FULL"):
         m = re.search(r"#define\s+" + cname + r"\s+(\d+)", txt)
         assert m and int(m.group(1)) == getattr(_lib, cname)

@@ -185,6 +185,44 @@ def test_rbf_full_cinv_at_example_scale(pl, orc):
     assert 1e-6 < np.median(ref) < 0.99
 
 
+def test_inverse_multiquadric_and_correlation_features(pl, orc):
+    """Widened rows on the same Gram engine: InverseMultiquadric(Euclidean) (kernels.jl:139-164) and
+    CorrelationMatrix features (features.jl:37-50) with DotProduct / RBF / IMQ, as test/kernels/kernel_tests.jl exercises them."""
+    rng = np.random.default_rng(55)
+    n, d = 260, 11
+    X = rng.standard_normal((n, d)) * 0.5 + 1.0
+    for c2, ell in ((1.0, 1.0), (0.3, 2.5)):
+        K = np.asarray(pl.KernelMatrix(X, pl.InverseMultiquadric(pl.Euclidean(d), c2=c2, ell=ell)))
+        ref = orc.symmetric(orc.kernel_matrix(X, orc.InverseMultiquadric(orc.Euclidean(d), c2=c2, ell=ell)))
+        assert relerr(K, ref) < RTOL and np.array_equal(K, K.T)
+        assert np.allclose(np.diag(K), c2 ** -0.5, rtol=1e-15)
+    cd = rng.uniform(0.5, 2.0, size=d)
+    Kx = pl.KernelMatrix(X[:30], X[30:90], pl.InverseMultiquadric(pl.Euclidean(pl.Diagonal(cd)), c2=2.0))
+    assert relerr(Kx, orc.kernel_matrix_cross(X[:30], X[30:90], orc.InverseMultiquadric(orc.Euclidean(d, cd), c2=2.0))) < RTOL
+    with pytest.raises(AssertionError):
+        pl.InverseMultiquadric(pl.Euclidean(d), c2=0.0)
+    assert pl.get_parameters(pl.InverseMultiquadric(pl.Euclidean(d), c2=2.0, ell=3.0)) == (2.0, 3.0)
+    # CorrelationMatrix features: 10 configs x 20 atoms x d = 8 (kernel_tests.jl:7-13, 27-33)
+    ds = fake_dataset(pl, rng, 10, 20, 8)
+    cm = pl.CorrelationMatrix()
+    f_cm = pl.compute_features(ds, cm)
+    assert isinstance(f_cm[0], pl.Symmetric) and f_cm[0].shape == (8, 8)  # :31
+    ref_cm = [orc.correlation_matrix(list(pl.get_values(pl.get_local_descriptors(c)))) for c in ds]
+    assert all(np.array_equal(np.asarray(a), b) for a, b in zip(f_cm, ref_cm))
+    e8 = pl.Euclidean(8)
+    assert np.isclose(pl.compute_kernel(f_cm[0], f_cm[0], pl.DotProduct()), 1.0)  # :68
+    assert np.isclose(pl.compute_kernel(f_cm[0], f_cm[0], pl.RBF(e8)), 1.0)  # :69
+    assert pl.compute_kernel(f_cm[0], f_cm[1], pl.DotProduct()) > 0 and pl.compute_kernel(f_cm[0], f_cm[1], pl.RBF(e8)) > 0  # :74-75
+    for k, ko in ((pl.DotProduct(), orc.DotProduct()), (pl.RBF(e8), orc.RBF(orc.Euclidean(8))),
+                  (pl.InverseMultiquadric(e8), orc.InverseMultiquadric(orc.Euclidean(8)))):
+        K = pl.KernelMatrix(f_cm, k)
+        assert isinstance(K, pl.Symmetric)  # :86, :88
+        assert relerr(np.asarray(K), orc.symmetric(orc.kernel_matrix(ref_cm, ko))) < RTOL
+    assert isinstance(pl.KernelMatrix(ds, cm, pl.DotProduct()), pl.Symmetric)
+    with pytest.raises(TypeError):
+        pl.KernelMatrix(f_cm, pl.RBF(pl.Euclidean(pl.Diagonal(np.ones(8)))))
+
+
 def test_rbf_extreme_arguments(pl, orc):
     """exp argument outside the fast range (< -708: results below 3e-308) and the whole dynamic range in between."""
     rng = np.random.default_rng(9)
