@@ -124,6 +124,13 @@ int pl_normal_eq(const double* A, int64_t R, int64_t Kf, int64_t lda, const doub
  * (pca.m persists, pca_state.jl:34); C = (1/n) sum_r (x_r-m)(x_r-m)'. C: Kf x Kf full, exactly symmetric. */
 int pl_cov(const double* X, int64_t n, int64_t Kf, int64_t ldx, double* mean_inout, int mean_given, int center, double* C);
 
+/* ---- predictions of the fitted linear model ("next" row f3 of SURVEY.md 8f) ------------------------------ */
+/* y[r] = A[r,:] . beta + (r < n_energy_rows ? beta0 : 0) over the same packed rows as pl_normal_eq: what
+ * get_all_energies(ds, lb) / get_all_forces(ds, lb) (src/Data/utils.jl:42-65) evaluate after learn! (B.beta + beta0, dB.beta). */
+int pl_predict(const double* A, int64_t R, int64_t Kf, int64_t lda, const double* beta, double beta0, int64_t n_energy_rows, double* y);
+int pl_predict_dev(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dbeta, double beta0, int64_t n_energy_rows,
+                   double* dy, void* stream);
+
 /* ---- device-resident entry points (enqueue only; `stream` is a cudaStream_t) ---------------------------- */
 
 /* Kernel matrix on device data. dX2 == NULL -> symmetric (n2/ldx2 ignored, `fill` applies); otherwise rectangular

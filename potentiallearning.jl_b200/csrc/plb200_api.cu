@@ -681,6 +681,52 @@ int pl_scale_div_dev(const double* dIn, double denom, int64_t count, double* dOu
   return PL_OK;
 }
 
+static int predict_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dbeta, double beta0, int64_t ne, double* dy,
+                            cudaStream_t st) {
+  PL_TRY(need_ready());
+  if (R < 0 || Kf <= 0 || lda < Kf || !dA || !dbeta || !dy) return set_err(PL_EINVAL, "bad arguments");
+  if (R == 0) return PL_OK;
+  const double* A;
+  int64_t ld;
+  PL_TRY(tma_operand(dA, R, Kf, lda, WS_PAD1, st, &A, &ld));
+  const double* b;
+  int64_t ldb;
+  PL_TRY(tma_operand(dbeta, 1, Kf, (Kf + 1) & ~(int64_t)1, WS_PADC, st, &b, &ldb));
+  int64_t blocks = (R * 32 + 255) / 256;
+  const int64_t cap = (int64_t)g.num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  predict_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, R, Kf, ld, b, beta0, ne, dy);
+  LAUNCH_CHECK();
+  return PL_OK;
+}
+
+int pl_predict_dev(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dbeta, double beta0, int64_t n_energy_rows, double* dy,
+                   void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return predict_dev_impl(dA, R, Kf, lda, dbeta, beta0, n_energy_rows, dy, (cudaStream_t)stream);
+}
+
+int pl_predict(const double* A, int64_t R, int64_t Kf, int64_t lda, const double* beta, double beta0, int64_t n_energy_rows, double* y) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!A || !beta || !y || R < 0 || Kf <= 0 || lda < Kf) return set_err(PL_EINVAL, "bad arguments");
+  if (R == 0) return PL_OK;
+  CUDA_TRY(cudaSetDevice(g.device));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  double *dA, *db;
+  int64_t ld;
+  PL_TRY(h2d_matrix(A, R, Kf, lda, WS_H_IN1, &dA, &ld));
+  PL_TRY(h2d_vector(beta, Kf, WS_H_IN2, &db));
+  void* dy;
+  PL_TRY(ws_get(WS_H_OUT2, (size_t)R * 8, &dy));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  PL_TRY(predict_dev_impl(dA, R, Kf, ld, db, beta0, n_energy_rows, (double*)dy, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaMemcpyAsync(y, dy, (size_t)R * 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();
+}
+
 int pl_sym_scale_div_dev(const double* dIn, int64_t K, double denom, double* dOut, void* stream) {
   std::lock_guard<std::mutex> lk(g_mu);
   PL_TRY(need_ready());

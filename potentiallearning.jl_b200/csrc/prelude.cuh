@@ -160,6 +160,33 @@ __global__ void scale_div_kernel(const double* __restrict__ in, double denom, in
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i] / denom;
 }
 
+// y[r] = sum_k A[r][k] * beta[k] + (r < ne ? beta0 : 0): the prediction of a linear basis potential over the packed rows
+// (energies of the first ne rows get the intercept, force rows do not — the same [1_N; 0_M] column as in the fit,
+// linear-learn.jl:239-241). HBM-bound GEMV: one warp per row, 128-bit coalesced loads, beta through the read-only cache,
+// warp-shuffle reduction. SURVEY.md 8f row f3 (what get_all_energies / get_all_forces(ds, lb) need after learn!).
+__global__ void predict_rows_kernel(const double* __restrict__ A, int64_t R, int64_t Kf, int64_t lda, const double* __restrict__ beta,
+                                    double beta0, int64_t ne, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t kpair = Kf & ~(int64_t)1;
+  for (int64_t r = warp0; r < R; r += nwarps) {
+    const double* a = A + r * lda;
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int64_t k = 2 * lane; k < kpair; k += 64) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(a + k));
+      const double2 b = __ldg(reinterpret_cast<const double2*>(beta + k));
+      acc0 = fma(v.x, b.x, acc0);
+      acc1 = fma(v.y, b.y, acc1);
+    }
+    if ((Kf & 1) && lane == 0) acc0 = fma(__ldg(a + Kf - 1), __ldg(beta + Kf - 1), acc0);
+    double acc = acc0 + acc1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) y[r] = acc + (r < ne ? beta0 : 0.0);
+  }
+}
+
 // out[i][j] = out[j][i] = in[min(i,j)][max(i,j)] / denom: exactly symmetric K x K result (covariance 1/n after the all-reduce)
 __global__ void sym_scale_div_kernel(const double* __restrict__ in, int64_t K, double denom, double* __restrict__ out) {
   const int64_t total = K * K;

@@ -7,14 +7,16 @@ from . import _lib
 from ._lib import PLB200Error, finalize, init, last_timing, launch_count
 from .data import (Configuration, DataSet, Energy, ForceDescriptors, Forces, LocalDescriptors, get_energy, get_force_descriptors,
                    get_forces, get_local_descriptors, get_values)
-from .dimred import PCA, ActiveSubspace, DimensionReducer, PCAState, compute_eigen, covariance, fit, fit_, select_eigendirections, transform_
+from .dimred import (PCA, ActiveSubspace, DimensionReducer, PCAState, compute_eigen, covariance, fit, fit_, project, select_eigendirections,
+                     transform_)
 from .dpp import (EllEnsemble, SubsetSelector, get_dpp_mode, get_inclusion_prob, get_random_subset, greedy_subset, inclusion_prob, kDPP,
                   rescale_, sample)
 from .kernels import (RBF, CorrelationMatrix, Diagonal, Distance, DotProduct, Euclidean, Feature, GlobalMean, GlobalSum, InverseMultiquadric, Kernel,
                       KernelMatrix, Symmetric,
                       compute_distance, compute_feature, compute_features, compute_kernel, get_parameters, gram_tile_coords,
                       kernel_matrix_dev)
-from .learning import (CovariateLinearProblem, LinearProblem, UnivariateLinearProblem, assemble_matrices, learn_, normal_equations,
-                       ols_sums, ooc_learn_, pack_rhs, pack_rows)
+from .learning import (CovariateLinearProblem, LinearBasisPotential, LinearProblem, UnivariateLinearProblem, assemble_matrices,
+                       get_all_energies, get_all_forces, learn_, learn_potential_, normal_equations, ols_sums, ooc_learn_, pack_rhs,
+                       pack_rows, predict)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

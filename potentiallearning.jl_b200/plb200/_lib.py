@@ -40,6 +40,8 @@ PROTOTYPES = {
     "pl_gram_cross": (_int, [_int, _dp, _i64, _i64, _dp, _i64, _i64, _i64, _int, _int, _dp, _dbl, _dbl, _dp, _i64]),
     "pl_normal_eq": (_int, [_dp, _i64, _i64, _i64, _dp, _i64, _dbl, _dbl, _dp, _int, _dbl, _dp, _dp]),
     "pl_cov": (_int, [_dp, _i64, _i64, _i64, _dp, _int, _int, _dp]),
+    "pl_predict": (_int, [_dp, _i64, _i64, _i64, _dp, _dbl, _i64, _dp]),
+    "pl_predict_dev": (_int, [_vp, _i64, _i64, _i64, _vp, _dbl, _i64, _vp, _vp]),
     "pl_gram_dev": (_int, [_int, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _int, _vp, _dbl, _dbl, _vp, _i64, _int, _int, _int, _int, _vp]),
     "pl_gram_tile_count": (_i64, [_i64, _i64, _int, _int]),
     "pl_gram_tile_coords": (_int, [_i64, _i64, _int, _int, _i64, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),

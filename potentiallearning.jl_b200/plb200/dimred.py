@@ -122,24 +122,45 @@ def fit_(ds: DataSet, pca: PCAState, use_force_descriptors: bool = False):
     return None
 
 
+def project(X, W, shift=None):
+    """(X - shift) · W on the GPU: X rows x K, W K x p. Runs on the LINEAR epilogue of the Gram engine (X · (Wᵀ)ᵀ); the shift is
+    applied as X·W - shift·W, exact to ~|shift|/σ ulps. The 128-wide output tile is wasteful for small p — the dedicated
+    skinny-N tile is future work — but the rows never leave the device path."""
+    from .kernels import KernelMatrix, _Linear
+
+    X = _lib.as_f64(X)
+    Wt = np.ascontiguousarray(np.asarray(W, dtype=np.float64).T)
+    Y = KernelMatrix(X, Wt, _Linear())
+    if shift is not None:
+        Y = Y - np.asarray(shift, dtype=np.float64) @ np.asarray(W, dtype=np.float64)
+    return Y
+
+
 def transform_(ds: DataSet, dr: PCAState):
-    """transform!(ds, dr) (pca_state.jl:42-62): W'(l - m/natoms_first) per atom, W'(fc - m) per force-descriptor row.
-    Host-side here (a 'next' row of SURVEY.md section 8f: tall-skinny projection over the same rows)."""
+    """transform!(ds, dr) (pca_state.jl:42-62): W'(l - m/natoms_first) per atom, W'(fc - m) per force-descriptor row
+    (SURVEY.md 8f row f3). The projections run on the GPU (`project`); the per-configuration re-wrapping stays on the host."""
     W = np.asarray(dr.W)
     m = np.asarray(dr.m)
     new = []
     try:
         ldc = [get_values(get_local_descriptors(c)) for c in ds]
         ml = m / ldc[0].shape[0]  # pca_state.jl:45: length(ldc[1]) = natoms of the FIRST configuration
-        for c, ld in zip(ds, ldc):
-            new.append(c + Configuration(LocalDescriptors((ld - ml) @ W)))
+        counts = [l.shape[0] for l in ldc]
+        Y = project(np.concatenate(ldc, axis=0), W, ml)
+        off = 0
+        for c, n in zip(ds, counts):
+            new.append(c + Configuration(LocalDescriptors(Y[off:off + n])))
+            off += n
     except KeyError:
         new = list(ds)
     try:
-        out = []
-        for c in new:
-            fd = get_values(get_force_descriptors(c))
-            out.append(c + Configuration(ForceDescriptors((fd - m) @ W)))
+        fds = [get_values(get_force_descriptors(c)) for c in new]
+        Yf = project(np.concatenate([fd.reshape(-1, fd.shape[2]) for fd in fds], axis=0), W, m)
+        out, off = [], 0
+        for c, fd in zip(new, fds):
+            n = fd.shape[0] * 3
+            out.append(c + Configuration(ForceDescriptors(Yf[off:off + n].reshape(fd.shape[0], 3, -1))))
+            off += n
         new = out
     except KeyError:
         pass

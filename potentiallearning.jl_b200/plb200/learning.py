@@ -240,3 +240,54 @@ def ooc_learn_(lb_beta: np.ndarray, configs, ws=(30.0, 1.0), symmetrize=True, λ
     print(f"condition number of AtWA: {np.linalg.cond(AtWA)}")
     lb_beta[:] = β
     return AtWA, AtWb
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# after the fit: learn!(lb, ds, args...) wrapper and predictions
+# ----------------------------------------------------------------------------------------------------------------
+class LinearBasisPotential:
+    """Stand-in for InteratomicPotentials.LinearBasisPotential ([external]): only the coefficient storage the hot path
+    touches (β, β0). The descriptor basis itself (ACE/SNAP evaluation) stays in InteratomicPotentials.jl."""
+
+    def __init__(self, dim: int = 0):
+        self.β = np.zeros(dim)
+        self.β0 = np.zeros(1)
+
+
+def learn_potential_(lb: LinearBasisPotential, ds: DataSet, *args, **kw):
+    """learn!(lb::LinearBasisPotential, ds::DataSet, args...) (linear-learning-problem.jl:158-170)."""
+    lp = LinearProblem(ds)
+    learn_(lp, *args, **kw)
+    lb.β = np.resize(lb.β, len(lp.β))  # resize!(lb.β, length(lp.β))
+    lb.β[:] = lp.β
+    lb.β0[:] = lp.β0
+    return lp
+
+
+def predict(A, beta, beta0=0.0, n_energy_rows=0):
+    """GPU evaluation y = A·β + β0·[r < n_energy_rows] over packed rows (pl_predict)."""
+    A = _lib.as_f64(A)
+    R, K = A.shape
+    beta = _lib.as_f64(beta)
+    if beta.shape != (K,):
+        raise ValueError("DimensionMismatch: β does not match the descriptor length")
+    y = np.empty(R)
+    _lib.check(_lib.lib().pl_predict(_lib.dptr(A), R, K, K, _lib.dptr(beta), float(beta0), int(n_energy_rows), _lib.dptr(y)), "pl_predict")
+    return y
+
+
+def get_all_energies(ds: DataSet, lb: LinearBasisPotential | None = None):
+    """get_all_energies(ds) / get_all_energies(ds, lb) (src/Data/utils.jl:10-15, 42-49): reference energies, or the
+    model's B·β + β0 with B the per-configuration global-sum descriptors."""
+    if lb is None:
+        return [get_values(get_energy(c)) for c in ds]
+    B = np.stack([np.add.reduce(get_values(get_local_descriptors(c)), axis=0) for c in ds])
+    return predict(B, lb.β, lb.β0[0], B.shape[0])
+
+
+def get_all_forces(ds: DataSet, lb: LinearBasisPotential | None = None):
+    """get_all_forces(ds) / get_all_forces(ds, lb) (src/Data/utils.jl:24-30, 58-65): flattened forces, or dB·β."""
+    if lb is None:
+        return np.concatenate([get_values(get_forces(c)).reshape(-1) for c in ds])
+    dB = np.concatenate([get_values(get_force_descriptors(c)).reshape(-1, len(lb.β)) for c in ds], axis=0)
+    return predict(dB, lb.β, 0.0, 0)

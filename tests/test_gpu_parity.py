@@ -591,3 +591,39 @@ def test_c_abi_layouts_and_errors(pl, orc):
     assert lib.pl_gram_dot(_lib.dptr(X), 0, d, d, 2, _lib.dptr(K0), 4, 3) == 0
     t = pl.last_timing()
     assert set(t) == {"kernel_ms", "h2d_ms", "d2h_ms"} and pl.launch_count() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# after the fit: predictions and the PCAState projection
+# ---------------------------------------------------------------------------------------------------------------
+def test_predictions_and_transform(pl, orc):
+    rng = np.random.default_rng(91)
+    d, nat, ncfg = 8, 20, 30
+    ds = fake_dataset(pl, rng, ncfg, nat, d, energies=True, forces=True)
+    lb = pl.LinearBasisPotential(d)
+    lp = pl.learn_potential_(lb, ds, [100.0, 1.0], True, λ=0.01)  # learn!(lb, ds, ws, int) (linear-learning-problem.jl:158-170)
+    assert np.array_equal(lb.β, lp.β) and np.array_equal(lb.β0, lp.β0)  # linear_tests.jl:106-107
+    e_pred = pl.get_all_energies(ds, lb)
+    f_pred = pl.get_all_forces(ds, lb)
+    B = np.stack(lp.B)
+    dB = np.concatenate([m.T for m in lp.dB])
+    assert np.allclose(e_pred, B @ lb.β + lb.β0[0], rtol=1e-13, atol=1e-13)
+    assert np.allclose(f_pred, dB @ lb.β, rtol=1e-12, atol=1e-13)
+    assert np.array_equal(pl.get_all_forces(ds), np.concatenate(lp.f)) and pl.get_all_energies(ds) == lp.e
+    for R, K in ((1, 1), (1000, 7), (5000, 500)):
+        A = rng.standard_normal((R, K))
+        beta = rng.standard_normal(K)
+        y = pl.predict(A, beta, 0.25, R // 3)
+        ref = A @ beta + np.concatenate([0.25 * np.ones(R // 3), np.zeros(R - R // 3)])
+        assert np.max(np.abs(y - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref)))
+    # transform!(ds, pca) (pca_state.jl:42-62) against the formula evaluated on the host
+    st = pl.PCAState(tol=3)
+    pl.fit_(ds, st)
+    ld0 = [pl.get_values(pl.get_local_descriptors(c)).copy() for c in ds]
+    fd0 = [pl.get_values(pl.get_force_descriptors(c)).copy() for c in ds]
+    pl.transform_(ds, st)
+    ml = st.m / nat
+    for c, l, f in zip(ds, ld0, fd0):
+        assert np.allclose(pl.get_values(pl.get_local_descriptors(c)), (l - ml) @ st.W, rtol=1e-11, atol=1e-12)
+        assert np.allclose(pl.get_values(pl.get_force_descriptors(c)), (f - st.m) @ st.W, rtol=1e-11, atol=1e-12)
+        assert pl.get_values(pl.get_local_descriptors(c)).shape == (nat, 3)
