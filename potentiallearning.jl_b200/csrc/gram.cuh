@@ -50,6 +50,7 @@ struct GramParams {
   int alpha;            // DOT power
   double s;             // RBF: -0.5 / ell^2 ; IMQ: 1 / ell^2
   double beta;          // RBF scale ; IMQ: c^2
+  double lnbeta, bmul;  // RBF: beta > 0 -> (ln beta, 1): the scale is folded into the exponent; else (0, beta)
   int T1, T2;           // tile rows / tile cols
   int64_t ntiles_total; // linear tile slots (symmetric: folded enumeration incl. a few invalid slots)
   int part, nparts;     // tile sharding across GPUs: slot l is ours iff l % nparts == part
@@ -133,12 +134,16 @@ __device__ __forceinline__ double exp_fast(double x) {
   return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 // Whole-range wrapper, still branch free (a per-element branch to a slow path stops the compiler from interleaving the
-// 64 independent exp chains of a thread, which left the FP64 pipe ~25% utilised in the epilogue): arguments below -708
-// (results under 3.3e-308, i.e. denormal or zero in the reference) flush to 0, arguments above 709 saturate at exp(709).
+// independent exp chains of a thread, which left the FP64 pipe ~25% utilised in the epilogue): arguments below -708
+// (results under 3.3e-308, i.e. denormal or zero in the reference) flush to 0 with an INTEGER compare + selects (every
+// FP64-pipe instruction here is time taken from the DMMAs: scalar FP64 and DMMA share one pipe).
+// Arguments above 709 cannot occur for an RBF kernel (x = -0.5 d2/ell^2 + ln(beta) with d2 >= 0); they are not clamped.
 __device__ __forceinline__ double exp_clamped(double x) {
-  const double xc = fmin(fmax(x, -708.0), 709.0);
-  const double e = exp_fast(xc);
-  return x < -708.0 ? 0.0 : e;
+  const double e = exp_fast(x);
+  // x <= -708.0 tested on the integer pipe: for negative doubles the magnitude grows with the unsigned bit pattern, and
+  // -708.0 is 0xC086200000000000 (NaN arguments also land here and give 0 rather than NaN; d2 is never NaN for finite input)
+  const bool tiny = (unsigned)__double2hiint(x) >= 0xC0862000u;
+  return __hiloint2double(tiny ? 0 : __double2hiint(e), tiny ? 0 : __double2loint(e));
 }
 
 // Fused epilogue of one warp tile. GENERAL = false: interior, off-diagonal tile (97% of the tiles of a large matrix):
@@ -146,7 +151,7 @@ __device__ __forceinline__ double exp_clamped(double x) {
 //   rel0: (j - i) of accumulator (0,0,0) for diagonal tiles (elements with j < i are produced by mirroring, j == i is the
 //         kernel diagonal), 4096 otherwise. w1 / w2: write the direct / mirrored position; in diagonal tiles both
 //         positions are always written and hold 0 when their triangle was not requested (zeros(n,n) storage).
-template <int EPI, bool GENERAL, int ALPHA /* DotProduct power: 1, 2, or 0 = general (runtime p.alpha) */>
+template <int EPI, bool GENERAL, int ALPHA /* 2: DotProduct power 2 / RBF scale folded; 0: general (runtime p.alpha, p.bmul) */>
 __device__ __forceinline__ void gram_epilogue(const double (&acc)[4][8][2], const GramParams& p, int64_t i0, int64_t j0, int rel0, bool w1, bool w2,
                                               double* __restrict__ prow, double* __restrict__ pcol, int64_t ldo) {
   unsigned imask = 0xfu;
@@ -159,7 +164,7 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[4][8][2], cons
       if (!ok) imask &= ~(1u << mt);
     }
     const double r = (EPI != EPI_LINEAR && ok) ? __ldg(p.ra + i0 + 8 * mt) : 0.0;
-    sa[mt] = (EPI == EPI_RBF || EPI == EPI_IMQ) ? p.s * r : r;
+    sa[mt] = (EPI == EPI_RBF) ? fma(p.s, r, p.lnbeta) : (EPI == EPI_IMQ ? p.s * r : r);  // RBF: beta*exp(x) = exp(x + ln beta)
   }
   const double m2s = -2.0 * p.s;
   // k(x,x): beta for RBF (d2 == 0), c2^(-1/2) for IMQ, n/sqrt(n*n) = 1 for DotProduct
@@ -190,7 +195,8 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[4][8][2], cons
             else if (ALPHA == 0) x = ipow_general(x, p.alpha);
           } else if (EPI == EPI_RBF) {
             // arg = s*(q_i + q_j - 2 G_ij) = -0.5 d2 / ell^2  (kernels.jl:73-74 with distances.jl:59 expanded)
-            x = exp_clamped(fma(x, m2s, fma(p.s, r, sa[mt]))) * p.beta;
+            x = exp_clamped(fma(x, m2s, fma(p.s, r, sa[mt])));
+            if (ALPHA == 0) x *= p.bmul;  // only for beta <= 0; for beta > 0 the scale is folded into the exponent (bmul == 1)
           } else if (EPI == EPI_IMQ) {
             // (c2 + d2/ell^2)^(-1/2)  (kernels.jl:156-164): d2/ell^2 = s*(q_i + q_j - 2 G_ij) with s = 1/ell^2
             x = rsqrt(p.beta + fma(x, m2s, fma(p.s, r, sa[mt])));
@@ -378,7 +384,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool interior = ((int64_t)(ti + 1) * GRAM_BM <= p.n1) && ((int64_t)(tj + 1) * GRAM_BN <= p.n2);
     const int rel0 = diag_tile ? (jl0 - il0) : 4096;
     const bool w1 = f1 || diag_tile, w2 = diag_tile ? true : f2;
-    if (EPI == EPI_DOT && p.alpha != 2) {  // uncommon powers: one general instantiation (alpha = 1 included)
+    // ALPHA doubles as the "uncommon parameters" switch: DotProduct power != 2, or an RBF scale beta <= 0 that cannot be
+    // folded into the exponent: one general instantiation
+    const bool common = (EPI == EPI_DOT) ? (p.alpha == 2) : (EPI == EPI_RBF ? (p.bmul == 1.0) : true);
+    if (!common) {
       gram_epilogue<EPI, true, 0>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo);
     } else if (interior && !diag_tile) {
       gram_epilogue<EPI, false, 2>(acc, p, i0, j0, 0, f1, f2, prow, pcol, ldo);

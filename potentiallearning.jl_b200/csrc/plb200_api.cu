@@ -66,6 +66,7 @@ enum WsSlot {
   WS_PADC,
   WS_SYRK_TILES,
   WS_SYRK_VEC,
+  WS_SYRK_RHO,
   WS_H_IN1,
   WS_H_IN2,
   WS_H_IN3,
@@ -220,6 +221,8 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   p.alpha = L.alpha;
   p.s = L.s;
   p.beta = L.beta;
+  p.lnbeta = (L.epi == EPI_RBF && L.beta > 0.0) ? log(L.beta) : 0.0;
+  p.bmul = (L.epi == EPI_RBF && L.beta > 0.0) ? 1.0 : L.beta;
   p.T1 = (int)((L.nA + GRAM_BM - 1) / GRAM_BM);
   p.T2 = (int)((L.nB + GRAM_BN - 1) / GRAM_BN);
   p.tcol_begin = L.tcol_begin;
@@ -440,7 +443,9 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
   choose_splits(R, p.ntiles, &p.splits, &p.rows_per_split);
   void *wst, *wsv = nullptr;
   PL_TRY(ws_get(WS_SYRK_TILES, (size_t)p.splits * p.ntiles * SYRK_TILE_ELEMS * 8, &wst));
-  if (p.want_vec) PL_TRY(ws_get(WS_SYRK_VEC, (size_t)p.splits * 2 * p.T * SYRK_BT * 8, &wsv));
+  void* rho = nullptr;
+  if (p.want_vec || dmean) PL_TRY(ws_get(WS_SYRK_VEC, (size_t)p.splits * 2 * p.T * SYRK_BT * 8, &wsv));
+  if (dmean) PL_TRY(ws_get(WS_SYRK_RHO, (size_t)Kf * 8, &rho));
   p.ws_tiles = (double*)wst;
   p.ws_vec = (double*)wsv;
 
@@ -450,14 +455,19 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
   dim3 grid((unsigned)p.ntiles, (unsigned)p.splits);
   MAIN_KERNEL_BEGIN(st);
   if (dmean)
-    syrk_kernel<true, false><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, p);
+    syrk_kernel<true, true><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, p);  // VEC: the rho vector of the one-sided centring
   else if (p.want_vec)
     syrk_kernel<false, true><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, p);
   else
     syrk_kernel<false, false><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, p);
   LAUNCH_CHECK();
   MAIN_KERNEL_END(st);
-  syrk_reduce_kernel<<<dim3((unsigned)p.ntiles, 8), 256, 0, st>>>(p.ws_tiles, p.ws_vec, p.T, p.ntiles, p.splits, Kf, dS, dvec, p.want_vec);
+  if (dmean) {
+    syrk_rho_kernel<<<(unsigned)((Kf + 127) / 128), 128, 0, st>>>(p.ws_vec, p.T, p.splits, Kf, (double*)rho);
+    LAUNCH_CHECK();
+  }
+  syrk_reduce_kernel<<<dim3((unsigned)p.ntiles, 8), 256, 0, st>>>(p.ws_tiles, p.ws_vec, p.T, p.ntiles, p.splits, Kf, dS, dvec, p.want_vec, dmean,
+                                                                  (const double*)rho);
   LAUNCH_CHECK();
   if (p.want_vec) {
     syrk_scalar_kernel<<<1, 1024, 0, st>>>(dw, db, ne, w_e, dvec + 2 * Kf);
@@ -550,7 +560,7 @@ int pl_init(int device) {
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_IMQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
   g.ready = true;
   return PL_OK;
 }

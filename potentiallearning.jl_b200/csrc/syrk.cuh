@@ -20,7 +20,11 @@
 //     one k4-step. The contraction index is permuted (MMA k <-> stage row 2t+par), which together with the 128B
 //     swizzle makes every quarter-warp hit 8 distinct 16-byte chunks (conflict-free);
 //   * the per-row weight (and the mean subtraction) is applied to the A fragment in registers: the weighted /
-//     centred matrix never exists in memory.
+//     centred matrix never exists in memory. Centring is ONE-SIDED: S'_ij = sum_r (a_ri - m_i) a_rj is accumulated and the
+//     second stage subtracts rho_i m_j with rho_i = sum_r (a_ri - m_i) (accumulated exactly like the moment vectors). This
+//     equals sum_r (a_ri - m_i)(a_rj - m_j) without the 8 extra FP64 subtractions per k4-step on the B fragments (scalar
+//     FP64 shares the pipe with the DMMAs); the terms are |sigma*m| instead of sigma^2, an error of order eps*(m/sigma)
+//     relative to the largest entry in the worst case, far inside the 1e-10 contract even at mean/sigma = 50.
 #pragma once
 #include "ptx.cuh"
 
@@ -171,7 +175,7 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
   const bool do_vec = VEC && WB.vec;
 
   // column means of this thread's fragment columns
-  double mi[2][2], mj[4][2];
+  double mi[2][2];
   if (CENTER) {
 #pragma unroll
     for (int bx = 0; bx < 2; ++bx)
@@ -179,13 +183,6 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
       for (int e = 0; e < 2; ++e) {
         const int64_t col = (int64_t)WB.cb_a * SYRK_BT + 32 * wm + 16 * bx + 2 * g + e;
         mi[bx][e] = col < p.Kf ? __ldg(p.mean + col) : 0.0;
-      }
-#pragma unroll
-    for (int bx = 0; bx < 4; ++bx)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int64_t col = (int64_t)WB.cb_b * SYRK_BT + 64 * wn + 16 * bx + 2 * g + e;
-        mj[bx][e] = col < p.Kf ? __ldg(p.mean + col) : 0.0;
       }
   }
 
@@ -225,7 +222,7 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
         wv[h][par] = w;
         if (VEC) {
           bv[h][par] = (ok && p.b) ? __ldg(p.b + r) : 0.0;
-          cv[h][par] = (ok && r < p.ne) ? 1.0 : 0.0;
+          cv[h][par] = (ok && (CENTER || r < p.ne)) ? 1.0 : 0.0;  // centred mode: rho = sum over ALL rows of (a - m)
         }
       }
 
@@ -248,11 +245,6 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
             a[bx].x -= mi[bx][0];
             a[bx].y -= mi[bx][1];
           }
-#pragma unroll
-          for (int bx = 0; bx < 4; ++bx) {
-            b[bx].x -= mj[bx][0];
-            b[bx].y -= mj[bx][1];
-          }
         }
         if (need_w) {
           const double w = wv[h][par];
@@ -267,8 +259,10 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
             const double bb = bv[h][par], cc = cv[h][par];
 #pragma unroll
             for (int bx = 0; bx < 2; ++bx) {
-              vb[bx][0] = fma(a[bx].x, bb, vb[bx][0]);
-              vb[bx][1] = fma(a[bx].y, bb, vb[bx][1]);
+              if (!CENTER) {  // centred mode has no right-hand side: only rho (the c slot) is accumulated
+                vb[bx][0] = fma(a[bx].x, bb, vb[bx][0]);
+                vb[bx][1] = fma(a[bx].y, bb, vb[bx][1]);
+              }
               vc[bx][0] = fma(a[bx].x, cc, vc[bx][0]);
               vc[bx][1] = fma(a[bx].y, cc, vc[bx][1]);
             }
@@ -345,8 +339,11 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
 //   mt = a>>4, nt = (a>>1)&7, c = a&1
 //   i = 128 cb_a + 32 wm + 16 (mt>>1) + 2 g + (mt&1)
 //   j = 128 cb_b + 64 wn + 16 (nt>>1) + 4 t + 2 c + (nt&1)
+// Centred mode (mean != NULL): rho (the reduced "c" vector, K doubles, produced by syrk_rho_kernel first) closes the
+// one-sided centring: S_ij = S'_ij - rho_i * m_j.
 __global__ void syrk_reduce_kernel(const double* __restrict__ ws_tiles, const double* __restrict__ ws_vec, int T, int ntiles,
-                                   int splits, int64_t Kf, double* __restrict__ S, double* __restrict__ vec, int want_vec) {
+                                   int splits, int64_t Kf, double* __restrict__ S, double* __restrict__ vec, int want_vec,
+                                   const double* __restrict__ mean, const double* __restrict__ rho) {
   const int unit = blockIdx.x;
   for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < SYRK_TILE_ELEMS; e += gridDim.y * blockDim.x) {
     const int a = e >> 8;
@@ -362,6 +359,7 @@ __global__ void syrk_reduce_kernel(const double* __restrict__ ws_tiles, const do
     if (j < i) continue;  // diagonal blocks: keep j >= i, mirror (weights are applied to one operand only)
     double sum = 0.0;
     for (int sp = 0; sp < splits; ++sp) sum += ws_tiles[((int64_t)sp * ntiles + unit) * SYRK_TILE_ELEMS + e];
+    if (mean) sum = fma(-rho[i], mean[j], sum);
     S[i * Kf + j] = sum;
     S[j * Kf + i] = sum;
   }
@@ -378,6 +376,15 @@ __global__ void syrk_reduce_kernel(const double* __restrict__ ws_tiles, const do
       vec[Kf + col] = sc;
     }
   }
+}
+
+// rho[col] = sum over splits (fixed order) of the "c" moment vector: rho_i = sum_r (a_ri - m_i) in centred mode
+__global__ void syrk_rho_kernel(const double* __restrict__ ws_vec, int T, int splits, int64_t Kf, double* __restrict__ rho) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= Kf) return;
+  double s = 0.0;
+  for (int sp = 0; sp < splits; ++sp) s += ws_vec[(int64_t)sp * 2 * T * SYRK_BT + (int64_t)T * SYRK_BT + col];
+  rho[col] = s;
 }
 
 // s[0] = sum_{r<ne} w_r, s[1] = sum_{r<ne} w_r b_r  (one block, fixed-order tree: deterministic)

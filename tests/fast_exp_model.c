@@ -26,9 +26,11 @@ static double exp_fast(double x) {
 }
 
 double exp_clamped_model(double x) {
-  const double xc = fmin(fmax(x, -708.0), 709.0);
-  const double e = exp_fast(xc);
-  return x < -708.0 ? 0.0 : e;
+  const double e = exp_fast(x);
+  uint64_t bits;
+  memcpy(&bits, &x, 8);
+  const int tiny = (uint32_t)(bits >> 32) >= 0xC0862000u; /* x <= -708.0 (or NaN with the sign bit): integer compare as in the kernel */
+  return tiny ? 0.0 : e;
 }
 
 /* max relative error against long double expl over n points uniformly spread on [lo, hi] */
