@@ -59,30 +59,36 @@ def rescale_(ell: EllEnsemble, k: int):
     return ell
 
 
-def _esp(lam, k):
-    """E[l, n] = e_l(λ_1..λ_n), elementary symmetric polynomials (Kulesza & Taskar Alg. 7)."""
+def _log_esp(lam, k):
+    """logE[l, n] = log e_l(λ_1..λ_n), elementary symmetric polynomials (Kulesza & Taskar Alg. 7) in the log domain:
+    with hundreds of items e_k spans hundreds of orders of magnitude and under/overflows in plain floating point."""
     N = len(lam)
-    E = np.zeros((k + 1, N + 1))
-    E[0, :] = 1.0
-    for l in range(1, k + 1):
-        for n in range(1, N + 1):
-            E[l, n] = E[l, n - 1] + lam[n - 1] * E[l - 1, n - 1]
-    return E
+    with np.errstate(divide="ignore"):
+        loglam = np.log(lam)
+    E = np.full((k + 1, N + 1), -np.inf)
+    E[0, :] = 0.0
+    for n in range(1, N + 1):
+        E[1:, n] = np.logaddexp(E[1:, n - 1], loglam[n - 1] + E[:-1, n - 1])
+    return E, loglam
 
 
 def sample(ell: EllEnsemble, k: int, rng=None):
     """Determinantal.sample(L, k): exact k-DPP sample (Kulesza & Taskar Alg. 8 + Alg. 1). Returns sorted 0-based indices."""
     rng = np.random.default_rng() if rng is None else rng
-    lam = ell.α * ell.λ
-    lam = lam / lam.max()  # e_k ratios are scale-invariant after normalising; avoids overflow
+    lam = np.maximum(ell.α * ell.λ, 0.0)
     N = len(lam)
-    E = _esp(lam, k)
+    E, loglam = _log_esp(lam, k)
     J = []
     l = k
     for n in range(N, 0, -1):
         if l == 0:
             break
-        if rng.random() < lam[n - 1] * E[l - 1, n - 1] / E[l, n]:
+        if l == n:  # every remaining eigenvector is needed
+            J.extend(range(n - 1, -1, -1))
+            l = 0
+            break
+        logp = loglam[n - 1] + E[l - 1, n - 1] - E[l, n]
+        if np.log(rng.random()) < logp:
             J.append(n - 1)
             l -= 1
     V = ell.U[:, J].copy()

@@ -167,6 +167,39 @@ if "c5" in cfgs:
         del tiles
     del X
 
+# ---- CPU legs on the box's host cores (rank 0, single-GPU run only): the reference's own formulation on a bounded sample ----
+if world == 1 and rank == 0 and "cpu" in cfgs:
+    import time
+
+    from oracle import oracle as orc
+
+    orc.build_c()
+    ncores = os.cpu_count()
+    rng = np.random.default_rng(7)
+    # C3: A'*(Q*A) exactly as linear-learn.jl:253 forms it (Q*A materialised, one BLAS gemm on all cores), 1/20 of the rows
+    Rs, K = 144_500, 500
+    A = rng.standard_normal((Rs, K))
+    q = np.concatenate([100.0 * np.ones(500), np.ones(Rs - 500)])
+    t0 = time.perf_counter()
+    M = A.T @ (q[:, None] * A)
+    dt = time.perf_counter() - t0
+    out["c3_cpu_reference_shaped"] = {"rows_per_s": Rs / dt, "tflops(RK(K+1))": Rs * K * (K + 1) / dt / 1e12, "cores": ncores, "kind": "port",
+                                      "sample": f"{Rs} of 2 890 000 rows: Q*A materialised then OpenBLAS dgemm A'*(QA) (numpy), {dt:.2f} s"}
+    # C4: the reference's per-row outer-product sum (dimension_reduction.jl:12), single thread, 1 500 rows x K = 1000
+    n4, K4 = 1500, 1000
+    X = 10.0 * rng.standard_normal(K4) + rng.standard_normal((n4, K4))
+    t0 = time.perf_counter()
+    orc.second_moment(X, use_c=True)
+    dt = time.perf_counter() - t0
+    out["c4_cpu_reference_shaped"] = {"rows_per_s": n4 / dt, "tflops(nK(K+1))": n4 * K4 * (K4 + 1) / dt / 1e12, "cores": 1, "kind": "port",
+                                      "sample": f"{n4} of 10^7 rows: sequential sum of K x K outer products (oracle/pl_oracle.c orc_outer_sum), {dt:.2f} s; "
+                                                "the reference form allocates one K x K temporary per row (80 TB at full size)"}
+    t0 = time.perf_counter()
+    Xc = X - X.mean(0)
+    C = Xc.T @ Xc / n4
+    dt = time.perf_counter() - t0
+    out["c4_cpu_strong_blas"] = {"rows_per_s": n4 / dt, "cores": ncores, "sample": f"numpy two-pass centred X'X/n on {n4} rows, {dt:.3f} s"}
+
 out["launches"] = plb200.launch_count()
 if rank == 0:
     print(json.dumps(out))

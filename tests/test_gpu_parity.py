@@ -627,3 +627,102 @@ def test_predictions_and_transform(pl, orc):
         assert np.allclose(pl.get_values(pl.get_local_descriptors(c)), (l - ml) @ st.W, rtol=1e-11, atol=1e-12)
         assert np.allclose(pl.get_values(pl.get_force_descriptors(c)), (f - st.m) @ st.W, rtol=1e-11, atol=1e-12)
         assert pl.get_values(pl.get_local_descriptors(c)).shape == (nat, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configurations at (or near) full size through size-independent properties
+# ---------------------------------------------------------------------------------------------------------------
+def test_config1_kdpp_full_size(pl, orc):
+    """BASELINE config 1: kDPP(ds, GlobalMean(), DotProduct()), N = 1 000 configurations x 26-dim descriptors
+    (examples/DPP-ACE-Si shape). K is compared entry by entry with the restated pair loop; the selector is exercised end to end.
+    A degree-2 polynomial kernel of 26-dim features has rank <= 26*27/2 = 351, so the batch size must stay below that."""
+    rng = np.random.default_rng(1001)
+    n, nat, d = 1000, 32, 26
+    mu = 2.0 * rng.standard_normal(d)
+    ds = pl.DataSet([pl.Configuration(pl.LocalDescriptors(mu + rng.standard_normal((nat, d)))) for _ in range(n)])
+    with pytest.raises(ValueError, match="numerical rank"):
+        pl.kDPP(ds[0:400], pl.GlobalMean(), pl.DotProduct(), batch_size=380)
+    dpp = pl.kDPP(ds, pl.GlobalMean(), pl.DotProduct(), batch_size=200)
+    F = np.stack(pl.compute_features(ds, pl.GlobalMean()))
+    ref = orc.symmetric(orc.kernel_matrix(F, orc.DotProduct()))
+    assert relerr(dpp.K.L, ref) < RTOL and np.array_equal(dpp.K.L, dpp.K.L.T)
+    assert abs(pl.get_inclusion_prob(dpp).sum() - 200.0) < 1e-6
+    sub = pl.get_random_subset(dpp, rng=np.random.default_rng(0))
+    assert len(sub) == len(set(sub)) == 200 and min(sub) >= 0 and max(sub) < n
+    # same eigendecomposition input (K within 1e-11) + same seed -> same indices as a selector built on the oracle's K
+    ell_ref = pl.EllEnsemble(ref)
+    pl.rescale_(ell_ref, 200)
+    assert pl.sample(ell_ref, 200, rng=np.random.default_rng(0)) == sub
+
+
+def test_config3_full_size_checksums(pl):
+    """BASELINE config 3 at full size (R = 2 890 000, K = 500, 11.56 GB): trace(A'WA) = sum_r w_r |a_r|^2, A'W1 column sums and
+    A'Wb against independent fp64 torch reductions; exact symmetry; linearity across a 2-way row split."""
+    import torch
+
+    from plb200.device import DeviceEngine
+
+    eng = DeviceEngine()
+    ncfg, natoms, K = 10000, 96, 500
+    ne, nf = ncfg, ncfg * 3 * natoms
+    g = torch.Generator(device="cuda").manual_seed(1003)
+    A = torch.empty((ne + nf, K), device="cuda", dtype=torch.float64)
+    for r0 in range(0, ne + nf, 1 << 19):
+        A[r0:r0 + (1 << 19)].normal_(generator=g)
+    A[:ne] *= np.sqrt(96.0)
+    b = torch.randn(ne + nf, device="cuda", dtype=torch.float64, generator=g)
+    we, wf = 100.0, 1.0
+    S, vec = eng.syrk_partial(A, None, ne, we, wf, b, None, True)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(S, S.T))
+    w = torch.cat([torch.full((ne,), we, device="cuda", dtype=torch.float64), torch.full((nf,), wf, device="cuda", dtype=torch.float64)])
+    tr_ref = float(((A * A).sum(1) * w).sum())
+    assert abs(float(torch.trace(S)) - tr_ref) / tr_ref < 1e-12
+    v_ref = torch.zeros(K, device="cuda", dtype=torch.float64)
+    for r0 in range(0, ne + nf, 1 << 19):
+        v_ref += A[r0:r0 + (1 << 19)].T @ (w[r0:r0 + (1 << 19)] * b[r0:r0 + (1 << 19)])
+    assert float((vec[:K] - v_ref).abs().max() / v_ref.abs().max()) < 1e-11
+    c_ref = we * A[:ne].sum(0)
+    assert float((vec[K:2 * K] - c_ref).abs().max() / c_ref.abs().max()) < 1e-12
+    assert abs(float(vec[2 * K]) - we * ne) < 1e-6 and abs(float(vec[2 * K + 1]) - float(we * b[:ne].sum())) < 1e-8
+    half = ne + nf // 2
+    S1, _ = eng.syrk_partial(A[:half], None, ne, we, wf, None, None, False)
+    S2, _ = eng.syrk_partial(A[half:], None, 0, we, wf, None, None, False)
+    assert float(((S1 + S2) - S).abs().max() / S.abs().max()) < 1e-13
+    del A, b, w
+
+
+def test_config4_slice_checksums(pl):
+    """BASELINE config 4 shape (K = 1 000, mean/sigma = 10) on a 1.25 M-row slice (10 GB): mean, trace of the centred covariance
+    and a random 64 x 64 sub-block against independent fp64 torch reductions; mean persistence."""
+    import torch
+
+    from plb200.device import DeviceEngine
+    from plb200.distributed import covariance_sharded
+
+    eng = DeviceEngine()
+    n, K = 1_250_000, 1000
+    g = torch.Generator(device="cuda").manual_seed(1004)
+    shift = 10.0 * torch.randn(K, device="cuda", dtype=torch.float64, generator=g)
+    X = torch.empty((n, K), device="cuda", dtype=torch.float64)
+    for r0 in range(0, n, 1 << 18):
+        X[r0:r0 + (1 << 18)].normal_(generator=g)
+        X[r0:r0 + (1 << 18)] += shift
+    C, m = covariance_sharded(X, n, engine=eng)
+    torch.cuda.synchronize()
+    m_ref = X.sum(0) / n
+    assert float(((m - m_ref).abs() / m_ref.abs()).max()) < 1e-12
+    assert bool(torch.equal(C, C.T))
+    idx = torch.randperm(K, device="cuda", generator=g)[:64]
+    Xs = X[:, idx] - m_ref[idx]
+    blk_ref = (Xs.T @ Xs) / n
+    blk = C[idx][:, idx]
+    assert float((blk - blk_ref).abs().max() / blk_ref.abs().max()) < 1e-11
+    tr_ref = 0.0
+    for r0 in range(0, n, 1 << 18):
+        Y = X[r0:r0 + (1 << 18)] - m_ref
+        tr_ref += float((Y * Y).sum())
+    assert abs(float(torch.trace(C)) - tr_ref / n) / (tr_ref / n) < 1e-12
+    C2, m2 = covariance_sharded(X, n, mean=m, engine=eng)  # pca.m persists (pca_state.jl:34)
+    assert bool(torch.equal(m2, m)) and bool(torch.equal(C2, C))
+    del X
