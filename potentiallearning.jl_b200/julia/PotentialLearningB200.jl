@@ -4,6 +4,7 @@
 # It ONLY adds more specific methods for the signatures below; everything else of PotentialLearning stays as is:
 #   KernelMatrix(F::Vector{Vector{Float64}}, k::DotProduct)                    src/Kernels/kernels.jl:211-223
 #   KernelMatrix(F::Vector{Vector{Float64}}, k::RBF)   (k.d isa Euclidean)     src/Kernels/kernels.jl:211-223
+#   KernelMatrix(F::Vector{Vector{Float64}}, k::InverseMultiquadric)           src/Kernels/kernels.jl:139-164, 211-223
 #   KernelMatrix(F1, F2, k)                                                    src/Kernels/kernels.jl:229-244
 #   learn!(lp::UnivariateLinearProblem, ws::Vector, int::Bool)                 src/Learning/linear-learn.jl:178-215
 #   learn!(lp::CovariateLinearProblem,  ws::Vector, int::Bool; λ)              src/Learning/linear-learn.jl:226-268
@@ -64,6 +65,17 @@ function KernelMatrix(F::Vector{Vector{Float64}}, k::RBF)
     GC.@preserve keep check(ccall((:pl_gram_rbf, libplb200), Cint,
                 (Ptr{Cdouble}, Int64, Int64, Int64, Cint, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cdouble}, Int64, Cint),
                 X, n, d, d, kind, cptr, Float64(k.ℓ), Float64(k.β), K, n, PL_FILL_JULIA_U), "pl_gram_rbf")
+    Symmetric(K)
+end
+
+function KernelMatrix(F::Vector{Vector{Float64}}, k::PotentialLearning.InverseMultiquadric)     # kernels.jl:139-164 (widened row)
+    k.d isa Euclidean || return invoke(KernelMatrix, Tuple{Vector{Vector{Float64}},PotentialLearning.Kernel}, F, k)
+    X = pack(F); d, n = size(X)
+    kind, cptr, keep = cinv_args(k.d)
+    K = zeros(n, n)
+    GC.@preserve keep check(ccall((:pl_gram_imq, libplb200), Cint,
+                (Ptr{Cdouble}, Int64, Int64, Int64, Cint, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cdouble}, Int64, Cint),
+                X, n, d, d, kind, cptr, Float64(k.c2), Float64(k.ℓ), K, n, PL_FILL_JULIA_U), "pl_gram_imq")
     Symmetric(K)
 end
 
