@@ -117,12 +117,53 @@ int pl_gram_part(int kernel_id, const double* X, int64_t n, int64_t d, int64_t l
 int pl_normal_eq(const double* A, int64_t R, int64_t Kf, int64_t lda, const double* w, int64_t n_energy_rows, double w_e,
                  double w_f, const double* b, int add_intercept, double lambda, double* AtWA, double* AtWb);
 
+/* Streamed form over a LIST of host row blocks (direct ingestion of the reference's containers, no host-side
+ * reduce(hcat/vcat) copy). blocks[k] is rows[k] x Kf row-major and dense (ld = Kf): lp.dB[i] (K x 3natoms column-major,
+ * linear-learning-problem.jl:127) and reduce(hcat, lp.B) are passed as they lie in memory. The logical matrix is the concatenation of
+ * the blocks in order; w and b index its R = sum(rows) rows; all other arguments as pl_normal_eq. Rows travel to the device in chunks
+ * of chunk_rows (<= 0: library default, ~512 MB) through two alternating buffers while the SYRK of the previous chunk runs; chunk
+ * partials are accumulated in chunk order (deterministic). Device footprint: two chunks, not R x Kf. */
+int pl_normal_eq_blocks(const double* const* blocks, const int64_t* rows, int64_t nblocks, int64_t Kf, const double* w, int64_t n_energy_rows,
+                        double w_e, double w_f, const double* b, int add_intercept, double lambda, int64_t chunk_rows, double* AtWA,
+                        double* AtWb);
+
+/* ---- GlobalSum / GlobalMean features on the device ("next" row f2 of SURVEY.md 8f) ------------------------ */
+/* locals: the local descriptors of all N configurations stacked, row-major (offsets[N]) x d, leading dimension ldl; configuration i owns
+ * rows [offsets[i], offsets[i+1]) (offsets[0] == 0, strictly increasing). X[i,:] = sum of its rows (mean == 0: compute_feature(B,
+ * ::GlobalSum) features.jl:19-21, sum.(get_values.(...)) linear-learning-problem.jl:75, pca_state.jl:23) or that sum / natoms_i
+ * (mean != 0: ::GlobalMean, features.jl:32-34). Summation order is Julia's (left to right below 1024 atoms, pairwise above). */
+int pl_global_feature(const double* locals, int64_t ldl, const int64_t* offsets, int64_t N, int64_t d, int mean, double* X, int64_t ldx);
+int pl_global_feature_dev(const double* dL, int64_t ldl, const int64_t* doffsets, int64_t N, int64_t d, int mean, double* dX, int64_t ldx,
+                          int64_t total_rows, void* stream);
+
 /* ---- covariance / second moment: replaces compute_eigen's Q (dimension_reduction.jl:11-12) and the
  *      mean/centre of fit!(ds, ::PCAState) (pca_state.jl:34-37) ------------------------------------------ */
 /* X: row-major n x Kf.  center == 0: C = (1/n) sum_r x_r x_r'   (PCA / ActiveSubspace, pca.jl:28, as.jl:25).
  * center != 0: if mean_given == 0, mean_inout <- sum_r x_r / n (pca_state.jl:35), else mean_inout is used as is
  * (pca.m persists, pca_state.jl:34); C = (1/n) sum_r (x_r-m)(x_r-m)'. C: Kf x Kf full, exactly symmetric. */
 int pl_cov(const double* X, int64_t n, int64_t Kf, int64_t ldx, double* mean_inout, int mean_given, int center, double* C);
+
+/* ---- symmetric eigendecomposition and the L-ensemble on the device ("next" row f1 of SURVEY.md 8f) ----------- */
+/* eigen(Symmetric(Q)) (dimension_reduction.jl:13; LAPACK in the reference) and the eigendecomposition inside EllEnsemble(K)
+ * (Determinantal.jl [external], reached from dpp.jl:26,41). The dense solver itself is cuSOLVER's Xsyevd (a library call, as in the
+ * reference), loaded with dlopen at first use (PLB200_CUSOLVER overrides the search path).
+ * A: symmetric n x n, only the `fill` triangle of the row-major view is read. W: n eigenvalues, ascending. V (may be NULL: values only):
+ * ROW k = unit eigenvector k, i.e. Julia's column-major `eigen(...).vectors` (column k) byte for byte. Signs are the solver's. */
+int pl_eigh(const double* A, int64_t n, int64_t lda, int fill, double* W, double* V, int64_t ldv);
+/* in place on device data: dA's rows become the eigenvectors; synchronises the stream (the solver reports through a device flag). */
+int pl_eigh_dev(double* dA, int64_t n, int64_t lda, int fill, int want_vectors, double* dW, void* stream);
+
+/* EllEnsemble(KernelMatrix(F, k)) (dpp.jl:25-26, 40-41) without the kernel matrix ever leaving the GPU: Gram kernel -> in-place
+ * eigendecomposition. lambda: n eigenvalues (ascending). Kout (may be NULL): the kernel matrix in Symmetric(:U) storage (as pl_gram_*
+ * with PL_FILL_JULIA_U; caller passes zeros(n,n)). U and lambda stay RESIDENT in the library until the next pl_ell_ensemble (or pl_finalize). */
+int pl_ell_ensemble(int kernel_id, const double* X, int64_t n, int64_t d, int64_t ldx, int alpha, int cinv_kind, const double* cinv, double ell,
+                    double beta, double* lambda, double* Kout, int64_t ldk);
+/* inclusion_prob of the resident ensemble rescaled by alpha_scale (rescale!, dpp.jl:27): p[i] = sum_k U[i,k]^2 g_k,
+ * g_k = a*lam_k/(1 + a*lam_k) (Determinantal.inclusion_prob, dpp.jl:69). */
+int pl_ell_inclusion_prob(double alpha_scale, int64_t n, double* p);
+/* rows idx[0..m) of the resident eigenvector matrix (the eigenvectors a k-DPP draw selected): V is m x n row-major. Only m*n doubles
+ * cross PCIe instead of n*n. */
+int pl_ell_eigvecs(const int64_t* idx, int64_t m, int64_t n, double* V, int64_t ldv);
 
 /* ---- predictions of the fitted linear model ("next" row f3 of SURVEY.md 8f) ------------------------------ */
 /* y[r] = A[r,:] . beta + (r < n_energy_rows ? beta0 : 0) over the same packed rows as pl_normal_eq: what

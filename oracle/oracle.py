@@ -93,6 +93,36 @@ def global_sum(local_descriptors) -> np.ndarray:
     return s
 
 
+def julia_sum(vals, blksize: int = 1024):
+    """Base.sum over a Vector of vectors = mapreduce_impl(identity, +, A, 1, n, pairwise_blocksize = 1024) (Julia Base
+    reduce.jl, stdlib — not under /root/reference; restated from its published source): fewer than `blksize` elements are
+    added left to right; longer ranges split at imid = ifirst + (ilast - ifirst) >> 1 and the halves are summed recursively.
+    global_sum / global_mean above are the n < 1024 case of this."""
+    vals = [np.asarray(v, dtype=np.float64) for v in vals]
+
+    def impl(lo, hi):  # inclusive, 0-based
+        if lo == hi:
+            return vals[lo].copy()
+        if hi - lo < blksize:
+            v = vals[lo] + vals[lo + 1]
+            for i in range(lo + 2, hi + 1):
+                v = v + vals[i]
+            return v
+        mid = lo + ((hi - lo) >> 1)
+        return impl(lo, mid) + impl(mid + 1, hi)
+
+    return impl(0, len(vals) - 1)
+
+
+def global_features(local_blocks, mean: bool) -> np.ndarray:
+    """compute_features(ds, GlobalMean() / GlobalSum()) (features.jl:76-78 over :19-21 / :32-34): one row per configuration."""
+    rows = []
+    for b in local_blocks:
+        s = julia_sum(list(np.asarray(b, dtype=np.float64)))
+        rows.append(s / len(b) if mean else s)
+    return np.stack(rows)
+
+
 @dataclass
 class Euclidean:
     """Euclidean(dim) / Euclidean(Cinv) (distances.jl:39-51). cinv: None (identity), 1-D (Diagonal) or 2-D (Symmetric)."""

@@ -9,7 +9,7 @@ OUT = os.path.join(HERE, "plb200", "libplb200.so")
 DEPS = [os.path.join(HERE, "csrc", f) for f in ("plb200_api.cu", "gram.cuh", "syrk.cuh", "prelude.cuh", "ptx.cuh")] + [
     os.path.join(HERE, "..", "include", "plb200.h")
 ]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -4,10 +4,13 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
+#include <cusolverDn.h>
+#include <dlfcn.h>
 
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -75,6 +78,21 @@ enum WsSlot {
   WS_H_OUT2,
   WS_H_S,
   WS_H_VEC,
+  WS_FEAT_L,
+  WS_FEAT_OFF,
+  WS_FEAT_X,
+  WS_NE_BUF0,
+  WS_NE_BUF1,
+  WS_NE_SACC,
+  WS_NE_VACC,
+  WS_EIG_A,
+  WS_EIG_W,
+  WS_EIG_WORK,
+  WS_EIG_INFO,
+  WS_EIG_GAMMA,
+  WS_EIG_P,
+  WS_EIG_IDX,
+  WS_EIG_SEL,
   WS_NSLOTS
 };
 
@@ -524,6 +542,217 @@ int finish_timing() {
   return PL_OK;
 }
 
+
+int global_feature_dev_impl(const double* dL, int64_t ldl, const int64_t* doff, int64_t N, int64_t d, int mean, double* dX, int64_t ldx,
+                            int64_t total_rows, cudaStream_t st) {
+  PL_TRY(need_ready());
+  if (N < 0 || d <= 0 || ldl < d || ldx < d || !dL || !doff || !dX) return set_err(PL_EINVAL, "bad arguments");
+  if (N == 0) return PL_OK;
+  const double* L;
+  int64_t ld;
+  PL_TRY(tma_operand(dL, total_rows, d, ldl, WS_PAD1, st, &L, &ld));  // 128-bit loads need 16-byte alignment and an even ld
+  int G = 1;
+  while (G < 32 && 2 * G < d) G <<= 1;
+  const int64_t nchunks = (d + 2 * G - 1) / (2 * G);
+  const int64_t threads = N * nchunks * G;
+  segment_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(L, ld, doff, N, d, G, mean, dX, ldx);
+  LAUNCH_CHECK();
+  return PL_OK;
+}
+
+// offsets must be non-decreasing with non-empty segments (sum / mean of an empty collection throws in the reference)
+int check_offsets(const int64_t* off, int64_t N) {
+  if (off[0] != 0) return set_err(PL_EINVAL, "offsets[0] must be 0");
+  for (int64_t i = 0; i < N; ++i)
+    if (off[i + 1] <= off[i]) return set_err(PL_EINVAL, "configuration %lld has no local descriptors (offsets must increase strictly)", (long long)i);
+  return PL_OK;
+}
+
+// Streamed weighted normal equations over a list of host row blocks: chunks of rows are copied on the copy stream into two
+// alternating device buffers while the SYRK of the previous chunk runs on the compute stream; the unscaled chunk partials are
+// accumulated in chunk order (deterministic), then finished exactly like the resident path.
+int normal_eq_stream(const double* const* blocks, const int64_t* rows, const int64_t* lds, int64_t nblocks, int64_t R, int64_t Kf, const double* w,
+                     int64_t ne, double w_e, double w_f, const double* b, int ic, double lambda, double* AtWA, double* AtWb, int64_t chunk_rows) {
+  const int64_t ldp = (Kf + 1) & ~(int64_t)1;
+  const int64_t n = Kf + ic;
+  const bool want_vec = ic || b;
+  if (chunk_rows > R) chunk_rows = R;
+  if (chunk_rows < 1) chunk_rows = 1;
+  void *buf[2], *dS, *dvec = nullptr, *dSacc, *dVacc = nullptr, *dM, *dv = nullptr;
+  double *dw = nullptr, *db = nullptr;
+  PL_TRY(ws_get(WS_NE_BUF0, (size_t)chunk_rows * ldp * 8, &buf[0]));
+  PL_TRY(ws_get(WS_NE_BUF1, (size_t)(R > chunk_rows ? chunk_rows : 1) * ldp * 8, &buf[1]));
+  PL_TRY(ws_get(WS_H_S, (size_t)Kf * Kf * 8, &dS));
+  PL_TRY(ws_get(WS_NE_SACC, (size_t)Kf * Kf * 8, &dSacc));
+  if (want_vec) {
+    PL_TRY(ws_get(WS_H_VEC, (size_t)(2 * Kf + 2) * 8, &dvec));
+    PL_TRY(ws_get(WS_NE_VACC, (size_t)(2 * Kf + 2) * 8, &dVacc));
+  }
+  PL_TRY(ws_get(WS_H_OUT1, (size_t)n * n * 8, &dM));
+  if (AtWb) PL_TRY(ws_get(WS_H_OUT2, (size_t)n * 8, &dv));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  if (w) PL_TRY(h2d_vector(w, R, WS_H_IN2, &dw));
+  if (b) PL_TRY(h2d_vector(b, R, WS_H_IN3, &db));
+  CUDA_TRY(cudaMemsetAsync(dSacc, 0, (size_t)Kf * Kf * 8, g.stream));
+  if (want_vec) CUDA_TRY(cudaMemsetAsync(dVacc, 0, (size_t)(2 * Kf + 2) * 8, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  // the copy stream must not overwrite buffers an earlier call's kernels may still be reading
+  CUDA_TRY(cudaEventRecord(g.chunk_ev[4], g.stream));
+  CUDA_TRY(cudaStreamWaitEvent(g.copy_stream, g.chunk_ev[4], 0));
+  int64_t blk = 0, blk_row = 0;  // cursor into the block list
+  int64_t r0 = 0;
+  for (int64_t c = 0; r0 < R; ++c) {
+    const int bi = (int)(c & 1);
+    const int64_t nr = R - r0 < chunk_rows ? R - r0 : chunk_rows;
+    if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(g.copy_stream, g.chunk_ev[2 + bi], 0));  // SYRK of chunk c-2 has released the buffer
+    int64_t filled = 0;
+    while (filled < nr) {
+      while (rows[blk] == blk_row) {
+        ++blk;
+        blk_row = 0;
+      }
+      int64_t take = rows[blk] - blk_row;
+      if (take > nr - filled) take = nr - filled;
+      const double* src = blocks[blk] + blk_row * lds[blk];
+      double* dst = (double*)buf[bi] + filled * ldp;
+      if (lds[blk] == Kf && ldp == Kf)
+        CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)take * Kf * 8, cudaMemcpyHostToDevice, g.copy_stream));
+      else
+        CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ldp * 8, src, (size_t)lds[blk] * 8, (size_t)Kf * 8, (size_t)take, cudaMemcpyHostToDevice, g.copy_stream));
+      filled += take;
+      blk_row += take;
+    }
+    CUDA_TRY(cudaEventRecord(g.chunk_ev[bi], g.copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(g.stream, g.chunk_ev[bi], 0));
+    int64_t ne_c = ne - r0;
+    ne_c = ne_c < 0 ? 0 : (ne_c > nr ? nr : ne_c);
+    PL_TRY(syrk_dev_impl((const double*)buf[bi], nr, Kf, ldp, dw ? dw + r0 : nullptr, ne_c, w_e, w_f, db ? db + r0 : nullptr, nullptr, (double*)dS,
+                         (double*)dvec, g.stream));
+    accumulate_kernel<<<g.num_sms * 4, 256, 0, g.stream>>>((const double*)dS, Kf * Kf, (double*)dSacc);
+    LAUNCH_CHECK();
+    if (want_vec) {
+      accumulate_kernel<<<8, 256, 0, g.stream>>>((const double*)dvec, 2 * Kf + 2, (double*)dVacc);
+      LAUNCH_CHECK();
+    }
+    CUDA_TRY(cudaEventRecord(g.chunk_ev[2 + bi], g.stream));
+    r0 += nr;
+  }
+  PL_TRY(finish_dev_impl((double*)dSacc, (double*)dVacc, Kf, ic, lambda, (double*)dM, (double*)dv, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaMemcpyAsync(AtWA, dM, (size_t)n * n * 8, cudaMemcpyDeviceToHost, g.stream));
+  if (AtWb) CUDA_TRY(cudaMemcpyAsync(AtWb, dv, (size_t)n * 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();
+}
+
+
+// ------------------------------------------------ symmetric eigendecomposition (row f1) ------------------------------------------------
+// The dense symmetric eigensolver is a LIBRARY call, as it is in the reference (LAPACK syevr behind Julia's eigen(Symmetric), reached through
+// Determinantal.jl's EllEnsemble and dimension_reduction.jl:13): cuSOLVER's Xsyevd, resolved with dlopen so that libplb200.so has no link-time
+// dependency beyond the CUDA runtime. What is ours is everything around it: the kernel matrix never leaves the device, and the L-ensemble
+// quantities that need all of U (inclusion probabilities, the selected eigenvectors) are computed / gathered there.
+struct Cusolver {
+  void* dl = nullptr;
+  cusolverDnHandle_t h = nullptr;
+  cusolverDnParams_t params = nullptr;
+  cusolverStatus_t (*Create)(cusolverDnHandle_t*) = nullptr;
+  cusolverStatus_t (*Destroy)(cusolverDnHandle_t) = nullptr;
+  cusolverStatus_t (*SetStream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
+  cusolverStatus_t (*CreateParams)(cusolverDnParams_t*) = nullptr;
+  cusolverStatus_t (*DestroyParams)(cusolverDnParams_t) = nullptr;
+  cusolverStatus_t (*XsyevdBufferSize)(cusolverDnHandle_t, cusolverDnParams_t, cusolverEigMode_t, cublasFillMode_t, int64_t, cudaDataType, const void*,
+                                       int64_t, cudaDataType, const void*, cudaDataType, size_t*, size_t*) = nullptr;
+  cusolverStatus_t (*Xsyevd)(cusolverDnHandle_t, cusolverDnParams_t, cusolverEigMode_t, cublasFillMode_t, int64_t, cudaDataType, void*, int64_t,
+                             cudaDataType, void*, cudaDataType, void*, size_t, void*, size_t, int*) = nullptr;
+} cs;
+
+int cusolver_ready() {
+  if (cs.h) return PL_OK;
+  const char* env = getenv("PLB200_CUSOLVER");
+  const char* cands[] = {env, "libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so", "libcusolver.so.12"};
+  for (const char* c : cands) {
+    if (!c || !*c) continue;
+    cs.dl = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (cs.dl) break;
+  }
+  if (!cs.dl) return set_err(PL_ECUDA, "cannot load libcusolver (%s); set PLB200_CUSOLVER to its path", dlerror());
+#define CS_SYM(field, name)                                                         \
+  do {                                                                              \
+    *(void**)(&cs.field) = dlsym(cs.dl, name);                                      \
+    if (!cs.field) return set_err(PL_ECUDA, "libcusolver does not export %s", name); \
+  } while (0)
+  CS_SYM(Create, "cusolverDnCreate");
+  CS_SYM(Destroy, "cusolverDnDestroy");
+  CS_SYM(SetStream, "cusolverDnSetStream");
+  CS_SYM(CreateParams, "cusolverDnCreateParams");
+  CS_SYM(DestroyParams, "cusolverDnDestroyParams");
+  CS_SYM(XsyevdBufferSize, "cusolverDnXsyevd_bufferSize");
+  CS_SYM(Xsyevd, "cusolverDnXsyevd");
+#undef CS_SYM
+  cusolverStatus_t r = cs.Create(&cs.h);
+  if (r != CUSOLVER_STATUS_SUCCESS) {
+    cs.h = nullptr;
+    return set_err(PL_ECUDA, "cusolverDnCreate failed with status %d", (int)r);
+  }
+  r = cs.CreateParams(&cs.params);
+  if (r != CUSOLVER_STATUS_SUCCESS) return set_err(PL_ECUDA, "cusolverDnCreateParams failed with status %d", (int)r);
+  return PL_OK;
+}
+
+// In place: the `fill` triangle (row-major view) of dA (n x n, leading dimension lda) is read; on return row k of dA is the unit eigenvector of
+// the k-th smallest eigenvalue dW[k] (column k in Julia's column-major view). Synchronises `st` (cuSOLVER reports through a device flag).
+int eigh_dev_impl(double* dA, int64_t n, int64_t lda, int fill, int want_vectors, double* dW, cudaStream_t st) {
+  PL_TRY(need_ready());
+  if (n <= 0 || lda < n || !dA || !dW) return set_err(PL_EINVAL, "bad arguments");
+  if (fill < 1 || fill > 3) return set_err(PL_EINVAL, "bad fill");
+  PL_TRY(cusolver_ready());
+  cusolverStatus_t r = cs.SetStream(cs.h, st);
+  if (r != CUSOLVER_STATUS_SUCCESS) return set_err(PL_ECUDA, "cusolverDnSetStream failed with status %d", (int)r);
+  // row-major [i][j], j <= i (PL_FILL_RM_LOWER) is column-major element (row j, col i), j <= i: the UPPER triangle for cuSOLVER
+  const cublasFillMode_t uplo = (fill & PL_FILL_RM_LOWER) ? CUBLAS_FILL_MODE_UPPER : CUBLAS_FILL_MODE_LOWER;
+  const cusolverEigMode_t jobz = want_vectors ? CUSOLVER_EIG_MODE_VECTOR : CUSOLVER_EIG_MODE_NOVECTOR;
+  size_t wdev = 0, whost = 0;
+  r = cs.XsyevdBufferSize(cs.h, cs.params, jobz, uplo, n, CUDA_R_64F, dA, lda, CUDA_R_64F, dW, CUDA_R_64F, &wdev, &whost);
+  if (r != CUSOLVER_STATUS_SUCCESS) return set_err(PL_ECUDA, "cusolverDnXsyevd_bufferSize failed with status %d (n = %lld)", (int)r, (long long)n);
+  void *dwork, *dinfo;
+  PL_TRY(ws_get(WS_EIG_WORK, wdev, &dwork));
+  PL_TRY(ws_get(WS_EIG_INFO, 16, &dinfo));
+  void* hwork = whost ? malloc(whost) : nullptr;
+  if (whost && !hwork) return set_err(PL_ENOMEM, "host workspace of %zu bytes", whost);
+  r = cs.Xsyevd(cs.h, cs.params, jobz, uplo, n, CUDA_R_64F, dA, lda, CUDA_R_64F, dW, CUDA_R_64F, dwork, wdev, hwork, whost, (int*)dinfo);
+  int info = -1;
+  cudaError_t e = cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  free(hwork);
+  if (r != CUSOLVER_STATUS_SUCCESS) return set_err(PL_ECUDA, "cusolverDnXsyevd failed with status %d", (int)r);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_err(PL_ECUDA, "eigensolver: %s", cudaGetErrorString(e));
+  }
+  if (info != 0) return set_err(PL_ECUDA, "cusolverDnXsyevd did not converge / bad argument (info = %d)", info);
+  return PL_OK;
+}
+
+// the resident L-ensemble of the last pl_ell_ensemble call
+struct EllState {
+  int64_t n = 0, ld = 0;
+  bool valid = false;
+} ell_state;
+
+int inclusion_prob_dev_impl(const double* dV, int64_t nvec, int64_t n, int64_t ldv, const double* dgamma, double* dp, cudaStream_t st) {
+  int64_t rpb = nvec / 64;
+  rpb = rpb < 16 ? 16 : (rpb + 1) / 2 * 2;
+  const int64_t nblk = (nvec + rpb - 1) / rpb;
+  void* part;
+  PL_TRY(ws_get(WS_COLSUM_PARTIAL, (size_t)nblk * n * 8, &part));
+  dim3 grid((unsigned)((n + 127) / 128), (unsigned)nblk);
+  weighted_colsumsq_partial_kernel<<<grid, 128, 0, st>>>(dV, nvec, n, ldv, dgamma, (int)rpb, (double*)part);
+  LAUNCH_CHECK();
+  colsum_final_kernel<<<(unsigned)((n + 31) / 32), 256, 0, st>>>((const double*)part, nblk, n, 0.0, dp);
+  LAUNCH_CHECK();
+  return PL_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -583,6 +812,13 @@ void pl_finalize(void) {
     if (ev) cudaEventDestroy(ev);
     ev = nullptr;
   }
+  if (cs.h) {
+    if (cs.params) cs.DestroyParams(cs.params);
+    cs.Destroy(cs.h);
+    cs.h = nullptr;
+    cs.params = nullptr;
+  }
+  ell_state.valid = false;
   if (g.stream) cudaStreamDestroy(g.stream);
   if (g.copy_stream) cudaStreamDestroy(g.copy_stream);
   g.stream = nullptr;
@@ -890,6 +1126,14 @@ int pl_normal_eq(const double* A, int64_t R, int64_t Kf, int64_t lda, const doub
   if (!A || !AtWA || R < 0 || Kf <= 0 || lda < Kf) return set_err(PL_EINVAL, "bad arguments");
   if (AtWb && !b) return set_err(PL_EINVAL, "AtWb requested without b");
   CUDA_TRY(cudaSetDevice(g.device));
+  if ((double)R * (double)Kf * 8.0 > 768.0 * 1048576.0) {
+    // large inputs: stream row chunks through two device buffers, H2D overlapped with the SYRK (same code as pl_normal_eq_blocks)
+    int64_t chunk_rows = (((int64_t)512 << 20) / (Kf * 8) + 15) / 16 * 16;
+    const double* blk[1] = {A};
+    const int64_t rows[1] = {R}, lds[1] = {lda};
+    const int64_t ne = n_energy_rows < 0 ? 0 : (n_energy_rows > R ? R : n_energy_rows);
+    return normal_eq_stream(blk, rows, lds, 1, R, Kf, w, ne, w_e, w_f, b, add_intercept ? 1 : 0, lambda, AtWA, AtWb, chunk_rows);
+  }
   CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
   double *dA, *dw = nullptr, *db = nullptr;
   int64_t ld;
@@ -950,6 +1194,180 @@ int pl_cov(const double* X, int64_t n, int64_t Kf, int64_t ldx, double* mean_ino
   CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
   CUDA_TRY(cudaMemcpyAsync(C, dC, (size_t)Kf * Kf * 8, cudaMemcpyDeviceToHost, g.stream));
   if (center && !mean_given) CUDA_TRY(cudaMemcpyAsync(mean_inout, dmean, (size_t)Kf * 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();
+}
+
+
+int pl_global_feature_dev(const double* dL, int64_t ldl, const int64_t* doffsets, int64_t N, int64_t d, int mean, double* dX, int64_t ldx,
+                          int64_t total_rows, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return global_feature_dev_impl(dL, ldl, doffsets, N, d, mean, dX, ldx, total_rows, (cudaStream_t)stream);
+}
+
+int pl_global_feature(const double* locals, int64_t ldl, const int64_t* offsets, int64_t N, int64_t d, int mean, double* X, int64_t ldx) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!locals || !offsets || !X || N < 0 || d <= 0 || ldl < d || ldx < d) return set_err(PL_EINVAL, "bad arguments");
+  if (N == 0) return PL_OK;
+  PL_TRY(check_offsets(offsets, N));
+  const int64_t total = offsets[N];
+  CUDA_TRY(cudaSetDevice(g.device));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  double* dL;
+  int64_t ld;
+  PL_TRY(h2d_matrix(locals, total, d, ldl, WS_FEAT_L, &dL, &ld));
+  void *doff, *dX;
+  PL_TRY(ws_get(WS_FEAT_OFF, (size_t)(N + 1) * 8, &doff));
+  CUDA_TRY(cudaMemcpyAsync(doff, offsets, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, g.stream));
+  const int64_t ldo = (d + 1) & ~(int64_t)1;
+  PL_TRY(ws_get(WS_FEAT_X, (size_t)N * ldo * 8, &dX));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  PL_TRY(global_feature_dev_impl(dL, ld, (const int64_t*)doff, N, d, mean, (double*)dX, ldo, total, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaMemcpy2DAsync(X, (size_t)ldx * 8, dX, (size_t)ldo * 8, (size_t)d * 8, (size_t)N, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();
+}
+
+int pl_normal_eq_blocks(const double* const* blocks, const int64_t* rows, int64_t nblocks, int64_t Kf, const double* w, int64_t n_energy_rows,
+                        double w_e, double w_f, const double* b, int add_intercept, double lambda, int64_t chunk_rows, double* AtWA,
+                        double* AtWb) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!blocks || !rows || !AtWA || nblocks < 0 || Kf <= 0) return set_err(PL_EINVAL, "bad arguments");
+  if (AtWb && !b) return set_err(PL_EINVAL, "AtWb requested without b");
+  int64_t R = 0;
+  for (int64_t k = 0; k < nblocks; ++k) {
+    if (rows[k] < 0 || (rows[k] > 0 && !blocks[k])) return set_err(PL_EINVAL, "block %lld: bad row count or NULL pointer", (long long)k);
+    R += rows[k];
+  }
+  CUDA_TRY(cudaSetDevice(g.device));
+  if (chunk_rows <= 0) {
+    chunk_rows = ((int64_t)512 << 20) / (Kf * 8);  // ~512 MB per buffer: long enough copies for full PCIe rate, SYRK still > 1 wave
+    if (chunk_rows < 4096) chunk_rows = 4096;
+  }
+  chunk_rows = (chunk_rows + 15) / 16 * 16;
+  // dense blocks: leading dimension Kf each
+  int64_t* lds = (int64_t*)malloc((size_t)(nblocks > 0 ? nblocks : 1) * sizeof(int64_t));
+  if (!lds) return set_err(PL_ENOMEM, "host allocation failed");
+  for (int64_t k = 0; k < nblocks; ++k) lds[k] = Kf;
+  int64_t ne = n_energy_rows < 0 ? 0 : (n_energy_rows > R ? R : n_energy_rows);
+  const int rc = normal_eq_stream(blocks, rows, lds, nblocks, R, Kf, w, ne, w_e, w_f, b, add_intercept ? 1 : 0, lambda, AtWA, AtWb, chunk_rows);
+  free(lds);
+  return rc;
+}
+
+
+int pl_eigh_dev(double* dA, int64_t n, int64_t lda, int fill, int want_vectors, double* dW, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return eigh_dev_impl(dA, n, lda, fill, want_vectors, dW, (cudaStream_t)stream);
+}
+
+int pl_eigh(const double* A, int64_t n, int64_t lda, int fill, double* W, double* V, int64_t ldv) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!A || !W || n <= 0 || lda < n || (V && ldv < n)) return set_err(PL_EINVAL, "bad arguments");
+  CUDA_TRY(cudaSetDevice(g.device));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  void *dA, *dW;  // not the WS_EIG_* slots: a resident L-ensemble survives plain eigendecompositions
+  PL_TRY(ws_get(WS_H_OUT1, (size_t)n * n * 8, &dA));
+  PL_TRY(ws_get(WS_H_OUT2, (size_t)n * 8, &dW));
+  CUDA_TRY(cudaMemcpy2DAsync(dA, (size_t)n * 8, A, (size_t)lda * 8, (size_t)n * 8, (size_t)n, cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  PL_TRY(eigh_dev_impl((double*)dA, n, n, fill, V != nullptr, (double*)dW, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaMemcpyAsync(W, dW, (size_t)n * 8, cudaMemcpyDeviceToHost, g.stream));
+  if (V) CUDA_TRY(cudaMemcpy2DAsync(V, (size_t)ldv * 8, dA, (size_t)n * 8, (size_t)n * 8, (size_t)n, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();
+}
+
+int pl_ell_ensemble(int kernel_id, const double* X, int64_t n, int64_t d, int64_t ldx, int alpha, int cinv_kind, const double* cinv, double ell,
+                    double beta, double* lambda, double* Kout, int64_t ldk) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!X || !lambda || n <= 0 || d <= 0 || ldx < d || (Kout && ldk < n)) return set_err(PL_EINVAL, "bad arguments");
+  CUDA_TRY(cudaSetDevice(g.device));
+  ell_state.valid = false;
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  double *dX, *dc = nullptr;
+  int64_t ld;
+  PL_TRY(h2d_matrix(X, n, d, ldx, WS_H_IN1, &dX, &ld));
+  if ((kernel_id == PL_KERNEL_RBF || kernel_id == PL_KERNEL_IMQ) && cinv_kind != PL_CINV_IDENTITY) {
+    if (!cinv) return set_err(PL_EINVAL, "cinv is NULL");
+    PL_TRY(h2d_vector(cinv, cinv_kind == PL_CINV_DIAGONAL ? d : d * d, WS_H_IN3, &dc));
+  }
+  const int64_t ldo = (n + 1) & ~(int64_t)1;
+  void *dA, *dW;
+  PL_TRY(ws_get(WS_EIG_A, (size_t)n * ldo * 8, &dA));
+  PL_TRY(ws_get(WS_EIG_W, (size_t)n * 8, &dW));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  // K = KernelMatrix(F, k) (dpp.jl:25,40) in the Symmetric(:U) storage, straight into the eigensolver's buffer
+  PL_TRY(gram_dev_impl(kernel_id, dX, n, ld, nullptr, 0, 0, d, alpha, cinv_kind, dc, ell, beta, (double*)dA, ldo, PL_FILL_JULIA_U, 0, 1, 0, g.stream));
+  if (Kout) {  // the caller also wants K itself (kDPP keeps it as ell.L): triangle rows, before the solver overwrites the buffer
+    for (int64_t r0 = 0; r0 < n; r0 += GRAM_BM) {
+      const int64_t r1 = r0 + GRAM_BM < n ? r0 + GRAM_BM : n;
+      CUDA_TRY(cudaMemcpy2DAsync(Kout + r0 * ldk, (size_t)ldk * 8, (double*)dA + r0 * ldo, (size_t)ldo * 8, (size_t)r1 * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, g.stream));
+    }
+  }
+  PL_TRY(eigh_dev_impl((double*)dA, n, ldo, PL_FILL_JULIA_U, 1, (double*)dW, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaMemcpyAsync(lambda, dW, (size_t)n * 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  PL_TRY(finish_timing());
+  ell_state.n = n;
+  ell_state.ld = ldo;
+  ell_state.valid = true;
+  return PL_OK;
+}
+
+int pl_ell_inclusion_prob(double alpha_scale, int64_t n, double* p) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!ell_state.valid) return set_err(PL_EINVAL, "no resident L-ensemble: call pl_ell_ensemble first");
+  if (n != ell_state.n || !p) return set_err(PL_EINVAL, "bad arguments (resident ensemble has %lld items)", (long long)ell_state.n);
+  CUDA_TRY(cudaSetDevice(g.device));
+  void *dg, *dp;
+  PL_TRY(ws_get(WS_EIG_GAMMA, (size_t)n * 8, &dg));
+  PL_TRY(ws_get(WS_EIG_P, (size_t)n * 8, &dp));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  ell_gamma_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>((const double*)g.ws[WS_EIG_W], n, alpha_scale, (double*)dg);
+  LAUNCH_CHECK();
+  PL_TRY(inclusion_prob_dev_impl((const double*)g.ws[WS_EIG_A], n, n, ell_state.ld, (const double*)dg, (double*)dp, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaMemcpyAsync(p, dp, (size_t)n * 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();
+}
+
+int pl_ell_eigvecs(const int64_t* idx, int64_t m, int64_t n, double* V, int64_t ldv) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!ell_state.valid) return set_err(PL_EINVAL, "no resident L-ensemble: call pl_ell_ensemble first");
+  if (n != ell_state.n || m < 0 || (m > 0 && (!idx || !V)) || ldv < n) return set_err(PL_EINVAL, "bad arguments");
+  if (m == 0) return PL_OK;
+  for (int64_t r = 0; r < m; ++r)
+    if (idx[r] < 0 || idx[r] >= n) return set_err(PL_EINVAL, "eigenvector index %lld out of range", (long long)idx[r]);
+  CUDA_TRY(cudaSetDevice(g.device));
+  void *didx, *dsel;
+  PL_TRY(ws_get(WS_EIG_IDX, (size_t)m * 8, &didx));
+  PL_TRY(ws_get(WS_EIG_SEL, (size_t)m * n * 8, &dsel));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  CUDA_TRY(cudaMemcpyAsync(didx, idx, (size_t)m * 8, cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  int64_t rem = m, done = 0;
+  while (rem > 0) {  // grid.y is limited to 65535
+    const int64_t take = rem < 32768 ? rem : 32768;
+    dim3 grid((unsigned)((n + 1023) / 1024 < 8 ? (n + 1023) / 1024 : 8), (unsigned)take);
+    gather_rows_kernel<<<grid, 256, 0, g.stream>>>((const double*)g.ws[WS_EIG_A], n, ell_state.ld, (const int64_t*)didx + done, take, (double*)dsel + done * n);
+    LAUNCH_CHECK();
+    rem -= take;
+    done += take;
+  }
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaMemcpy2DAsync(V, (size_t)ldv * 8, dsel, (size_t)n * 8, (size_t)n * 8, (size_t)m, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
   return finish_timing();
 }

@@ -196,4 +196,164 @@ __global__ void sym_scale_div_kernel(const double* __restrict__ in, int64_t K, d
   }
 }
 
+// ---- GlobalSum / GlobalMean features over the stacked local descriptors of all configurations ----
+// X[i][:] = sum_{a in [off[i], off[i+1])} L[a][:]  (/ natoms_i for the mean): compute_feature(B, ::GlobalSum / ::GlobalMean)
+// (src/Kernels/features.jl:19-21, 32-34), B[i] = sum(get_values(local descriptors)) (linear-learning-problem.jl:75) and the rows
+// of fit!(::PCAState) (pca_state.jl:23). HBM-bound segmented reduction: a group of G lanes (G = 1..32, a power of two) owns one
+// (configuration, 2G-column chunk); each lane carries one 16-byte column pair through the atoms with 4 loads in flight.
+// The summation ORDER is Julia's: Base.sum over a Vector{Vector} is mapreduce_impl with pairwise_blocksize 1024 — a plain
+// left-to-right sum for fewer than 1024 atoms, and above that a recursive split at imid = ifirst + (ilast - ifirst) >> 1 whose
+// leaves are summed left to right. The same tree is walked here with an explicit stack, so the result is bit-identical to the
+// reference's for every natoms (the mean divides the finished sum by natoms, as Statistics.mean does).
+struct SegFrame {
+  int64_t lo, hi;
+  double2 v1;
+  int stage;
+};
+__device__ __forceinline__ double2 seg_sum_seq(const double* __restrict__ base, int64_t ld, int64_t lo, int64_t hi, bool pair) {
+  // rows lo..hi inclusive, sequential; `base` already points at this lane's column pair
+  double2 s;
+  const double* p = base + lo * ld;
+  if (pair) {
+    s = __ldg(reinterpret_cast<const double2*>(p));
+    int64_t r = lo + 1;
+    p += ld;
+    for (; r + 3 <= hi; r += 4) {
+      const double2 a0 = __ldg(reinterpret_cast<const double2*>(p));
+      const double2 a1 = __ldg(reinterpret_cast<const double2*>(p + ld));
+      const double2 a2 = __ldg(reinterpret_cast<const double2*>(p + 2 * ld));
+      const double2 a3 = __ldg(reinterpret_cast<const double2*>(p + 3 * ld));
+      s.x += a0.x; s.y += a0.y;
+      s.x += a1.x; s.y += a1.y;
+      s.x += a2.x; s.y += a2.y;
+      s.x += a3.x; s.y += a3.y;
+      p += 4 * ld;
+    }
+    for (; r <= hi; ++r) {
+      const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+      s.x += a.x; s.y += a.y;
+      p += ld;
+    }
+  } else {
+    s.x = __ldg(p);
+    s.y = 0.0;
+    for (int64_t r = lo + 1; r <= hi; ++r) {
+      p += ld;
+      s.x += __ldg(p);
+    }
+  }
+  return s;
+}
+constexpr int SEG_PAIRWISE_BLOCK = 1024;  // Base.pairwise_blocksize(identity, +)
+__global__ void segment_reduce_kernel(const double* __restrict__ L, int64_t ldl, const int64_t* __restrict__ off, int64_t N, int64_t d, int G,
+                                      int mean, double* __restrict__ X, int64_t ldx) {
+  const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t group = gthread / G;
+  const int gl = (int)(gthread % G);
+  const int64_t nchunks = (d + 2 * G - 1) / (2 * G);
+  const int64_t cfg = group / nchunks;
+  if (cfg >= N) return;
+  const int64_t c0 = (group % nchunks) * 2 * G + 2 * gl;
+  if (c0 >= d) return;
+  const bool pair = c0 + 1 < d;
+  const int64_t lo = off[cfg], hi = off[cfg + 1] - 1;
+  double2 s;
+  const double* base = L + c0;
+  if (hi < lo) {
+    s.x = s.y = 0.0;  // empty configuration: the reference's sum/mean of an empty collection throws; the host rejects it
+  } else if (hi - lo < SEG_PAIRWISE_BLOCK) {
+    s = seg_sum_seq(base, ldl, lo, hi, pair);
+  } else {
+    SegFrame st[48];
+    int sp = 0;
+    st[0].lo = lo; st[0].hi = hi; st[0].stage = 0;
+    double2 ret;
+    ret.x = ret.y = 0.0;
+    while (sp >= 0) {
+      SegFrame& f = st[sp];
+      if (f.stage == 0) {
+        if (f.hi - f.lo < SEG_PAIRWISE_BLOCK) {
+          ret = seg_sum_seq(base, ldl, f.lo, f.hi, pair);
+          --sp;
+        } else {
+          const int64_t mid = f.lo + ((f.hi - f.lo) >> 1);
+          f.stage = 1;
+          st[sp + 1].lo = f.lo; st[sp + 1].hi = mid; st[sp + 1].stage = 0;
+          ++sp;
+        }
+      } else if (f.stage == 1) {
+        f.v1 = ret;
+        const int64_t mid = f.lo + ((f.hi - f.lo) >> 1);
+        f.stage = 2;
+        st[sp + 1].lo = mid + 1; st[sp + 1].hi = f.hi; st[sp + 1].stage = 0;
+        ++sp;
+      } else {
+        ret.x = f.v1.x + ret.x;
+        ret.y = f.v1.y + ret.y;
+        --sp;
+      }
+    }
+    s = ret;
+  }
+  if (mean) {
+    const double n = (double)(hi - lo + 1);
+    s.x /= n;
+    s.y /= n;
+  }
+  double* out = X + cfg * ldx + c0;
+  if (pair && !(ldx & 1) && !(reinterpret_cast<uintptr_t>(X) & 15u)) *reinterpret_cast<double2*>(out) = s;
+  else {
+    out[0] = s.x;
+    if (pair) out[1] = s.y;
+  }
+}
+
+// acc[i] += x[i]: accumulation of the chunk partials of the streamed normal equations in fixed (chunk) order
+__global__ void accumulate_kernel(const double* __restrict__ x, int64_t count, double* __restrict__ acc) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) acc[i] += x[i];
+}
+
+// ---- L-ensemble helpers on the device-resident eigenvectors ----
+// V: row k = eigenvector k (n contiguous doubles, leading dimension ldv). partial[blockIdx.y][i] = sum over this block's
+// eigenvector range of gamma[k] * V[k][i]^2; colsum_final_kernel adds the partials in fixed order:
+// inclusion_prob(L) = diag(U diag(a*lam/(1+a*lam)) U') (Determinantal.jl [external], called at src/SubsetSelection/dpp.jl:69).
+__global__ void weighted_colsumsq_partial_kernel(const double* __restrict__ V, int64_t nvec, int64_t n, int64_t ldv, const double* __restrict__ gamma,
+                                                 int rpb, double* __restrict__ partial) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t k0 = (int64_t)blockIdx.y * rpb;
+  int64_t k1 = k0 + rpb;
+  if (k1 > nvec) k1 = nvec;
+  double s0 = 0.0, s1 = 0.0;
+  int64_t k = k0;
+  for (; k + 2 <= k1; k += 2) {
+    const double a = __ldg(V + k * ldv + i), b = __ldg(V + (k + 1) * ldv + i);
+    s0 = fma(__ldg(gamma + k) * a, a, s0);
+    s1 = fma(__ldg(gamma + k + 1) * b, b, s1);
+  }
+  if (k < k1) {
+    const double a = __ldg(V + k * ldv + i);
+    s0 = fma(__ldg(gamma + k) * a, a, s0);
+  }
+  partial[(int64_t)blockIdx.y * n + i] = s0 + s1;
+}
+
+// gamma[k] = a*max(lam[k],0) / (1 + a*max(lam[k],0))
+__global__ void ell_gamma_kernel(const double* __restrict__ lam, int64_t n, double alpha, double* __restrict__ gamma) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double l = lam[k];
+  l = l > 0.0 ? l : 0.0;
+  const double g = alpha * l;
+  gamma[k] = g / (1.0 + g);
+}
+
+// out[r][:] = V[idx[r]][:]: the eigenvectors the k-DPP sampler selected, packed for one D2H copy
+__global__ void gather_rows_kernel(const double* __restrict__ V, int64_t n, int64_t ldv, const int64_t* __restrict__ idx, int64_t m, double* __restrict__ out) {
+  const int64_t r = blockIdx.y;
+  if (r >= m) return;
+  const double* src = V + idx[r] * ldv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[r * n + i] = src[i];
+}
+
 }  // namespace plb

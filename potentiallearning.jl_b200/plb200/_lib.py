@@ -39,7 +39,15 @@ PROTOTYPES = {
     "pl_gram_imq": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _dbl, _dbl, _dp, _i64, _int]),
     "pl_gram_cross": (_int, [_int, _dp, _i64, _i64, _dp, _i64, _i64, _i64, _int, _int, _dp, _dbl, _dbl, _dp, _i64]),
     "pl_normal_eq": (_int, [_dp, _i64, _i64, _i64, _dp, _i64, _dbl, _dbl, _dp, _int, _dbl, _dp, _dp]),
+    "pl_normal_eq_blocks": (_int, [ctypes.POINTER(_dp), ctypes.POINTER(_i64), _i64, _i64, _dp, _i64, _dbl, _dbl, _dp, _int, _dbl, _i64, _dp, _dp]),
+    "pl_global_feature": (_int, [_dp, _i64, ctypes.POINTER(_i64), _i64, _i64, _int, _dp, _i64]),
+    "pl_global_feature_dev": (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _i64, _i64, _vp]),
     "pl_cov": (_int, [_dp, _i64, _i64, _i64, _dp, _int, _int, _dp]),
+    "pl_eigh": (_int, [_dp, _i64, _i64, _int, _dp, _dp, _i64]),
+    "pl_eigh_dev": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp]),
+    "pl_ell_ensemble": (_int, [_int, _dp, _i64, _i64, _i64, _int, _int, _dp, _dbl, _dbl, _dp, _dp, _i64]),
+    "pl_ell_inclusion_prob": (_int, [_dbl, _i64, _dp]),
+    "pl_ell_eigvecs": (_int, [ctypes.POINTER(_i64), _i64, _i64, _dp, _i64]),
     "pl_predict": (_int, [_dp, _i64, _i64, _i64, _dp, _dbl, _i64, _dp]),
     "pl_predict_dev": (_int, [_vp, _i64, _i64, _i64, _vp, _dbl, _i64, _vp, _vp]),
     "pl_gram_dev": (_int, [_int, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _int, _vp, _dbl, _dbl, _vp, _i64, _int, _int, _int, _int, _vp]),

@@ -38,8 +38,10 @@ def covariance(rows, mean=None, center: bool = False):
 
 def compute_eigen(d, _precentered_mean=None):
     """compute_eigen(d) (dimension_reduction.jl:11-14): Q = Symmetric(mean(di*di')), eigen(Symmetric(Q)) -> (λ ascending, ϕ)."""
+    from .dpp import eigh
+
     Q, _ = covariance(d)
-    lam, phi = np.linalg.eigh(Q)  # Q is exactly symmetric by construction; eigh == LAPACK syevd on the 'L' triangle
+    lam, phi = eigh(Q)  # eigen(Symmetric(Q)) on the GPU (pl_eigh); Q is exactly symmetric by construction
     return lam, phi
 
 
@@ -85,7 +87,9 @@ class PCAState(DimensionReducer):
 
 def _global_sums(ds: DataSet):
     try:
-        return [np.add.reduce(get_values(get_local_descriptors(c)), axis=0) for c in ds]
+        from .kernels import global_features
+
+        return global_features([get_values(get_local_descriptors(c)) for c in ds], mean=False)  # sum.(get_values.(...)) on the GPU
     except KeyError:
         raise RuntimeError("No local descriptors found in DataSet") from None
 
@@ -117,7 +121,9 @@ def fit_(ds: DataSet, pca: PCAState, use_force_descriptors: bool = False):
     Q, m = covariance(rows, mean=pca.m if mean_given else None, center=True)
     if not mean_given:
         pca.m = m
-    lam, phi = np.linalg.eigh(Q)
+    from .dpp import eigh
+
+    lam, phi = eigh(Q)
     pca.λ, pca.W = _select(lam, phi, pca.tol)
     return None
 

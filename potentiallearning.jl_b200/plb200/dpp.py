@@ -14,28 +14,128 @@ from __future__ import annotations
 import numpy as np
 
 from .data import DataSet, LocalDescriptors
-from .kernels import Feature, Kernel, KernelMatrix, Symmetric
+from . import _lib
+from .kernels import Feature, Kernel, KernelMatrix, Symmetric, compute_features
 
 
 class SubsetSelector:
     pass
 
 
-class EllEnsemble:
-    """L-ensemble: L = U diag(λ) U', scaled by α (Determinantal.jl EllEnsemble + rescale!)."""
+def eigh(A, fill: str = "full", vectors: bool = True):
+    """eigen(Symmetric(A)) on the GPU (pl_eigh): (λ ascending, U with U[:, k] = eigenvector k) like numpy.linalg.eigh."""
+    A = np.asarray(A) if isinstance(A, Symmetric) else _lib.as_f64(A)
+    A = np.ascontiguousarray(A)
+    n = A.shape[0]
+    if A.ndim != 2 or A.shape[1] != n:
+        raise ValueError("eigh needs a square matrix")
+    W = np.empty(n)
+    V = np.empty((n, n)) if vectors else None
+    fl = {"full": _lib.PL_FILL_FULL, "U": _lib.PL_FILL_RM_UPPER, "L": _lib.PL_FILL_RM_LOWER}[fill]
+    _lib.check(_lib.lib().pl_eigh(_lib.dptr(A), n, n, fl, _lib.dptr(W), _lib.dptr(V), n), "pl_eigh")
+    return (W, V.T) if vectors else W
 
-    def __init__(self, K):
+
+_resident_owner = None  # the EllEnsemble whose eigenvectors currently live in the library (one at a time)
+
+
+class EllEnsemble:
+    """L-ensemble: L = U diag(λ) U', scaled by α (Determinantal.jl EllEnsemble + rescale!).
+
+    EllEnsemble(K): eigendecomposition of a host kernel matrix on the GPU (pl_eigh).
+    EllEnsemble.from_features(X, kernel): SURVEY.md 8f row f1 — kernel matrix AND eigendecomposition on the GPU (pl_ell_ensemble);
+    U stays device-resident: inclusion probabilities are computed there and a k-DPP draw downloads only the eigenvectors it selected."""
+
+    def __init__(self, K=None):
+        self.α = 1.0
+        self._U = None
+        self._resident = False
+        if K is None:
+            return
         self.L = np.asarray(K) if isinstance(K, Symmetric) else np.asarray(K, dtype=np.float64)
         if self.L.shape[0] != self.L.shape[1]:
             raise ValueError("EllEnsemble needs a square kernel matrix")
-        lam, U = np.linalg.eigh(self.L)
+        lam, U = eigh(self.L)
         self.λ = np.maximum(lam, 0.0)  # clip round-off negatives of a PSD kernel
-        self.U = U
-        self.α = 1.0
+        self._U = U
+
+    @classmethod
+    def from_eigen(cls, lam, U, L=None):
+        """wrap an eigendecomposition computed elsewhere (what a Julia caller does when it hands Determinantal a precomputed (λ, U))"""
+        self = cls()
+        self.λ = np.maximum(np.asarray(lam, dtype=np.float64), 0.0)
+        self._U = np.asarray(U, dtype=np.float64)
+        if L is not None:
+            self.L = np.asarray(L, dtype=np.float64)
+        return self
+
+    @classmethod
+    def from_features(cls, X, k: Kernel, keep_L: bool = True):
+        global _resident_owner
+        from .kernels import _features_matrix, _for_flattened, _kargs
+
+        F = X
+        X = _features_matrix(F)
+        n, d = X.shape
+        kid, alpha, kind, cinv, ell_, beta = _kargs(_for_flattened(k, F, d), d)
+        self = cls()
+        if _resident_owner is not None and _resident_owner is not self:
+            _resident_owner._evict()
+        lam = np.empty(n)
+        Kst = np.zeros((n, n)) if keep_L else None  # zeros(n, n) (kernels.jl:216)
+        _lib.check(_lib.lib().pl_ell_ensemble(kid, _lib.dptr(X), n, d, d, alpha, kind, _lib.dptr(cinv), ell_, beta, _lib.dptr(lam), _lib.dptr(Kst), n),
+                   "pl_ell_ensemble")
+        self._Lsym = Symmetric(Kst.T, "U") if keep_L else None  # row-major lower == Julia's column-major uplo = :U
+        self.λ = np.maximum(lam, 0.0)
+        self._n = n
+        self._resident = True
+        _resident_owner = self
+        return self
+
+    # the kernel matrix (greedy_subset needs it); materialised from the Symmetric storage on first use
+    @property
+    def L(self):
+        if "_Lfull" not in self.__dict__:
+            if getattr(self, "_Lsym", None) is None:
+                raise _lib.PLB200Error("this L-ensemble was built with keep_L=False")
+            self._Lfull = np.asarray(self._Lsym)
+        return self._Lfull
+
+    @L.setter
+    def L(self, v):
+        self._Lfull = v
 
     @property
     def nitems(self):
-        return self.L.shape[0]
+        return len(self.λ)
+
+    @property
+    def U(self):
+        """all eigenvectors as columns (downloaded from the device on first use for a resident ensemble)"""
+        if self._U is None:
+            self._U = self.eigvecs(np.arange(self.nitems))
+        return self._U
+
+    def eigvecs(self, J):
+        """U[:, J] — for a resident ensemble only these len(J) eigenvectors cross PCIe (pl_ell_eigvecs)."""
+        import ctypes
+
+        J = np.ascontiguousarray(J, dtype=np.int64)
+        if self._U is not None:
+            return self._U[:, J].copy()
+        if not self._resident:
+            raise _lib.PLB200Error("the device-resident eigenvectors of this L-ensemble were replaced by a newer ensemble; rebuild it")
+        V = np.empty((len(J), self._n))
+        _lib.check(_lib.lib().pl_ell_eigvecs(J.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), len(J), self._n, _lib.dptr(V), self._n), "pl_ell_eigvecs")
+        return np.ascontiguousarray(V.T)
+
+    def _evict(self):
+        """another ensemble takes the device slot: keep small ones usable by downloading U first"""
+        global _resident_owner
+        if self._resident and self._U is None and self.nitems <= 4096:
+            self._U = self.eigvecs(np.arange(self.nitems))
+        self._resident = False
+        _resident_owner = None
 
 
 def rescale_(ell: EllEnsemble, k: int):
@@ -91,7 +191,7 @@ def sample(ell: EllEnsemble, k: int, rng=None):
         if np.log(rng.random()) < logp:
             J.append(n - 1)
             l -= 1
-    V = ell.U[:, J].copy()
+    V = ell.eigvecs(J)
     items = []
     for _ in range(len(J)):
         p = np.sum(V * V, axis=1)
@@ -129,6 +229,10 @@ def greedy_subset(ell: EllEnsemble, k: int):
 
 def inclusion_prob(ell: EllEnsemble):
     """Determinantal.inclusion_prob(L): diagonal of the marginal kernel U diag(αλ/(1+αλ)) U'."""
+    if ell._resident and _resident_owner is ell:
+        p = np.empty(ell.nitems)
+        _lib.check(_lib.lib().pl_ell_inclusion_prob(float(ell.α), ell.nitems, _lib.dptr(p)), "pl_ell_inclusion_prob")
+        return p
     g = ell.α * ell.λ
     g = g / (1.0 + g)
     return np.sum(ell.U * ell.U * g[None, :], axis=1)
@@ -141,16 +245,15 @@ class kDPP(SubsetSelector):
     def __init__(self, *args, batch_size=None, dt=LocalDescriptors):
         if len(args) == 3 and isinstance(args[0], DataSet) and isinstance(args[1], Feature) and isinstance(args[2], Kernel):
             ds, f, k = args
-            n = len(ds)
-            Kmat = KernelMatrix(ds, f, k, dt=dt)  # dpp.jl:25  <- the hot path
+            features = compute_features(ds, f, dt=dt)  # kernels.jl:251
         elif len(args) == 2 and isinstance(args[1], Kernel):
             features, k = args
-            n = len(features)
-            Kmat = KernelMatrix(features, k)  # dpp.jl:40
         else:
             raise TypeError("kDPP(ds, f, k; batch_size, dt) | kDPP(features, k; batch_size)")
+        n = len(features)
         self.batch_size = n // 2 if batch_size is None else int(batch_size)
-        ell = EllEnsemble(Kmat)
+        # K = KernelMatrix(...) (dpp.jl:25, :40) and EllEnsemble(K) (:26, :41) fused on the GPU; K is kept as ell.L
+        ell = EllEnsemble.from_features(features, k)
         rescale_(ell, self.batch_size)
         self.K = ell
 

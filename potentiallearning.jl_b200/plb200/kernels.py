@@ -52,8 +52,55 @@ def compute_feature(x, f: Feature, dt=LocalDescriptors) -> np.ndarray:
 
 
 def compute_features(ds: DataSet, f: Feature, dt=LocalDescriptors):
-    """compute_features(ds, f; dt) = compute_feature.(ds, (f,); dt) (features.jl:76-78)."""
+    """compute_features(ds, f; dt) = compute_feature.(ds, (f,); dt) (features.jl:76-78).
+    GlobalMean / GlobalSum over a whole DataSet run on the GPU (pl_global_feature: one segmented reduction over the stacked local
+    descriptors, Julia's summation order); returns the N x d feature matrix (row i = feature of configuration i)."""
+    if isinstance(f, (GlobalMean, GlobalSum)):
+        return global_features([get_values(get_local_descriptors(c)) for c in ds], mean=isinstance(f, GlobalMean))
     return [compute_feature(c, f, dt=dt) for c in ds]
+
+
+def stack_locals(local_blocks):
+    """per-configuration natoms_i x d arrays -> (stacked rows, int64 offsets[N+1])"""
+    blocks = [_lib.as_f64(b) for b in local_blocks]
+    if any(b.ndim != 2 for b in blocks):
+        raise ValueError("local descriptors must be natoms x d per configuration")
+    offsets = np.zeros(len(blocks) + 1, dtype=np.int64)
+    np.cumsum([b.shape[0] for b in blocks], out=offsets[1:])
+    L = np.ascontiguousarray(np.concatenate(blocks, axis=0)) if blocks else np.zeros((0, 1))
+    return L, offsets
+
+
+def global_features(local_blocks, mean: bool = True, stacked=None) -> np.ndarray:
+    """GlobalMean (mean=True) / GlobalSum (mean=False) features of N configurations on the GPU (pl_global_feature).
+    local_blocks: list of natoms_i x d arrays, or stacked=(L, offsets) if the caller already holds the packed form."""
+    import ctypes
+
+    L, offsets = stack_locals(local_blocks) if stacked is None else (_lib.as_f64(stacked[0]), np.ascontiguousarray(stacked[1], dtype=np.int64))
+    N = len(offsets) - 1
+    if N == 0:
+        return np.zeros((0, L.shape[1]))
+    if np.any(np.diff(offsets) <= 0):
+        raise ValueError("ArgumentError: reducing over an empty collection is not allowed (configuration without local descriptors)")
+    d = L.shape[1]
+    X = np.empty((N, d))
+    _lib.check(_lib.lib().pl_global_feature(_lib.dptr(L), d, offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), N, d, 1 if mean else 0,
+                                            _lib.dptr(X), d), "pl_global_feature")
+    return X
+
+
+def global_features_dev(L, offsets, mean: bool = True, out=None):
+    """Device-resident form on CUDA tensors: L (total_atoms x d float64), offsets (N+1 int64). Enqueues on the current stream."""
+    import torch
+
+    assert L.is_cuda and L.dtype == torch.float64 and L.dim() == 2 and L.stride(1) == 1
+    assert offsets.is_cuda and offsets.dtype == torch.int64 and offsets.is_contiguous()
+    N, d = offsets.numel() - 1, L.shape[1]
+    if out is None:
+        out = torch.empty((N, d + (d & 1)), device=L.device, dtype=torch.float64)[:, :d]
+    _lib.check(_lib.lib().pl_global_feature_dev(L.data_ptr(), L.stride(0), offsets.data_ptr(), N, d, 1 if mean else 0, out.data_ptr(), out.stride(0),
+                                                L.shape[0], torch.cuda.current_stream(L.device).cuda_stream), "pl_global_feature_dev")
+    return out
 
 
 # ------------------------------------------------------------------ distances (distances.jl) ----------------------

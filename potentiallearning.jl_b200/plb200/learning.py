@@ -111,6 +111,47 @@ def normal_equations(A, b=None, w=None, n_energy_rows=0, w_e=1.0, w_f=1.0, inter
     return M, v
 
 
+def normal_equations_blocks(blocks, b=None, w=None, n_energy_rows=0, w_e=1.0, w_f=1.0, intercept=False, lam=0.0, chunk_rows=0):
+    """Streamed GPU assembly over a LIST of row blocks (pl_normal_eq_blocks): no host-side concatenation. Each block is either a
+    K-vector (one row), a rows x K C-contiguous array, or a K x m Fortran-ordered / transposed view (Julia's column-major K x 3natoms
+    force-descriptor block, linear-learning-problem.jl:127) whose memory already is m rows of K."""
+    import ctypes
+
+    keep, ptrs, rows = [], [], []
+    K = None
+    for blk in blocks:
+        a = np.asarray(blk, dtype=np.float64)
+        if a.ndim == 1:
+            a = a[None, :]
+        elif not a.flags.c_contiguous and a.T.flags.c_contiguous:
+            a = a.T  # K x m column-major == m x K row-major: the bytes are used as they are
+        a = np.ascontiguousarray(a)
+        if K is None:
+            K = a.shape[1]
+        if a.shape[1] != K:
+            raise ValueError("DimensionMismatch: blocks of different descriptor length")
+        keep.append(a)
+        ptrs.append(a.ctypes.data)
+        rows.append(a.shape[0])
+    if K is None:
+        raise ValueError("no blocks")
+    nb = len(keep)
+    PtrArr = ctypes.POINTER(ctypes.c_double) * nb
+    parr = PtrArr(*[ctypes.cast(p, ctypes.POINTER(ctypes.c_double)) for p in ptrs])
+    rarr = (ctypes.c_int64 * nb)(*rows)
+    n = K + (1 if intercept else 0)
+    b = None if b is None else _lib.as_f64(b)
+    w = None if w is None else _lib.as_f64(w)
+    M = np.empty((n, n))
+    v = np.empty(n) if b is not None else None
+    _lib.check(
+        _lib.lib().pl_normal_eq_blocks(parr, rarr, nb, K, _lib.dptr(w), int(n_energy_rows), float(w_e), float(w_f), _lib.dptr(b),
+                                       1 if intercept else 0, float(lam), int(chunk_rows), _lib.dptr(M), _lib.dptr(v)),
+        "pl_normal_eq_blocks",
+    )
+    return M, v
+
+
 def _solve(M, v):
     """βs = M \\ v, falling back to pinv(M)*v on a singular system (linear-learn.jl:199-205, 252-258)."""
     try:
@@ -156,8 +197,9 @@ def _learn_wls(lp, ws, intercept: bool, λ: float = 0.0, lam: float | None = Non
         # Q = Diagonal(ws[1] * ones(length(e_train))) (:196); the intercept column is all ones (:189-190)
         M, v = normal_equations(A, b, None, A.shape[0], ws[0], ws[0], intercept, 0.0)
     else:
-        A, _, b = assemble_matrices(lp, ws)
-        M, v = normal_equations(A, b, None, len(lp.e), ws[0], ws[1], intercept, λ)
+        # A = [B; dB] (linear-learn.jl:238-244) is never materialised on the host: lp.B / lp.dB[i] are handed to the library as they lie
+        b = np.concatenate([pack_rhs(lp.e), pack_rhs(lp.f)])
+        M, v = normal_equations_blocks(list(lp.B) + list(lp.dB), b, None, len(lp.e), ws[0], ws[1], intercept, λ)
     βs = _solve(M, v)
     if intercept:
         lp.β0[:] = βs[0]

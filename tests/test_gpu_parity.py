@@ -726,3 +726,166 @@ def test_config4_slice_checksums(pl):
     C2, m2 = covariance_sharded(X, n, mean=m, engine=eng)  # pca.m persists (pca_state.jl:34)
     assert bool(torch.equal(m2, m)) and bool(torch.equal(C2, C))
     del X
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# feature / row packing on the device
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [1, 7, 8, 26, 63, 64, 65, 300])
+def test_global_features_bit_exact(pl, orc, d):
+    """GlobalMean / GlobalSum on the GPU walk Julia's summation tree: bit-identical to the restated reference sum."""
+    rng = np.random.default_rng(d)
+    natoms = [1, 2, 3, 20, 96, 1023, 1024, 1025, 2500] if d <= 26 else [1, 20, 96, 1030]
+    blocks = [rng.standard_normal((n, d)) * 3.0 + rng.standard_normal(d) for n in natoms for _ in range(2)]
+    for mean in (True, False):
+        X = pl.global_features(blocks, mean=mean)
+        Xo = orc.global_features(blocks, mean)
+        assert X.shape == (len(blocks), d)
+        assert np.array_equal(X, Xo), (d, mean, float(np.max(np.abs(X - Xo))))
+    with pytest.raises(ValueError):
+        pl.global_features([np.ones((2, d)), np.ones((0, d))])
+
+
+def test_compute_features_and_kernel_matrix_from_dataset(pl, orc):
+    """KernelMatrix(ds, GlobalMean(), k) (kernels.jl:250-253): features on the GPU, then the Gram kernel."""
+    rng = np.random.default_rng(12)
+    ds = fake_dataset(pl, rng, 40, 20, 8)
+    F = pl.compute_features(ds, pl.GlobalMean())
+    Fo = [orc.global_mean(list(pl.get_values(pl.get_local_descriptors(c)))) for c in ds]
+    assert np.array_equal(F, np.stack(Fo))
+    S = pl.compute_features(ds, pl.GlobalSum())
+    assert np.array_equal(S, np.stack([orc.global_sum(list(pl.get_values(pl.get_local_descriptors(c)))) for c in ds]))
+    K = np.asarray(pl.KernelMatrix(ds, pl.GlobalMean(), pl.RBF(pl.Euclidean(8))))
+    Ko = orc.symmetric(orc.kernel_matrix(Fo, orc.RBF(orc.Euclidean(8))))
+    assert relerr(K, Ko) < RTOL
+
+
+def test_global_features_device_resident_bandwidth_shape(pl, orc):
+    """device-resident form on torch tensors (config-2 shape scaled down: 2000 configurations x 96 atoms x 300)."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    N, nat, d = 2000, 96, 300
+    L = rng.standard_normal((N * nat, d))
+    off = np.arange(N + 1, dtype=np.int64) * nat
+    Ld, offd = torch.from_numpy(L).cuda(), torch.from_numpy(off).cuda()
+    X = pl.global_features_dev(Ld, offd, mean=True)
+    torch.cuda.synchronize()
+    Xo = orc.global_features([L[i * nat:(i + 1) * nat] for i in range(0, N, 97)], True)
+    assert np.array_equal(X.cpu().numpy()[::97], Xo)
+
+
+@pytest.mark.parametrize("chunk_rows", [0, 16, 64, 1000])
+def test_normal_equations_blocks_streamed(pl, orc, chunk_rows):
+    """pl_normal_eq_blocks: lp.B / lp.dB[i] handed over as they lie in memory, rows streamed in chunks (any chunking must
+    give the same answer to rounding; the chunk partials are accumulated in fixed order)."""
+    rng = np.random.default_rng(33)
+    K, ncfg = 24, 37
+    natoms = rng.integers(1, 9, size=ncfg)
+    B = [rng.standard_normal(K) * 4 for _ in range(ncfg)]
+    dB = [np.asfortranarray(rng.standard_normal((K, 3 * n))) for n in natoms]  # Julia's column-major K x 3natoms
+    e = rng.standard_normal(ncfg)
+    f = [rng.standard_normal(3 * n) for n in natoms]
+    A = np.concatenate([np.stack(B)] + [m.T for m in dB], axis=0)
+    b = np.concatenate([e] + f)
+    R = A.shape[0]
+    for intercept, lam, (we, wf) in ((False, 0.0, (1.0, 1.0)), (True, 0.01, (100.0, 1.0))):
+        M, v = pl.normal_equations_blocks(B + dB, b, None, ncfg, we, wf, intercept, lam, chunk_rows=chunk_rows)
+        q = np.concatenate([we * np.ones(ncfg), wf * np.ones(R - ncfg)])
+        Ai = np.hstack([np.concatenate([np.ones(ncfg), np.zeros(R - ncfg)])[:, None], A]) if intercept else A
+        Mo, vo = orc.normal_equations(Ai, b, q, lam)
+        assert normerr(M, Mo) < RTOL and normerr(v, vo) < RTOL
+        assert np.array_equal(M, M.T)
+    w = rng.uniform(0.1, 3.0, size=R)
+    M, v = pl.normal_equations_blocks(B + dB, b, w, chunk_rows=chunk_rows)
+    Mo, vo = orc.normal_equations(A, b, w, 0.0)
+    assert normerr(M, Mo) < RTOL and normerr(v, vo) < RTOL
+    # the same call twice is bitwise reproducible
+    M2, v2 = pl.normal_equations_blocks(B + dB, b, w, chunk_rows=chunk_rows)
+    assert np.array_equal(M, M2) and np.array_equal(v, v2)
+
+
+def test_normal_equations_large_input_streams(pl, orc):
+    """pl_normal_eq switches to the streamed path above 768 MB of rows; same result as the resident device path."""
+    import torch
+
+    rng = np.random.default_rng(8)
+    R, K = 420_000, 256  # 860 MB
+    A = rng.standard_normal((R, K))
+    b = rng.standard_normal(R)
+    M, v = pl.normal_equations(A, b, None, 1000, 30.0, 1.0, True, 0.01)
+    from plb200.device import DeviceEngine
+
+    eng = DeviceEngine()
+    S, vec = eng.syrk_partial(torch.from_numpy(A).cuda(), None, 1000, 30.0, 1.0, torch.from_numpy(b).cuda(), None, True)
+    Md, vd = eng.normal_eq_finish(S, vec, True, 0.01)
+    assert normerr(M, Md.cpu().numpy()) < 1e-13 and normerr(v, vd.cpu().numpy()) < 1e-13
+    assert np.array_equal(M, M.T)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY.md 8f row f1: eigendecomposition and the L-ensemble on the device
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 7, 130, 1000])
+def test_eigh_matches_lapack(pl, orc, n):
+    """pl_eigh against LAPACK (numpy.linalg.eigh — the same syev family the reference reaches through eigen(Symmetric))."""
+    from plb200.dpp import eigh
+
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, n + 3))
+    A = B @ B.T / (n + 3) + np.diag(rng.uniform(0, 2, n))
+    lam, U = eigh(A)
+    lo, _ = np.linalg.eigh(A)
+    scale = np.max(np.abs(lo))
+    assert np.max(np.abs(lam - lo)) / scale < 1e-13
+    assert np.all(np.diff(lam) >= 0), "ascending, as eigen() returns"
+    assert np.max(np.abs(A @ U - U * lam[None, :])) / scale < 1e-12, "residual"
+    assert np.max(np.abs(U.T @ U - np.eye(n))) < 1e-12, "orthonormal"
+    # one triangle is enough: Symmetric(:U) storage (the other triangle holds garbage)
+    Au = np.triu(A) + np.tril(rng.standard_normal((n, n)), -1)
+    lam_u = eigh(Au, fill="U", vectors=False)
+    assert np.max(np.abs(lam_u - lo)) / scale < 1e-13
+
+
+def test_ell_ensemble_resident_pipeline(pl, orc):
+    """EllEnsemble(KernelMatrix(F, k)) fused on the device: λ, K, inclusion probabilities and selected eigenvectors against the
+    host-side definitions evaluated on the oracle's kernel matrix."""
+    rng = np.random.default_rng(77)
+    n, d = 700, 12
+    X = rng.standard_normal((n, d)) * 0.4 + rng.standard_normal(d)
+    k = pl.RBF(pl.Euclidean(d), ell=1.5)
+    ell = pl.EllEnsemble.from_features(X, k)
+    Ko = orc.symmetric(orc.kernel_matrix(X, orc.RBF(orc.Euclidean(d), ell=1.5)))
+    assert relerr(ell.L, Ko) < RTOL
+    lo, Uo = np.linalg.eigh(Ko)
+    assert np.max(np.abs(ell.λ - np.maximum(lo, 0))) / lo.max() < 1e-12
+    pl.rescale_(ell, 50)
+    p = pl.inclusion_prob(ell)  # device: U never downloaded
+    assert ell._U is None
+    g = ell.α * np.maximum(lo, 0)
+    g = g / (1 + g)
+    po = np.sum(Uo * Uo * g[None, :], axis=1)
+    assert abs(p.sum() - 50.0) < 1e-8 and np.max(np.abs(p - po)) < 1e-10
+    J = [n - 1, n - 2, 5, n - 40]
+    V = ell.eigvecs(J)
+    assert V.shape == (n, 4) and ell._U is None
+    for c, jj in enumerate(J):
+        if lo[jj] > 1e-6 * lo.max():  # (eigenvectors of the numerically-null space are not unique)
+            assert np.max(np.abs(Ko @ V[:, c] - lo[jj] * V[:, c])) / lo.max() < 1e-11
+    s1 = pl.sample(ell, 50, rng=np.random.default_rng(3))
+    assert len(set(s1)) == 50
+    # a second resident ensemble evicts the first one, which stays usable (small: U is downloaded on eviction)
+    ell2 = pl.EllEnsemble.from_features(X[:100], pl.DotProduct())
+    assert ell._U is not None and not ell._resident and ell2._resident
+    assert pl.sample(ell, 50, rng=np.random.default_rng(3)) == s1
+
+
+def test_compute_eigen_and_pca_on_device(pl, orc):
+    """compute_eigen (dimension_reduction.jl:11-14): covariance and eigen both on the GPU; eigenvalues against the oracle."""
+    rng = np.random.default_rng(4)
+    rows = rng.standard_normal((500, 30)) @ np.diag(np.linspace(0.1, 3, 30))
+    lam, phi = pl.compute_eigen(rows)
+    lo, _ = orc.compute_eigen(list(rows))
+    assert np.max(np.abs(lam - lo)) / lo.max() < 1e-12
+    Q = rows.T @ rows / 500
+    assert np.max(np.abs(Q @ phi - phi * lam[None, :])) / lo.max() < 1e-12

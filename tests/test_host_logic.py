@@ -30,7 +30,9 @@ def test_features_match_reference_definition():
         assert np.array_equal(pl.compute_feature(c, gm), orc.global_mean(list(b)))
         assert np.array_equal(pl.compute_feature(c, gs), orc.global_sum(list(b)))
         assert np.array_equal(pl.compute_feature(c, gm, dt=pl.ForceDescriptors), pl.compute_feature(c, gm))  # dt ignored (features.jl:59-61)
-    assert len(pl.compute_features(ds, gm)) == len(ds)
+    # compute_features over a whole DataSet is a GPU segmented reduction (pl_global_feature): see tests/test_gpu_parity.py
+    L, off = pl.stack_locals([pl.get_values(pl.get_local_descriptors(c)) for c in ds])
+    assert L.shape == (120, 8) and list(off) == [0, 20, 40, 60, 80, 100, 120]
     with pytest.raises(KeyError):
         pl.get_energy(ds[0])
 
@@ -113,7 +115,7 @@ def test_kdpp_host_routines_on_oracle_kernel():
     rng = np.random.default_rng(5)
     X = rng.standard_normal((40, 6)) + 1.0
     K = orc.symmetric(orc.kernel_matrix(X, orc.DotProduct()))
-    ell = pl.EllEnsemble(K)
+    ell = pl.EllEnsemble.from_eigen(*np.linalg.eigh(K), L=K)  # the GPU eigendecomposition (pl_eigh) is covered by the gpu tests
     pl.rescale_(ell, 5)
     ip = pl.inclusion_prob(ell)
     assert abs(ip.sum() - 5.0) < 1e-8 and np.all(ip > 0) and np.all(ip < 1)
