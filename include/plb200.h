@@ -186,11 +186,11 @@ int64_t pl_gram_tile_count(int64_t n1, int64_t n2, int part, int nparts);
 /* tile-row / tile-column (units of 128) of the k-th tile owned by `part`; returns 0 or PL_EINVAL */
 int pl_gram_tile_coords(int64_t n1, int64_t n2, int part, int nparts, int64_t k, int64_t* ti, int64_t* tj);
 
-/* Partial weighted SYRK of a row shard: S = sum_r w_r (a_r-m)(a_r-m)' and, if db or n_energy_rows>0 requested,
+/* Partial weighted SYRK of a row shard: S = sum_r w_r (a_r-m)(a_r-m)' and, if dvec != NULL,
  * v = sum_r w_r b_r a_r, c = sum_{r<n_energy_rows} w_r a_r, s = [sum_{r<ne} w_r, sum_{r<ne} w_r b_r].
  * dmean == NULL -> no centring. Outputs are UNSCALED sums so shards can be all-reduced:
  *   dS  : Kf x Kf full symmetric, leading dim Kf
- *   dvec: 2*Kf + 2 doubles = [v (Kf) ; c (Kf) ; s (2)]  (may be NULL if neither b nor the intercept is wanted) */
+ *   dvec: 2*Kf + 2 doubles = [v (Kf) ; c (Kf) ; s (2)]  (may be NULL if neither b nor the intercept is wanted; not with dmean) */
 int pl_syrk_dev(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dw, int64_t n_energy_rows, double w_e,
                 double w_f, const double* db, const double* dmean, double* dS, double* dvec, void* stream);
 /* Assemble (AtWA, AtWb) of order Kf+ic from (all-reduced) S / vec as pl_normal_eq defines them. */

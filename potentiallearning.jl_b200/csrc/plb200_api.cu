@@ -93,6 +93,8 @@ enum WsSlot {
   WS_EIG_P,
   WS_EIG_IDX,
   WS_EIG_SEL,
+  WS_TRACE,
+  WS_SYRK_AUX,
   WS_NSLOTS
 };
 
@@ -188,21 +190,55 @@ int tma_operand(const double* src, int64_t rows, int64_t cols, int64_t ld, int s
   return PL_OK;
 }
 
-int colsum(const double* dA, int64_t R, int64_t Kf, int64_t lda, double denom, double* dout, cudaStream_t st) {
+int64_t colsum_rows_per_block(int64_t R, int64_t Kf) {
   // rows per block: aim at >= 16 blocks per SM, between 32 and 512 rows each (fixed for a given shape: deterministic)
   const int64_t colblocks = ((Kf + 1) / 2 + 127) / 128;
   int64_t rpb = R * colblocks / ((int64_t)g.num_sms * 16);
-  rpb = rpb < 32 ? 32 : (rpb > COLSUM_MAX_ROWS_PER_BLOCK ? COLSUM_MAX_ROWS_PER_BLOCK : (rpb + 3) / 4 * 4);
+  return rpb < 32 ? 32 : (rpb > COLSUM_MAX_ROWS_PER_BLOCK ? COLSUM_MAX_ROWS_PER_BLOCK : (rpb + 3) / 4 * 4);
+}
+
+int colsum(const double* dA, int64_t R, int64_t Kf, int64_t lda, double denom, double* dout, cudaStream_t st, const double* dshift = nullptr) {
+  const int64_t rpb = colsum_rows_per_block(R, Kf);
   const int64_t nblk = (R + rpb - 1) / rpb;
   void* part;
   PL_TRY(ws_get(WS_COLSUM_PARTIAL, (size_t)(nblk > 0 ? nblk : 1) * Kf * 8, &part));
   if (nblk > 0) {
     const int64_t pairs = (Kf + 1) / 2;
     dim3 grid((unsigned)((pairs + 127) / 128), (unsigned)nblk);
-    colsum_partial_kernel<<<grid, 128, 0, st>>>(dA, R, Kf, lda, (int)rpb, (double*)part);
+    colsum_partial_kernel<<<grid, 128, 0, st>>>(dA, R, Kf, lda, (int)rpb, (double*)part, dshift);
     LAUNCH_CHECK();
   }
   colsum_final_kernel<<<(unsigned)((Kf + 31) / 32), 256, 0, st>>>((const double*)part, nblk, Kf, denom, dout);
+  LAUNCH_CHECK();
+  return PL_OK;
+}
+
+// moment vectors of the normal equations: dv (may be NULL iff db is NULL) = A'(w.b), dc = A'(w.[r < ne]); unscaled, deterministic
+int moment_vectors(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dw, int64_t ne, double w_e, double w_f, const double* db,
+                   double* dv, double* dc, cudaStream_t st) {
+  // without a right-hand side only the first ne rows contribute
+  const int64_t Rv = db ? R : ne;
+  const int64_t rpb = colsum_rows_per_block(Rv, Kf);
+  const int64_t nblk = (Rv + rpb - 1) / rpb;
+  void* part;
+  PL_TRY(ws_get(WS_COLSUM_PARTIAL, (size_t)(nblk > 0 ? nblk : 1) * Kf * 8 * 2, &part));
+  double* pv = (double*)part;
+  double* pc = pv + (nblk > 0 ? nblk : 1) * Kf;
+  if (nblk > 0) {
+    const int64_t pairs = (Kf + 1) / 2;
+    dim3 grid((unsigned)((pairs + 127) / 128), (unsigned)nblk);
+    wcolsum_partial_kernel<<<grid, 128, 0, st>>>(dA, Rv, Kf, lda, dw, ne, w_e, w_f, db, (int)rpb, pv, pc);
+    LAUNCH_CHECK();
+  }
+  // blocks beyond the energy rows hold zeros in pc: only the first ceil(ne / rpb) blocks are summed
+  const int64_t nblk_c = ne > 0 ? (ne + rpb - 1) / rpb : 0;
+  if (db) {
+    colsum_final_kernel<<<(unsigned)((Kf + 31) / 32), 256, 0, st>>>(pv, nblk, Kf, 0.0, dv);
+    LAUNCH_CHECK();
+  } else if (dv) {
+    CUDA_TRY(cudaMemsetAsync(dv, 0, (size_t)Kf * 8, st));
+  }
+  colsum_final_kernel<<<(unsigned)((Kf + 31) / 32), 256, 0, st>>>(pc, nblk_c < nblk ? nblk_c : nblk, Kf, 0.0, dc);
   LAUNCH_CHECK();
   return PL_OK;
 }
@@ -408,23 +444,20 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
 }
 
 void choose_splits(int64_t R, int nunits, int* splits, int64_t* rows_per_split) {
-  // one CTA per (work unit, row split), one CTA per SM at a time. Pick the number of waves (1..6) whose last wave is
-  // fullest; ties go to MORE waves (work units are not perfectly equal — e.g. blocks that also accumulate A'Wb — and the
-  // hardware block scheduler evens that out only when there is more than one wave). Keep >= 256 rows per CTA.
-  int best = 1;
-  double best_eff = 0.0;
-  for (int w = 1; w <= 6; ++w) {
-    const int s = (g.num_sms * w) / nunits;
-    if (s < 1) continue;
-    const double eff = (double)(nunits * s) / (double)(g.num_sms * w);
-    if (eff >= best_eff - 1e-9) {
-      best_eff = eff;
-      best = s;
-    }
-  }
-  int64_t max_by_rows = R / 256;
+  // One CTA per (work unit, row split), one CTA resident per SM. Work units are not equal (a diagonal unit costs ~1.06-1.19 x an
+  // off-diagonal one) and the hardware hands CTAs to SMs as they free up, so the makespan is total/148 plus about one CTA: keep CTAs
+  // SHORT — ~20 per SM (measured with the trace hook: 5-6 long CTAs per SM left 9 % of the machine idle at the tail) — while each
+  // still streams >= 1024 rows (64 pipeline stages) so that pipeline fill and the 160 KB partial it writes stay below 1 %.
+  static const int waves = [] {
+    const char* e = getenv("PLB200_SYRK_WAVES");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 20;
+  }();
+  int64_t s = ((int64_t)g.num_sms * waves + nunits - 1) / nunits;
+  int64_t max_by_rows = R / 1024;
   if (max_by_rows < 1) max_by_rows = 1;
-  int64_t s = best < max_by_rows ? best : max_by_rows;
+  if (s > max_by_rows) s = max_by_rows;
+  if (s < 1) s = 1;
   int64_t rps = (R + s - 1) / s;
   rps = (rps + SYRK_BK - 1) / SYRK_BK * SYRK_BK;
   if (rps < SYRK_BK) rps = SYRK_BK;
@@ -455,39 +488,80 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
   p.w_f = w_f;
   p.b = db;
   p.mean = dmean;
-  p.want_vec = dvec ? 1 : 0;
   p.T = (int)((Kf + SYRK_BT - 1) / SYRK_BT);
   p.ntiles = syrk_num_units(p.T);
   choose_splits(R, p.ntiles, &p.splits, &p.rows_per_split);
-  void *wst, *wsv = nullptr;
+  void* wst;
   PL_TRY(ws_get(WS_SYRK_TILES, (size_t)p.splits * p.ntiles * SYRK_TILE_ELEMS * 8, &wst));
   void* rho = nullptr;
-  if (p.want_vec || dmean) PL_TRY(ws_get(WS_SYRK_VEC, (size_t)p.splits * 2 * p.T * SYRK_BT * 8, &wsv));
   if (dmean) PL_TRY(ws_get(WS_SYRK_RHO, (size_t)Kf * 8, &rho));
   p.ws_tiles = (double*)wst;
-  p.ws_vec = (double*)wsv;
 
-  CUtensorMap tm;
+  // developer hook: PLB200_SYRK_TRACE=<file> dumps per-CTA timing (start, SM, end time of each consumer warp) of every SYRK launch
+  const char* trace_path = getenv("PLB200_SYRK_TRACE");
+  p.trace = nullptr;
+  if (trace_path && *trace_path) {
+    void* tr;
+    PL_TRY(ws_get(WS_TRACE, (size_t)p.ntiles * p.splits * 10 * 8, &tr));
+    CUDA_TRY(cudaMemsetAsync(tr, 0, (size_t)p.ntiles * p.splits * 10 * 8, st));
+    p.trace = (long long*)tr;
+  }
+
+  CUtensorMap tm, tmx;
   // R == 0: the kernel loads nothing (KT = 0) but the descriptor still needs a non-zero extent
   PL_TRY(make_tmap_2d(&tm, A, Kf, R > 0 ? R : 1, ld, 16, SYRK_BK));
+  // Moment vectors: ride along as two extra columns of the last (padded) column block whenever it has room — the box holding
+  // column Kf is then loaded from an auxiliary R x 16 tensor (syrk_aux_box_kernel). Otherwise (Kf % 16 == 15 or Kf % 128 == 0):
+  // a weighted column-sum pass after the SYRK.
+  const bool aug = dvec && !dmean && R > 0 && (Kf % 128) != 0 && (Kf % 16) <= 14 && !getenv("PLB200_SYRK_NO_AUG");
+  p.aux_box = -1;
+  tmx = tm;
+  if (aug) {
+    void* aux;
+    PL_TRY(ws_get(WS_SYRK_AUX, (size_t)R * 16 * 8, &aux));
+    syrk_aux_box_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, st>>>(A, R, Kf, ld, db, ne, (double*)aux);
+    LAUNCH_CHECK();
+    PL_TRY(make_tmap_2d(&tmx, (const double*)aux, 16, R, 16, 16, SYRK_BK));
+    p.aux_box = (int)(Kf / 16);
+  }
   dim3 grid((unsigned)p.ntiles, (unsigned)p.splits);
   MAIN_KERNEL_BEGIN(st);
   if (dmean)
-    syrk_kernel<true, true><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, p);  // VEC: the rho vector of the one-sided centring
-  else if (p.want_vec)
-    syrk_kernel<false, true><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, p);
+    syrk_kernel<true><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, tmx, p);
   else
-    syrk_kernel<false, false><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, p);
+    syrk_kernel<false><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, tmx, p);
   LAUNCH_CHECK();
   MAIN_KERNEL_END(st);
-  if (dmean) {
-    syrk_rho_kernel<<<(unsigned)((Kf + 127) / 128), 128, 0, st>>>(p.ws_vec, p.T, p.splits, Kf, (double*)rho);
-    LAUNCH_CHECK();
+  if (p.trace) {
+    const size_t cnt = (size_t)p.ntiles * p.splits * 10;
+    long long* h = (long long*)malloc(cnt * 8);
+    if (h) {
+      CUDA_TRY(cudaMemcpyAsync(h, p.trace, cnt * 8, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      FILE* f = fopen(trace_path, "w");
+      if (f) {
+        fprintf(f, "# units %d splits %d T %d R %lld Kf %lld\n", p.ntiles, p.splits, p.T, (long long)R, (long long)Kf);
+        for (int sp = 0; sp < p.splits; ++sp)
+          for (int u = 0; u < p.ntiles; ++u) {
+            const long long* e = h + ((size_t)sp * p.ntiles + u) * 10;
+            fprintf(f, "%d %d %lld %lld", u, sp, e[0], e[1]);
+            for (int w = 0; w < 8; ++w) fprintf(f, " %lld", e[2 + w]);
+            fprintf(f, "\n");
+          }
+        fclose(f);
+      }
+      free(h);
+    }
   }
-  syrk_reduce_kernel<<<dim3((unsigned)p.ntiles, 8), 256, 0, st>>>(p.ws_tiles, p.ws_vec, p.T, p.ntiles, p.splits, Kf, dS, dvec, p.want_vec, dmean,
-                                                                  (const double*)rho);
+  if (dmean) {
+    // rho_i = sum_r (a_ri - m_i) closes the one-sided centring (S_ij = S'_ij - rho_i m_j): one HBM-rate pass, differences first
+    PL_TRY(colsum(A, R, Kf, ld, 0.0, (double*)rho, st, dmean));
+  }
+  syrk_reduce_kernel<<<dim3((unsigned)p.ntiles, SYRK_TILE_ELEMS / 256), 256, 0, st>>>(p.ws_tiles, p.T, p.ntiles, p.splits, Kf, dS, dmean, (const double*)rho,
+                                                                                   aug ? dvec : nullptr);
   LAUNCH_CHECK();
-  if (p.want_vec) {
+  if (dvec && !aug) {
+    PL_TRY(moment_vectors(A, R, Kf, ld, dw, ne, w_e, w_f, db, dvec, dvec + Kf, st));
     syrk_scalar_kernel<<<1, 1024, 0, st>>>(dw, db, ne, w_e, dvec + 2 * Kf);
     LAUNCH_CHECK();
   }
@@ -787,9 +861,8 @@ int pl_init(int device) {
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_IMQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
   g.ready = true;
   return PL_OK;
 }

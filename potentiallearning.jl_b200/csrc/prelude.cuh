@@ -12,9 +12,11 @@ namespace plb {
 
 constexpr int COLSUM_MAX_ROWS_PER_BLOCK = 512;
 
-// partial[blockIdx.y][col] = sum of rows [blockIdx.y*rpb, ...) of column col. blockDim.x threads x 2 columns each.
-// rpb (rows per block) is chosen by the host so that small matrices still fill the machine.
-__global__ void colsum_partial_kernel(const double* __restrict__ A, int64_t R, int64_t Kf, int64_t lda, int rpb, double* __restrict__ partial) {
+// partial[blockIdx.y][col] = sum of rows [blockIdx.y*rpb, ...) of column col (minus shift[col] per element if shift != NULL: the
+// centred column sums rho = sum_r (a_r - m) that close the SYRK's one-sided centring — differences first, so nothing cancels).
+// blockDim.x threads x 2 columns each. rpb (rows per block) is chosen by the host so that small matrices still fill the machine.
+__global__ void colsum_partial_kernel(const double* __restrict__ A, int64_t R, int64_t Kf, int64_t lda, int rpb, double* __restrict__ partial,
+                                      const double* __restrict__ shift) {
   const int64_t c0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (c0 >= Kf) return;
   const int64_t r0 = (int64_t)blockIdx.y * rpb;
@@ -22,6 +24,8 @@ __global__ void colsum_partial_kernel(const double* __restrict__ A, int64_t R, i
   if (r1 > R) r1 = R;
   const bool pair = (c0 + 1 < Kf);
   double s0 = 0.0, s1 = 0.0;
+  const double z0 = shift ? __ldg(shift + c0) : 0.0;
+  const double z1 = (shift && pair) ? __ldg(shift + c0 + 1) : 0.0;
   const double* ptr = A + r0 * lda + c0;
   int64_t r = r0;
   if (pair) {
@@ -31,20 +35,20 @@ __global__ void colsum_partial_kernel(const double* __restrict__ A, int64_t R, i
       const double2 v1 = __ldg(reinterpret_cast<const double2*>(ptr + lda));
       const double2 v2 = __ldg(reinterpret_cast<const double2*>(ptr + 2 * lda));
       const double2 v3 = __ldg(reinterpret_cast<const double2*>(ptr + 3 * lda));
-      s0 += v0.x; s1 += v0.y;
-      s0 += v1.x; s1 += v1.y;
-      s0 += v2.x; s1 += v2.y;
-      s0 += v3.x; s1 += v3.y;
+      s0 += v0.x - z0; s1 += v0.y - z1;
+      s0 += v1.x - z0; s1 += v1.y - z1;
+      s0 += v2.x - z0; s1 += v2.y - z1;
+      s0 += v3.x - z0; s1 += v3.y - z1;
       ptr += 4 * lda;
     }
     for (; r < r1; ++r) {
       const double2 v = __ldg(reinterpret_cast<const double2*>(ptr));
-      s0 += v.x; s1 += v.y;
+      s0 += v.x - z0; s1 += v.y - z1;
       ptr += lda;
     }
   } else {
     for (; r < r1; ++r) {
-      s0 += __ldg(ptr);
+      s0 += __ldg(ptr) - z0;
       ptr += lda;
     }
   }
@@ -354,6 +358,67 @@ __global__ void gather_rows_kernel(const double* __restrict__ V, int64_t n, int6
   if (r >= m) return;
   const double* src = V + idx[r] * ldv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[r * n + i] = src[i];
+}
+
+// Weighted column sums of a row block — the moment vectors of the normal equations (an HBM-rate pass of their own: inside the DMMA
+// loop of the SYRK every scalar FP64 instruction costs about a DMMA, see syrk.cuh):
+//   pv[blk][col] = sum_r w_r b_r A[r][col]   (A'Wb, linear-learn.jl:200, 253)        — only if b != NULL
+//   pc[blk][col] = sum_{r < ne} w_r A[r][col] (the intercept row/column [1_N; 0_M]' W A, linear-learn.jl:239-241)
+// w_r = w[r] if w != NULL else (r < ne ? w_e : w_f). Same geometry as colsum_partial_kernel; colsum_final_kernel adds the blocks.
+__global__ void wcolsum_partial_kernel(const double* __restrict__ A, int64_t R, int64_t Kf, int64_t lda, const double* __restrict__ w, int64_t ne,
+                                       double w_e, double w_f, const double* __restrict__ b, int rpb, double* __restrict__ pv, double* __restrict__ pc) {
+  const int64_t c0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (c0 >= Kf) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rpb;
+  int64_t r1 = r0 + rpb;
+  if (r1 > R) r1 = R;
+  const bool pair = (c0 + 1 < Kf);
+  double v0 = 0.0, v1 = 0.0, s0 = 0.0, s1 = 0.0;
+  const double* ptr = A + r0 * lda + c0;
+  auto row = [&](int64_t r, double2 a) {
+    const double wr = w ? __ldg(w + r) : (r < ne ? w_e : w_f);
+    if (b) {
+      const double wb = wr * __ldg(b + r);
+      v0 = fma(a.x, wb, v0);
+      v1 = fma(a.y, wb, v1);
+    }
+    if (r < ne) {
+      s0 = fma(a.x, wr, s0);
+      s1 = fma(a.y, wr, s1);
+    }
+  };
+  int64_t r = r0;
+  if (pair) {
+    for (; r + 4 <= r1; r += 4) {
+      const double2 a0 = __ldg(reinterpret_cast<const double2*>(ptr));
+      const double2 a1 = __ldg(reinterpret_cast<const double2*>(ptr + lda));
+      const double2 a2 = __ldg(reinterpret_cast<const double2*>(ptr + 2 * lda));
+      const double2 a3 = __ldg(reinterpret_cast<const double2*>(ptr + 3 * lda));
+      row(r, a0);
+      row(r + 1, a1);
+      row(r + 2, a2);
+      row(r + 3, a3);
+      ptr += 4 * lda;
+    }
+    for (; r < r1; ++r) {
+      row(r, __ldg(reinterpret_cast<const double2*>(ptr)));
+      ptr += lda;
+    }
+  } else {
+    for (; r < r1; ++r) {
+      double2 a;
+      a.x = __ldg(ptr);
+      a.y = 0.0;
+      row(r, a);
+      ptr += lda;
+    }
+  }
+  if (b) {
+    pv[(int64_t)blockIdx.y * Kf + c0] = v0;
+    if (pair) pv[(int64_t)blockIdx.y * Kf + c0 + 1] = v1;
+  }
+  pc[(int64_t)blockIdx.y * Kf + c0] = s0;
+  if (pair) pc[(int64_t)blockIdx.y * Kf + c0 + 1] = s1;
 }
 
 }  // namespace plb

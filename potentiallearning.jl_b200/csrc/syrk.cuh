@@ -7,12 +7,10 @@
 //
 // Geometry: the contraction runs over ROWS of one row-major R x Kf matrix, so both MMA operands are "MN-major"
 // (the output index is contiguous in memory) — the transpose of the Gram kernel's geometry:
-//   * CTA (unit, split): a work unit is 8 warp blocks of 32 (i) x 64 (j) output elements x a contiguous row range.
-//     Off-diagonal 128 x 128 tiles are one unit each (4 x 2 warp blocks). A diagonal tile only needs 6 of its 8 warp
-//     blocks (the two below the diagonal are pure mirror images), so the diagonal blocks of ALL tiles are packed 8 per
-//     unit (a unit then spans at most two column blocks, the same shared-memory footprint as an off-diagonal tile):
-//     T(T-1)/2 + ceil(6T/8) units instead of T(T+1)/2 tiles, e.g. 9 instead of 10 at K = 500, and every warp of every
-//     unit does useful work. Partial blocks go to a workspace in fragment order (perfectly coalesced) and a
+//   * CTA (unit, split): a work unit is 8 warp jobs x a contiguous row range. Off-diagonal 128 x 128 tiles are one unit
+//     each (4 x 2 warp blocks of 32 x 64). Diagonal tiles are packed two per unit as four 64 x 64 diagonal squares (one warp
+//     each, only the 10 upper box pairs of the 4 x 4 grid of 16-column fragment boxes) plus their four upper-right 32 x 64
+//     blocks — see syrk_warp_block. Partials go to a workspace in fragment order (perfectly coalesced) and a
 //     deterministic second-stage kernel sums the splits in fixed order, mirrors, and applies scale / ridge / intercept;
 //   * stage = 16 rows x 128 columns per operand, brought in as 8 TMA boxes of 16 rows x 16 columns (128 bytes wide,
 //     128B swizzle); diagonal tiles load one operand only;
@@ -26,6 +24,8 @@
 //     FP64 shares the pipe with the DMMAs); the terms are |sigma*m| instead of sigma^2, an error of order eps*(m/sigma)
 //     relative to the largest entry in the worst case, far inside the 1e-10 contract even at mean/sigma = 50.
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace plb {
@@ -38,7 +38,8 @@ constexpr int SYRK_THREADS = (SYRK_CONSUMER_WARPS + 4) * 32;  // 2 DMMA warpgrou
 constexpr int SYRK_BOX_BYTES = SYRK_BK * 16 * 8;        // 2 KB: 16 rows x 16 cols
 constexpr int SYRK_OP_BYTES = 8 * SYRK_BOX_BYTES;       // 16 KB per operand per stage
 constexpr int SYRK_SMEM_BYTES = SYRK_STAGES * 2 * SYRK_OP_BYTES + 1024 + 256;
-constexpr int SYRK_TILE_ELEMS = SYRK_BT * SYRK_BT;      // 16384 accumulators per partial tile
+constexpr int SYRK_UNIT_ACC = 80;                        // accumulator slots per thread in a unit's partial (squares: 80, blocks: 64)
+constexpr int SYRK_TILE_ELEMS = SYRK_UNIT_ACC * 256;     // doubles per (split, unit) partial
 
 struct SyrkParams {
   int64_t R, Kf;
@@ -47,27 +48,37 @@ struct SyrkParams {
   double w_e, w_f;
   const double* b;        // right-hand side or NULL
   const double* mean;     // column means (centred mode) or NULL
-  int want_vec;           // accumulate v / c on diagonal tiles
   int T;                  // column blocks = ceil(Kf / 128)
-  int ntiles;             // work units: T (T-1) / 2 off-diagonal tiles + ceil(6 T / 8) packs of diagonal warp blocks
+  int ntiles;             // work units: T (T-1) / 2 off-diagonal tiles + ceil(T / 2) diagonal units
   int splits;             // row splits
   int64_t rows_per_split; // multiple of SYRK_BK
-  double* ws_tiles;       // [split][tile][64 acc][256 threads]
-  double* ws_vec;         // [split][2][T*128]   (v then c), only if want_vec
+  double* ws_tiles;       // [split][unit][80 acc][256 threads]
+  int aux_box;            // >= 0: the 16-column box (global index) that is loaded from the auxiliary tensor instead of A (see
+                          // syrk_aux_box_kernel: the moment vectors ride along as two extra columns); -1: none
+  long long* trace;       // NULL, or 10 int64 per CTA: [globaltimer at start, SM id, end time of consumer warps 0..7] (PLB200_SYRK_TRACE)
 };
 
-// The 6 warp blocks (wm = 32-column slab of i, wn = 64-column slab of j) of a diagonal tile that touch j >= i.
-// Blocks 0, 2, 4, 5 — one per wm — also accumulate the moment vectors of their 32 i-columns.
-__host__ __device__ __forceinline__ int syrk_num_units(int T) { return T * (T - 1) / 2 + (6 * T + 7) / 8; }
+// Work decomposition of the upper triangle of the T x T grid of 128 x 128 tiles.
+//   * off-diagonal tile (ti < tj): one unit, 8 warps x (32 x 64) "blocks" = 32 DMMA tiles per k4-step each;
+//   * a diagonal tile needs its upper-right 64 x 64 quarter (two 32 x 64 blocks) and two 64 x 64 diagonal SQUARES. A square is
+//     computed by ONE warp at the granularity of the 16-column fragment boxes: the 10 box pairs (bi <= bj) of its 4 x 4 box grid =
+//     40 DMMA tiles per k4-step (80 accumulators), instead of the 64 tiles two full blocks would spend — and its A and B
+//     fragments are the same registers (4 LDS.128 per 40 DMMAs);
+//   * a diagonal UNIT packs two diagonal tiles: warps 0-3 = the four squares, warps 4-7 = the four upper-right blocks, so every
+//     SM sub-partition (warp w and w+4) carries 40 + 32 = 72 DMMA tiles per k4-step: 1.125 x an off-diagonal unit for two diagonal
+//     tiles. K = 500: 6 + 2 units costing 8.25 (the 6-of-8-blocks packing cost 9, whole diagonal tiles 10); computed / algorithmic
+//     flops 1.08 instead of 1.18.
+__host__ __device__ __forceinline__ int syrk_num_units(int T) { return T * (T - 1) / 2 + (T + 1) / 2; }
 
 struct SyrkWarpBlock {
-  int cb_a, wm;   // i columns: 128 cb_a + 32 wm + [0, 32)
-  int cb_b, wn;   // j columns: 128 cb_b + 64 wn + [0, 64)
+  int kind;       // 0: 32 x 64 block, 1: 64 x 64 diagonal square
+  int cb_a, wm;   // block: i columns 128 cb_a + 32 wm + [0, 32) ; square: i and j columns 128 cb_a + 64 wm + [0, 64)
+  int cb_b, wn;   // block: j columns 128 cb_b + 64 wn + [0, 64)
   int src_a, src_b;  // which of the unit's two operand buffers holds that column block
-  bool valid, vec;
+  bool valid;
 };
 
-// work unit u, warp w -> its block. cb0 / cb1: the (at most two) column blocks the unit loads into buffers 0 / 1.
+// work unit u, warp w -> its job. cb0 / cb1: the (at most two) column blocks the unit loads into buffers 0 / 1.
 __host__ __device__ __forceinline__ SyrkWarpBlock syrk_warp_block(int T, int u, int w, int& cb0, int& cb1) {
   SyrkWarpBlock B;
   const int noff = T * (T - 1) / 2;
@@ -79,117 +90,79 @@ __host__ __device__ __forceinline__ SyrkWarpBlock syrk_warp_block(int T, int u, 
     }
     cb0 = ti;
     cb1 = ti + 1 + rem;
+    B.kind = 0;
     B.cb_a = cb0; B.wm = w >> 1; B.src_a = 0;
     B.cb_b = cb1; B.wn = w & 1; B.src_b = 1;
     B.valid = true;
-    B.vec = false;
     return B;
   }
-  const int q = u - noff;  // pack q holds diagonal warp blocks 8q .. 8q+7 of the list (tile t, k): index 6t + k
-  const int first = 8 * q, last = (8 * q + 7 < 6 * T - 1) ? 8 * q + 7 : 6 * T - 1;
-  cb0 = first / 6;
-  cb1 = last / 6;
-  const int idx = first + w;
-  B.valid = idx < 6 * T;
-  const int t = B.valid ? idx / 6 : cb0, k = B.valid ? idx % 6 : 0;
-  // k: 0 -> (0,0)  1 -> (0,1)  2 -> (1,0)  3 -> (1,1)  4 -> (2,1)  5 -> (3,1)
-  B.wm = k < 4 ? (k >> 1) : (k - 2);
-  B.wn = k < 4 ? (k & 1) : 1;
+  const int q = u - noff;  // diagonal unit q: diagonal tiles 2q and (if it exists) 2q + 1
+  const bool two = 2 * q + 1 < T;
+  cb0 = 2 * q;
+  cb1 = two ? 2 * q + 1 : 2 * q;
+  const int ww = w & 3;
+  const int sel = ww >> 1;  // which of the unit's tiles
+  B.valid = (sel == 0) || two;
+  const int t = (sel == 1 && two) ? cb1 : cb0;  // idle warps of an odd last unit shadow tile 2q (their result is dropped)
   B.cb_a = B.cb_b = t;
   B.src_a = B.src_b = (t == cb0) ? 0 : 1;
-  B.vec = B.valid && (k == 0 || k == 2 || k == 4 || k == 5);
+  if (w < 4) {
+    B.kind = 1;
+    B.wm = B.wn = ww & 1;  // upper-left / lower-right square
+  } else {
+    B.kind = 0;
+    B.wm = ww & 1;  // rows 0-31 / 32-63 of the tile
+    B.wn = 1;       // columns 64-127
+  }
   return B;
 }
 
-template <bool CENTER, bool VEC>
-__global__ void __launch_bounds__(SYRK_THREADS, 1)
-syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + SYRK_STAGES * 2 * SYRK_OP_BYTES;
+// box pair p = 0..9 of a diagonal square -> (bi, bj), bi <= bj, row-major over the upper triangle of the 4 x 4 box grid
+__host__ __device__ __forceinline__ void syrk_square_pair(int p, int& bi, int& bj) {
+  bi = p < 4 ? 0 : (p < 7 ? 1 : (p < 9 ? 2 : 3));
+  bj = p - (bi == 0 ? 0 : (bi == 1 ? 3 : (bi == 2 ? 5 : 6)));
+}
+
+// The consumer loop of one warp. SQUARE = false: 32 x 64 block (A: 2 boxes, B: 4 boxes, 32 DMMA tiles);
+// SQUARE = true: 64 x 64 diagonal square (4 boxes serve as A and B, 40 DMMA tiles).
+//
+// Nothing but LDS + DMMA lives in this loop. Measured with the per-CTA trace hook (scripts/syrk_trace.py): any extra work inside it
+// costs far more than its instruction count — scalar FP64 shares the pipe with the DMMAs, and fusing the moment vectors here (as DFMAs
+// on the fragments, or as one more DMMA n-tile) made a diagonal unit 1.5 - 1.7 x an off-diagonal one instead of 1.06 x. Hence:
+//   * the per-row weight is only multiplied in when the CTA's rows do not all share one weight (NEEDW: a real branch per stage with
+//     two instantiations of the body — a select would execute the multiplies always);
+//   * the moment vectors are NOT accumulated here: they are weighted column sums, an HBM-rate pass of their own
+//     (wcolsum_partial_kernel, prelude.cuh), and the rho of the one-sided centring is the centred column sum (colsum with a shift).
+template <bool CENTER, bool SQUARE>
+__device__ __forceinline__ void syrk_consume(const SyrkParams& p, const SyrkWarpBlock& WB, const uint32_t smem_base, const uint32_t bar_base,
+                                             const int KT, const int64_t r_begin, const int64_t r_end, const int tile, const int split, const int lane) {
+  constexpr int NA = SQUARE ? 4 : 2;       // fragment boxes of the A operand
+  constexpr int NT = SQUARE ? 40 : 32;     // DMMA tiles = accumulator pairs
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (SYRK_STAGES + s); };
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;  // work unit
-  const int split = blockIdx.y;
-  int cb0, cb1;
-  const SyrkWarpBlock WB = syrk_warp_block(p.T, tile, warp < SYRK_CONSUMER_WARPS ? warp : 0, cb0, cb1);
-  const bool one_buf = (cb0 == cb1);
-  const int64_t r_begin = (int64_t)split * p.rows_per_split;
-  int64_t r_end = r_begin + p.rows_per_split;
-  if (r_end > p.R) r_end = p.R;
-  const int KT = r_end > r_begin ? (int)((r_end - r_begin + SYRK_BK - 1) / SYRK_BK) : 0;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < SYRK_STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), SYRK_CONSUMER_WARPS);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-
-  if (warp >= SYRK_CONSUMER_WARPS) {
-    setmaxnreg_dec<24>();  // 256*240 + 128*24 = 64512 = 384 threads x 168 registers (the CTA pool)
-    if (warp == SYRK_CONSUMER_WARPS && lane == 0) {
-      tma_prefetch_desc(&tm);
-      const uint32_t bytes = one_buf ? SYRK_OP_BYTES : 2 * SYRK_OP_BYTES;
-      for (int kt = 0; kt < KT; ++kt) {
-        const int s = kt % SYRK_STAGES;
-        const uint32_t ph = (kt / SYRK_STAGES) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_arrive_expect_tx(full_bar(s), bytes);
-        const uint32_t dst = smem_base + s * 2 * SYRK_OP_BYTES;
-        const int r0 = (int)(r_begin + (int64_t)kt * SYRK_BK);
-        // NOTE: the last stage of a split may read rows of the next split (r >= r_end); they are zero-weighted below.
-#pragma unroll
-        for (int bx = 0; bx < 8; ++bx) tma_load_2d(dst + bx * SYRK_BOX_BYTES, &tm, full_bar(s), cb0 * SYRK_BT + 16 * bx, r0);
-        if (!one_buf) {
-#pragma unroll
-          for (int bx = 0; bx < 8; ++bx)
-            tma_load_2d(dst + SYRK_OP_BYTES + bx * SYRK_BOX_BYTES, &tm, full_bar(s), cb1 * SYRK_BT + 16 * bx, r0);
-        }
-      }
-    }
-    return;
-  }
-
-  // ------------------------------ consumers ------------------------------
-  setmaxnreg_inc<240>();
-  const int wm = WB.wm;  // 32-column slab of the i (row of S) index inside column block WB.cb_a
-  const int wn = WB.wn;  // 64-column slab of the j index inside column block WB.cb_b
   const int g = lane >> 2;
   const int t = lane & 3;
+  const int colA0 = WB.cb_a * SYRK_BT + (SQUARE ? 64 : 32) * WB.wm;  // first i column of this warp
 
-  double acc[4][8][2];
+  double acc[NT][2];
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = 0.0;
 
-  // moment vectors (one diagonal warp block per 32-column slab): columns i = 128 cb_a + 32 wm + 16 bx + 2g + e
-  double vb[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-  double vc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-  const bool do_vec = VEC && WB.vec;
-
-  // column means of this thread's fragment columns
-  double mi[2][2];
+  // column means of this thread's A fragment columns
+  double mi[NA][2];
   if (CENTER) {
 #pragma unroll
-    for (int bx = 0; bx < 2; ++bx)
+    for (int bx = 0; bx < NA; ++bx)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int64_t col = (int64_t)WB.cb_a * SYRK_BT + 32 * wm + 16 * bx + 2 * g + e;
+        const int64_t col = (int64_t)colA0 + 16 * bx + 2 * g + e;
         mi[bx][e] = col < p.Kf ? __ldg(p.mean + col) : 0.0;
       }
   }
 
   // Uniform-weight fast path: when every row of this CTA's range carries the same weight (the two-segment form
   // Q = Diagonal([ws1*1_N; ws2*1_M]) away from the segment boundary, or plain sums), the weight is factored out of the
-  // sum and applied once to the 64 accumulators at the end instead of to every A fragment: the FP64 multiplies would
-  // otherwise queue behind the DMMAs on the shared FP64 pipe inside the main loop.
+  // sum and applied once to the accumulators at the end instead of to every A fragment.
   bool uniform = (p.w == nullptr);
   double wscale = 1.0;
   if (uniform) {
@@ -201,135 +174,202 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
   // r_end < r_begin + rows_per_split only at the end of the matrix); only the centred mode has to mask them (0 - mean != 0)
   const int64_t r_full_end = r_end - (r_end - r_begin) % SYRK_BK;  // stages starting at or after this row are ragged
 
-  // byte offset of lane's chunk for step (h, par): row rho = 8h + 2t + par, chunk g ^ (rho & 7)
-  // rho & 7 = 2t + par  ->  (g ^ (2t+par)) << 4 ;  row offset rho * 128
+  const uint32_t offA = WB.src_a * SYRK_OP_BYTES + (SQUARE ? 4 : 2) * WB.wm * SYRK_BOX_BYTES;
+  const uint32_t offB = WB.src_b * SYRK_OP_BYTES + 4 * WB.wn * SYRK_BOX_BYTES;
+
+  // one pipeline stage (16 rows = 4 k4-steps); NEEDW: multiply the per-row weight into the A fragments
+  auto stage_body = [&](auto needw_tag, const uint32_t sA, const uint32_t sB, const double (&wv)[2][2]) {
+    constexpr bool NEEDW = decltype(needw_tag)::value;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        // byte offset of lane's chunk for step (h, par): row rho = 8h + 2t + par, chunk g ^ (rho & 7) = g ^ (2t + par)
+        const uint32_t off = (uint32_t)((8 * h + 2 * t + par) * 128 + ((g ^ (2 * t + par)) << 4));
+        double2 a[NA];
+#pragma unroll
+        for (int bx = 0; bx < NA; ++bx) a[bx] = lds128(sA + bx * SYRK_BOX_BYTES + off);
+        const double w = wv[h][par];
+        if (SQUARE) {
+          // The raw fragments a[] are the B operand; the A operand x = (a - mean) * w is a second copy (weights / centring go on
+          // ONE operand only). Without centring and weights the copy is the same registers.
+          double2 x[NA];
+#pragma unroll
+          for (int bx = 0; bx < NA; ++bx) {
+            x[bx] = a[bx];
+            if (CENTER) {
+              x[bx].x -= mi[bx][0];
+              x[bx].y -= mi[bx][1];
+            }
+            if (NEEDW) {
+              x[bx].x *= w;
+              x[bx].y *= w;
+            }
+          }
+          // box pairs (bi <= bj) of the 4 x 4 box grid, 4 DMMA tiles (e, e') each: tile index (pair*2 + e)*2 + e'
+          int pr = 0;
+#pragma unroll
+          for (int bi = 0; bi < 4; ++bi)
+#pragma unroll
+            for (int bj = bi; bj < 4; ++bj, ++pr) {
+              const double2 xx = x[bi < NA ? bi : 0], yy = a[bj < NA ? bj : 0];
+              dmma884(acc[4 * pr + 0][0], acc[4 * pr + 0][1], xx.x, yy.x);
+              dmma884(acc[4 * pr + 1][0], acc[4 * pr + 1][1], xx.x, yy.y);
+              dmma884(acc[4 * pr + 2][0], acc[4 * pr + 2][1], xx.y, yy.x);
+              dmma884(acc[4 * pr + 3][0], acc[4 * pr + 3][1], xx.y, yy.y);
+            }
+        } else {
+          double2 b[4];
+#pragma unroll
+          for (int bx = 0; bx < 4; ++bx) b[bx] = lds128(sB + bx * SYRK_BOX_BYTES + off);
+          if (CENTER) {
+#pragma unroll
+            for (int bx = 0; bx < NA; ++bx) {
+              a[bx].x -= mi[bx][0];
+              a[bx].y -= mi[bx][1];
+            }
+          }
+          if (NEEDW) {
+#pragma unroll
+            for (int bx = 0; bx < NA; ++bx) {
+              a[bx].x *= w;
+              a[bx].y *= w;
+            }
+          }
+          // m-tile mt = 2 bx + e = columns 16 bx + 2g + e ; n-tile nt = 2 by + e' likewise: tile index mt*8 + nt
+#pragma unroll
+          for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+            for (int by = 0; by < 4; ++by) {
+              dmma884(acc[(2 * bx + 0) * 8 + 2 * by + 0][0], acc[(2 * bx + 0) * 8 + 2 * by + 0][1], a[bx].x, b[by].x);
+              dmma884(acc[(2 * bx + 0) * 8 + 2 * by + 1][0], acc[(2 * bx + 0) * 8 + 2 * by + 1][1], a[bx].x, b[by].y);
+              dmma884(acc[(2 * bx + 1) * 8 + 2 * by + 0][0], acc[(2 * bx + 1) * 8 + 2 * by + 0][1], a[bx].y, b[by].x);
+              dmma884(acc[(2 * bx + 1) * 8 + 2 * by + 1][0], acc[(2 * bx + 1) * 8 + 2 * by + 1][1], a[bx].y, b[by].y);
+            }
+        }
+      }
+    }
+  };
+
   for (int kt = 0; kt < KT; ++kt) {
     const int s = kt % SYRK_STAGES;
     const uint32_t ph = (kt / SYRK_STAGES) & 1u;
     const int64_t r0 = r_begin + (int64_t)kt * SYRK_BK;
     const bool need_w = !uniform || (CENTER && r0 >= r_full_end);
-
-    // per-row weights / rhs of the 4 stage rows this lane contracts over (independent of the TMA data)
-    double wv[2][2], bv[2][2], cv[2][2];
+    const uint32_t sA = smem_base + s * 2 * SYRK_OP_BYTES + offA;
+    const uint32_t sB = smem_base + s * 2 * SYRK_OP_BYTES + offB;
+    // per-row weights of the 4 stage rows this lane contracts over: independent of the TMA data, in flight during the wait
+    double wv[2][2];
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
       for (int par = 0; par < 2; ++par) {
         const int64_t r = r0 + 8 * h + 2 * t + par;
-        const bool ok = r < r_end;
         double w = 0.0;
-        if (ok) w = uniform ? 1.0 : (p.w ? __ldg(p.w + r) : (r < p.ne ? p.w_e : p.w_f));
+        if (need_w && r < r_end) w = p.w ? __ldg(p.w + r) : (r < p.ne ? p.w_e : p.w_f);
         wv[h][par] = w;
-        if (VEC) {
-          bv[h][par] = (ok && p.b) ? __ldg(p.b + r) : 0.0;
-          cv[h][par] = (ok && (CENTER || r < p.ne)) ? 1.0 : 0.0;  // centred mode: rho = sum over ALL rows of (a - m)
-        }
       }
-
     mbar_wait(full_bar(s), ph);
-    const uint32_t sA = smem_base + s * 2 * SYRK_OP_BYTES + WB.src_a * SYRK_OP_BYTES + (2 * wm) * SYRK_BOX_BYTES;
-    const uint32_t sB = smem_base + s * 2 * SYRK_OP_BYTES + WB.src_b * SYRK_OP_BYTES + (4 * wn) * SYRK_BOX_BYTES;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-#pragma unroll
-      for (int par = 0; par < 2; ++par) {
-        const uint32_t off = (uint32_t)((8 * h + 2 * t + par) * 128 + ((g ^ (2 * t + par)) << 4));
-        double2 a[2], b[4];
-#pragma unroll
-        for (int bx = 0; bx < 2; ++bx) a[bx] = lds128(sA + bx * SYRK_BOX_BYTES + off);
-#pragma unroll
-        for (int bx = 0; bx < 4; ++bx) b[bx] = lds128(sB + bx * SYRK_BOX_BYTES + off);
-        if (CENTER) {
-#pragma unroll
-          for (int bx = 0; bx < 2; ++bx) {
-            a[bx].x -= mi[bx][0];
-            a[bx].y -= mi[bx][1];
-          }
-        }
-        if (need_w) {
-          const double w = wv[h][par];
-#pragma unroll
-          for (int bx = 0; bx < 2; ++bx) {
-            a[bx].x *= w;
-            a[bx].y *= w;
-          }
-        }
-        if (VEC) {
-          if (do_vec) {
-            const double bb = bv[h][par], cc = cv[h][par];
-#pragma unroll
-            for (int bx = 0; bx < 2; ++bx) {
-              if (!CENTER) {  // centred mode has no right-hand side: only rho (the c slot) is accumulated
-                vb[bx][0] = fma(a[bx].x, bb, vb[bx][0]);
-                vb[bx][1] = fma(a[bx].y, bb, vb[bx][1]);
-              }
-              vc[bx][0] = fma(a[bx].x, cc, vc[bx][0]);
-              vc[bx][1] = fma(a[bx].y, cc, vc[bx][1]);
-            }
-          }
-        }
-        // m-tile (bx, e) = columns 16 bx + 2g + e ; n-tile (bx', e') likewise: 4 x 8 DMMA tiles per k4-step
-#pragma unroll
-        for (int bx = 0; bx < 2; ++bx)
-#pragma unroll
-          for (int by = 0; by < 4; ++by) {
-            dmma884(acc[2 * bx + 0][2 * by + 0][0], acc[2 * bx + 0][2 * by + 0][1], a[bx].x, b[by].x);
-            dmma884(acc[2 * bx + 0][2 * by + 1][0], acc[2 * bx + 0][2 * by + 1][1], a[bx].x, b[by].y);
-            dmma884(acc[2 * bx + 1][2 * by + 0][0], acc[2 * bx + 1][2 * by + 0][1], a[bx].y, b[by].x);
-            dmma884(acc[2 * bx + 1][2 * by + 1][0], acc[2 * bx + 1][2 * by + 1][1], a[bx].y, b[by].y);
-          }
-      }
-    }
+    if (need_w) stage_body(std::true_type{}, sA, sB, wv);
+    else stage_body(std::false_type{}, sA, sB, wv);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar(s));
   }
   if (uniform && wscale != 1.0) {
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        acc[mt][nt][0] *= wscale;
-        acc[mt][nt][1] *= wscale;
-      }
-#pragma unroll
-    for (int bx = 0; bx < 2; ++bx)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        vb[bx][e] *= wscale;
-        vc[bx][e] *= wscale;
-      }
+    for (int i = 0; i < NT; ++i) {
+      acc[i][0] *= wscale;
+      acc[i][1] *= wscale;
+    }
   }
 
-  // ---- partial tile to the workspace in fragment order: [acc index][consumer thread] (coalesced) ----
+  // ---- partial to the workspace in fragment order: [acc index][consumer thread] (coalesced) ----
   double* wst = p.ws_tiles + ((int64_t)split * p.ntiles + tile) * SYRK_TILE_ELEMS;
   const int ctid = threadIdx.x;  // 0..255
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
+  for (int i = 0; i < NT; ++i)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int c = 0; c < 2; ++c) wst[((mt * 8 + nt) * 2 + c) * 256 + ctid] = acc[mt][nt][c];
+    for (int c = 0; c < 2; ++c) wst[(i * 2 + c) * 256 + ctid] = acc[i][c];
+}
 
-  if (VEC) {
-    if (do_vec) {
-      // reduce over the 4 lanes t = 0..3 that share g (they hold disjoint stage rows)
+template <bool CENTER>
+__global__ void __launch_bounds__(SYRK_THREADS, 1)
+syrk_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmx, const SyrkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tile = blockIdx.x;  // work unit
+  const int split = blockIdx.y;
+  const int64_t r_begin = (int64_t)split * p.rows_per_split;
+  int64_t r_end = r_begin + p.rows_per_split;
+  if (r_end > p.R) r_end = p.R;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + SYRK_STAGES * 2 * SYRK_OP_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (SYRK_STAGES + s); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  int cb0, cb1;
+  const SyrkWarpBlock WB = syrk_warp_block(p.T, tile, warp < SYRK_CONSUMER_WARPS ? warp : 0, cb0, cb1);
+  const bool one_buf = (cb0 == cb1);
+  const int KT = r_end > r_begin ? (int)((r_end - r_begin + SYRK_BK - 1) / SYRK_BK) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SYRK_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), SYRK_CONSUMER_WARPS);
+    }
+    fence_barrier_init();
+    if (p.trace) {
+      long long* tr = p.trace + ((int64_t)blockIdx.y * p.ntiles + blockIdx.x) * 10;
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      long long t0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      tr[0] = t0;
+      tr[1] = smid;
+    }
+  }
+  __syncthreads();
+
+  if (warp >= SYRK_CONSUMER_WARPS) {
+    setmaxnreg_dec<24>();  // 256*240 + 128*24 = 64512 = 384 threads x 168 registers (the CTA pool)
+    if (warp == SYRK_CONSUMER_WARPS && lane == 0) {
+      tma_prefetch_desc(&tm);
+      if (p.aux_box >= 0) tma_prefetch_desc(&tmx);
+      const uint32_t bytes = one_buf ? SYRK_OP_BYTES : 2 * SYRK_OP_BYTES;
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % SYRK_STAGES;
+        const uint32_t ph = (kt / SYRK_STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_arrive_expect_tx(full_bar(s), bytes);
+        const uint32_t dst = smem_base + s * 2 * SYRK_OP_BYTES;
+        const int r0 = (int)(r_begin + (int64_t)kt * SYRK_BK);
+        // NOTE: the last stage of a split may read rows of the next split (r >= r_end); they are zero-weighted below.
 #pragma unroll
-      for (int bx = 0; bx < 2; ++bx)
+        for (int bx = 0; bx < 8; ++bx) {
+          if (cb0 * 8 + bx == p.aux_box) tma_load_2d(dst + bx * SYRK_BOX_BYTES, &tmx, full_bar(s), 0, r0);
+          else tma_load_2d(dst + bx * SYRK_BOX_BYTES, &tm, full_bar(s), cb0 * SYRK_BT + 16 * bx, r0);
+        }
+        if (!one_buf) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          double x = vb[bx][e], y = vc[bx][e];
-          x += __shfl_xor_sync(0xffffffffu, x, 1);
-          x += __shfl_xor_sync(0xffffffffu, x, 2);
-          y += __shfl_xor_sync(0xffffffffu, y, 1);
-          y += __shfl_xor_sync(0xffffffffu, y, 2);
-          if (t == 0) {
-            const int col = WB.cb_a * SYRK_BT + 32 * wm + 16 * bx + 2 * g + e;
-            double* wv2 = p.ws_vec + (int64_t)split * 2 * p.T * SYRK_BT;
-            wv2[col] = x;
-            wv2[p.T * SYRK_BT + col] = y;
+          for (int bx = 0; bx < 8; ++bx) {
+            if (cb1 * 8 + bx == p.aux_box) tma_load_2d(dst + SYRK_OP_BYTES + bx * SYRK_BOX_BYTES, &tmx, full_bar(s), 0, r0);
+            else tma_load_2d(dst + SYRK_OP_BYTES + bx * SYRK_BOX_BYTES, &tm, full_bar(s), cb1 * SYRK_BT + 16 * bx, r0);
           }
         }
+      }
     }
+    return;
+  }
+
+  // ------------------------------ consumers ------------------------------
+  setmaxnreg_inc<240>();
+  if (WB.kind == 1) syrk_consume<CENTER, true>(p, WB, smem_base, bar_base, KT, r_begin, r_end, tile, split, lane);
+  else syrk_consume<CENTER, false>(p, WB, smem_base, bar_base, KT, r_begin, r_end, tile, split, lane);
+  if (p.trace && lane == 0) {
+    long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    p.trace[((int64_t)blockIdx.y * p.ntiles + blockIdx.x) * 10 + 2 + warp] = t1;
   }
 }
 
@@ -341,50 +381,77 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const SyrkParams p) {
 //   j = 128 cb_b + 64 wn + 16 (nt>>1) + 4 t + 2 c + (nt&1)
 // Centred mode (mean != NULL): rho (the reduced "c" vector, K doubles, produced by syrk_rho_kernel first) closes the
 // one-sided centring: S_ij = S'_ij - rho_i * m_j.
-__global__ void syrk_reduce_kernel(const double* __restrict__ ws_tiles, const double* __restrict__ ws_vec, int T, int ntiles,
-                                   int splits, int64_t Kf, double* __restrict__ S, double* __restrict__ vec, int want_vec,
-                                   const double* __restrict__ mean, const double* __restrict__ rho) {
+// vec != NULL ("augmented" mode): columns Kf and Kf+1 of the contraction held (b_r) and ([r < ne]) — see syrk_aux_box_kernel — so
+//   S_aug[i][Kf] = v_i, S_aug[i][Kf+1] = c_i (i < Kf), S_aug[Kf+1][Kf+1] = s_0, S_aug[Kf][Kf+1] = s_1   ->   vec = [v ; c ; s].
+__global__ void syrk_reduce_kernel(const double* __restrict__ ws_tiles, int T, int ntiles, int splits, int64_t Kf, double* __restrict__ S,
+                                   const double* __restrict__ mean, const double* __restrict__ rho, double* __restrict__ vec) {
   const int unit = blockIdx.x;
-  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < SYRK_TILE_ELEMS; e += gridDim.y * blockDim.x) {
-    const int a = e >> 8;
-    const int tid = e & 255;
-    const int warp = tid >> 5, g = (tid & 31) >> 2, t = tid & 3;
-    int cb0, cb1;
-    const SyrkWarpBlock WB = syrk_warp_block(T, unit, warp, cb0, cb1);
-    if (!WB.valid) continue;
+  const int e = blockIdx.y * blockDim.x + threadIdx.x;  // one partial element per thread: grid = (units, SYRK_TILE_ELEMS / 256)
+  if (e >= SYRK_TILE_ELEMS) return;
+  const int a = e >> 8;
+  const int tid = e & 255;
+  const int warp = tid >> 5, g = (tid & 31) >> 2, t = tid & 3;
+  int cb0, cb1;
+  const SyrkWarpBlock WB = syrk_warp_block(T, unit, warp, cb0, cb1);
+  if (!WB.valid) return;
+  int64_t i, j;
+  if (WB.kind == 0) {
+    if (a >= 64) return;
     const int mt = a >> 4, nt = (a >> 1) & 7, c = a & 1;
-    const int64_t i = (int64_t)WB.cb_a * SYRK_BT + 32 * WB.wm + 16 * (mt >> 1) + 2 * g + (mt & 1);
-    const int64_t j = (int64_t)WB.cb_b * SYRK_BT + 64 * WB.wn + 16 * (nt >> 1) + 4 * t + 2 * c + (nt & 1);
-    if (i >= Kf || j >= Kf) continue;
-    if (j < i) continue;  // diagonal blocks: keep j >= i, mirror (weights are applied to one operand only)
-    double sum = 0.0;
-    for (int sp = 0; sp < splits; ++sp) sum += ws_tiles[((int64_t)sp * ntiles + unit) * SYRK_TILE_ELEMS + e];
-    if (mean) sum = fma(-rho[i], mean[j], sum);
-    S[i * Kf + j] = sum;
-    S[j * Kf + i] = sum;
+    i = (int64_t)WB.cb_a * SYRK_BT + 32 * WB.wm + 16 * (mt >> 1) + 2 * g + (mt & 1);
+    j = (int64_t)WB.cb_b * SYRK_BT + 64 * WB.wn + 16 * (nt >> 1) + 4 * t + 2 * c + (nt & 1);
+  } else {
+    int bi, bj;
+    syrk_square_pair(a >> 3, bi, bj);
+    const int e1 = (a >> 2) & 1, e2 = (a >> 1) & 1, c = a & 1;
+    const int64_t base = (int64_t)WB.cb_a * SYRK_BT + 64 * WB.wm;
+    i = base + 16 * bi + 2 * g + e1;
+    j = base + 16 * bj + 4 * t + 2 * c + e2;
   }
-  if (want_vec && blockIdx.y == 0) {
-    // every column block's moment vectors: handled by the first T units' blocks (any mapping works: one writer per column)
-    for (int64_t col = (int64_t)unit * blockDim.x + threadIdx.x; col < Kf; col += (int64_t)gridDim.x * blockDim.x) {
-      double sv = 0.0, sc = 0.0;
-      for (int sp = 0; sp < splits; ++sp) {
-        const double* wv2 = ws_vec + (int64_t)sp * 2 * T * SYRK_BT;
-        sv += wv2[col];
-        sc += wv2[(int64_t)T * SYRK_BT + col];
-      }
-      vec[col] = sv;
-      vec[Kf + col] = sc;
-    }
+  if (j < i) return;  // diagonal boxes: keep j >= i, mirror (weights are applied to one operand only)
+  const int64_t Ka = vec ? Kf + 2 : Kf;
+  if (j >= Ka) return;  // (i <= j)
+  // four interleaved partial sums (splits sp, sp+1, sp+2, sp+3 mod 4) keep 4 loads in flight; the order is fixed -> deterministic
+  const double* src = ws_tiles + (int64_t)unit * SYRK_TILE_ELEMS + e;
+  const int64_t stride = (int64_t)ntiles * SYRK_TILE_ELEMS;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int sp = 0;
+  for (; sp + 4 <= splits; sp += 4) {
+    s0 += src[(int64_t)sp * stride];
+    s1 += src[(int64_t)(sp + 1) * stride];
+    s2 += src[(int64_t)(sp + 2) * stride];
+    s3 += src[(int64_t)(sp + 3) * stride];
   }
+  for (; sp < splits; ++sp) s0 += src[(int64_t)sp * stride];
+  double sum = (s0 + s1) + (s2 + s3);
+  if (j >= Kf) {  // augmented columns: the moment vectors and the two scalars
+    if (i < Kf) vec[(j - Kf) * Kf + i] = sum;
+    else if (j == Kf + 1) vec[2 * Kf + (i == Kf ? 1 : 0)] = sum;
+    return;
+  }
+  if (mean) sum = fma(-rho[i], mean[j], sum);
+  S[i * Kf + j] = sum;
+  S[j * Kf + i] = sum;
 }
 
-// rho[col] = sum over splits (fixed order) of the "c" moment vector: rho_i = sum_r (a_ri - m_i) in centred mode
-__global__ void syrk_rho_kernel(const double* __restrict__ ws_vec, int T, int splits, int64_t Kf, double* __restrict__ rho) {
-  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= Kf) return;
-  double s = 0.0;
-  for (int sp = 0; sp < splits; ++sp) s += ws_vec[(int64_t)sp * 2 * T * SYRK_BT + (int64_t)T * SYRK_BT + col];
-  rho[col] = s;
+// The auxiliary 16-column box of the augmented contraction: for every row r
+//   aux[r][0 .. rem) = A[r][16 q .. 16 q + rem)   (the last real columns, q = Kf / 16, rem = Kf % 16 <= 14)
+//   aux[r][rem] = b_r (0 without a right-hand side),  aux[r][rem + 1] = [r < ne],  the rest 0.
+// The SYRK producer loads box q from this tensor instead of A, so A'Wb, the intercept row A'W 1_e and the two scalars fall out of
+// the SAME DMMA contraction as two more columns of the (already padded) last column block: no instruction is added to the main loop,
+// and no second pass over A is needed (a weighted column-sum pass costs 2.3 ms of HBM time at config 3, 10 % of the SYRK).
+__global__ void syrk_aux_box_kernel(const double* __restrict__ A, int64_t R, int64_t Kf, int64_t lda, const double* __restrict__ b, int64_t ne,
+                                    double* __restrict__ aux) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= R * 16) return;
+  const int64_t r = e >> 4;
+  const int c = (int)(e & 15);
+  const int rem = (int)(Kf & 15);
+  double v = 0.0;
+  if (c < rem) v = A[r * lda + (Kf - rem) + c];
+  else if (c == rem) v = b ? b[r] : 0.0;
+  else if (c == rem + 1) v = r < ne ? 1.0 : 0.0;
+  aux[e] = v;
 }
 
 // s[0] = sum_{r<ne} w_r, s[1] = sum_{r<ne} w_r b_r  (one block, fixed-order tree: deterministic)

@@ -1,0 +1,121 @@
+"""GPU probe of the widened rows: feature-reduction bandwidth, streamed normal equations end to end
+from pinned host memory, eigendecomposition timings. CUDA-event timings, results as one JSON object."""
+import ctypes
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "potentiallearning.jl_b200"))
+import numpy as np
+import torch
+
+import plb200
+from plb200 import _lib
+
+plb200.init(0)
+out = {}
+
+
+def timeit(fn, warm=2, reps=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), float(np.median(ts))
+
+
+which = sys.argv[1:] or ["feat", "neq", "eig"]
+
+if "feat" in which:
+    # config-2 shape: 20 000 configurations x 96 atoms x 300 descriptors = 4.6 GB of local descriptors
+    for N, nat, d in ((20000, 96, 300), (1000, 32, 26), (200000, 8, 500)):
+        g = torch.Generator(device="cuda").manual_seed(1)
+        L = torch.randn((N * nat, d), device="cuda", dtype=torch.float64, generator=g)
+        off = (torch.arange(N + 1, device="cuda", dtype=torch.int64) * nat).contiguous()
+        X = torch.empty((N, d), device="cuda", dtype=torch.float64)
+        best, med = timeit(lambda: plb200.global_features_dev(L, off, True, out=X))
+        ref = L.view(N, nat, d).sum(1) / nat
+        out[f"feat_{N}x{nat}x{d}"] = {"ms": best, "GBs": (L.numel() + X.numel()) * 8 / best / 1e6,
+                                      "max_abs_vs_torch": float((X - ref).abs().max())}
+        del L, X, ref
+
+if "neq" in which:
+    # config 3 end to end from pinned host memory, 1/4 size by default (PLB_NEQ_FRAC=1 for all 11.56 GB)
+    frac = float(os.environ.get("PLB_NEQ_FRAC", "0.25"))
+    ncfg, nat, K = int(10000 * frac), 96, 500
+    R = ncfg * (1 + 3 * nat)
+    A = torch.empty((R, K), dtype=torch.float64).pin_memory()
+    gen = torch.Generator().manual_seed(3)
+    step = 1 << 18
+    for r0 in range(0, R, step):
+        A[r0:r0 + step].normal_(generator=gen)
+    b = torch.randn(R, dtype=torch.float64, generator=gen).pin_memory()
+    n = K + 1
+    M = torch.empty((n, n), dtype=torch.float64).pin_memory()
+    v = torch.empty(n, dtype=torch.float64).pin_memory()
+    lib = _lib.lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    P = lambda t: ctypes.cast(t.data_ptr(), dp)
+
+    def run():
+        _lib.check(lib.pl_normal_eq(P(A), R, K, K, None, ncfg, 100.0, 1.0, P(b), 1, 0.01, P(M), P(v)), "pl_normal_eq")
+
+    ts = []
+    for i in range(4):
+        t0 = time.perf_counter()
+        run()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    out["neq_stream_pinned"] = {"R": R, "K": K, "GB": R * K * 8 / 1e9, "ms_best": min(ts[1:]), "ms_all": ts,
+                                "rows_per_s": R / (min(ts[1:]) / 1e3), "h2d_GBs": R * K * 8 / (min(ts[1:]) / 1e3) / 1e9,
+                                "timing": plb200.last_timing()}
+    # block-list form: the same rows as ncfg+1 blocks, as lp.B / lp.dB[i] lie in memory
+    An = A.numpy()
+    blocks = [An[:ncfg]] + [An[ncfg + i * 3 * nat: ncfg + (i + 1) * 3 * nat] for i in range(ncfg)]
+    t0 = time.perf_counter()
+    M2, v2 = plb200.normal_equations_blocks(blocks, b.numpy(), None, ncfg, 100.0, 1.0, True, 0.01)
+    out["neq_blocks_pinned"] = {"nblocks": len(blocks), "ms": (time.perf_counter() - t0) * 1e3,
+                                "max_rel_vs_contiguous": float(np.max(np.abs(M2 - M.numpy())) / np.max(np.abs(M.numpy())))}
+    del A
+
+if "eig" in which:
+    from plb200.dpp import eigh
+
+    for n in (1000, 4000) + ((20000,) if os.environ.get("PLB_EIG_BIG") else ()):
+        rng = np.random.default_rng(n)
+        X = rng.standard_normal((n, 300)) / np.sqrt(96) + rng.standard_normal(300)
+        k = plb200.RBF(plb200.Euclidean(300))
+        t0 = time.perf_counter()
+        ell = plb200.EllEnsemble.from_features(X, k, keep_L=False)
+        t_first = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        ell = plb200.EllEnsemble.from_features(X, k, keep_L=False)
+        t_dev = (time.perf_counter() - t0) * 1e3
+        rec = {"ell_ensemble_ms_first": t_first, "ell_ensemble_ms": t_dev, "timing": plb200.last_timing()}
+        t0 = time.perf_counter()
+        plb200.rescale_(ell, n // 10)
+        p = plb200.inclusion_prob(ell)
+        rec["inclusion_prob_ms"] = (time.perf_counter() - t0) * 1e3
+        rec["inclusion_sum_err"] = float(abs(p.sum() - n // 10))
+        if n <= 4000:
+            K = np.asarray(plb200.KernelMatrix(X, k))
+            t0 = time.perf_counter()
+            lo = np.linalg.eigvalsh(K)
+            rec["numpy_eigvalsh_ms"] = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter()
+            lo, Uo = np.linalg.eigh(K)
+            rec["numpy_eigh_ms"] = (time.perf_counter() - t0) * 1e3
+            rec["lambda_max_rel_err"] = float(np.max(np.abs(ell.λ - np.maximum(lo, 0))) / lo.max())
+        out[f"eig_{n}"] = rec
+
+out["launches"] = plb200.launch_count()
+print(json.dumps(out))

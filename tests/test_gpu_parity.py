@@ -819,7 +819,7 @@ def test_normal_equations_large_input_streams(pl, orc):
     eng = DeviceEngine()
     S, vec = eng.syrk_partial(torch.from_numpy(A).cuda(), None, 1000, 30.0, 1.0, torch.from_numpy(b).cuda(), None, True)
     Md, vd = eng.normal_eq_finish(S, vec, True, 0.01)
-    assert normerr(M, Md.cpu().numpy()) < 1e-13 and normerr(v, vd.cpu().numpy()) < 1e-13
+    assert normerr(M, Md.cpu().numpy()) < 1e-12 and normerr(v, vd.cpu().numpy()) < 1e-12  # chunked vs one-pass summation order
     assert np.array_equal(M, M.T)
 
 

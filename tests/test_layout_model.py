@@ -174,7 +174,8 @@ def test_folded_triangle_enumeration_covers_every_tile_once():
 
 
 def _syrk_warp_block(T, u, w):
-    """Python restatement of syrk_warp_block (csrc/syrk.cuh): work unit u, warp w -> (cb_a, wm, cb_b, wn, valid, vec, cb0, cb1)."""
+    """Python restatement of syrk_warp_block (csrc/syrk.cuh): work unit u, warp w ->
+    (kind, cb_a, wm, cb_b, wn, valid, vec, cb0, cb1); kind 0 = 32 x 64 block, 1 = 64 x 64 diagonal square."""
     noff = T * (T - 1) // 2
     if u < noff:
         ti, rem = 0, u
@@ -182,38 +183,68 @@ def _syrk_warp_block(T, u, w):
             rem -= T - 1 - ti
             ti += 1
         cb0, cb1 = ti, ti + 1 + rem
-        return cb0, w >> 1, cb1, w & 1, True, False, cb0, cb1
+        return 0, cb0, w >> 1, cb1, w & 1, True, False, cb0, cb1
     q = u - noff
-    first, last = 8 * q, min(8 * q + 7, 6 * T - 1)
-    cb0, cb1 = first // 6, last // 6
-    idx = first + w
-    valid = idx < 6 * T
-    t, k = (idx // 6, idx % 6) if valid else (cb0, 0)
-    wm = (k >> 1) if k < 4 else (k - 2)
-    wn = (k & 1) if k < 4 else 1
-    return t, wm, t, wn, valid, valid and k in (0, 2, 4, 5), cb0, cb1
+    two = 2 * q + 1 < T
+    cb0 = 2 * q
+    cb1 = 2 * q + 1 if two else 2 * q
+    ww = w & 3
+    sel = ww >> 1
+    valid = sel == 0 or two
+    t = cb1 if (sel == 1 and two) else cb0
+    if w < 4:
+        return 1, t, ww & 1, t, ww & 1, valid, False, cb0, cb1
+    return 0, t, ww & 1, t, 1, valid, valid, cb0, cb1
+
+
+def _square_pair(p):
+    bi = 0 if p < 4 else (1 if p < 7 else (2 if p < 9 else 3))
+    bj = p - (0, 3, 5, 6)[bi]
+    return bi, bj
 
 
 def test_syrk_work_units_cover_upper_triangle_once():
-    """Off-diagonal tiles + packed diagonal warp blocks: every (i, j), j >= i, of the K x K result is produced exactly once,
-    every 32-column slab has exactly one moment-vector writer, and a unit never needs more than two column blocks."""
+    """Off-diagonal tiles + diagonal units (two diagonal tiles each: four 64 x 64 squares at box granularity + four upper-right
+    32 x 64 blocks): every (i, j), j >= i, of the K x K result is produced exactly once by the reduce kernel's decode, every column
+    has exactly one moment-vector writer, a unit never needs more than two column blocks, and the two warps of an SM sub-partition
+    (w, w + 4) of a diagonal unit carry one square and one block."""
+    assert [_square_pair(p) for p in range(10)] == [(0, 0), (0, 1), (0, 2), (0, 3), (1, 1), (1, 2), (1, 3), (2, 2), (2, 3), (3, 3)]
     for T in (1, 2, 3, 4, 8, 9):
         K = 128 * T
-        units = T * (T - 1) // 2 + (6 * T + 7) // 8
+        units = T * (T - 1) // 2 + (T + 1) // 2
         cover = np.zeros((K, K), dtype=np.int32)
         vec_writers = np.zeros(K, dtype=np.int32)
         for u in range(units):
+            kinds = []
             for w in range(8):
-                cb_a, wm, cb_b, wn, valid, vec, cb0, cb1 = _syrk_warp_block(T, u, w)
+                kind, cb_a, wm, cb_b, wn, valid, vec, cb0, cb1 = _syrk_warp_block(T, u, w)
+                kinds.append(kind)
                 assert cb_a in (cb0, cb1) and cb_b in (cb0, cb1) and cb1 - cb0 >= 0
                 if not valid:
                     continue
-                i0, j0 = 128 * cb_a + 32 * wm, 128 * cb_b + 64 * wn
-                ii, jj = np.meshgrid(np.arange(i0, i0 + 32), np.arange(j0, j0 + 64), indexing="ij")
-                keep = jj >= ii
-                cover[ii[keep], jj[keep]] += 1
+                # the reduce kernel's decode of (acc index a, lane (g, t)) -> (i, j)
+                g, t = np.meshgrid(np.arange(8), np.arange(4), indexing="ij")
+                for a in range(80 if kind == 1 else 64):
+                    if kind == 0:
+                        mt, nt, c = a >> 4, (a >> 1) & 7, a & 1
+                        i = 128 * cb_a + 32 * wm + 16 * (mt >> 1) + 2 * g + (mt & 1)
+                        j = 128 * cb_b + 64 * wn + 16 * (nt >> 1) + 4 * t + 2 * c + (nt & 1)
+                    else:
+                        bi, bj = _square_pair(a >> 3)
+                        e1, e2, c = (a >> 2) & 1, (a >> 1) & 1, a & 1
+                        base = 128 * cb_a + 64 * wm
+                        i = base + 16 * bi + 2 * g + e1
+                        j = base + 16 * bj + 4 * t + 2 * c + e2
+                    keep = j >= i
+                    np.add.at(cover, (i[keep], j[keep]), 1)
                 if vec:
-                    vec_writers[i0:i0 + 32] += 1
+                    assert kind == 0
+                    a0 = 128 * cb_a + 32 * wm
+                    b0 = 128 * cb_b + 64 * wn + 32 * wm
+                    vec_writers[a0:a0 + 32] += 1
+                    vec_writers[b0:b0 + 32] += 1
+            if u >= T * (T - 1) // 2:
+                assert all(kinds[w] + kinds[w + 4] == 1 for w in range(4)), "one square and one block per SM sub-partition"
         assert np.array_equal(np.triu(cover), np.triu(np.ones((K, K), dtype=np.int32))), T
         assert np.all(vec_writers == 1)
-    assert 4 * 3 // 2 + (6 * 4 + 7) // 8 == 9  # K = 500: 9 units instead of 10 tiles
+    assert 4 * 3 // 2 + (4 + 1) // 2 == 8  # K = 500: 6 + 2 units (cost 8.25) instead of 9 packed units / 10 tiles
