@@ -513,13 +513,13 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
   // Moment vectors: ride along as two extra columns of the last (padded) column block whenever it has room — the box holding
   // column Kf is then loaded from an auxiliary R x 16 tensor (syrk_aux_box_kernel). Otherwise (Kf % 16 == 15 or Kf % 128 == 0):
   // a weighted column-sum pass after the SYRK.
-  const bool aug = dvec && !dmean && R > 0 && (Kf % 128) != 0 && (Kf % 16) <= 14 && !getenv("PLB200_SYRK_NO_AUG");
+  const bool aug = (dvec || dmean) && R > 0 && (Kf % 128) != 0 && (Kf % 16) <= 14 && !getenv("PLB200_SYRK_NO_AUG");
   p.aux_box = -1;
   tmx = tm;
   if (aug) {
     void* aux;
     PL_TRY(ws_get(WS_SYRK_AUX, (size_t)R * 16 * 8, &aux));
-    syrk_aux_box_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, st>>>(A, R, Kf, ld, db, ne, (double*)aux);
+    syrk_aux_box_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, st>>>(A, R, Kf, ld, db, ne, dmean ? 1 : 0, (double*)aux);
     LAUNCH_CHECK();
     PL_TRY(make_tmap_2d(&tmx, (const double*)aux, 16, R, 16, 16, SYRK_BK));
     p.aux_box = (int)(Kf / 16);
@@ -553,13 +553,24 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
       free(h);
     }
   }
-  if (dmean) {
+  double* augvec = aug ? dvec : nullptr;
+  if (dmean && aug) {  // rho arrives as the augmented column: reduce S' first, then subtract rho_i m_j
+    void* tmp;
+    PL_TRY(ws_get(WS_SYRK_VEC, (size_t)(2 * Kf + 2) * 8, &tmp));
+    augvec = (double*)tmp;
+  } else if (dmean) {
     // rho_i = sum_r (a_ri - m_i) closes the one-sided centring (S_ij = S'_ij - rho_i m_j): one HBM-rate pass, differences first
     PL_TRY(colsum(A, R, Kf, ld, 0.0, (double*)rho, st, dmean));
   }
-  syrk_reduce_kernel<<<dim3((unsigned)p.ntiles, SYRK_TILE_ELEMS / 256), 256, 0, st>>>(p.ws_tiles, p.T, p.ntiles, p.splits, Kf, dS, dmean, (const double*)rho,
-                                                                                   aug ? dvec : nullptr);
+  syrk_reduce_kernel<<<dim3((unsigned)p.ntiles, SYRK_TILE_ELEMS / 256), 256, 0, st>>>(p.ws_tiles, p.T, p.ntiles, p.splits, Kf, dS, (dmean && !aug) ? dmean : nullptr,
+                                                                                   (const double*)rho, augvec);
   LAUNCH_CHECK();
+  if (dmean && aug) {
+    int blocks = (int)((Kf * Kf + 255) / 256);
+    if (blocks > g.num_sms * 8) blocks = g.num_sms * 8;
+    syrk_center_fix_kernel<<<blocks, 256, 0, st>>>(dS, Kf, augvec, dmean);
+    LAUNCH_CHECK();
+  }
   if (dvec && !aug) {
     PL_TRY(moment_vectors(A, R, Kf, ld, dw, ne, w_e, w_f, db, dvec, dvec + Kf, st));
     syrk_scalar_kernel<<<1, 1024, 0, st>>>(dw, db, ne, w_e, dvec + 2 * Kf);

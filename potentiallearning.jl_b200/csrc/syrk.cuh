@@ -440,8 +440,10 @@ __global__ void syrk_reduce_kernel(const double* __restrict__ ws_tiles, int T, i
 // The SYRK producer loads box q from this tensor instead of A, so A'Wb, the intercept row A'W 1_e and the two scalars fall out of
 // the SAME DMMA contraction as two more columns of the (already padded) last column block: no instruction is added to the main loop,
 // and no second pass over A is needed (a weighted column-sum pass costs 2.3 ms of HBM time at config 3, 10 % of the SYRK).
+// ones != 0 (centred mode): column rem holds 1 instead of b_r, so that S'_aug[i][Kf] = sum_r (a_ri - m_i) = rho_i — exactly the sum of
+// the rounded differences the kernel contracted, which is what closes the one-sided centring.
 __global__ void syrk_aux_box_kernel(const double* __restrict__ A, int64_t R, int64_t Kf, int64_t lda, const double* __restrict__ b, int64_t ne,
-                                    double* __restrict__ aux) {
+                                    int ones, double* __restrict__ aux) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= R * 16) return;
   const int64_t r = e >> 4;
@@ -449,7 +451,7 @@ __global__ void syrk_aux_box_kernel(const double* __restrict__ A, int64_t R, int
   const int rem = (int)(Kf & 15);
   double v = 0.0;
   if (c < rem) v = A[r * lda + (Kf - rem) + c];
-  else if (c == rem) v = b ? b[r] : 0.0;
+  else if (c == rem) v = ones ? 1.0 : (b ? b[r] : 0.0);
   else if (c == rem + 1) v = r < ne ? 1.0 : 0.0;
   aux[e] = v;
 }
@@ -504,6 +506,19 @@ __global__ void normal_eq_finish_kernel(const double* __restrict__ S, const doub
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
       AtWb[i] = (ic && i == 0) ? vec[2 * Kf + 1] : vec[i - ic];
     }
+  }
+}
+
+// S[i][j] = S[j][i] = S'[i][j] - rho_i m_j over the j >= i triangle: closes the one-sided centring when rho came out of the
+// augmented contraction (the reduce kernel has already mirrored S', so both triangles hold S'[min][max])
+__global__ void syrk_center_fix_kernel(double* __restrict__ S, int64_t Kf, const double* __restrict__ rho, const double* __restrict__ mean) {
+  const int64_t total = Kf * Kf;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / Kf, j = e % Kf;
+    if (j < i) continue;
+    const double v = fma(-rho[i], mean[j], S[e]);
+    S[e] = v;
+    S[j * Kf + i] = v;
   }
 }
 
