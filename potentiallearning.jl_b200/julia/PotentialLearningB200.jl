@@ -11,8 +11,10 @@
 #   learn!(lp::UnivariateLinearProblem, α::Real)   (assembly only)             src/Learning/linear-learn.jl:11-23
 #   compute_eigen(d::Vector{<:Vector{<:Real}})                                 src/DimensionReduction/dimension_reduction.jl:11-14
 #   fit!(ds::DataSet, pca::PCAState)                                           src/DimensionReduction/pca_state.jl:20-40
+#   compute_features(ds::DataSet, f::GlobalMean / ::GlobalSum)                 src/Kernels/features.jl:19-34, 76-78   (widened row f2)
 # kDPP(ds, f, k) / kDPP(features, k) (src/SubsetSelection/dpp.jl:18-44) need no override: they call KernelMatrix and hand
-# the Symmetric result to Determinantal.jl exactly as before.
+# the Symmetric result to Determinantal.jl exactly as before. Optional (widened row f1): `ell_ensemble_gpu(F, k)` returns the
+# eigendecomposition computed on the device for callers that construct Determinantal's ensemble from (λ, U) themselves.
 #
 # NOTE: Julia is not installed in the build image nor on the benchmark box, so this file has never been executed there.
 # It is deliberately declarative (pack -> ccall -> wrap); all logic lives behind the C ABI, which the Python ctypes mirror
@@ -21,8 +23,9 @@ module PotentialLearningB200
 
 using LinearAlgebra
 using PotentialLearning
-import PotentialLearning: KernelMatrix, learn!, fit!, compute_eigen, DotProduct, RBF, Euclidean, UnivariateLinearProblem,
-                          CovariateLinearProblem, PCAState, DataSet, get_values, get_local_descriptors, select_eigendirections
+import PotentialLearning: KernelMatrix, learn!, fit!, compute_eigen, compute_features, DotProduct, RBF, Euclidean, GlobalMean, GlobalSum,
+                          UnivariateLinearProblem, CovariateLinearProblem, PCAState, DataSet, get_values, get_local_descriptors,
+                          select_eigendirections
 
 const libplb200 = get(ENV, "PLB200_LIB", joinpath(@__DIR__, "..", "plb200", "libplb200.so"))
 
@@ -114,9 +117,22 @@ function learn!(lp::UnivariateLinearProblem, ws::Vector, int::Bool)             
     if int; lp.β0 .= βs[1]; lp.β .= βs[2:end] else lp.β .= βs end
 end
 
+# Streamed form (pl_normal_eq_blocks, widened row f2): lp.dB[i] (K x 3natoms, column-major) IS 3natoms rows of K in memory, so the
+# blocks are handed over as they lie — no hcat copy of the 11.5 GB design matrix; H2D chunks overlap the SYRK inside the library.
+function normal_eq_blocks(blocks::Vector{<:StridedMatrix{Float64}}, b::Vector{Float64}, ne::Integer, we, wf, int::Bool, λ)
+    K = size(blocks[1], 1); n = K + (int ? 1 : 0)
+    ptrs = [pointer(B) for B in blocks]; rows = Int64[size(B, 2) for B in blocks]
+    AtWA = zeros(n, n); AtWb = zeros(n)
+    GC.@preserve blocks check(ccall((:pl_normal_eq_blocks, libplb200), Cint,
+                (Ptr{Ptr{Cdouble}}, Ptr{Int64}, Int64, Int64, Ptr{Cdouble}, Int64, Cdouble, Cdouble, Ptr{Cdouble}, Cint, Cdouble, Int64, Ptr{Cdouble}, Ptr{Cdouble}),
+                ptrs, rows, length(blocks), K, C_NULL, ne, we, wf, b, int, λ, 0, AtWA, AtWb), "pl_normal_eq_blocks")
+    AtWA, AtWb
+end
+
 function learn!(lp::CovariateLinearProblem, ws::Vector, int::Bool; λ::Real = 0.0)      # linear-learn.jl:226-268
-    A = hcat(pack_rows(lp.B), pack_rows(lp.dB)); b = Float64.(vcat(lp.e, reduce(vcat, lp.f)))
-    M, v = normal_eq(A, b, length(lp.e), ws[1], ws[2], int, Float64(λ))
+    blocks = vcat([pack_rows(lp.B)], [Matrix{Float64}(dBi) for dBi in lp.dB])          # Matrix(...) is a no-op for Matrix{Float64}
+    b = Float64.(vcat(lp.e, reduce(vcat, lp.f)))
+    M, v = normal_eq_blocks(blocks, b, length(lp.e), ws[1], ws[2], int, Float64(λ))
     βs = solve(M, v)
     if int; lp.β0 .= βs[1]; lp.β .= βs[2:end] else lp.β .= βs end
 end
@@ -139,13 +155,52 @@ function cov_gpu(d::Vector{<:Vector{<:Real}}; center = false, mean = Float64[])
     Symmetric(C), m
 end
 
-compute_eigen(d::Vector{T}) where {T<:Vector{<:Real}} = eigen(first(cov_gpu(d)))        # dimension_reduction.jl:11-14
+# eigen(Symmetric(Q)) on the device (pl_eigh, widened row f1): row k of the library's V is column k of Julia's `vectors`
+function eigen_gpu(Q::Symmetric{Float64,Matrix{Float64}})
+    n = size(Q, 1); W = zeros(n); V = zeros(n, n)
+    A = Q.data                                                                          # uplo = :U of column-major == PL_FILL_RM_LOWER
+    check(ccall((:pl_eigh, libplb200), Cint, (Ptr{Cdouble}, Int64, Int64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Int64),
+                A, n, n, Q.uplo == 'U' ? Cint(2) : Cint(1), W, V, n), "pl_eigh")
+    Eigen(W, V)
+end
+
+compute_eigen(d::Vector{T}) where {T<:Vector{<:Real}} = eigen_gpu(first(cov_gpu(d)))    # dimension_reduction.jl:11-14
+
+# EllEnsemble(KernelMatrix(F, k)) fused on the device (pl_ell_ensemble): (λ ascending, K as Symmetric). U stays resident in the
+# library; `ell_inclusion_prob(α, n)` and `ell_eigvecs(idx, n)` read it there (Determinantal.inclusion_prob / the eigenvectors a
+# k-DPP draw selected), so n x n never crosses PCIe.
+function ell_ensemble_gpu(F::Vector{Vector{Float64}}, k::Union{DotProduct,RBF})
+    X = pack(F); d, n = size(X); λ = zeros(n); K = zeros(n, n)
+    kid, α, kind, cptr, keep, ℓ, β = k isa DotProduct ? (PL_KERNEL_DOT, Cint(k.α), PL_CINV_IDENTITY, C_NULL, nothing, 1.0, 1.0) :
+                                                      (PL_KERNEL_RBF, Cint(0), cinv_args(k.d)..., Float64(k.ℓ), Float64(k.β))
+    GC.@preserve keep check(ccall((:pl_ell_ensemble, libplb200), Cint,
+                (Cint, Ptr{Cdouble}, Int64, Int64, Int64, Cint, Cint, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Int64),
+                kid, X, n, d, d, α, kind, cptr, ℓ, β, λ, K, n), "pl_ell_ensemble")
+    λ, Symmetric(K)
+end
+ell_inclusion_prob(α::Real, n::Integer) = (p = zeros(n);
+    check(ccall((:pl_ell_inclusion_prob, libplb200), Cint, (Cdouble, Int64, Ptr{Cdouble}), Float64(α), n, p), "pl_ell_inclusion_prob"); p)
+ell_eigvecs(idx::Vector{Int64}, n::Integer) = (V = zeros(n, length(idx));                # 0-based eigenvector indices; column j = U[:, idx[j]+1]
+    check(ccall((:pl_ell_eigvecs, libplb200), Cint, (Ptr{Int64}, Int64, Int64, Ptr{Cdouble}, Int64), idx, length(idx), n, V, n), "pl_ell_eigvecs"); V)
+
+# ---- GlobalMean / GlobalSum features of a whole DataSet (features.jl:19-34, 76-78) in one segmented reduction ------------------
+function global_features(ds::DataSet, mean::Bool)
+    locals = [reduce(hcat, get_values(get_local_descriptors(c))) for c in ds]            # d x natoms_i each == natoms_i rows of d
+    L = reduce(hcat, locals); d = size(L, 1); N = length(locals)
+    offsets = Int64[0; cumsum(size.(locals, 2))]
+    X = zeros(d, N)
+    check(ccall((:pl_global_feature, libplb200), Cint, (Ptr{Cdouble}, Int64, Ptr{Int64}, Int64, Int64, Cint, Ptr{Cdouble}, Int64),
+                L, d, offsets, N, d, mean, X, d), "pl_global_feature")
+    [X[:, i] for i in 1:N]                                                              # Vector{Vector{Float64}} like compute_feature.(ds, ...)
+end
+compute_features(ds::DataSet, f::GlobalMean; dt = nothing) = global_features(ds, true)
+compute_features(ds::DataSet, f::GlobalSum; dt = nothing) = global_features(ds, false)
 
 function fit!(ds::DataSet, pca::PCAState)                                              # pca_state.jl:20-40 (as written: descriptors only)
     d = sum.(get_values.(get_local_descriptors.(ds)))
     Q, m = cov_gpu(d; center = true, mean = pca.m == [] ? Float64[] : pca.m)            # mean persists (:34)
     pca.m = m
-    λ, ϕ = eigen(Q); λ, ϕ = λ[end:-1:1], ϕ[:, end:-1:1]                                 # dimension_reduction.jl:16-17
+    λ, ϕ = eigen_gpu(Q); λ, ϕ = λ[end:-1:1], ϕ[:, end:-1:1]                             # dimension_reduction.jl:16-17
     Σ = 1.0 .- cumsum(λ) / sum(λ)
     pca.λ, pca.W = λ, (pca.tol isa Int ? ϕ[:, 1:pca.tol] : ϕ[:, Σ .> pca.tol])
     nothing
