@@ -331,7 +331,9 @@ def test_reference_covariate_linear_tests(pl, orc):
     assert normerr(AtAe, re) < RTOL and normerr(Atbe, rbe) < RTOL and normerr(AtAf, rf) < RTOL and normerr(Atbf, rbf) < RTOL
 
 
-@pytest.mark.parametrize("R,K,ne", [(1, 1, 1), (17, 3, 5), (1000, 127, 0), (4099, 128, 99), (20000, 500, 700), (3000, 300, 3000)])
+# K = 127, 128, 255 exercise the weighted-column-sum fallback for the moment vectors, the others the augmented columns
+@pytest.mark.parametrize("R,K,ne", [(1, 1, 1), (17, 3, 5), (1000, 127, 0), (4099, 128, 99), (20000, 500, 700), (3000, 300, 3000), (2500, 255, 40), (5000, 142, 5000),
+                                    (70000, 14, 123)])
 def test_normal_equations_shapes(pl, orc, R, K, ne):
     rng = np.random.default_rng(R + K)
     A = rng.standard_normal((R, K))
@@ -400,7 +402,9 @@ def test_reference_dimension_reduction_tests(pl, orc):
     assert st_f.W.shape == W_f.shape
 
 
-@pytest.mark.parametrize("n,K", [(1, 1), (10, 8), (999, 129), (5000, 1000), (40000, 64)])
+# K = 15, 128, 255: shapes where the rho column cannot ride along as an augmented column (K % 16 == 15 or K % 128 == 0): the shifted
+# column-sum pass closes the one-sided centring instead
+@pytest.mark.parametrize("n,K", [(1, 1), (10, 8), (999, 129), (5000, 1000), (40000, 64), (700, 15), (3000, 128), (2000, 255)])
 def test_covariance_parity(pl, orc, n, K):
     rng = np.random.default_rng(n + K)
     X = 10.0 * rng.standard_normal(K) + rng.standard_normal((n, K))  # mean/sigma ~ 10: kills one-pass formulas
@@ -889,3 +893,25 @@ def test_compute_eigen_and_pca_on_device(pl, orc):
     assert np.max(np.abs(lam - lo)) / lo.max() < 1e-12
     Q = rows.T @ rows / 500
     assert np.max(np.abs(Q @ phi - phi * lam[None, :])) / lo.max() < 1e-12
+
+
+def test_normal_equations_aug_and_fallback_agree(pl, orc, monkeypatch):
+    """The moment vectors through the augmented columns (default) and through the weighted column-sum pass (PLB200_SYRK_NO_AUG)
+    are two routes to the same sums: they must agree to rounding, and S itself must be bit-identical (the main contraction is
+    untouched by the extra columns)."""
+    import os
+
+    rng = np.random.default_rng(91)
+    R, K, ne = 30000, 500, 1200
+    A = rng.standard_normal((R, K)) + 0.3
+    b = rng.standard_normal(R)
+    w = rng.uniform(0.1, 3.0, size=R)
+    for ww in (None, w):
+        M1, v1 = pl.normal_equations(A, b, ww, ne, 100.0, 1.0, True, 0.0)
+        os.environ["PLB200_SYRK_NO_AUG"] = "1"
+        try:
+            M2, v2 = pl.normal_equations(A, b, ww, ne, 100.0, 1.0, True, 0.0)
+        finally:
+            del os.environ["PLB200_SYRK_NO_AUG"]
+        assert np.array_equal(M1[1:, 1:], M2[1:, 1:])
+        assert normerr(M1, M2) < 1e-12 and normerr(v1, v2) < 1e-12  # two summation orders of the same 30 000 terms
