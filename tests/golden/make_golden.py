@@ -86,6 +86,23 @@ def main():
     out["cov_X"] = Xc
     out["cov_mean"], out["cov_centered"] = truth_cov(Xc, True)
     _, out["cov_raw"] = truth_cov(Xc, False)
+    # ---- widened rows, appended after the draws above so the earlier vectors stay bit-identical ----
+    # f2: GlobalSum / GlobalMean of ragged configurations, one of them beyond Julia's pairwise block size (1024 atoms)
+    nat = [1, 2, 17, 96, 1500]
+    mu6 = 3.0 * rng.standard_normal(6)
+    loc = [mu6 + rng.standard_normal((n, 6)) for n in nat]
+    out["gf_offsets"] = np.concatenate([[0], np.cumsum(nat)]).astype(np.int64)
+    out["gf_local"] = np.concatenate(loc, axis=0)
+    out["gf_sum"] = np.stack([l.astype(LD).sum(axis=0) for l in loc]).astype(np.float64)
+    out["gf_mean"] = np.stack([l.astype(LD).sum(axis=0) / LD(len(l)) for l in loc]).astype(np.float64)
+    # f4: InverseMultiquadric(Euclidean) (kernels.jl:156-164) on the config-1 slice
+    Xl = f1.astype(LD)
+    D2 = ((Xl[:, None, :] - Xl[None, :, :]) ** 2).sum(axis=2)
+    out["c1_imq"] = ((LD(1.3) + D2 / LD(0.9) ** 2) ** LD(-0.5)).astype(np.float64)
+    # f3: predictions A·β + β0 on the energy rows (Data/utils.jl:42-65)
+    beta = rng.standard_normal(d)
+    out["pr_beta"] = beta
+    out["pr_y"] = (A.astype(LD) @ beta.astype(LD) + LD(0.37) * np.concatenate([np.ones(ncfg), np.zeros(dB.shape[0])]).astype(LD)).astype(np.float64)
     np.savez_compressed(os.path.join(HERE, "hotpath_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "hotpath_golden.npz"), {k: v.shape for k, v in out.items()})
 

@@ -915,3 +915,30 @@ def test_normal_equations_aug_and_fallback_agree(pl, orc, monkeypatch):
             del os.environ["PLB200_SYRK_NO_AUG"]
         assert np.array_equal(M1[1:, 1:], M2[1:, 1:])
         assert normerr(M1, M2) < 1e-12 and normerr(v1, v2) < 1e-12  # two summation orders of the same 30 000 terms
+
+
+def test_golden_vectors_through_the_c_abi(pl):
+    """The committed extended-precision golden vectors (tests/golden/hotpath_golden.npz) straight against the CUDA path."""
+    import os
+
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "hotpath_golden.npz"))
+    F = G["c1_feat"]
+    assert relerr(np.asarray(pl.KernelMatrix(F, pl.DotProduct(3))), G["c1_dot3"]) < RTOL
+    assert relerr(np.asarray(pl.KernelMatrix(F, pl.RBF(pl.Euclidean(26), ell=0.8, beta=2.0))), G["c1_rbf"]) < RTOL
+    assert relerr(np.asarray(pl.KernelMatrix(F, pl.RBF(pl.Euclidean(pl.Diagonal(G["c1_cdiag"])), ell=1.5))), G["c1_rbf_diag"]) < RTOL
+    assert relerr(np.asarray(pl.KernelMatrix(F, pl.RBF(pl.Euclidean(pl.Symmetric(G["c1_cfull"])), ell=2.0))), G["c1_rbf_full"]) < RTOL
+    assert relerr(np.asarray(pl.KernelMatrix(F, pl.InverseMultiquadric(pl.Euclidean(26), c2=1.3, ell=0.9))), G["c1_imq"]) < RTOL
+    A, b, q = G["ne_A"], G["ne_b"], G["ne_q"]
+    M, v = pl.normal_equations(A, b, None, 12, 100.0, 1.0, False, 0.0)
+    assert normerr(M, G["ne_M"]) < RTOL and normerr(v, G["ne_v"]) < RTOL
+    M, v = pl.normal_equations(A, b, q, 12, 1.0, 1.0, True, 0.01)  # the same weights as a per-row array, with intercept and ridge
+    assert normerr(M, G["ne_Mi"]) < RTOL and normerr(v, G["ne_vi"]) < RTOL
+    C, m = pl.covariance(G["cov_X"], center=True)
+    assert relerr(m, G["cov_mean"]) < 1e-13 and normerr(C, G["cov_centered"]) < RTOL
+    C0, _ = pl.covariance(G["cov_X"], center=False)
+    assert normerr(C0, G["cov_raw"]) < RTOL
+    off, L = G["gf_offsets"], G["gf_local"]
+    assert relerr(pl.global_features(None, mean=False, stacked=(L, off)), G["gf_sum"]) < 1e-13
+    assert relerr(pl.global_features(None, mean=True, stacked=(L, off)), G["gf_mean"]) < 1e-13
+    y = pl.predict(A, G["pr_beta"], 0.37, 12)
+    assert normerr(y, G["pr_y"]) < RTOL

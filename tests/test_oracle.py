@@ -180,3 +180,26 @@ def test_design_numerics_mean_shift_and_two_pass():
 def test_pair_loop_sampler_counts_pairs():
     X = np.random.default_rng(1).standard_normal((50, 6))
     assert orc.kernel_matrix_rows(X, orc.RBF(orc.Euclidean(6)), 0, 4) == 50 + 49 + 48 + 47
+
+
+def test_golden_widened_rows():
+    """GlobalSum/GlobalMean in Julia's summation order (incl. the pairwise branch above 1024 atoms),
+    InverseMultiquadric, and the linear predictions, against the extended-precision golden vectors."""
+    off, L = GOLD["gf_offsets"], GOLD["gf_local"]
+    blocks = [L[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    S = orc.global_features(blocks, mean=False)
+    M = orc.global_features(blocks, mean=True)
+    assert relerr(S, GOLD["gf_sum"]) < 1e-13 and relerr(M, GOLD["gf_mean"]) < 1e-13
+    # below 1024 atoms the tree degenerates to the plain left-to-right sum (global_sum / global_mean)
+    for b, s, m in zip(blocks[:4], S, M):
+        assert np.array_equal(s, orc.global_sum(list(b))) and np.array_equal(m, orc.global_mean(list(b)))
+    # ... and above it is NOT the left-to-right sum but stays within rounding of it
+    seq = orc.global_sum(list(blocks[4]))
+    assert not np.array_equal(S[4], seq) and relerr(S[4], seq) < 1e-13
+    F = GOLD["c1_feat"]
+    for use_c in (False, True):
+        K = orc.symmetric(orc.kernel_matrix(F, orc.InverseMultiquadric(orc.Euclidean(26), c2=1.3, ell=0.9), use_c=use_c))
+        assert relerr(K, GOLD["c1_imq"]) < 1e-13
+    A = GOLD["ne_A"]
+    y = A @ GOLD["pr_beta"] + 0.37 * np.concatenate([np.ones(12), np.zeros(A.shape[0] - 12)])
+    assert normerr(y, GOLD["pr_y"]) < ULPS
