@@ -151,13 +151,13 @@ __device__ __forceinline__ double exp_clamped(double x) {
 //   rel0: (j - i) of accumulator (0,0,0) for diagonal tiles (elements with j < i are produced by mirroring, j == i is the
 //         kernel diagonal), 4096 otherwise. w1 / w2: write the direct / mirrored position; in diagonal tiles both
 //         positions are always written and hold 0 when their triangle was not requested (zeros(n,n) storage).
-template <int EPI, bool GENERAL, int ALPHA /* 2: DotProduct power 2 / RBF scale folded; 0: general (runtime p.alpha, p.bmul) */>
-__device__ __forceinline__ void gram_epilogue(const double (&acc)[4][8][2], const GramParams& p, int64_t i0, int64_t j0, int rel0, bool w1, bool w2,
+template <int EPI, bool GENERAL, int ALPHA /* 2: DotProduct power 2 / RBF scale folded; 0: general (runtime p.alpha, p.bmul) */, int MT, int NT>
+__device__ __forceinline__ void gram_epilogue(const double (&acc)[MT][NT][2], const GramParams& p, int64_t i0, int64_t j0, int rel0, bool w1, bool w2,
                                               double* __restrict__ prow, double* __restrict__ pcol, int64_t ldo) {
-  unsigned imask = 0xfu;
-  double sa[4];
+  unsigned imask = (1u << MT) - 1u;
+  double sa[MT];
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     bool ok = true;
     if (GENERAL) {
       ok = i0 + 8 * mt < p.n1;
@@ -175,10 +175,10 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[4][8][2], cons
   // 8 independent elements per step (one row, 4 column blocks x 2 columns = 2 full 128-byte lines of the direct store)
   // keep the FP64 pipe busy through the exp chains without blowing up the live register set
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     double* const pr = prow + (int64_t)(8 * mt) * ldo;
 #pragma unroll
-    for (int ng = 0; ng < 2; ++ng) {
+    for (int ng = 0; ng < NT / 4; ++ng) {
       double v[4][2];
       bool jok[4][2];
 #pragma unroll
@@ -224,9 +224,18 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[4][8][2], cons
   }
 }
 
-template <int EPI>
+// NARROW = 0: 128 x 128 output tile, warps 4 (m) x 2 (n), warp tile 32 x 64.
+// NARROW = 1: 128 x 32 output tile for rectangular results with few columns (projections W'(x - m) of transform!, pca_state.jl:42-62;
+//             KernelMatrix(F1, F2, k) against a handful of reference points): warps 8 (m) x 1, warp tile 16 x 32. A 128-wide tile
+//             would spend 128 / n2 times the DMMAs such a result needs; at n2 <= 32 the narrow tile is within 1.4 x of the HBM time of
+//             streaming the tall operand once.
+template <int EPI, int NARROW>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GramParams p) {
+  constexpr int BN = NARROW ? 32 : GRAM_BN;
+  constexpr int MT = NARROW ? 2 : 4;   // 8-row DMMA m-tiles per warp
+  constexpr int NT = NARROW ? 4 : 8;   // 8-column DMMA n-tiles per warp
+  constexpr uint32_t B_TILE_BYTES = BN * GRAM_BK * 8;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -262,7 +271,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (p.tcol_begin >= 0) gram_colrange_slot_to_tile(p.tcol_begin, l, ti, tj);
         else if (!gram_slot_to_tile(p.T1, p.T2, p.symmetric, l, ti, tj)) continue;
         const bool one_tile = p.same_operand && (ti == tj);
-        const uint32_t bytes = one_tile ? GRAM_TILE_BYTES : 2 * GRAM_TILE_BYTES;
+        const uint32_t bytes = one_tile ? GRAM_TILE_BYTES : GRAM_TILE_BYTES + B_TILE_BYTES;
         for (int kt = 0; kt < KT; ++kt, ++it) {
           const int s = it % GRAM_STAGES;
           const uint32_t ph = (it / GRAM_STAGES) & 1u;
@@ -270,7 +279,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_arrive_expect_tx(full_bar(s), bytes);
           const uint32_t dstA = smem_base + s * 2 * GRAM_TILE_BYTES;
           tma_load_2d(dstA, &tmA, full_bar(s), kt * GRAM_BK, ti * GRAM_BM);
-          if (!one_tile) tma_load_2d(dstA + GRAM_TILE_BYTES, &tmB, full_bar(s), kt * GRAM_BK, tj * GRAM_BN);
+          if (!one_tile) tma_load_2d(dstA + GRAM_TILE_BYTES, &tmB, full_bar(s), kt * GRAM_BK, tj * BN);
         }
       }
     }
@@ -279,15 +288,15 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   // ------------------------------ DMMA consumers ------------------------------
   setmaxnreg_inc<CONSUMER_REGS>();
-  const int wm = warp >> 1;  // 0..3 : 32-row slab
-  const int wn = warp & 1;   // 0..1 : 64-col slab
+  const int wm = NARROW ? warp : warp >> 1;  // 8*MT-row slab
+  const int wn = NARROW ? 0 : warp & 1;      // 8*NT-col slab
   const int g = lane >> 2;
   const int t = lane & 3;
   const int pg = ((g & 1) << 2) | (g >> 1);  // tile row (within an 8-row group) served by fragment row g
   // byte offset of this thread's 16B chunk inside a 128B row for k-half 0; k-half 1 is the same ^ 64
   const uint32_t xo = (uint32_t)((t ^ pg) << 4);
-  const uint32_t offA0 = (uint32_t)((32 * wm + pg) * 128) + xo;  // + mt * 1024
-  const uint32_t offB0 = (uint32_t)((64 * wn + pg) * 128) + xo;  // + nt * 1024
+  const uint32_t offA0 = (uint32_t)((8 * MT * wm + pg) * 128) + xo;  // + mt * 1024
+  const uint32_t offB0 = (uint32_t)((8 * NT * wn + pg) * 128) + xo;  // + nt * 1024
 
   uint32_t it = 0;
   for (int64_t l = slot0; l < p.ntiles_total; l += slot_stride) {
@@ -296,25 +305,25 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     else if (!gram_slot_to_tile(p.T1, p.T2, p.symmetric, l, ti, tj)) continue;
     const bool one_tile = p.same_operand && (ti == tj);
 
-    double acc[4][8][2];
+    double acc[MT][NT][2];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
     // Software-pipelined main loop: the fragments of the next half-step (and, across k-iterations, the barrier wait of the
     // next stage) are issued before the 64 DMMAs of the current half-step, so LDS latency and mbarrier wake-up never
     // expose the DMMA pipe. Two fragment buffers of 12 x 128 bit (96 registers) on top of the 128 accumulator registers.
-    double2 a0[4], b0[8], a1[4], b1[8];
+    double2 a0[MT], b0[NT], a1[MT], b1[NT];
     {
       const int s = it % GRAM_STAGES;
       mbar_wait(full_bar(s), (it / GRAM_STAGES) & 1u);
       const uint32_t sA = smem_base + s * 2 * GRAM_TILE_BYTES;
       const uint32_t sB = one_tile ? sA : sA + GRAM_TILE_BYTES;
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) a0[mt] = lds128(sA + (offA0 + mt * 1024));
+      for (int mt = 0; mt < MT; ++mt) a0[mt] = lds128(sA + (offA0 + mt * 1024));
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) b0[nt] = lds128(sB + (offB0 + nt * 1024));
+      for (int nt = 0; nt < NT; ++nt) b0[nt] = lds128(sB + (offB0 + nt * 1024));
     }
     for (int kt = 0; kt < KT; ++kt, ++it) {
       const int s = it % GRAM_STAGES;
@@ -322,35 +331,35 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t sB = one_tile ? sA : sA + GRAM_TILE_BYTES;
       // second k-half of this stage -> buffer 1, then the stage can go back to the producer
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) a1[mt] = lds128(sA + ((offA0 + mt * 1024) ^ 64u));
+      for (int mt = 0; mt < MT; ++mt) a1[mt] = lds128(sA + ((offA0 + mt * 1024) ^ 64u));
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) b1[nt] = lds128(sB + ((offB0 + nt * 1024) ^ 64u));
+      for (int nt = 0; nt < NT; ++nt) b1[nt] = lds128(sB + ((offB0 + nt * 1024) ^ 64u));
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a0[mt].x, b0[nt].x);
+        for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a0[mt].x, b0[nt].x);
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a0[mt].y, b0[nt].y);
+        for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a0[mt].y, b0[nt].y);
       if (kt + 1 < KT) {
         const int s2 = (it + 1) % GRAM_STAGES;
         mbar_wait(full_bar(s2), ((it + 1) / GRAM_STAGES) & 1u);
         const uint32_t sA2 = smem_base + s2 * 2 * GRAM_TILE_BYTES;
         const uint32_t sB2 = one_tile ? sA2 : sA2 + GRAM_TILE_BYTES;
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) a0[mt] = lds128(sA2 + (offA0 + mt * 1024));
+        for (int mt = 0; mt < MT; ++mt) a0[mt] = lds128(sA2 + (offA0 + mt * 1024));
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) b0[nt] = lds128(sB2 + (offB0 + nt * 1024));
+        for (int nt = 0; nt < NT; ++nt) b0[nt] = lds128(sB2 + (offB0 + nt * 1024));
       }
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a1[mt].x, b1[nt].x);
+        for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a1[mt].x, b1[nt].x);
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a1[mt].y, b1[nt].y);
+        for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a1[mt].y, b1[nt].y);
       // all fragments of stage s have been consumed from registers (a DMMA reads its operands at issue): release the stage
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar(s));
@@ -359,18 +368,18 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------ fused epilogue ------------------------------
     // accumulator (mt, nt, c) of lane (g, t) is element
     //   i = 128*ti + 32*wm + 8*mt + perm(g),   j = 128*tj + 64*wn + 8*nt + perm(2t + c) = ... + t + 4c
-    const int il0 = 32 * wm + pg;  // local row of mt = 0
-    const int jl0 = 64 * wn + t;   // local col of (nt = 0, c = 0)
+    const int il0 = 8 * MT * wm + pg;  // local row of mt = 0
+    const int jl0 = 8 * NT * wn + t;   // local col of (nt = 0, c = 0)
     const int64_t i0 = (int64_t)ti * GRAM_BM + il0;
-    const int64_t j0 = (int64_t)tj * GRAM_BN + jl0;
+    const int64_t j0 = (int64_t)tj * BN + jl0;
     const bool diag_tile = p.symmetric && (ti == tj);
     const bool f1 = p.packed || !p.symmetric || (p.fill & 1);            // write [i][j]
     const bool f2 = !p.packed && p.symmetric && (p.fill & 2);            // write [j][i] (off-diagonal tiles)
     double* base;
     int64_t ldo, ib, jb;
     if (p.packed) {  // tile k = (l - part) / nparts of this part, 128 x 128 row-major
-      base = p.out + ((l - p.part) / p.nparts) * (int64_t)(GRAM_BM * GRAM_BN);
-      ldo = GRAM_BN;
+      base = p.out + ((l - p.part) / p.nparts) * (int64_t)(GRAM_BM * BN);
+      ldo = BN;
       ib = il0;
       jb = jl0;
     } else {
@@ -381,18 +390,18 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     double* const prow = base + ib * ldo + jb;  // direct:  prow[8*mt*ldo + 8*nt + 4*c]
     double* const pcol = base + jb * ldo + ib;  // mirror:  pcol[(8*nt + 4*c)*ldo + 8*mt]
-    const bool interior = ((int64_t)(ti + 1) * GRAM_BM <= p.n1) && ((int64_t)(tj + 1) * GRAM_BN <= p.n2);
+    const bool interior = ((int64_t)(ti + 1) * GRAM_BM <= p.n1) && ((int64_t)(tj + 1) * BN <= p.n2);
     const int rel0 = diag_tile ? (jl0 - il0) : 4096;
     const bool w1 = f1 || diag_tile, w2 = diag_tile ? true : f2;
     // ALPHA doubles as the "uncommon parameters" switch: DotProduct power != 2, or an RBF scale beta <= 0 that cannot be
     // folded into the exponent: one general instantiation
     const bool common = (EPI == EPI_DOT) ? (p.alpha == 2) : (EPI == EPI_RBF ? (p.bmul == 1.0) : true);
     if (!common) {
-      gram_epilogue<EPI, true, 0>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo);
+      gram_epilogue<EPI, true, 0, MT, NT>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo);
     } else if (interior && !diag_tile) {
-      gram_epilogue<EPI, false, 2>(acc, p, i0, j0, 0, f1, f2, prow, pcol, ldo);
+      gram_epilogue<EPI, false, 2, MT, NT>(acc, p, i0, j0, 0, f1, f2, prow, pcol, ldo);
     } else {
-      gram_epilogue<EPI, true, 2>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo);
+      gram_epilogue<EPI, true, 2, MT, NT>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo);
     }
   }
 }

@@ -257,9 +257,12 @@ struct GramLaunch {
 
 int launch_gram(const GramLaunch& L, cudaStream_t st) {
   if (L.nA == 0 || L.nB == 0) return PL_OK;
+  // rectangular results with few columns (projections, cross kernels against a handful of points): the 128 x 32 tile
+  const bool narrow = !L.symmetric && !L.packed && L.nB <= 96;
+  const int BN = narrow ? 32 : GRAM_BN;
   CUtensorMap tmA, tmB;
   PL_TRY(make_tmap_2d(&tmA, L.A, L.d, L.nA, L.ldA, GRAM_BK, GRAM_BM));
-  PL_TRY(make_tmap_2d(&tmB, L.B, L.d, L.nB, L.ldB, GRAM_BK, GRAM_BN));
+  PL_TRY(make_tmap_2d(&tmB, L.B, L.d, L.nB, L.ldB, GRAM_BK, BN));
   GramParams p;
   p.n1 = L.nA;
   p.n2 = L.nB;
@@ -278,7 +281,7 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   p.lnbeta = (L.epi == EPI_RBF && L.beta > 0.0) ? log(L.beta) : 0.0;
   p.bmul = (L.epi == EPI_RBF && L.beta > 0.0) ? 1.0 : L.beta;
   p.T1 = (int)((L.nA + GRAM_BM - 1) / GRAM_BM);
-  p.T2 = (int)((L.nB + GRAM_BN - 1) / GRAM_BN);
+  p.T2 = (int)((L.nB + BN - 1) / BN);
   p.tcol_begin = L.tcol_begin;
   p.tcol_end = L.tcol_end;
   p.ntiles_total = L.tcol_begin >= 0 ? gram_colrange_num_slots(L.tcol_begin, L.tcol_end) : gram_num_slots(p.T1, p.T2, p.symmetric);
@@ -288,12 +291,22 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   if (mine <= 0) return PL_OK;
   const int grid = (int)(mine < g.num_sms ? mine : g.num_sms);
   if (L.epi != EPI_LINEAR || L.packed || L.symmetric) MAIN_KERNEL_BEGIN(st);
-  switch (L.epi) {
-    case EPI_LINEAR: gram_kernel<EPI_LINEAR><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
-    case EPI_DOT: gram_kernel<EPI_DOT><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
-    case EPI_RBF: gram_kernel<EPI_RBF><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
-    case EPI_IMQ: gram_kernel<EPI_IMQ><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
-    default: return set_err(PL_EINVAL, "unknown epilogue %d", L.epi);
+  if (narrow) {
+    switch (L.epi) {
+      case EPI_LINEAR: gram_kernel<EPI_LINEAR, 1><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
+      case EPI_DOT: gram_kernel<EPI_DOT, 1><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
+      case EPI_RBF: gram_kernel<EPI_RBF, 1><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
+      case EPI_IMQ: gram_kernel<EPI_IMQ, 1><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
+      default: return set_err(PL_EINVAL, "unknown epilogue %d", L.epi);
+    }
+  } else {
+    switch (L.epi) {
+      case EPI_LINEAR: gram_kernel<EPI_LINEAR, 0><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
+      case EPI_DOT: gram_kernel<EPI_DOT, 0><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
+      case EPI_RBF: gram_kernel<EPI_RBF, 0><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
+      case EPI_IMQ: gram_kernel<EPI_IMQ, 0><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
+      default: return set_err(PL_EINVAL, "unknown epilogue %d", L.epi);
+    }
   }
   LAUNCH_CHECK();
   if (L.epi != EPI_LINEAR || L.packed || L.symmetric) MAIN_KERNEL_END(st);
@@ -868,10 +881,14 @@ int pl_init(int device) {
   CUDA_TRY(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
   for (auto& ev : g.ev) CUDA_TRY(cudaEventCreate(&ev));
   for (auto& ev : g.chunk_ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_IMQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_LINEAR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_DOT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_RBF, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_IMQ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_LINEAR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_DOT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_RBF, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_IMQ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
   g.ready = true;

@@ -34,7 +34,7 @@ def timeit(fn, warm=2, reps=5):
     return min(ts), float(np.median(ts))
 
 
-which = sys.argv[1:] or ["feat", "neq", "eig"]
+which = sys.argv[1:] or ["feat", "neq", "eig", "proj"]
 
 if "feat" in which:
     # config-2 shape: 20 000 configurations x 96 atoms x 300 descriptors = 4.6 GB of local descriptors
@@ -116,6 +116,22 @@ if "eig" in which:
             rec["numpy_eigh_ms"] = (time.perf_counter() - t0) * 1e3
             rec["lambda_max_rel_err"] = float(np.max(np.abs(ell.λ - np.maximum(lo, 0))) / lo.max())
         out[f"eig_{n}"] = rec
+
+if "proj" in which:
+    # transform!-shaped projections: 2.5 M rows x K = 1000 onto p directions, device-resident (the LINEAR Gram epilogue)
+    from plb200.kernels import _Linear, kernel_matrix_dev
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Rp, Kp = 2_500_000, 1000
+    Xd = torch.randn((Rp, Kp), device="cuda", dtype=torch.float64, generator=g)
+    for pdim in (8, 32, 64, 96, 128):
+        Wt = torch.randn((pdim, Kp), device="cuda", dtype=torch.float64, generator=g)
+        Yd = torch.empty((Rp, pdim + (pdim & 1)), device="cuda", dtype=torch.float64)[:, :pdim]
+        best, med = timeit(lambda: kernel_matrix_dev(Xd, _Linear(), out=Yd, X2=Wt), 1, 3)
+        ref = Xd[:4096] @ Wt.T
+        out[f"project_{Rp}x{Kp}_p{pdim}"] = {"ms": best, "read_GBs": Rp * Kp * 8 / best / 1e6, "tflops": 2.0 * Rp * Kp * pdim / best / 1e9,
+                                             "max_abs_err_4096_rows": float((Yd[:4096] - ref).abs().max())}
+    del Xd
 
 out["launches"] = plb200.launch_count()
 print(json.dumps(out))

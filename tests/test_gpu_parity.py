@@ -942,3 +942,28 @@ def test_golden_vectors_through_the_c_abi(pl):
     assert relerr(pl.global_features(None, mean=True, stacked=(L, off)), G["gf_mean"]) < 1e-13
     y = pl.predict(A, G["pr_beta"], 0.37, 12)
     assert normerr(y, G["pr_y"]) < RTOL
+
+
+@pytest.mark.parametrize("n2", [1, 5, 31, 32, 33, 64, 96, 97, 130])
+def test_narrow_tile_cross_kernels_and_projections(pl, orc, n2):
+    """Rectangular results with few columns run on the 128 x 32 tile (n2 <= 96) instead of the 128 x 128 one: every kernel
+    against the oracle across the switch-over, plus the projection W'(x - m) of transform! (pca_state.jl:42-62)."""
+    rng = np.random.default_rng(1000 + n2)
+    m, d = 300, 37
+    mu = 2.0 * rng.standard_normal(d)  # a common mean: cosines stay away from 0 (a relative test of cos^3 near 0 measures cancellation)
+    F1 = rng.standard_normal((m, d)) * 0.5 + mu
+    F2 = rng.standard_normal((n2, d)) * 0.5 + mu
+    cd = rng.uniform(0.5, 2.0, size=d)
+    for kp, ko in ((pl.DotProduct(3), orc.DotProduct(3)),
+                   (pl.RBF(pl.Euclidean(d), ell=1.7, beta=0.5), orc.RBF(orc.Euclidean(d), ell=1.7, beta=0.5)),
+                   (pl.RBF(pl.Euclidean(pl.Diagonal(cd)), ell=2.0), orc.RBF(orc.Euclidean(d, cd), ell=2.0)),
+                   (pl.InverseMultiquadric(pl.Euclidean(d), c2=0.7, ell=1.1), orc.InverseMultiquadric(orc.Euclidean(d), c2=0.7, ell=1.1))):
+        K = pl.KernelMatrix(F1, F2, kp)
+        Ko = orc.kernel_matrix_cross(F1, F2, ko, use_c=True)
+        assert K.shape == (m, n2) and relerr(K, Ko) < RTOL, type(kp).__name__
+    # projection: X (rows x K) times W (K x p), shifted
+    X = rng.standard_normal((1000, 64)) + 3.0
+    W = np.linalg.qr(rng.standard_normal((64, min(n2, 64))))[0]
+    shift = X.mean(0)
+    Y = pl.project(X, W, shift)
+    assert normerr(Y, (X - shift) @ W) < 1e-11  # the shift is applied as X·W - shift·W (|shift|/sigma = 3)
