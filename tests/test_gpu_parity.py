@@ -967,3 +967,83 @@ def test_narrow_tile_cross_kernels_and_projections(pl, orc, n2):
     shift = X.mean(0)
     Y = pl.project(X, W, shift)
     assert normerr(Y, (X - shift) @ W) < 1e-11  # the shift is applied as X·W - shift·W (|shift|/sigma = 3)
+
+
+def test_no_out_of_bounds_writes(pl):
+    """Guard-band check of every device entry point that writes a caller buffer (compute-sanitizer is not available on the
+    pool): outputs are views into larger sentinel-filled allocations; after the call the sentinels must be intact —
+    leading/trailing guard regions and, for matrices, the padding columns between n and the leading dimension."""
+    import torch
+
+    from plb200 import _lib
+
+    lib = _lib.lib()
+    dev = torch.device("cuda")
+    SENT = -777.25
+    st = torch.cuda.current_stream().cuda_stream
+
+    def guarded(rows, cols, ld):
+        off = (ld + 17) & ~1  # even element offset: the view stays 16-byte aligned
+        buf = torch.full((off + (rows + 1) * ld + 64,), SENT, device=dev, dtype=torch.float64)
+        view = buf[off: off + rows * ld].view(rows, ld)
+        return buf, view
+
+    def check(buf, view, rows, cols, ld, what, written_mask=None):
+        torch.cuda.synchronize()
+        off = (ld + 17) & ~1
+        b = buf.clone()
+        v = b[off: off + rows * ld].view(rows, ld)
+        inner = v[:, :cols]
+        assert torch.all(v[:, cols:] == SENT), f"{what}: padding columns overwritten"
+        if written_mask is not None:
+            assert torch.all(inner[~written_mask] == SENT), f"{what}: wrote outside the requested triangle"
+        inner.fill_(SENT)
+        assert torch.all(b == SENT), f"{what}: wrote outside the output matrix"
+
+    g = torch.Generator(device=dev).manual_seed(11)
+    for n, d in ((1, 3), (129, 26), (300, 300), (517, 77)):
+        X = torch.randn((n, d + (d & 1)), device=dev, dtype=torch.float64, generator=g)[:, :d]
+        for kid in (_lib.PL_KERNEL_DOT, _lib.PL_KERNEL_RBF, _lib.PL_KERNEL_IMQ):
+            for fill in (_lib.PL_FILL_FULL, _lib.PL_FILL_RM_UPPER, _lib.PL_FILL_RM_LOWER):
+                ld = (n + 7) & ~1
+                buf, out = guarded(n, n, ld)
+                _lib.check(lib.pl_gram_dev(kid, X.data_ptr(), n, X.stride(0), None, 0, 0, d, 2, 0, None, 1.0, 1.0, out.data_ptr(), ld, fill, 0, 1, 0, st), "pl_gram_dev")
+                # inside diagonal 128 x 128 tiles the unrequested half is written as 0 (zeros(n,n) storage); whole tiles of the
+                # unrequested triangle must stay untouched
+                ii, jj = torch.meshgrid(torch.arange(n, device=dev), torch.arange(n, device=dev), indexing="ij")
+                same_tile = (ii // 128) == (jj // 128)
+                mask = torch.ones((n, n), dtype=torch.bool, device=dev) if fill == _lib.PL_FILL_FULL else (
+                    ((jj >= ii) | same_tile) if fill == _lib.PL_FILL_RM_UPPER else ((jj <= ii) | same_tile))
+                check(buf, out, n, n, ld, f"gram sym kid={kid} fill={fill} n={n}", mask)
+        for n2 in (1, 33, 97, 200):  # narrow and wide rectangular tiles
+            X2 = torch.randn((n2, d + (d & 1)), device=dev, dtype=torch.float64, generator=g)[:, :d]
+            ld = (n2 + 5) & ~1
+            buf, out = guarded(n, n2, ld)
+            _lib.check(lib.pl_gram_dev(_lib.PL_KERNEL_RBF, X.data_ptr(), n, X.stride(0), X2.data_ptr(), n2, X2.stride(0), d, 0, 0, None, 1.3, 1.0,
+                                       out.data_ptr(), ld, 3, 0, 1, 0, st), "pl_gram_dev")
+            check(buf, out, n, n2, ld, f"gram cross n={n} n2={n2}")
+    for R, K, ne in ((1, 1, 1), (1000, 127, 10), (5000, 500, 100), (2049, 128, 0), (700, 1000, 700)):
+        A = torch.randn((R, K + (K & 1)), device=dev, dtype=torch.float64, generator=g)[:, :K]
+        b = torch.randn(R, device=dev, dtype=torch.float64, generator=g)
+        m = A.mean(0).contiguous()
+        for centred in (False, True):
+            bufS, S = guarded(K, K, K)
+            bufv, vec = guarded(1, 2 * K + 2, 2 * K + 2)
+            _lib.check(lib.pl_syrk_dev(A.data_ptr(), R, K, A.stride(0), None, ne, 30.0, 1.0, None if centred else b.data_ptr(),
+                                       m.data_ptr() if centred else None, S.data_ptr(), None if centred else vec.data_ptr(), st), "pl_syrk_dev")
+            check(bufS, S, K, K, K, f"syrk S R={R} K={K} centred={centred}")
+            check(bufv, vec, 1, 2 * K + 2, 2 * K + 2, f"syrk vec R={R} K={K}")
+        bufy, y = guarded(1, R, R)
+        beta = torch.randn(K, device=dev, dtype=torch.float64, generator=g)
+        _lib.check(lib.pl_predict_dev(A.data_ptr(), R, K, A.stride(0), beta.data_ptr(), 0.5, ne, y.data_ptr(), st), "pl_predict_dev")
+        check(bufy, y, 1, R, R, f"predict R={R} K={K}")
+        bufc, cs = guarded(1, K, K)
+        _lib.check(lib.pl_colsum_dev(A.data_ptr(), R, K, A.stride(0), cs.data_ptr(), st), "pl_colsum_dev")
+        check(bufc, cs, 1, K, K, f"colsum R={R} K={K}")
+    for N, nat, d in ((1, 1, 1), (37, 5, 26), (10, 1100, 7), (300, 3, 301)):
+        L = torch.randn((N * nat, d + (d & 1)), device=dev, dtype=torch.float64, generator=g)[:, :d]
+        off = (torch.arange(N + 1, device=dev, dtype=torch.int64) * nat).contiguous()
+        ld = (d + 4) & ~1
+        buf, Xo = guarded(N, d, ld)
+        _lib.check(lib.pl_global_feature_dev(L.data_ptr(), L.stride(0), off.data_ptr(), N, d, 1, Xo.data_ptr(), ld, N * nat, st), "pl_global_feature_dev")
+        check(buf, Xo, N, d, ld, f"global_feature N={N} d={d}")
