@@ -27,12 +27,15 @@ constexpr int GRAM_BM = 128;
 constexpr int GRAM_BN = 128;
 constexpr int GRAM_BK = 16;  // doubles per stage row: 128 bytes, the TMA 128B-swizzle span
 constexpr int GRAM_STAGES = 5;
+constexpr int GRAM_STAGES_TMAST = 3;            // operand ring of the TMA-store variant (shallow contractions: few k-steps per tile)
+constexpr int GRAM_STAGING_BYTES = 8 * 16384;   // one 32 x 64 staging tile per consumer warp
 constexpr int GRAM_CONSUMER_WARPS = 8;
 constexpr int GRAM_THREADS = (GRAM_CONSUMER_WARPS + 4) * 32;  // 2 DMMA warpgroups + 1 producer warpgroup (setmaxnreg needs whole warpgroups)
 constexpr int PRODUCER_REGS = 24;
 constexpr int CONSUMER_REGS = 240;  // per SMSP: 2 x 240 + 24 = 504 <= 512 registers per lane
 constexpr int GRAM_TILE_BYTES = GRAM_BM * GRAM_BK * 8;  // 16 KB per operand per stage
 constexpr int GRAM_SMEM_BYTES = GRAM_STAGES * 2 * GRAM_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GRAM_SMEM_BYTES_TMAST = GRAM_STAGES_TMAST * 2 * GRAM_TILE_BYTES + GRAM_STAGING_BYTES + 1024 + 256;
 
 enum { EPI_LINEAR = 0, EPI_DOT = 1, EPI_RBF = 2, EPI_IMQ = 3 };
 
@@ -55,6 +58,7 @@ struct GramParams {
   int64_t ntiles_total; // linear tile slots (symmetric: folded enumeration incl. a few invalid slots)
   int part, nparts;     // tile sharding across GPUs: slot l is ours iff l % nparts == part
   int tcol_begin;       // >= 0: "column range" enumeration (symmetric only): tiles (ti <= tj) of tile columns
+  int tma_out;          // TMAST variant: the output matrix is described by the third tensor map (dense, 16-byte aligned, even ldo)
   int tcol_end;         //       [tcol_begin, tcol_end), column by column — lets the host stream finished rows of the
                         //       Symmetric(:U) storage to the host while later columns are still being computed
 };
@@ -224,14 +228,98 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[MT][NT][2], co
   }
 }
 
+// Shared-memory staged, TMA-stored epilogue of one interior off-diagonal 32 x 64 warp tile (TMAST kernel variant).
+// The fragment stores of gram_epilogue touch 8 rows x 32 B (direct) or 4 rows x 64 B (mirror) per instruction; when the contraction is
+// shallow (d <= 128: config 1's d = 26) the kernel is bound by WRITING K and those stores neither reach the HBM rate nor overlap the
+// next tile's DMMAs (measured: time = compute + stores). Here the values go to a 16 KB per-warp staging buffer in the 128B-swizzled
+// box layout (conflict-free st.shared), one lane hands 16 x 32 boxes to the TMA unit, and the warp moves on to the next tile while the
+// full-line writes drain asynchronously. The mirrored copy is staged transposed through the same buffer.
+//   direct box b (columns 16b..16b+15 of the warp tile, 32 rows): stg + 4096 b + 128 row + ((8 (col & 15)) ^ (16 (row & 7)))
+//   mirror box (ih, jh) (16 i-columns x 32 j-rows):               stg + 4096 (2 ih + jh) + 128 (j & 31) + ((8 (i & 15)) ^ (16 (j & 7)))
+template <int EPI>
+__device__ __forceinline__ void gram_epilogue_staged(double (&acc)[4][8][2], const GramParams& p, const int64_t i0, const int64_t j0, const bool f1,
+                                                     const bool f2, const uint32_t stg, const CUtensorMap* tmO, const int gi0w, const int gj0w,
+                                                     const int lane, const int pg, const int t) {
+  // the previous tile's stores must have finished reading the staging buffer
+  if (lane == 0) tma_store_wait_read();
+  __syncwarp();
+  const double m2s = -2.0 * p.s;
+  // values in place (the common parameters only: DotProduct alpha = 2, RBF scale folded into the exponent)
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const double ri = (EPI != EPI_LINEAR) ? __ldg(p.ra + i0 + 8 * mt) : 0.0;
+    const double sa = (EPI == EPI_RBF) ? fma(p.s, ri, p.lnbeta) : (EPI == EPI_IMQ ? p.s * ri : ri);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const double r = (EPI != EPI_LINEAR) ? __ldg(p.rb + j0 + 8 * nt + 4 * c) : 0.0;
+        double x = acc[mt][nt][c];
+        if (EPI == EPI_DOT) {
+          x = x * sa * r;
+          x = x * x;
+        } else if (EPI == EPI_RBF) {
+          x = exp_clamped(fma(x, m2s, fma(p.s, r, sa)));
+        } else if (EPI == EPI_IMQ) {
+          x = rsqrt(p.beta + fma(x, m2s, fma(p.s, r, sa)));
+        }
+        acc[mt][nt][c] = x;
+      }
+  }
+  if (f1) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = 8 * nt + t + 4 * c;  // row = 8 mt + pg, row & 7 = pg
+          sts64(stg + (uint32_t)((col >> 4) * 4096 + (8 * mt + pg) * 128 + (((col & 15) << 3) ^ (pg << 4))), acc[mt][nt][c]);
+        }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) tma_store_2d(tmO, stg + b * 4096, gj0w + 16 * b, gi0w);
+      tma_store_commit();
+      if (f2) tma_store_wait_read();
+    }
+    __syncwarp();
+  }
+  if (f2) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int il = 8 * mt + pg, jl = 8 * nt + t + 4 * c;  // jl & 7 = t + 4 c
+          sts64(stg + (uint32_t)((2 * (mt >> 1) + (nt >> 2)) * 4096 + (jl & 31) * 128 + (((il & 15) << 3) ^ ((t + 4 * c) << 4))), acc[mt][nt][c]);
+        }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int ih = 0; ih < 2; ++ih)
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) tma_store_2d(tmO, stg + (2 * ih + jh) * 4096, gi0w + 16 * ih, gj0w + 32 * jh);
+      tma_store_commit();
+    }
+    __syncwarp();
+  }
+}
+
 // NARROW = 0: 128 x 128 output tile, warps 4 (m) x 2 (n), warp tile 32 x 64.
 // NARROW = 1: 128 x 32 output tile for rectangular results with few columns (projections W'(x - m) of transform!, pca_state.jl:42-62;
 //             KernelMatrix(F1, F2, k) against a handful of reference points): warps 8 (m) x 1, warp tile 16 x 32. A 128-wide tile
 //             would spend 128 / n2 times the DMMAs such a result needs; at n2 <= 32 the narrow tile is within 1.4 x of the HBM time of
 //             streaming the tall operand once.
-template <int EPI, int NARROW>
+// TMAST = 1 (NARROW = 0 only): 3-stage operand ring + 8 x 16 KB staging buffers; interior off-diagonal tiles of a dense result leave
+//             through gram_epilogue_staged (tmO describes the output matrix with a 16 x 32 box). Used for shallow contractions.
+template <int EPI, int NARROW, int TMAST>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
-gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GramParams p) {
+gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const GramParams p) {
+  constexpr int NSTAGE = TMAST ? GRAM_STAGES_TMAST : GRAM_STAGES;
   constexpr int BN = NARROW ? 32 : GRAM_BN;
   constexpr int MT = NARROW ? 2 : 4;   // 8-row DMMA m-tiles per warp
   constexpr int NT = NARROW ? 4 : 8;   // 8-column DMMA n-tiles per warp
@@ -239,15 +327,15 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + GRAM_STAGES * 2 * GRAM_TILE_BYTES;  // full[S] then empty[S], 8 bytes each
+  const uint32_t bar_base = smem_base + NSTAGE * 2 * GRAM_TILE_BYTES + (TMAST ? GRAM_STAGING_BYTES : 0);  // full[S] then empty[S], 8 bytes each
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (GRAM_STAGES + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < GRAM_STAGES; ++s) {
+    for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), GRAM_CONSUMER_WARPS);
     }
@@ -273,8 +361,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const bool one_tile = p.same_operand && (ti == tj);
         const uint32_t bytes = one_tile ? GRAM_TILE_BYTES : GRAM_TILE_BYTES + B_TILE_BYTES;
         for (int kt = 0; kt < KT; ++kt, ++it) {
-          const int s = it % GRAM_STAGES;
-          const uint32_t ph = (it / GRAM_STAGES) & 1u;
+          const int s = it % NSTAGE;
+          const uint32_t ph = (it / NSTAGE) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_arrive_expect_tx(full_bar(s), bytes);
           const uint32_t dstA = smem_base + s * 2 * GRAM_TILE_BYTES;
@@ -316,8 +404,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // expose the DMMA pipe. Two fragment buffers of 12 x 128 bit (96 registers) on top of the 128 accumulator registers.
     double2 a0[MT], b0[NT], a1[MT], b1[NT];
     {
-      const int s = it % GRAM_STAGES;
-      mbar_wait(full_bar(s), (it / GRAM_STAGES) & 1u);
+      const int s = it % NSTAGE;
+      mbar_wait(full_bar(s), (it / NSTAGE) & 1u);
       const uint32_t sA = smem_base + s * 2 * GRAM_TILE_BYTES;
       const uint32_t sB = one_tile ? sA : sA + GRAM_TILE_BYTES;
 #pragma unroll
@@ -326,7 +414,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int nt = 0; nt < NT; ++nt) b0[nt] = lds128(sB + (offB0 + nt * 1024));
     }
     for (int kt = 0; kt < KT; ++kt, ++it) {
-      const int s = it % GRAM_STAGES;
+      const int s = it % NSTAGE;
       const uint32_t sA = smem_base + s * 2 * GRAM_TILE_BYTES;
       const uint32_t sB = one_tile ? sA : sA + GRAM_TILE_BYTES;
       // second k-half of this stage -> buffer 1, then the stage can go back to the producer
@@ -343,8 +431,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a0[mt].y, b0[nt].y);
       if (kt + 1 < KT) {
-        const int s2 = (it + 1) % GRAM_STAGES;
-        mbar_wait(full_bar(s2), ((it + 1) / GRAM_STAGES) & 1u);
+        const int s2 = (it + 1) % NSTAGE;
+        mbar_wait(full_bar(s2), ((it + 1) / NSTAGE) & 1u);
         const uint32_t sA2 = smem_base + s2 * 2 * GRAM_TILE_BYTES;
         const uint32_t sB2 = one_tile ? sA2 : sA2 + GRAM_TILE_BYTES;
 #pragma unroll
@@ -396,7 +484,12 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ALPHA doubles as the "uncommon parameters" switch: DotProduct power != 2, or an RBF scale beta <= 0 that cannot be
     // folded into the exponent: one general instantiation
     const bool common = (EPI == EPI_DOT) ? (p.alpha == 2) : (EPI == EPI_RBF ? (p.bmul == 1.0) : true);
-    if (!common) {
+    if (TMAST && !NARROW && common && interior && !diag_tile && p.tma_out) {
+      if constexpr (TMAST && !NARROW) {
+        const uint32_t stg = smem_base + NSTAGE * 2 * GRAM_TILE_BYTES + warp * (GRAM_STAGING_BYTES / GRAM_CONSUMER_WARPS);
+        gram_epilogue_staged<EPI>(acc, p, i0, j0, f1, f2, stg, &tmO, ti * GRAM_BM + 32 * wm, tj * GRAM_BN + 64 * wn, lane, pg, t);
+      }
+    } else if (!common) {
       gram_epilogue<EPI, true, 0, MT, NT>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo);
     } else if (interior && !diag_tile) {
       gram_epilogue<EPI, false, 2, MT, NT>(acc, p, i0, j0, 0, f1, f2, prow, pcol, ldo);
@@ -404,6 +497,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       gram_epilogue<EPI, true, 2, MT, NT>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo);
     }
   }
+  if (TMAST && lane == 0) tma_store_wait_all();  // the staging buffers must outlive the bulk stores that read them
 }
 
 }  // namespace plb

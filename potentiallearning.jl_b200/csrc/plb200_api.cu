@@ -274,6 +274,7 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   p.symmetric = L.symmetric;
   p.same_operand = L.same_operand;
   p.fill = L.fill;
+  if (getenv("PLB200_GRAM_NOSTORE") && L.symmetric && !L.packed) p.fill = 0;  // developer experiment: epilogue without off-diagonal stores
   p.packed = L.packed;
   p.alpha = L.alpha;
   p.s = L.s;
@@ -290,24 +291,37 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   const int64_t mine = (p.ntiles_total - L.part + L.nparts - 1) / L.nparts;
   if (mine <= 0) return PL_OK;
   const int grid = (int)(mine < g.num_sms ? mine : g.num_sms);
-  if (L.epi != EPI_LINEAR || L.packed || L.symmetric) MAIN_KERNEL_BEGIN(st);
-  if (narrow) {
-    switch (L.epi) {
-      case EPI_LINEAR: gram_kernel<EPI_LINEAR, 1><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
-      case EPI_DOT: gram_kernel<EPI_DOT, 1><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
-      case EPI_RBF: gram_kernel<EPI_RBF, 1><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
-      case EPI_IMQ: gram_kernel<EPI_IMQ, 1><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
-      default: return set_err(PL_EINVAL, "unknown epilogue %d", L.epi);
-    }
-  } else {
-    switch (L.epi) {
-      case EPI_LINEAR: gram_kernel<EPI_LINEAR, 0><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
-      case EPI_DOT: gram_kernel<EPI_DOT, 0><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
-      case EPI_RBF: gram_kernel<EPI_RBF, 0><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
-      case EPI_IMQ: gram_kernel<EPI_IMQ, 0><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(tmA, tmB, p); break;
-      default: return set_err(PL_EINVAL, "unknown epilogue %d", L.epi);
-    }
+  // Shallow contractions of a dense result are bound by writing it: the TMA-store variant (smem-staged epilogue). Needs an output the
+  // TMA unit can address (16-byte aligned, even leading dimension). PLB200_GRAM_TMAST=0/1 overrides the depth rule (experiments).
+  // (not for RBF: its exp epilogue is tuned in groups of 8 interleaved chains in gram_epilogue and measured 3-6 % slower staged)
+  bool tmast = !narrow && !L.packed && L.tcol_begin < 0 && L.d <= 128 && L.epi != EPI_RBF && !(reinterpret_cast<uintptr_t>(L.out) & 15u) && !(L.ldo & 1);
+  if (const char* e = getenv("PLB200_GRAM_TMAST")) {
+    if (e[0] == '0') tmast = false;
+    else if (e[0] == '1') tmast = !narrow && !L.packed && !(reinterpret_cast<uintptr_t>(L.out) & 15u) && !(L.ldo & 1);
   }
+  CUtensorMap tmO = tmA;
+  p.tma_out = 0;
+  if (tmast) {
+    PL_TRY(make_tmap_2d(&tmO, L.out, L.nB, L.nA, L.ldo, 16, 32));
+    p.tma_out = 1;
+  }
+  if (L.epi != EPI_LINEAR || L.packed || L.symmetric) MAIN_KERNEL_BEGIN(st);
+#define GRAM_LAUNCH(NARROW_, TMAST_, SMEM_)                                                                                       \
+  switch (L.epi) {                                                                                                                \
+    case EPI_LINEAR: gram_kernel<EPI_LINEAR, NARROW_, TMAST_><<<grid, GRAM_THREADS, SMEM_, st>>>(tmA, tmB, tmO, p); break;        \
+    case EPI_DOT: gram_kernel<EPI_DOT, NARROW_, TMAST_><<<grid, GRAM_THREADS, SMEM_, st>>>(tmA, tmB, tmO, p); break;              \
+    case EPI_RBF: gram_kernel<EPI_RBF, NARROW_, TMAST_><<<grid, GRAM_THREADS, SMEM_, st>>>(tmA, tmB, tmO, p); break;              \
+    case EPI_IMQ: gram_kernel<EPI_IMQ, NARROW_, TMAST_><<<grid, GRAM_THREADS, SMEM_, st>>>(tmA, tmB, tmO, p); break;              \
+    default: return set_err(PL_EINVAL, "unknown epilogue %d", L.epi);                                                            \
+  }
+  if (narrow) {
+    GRAM_LAUNCH(1, 0, GRAM_SMEM_BYTES)
+  } else if (tmast) {
+    GRAM_LAUNCH(0, 1, GRAM_SMEM_BYTES_TMAST)
+  } else {
+    GRAM_LAUNCH(0, 0, GRAM_SMEM_BYTES)
+  }
+#undef GRAM_LAUNCH
   LAUNCH_CHECK();
   if (L.epi != EPI_LINEAR || L.packed || L.symmetric) MAIN_KERNEL_END(st);
   return PL_OK;
@@ -881,14 +895,15 @@ int pl_init(int device) {
   CUDA_TRY(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
   for (auto& ev : g.ev) CUDA_TRY(cudaEventCreate(&ev));
   for (auto& ev : g.chunk_ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_LINEAR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_DOT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_RBF, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_IMQ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_LINEAR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_DOT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_RBF, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_IMQ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
+#define GRAM_ATTR(EPI_)                                                                                                                  \
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));                 \
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));                 \
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES_TMAST));
+  GRAM_ATTR(EPI_LINEAR)
+  GRAM_ATTR(EPI_DOT)
+  GRAM_ATTR(EPI_RBF)
+  GRAM_ATTR(EPI_IMQ)
+#undef GRAM_ATTR
   CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
   g.ready = true;

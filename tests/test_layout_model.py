@@ -248,3 +248,62 @@ def test_syrk_work_units_cover_upper_triangle_once():
         assert np.array_equal(np.triu(cover), np.triu(np.ones((K, K), dtype=np.int32))), T
         assert np.all(vec_writers == 1)
     assert 4 * 3 // 2 + (4 + 1) // 2 == 8  # K = 500: 6 + 2 units (cost 8.25) instead of 9 packed units / 10 tiles
+
+
+def test_staged_epilogue_box_layout():
+    """gram_epilogue_staged (csrc/gram.cuh): the per-warp staging buffer holds 16-column x 32-row boxes in TMA's 128B-swizzled
+    layout (16-byte chunk index XOR (row & 7)). Replays the st.shared address math of the direct and the mirrored pass and checks
+    that (a) it is a bijection onto the 16 KB buffer, (b) un-swizzling box by box gives the warp tile resp. its transpose,
+    (c) every store instruction needs the minimum of 2 (direct) / at most 4 (mirror) shared-memory wavefronts."""
+    def perm(g):
+        return ((g & 1) << 2) | (g >> 1)
+
+    def wavefronts(addrs):  # 8-byte accesses, 32 banks x 4 bytes
+        waves = 0
+        remaining = list(addrs)
+        while remaining:
+            used, nxt = set(), []
+            for a in remaining:
+                banks = {(a // 4) % 32, (a // 4 + 1) % 32}
+                if banks & used:
+                    nxt.append(a)
+                else:
+                    used |= banks
+            waves += 1
+            remaining = nxt
+        return waves
+
+    tile = np.arange(32 * 64, dtype=np.float64).reshape(32, 64)  # value = 64 i + j
+    for mirror in (False, True):
+        buf = np.full(16384 // 8, np.nan)
+        worst = 0
+        for mt in range(4):
+            for nt in range(8):
+                for c in range(2):
+                    addrs = []
+                    for lane in range(32):
+                        g, t = lane >> 2, lane & 3
+                        pg = perm(g)
+                        il, jl = 8 * mt + pg, 8 * nt + t + 4 * c
+                        if not mirror:
+                            a = (jl >> 4) * 4096 + il * 128 + (((jl & 15) << 3) ^ (pg << 4))
+                        else:
+                            a = (2 * (mt >> 1) + (nt >> 2)) * 4096 + (jl & 31) * 128 + (((il & 15) << 3) ^ ((t + 4 * c) << 4))
+                        assert np.isnan(buf[a // 8])
+                        buf[a // 8] = tile[il, jl]
+                        addrs.append(a)
+                    worst = max(worst, wavefronts(addrs))
+        assert not np.isnan(buf).any()
+        assert worst <= (4 if mirror else 2)
+        # what the TMA unit reads: box k, row r, 16-byte chunk q lives at chunk q ^ (r & 7)
+        for box in range(4):
+            got = np.empty((32, 16))
+            for r in range(32):
+                for col in range(16):
+                    a = box * 4096 + r * 128 + ((col << 3) ^ ((r & 7) << 4))
+                    got[r, col] = buf[a // 8]
+            if not mirror:
+                assert np.array_equal(got, tile[:, 16 * box:16 * box + 16])
+            else:
+                ih, jh = box >> 1, box & 1
+                assert np.array_equal(got, tile[16 * ih:16 * ih + 16, 32 * jh:32 * jh + 32].T)
