@@ -291,10 +291,11 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   const int64_t mine = (p.ntiles_total - L.part + L.nparts - 1) / L.nparts;
   if (mine <= 0) return PL_OK;
   const int grid = (int)(mine < g.num_sms ? mine : g.num_sms);
-  // Shallow contractions of a dense result are bound by writing it: the TMA-store variant (smem-staged epilogue). Needs an output the
-  // TMA unit can address (16-byte aligned, even leading dimension). PLB200_GRAM_TMAST=0/1 overrides the depth rule (experiments).
+  // Dense results of the DotProduct / IMQ / LINEAR kernels leave through the TMA-store variant (smem-staged epilogue): 9-16 % faster when
+  // the contraction is shallow and the kernel is bound by writing K, still 1-2 % at d = 300. Needs an output the TMA unit can address
+  // (16-byte aligned, even leading dimension). PLB200_GRAM_TMAST=0/1 overrides the rule (experiments).
   // (not for RBF: its exp epilogue is tuned in groups of 8 interleaved chains in gram_epilogue and measured 3-6 % slower staged)
-  bool tmast = !narrow && !L.packed && L.tcol_begin < 0 && L.d <= 128 && L.epi != EPI_RBF && !(reinterpret_cast<uintptr_t>(L.out) & 15u) && !(L.ldo & 1);
+  bool tmast = !narrow && !L.packed && L.epi != EPI_RBF && !(reinterpret_cast<uintptr_t>(L.out) & 15u) && !(L.ldo & 1);
   if (const char* e = getenv("PLB200_GRAM_TMAST")) {
     if (e[0] == '0') tmast = false;
     else if (e[0] == '1') tmast = !narrow && !L.packed && !(reinterpret_cast<uintptr_t>(L.out) & 15u) && !(L.ldo & 1);
