@@ -127,6 +127,16 @@ int pl_normal_eq_blocks(const double* const* blocks, const int64_t* rows, int64_
                         double w_e, double w_f, const double* b, int add_intercept, double lambda, int64_t chunk_rows, double* AtWA,
                         double* AtWb);
 
+/* Out-of-core accumulation — ooc_learn! (linear-learn.jl:301-391) computes the descriptors of one configuration at a time and adds
+ * A'WA, A'Wb to running sums (:355-356); the data never exists as one matrix. pl_neq_begin zeroes accumulators resident on the
+ * device; every pl_neq_add contributes a batch of rows laid out [n_energy_rows energy rows ; force rows] with the weights of
+ * pl_normal_eq (per-row w for the per-configuration energy weights ws1*{1, 1/natoms, 1/natoms^2}, :341-352), synchronously (the
+ * host buffers may be reused on return); pl_neq_finish assembles (AtWA, AtWb) like pl_normal_eq and may be called any number of
+ * times. Batches are summed in call order: deterministic for a fixed batching. */
+int pl_neq_begin(int64_t Kf);
+int pl_neq_add(const double* A, int64_t R, int64_t lda, const double* w, int64_t n_energy_rows, double w_e, double w_f, const double* b);
+int pl_neq_finish(int add_intercept, double lambda, double* AtWA, double* AtWb);
+
 /* ---- GlobalSum / GlobalMean features on the device ("next" row f2 of SURVEY.md 8f) ------------------------ */
 /* locals: the local descriptors of all N configurations stacked, row-major (offsets[N]) x d, leading dimension ldl; configuration i owns
  * rows [offsets[i], offsets[i+1]) (offsets[0] == 0, strictly increasing). X[i,:] = sum of its rows (mean == 0: compute_feature(B,

@@ -95,6 +95,8 @@ enum WsSlot {
   WS_EIG_SEL,
   WS_TRACE,
   WS_SYRK_AUX,
+  WS_ACC_S,
+  WS_ACC_V,
   WS_NSLOTS
 };
 
@@ -866,6 +868,13 @@ int inclusion_prob_dev_impl(const double* dV, int64_t nvec, int64_t n, int64_t l
   return PL_OK;
 }
 
+
+// resident accumulator of the out-of-core normal equations (pl_neq_begin / pl_neq_add / pl_neq_finish)
+struct NeqState {
+  int64_t Kf = 0, rows = 0, batches = 0;
+  bool open = false;
+} neq_state;
+
 }  // namespace
 
 extern "C" {
@@ -936,6 +945,7 @@ void pl_finalize(void) {
     cs.params = nullptr;
   }
   ell_state.valid = false;
+  neq_state.open = false;
   if (g.stream) cudaStreamDestroy(g.stream);
   if (g.copy_stream) cudaStreamDestroy(g.copy_stream);
   g.stream = nullptr;
@@ -1487,6 +1497,78 @@ int pl_ell_eigvecs(const int64_t* idx, int64_t m, int64_t n, double* V, int64_t 
   CUDA_TRY(cudaMemcpy2DAsync(V, (size_t)ldv * 8, dsel, (size_t)n * 8, (size_t)n * 8, (size_t)m, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
   return finish_timing();
+}
+
+
+// ---- out-of-core accumulation: ooc_learn! (linear-learn.jl:301-391) keeps AtWA / AtWb and adds one configuration at a time --------------
+int pl_neq_begin(int64_t Kf) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (Kf <= 0) return set_err(PL_EINVAL, "bad descriptor length %lld", (long long)Kf);
+  CUDA_TRY(cudaSetDevice(g.device));
+  void *dS, *dV;
+  PL_TRY(ws_get(WS_ACC_S, (size_t)Kf * Kf * 8, &dS));
+  PL_TRY(ws_get(WS_ACC_V, (size_t)(2 * Kf + 2) * 8, &dV));
+  CUDA_TRY(cudaMemsetAsync(dS, 0, (size_t)Kf * Kf * 8, g.stream));
+  CUDA_TRY(cudaMemsetAsync(dV, 0, (size_t)(2 * Kf + 2) * 8, g.stream));
+  neq_state.Kf = Kf;
+  neq_state.rows = 0;
+  neq_state.batches = 0;
+  neq_state.open = true;
+  return PL_OK;
+}
+
+int pl_neq_add(const double* A, int64_t R, int64_t lda, const double* w, int64_t n_energy_rows, double w_e, double w_f, const double* b) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!neq_state.open) return set_err(PL_EINVAL, "pl_neq_add without pl_neq_begin");
+  const int64_t Kf = neq_state.Kf;
+  if (!A || R < 0 || lda < Kf) return set_err(PL_EINVAL, "bad arguments");
+  if (R == 0) return PL_OK;
+  CUDA_TRY(cudaSetDevice(g.device));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  double *dA, *dw = nullptr, *db = nullptr;
+  int64_t ld;
+  PL_TRY(h2d_matrix(A, R, Kf, lda, WS_H_IN1, &dA, &ld));
+  if (w) PL_TRY(h2d_vector(w, R, WS_H_IN2, &dw));
+  if (b) PL_TRY(h2d_vector(b, R, WS_H_IN3, &db));
+  void *dS, *dvec;
+  PL_TRY(ws_get(WS_H_S, (size_t)Kf * Kf * 8, &dS));
+  PL_TRY(ws_get(WS_H_VEC, (size_t)(2 * Kf + 2) * 8, &dvec));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  const int64_t ne = n_energy_rows < 0 ? 0 : (n_energy_rows > R ? R : n_energy_rows);
+  PL_TRY(syrk_dev_impl(dA, R, Kf, ld, dw, ne, w_e, w_f, db, nullptr, (double*)dS, (double*)dvec, g.stream));
+  accumulate_kernel<<<g.num_sms * 4, 256, 0, g.stream>>>((const double*)dS, Kf * Kf, (double*)g.ws[WS_ACC_S]);
+  LAUNCH_CHECK();
+  accumulate_kernel<<<8, 256, 0, g.stream>>>((const double*)dvec, 2 * Kf + 2, (double*)g.ws[WS_ACC_V]);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  neq_state.rows += R;
+  neq_state.batches += 1;
+  return finish_timing();  // synchronises: the host buffers of this batch may be reused by the caller
+}
+
+int pl_neq_finish(int add_intercept, double lambda, double* AtWA, double* AtWb) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!neq_state.open) return set_err(PL_EINVAL, "pl_neq_finish without pl_neq_begin");
+  if (!AtWA) return set_err(PL_EINVAL, "null pointer");
+  const int64_t Kf = neq_state.Kf;
+  const int ic = add_intercept ? 1 : 0;
+  const int64_t n = Kf + ic;
+  CUDA_TRY(cudaSetDevice(g.device));
+  void *dM, *dv = nullptr;
+  PL_TRY(ws_get(WS_H_OUT1, (size_t)n * n * 8, &dM));
+  if (AtWb) PL_TRY(ws_get(WS_H_OUT2, (size_t)n * 8, &dv));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  PL_TRY(finish_dev_impl((const double*)g.ws[WS_ACC_S], (const double*)g.ws[WS_ACC_V], Kf, ic, lambda, (double*)dM, (double*)dv, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaMemcpyAsync(AtWA, dM, (size_t)n * n * 8, cudaMemcpyDeviceToHost, g.stream));
+  if (AtWb) CUDA_TRY(cudaMemcpyAsync(AtWb, dv, (size_t)n * 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();  // the accumulators stay open: more batches may follow (ooc_learn! can be resumed with AtWA / AtWb)
 }
 
 }  // extern "C"

@@ -40,6 +40,9 @@ PROTOTYPES = {
     "pl_gram_cross": (_int, [_int, _dp, _i64, _i64, _dp, _i64, _i64, _i64, _int, _int, _dp, _dbl, _dbl, _dp, _i64]),
     "pl_normal_eq": (_int, [_dp, _i64, _i64, _i64, _dp, _i64, _dbl, _dbl, _dp, _int, _dbl, _dp, _dp]),
     "pl_normal_eq_blocks": (_int, [ctypes.POINTER(_dp), ctypes.POINTER(_i64), _i64, _i64, _dp, _i64, _dbl, _dbl, _dp, _int, _dbl, _i64, _dp, _dp]),
+    "pl_neq_begin": (_int, [_i64]),
+    "pl_neq_add": (_int, [_dp, _i64, _i64, _dp, _i64, _dbl, _dbl, _dp]),
+    "pl_neq_finish": (_int, [_int, _dbl, _dp, _dp]),
     "pl_global_feature": (_int, [_dp, _i64, ctypes.POINTER(_i64), _i64, _i64, _int, _dp, _i64]),
     "pl_global_feature_dev": (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _i64, _i64, _vp]),
     "pl_cov": (_int, [_dp, _i64, _i64, _i64, _dp, _int, _int, _dp]),

@@ -152,6 +152,44 @@ def normal_equations_blocks(blocks, b=None, w=None, n_energy_rows=0, w_e=1.0, w_
     return M, v
 
 
+class NormalEquationAccumulator:
+    """Out-of-core accumulation of (A'WA, A'Wb) on the GPU (pl_neq_begin / pl_neq_add / pl_neq_finish): what ooc_learn! does with
+    `AtWA .+= A'*W*A; AtWb .+= A'*W*b` per configuration (linear-learn.jl:355-356), without the rows ever existing as one matrix.
+    Rows are buffered on the host up to `batch_rows` and shipped as one batch (a per-configuration launch would be latency-bound)."""
+
+    def __init__(self, K: int, batch_rows: int = 1 << 16):
+        self.K = int(K)
+        self.batch_rows = int(batch_rows)
+        self._rows, self._rhs, self._w, self._n = [], [], [], 0
+        _lib.check(_lib.lib().pl_neq_begin(self.K), "pl_neq_begin")
+
+    def add(self, A, b, w):
+        """rows A (m x K), right-hand sides b (m), per-row weights w (m)"""
+        A = np.asarray(A, dtype=np.float64).reshape(-1, self.K)
+        self._rows.append(A)
+        self._rhs.append(np.asarray(b, dtype=np.float64).reshape(-1))
+        self._w.append(np.asarray(w, dtype=np.float64).reshape(-1))
+        self._n += A.shape[0]
+        if self._n >= self.batch_rows:
+            self.flush()
+
+    def flush(self):
+        if self._n == 0:
+            return
+        A = np.ascontiguousarray(np.concatenate(self._rows, axis=0))
+        b = np.ascontiguousarray(np.concatenate(self._rhs))
+        w = np.ascontiguousarray(np.concatenate(self._w))
+        _lib.check(_lib.lib().pl_neq_add(_lib.dptr(A), A.shape[0], self.K, _lib.dptr(w), 0, 1.0, 1.0, _lib.dptr(b)), "pl_neq_add")
+        self._rows, self._rhs, self._w, self._n = [], [], [], 0
+
+    def result(self, intercept: bool = False, lam: float = 0.0):
+        self.flush()
+        n = self.K + (1 if intercept else 0)
+        M, v = np.empty((n, n)), np.empty(n)
+        _lib.check(_lib.lib().pl_neq_finish(1 if intercept else 0, float(lam), _lib.dptr(M), _lib.dptr(v)), "pl_neq_finish")
+        return M, v
+
+
 def _solve(M, v):
     """βs = M \\ v, falling back to pinv(M)*v on a singular system (linear-learn.jl:199-205, 252-258)."""
     try:
@@ -238,15 +276,16 @@ def _pinv_atol(M, atol):
 
 
 def ooc_learn_(lb_beta: np.ndarray, configs, ws=(30.0, 1.0), symmetrize=True, λ=0.01, reg_style="default", AtWA=None, AtWb=None,
-               eweight_normalized="squared"):
+               eweight_normalized="squared", batch_rows: int = 1 << 16):
     """ooc_learn!(lb, ds_train; ...) (linear-learn.jl:301-391) with the per-configuration accumulation
-    AtWA .+= A'*W*A; AtWb .+= A'*W*b (:355-356) done in ONE GPU pass over the stacked rows with per-row weights
-    (the energy weight ws[1]*{1, 1/natoms, 1/natoms^2} differs per configuration, :341-352).
+    AtWA .+= A'*W*A; AtWb .+= A'*W*b (:355-356) accumulated OUT OF CORE on the GPU (NormalEquationAccumulator: batches of
+    `batch_rows` rows, per-row weights — the energy weight ws[1]*{1, 1/natoms, 1/natoms^2} differs per configuration, :341-352);
+    `configs` may be a generator: nothing but the running sums is kept.
     configs: iterable of (global_descr K, force_descrs 3natoms x K, ref_energy, ref_forces 3natoms); descriptor evaluation
     itself (InteratomicPotentials) is upstream of the hot path. Returns (AtWA, AtWb) like the reference."""
     if AtWA is None or AtWb is None:
-        rows, rhs, wts = [], [], []
-        for gd, fdm, e, f in configs:
+        acc = None
+        for gd, fdm, e, f in configs:  # one configuration at a time, as the reference: nothing is kept but the running sums
             fdm = np.asarray(fdm, dtype=np.float64)
             natoms = fdm.shape[0] // 3
             if eweight_normalized is None:
@@ -257,14 +296,14 @@ def ooc_learn_(lb_beta: np.ndarray, configs, ws=(30.0, 1.0), symmetrize=True, λ
                 we_norm = 1 / natoms ** 2
             else:
                 raise ValueError("eweight_normalized can only be nothing, :standard, or :squared")
-            rows.append(np.asarray(gd, dtype=np.float64)[None, :])
-            rows.append(fdm)
-            rhs.append(np.atleast_1d(np.float64(e)))
-            rhs.append(np.asarray(f, dtype=np.float64))
-            wts.append(np.array([we_norm * ws[0]]))
-            wts.append(ws[1] * np.ones(fdm.shape[0]))
-        A = np.ascontiguousarray(np.concatenate(rows, axis=0))
-        AtWA, AtWb = normal_equations(A, np.concatenate(rhs), np.concatenate(wts))
+            gd = np.asarray(gd, dtype=np.float64)
+            if acc is None:
+                acc = NormalEquationAccumulator(gd.shape[0], batch_rows)
+            acc.add(np.concatenate([gd[None, :], fdm], axis=0), np.concatenate([[np.float64(e)], np.asarray(f, dtype=np.float64)]),
+                    np.concatenate([[we_norm * ws[0]], ws[1] * np.ones(fdm.shape[0])]))
+        if acc is None:
+            raise ValueError("no configurations")
+        AtWA, AtWb = acc.result()
     else:
         AtWA, AtWb = np.array(AtWA, copy=True), np.array(AtWb, copy=True)
     if symmetrize:

@@ -1047,3 +1047,39 @@ def test_no_out_of_bounds_writes(pl):
         buf, Xo = guarded(N, d, ld)
         _lib.check(lib.pl_global_feature_dev(L.data_ptr(), L.stride(0), off.data_ptr(), N, d, 1, Xo.data_ptr(), ld, N * nat, st), "pl_global_feature_dev")
         check(buf, Xo, N, d, ld, f"global_feature N={N} d={d}")
+
+
+def test_out_of_core_accumulator(pl, orc):
+    """pl_neq_begin / pl_neq_add / pl_neq_finish: ooc_learn!'s running sums (linear-learn.jl:355-356). Any batching gives the one-shot
+    result to rounding, a fixed batching is bitwise reproducible, finish is non-destructive, and a generator of configurations works."""
+    rng = np.random.default_rng(17)
+    K = 40
+    natoms = rng.integers(2, 30, size=120)
+
+    def gen():
+        r = np.random.default_rng(18)
+        for n in natoms:
+            yield (r.standard_normal(K) * n, r.standard_normal((3 * n, K)), r.standard_normal() * n, r.standard_normal(3 * n))
+
+    configs = list(gen())
+    Ao, bo = orc.ooc_accumulate(configs, ws=(30.0, 1.0), eweight_normalized="squared")
+    results = []
+    for batch_rows in (1, 100, 1 << 16):
+        beta = np.zeros(K)
+        M, v = pl.ooc_learn_(beta, gen(), ws=(30.0, 1.0), λ=None, eweight_normalized="squared", batch_rows=batch_rows)
+        assert normerr(M, Ao) < RTOL and normerr(v, bo) < RTOL
+        results.append((M, v))
+    M2, v2 = pl.ooc_learn_(np.zeros(K), gen(), ws=(30.0, 1.0), λ=None, eweight_normalized="squared", batch_rows=100)
+    assert np.array_equal(M2, results[1][0]) and np.array_equal(v2, results[1][1])
+    acc = pl.NormalEquationAccumulator(K, batch_rows=64)
+    for gd, fdm, e, f in configs[:50]:
+        acc.add(np.concatenate([gd[None, :], fdm]), np.concatenate([[e], f]), np.ones(1 + fdm.shape[0]))
+    Ma, va = acc.result()
+    Mb, vb = acc.result(intercept=False, lam=0.5)  # finish twice: the accumulators stay open
+    assert np.array_equal(Mb - 0.5 * np.eye(K), Ma) or normerr(Mb - 0.5 * np.eye(K), Ma) < 1e-15
+    for gd, fdm, e, f in configs[50:]:
+        acc.add(np.concatenate([gd[None, :], fdm]), np.concatenate([[e], f]), np.ones(1 + fdm.shape[0]))
+    Mc, vc = acc.result()
+    A = np.concatenate([np.concatenate([gd[None, :], fdm]) for gd, fdm, e, f in configs])
+    b = np.concatenate([np.concatenate([[e], f]) for gd, fdm, e, f in configs])
+    assert normerr(Mc, A.T @ A) < RTOL and normerr(vc, A.T @ b) < RTOL
