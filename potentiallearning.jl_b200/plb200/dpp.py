@@ -1,12 +1,16 @@
-"""Host mirror of reference src/SubsetSelection/dpp.jl: kDPP over an L-ensemble whose kernel matrix is built on the GPU.
+"""Host mirror of reference src/SubsetSelection/dpp.jl: kDPP over an L-ensemble whose kernel matrix AND eigendecomposition are
+built on the GPU.
 
-The ONLY hot-path piece is `K = KernelMatrix(...)` inside the constructors (dpp.jl:25, :40). Everything after it is
-Determinantal.jl in the reference ([external], version unpinned — Project.toml has no compat bound, Manifest is
-git-ignored): EllEnsemble (dense symmetric eigendecomposition), rescale!, sample, greedy_subset, inclusion_prob.
-In a Julia deployment those calls stay in Determinantal.jl and see the GPU-built Symmetric K.
-So that a Python user of this mirror still gets a working selector, the published algorithms are restated here
-(Kulesza & Taskar, "Determinantal point processes for machine learning", 2012: Alg. 1 spectral sampling, Alg. 7/8
-k-DPP eigenvector selection via elementary symmetric polynomials; greedy MAP by Schur-complement updates).
+Hot path: `K = KernelMatrix(...)` inside the constructors (dpp.jl:25, :40). Widened: `EllEnsemble(K)`'s dense
+symmetric eigendecomposition (Determinantal.jl [external], dpp.jl:26, :41) runs on the device right behind the Gram kernel
+(pl_ell_ensemble; cuSOLVER under the C ABI); U stays device-resident, inclusion probabilities are computed there and a k-DPP draw
+downloads only the eigenvectors it selected.
+
+What stays on the host is Determinantal.jl's sampling logic, restated so that a Python user of this mirror gets a working
+selector (Kulesza & Taskar, "Determinantal point processes for machine learning", 2012: Alg. 1 spectral sampling, Alg. 7/8
+k-DPP eigenvector selection via elementary symmetric polynomials; greedy MAP by Schur-complement updates). In a Julia deployment
+those calls stay in Determinantal.jl (version unpinned — Project.toml has no compat bound, Manifest is git-ignored) and see the
+GPU-built Symmetric K or the (λ, U) pair.
 PARITY UNPINNED for these host routines: they use numpy's RNG, not Julia's, so indices are not comparable draw-for-draw.
 """
 from __future__ import annotations
@@ -15,7 +19,7 @@ import numpy as np
 
 from .data import DataSet, LocalDescriptors
 from . import _lib
-from .kernels import Feature, Kernel, KernelMatrix, Symmetric, compute_features
+from .kernels import Feature, Kernel, Symmetric, compute_features
 
 
 class SubsetSelector:

@@ -88,7 +88,6 @@ if "neq" in which:
     del A
 
 if "eig" in which:
-    from plb200.dpp import eigh
 
     for n in (1000, 4000) + ((20000,) if os.environ.get("PLB_EIG_BIG") else ()):
         rng = np.random.default_rng(n)
