@@ -146,6 +146,11 @@ int pl_global_feature(const double* locals, int64_t ldl, const int64_t* offsets,
 int pl_global_feature_dev(const double* dL, int64_t ldl, const int64_t* doffsets, int64_t N, int64_t d, int mean, double* dX, int64_t ldx,
                           int64_t total_rows, void* stream);
 
+/* CorrelationMatrix features (src/Kernels/features.jl:48-50, widened row f4): C[i] = mean(b*b' for b in the local descriptors of
+ * configuration i), N matrices d x d (row-major, full symmetric), same stacked layout / offsets as pl_global_feature. Products and
+ * sums are formed in the reference's order without fma contraction: bit-identical features. */
+int pl_correlation_feature(const double* locals, int64_t ldl, const int64_t* offsets, int64_t N, int64_t d, double* C);
+
 /* ---- covariance / second moment: replaces compute_eigen's Q (dimension_reduction.jl:11-12) and the
  *      mean/centre of fit!(ds, ::PCAState) (pca_state.jl:34-37) ------------------------------------------ */
 /* X: row-major n x Kf.  center == 0: C = (1/n) sum_r x_r x_r'   (PCA / ActiveSubspace, pca.jl:28, as.jl:25).

@@ -1571,4 +1571,30 @@ int pl_neq_finish(int add_intercept, double lambda, double* AtWA, double* AtWb) 
   return finish_timing();  // the accumulators stay open: more batches may follow (ooc_learn! can be resumed with AtWA / AtWb)
 }
 
+
+int pl_correlation_feature(const double* locals, int64_t ldl, const int64_t* offsets, int64_t N, int64_t d, double* C) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!locals || !offsets || !C || N < 0 || d <= 0 || ldl < d) return set_err(PL_EINVAL, "bad arguments");
+  if (N == 0) return PL_OK;
+  PL_TRY(check_offsets(offsets, N));
+  const int64_t total = offsets[N];
+  CUDA_TRY(cudaSetDevice(g.device));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  double* dL;
+  int64_t ld;
+  PL_TRY(h2d_matrix(locals, total, d, ldl, WS_FEAT_L, &dL, &ld));
+  void *doff, *dC;
+  PL_TRY(ws_get(WS_FEAT_OFF, (size_t)(N + 1) * 8, &doff));
+  CUDA_TRY(cudaMemcpyAsync(doff, offsets, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, g.stream));
+  PL_TRY(ws_get(WS_FEAT_X, (size_t)N * d * d * 8, &dC));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  correlation_feature_kernel<<<(unsigned)N, 256, 0, g.stream>>>(dL, ld, (const int64_t*)doff, d, (double*)dC);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaMemcpyAsync(C, dC, (size_t)N * d * d * 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();
+}
+
 }  // extern "C"

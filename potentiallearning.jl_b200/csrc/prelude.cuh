@@ -421,4 +421,26 @@ __global__ void wcolsum_partial_kernel(const double* __restrict__ A, int64_t R, 
   if (pair) pc[(int64_t)blockIdx.y * Kf + c0 + 1] = s1;
 }
 
+// CorrelationMatrix features (src/Kernels/features.jl:48-50): C_i = mean(b b' for b in B_i), the d x d second moment of configuration
+// i's local descriptors. One CTA per configuration, one thread per (a, b) entry (strided). The reference forms each outer product
+// (rounded products) and adds the matrices in atom order — a generator, so Statistics.mean accumulates sequentially — then divides by
+// natoms: separate multiply and add here (no fma contraction) in the same order, so the features are bit-identical.
+// out: N x d x d row-major (full symmetric matrices).
+__global__ void correlation_feature_kernel(const double* __restrict__ L, int64_t ldl, const int64_t* __restrict__ off, int64_t d,
+                                           double* __restrict__ out) {
+  const int64_t cfg = blockIdx.x;
+  const int64_t lo = off[cfg], hi = off[cfg + 1];
+  const double n = (double)(hi - lo);
+  double* C = out + cfg * d * d;
+  for (int64_t e = threadIdx.x; e < d * d; e += blockDim.x) {
+    const int64_t a = e / d, b = e % d;
+    double s = 0.0;
+    if (hi > lo) {
+      s = __dmul_rn(__ldg(L + lo * ldl + a), __ldg(L + lo * ldl + b));
+      for (int64_t r = lo + 1; r < hi; ++r) s = __dadd_rn(s, __dmul_rn(__ldg(L + r * ldl + a), __ldg(L + r * ldl + b)));
+    }
+    C[e] = s / n;
+  }
+}
+
 }  // namespace plb

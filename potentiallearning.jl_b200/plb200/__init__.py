@@ -13,7 +13,7 @@ from .dpp import (EllEnsemble, SubsetSelector, get_dpp_mode, get_inclusion_prob,
                   rescale_, sample)
 from .kernels import (RBF, CorrelationMatrix, Diagonal, Distance, DotProduct, Euclidean, Feature, GlobalMean, GlobalSum, InverseMultiquadric, Kernel,
                       KernelMatrix, Symmetric,
-                      compute_distance, compute_feature, compute_features, compute_kernel, get_parameters, global_features, global_features_dev,
+                      compute_distance, compute_feature, compute_features, compute_kernel, correlation_features, get_parameters, global_features, global_features_dev,
                       gram_tile_coords, kernel_matrix_dev, stack_locals)
 from .learning import (CovariateLinearProblem, LinearBasisPotential, NormalEquationAccumulator, LinearProblem, UnivariateLinearProblem, assemble_matrices,
                        get_all_energies, get_all_forces, learn_, learn_potential_, normal_equations, normal_equations_blocks, ols_sums, ooc_learn_, pack_rhs,

@@ -57,7 +57,27 @@ def compute_features(ds: DataSet, f: Feature, dt=LocalDescriptors):
     descriptors, Julia's summation order); returns the N x d feature matrix (row i = feature of configuration i)."""
     if isinstance(f, (GlobalMean, GlobalSum)):
         return global_features([get_values(get_local_descriptors(c)) for c in ds], mean=isinstance(f, GlobalMean))
+    if isinstance(f, CorrelationMatrix) and dt is LocalDescriptors:
+        return correlation_features([get_values(get_local_descriptors(c)) for c in ds])
     return [compute_feature(c, f, dt=dt) for c in ds]
+
+
+def correlation_features(local_blocks):
+    """CorrelationMatrix features of N configurations on the GPU (pl_correlation_feature): a list of Symmetric d x d matrices,
+    bit-identical to mean(Bi*Bi' for Bi in B) evaluated in the reference's order (features.jl:48-50)."""
+    import ctypes
+
+    L, offsets = stack_locals(local_blocks)
+    N = len(offsets) - 1
+    if N == 0:
+        return []
+    if np.any(np.diff(offsets) <= 0):
+        raise ValueError("ArgumentError: reducing over an empty collection is not allowed (configuration without local descriptors)")
+    d = L.shape[1]
+    C = np.empty((N, d, d))
+    _lib.check(_lib.lib().pl_correlation_feature(_lib.dptr(L), d, offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), N, d, _lib.dptr(C)),
+               "pl_correlation_feature")
+    return [Symmetric(C[i]) for i in range(N)]
 
 
 def stack_locals(local_blocks):

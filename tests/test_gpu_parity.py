@@ -1083,3 +1083,14 @@ def test_out_of_core_accumulator(pl, orc):
     A = np.concatenate([np.concatenate([gd[None, :], fdm]) for gd, fdm, e, f in configs])
     b = np.concatenate([np.concatenate([[e], f]) for gd, fdm, e, f in configs])
     assert normerr(Mc, A.T @ A) < RTOL and normerr(vc, A.T @ b) < RTOL
+
+
+def test_correlation_features_bit_exact_ragged(pl, orc):
+    """pl_correlation_feature over ragged configurations (1 .. 300 atoms): bit-identical to the reference-order evaluation."""
+    rng = np.random.default_rng(23)
+    for d in (1, 5, 26):
+        blocks = [rng.standard_normal((n, d)) * 2.0 + rng.standard_normal(d) for n in (1, 2, 3, 32, 300)]
+        C = pl.correlation_features(blocks)
+        for c, b in zip(C, blocks):
+            ref = orc.correlation_matrix(list(b))
+            assert np.array_equal(np.asarray(c), ref) and np.array_equal(c.data, c.data.T)
