@@ -151,6 +151,13 @@ int pl_global_feature_dev(const double* dL, int64_t ldl, const int64_t* doffsets
  * sums are formed in the reference's order without fma contraction: bit-identical features. */
 int pl_correlation_feature(const double* locals, int64_t ldl, const int64_t* offsets, int64_t N, int64_t d, double* C);
 
+/* KernelSteinDiscrepancy with an RBF(Euclidean) kernel: compute_divergence(x, ::KernelSteinDiscrepancy) (src/Kernels/divergences.jl:27-49,
+ * widened row f4). X: the n samples (row-major n x d), S: their scores div.score.(x) evaluated by the caller (n x d). The O(n^2 d)
+ * pair loop becomes four Gram matrices on the DMMA engine plus one fused pair reduction; the reference's formulas are kept as written
+ * (including the scalar broadcast inside compute_gradxy_kernel, kernels.jl:121-125). Needs 4 n^2 doubles of device workspace. */
+int pl_ksd_rbf(const double* X, const double* S, int64_t n, int64_t d, int64_t ldx, int64_t lds, int cinv_kind, const double* cinv, double ell,
+               double beta, double* ksd);
+
 /* ---- covariance / second moment: replaces compute_eigen's Q (dimension_reduction.jl:11-12) and the
  *      mean/centre of fit!(ds, ::PCAState) (pca_state.jl:34-37) ------------------------------------------ */
 /* X: row-major n x Kf.  center == 0: C = (1/n) sum_r x_r x_r'   (PCA / ActiveSubspace, pca.jl:28, as.jl:25).

@@ -497,3 +497,40 @@ def centered_cov(X, mean=None):
         mean = X.sum(axis=0) / n
     Xc = X - mean
     return mean, (Xc.T @ Xc) / n
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# KernelSteinDiscrepancy (src/Kernels/divergences.jl:27-49) with the RBF gradient kernels (kernels.jl:81-126, distances.jl:76-110)
+# ----------------------------------------------------------------------------------------------------------------
+def _cinv_matrix(e: Euclidean) -> np.ndarray:
+    if e.cinv is None:
+        return np.eye(e.dim)
+    return np.diag(e.cinv) if np.ndim(e.cinv) == 1 else np.asarray(e.cinv, dtype=np.float64)
+
+
+def compute_divergence_ksd(x, score, k: RBF) -> float:
+    """compute_divergence(x, ::KernelSteinDiscrepancy) restated literally: the i <= j pair loop, every gradient function as written
+    (compute_gradx/grady/gradxy_distance: 2*Cinv*(A-B), -2*Cinv*(A-B), -2*Cinv; compute_gradx/grady_kernel: -0.5*k*grad_d/l^2;
+    compute_gradxy_kernel: k .* (-0.5*gradxy_d/l^2 .+ 0.25*gradx_d'*grady_d/l^4) — the `.+` broadcasts the scalar over the matrix)."""
+    xs = [np.asarray(v, dtype=np.float64) for v in x]
+    N = len(xs)
+    sq = [np.asarray(score(v), dtype=np.float64) for v in xs]
+    C = _cinv_matrix(k.d)
+    ksd = 0.0
+    for i in range(N):
+        for j in range(i, N):
+            m = 1 if i == j else 2
+            kk = compute_kernel(xs[i], xs[j], k)
+            gxd = 2 * C @ (xs[i] - xs[j])
+            gyd = -2 * C @ (xs[i] - xs[j])
+            gxyd = -2 * C
+            grady_k = -0.5 * kk * gyd / k.ell ** 2
+            gradx_k = -0.5 * kk * gxd / k.ell ** 2
+            gradxy_k = kk * (-0.5 * gxyd / k.ell ** 2 + 0.25 * (gxd @ gyd) / k.ell ** 4)
+            sks = sq[i] @ (kk * sq[j])
+            sk = sq[i] @ grady_k
+            ks = gradx_k @ sq[j]
+            trk = np.trace(gradxy_k)
+            ksd += m * (sks + sk + ks + trk) / (N * (N - 1.0))
+    return float(ksd)
+

@@ -97,6 +97,12 @@ enum WsSlot {
   WS_SYRK_AUX,
   WS_ACC_S,
   WS_ACC_V,
+  WS_KSD_G1,
+  WS_KSD_G2,
+  WS_KSD_G3,
+  WS_KSD_H,
+  WS_KSD_S,
+  WS_KSD_PART,
   WS_NSLOTS
 };
 
@@ -1594,6 +1600,106 @@ int pl_correlation_feature(const double* locals, int64_t ldl, const int64_t* off
   CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
   CUDA_TRY(cudaMemcpyAsync(C, dC, (size_t)N * d * d * 8, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();
+}
+
+
+int pl_ksd_rbf(const double* X, const double* S, int64_t n, int64_t d, int64_t ldx, int64_t lds, int cinv_kind, const double* cinv, double ell,
+               double beta, double* ksd) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!X || !S || !ksd || n < 2 || d <= 0 || ldx < d || lds < d) return set_err(PL_EINVAL, "bad arguments (KSD needs n >= 2 samples)");
+  if (n > 65535) return set_err(PL_EINVAL, "KSD supports up to 65535 samples (four n x n Gram matrices are kept on the device)");
+  if (!(ell != 0.0)) return set_err(PL_EINVAL, "length scale must be non-zero");
+  if (cinv_kind != PL_CINV_IDENTITY && cinv_kind != PL_CINV_DIAGONAL && cinv_kind != PL_CINV_FULL) return set_err(PL_EINVAL, "unknown cinv_kind %d", cinv_kind);
+  if (cinv_kind != PL_CINV_IDENTITY && !cinv) return set_err(PL_EINVAL, "cinv is NULL");
+  CUDA_TRY(cudaSetDevice(g.device));
+  cudaStream_t st = g.stream;
+  CUDA_TRY(cudaEventRecord(g.ev[0], st));
+  double *dX, *dS, *dc = nullptr;
+  int64_t l1, l2;
+  PL_TRY(h2d_matrix(X, n, d, ldx, WS_H_IN1, &dX, &l1));
+  PL_TRY(h2d_matrix(S, n, d, lds, WS_KSD_S, &dS, &l2));
+  double trC = (double)d;
+  if (cinv_kind == PL_CINV_DIAGONAL) {
+    PL_TRY(h2d_vector(cinv, d, WS_H_IN3, &dc));
+    trC = 0.0;
+    for (int64_t k = 0; k < d; ++k) trC += cinv[k];
+  } else if (cinv_kind == PL_CINV_FULL) {
+    PL_TRY(h2d_vector(cinv, d * d, WS_H_IN3, &dc));
+    trC = 0.0;
+    for (int64_t k = 0; k < d; ++k) trC += cinv[k * d + k];
+  }
+  CUDA_TRY(cudaEventRecord(g.ev[1], st));
+  // Xc = X - mean (the pair differences are translation invariant; the Gram forms below must not cancel against |mean|^2)
+  const int64_t ldc = (d + 1) & ~(int64_t)1;
+  void *mean, *xc, *y = nullptr;
+  PL_TRY(ws_get(WS_MEAN, (size_t)ldc * 8, &mean));
+  PL_TRY(colsum(dX, n, d, l1, (double)n, (double*)mean, st));
+  PL_TRY(ws_get(WS_XC1, (size_t)n * ldc * 8, &xc));
+  PL_TRY(launch_prep<PREP_CENTER_ONLY>(dX, n, d, l1, (double*)mean, nullptr, (double*)xc, nullptr, ldc, nullptr, st));
+  const double* Y = (const double*)xc;
+  if (cinv_kind != PL_CINV_IDENTITY) {
+    PL_TRY(ws_get(WS_Y1, (size_t)n * ldc * 8, &y));
+    if (cinv_kind == PL_CINV_DIAGONAL) {
+      int blocks = (int)((n * d + 255) / 256 < g.num_sms * 8 ? (n * d + 255) / 256 : g.num_sms * 8);
+      scale_cols_kernel<<<blocks, 256, 0, st>>>((const double*)xc, n, d, ldc, dc, (double*)y);
+      LAUNCH_CHECK();
+    } else {
+      const double* cf;
+      int64_t ldcf;
+      PL_TRY(tma_operand(dc, d, d, d, WS_PADC, st, &cf, &ldcf));
+      GramLaunch Ly{};
+      Ly.epi = EPI_LINEAR;
+      Ly.A = (const double*)xc; Ly.nA = n; Ly.ldA = ldc;
+      Ly.B = cf; Ly.nB = d; Ly.ldB = ldcf;
+      Ly.d = d;
+      Ly.out = (double*)y; Ly.ldo = ldc;
+      Ly.nparts = 1;
+      PL_TRY(launch_gram(Ly, st));
+    }
+    Y = (const double*)y;
+  }
+  const int64_t ldg = (n + 1) & ~(int64_t)1;
+  void *g1, *g2, *g3, *h;
+  PL_TRY(ws_get(WS_KSD_G2, (size_t)n * ldg * 8, &g2));
+  PL_TRY(ws_get(WS_KSD_G3, (size_t)n * ldg * 8, &g3));
+  PL_TRY(ws_get(WS_KSD_H, (size_t)n * ldg * 8, &h));
+  auto linear = [&](const double* A, int64_t lda, const double* B, int64_t ldb, bool sym, double* out) -> int {
+    GramLaunch L{};
+    L.epi = EPI_LINEAR;
+    L.A = A; L.nA = n; L.ldA = lda;
+    L.B = B; L.nB = n; L.ldB = ldb;
+    L.d = d;
+    L.out = out; L.ldo = ldg;
+    L.symmetric = sym ? 1 : 0;
+    L.same_operand = sym ? 1 : 0;
+    L.fill = PL_FILL_FULL;
+    L.nparts = 1;
+    return launch_gram(L, st);
+  };
+  PL_TRY(linear(Y, ldc, Y, ldc, true, (double*)g2));                       // G2 = Y Y'
+  PL_TRY(linear(dS, l2, dS, l2, true, (double*)g3));                      // G3 = S S'
+  PL_TRY(linear(dS, l2, Y, ldc, false, (double*)h));                      // H  = S Y'
+  if (cinv_kind == PL_CINV_IDENTITY) {
+    g1 = g2;                                                               // Y == Xc
+  } else {
+    PL_TRY(ws_get(WS_KSD_G1, (size_t)n * ldg * 8, &g1));
+    PL_TRY(linear((const double*)xc, ldc, Y, ldc, false, (double*)g1));   // G1 = Xc Y' (symmetric because Cinv is)
+  }
+  int bx = (int)((n + 255) / 256);
+  if (bx > 8) bx = 8;
+  void *part, *dout;
+  PL_TRY(ws_get(WS_KSD_PART, (size_t)(n * bx + 1) * 8, &part));
+  dout = (double*)part + n * bx;
+  ksd_reduce_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, st>>>((const double*)g1, (const double*)g2, (const double*)g3, (const double*)h, n, ldg, beta,
+                                                                     1.0 / (ell * ell), trC, (double)d, (double*)part);
+  LAUNCH_CHECK();
+  ksd_final_kernel<<<1, 1024, 0, st>>>((const double*)part, n * bx, (double)n * ((double)n - 1.0), (double*)dout);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaEventRecord(g.ev[2], st));
+  CUDA_TRY(cudaMemcpyAsync(ksd, dout, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(g.ev[3], st));
   return finish_timing();
 }
 

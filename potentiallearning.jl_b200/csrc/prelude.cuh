@@ -443,4 +443,59 @@ __global__ void correlation_feature_kernel(const double* __restrict__ L, int64_t
   }
 }
 
+// ---- KernelSteinDiscrepancy with an RBF(Euclidean) kernel (src/Kernels/divergences.jl:27-49) ----
+// The reference's double loop evaluates, per pair i <= j with u = x_i - x_j, C = Cinv, k = beta exp(-u'Cu / 2l^2):
+//   sks = s_i.s_j k ;  sk = s_i'(grad_y k) = k s_i'Cu / l^2 ;  ks = (grad_x k)'s_j = -k u'C s_j / l^2 ;
+//   trk = tr(k .* (C/l^2 .- (u'C^2 u)/l^4)) = k (tr C / l^2 - D u'C^2u / l^4)
+// (kernels.jl:81-126, distances.jl:76-110; the `.-` broadcasts the scalar onto EVERY entry of the D x D matrix, so the trace picks it
+// up D times — kept as written), and sums m (sks + sk + ks + trk) / (N (N-1)), m = 1 on the diagonal, 2 off it.
+// With Y = Xc C (Xc = mean-shifted X: u is translation invariant) all five pair quantities are entries of four Gram matrices built by
+// the DMMA engine: G1 = Xc Y', G2 = Y Y', G3 = S S', H = S Y':
+//   u'Cu = G1_ii + G1_jj - 2 G1_ij,  u'C^2u = G2_ii + G2_jj - 2 G2_ij,  s_i.s_j = G3_ij,  s_i'Cu - u'Cs_j = H_ii - H_ij - H_ji + H_jj.
+// This kernel is the fused pair reduction over the upper triangle: one partial sum per block (fixed order inside the block),
+// added by ksd_final_kernel in block order -> deterministic.
+__global__ void ksd_reduce_kernel(const double* __restrict__ G1, const double* __restrict__ G2, const double* __restrict__ G3,
+                                  const double* __restrict__ H, int64_t n, int64_t ld, double beta, double inv_l2, double trC, double D,
+                                  double* __restrict__ partial) {
+  __shared__ double sh[256];
+  const int64_t i = blockIdx.y;
+  double acc = 0.0;
+  const double g1ii = G1[i * ld + i], g2ii = G2[i * ld + i], hii = H[i * ld + i];
+  for (int64_t j = i + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const double d2 = g1ii + G1[j * ld + j] - 2.0 * G1[i * ld + j];
+    const double c2 = g2ii + G2[j * ld + j] - 2.0 * G2[i * ld + j];
+    const double k = beta * exp(-0.5 * d2 * inv_l2);
+    const double cross = hii - H[i * ld + j] - H[j * ld + i] + H[j * ld + j];
+    const double t = k * (G3[i * ld + j] + cross * inv_l2 + trC * inv_l2 - D * c2 * inv_l2 * inv_l2);
+    acc += (j == i) ? t : 2.0 * t;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = sh[0];
+}
+__global__ void ksd_final_kernel(const double* __restrict__ partial, int64_t count, double denom, double* __restrict__ out) {
+  __shared__ double sh[1024];
+  double a = 0.0;
+  for (int64_t k = threadIdx.x; k < count; k += blockDim.x) a += partial[k];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0] / denom;
+}
+// Y = X .* c (row-wise scaling by a diagonal Cinv) for an already centred X
+__global__ void scale_cols_kernel(const double* __restrict__ X, int64_t n, int64_t d, int64_t ld, const double* __restrict__ c, double* __restrict__ Y) {
+  const int64_t total = n * d;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / d, k = e % d;
+    Y[r * ld + k] = X[r * ld + k] * c[k];
+  }
+}
+
 }  // namespace plb

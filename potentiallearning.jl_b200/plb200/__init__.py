@@ -11,7 +11,7 @@ from .dimred import (PCA, ActiveSubspace, DimensionReducer, PCAState, compute_ei
                      transform_)
 from .dpp import (EllEnsemble, SubsetSelector, get_dpp_mode, get_inclusion_prob, get_random_subset, greedy_subset, inclusion_prob, kDPP,
                   rescale_, sample)
-from .kernels import (RBF, CorrelationMatrix, Diagonal, Distance, DotProduct, Euclidean, Feature, GlobalMean, GlobalSum, InverseMultiquadric, Kernel,
+from .kernels import (RBF, CorrelationMatrix, Diagonal, Distance, Divergence, DotProduct, KernelSteinDiscrepancy, compute_divergence, Euclidean, Feature, GlobalMean, GlobalSum, InverseMultiquadric, Kernel,
                       KernelMatrix, Symmetric,
                       compute_distance, compute_feature, compute_features, compute_kernel, correlation_features, get_parameters, global_features, global_features_dev,
                       gram_tile_coords, kernel_matrix_dev, stack_locals)

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "pl_neq_add": (_int, [_dp, _i64, _i64, _dp, _i64, _dbl, _dbl, _dp]),
     "pl_neq_finish": (_int, [_int, _dbl, _dp, _dp]),
     "pl_global_feature": (_int, [_dp, _i64, ctypes.POINTER(_i64), _i64, _i64, _int, _dp, _i64]),
+    "pl_ksd_rbf": (_int, [_dp, _dp, _i64, _i64, _i64, _i64, _int, _dp, _dbl, _dbl, _dp]),
     "pl_correlation_feature": (_int, [_dp, _i64, ctypes.POINTER(_i64), _i64, _i64, _dp]),
     "pl_global_feature_dev": (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _i64, _i64, _vp]),
     "pl_cov": (_int, [_dp, _i64, _i64, _i64, _dp, _int, _int, _dp]),

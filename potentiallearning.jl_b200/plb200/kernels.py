@@ -5,7 +5,8 @@ Same names, argument meaning and error behaviour as the Julia API; the arithmeti
 Widened beyond the north-star kernels on the same Gram engine: InverseMultiquadric(Euclidean) and
 CorrelationMatrix features (a Symmetric d x d feature is flattened: dot(A,B) and the identity-Cinv Euclidean distance of two
 Symmetric matrices are the dot product / squared distance of their d*d entries).
-Out of scope (stay Julia): Forstner, kernel gradients, KernelSteinDiscrepancy.
+KernelSteinDiscrepancy with an RBF(Euclidean) kernel runs as four Gram matrices + one fused pair reduction (pl_ksd_rbf).
+Out of scope (stay Julia): Forstner, stand-alone kernel gradients.
 """
 from __future__ import annotations
 
@@ -393,3 +394,36 @@ def gram_tile_coords(n1: int, n2: int, part: int, nparts: int):
         _lib.check(lib.pl_gram_tile_coords(n1, n2, part, nparts, k, ctypes.byref(ti), ctypes.byref(tj)), "pl_gram_tile_coords")
         out[k] = (ti.value, tj.value)
     return out
+
+
+# ------------------------------------------------------------------ divergences (divergences.jl) ------------------
+class Divergence:
+    """abstract type Divergence (divergences.jl:7)."""
+
+
+class KernelSteinDiscrepancy(Divergence):
+    """KernelSteinDiscrepancy(; score, kernel) (divergences.jl:18-25)."""
+
+    def __init__(self, score=None, kernel=None):
+        if score is None or kernel is None:
+            raise TypeError("KernelSteinDiscrepancy(; score, kernel)")
+        self.score, self.kernel = score, kernel
+
+
+def compute_divergence(x, div: KernelSteinDiscrepancy) -> float:
+    """compute_divergence(x, div::KernelSteinDiscrepancy) (divergences.jl:27-49) on the GPU (pl_ksd_rbf): the scores div.score.(x) are
+    evaluated here (a user function, as in the reference); the O(N^2 d) pair loop runs as four Gram matrices + one fused reduction.
+    Only RBF(Euclidean) kernels (the reference's IMQ cross derivative multiplies two column vectors and throws for d > 1)."""
+    k = div.kernel
+    if not isinstance(k, RBF):
+        raise TypeError("KernelSteinDiscrepancy on the GPU needs an RBF(Euclidean) kernel")
+    X = _features_matrix([np.atleast_1d(np.asarray(v, dtype=np.float64)) for v in x])
+    S = _lib.as_f64([np.atleast_1d(np.asarray(div.score(v), dtype=np.float64)) for v in X])
+    n, d = X.shape
+    if S.shape != X.shape:
+        raise ValueError("DimensionMismatch: score(x) must have the length of x")
+    _, _, kind, cinv, ell, beta = _kargs(k, d)
+    out = np.zeros(1)
+    _lib.check(_lib.lib().pl_ksd_rbf(_lib.dptr(X), _lib.dptr(S), n, d, d, d, kind, _lib.dptr(cinv), ell, beta, _lib.dptr(out)), "pl_ksd_rbf")
+    return float(out[0])
+

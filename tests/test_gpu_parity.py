@@ -1094,3 +1094,29 @@ def test_correlation_features_bit_exact_ragged(pl, orc):
         for c, b in zip(C, blocks):
             ref = orc.correlation_matrix(list(b))
             assert np.array_equal(np.asarray(c), ref) and np.array_equal(c.data, c.data.T)
+
+
+@pytest.mark.parametrize("n,d", [(2, 1), (30, 8), (150, 26), (300, 7)])
+def test_kernel_stein_discrepancy(pl, orc, n, d):
+    """compute_divergence(x, ::KernelSteinDiscrepancy) (divergences.jl:27-49) through pl_ksd_rbf against the literal pair loop,
+    for identity / Diagonal / Symmetric Cinv, plus the reference's own test (kernel_tests.jl:93-97)."""
+    rng = np.random.default_rng(n * 100 + d)
+    x = [rng.standard_normal(d) * 0.8 + 5.0 for _ in range(n)]  # mean-heavy on purpose: the Gram forms must not cancel
+    score = lambda v: -(v - 5.0)
+    cd = rng.uniform(0.5, 2.0, size=d)
+    B = rng.standard_normal((d, d))
+    cf = B @ B.T / d + np.eye(d)
+    for ep, eo in ((pl.Euclidean(d), orc.Euclidean(d)), (pl.Euclidean(pl.Diagonal(cd)), orc.Euclidean(d, cd)),
+                   (pl.Euclidean(pl.Symmetric(cf)), orc.Euclidean(d, cf))):
+        for ell, beta in ((1.0, 1.0), (2.5, 0.7)):
+            got = pl.compute_divergence(x, pl.KernelSteinDiscrepancy(score=score, kernel=pl.RBF(ep, ell=ell, beta=beta)))
+            ref = orc.compute_divergence_ksd(x, score, orc.RBF(eo, ell=ell, beta=beta))
+            assert abs(got - ref) <= 1e-10 * max(abs(ref), 1e-3), (got, ref)
+    if n >= 30:
+        f_mvn = [rng.standard_normal(d) for _ in range(n)]
+        f_gm = [rng.standard_normal(d) + (3.0 if i % 2 else -3.0) for i in range(n)]
+        ksd = pl.KernelSteinDiscrepancy(score=lambda v: -v, kernel=pl.RBF(pl.Euclidean(d)))
+        assert isinstance(ksd, pl.Divergence)
+        assert pl.compute_divergence(f_mvn, ksd) < pl.compute_divergence(f_gm, ksd)
+    with pytest.raises(TypeError):
+        pl.compute_divergence(x, pl.KernelSteinDiscrepancy(score=score, kernel=pl.DotProduct()))

@@ -203,3 +203,20 @@ def test_golden_widened_rows():
     A = GOLD["ne_A"]
     y = A @ GOLD["pr_beta"] + 0.37 * np.concatenate([np.ones(12), np.zeros(A.shape[0] - 12)])
     assert normerr(y, GOLD["pr_y"]) < ULPS
+
+
+def test_reference_ksd_property():
+    """test/kernels/kernel_tests.jl:93-97 re-stated on the oracle: with the standard-Gaussian score, samples of a standard normal
+    have a smaller kernel Stein discrepancy than samples of a two-component mixture."""
+    rng = np.random.default_rng(0)
+    d = 8
+    f_mvn = [rng.standard_normal(d) for _ in range(30)]
+    f_gm = [rng.standard_normal(d) + (3.0 if i % 2 else -3.0) for i in range(30)]
+    k = orc.RBF(orc.Euclidean(d))
+    a = orc.compute_divergence_ksd(f_mvn, lambda x: -x, k)
+    b = orc.compute_divergence_ksd(f_gm, lambda x: -x, k)
+    assert a < b
+    # 1-D samples (the Real branch of the reference signature) behave the same way
+    a1 = orc.compute_divergence_ksd([np.array([v]) for v in rng.standard_normal(40)], lambda x: -x, orc.RBF(orc.Euclidean(1)))
+    b1 = orc.compute_divergence_ksd([np.array([v + 4.0]) for v in rng.standard_normal(40)], lambda x: -x, orc.RBF(orc.Euclidean(1)))
+    assert a1 < b1
