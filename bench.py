@@ -39,6 +39,28 @@ METRIC = "gram_rbf_fp64_gflops"
 UNIT = "GFLOP/s"
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries (NCCL's version banner, torchrun children, BLAS warnings) write to fd 1 too:
+    keep a private duplicate of the real stdout for the line and point fd 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def make_features_host(n=N_CFG, d=D_CFG, seed=SEED):
     rng = np.random.default_rng(seed)
     mu = 2.0 * rng.standard_normal(d)
@@ -253,7 +275,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": sample + "; the reference loop is single-threaded Julia (kernels.jl:217-221), restated in C (oracle/pl_oracle.c)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -267,6 +289,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the extra (non-headline) BASELINE shapes reported under 'also'")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -447,7 +470,7 @@ def main():
             "config": workload_config({"parallelism": f"tiles round-robin over {world} GPU(s), no collective", "output": "tile-packed shards" if packed else "dense N x N storage, Symmetric uplo=:U triangle written (reference contract, kernels.jl:216-222)"}),
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
             "wall_s_timed_region": t_wall, "also": also}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
