@@ -254,6 +254,19 @@ def ols_sums(iv_data, dv_data):
     return normal_equations(A, b)
 
 
+def batch_sums(lp: LinearProblem, inds):
+    """The per-step assembly of the minibatch learn!(lp, ss::SubsetSelector, α; …) variants (linear-learn.jl:92-95 univariate,
+    :137-143 covariate): sums over the configurations `inds = get_random_subset(ss)` only. The selected blocks are streamed to the GPU
+    as they lie (pl_normal_eq_blocks); the Flux / Adam / MvNormal optimisation around these sums stays in PotentialLearning.jl.
+    Returns (AtA, Atb) resp. (AtAe, Atbe, AtAf, Atbf). The final full-data sums (:107, :157-158) are ols_sums(...)."""
+    inds = [int(i) for i in inds]
+    if isinstance(lp, UnivariateLinearProblem):
+        return normal_equations_blocks([lp.iv_data[i] for i in inds], pack_rhs([lp.dv_data[i] for i in inds]))
+    AtAe, Atbe = normal_equations_blocks([lp.B[i] for i in inds], pack_rhs([lp.e[i] for i in inds]))
+    AtAf, Atbf = normal_equations_blocks([lp.dB[i] for i in inds], pack_rhs([lp.f[i] for i in inds]))
+    return AtAe, Atbe, AtAf, Atbf
+
+
 def _learn_ols(lp, α: float):
     if isinstance(lp, UnivariateLinearProblem):
         AtA, Atb = ols_sums(lp.iv_data, lp.dv_data)  # :16-17 on the GPU

@@ -1120,3 +1120,20 @@ def test_kernel_stein_discrepancy(pl, orc, n, d):
         assert pl.compute_divergence(f_mvn, ksd) < pl.compute_divergence(f_gm, ksd)
     with pytest.raises(TypeError):
         pl.compute_divergence(x, pl.KernelSteinDiscrepancy(score=score, kernel=pl.DotProduct()))
+
+
+def test_minibatch_assembly_sums(pl, orc):
+    """learn!(lp, ss::SubsetSelector, α) (linear-learn.jl:92-95, 137-143): the per-step sums over a random subset of configurations."""
+    rng = np.random.default_rng(41)
+    ds = fake_dataset(pl, rng, 60, 7, 8, energies=True, forces=True)
+    lp = pl.LinearProblem(ds)
+    inds = rng.choice(60, size=25, replace=True)  # get_random_subset may repeat indices (random.jl / dbscan.jl sample with replacement)
+    AtAe, Atbe, AtAf, Atbf = pl.batch_sums(lp, inds)
+    re, rbe = orc.ols_sums([lp.B[i] for i in inds], [lp.e[i] for i in inds])
+    rf, rbf = orc.ols_sums([lp.dB[i] for i in inds], [lp.f[i] for i in inds])
+    assert normerr(AtAe, re) < RTOL and normerr(Atbe, rbe) < RTOL and normerr(AtAf, rf) < RTOL and normerr(Atbf, rbf) < RTOL
+    ds_e = fake_dataset(pl, rng, 30, 5, 6, energies=True)
+    lpu = pl.LinearProblem(ds_e)
+    AtA, Atb = pl.batch_sums(lpu, [3, 3, 7, 29])
+    ra, rb = orc.ols_sums([lpu.iv_data[i] for i in (3, 3, 7, 29)], [lpu.dv_data[i] for i in (3, 3, 7, 29)])
+    assert normerr(AtA, ra) < RTOL and normerr(Atb, rb) < RTOL
