@@ -233,10 +233,10 @@ def other_configs(dev, peak_tflops):
         n, K = 2_500_000, 1000
         X = torch.randn((n, K), device=dev, dtype=torch.float64, generator=g) + 10.0 * torch.randn(K, device=dev, dtype=torch.float64, generator=g)
 
+        from plb200.distributed import covariance_sharded
+
         def cov():
-            m = eng.scale_div(eng.colsum(X), float(n))
-            S, _ = eng.syrk_partial(X, None, 0, 1.0, 1.0, None, m, False)
-            eng.sym_scale_div(S, float(n))
+            covariance_sharded(X, n, engine=eng)  # prefix mean -> shifted SYRK (one pass over the rows) -> re-centre -> 1/n
 
         ms = best_ms(cov, reps=3)
         tf = n * K * (K + 1.0) / (ms * 1e-3) / 1e12

@@ -215,6 +215,12 @@ int pl_gram_tile_coords(int64_t n1, int64_t n2, int part, int nparts, int64_t k,
  *   dvec: 2*Kf + 2 doubles = [v (Kf) ; c (Kf) ; s (2)]  (may be NULL if neither b nor the intercept is wanted; not with dmean) */
 int pl_syrk_dev(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dw, int64_t n_energy_rows, double w_e,
                 double w_f, const double* db, const double* dmean, double* dS, double* dvec, void* stream);
+/* One-pass centred covariance of a row shard (no separate mean pass over the data): with a shift z close to the mean (e.g. the mean
+ * of a prefix of the rows, pl_colsum_dev), pl_cov_shifted_dev returns S_z = sum_r (x_r - z)(x_r - z)' and rho = sum_r (x_r - z).
+ * The shard's column sum is n_r z + rho (all-reduce it for the global mean m); pl_cov_recentre_dev then moves S_z to the mean:
+ * S <- S - rho delta' - delta rho' + n_r delta delta', delta = m - z. Because z is within sigma/sqrt(prefix) of m nothing cancels. */
+int pl_cov_shifted_dev(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dz, double* dS, double* drho, void* stream);
+int pl_cov_recentre_dev(double* dS, int64_t Kf, const double* drho, const double* ddelta, double n_rows, void* stream);
 /* Assemble (AtWA, AtWb) of order Kf+ic from (all-reduced) S / vec as pl_normal_eq defines them. */
 int pl_normal_eq_finish_dev(const double* dS, const double* dvec, int64_t Kf, int add_intercept, double lambda,
                             double* dAtWA, double* dAtWb, void* stream);

@@ -103,6 +103,9 @@ enum WsSlot {
   WS_KSD_H,
   WS_KSD_S,
   WS_KSD_PART,
+  WS_COV_Z,
+  WS_COV_RHO,
+  WS_COV_DELTA,
   WS_NSLOTS
 };
 
@@ -503,8 +506,9 @@ void choose_splits(int64_t R, int nunits, int* splits, int64_t* rows_per_split) 
   *rows_per_split = rps;
 }
 
+// drho_out (centred mode, optional): rho = sum_r (a_r - mean) of this shard, the by-product of the one-sided centring
 int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dw, int64_t ne, double w_e, double w_f, const double* db,
-                  const double* dmean, double* dS, double* dvec, cudaStream_t st) {
+                  const double* dmean, double* dS, double* dvec, cudaStream_t st, double* drho_out = nullptr) {
   PL_TRY(need_ready());
   if (R < 0 || Kf <= 0 || lda < Kf) return set_err(PL_EINVAL, "bad shape R=%lld Kf=%lld lda=%lld", (long long)R, (long long)Kf, (long long)lda);
   if (!dA || !dS) return set_err(PL_EINVAL, "null pointer");
@@ -607,6 +611,7 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
     syrk_center_fix_kernel<<<blocks, 256, 0, st>>>(dS, Kf, augvec, dmean);
     LAUNCH_CHECK();
   }
+  if (dmean && drho_out) CUDA_TRY(cudaMemcpyAsync(drho_out, aug ? (const void*)augvec : (const void*)rho, (size_t)Kf * 8, cudaMemcpyDeviceToDevice, st));
   if (dvec && !aug) {
     PL_TRY(moment_vectors(A, R, Kf, ld, dw, ne, w_e, w_f, db, dvec, dvec + Kf, st));
     syrk_scalar_kernel<<<1, 1024, 0, st>>>(dw, db, ne, w_e, dvec + 2 * Kf);
@@ -880,6 +885,25 @@ struct NeqState {
   int64_t Kf = 0, rows = 0, batches = 0;
   bool open = false;
 } neq_state;
+
+
+// One-pass centred second moment about a SHIFT z close to the mean: S_z = sum_r (x_r - z)(x_r - z)', rho = sum_r (x_r - z).
+// With the true mean m = z + rho / n the centred sum is S_z - rho (m-z)' - (m-z) rho' + n (m-z)(m-z)'; because z is already within
+// sigma / sqrt(prefix) of m the correction is ~1e-5 of S and nothing cancels — the mean pass over the data is not needed.
+int cov_shifted_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dz, double* dS, double* drho, cudaStream_t st) {
+  if (!dz || !drho) return set_err(PL_EINVAL, "null pointer");
+  return syrk_dev_impl(dA, R, Kf, lda, nullptr, 0, 1.0, 1.0, nullptr, dz, dS, nullptr, st, drho);
+}
+
+int cov_recentre_dev_impl(double* dS, int64_t Kf, const double* drho, const double* ddelta, double n_rows, cudaStream_t st) {
+  PL_TRY(need_ready());
+  if (!dS || !drho || !ddelta || Kf <= 0) return set_err(PL_EINVAL, "bad arguments");
+  int blocks = (int)((Kf * Kf + 255) / 256);
+  if (blocks > g.num_sms * 8) blocks = g.num_sms * 8;
+  cov_recentre_kernel<<<blocks, 256, 0, st>>>(dS, Kf, drho, ddelta, n_rows);
+  LAUNCH_CHECK();
+  return PL_OK;
+}
 
 }  // namespace
 
@@ -1315,8 +1339,24 @@ int pl_cov(const double* X, int64_t n, int64_t Kf, int64_t ldx, double* mean_ino
   PL_TRY(ws_get(WS_H_S, (size_t)Kf * Kf * 8, &dS));
   PL_TRY(ws_get(WS_H_OUT1, (size_t)Kf * Kf * 8, &dC));
   CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
-  if (center && !mean_given) PL_TRY(colsum(dX, n, Kf, ld, (double)n, dmean, g.stream));  // pca.m = sum(d)/length(d)
-  PL_TRY(syrk_dev_impl(dX, n, Kf, ld, nullptr, 0, 1.0, 1.0, nullptr, dmean, (double*)dS, nullptr, g.stream));
+  if (center && !mean_given) {
+    // one pass over the rows: shift z = mean of a prefix, S_z and rho from the SYRK, then m = z + rho/n (pca.m = sum(d)/length(d),
+    // pca_state.jl:35) and the re-centring about m
+    void *z, *rho, *delta;
+    PL_TRY(ws_get(WS_COV_Z, (size_t)Kf * 8, &z));
+    PL_TRY(ws_get(WS_COV_RHO, (size_t)Kf * 8, &rho));
+    PL_TRY(ws_get(WS_COV_DELTA, (size_t)Kf * 8, &delta));
+    const int64_t prefix = n < 65536 ? n : 65536;
+    PL_TRY(colsum(dX, prefix, Kf, ld, (double)prefix, (double*)z, g.stream));
+    PL_TRY(cov_shifted_dev_impl(dX, n, Kf, ld, (const double*)z, (double*)dS, (double*)rho, g.stream));
+    scale_div_kernel<<<(unsigned)((Kf + 255) / 256), 256, 0, g.stream>>>((const double*)rho, (double)n, Kf, (double*)delta);  // delta = m - z
+    LAUNCH_CHECK();
+    axpy1_kernel<<<(unsigned)((Kf + 255) / 256), 256, 0, g.stream>>>((const double*)z, (const double*)delta, Kf, dmean);      // m = z + delta
+    LAUNCH_CHECK();
+    PL_TRY(cov_recentre_dev_impl((double*)dS, Kf, (const double*)rho, (const double*)delta, (double)n, g.stream));
+  } else {
+    PL_TRY(syrk_dev_impl(dX, n, Kf, ld, nullptr, 0, 1.0, 1.0, nullptr, dmean, (double*)dS, nullptr, g.stream));
+  }
   {
     const int64_t count = Kf * Kf;
     int blocks = (int)((count + 255) / 256);
@@ -1701,6 +1741,17 @@ int pl_ksd_rbf(const double* X, const double* S, int64_t n, int64_t d, int64_t l
   CUDA_TRY(cudaMemcpyAsync(ksd, dout, 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaEventRecord(g.ev[3], st));
   return finish_timing();
+}
+
+
+int pl_cov_shifted_dev(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dz, double* dS, double* drho, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return cov_shifted_dev_impl(dA, R, Kf, lda, dz, dS, drho, (cudaStream_t)stream);
+}
+
+int pl_cov_recentre_dev(double* dS, int64_t Kf, const double* drho, const double* ddelta, double n_rows, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return cov_recentre_dev_impl(dS, Kf, drho, ddelta, n_rows, (cudaStream_t)stream);
 }
 
 }  // extern "C"

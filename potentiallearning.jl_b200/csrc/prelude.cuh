@@ -498,4 +498,25 @@ __global__ void scale_cols_kernel(const double* __restrict__ X, int64_t n, int64
   }
 }
 
+// S_ij <- S_ij - rho_i delta_j - delta_i rho_j + n delta_i delta_j over the j >= i triangle, mirrored: re-centres a second moment taken
+// about a shift z (S = sum (x-z)(x-z)', rho = sum (x-z)) to the mean m = z + delta. Exactly symmetric by construction.
+__global__ void cov_recentre_kernel(double* __restrict__ S, int64_t K, const double* __restrict__ rho, const double* __restrict__ delta, double n) {
+  const int64_t total = K * K;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / K, j = e % K;
+    if (j < i) continue;
+    double v = S[e];
+    v = fma(-rho[i], delta[j], v);
+    v = fma(-delta[i], rho[j], v);
+    v = fma(n * delta[i], delta[j], v);
+    S[e] = v;
+    S[j * K + i] = v;
+  }
+}
+// out[i] = a[i] + b[i]
+__global__ void axpy1_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t count, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = a[i] + b[i];
+}
+
 }  // namespace plb

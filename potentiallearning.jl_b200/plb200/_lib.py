@@ -59,6 +59,8 @@ PROTOTYPES = {
     "pl_gram_tile_count": (_i64, [_i64, _i64, _int, _int]),
     "pl_gram_tile_coords": (_int, [_i64, _i64, _int, _int, _i64, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
     "pl_syrk_dev": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp]),
+    "pl_cov_shifted_dev": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "pl_cov_recentre_dev": (_int, [_vp, _i64, _vp, _vp, _dbl, _vp]),
     "pl_normal_eq_finish_dev": (_int, [_vp, _vp, _i64, _int, _dbl, _vp, _vp, _vp]),
     "pl_colsum_dev": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "pl_scale_div_dev": (_int, [_vp, _dbl, _i64, _vp, _vp]),

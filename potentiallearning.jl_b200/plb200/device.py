@@ -53,6 +53,22 @@ class DeviceEngine:
         )
         return M, v
 
+    def cov_shifted(self, X, z):
+        """S_z = sum (x - z)(x - z)' and rho = sum (x - z) of a row shard in ONE pass over the rows (pl_cov_shifted_dev)."""
+        import torch
+
+        _check_mat(X, "X")
+        R, K = X.shape
+        S = torch.empty((K, K), device=X.device, dtype=torch.float64)
+        rho = torch.empty(K, device=X.device, dtype=torch.float64)
+        _lib.check(_lib.lib().pl_cov_shifted_dev(X.data_ptr(), R, K, X.stride(0), z.data_ptr(), S.data_ptr(), rho.data_ptr(), _stream(X)), "pl_cov_shifted_dev")
+        return S, rho
+
+    def cov_recentre(self, S, rho, delta, n_rows):
+        """in place: S <- S - rho delta' - delta rho' + n delta delta' (moves a second moment about z to the mean z + delta)"""
+        _lib.check(_lib.lib().pl_cov_recentre_dev(S.data_ptr(), S.shape[0], rho.data_ptr(), delta.data_ptr(), float(n_rows), _stream(S)), "pl_cov_recentre_dev")
+        return S
+
     def colsum(self, A):
         import torch
 

@@ -3,7 +3,8 @@ contraction has. The reference has no distributed code at all (SURVEY.md section
 
   * normal equations / covariance: shard ROWS (whole configurations per rank), each rank produces unscaled partial
     sums with the fused SYRK kernel, ONE all-reduce of K*K (+2K+2) doubles, then the tiny finish kernel;
-    the centred covariance needs one earlier all-reduce of the K column sums (two-pass, required for 1e-10).
+    the centred covariance needs one earlier all-reduce of the K column sums, but still only one pass over the rows
+    (shifted second moment + re-centring, see covariance_sharded).
   * Gram matrices: tiles are dealt round-robin to ranks; X is replicated; NO collective on the result (tile-packed
     shards stay on their GPU).
 
@@ -52,16 +53,28 @@ def normal_equations_sharded(A_local, b_local=None, w_local=None, n_energy_rows_
 
 
 def covariance_sharded(X_local, n_total: int, mean=None, center=True, group=None, engine=None):
-    """(Q, m) with Q = (1/n) sum_r (x_r - m)(x_r - m)' over all ranks' rows (compute_eigen's Q + PCAState centring)."""
+    """(Q, m) with Q = (1/n) sum_r (x_r - m)(x_r - m)' over all ranks' rows (compute_eigen's Q + PCAState centring).
+
+    center and no mean given: ONE pass over the rows per rank. Each rank shifts by z = the mean of a prefix of its own rows, the SYRK
+    returns S_z = sum (x - z)(x - z)' and rho = sum (x - z); the column sums n_r z + rho are all-reduced for the global mean m
+    (pca.m = sum(d)/length(d), pca_state.jl:35), every rank re-centres its S_z about m (delta = m - z: tiny, nothing cancels), and ONE
+    all-reduce adds the shards. A persisted mean (pca.m set, pca_state.jl:34) centres directly."""
     engine = engine or DeviceEngine()
-    m = None
-    if center:
-        if mean is None:
-            s = engine.colsum(X_local)
-            _all_reduce(s, group)
-            m = engine.scale_div(s, float(n_total))  # pca.m = sum(d) / length(d)
+    n_local = X_local.shape[0]
+    if center and mean is None:
+        prefix = min(n_local, 65536)
+        if prefix > 0:
+            z = engine.scale_div(engine.colsum(X_local[:prefix]), float(prefix))
         else:
-            m = mean
+            z = X_local.new_zeros(X_local.shape[1])
+        S, rho = engine.cov_shifted(X_local, z)
+        s = z * float(n_local) + rho  # this shard's column sums (K numbers: glue, not compute)
+        _all_reduce(s, group)
+        m = engine.scale_div(s, float(n_total))
+        engine.cov_recentre(S, rho, m - z, float(n_local))
+        _all_reduce(S, group)
+        return engine.sym_scale_div(S, float(n_total)), m
+    m = mean if center else None
     S, _ = engine.syrk_partial(X_local, None, 0, 1.0, 1.0, None, m, False)
     _all_reduce(S, group)
     return engine.sym_scale_div(S, float(n_total)), m  # exactly symmetric even after a >2-rank ring all-reduce

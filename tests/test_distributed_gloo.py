@@ -49,6 +49,15 @@ class CheckerEngine:
         M = np.triu(M) + np.triu(M, 1).T + lam * np.eye(M.shape[0])  # j >= i triangle only, like normal_eq_finish_kernel
         return torch.from_numpy(M), (torch.from_numpy(rhs) if (want_rhs and rhs is not None) else None)
 
+    def cov_shifted(self, X, z):
+        Y = X.numpy() - z.numpy()
+        return torch.from_numpy(Y.T @ Y), torch.from_numpy(Y.sum(axis=0))
+
+    def cov_recentre(self, S, rho, delta, n_rows):
+        r, dl = rho.numpy(), delta.numpy()
+        S -= torch.from_numpy(np.outer(r, dl) + np.outer(dl, r) - n_rows * np.outer(dl, dl))
+        return S
+
     def colsum(self, A):
         return A.sum(dim=0)
 

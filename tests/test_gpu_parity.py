@@ -728,7 +728,8 @@ def test_config4_slice_checksums(pl):
         tr_ref += float((Y * Y).sum())
     assert abs(float(torch.trace(C)) - tr_ref / n) / (tr_ref / n) < 1e-12
     C2, m2 = covariance_sharded(X, n, mean=m, engine=eng)  # pca.m persists (pca_state.jl:34)
-    assert bool(torch.equal(m2, m)) and bool(torch.equal(C2, C))
+    # (the persisted-mean path centres directly, the first fit went through the one-pass shifted form: same sums, different rounding)
+    assert bool(torch.equal(m2, m)) and float((C2 - C).abs().max() / C.abs().max()) < 1e-13 and bool(torch.equal(C2, C2.T))
     del X
 
 
