@@ -35,7 +35,7 @@ torch.cuda.set_device(local_rank)
 dev = torch.device("cuda", local_rank)
 if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ["NCCL_DEBUG"] = "WARN"  # (NCCL still prints its version banner on stdout: the result is also written to gpurun_out/scale_n<N>.json)
     dist.init_process_group("nccl", device_id=dev)
 plb200.init(local_rank)
 eng = DeviceEngine()
