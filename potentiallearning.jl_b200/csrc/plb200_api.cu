@@ -205,7 +205,9 @@ int64_t colsum_rows_per_block(int64_t R, int64_t Kf) {
   // rows per block: aim at >= 16 blocks per SM, between 32 and 512 rows each (fixed for a given shape: deterministic)
   const int64_t colblocks = ((Kf + 1) / 2 + 127) / 128;
   int64_t rpb = R * colblocks / ((int64_t)g.num_sms * 16);
-  return rpb < 32 ? 32 : (rpb > COLSUM_MAX_ROWS_PER_BLOCK ? COLSUM_MAX_ROWS_PER_BLOCK : (rpb + 3) / 4 * 4);
+  rpb = rpb < 32 ? 32 : (rpb > COLSUM_MAX_ROWS_PER_BLOCK ? COLSUM_MAX_ROWS_PER_BLOCK : (rpb + 3) / 4 * 4);
+  const int64_t min_rpb = ((R + 65534) / 65535 + 3) / 4 * 4;  // gridDim.y is limited to 65535 row blocks
+  return rpb < min_rpb ? min_rpb : rpb;
 }
 
 int colsum(const double* dA, int64_t R, int64_t Kf, int64_t lda, double denom, double* dout, cudaStream_t st, const double* dshift = nullptr) {
