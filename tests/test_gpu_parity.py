@@ -1138,3 +1138,72 @@ def test_minibatch_assembly_sums(pl, orc):
     AtA, Atb = pl.batch_sums(lpu, [3, 3, 7, 29])
     ra, rb = orc.ols_sums([lpu.iv_data[i] for i in (3, 3, 7, 29)], [lpu.dv_data[i] for i in (3, 3, 7, 29)])
     assert normerr(AtA, ra) < RTOL and normerr(Atb, rb) < RTOL
+
+
+def test_randomized_shape_sweep(pl):
+    """Seeded sweep over odd shapes (every tile / box / split boundary gets hit sooner or later): all kernel families against
+    vectorised fp64 numpy evaluations of the reference formulas. Tolerance 1e-10 (the contract); typical errors are 1e-14."""
+    rng = np.random.default_rng(20261020)
+
+    def rbf_ref(X1, X2, C, ell, beta):
+        U = X1[:, None, :] - X2[None, :, :]
+        d2 = np.einsum("ijk,kl,ijl->ij", U, C, U)
+        return beta * np.exp(-0.5 * d2 / ell ** 2)
+
+    for trial in range(40):
+        n = int(rng.choice([1, 2, 7, 127, 128, 129, 255, 257, 300, 511]))
+        d = int(rng.choice([1, 2, 3, 15, 16, 17, 31, 33, 64, 65]))
+        mu = 2.0 * rng.standard_normal(d)
+        X = rng.standard_normal((n, d)) * 0.4 + mu
+        ell, beta = float(rng.uniform(0.5, 3.0)), float(rng.uniform(0.2, 2.0))
+        kind = trial % 3
+        if kind == 0:
+            e, C = pl.Euclidean(d), np.eye(d)
+        elif kind == 1:
+            cd = rng.uniform(0.5, 2.0, size=d)
+            e, C = pl.Euclidean(pl.Diagonal(cd)), np.diag(cd)
+        else:
+            B = rng.standard_normal((d, d))
+            C = B @ B.T / d + np.eye(d)
+            e = pl.Euclidean(pl.Symmetric(C))
+        K = np.asarray(pl.KernelMatrix(X, pl.RBF(e, ell=ell, beta=beta)))
+        assert relerr(K, rbf_ref(X, X, C, ell, beta)) < 1e-10, ("rbf", n, d, kind)
+        assert np.array_equal(K, K.T)
+        G = X @ X.T
+        nr = np.sqrt(np.diag(G))
+        alpha = int(rng.choice([1, 2, 3]))
+        Kd = np.asarray(pl.KernelMatrix(X, pl.DotProduct(alpha)))
+        assert np.max(np.abs(Kd - (G / np.outer(nr, nr)) ** alpha)) < 1e-10, ("dot", n, d, alpha)
+        n2 = int(rng.choice([1, 3, 32, 33, 96, 97, 200]))
+        X2 = rng.standard_normal((n2, d)) * 0.4 + mu
+        Kx = pl.KernelMatrix(X, X2, pl.RBF(e, ell=ell, beta=beta))
+        assert relerr(Kx, rbf_ref(X, X2, C, ell, beta)) < 1e-10, ("rbf cross", n, n2, d, kind)
+        Ki = np.asarray(pl.KernelMatrix(X, pl.InverseMultiquadric(e, c2=beta, ell=ell)))
+        U = X[:, None, :] - X[None, :, :]
+        assert relerr(Ki, (beta + np.einsum("ijk,kl,ijl->ij", U, C, U) / ell ** 2) ** -0.5) < 1e-10, ("imq", n, d, kind)
+    for trial in range(40):
+        R = int(rng.choice([1, 5, 15, 16, 17, 255, 1023, 1024, 1025, 4097]))
+        Kf = int(rng.choice([1, 2, 14, 15, 16, 17, 63, 127, 128, 129, 143, 255, 256, 300]))
+        ne = int(rng.integers(0, R + 1))
+        A = rng.standard_normal((R, Kf)) + 0.5
+        b = rng.standard_normal(R)
+        intercept = bool(trial % 2)
+        lam = float(rng.choice([0.0, 0.01]))
+        we, wf = float(rng.uniform(0.5, 100.0)), float(rng.uniform(0.5, 2.0))
+        w = rng.uniform(0.1, 3.0, size=R) if trial % 3 == 0 else None
+        M, v = pl.normal_equations(A, b, w, ne, we, wf, intercept, lam)
+        q = w if w is not None else np.concatenate([we * np.ones(ne), wf * np.ones(R - ne)])
+        Ai = np.hstack([np.concatenate([np.ones(ne), np.zeros(R - ne)])[:, None], A]) if intercept else A
+        Mo = Ai.T @ (q[:, None] * Ai) + lam * np.eye(Ai.shape[1])
+        vo = Ai.T @ (q * b)
+        assert np.max(np.abs(M - Mo)) / np.max(np.abs(Mo)) < 1e-10, ("neq", R, Kf, ne, intercept)
+        assert np.max(np.abs(v - vo)) / max(np.max(np.abs(vo)), 1e-300) < 1e-10, ("neq rhs", R, Kf, ne)
+        assert np.array_equal(M, M.T)
+        Xc = A + 10.0 * rng.standard_normal(Kf)
+        Cc, m = pl.covariance(Xc, center=True)
+        mo = Xc.mean(0)
+        Co = (Xc - mo).T @ (Xc - mo) / R
+        assert np.max(np.abs(m - mo) / np.abs(mo)) < 1e-12
+        if R > 1:
+            assert np.max(np.abs(Cc - Co)) / np.max(np.abs(Co)) < 1e-10, ("cov", R, Kf)
+        assert np.array_equal(Cc, Cc.T)
