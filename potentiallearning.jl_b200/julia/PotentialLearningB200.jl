@@ -11,7 +11,8 @@
 #   learn!(lp::UnivariateLinearProblem, α::Real)   (assembly only)             src/Learning/linear-learn.jl:11-23
 #   compute_eigen(d::Vector{<:Vector{<:Real}})                                 src/DimensionReduction/dimension_reduction.jl:11-14
 #   fit!(ds::DataSet, pca::PCAState)                                           src/DimensionReduction/pca_state.jl:20-40
-#   compute_features(ds::DataSet, f::GlobalMean / ::GlobalSum)                 src/Kernels/features.jl:19-34, 76-78   (widened row f2)
+#   compute_features(ds::DataSet, f::GlobalMean / ::GlobalSum / ::CorrelationMatrix)   src/Kernels/features.jl:19-50, 76-78   (widened rows f2, f4)
+#   compute_divergence(x, ::KernelSteinDiscrepancy)   (RBF over Euclidean)    src/Kernels/divergences.jl:27-49       (widened row f4)
 # kDPP(ds, f, k) / kDPP(features, k) (src/SubsetSelection/dpp.jl:18-44) need no override: they call KernelMatrix and hand
 # the Symmetric result to Determinantal.jl exactly as before. Optional (widened row f1): `ell_ensemble_gpu(F, k)` returns the
 # eigendecomposition computed on the device for callers that construct Determinantal's ensemble from (λ, U) themselves.
@@ -204,6 +205,54 @@ function fit!(ds::DataSet, pca::PCAState)                                       
     Σ = 1.0 .- cumsum(λ) / sum(λ)
     pca.λ, pca.W = λ, (pca.tol isa Int ? ϕ[:, 1:pca.tol] : ϕ[:, Σ .> pca.tol])
     nothing
+end
+
+compute_features(ds::DataSet, f::PotentialLearning.CorrelationMatrix; dt = nothing) = begin                  # features.jl:48-50
+    locals = [reduce(hcat, get_values(get_local_descriptors(c))) for c in ds]
+    L = reduce(hcat, locals); d = size(L, 1); N = length(locals)
+    offsets = Int64[0; cumsum(size.(locals, 2))]
+    C = zeros(d, d, N)
+    check(ccall((:pl_correlation_feature, libplb200), Cint, (Ptr{Cdouble}, Int64, Ptr{Int64}, Int64, Int64, Ptr{Cdouble}),
+                L, d, offsets, N, d, C), "pl_correlation_feature")
+    [Symmetric(C[:, :, i]) for i in 1:N]
+end
+
+# ---- predictions of a fitted linear model: get_all_energies(ds, lb) / get_all_forces(ds, lb) (Data/utils.jl:42-65) ------------
+function predict_gpu(A::Matrix{Float64}, β::Vector{Float64}, β0::Float64, ne::Integer)                       # A: K x R (rows of the design matrix as columns)
+    K, R = size(A); y = zeros(R)
+    check(ccall((:pl_predict, libplb200), Cint, (Ptr{Cdouble}, Int64, Int64, Int64, Ptr{Cdouble}, Cdouble, Int64, Ptr{Cdouble}),
+                A, R, K, K, β, β0, ne, y), "pl_predict")
+    y
+end
+
+# ---- ooc_learn! running sums (linear-learn.jl:301-391): AtWA .+= A'*W*A; AtWb .+= A'*W*b (:355-356) stay on the device ------------
+# Inside ooc_learn!'s `for config in ds_train` loop: A = [global_descr'; force_descrs] (rows x K), buffer a few configurations, then
+#   neq_add(permutedims(A), b, w)      # per-row weights w = [ws[1]*e_norm; ws[2]*ones(3natoms)]  (:341-352)
+# and after the loop `AtWA, AtWb = neq_finish(K)`; the ridge / solve / cond print of :358-391 are unchanged.
+neq_begin(K::Integer) = check(ccall((:pl_neq_begin, libplb200), Cint, (Int64,), K), "pl_neq_begin")
+function neq_add(At::Matrix{Float64}, b::Vector{Float64}, w::Vector{Float64})                                   # At: K x rows
+    K, R = size(At)
+    check(ccall((:pl_neq_add, libplb200), Cint, (Ptr{Cdouble}, Int64, Int64, Ptr{Cdouble}, Int64, Cdouble, Cdouble, Ptr{Cdouble}),
+                At, R, K, w, 0, 1.0, 1.0, b), "pl_neq_add")
+end
+function neq_finish(K::Integer; int::Bool = false, λ::Real = 0.0)
+    n = K + (int ? 1 : 0); AtWA = zeros(n, n); AtWb = zeros(n)
+    check(ccall((:pl_neq_finish, libplb200), Cint, (Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}), int, Float64(λ), AtWA, AtWb), "pl_neq_finish")
+    AtWA, AtWb
+end
+
+# ---- KernelSteinDiscrepancy with an RBF(Euclidean) kernel (divergences.jl:27-49) ----------------------------------------------------
+function PotentialLearning.compute_divergence(x::Vector{Vector{Float64}}, div::PotentialLearning.KernelSteinDiscrepancy)
+    k = div.kernel
+    (k isa RBF && k.d isa Euclidean) || return invoke(PotentialLearning.compute_divergence,
+                                                      Tuple{Vector{<:Union{Real,Vector{<:Real}}},PotentialLearning.KernelSteinDiscrepancy}, x, div)
+    X = pack(x); S = pack(Vector{Float64}.(div.score.(x))); d, n = size(X)
+    kind, cptr, keep = cinv_args(k.d)
+    out = zeros(1)
+    GC.@preserve keep check(ccall((:pl_ksd_rbf, libplb200), Cint,
+                (Ptr{Cdouble}, Ptr{Cdouble}, Int64, Int64, Int64, Int64, Cint, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cdouble}),
+                X, S, n, d, d, d, kind, cptr, Float64(k.ℓ), Float64(k.β), out), "pl_ksd_rbf")
+    out[1]
 end
 
 end # module
