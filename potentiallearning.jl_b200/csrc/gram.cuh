@@ -219,7 +219,9 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[MT][NT][2], co
           } else {
             const bool ok = ((imask >> mt) & 1u) && jok[q][c];
             const int rel = rel0 + (8 * nt + 4 * c - 8 * mt);
-            if (EPI != EPI_LINEAR && rel == 0) x = diagval;  // k(x,x): beta (d2 == 0), resp. n/sqrt(n*n) = 1 in the reference
+            // k(x,x): beta (d2 == 0), resp. n/sqrt(n*n) = 1 in the reference — unless it is NaN there too (a zero feature vector gives
+            // 0/sqrt(0) in DotProduct, NaN inputs propagate): x == x keeps those
+            if (EPI != EPI_LINEAR && rel == 0 && x == x) x = diagval;
             if (ok && w1 && rel >= 0) pr[8 * nt + 4 * c] = (!dg || fill1 || rel == 0) ? x : 0.0;
             if (ok && w2 && rel > 0) pcol[(int64_t)(8 * nt + 4 * c) * ldo + 8 * mt] = (!dg || fill2) ? x : 0.0;
           }

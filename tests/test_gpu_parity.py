@@ -1207,3 +1207,25 @@ def test_randomized_shape_sweep(pl):
         if R > 1:
             assert np.max(np.abs(Cc - Co)) / np.max(np.abs(Co)) < 1e-10, ("cov", R, Kf)
         assert np.array_equal(Cc, Cc.T)
+
+
+def test_degenerate_inputs_propagate_like_the_reference(pl, orc):
+    """A zero feature vector makes DotProduct 0/sqrt(0) = NaN in the reference (kernels.jl:35), its own diagonal entry included; NaN
+    inputs propagate through every kernel. The GPU path must not paper over either (the diagonal is only forced to its exact value
+    where the reference value is finite)."""
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((200, 9)) + 1.0
+    X[17] = 0.0
+    with np.errstate(all="ignore"):
+        Ko = orc.symmetric(orc.kernel_matrix(X, orc.DotProduct(), use_c=False))
+    K = np.asarray(pl.KernelMatrix(X, pl.DotProduct()))
+    assert np.isnan(Ko[17, 17]) and np.isnan(K[17]).all() and np.isnan(K[:, 17]).all()
+    ok = ~np.isnan(Ko)
+    assert np.array_equal(np.isnan(K), np.isnan(Ko)) and relerr(K[ok], Ko[ok]) < RTOL
+    Kr = np.asarray(pl.KernelMatrix(X, pl.RBF(pl.Euclidean(9))))  # a zero vector is an ordinary point for a distance kernel
+    assert relerr(Kr, orc.symmetric(orc.kernel_matrix(X, orc.RBF(orc.Euclidean(9)), use_c=False))) < RTOL and Kr[17, 17] == 1.0
+    Xn = X.copy()
+    Xn[17] = 1.0
+    Xn[5, 3] = np.nan
+    Kn = np.asarray(pl.KernelMatrix(Xn, pl.DotProduct()))
+    assert np.isnan(Kn[5]).all() and np.isnan(Kn[:, 5]).all() and not np.isnan(np.delete(np.delete(Kn, 5, 0), 5, 1)).any()
