@@ -4,7 +4,7 @@ Layout: csrc/ (sm_100a CUDA + C ABI -> plb200/libplb200.so), plb200/ (this packa
 operator interface for the path), julia/ (the ccall shim a Julia deployment loads). See DESIGN.md / INTEGRATION.md.
 """
 from . import _lib
-from ._lib import PLB200Error, finalize, init, last_timing, launch_count
+from ._lib import PLB200Error, finalize, init, last_timing, launch_count, pinned_zeros
 from .data import (Configuration, DataSet, Energy, ForceDescriptors, Forces, LocalDescriptors, get_energy, get_force_descriptors,
                    get_forces, get_local_descriptors, get_values)
 from .dimred import (PCA, ActiveSubspace, DimensionReducer, PCAState, compute_eigen, covariance, fit, fit_, project, select_eigendirections,

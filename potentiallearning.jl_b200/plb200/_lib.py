@@ -33,6 +33,8 @@ PROTOTYPES = {
     "pl_workspace_bytes": (_i64, []),
     "pl_set_profiling": (_int, [_int]),
     "pl_last_main_kernel_ms": (_int, [_dp]),
+    "pl_host_alloc": (_vp, [_i64]),
+    "pl_host_free": (_int, [_vp]),
     "pl_gram_part": (_int, [_int, _dp, _i64, _i64, _i64, _int, _int, _dp, _dbl, _dbl, _int, _int, _dp]),
     "pl_gram_dot": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _i64, _int]),
     "pl_gram_rbf": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _dbl, _dbl, _dp, _i64, _int]),
@@ -154,3 +156,20 @@ def dptr(a: np.ndarray | None):
 
 def as_f64(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def pinned_zeros(shape):
+    """zeros(shape) in pinned host memory owned by the library (pl_host_alloc): results land there at the PCIe rate. The array keeps
+    its allocation alive; it is returned to the driver when the array (and every view of it) is garbage collected."""
+    import weakref
+
+    n = int(np.prod(shape))
+    lib_ = lib()
+    ptr = lib_.pl_host_alloc(max(n, 1) * 8)
+    if not ptr:
+        raise PLB200Error(f"pl_host_alloc failed: {last_error()}")
+    buf = (ctypes.c_double * max(n, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
+    weakref.finalize(buf, lib_.pl_host_free, ptr)
+    return arr
+

@@ -1229,3 +1229,19 @@ def test_degenerate_inputs_propagate_like_the_reference(pl, orc):
     Xn[5, 3] = np.nan
     Kn = np.asarray(pl.KernelMatrix(Xn, pl.DotProduct()))
     assert np.isnan(Kn[5]).all() and np.isnan(Kn[:, 5]).all() and not np.isnan(np.delete(np.delete(Kn, 5, 0), 5, 1)).any()
+
+
+def test_pinned_result_buffer_reuse(pl, orc):
+    """KernelMatrix(F, k, out=pinned_zeros(...)): a caller-owned pinned result buffer reused across calls gives the same matrix."""
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((300, 12)) * 0.5 + 1.0
+    buf = pl.pinned_zeros((300, 300))
+    assert buf.shape == (300, 300) and not buf.any()
+    K1 = pl.KernelMatrix(X, pl.RBF(pl.Euclidean(12)), out=buf)
+    ref = np.asarray(pl.KernelMatrix(X, pl.RBF(pl.Euclidean(12))))
+    assert np.array_equal(np.asarray(K1), ref)
+    K2 = pl.KernelMatrix(X[::-1].copy(), pl.DotProduct(), out=buf)  # reuse: the buffer is re-zeroed, no stale triangle survives
+    assert np.array_equal(np.asarray(K2), np.asarray(pl.KernelMatrix(X[::-1].copy(), pl.DotProduct())))
+    with pytest.raises(ValueError):
+        pl.KernelMatrix(X, pl.DotProduct(), out=np.zeros((5, 5)))
+    del K1, K2, buf
