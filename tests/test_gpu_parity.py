@@ -1245,3 +1245,19 @@ def test_pinned_result_buffer_reuse(pl, orc):
     with pytest.raises(ValueError):
         pl.KernelMatrix(X, pl.DotProduct(), out=np.zeros((5, 5)))
     del K1, K2, buf
+
+
+def test_example_workflow_runs_end_to_end(pl):
+    """examples/dpp_subsample_fit_pca.py: the reference examples' workflow (kDPP subsample -> learn! -> predictions -> PCAState
+    fit!/transform!) on synthetic descriptors; the linear model must be recovered from the DPP subset."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "dpp_subsample_fit_pca.py")
+    spec = importlib.util.spec_from_file_location("example_workflow", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r = mod.main(n=300, natoms=8, K=12, batch=40, verbose=False)
+    assert len(set(r["subset"])) == 40 and abs(r["inclusion_sum"] - 40.0) < 1e-6
+    assert r["beta_err"] < 1e-2 and r["e_mae"] < 1e-2 and r["f_mae"] < 1e-2
+    assert r["pca_dim"] == 8 and 0.0 < r["var_kept"] <= 1.0
