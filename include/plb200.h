@@ -193,6 +193,13 @@ int pl_ell_inclusion_prob(double alpha_scale, int64_t n, double* p);
  * cross PCIe instead of n*n. */
 int pl_ell_eigvecs(const int64_t* idx, int64_t m, int64_t n, double* V, int64_t ldv);
 
+/* Second phase of a k-DPP draw on the resident ensemble (Determinantal.sample, dpp.jl:51 [external]; Kulesza & Taskar 2012 Alg. 1 in its
+ * O(n m^2) Gram-Schmidt form): projection-DPP sampling over the m eigenvectors eig_idx selected by the first phase (elementary symmetric
+ * polynomials, on the host). uniforms: m numbers in [0, 1) from the CALLER's generator (the RNG stays in Julia / numpy), one per step.
+ * items: the m selected item indices (0-based, in draw order). U never leaves the device; config-2 size (n = 20 000) draws thousands of
+ * items in seconds where the host algorithm needs n x m^2 flops on one core. */
+int pl_ell_sample(const int64_t* eig_idx, int64_t m, int64_t n, const double* uniforms, int64_t* items);
+
 /* ---- predictions of the fitted linear model ("next" row f3 of SURVEY.md 8f) ------------------------------ */
 /* y[r] = A[r,:] . beta + (r < n_energy_rows ? beta0 : 0) over the same packed rows as pl_normal_eq: what
  * get_all_energies(ds, lb) / get_all_forces(ds, lb) (src/Data/utils.jl:42-65) evaluate after learn! (B.beta + beta0, dB.beta). */

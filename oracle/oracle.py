@@ -534,3 +534,32 @@ def compute_divergence_ksd(x, score, k: RBF) -> float:
             ksd += m * (sks + sk + ks + trk) / (N * (N - 1.0))
     return float(ksd)
 
+
+def sample_projection_dpp(V, uniforms):
+    """Projection-DPP sampling over the orthonormal columns of V (n x m) with caller-supplied uniforms, one per step — the O(n m^2)
+    Gram-Schmidt form of Kulesza & Taskar (2012) Alg. 1 that Determinantal.jl's sample_pdpp implements (Determinantal.jl is an external
+    dependency of the reference, version unpinned; restated from the published algorithm). Inverse-CDF item choice: the first j with
+    cumsum(p)[j] > u * sum(p). Returns the items in draw order."""
+    V = np.asarray(V, dtype=np.float64)
+    n, m = V.shape
+    p = np.sum(V * V, axis=1)
+    F = np.zeros((m, 0))
+    items = []
+    for i in range(m):
+        pc = np.maximum(p, 0.0)
+        cs = np.cumsum(pc)
+        target = uniforms[i] * cs[-1]
+        cand = np.nonzero((cs > target) & (pc > 0.0))[0]
+        item = int(cand[0]) if len(cand) else int(np.nonzero(pc > 0.0)[0][-1])
+        items.append(item)
+        f = V[item, :].copy()
+        for _ in range(2):
+            f = f - F @ (F.T @ f)
+        f = f / np.sqrt(f @ f)
+        F = np.hstack([F, f[:, None]])
+        t = V @ f
+        p = p - t * t
+        p[p < 0.0] = 0.0
+        p[item] = 0.0
+    return items
+

@@ -106,6 +106,12 @@ enum WsSlot {
   WS_COV_Z,
   WS_COV_RHO,
   WS_COV_DELTA,
+  WS_DPP_P,
+  WS_DPP_F,
+  WS_DPP_VEC,
+  WS_DPP_TMP,
+  WS_DPP_ITEMS,
+  WS_DPP_U,
   WS_NSLOTS
 };
 
@@ -1782,6 +1788,81 @@ int pl_host_free(void* p) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!p) return PL_OK;
   CUDA_TRY(cudaFreeHost(p));
+  return PL_OK;
+}
+
+
+int pl_ell_sample(const int64_t* eig_idx, int64_t m, int64_t n, const double* uniforms, int64_t* items) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!ell_state.valid) return set_err(PL_EINVAL, "no resident L-ensemble: call pl_ell_ensemble first");
+  if (n != ell_state.n || m < 0 || m > n || (m > 0 && (!eig_idx || !uniforms || !items))) return set_err(PL_EINVAL, "bad arguments");
+  if (m == 0) return PL_OK;
+  for (int64_t r = 0; r < m; ++r) {
+    if (eig_idx[r] < 0 || eig_idx[r] >= n) return set_err(PL_EINVAL, "eigenvector index %lld out of range", (long long)eig_idx[r]);
+    if (!(uniforms[r] >= 0.0 && uniforms[r] < 1.0)) return set_err(PL_EINVAL, "uniforms must lie in [0, 1)");
+  }
+  CUDA_TRY(cudaSetDevice(g.device));
+  cudaStream_t st = g.stream;
+  void *didx, *dVt, *dp, *dF, *dvec, *dtmp, *ditems, *du;
+  PL_TRY(ws_get(WS_EIG_IDX, (size_t)m * 8, &didx));
+  PL_TRY(ws_get(WS_EIG_SEL, (size_t)m * n * 8, &dVt));
+  PL_TRY(ws_get(WS_DPP_P, (size_t)n * 8, &dp));
+  PL_TRY(ws_get(WS_DPP_F, (size_t)m * m * 8, &dF));
+  PL_TRY(ws_get(WS_DPP_VEC, (size_t)2 * m * 8, &dvec));
+  int nslices = (int)((m + 511) / 512);  // enough blocks in flight for the pass over Vt: (n / 128) x nslices
+  if (nslices > 16) nslices = 16;
+  const int64_t kslice = (m + nslices - 1) / nslices;
+  PL_TRY(ws_get(WS_DPP_TMP, (size_t)nslices * n * 8, &dtmp));
+  PL_TRY(ws_get(WS_DPP_ITEMS, (size_t)m * 8, &ditems));
+  PL_TRY(ws_get(WS_DPP_U, (size_t)m * 8, &du));
+  double* v = (double*)dvec;
+  double* c = v + m;
+  CUDA_TRY(cudaEventRecord(g.ev[0], st));
+  CUDA_TRY(cudaMemcpyAsync(didx, eig_idx, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(du, uniforms, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(ditems, 0xff, (size_t)m * 8, st));  // -1: "no item picked" stays visible
+  CUDA_TRY(cudaEventRecord(g.ev[1], st));
+  {  // Vt = the selected rows of the resident eigenvector matrix (m x n, dense)
+    int64_t rem = m, done = 0;
+    while (rem > 0) {
+      const int64_t take = rem < 32768 ? rem : 32768;
+      dim3 grid((unsigned)((n + 1023) / 1024 < 8 ? (n + 1023) / 1024 : 8), (unsigned)take);
+      gather_rows_kernel<<<grid, 256, 0, st>>>((const double*)g.ws[WS_EIG_A], n, ell_state.ld, (const int64_t*)didx + done, take, (double*)dVt + done * n);
+      LAUNCH_CHECK();
+      rem -= take;
+      done += take;
+    }
+  }
+  const unsigned nb = (unsigned)((n + 127) / 128), mb = (unsigned)((m + 127) / 128);
+  dpp_init_p_kernel<<<nb, 128, 0, st>>>((const double*)dVt, m, n, (double*)dp);
+  LAUNCH_CHECK();
+  for (int64_t i = 0; i < m; ++i) {
+    dpp_pick_kernel<<<1, 1024, 0, st>>>((const double*)dp, n, (const double*)du, i, (int64_t*)ditems);
+    LAUNCH_CHECK();
+    dpp_gather_v_kernel<<<mb, 128, 0, st>>>((const double*)dVt, m, n, (const int64_t*)ditems, i, v);
+    LAUNCH_CHECK();
+    if (i > 0) {
+      for (int pass = 0; pass < 2; ++pass) {  // classical Gram-Schmidt, twice (keeps F orthonormal to rounding for thousands of steps)
+        dpp_rowdots_kernel<<<(unsigned)((i * 32 + 255) / 256), 256, 0, st>>>((const double*)dF, i, m, v, c);
+        LAUNCH_CHECK();
+        dpp_subtract_kernel<<<mb, 128, 0, st>>>((const double*)dF, i, m, c, v);
+        LAUNCH_CHECK();
+      }
+    }
+    dpp_normalise_kernel<<<1, 1024, 0, st>>>(v, m, (double*)dF + i * m);
+    LAUNCH_CHECK();
+    dpp_update_partial_kernel<<<dim3(nb, (unsigned)nslices), 128, 0, st>>>((const double*)dVt, m, n, (const double*)dF + i * m, kslice, (double*)dtmp);
+    LAUNCH_CHECK();
+    dpp_update_finish_kernel<<<nb, 128, 0, st>>>((const double*)dtmp, nslices, n, (const int64_t*)ditems, i, (double*)dp);
+    LAUNCH_CHECK();
+  }
+  CUDA_TRY(cudaEventRecord(g.ev[2], st));
+  CUDA_TRY(cudaMemcpyAsync(items, ditems, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(g.ev[3], st));
+  PL_TRY(finish_timing());
+  for (int64_t r = 0; r < m; ++r)
+    if (items[r] < 0) return set_err(PL_ECUDA, "k-DPP draw: step %lld found no admissible item (the selected eigenvectors are rank deficient)", (long long)r);
   return PL_OK;
 }
 

@@ -519,4 +519,139 @@ __global__ void axpy1_kernel(const double* __restrict__ a, const double* __restr
   if (i < count) out[i] = a[i] + b[i];
 }
 
+// ---- projection-DPP sampling over the selected eigenvectors of the resident L-ensemble (second phase of a k-DPP draw) ----
+// Kulesza & Taskar 2012, Alg. 1 in its O(n m^2) Gram-Schmidt form (what Determinantal.jl's sample_pdpp does): with V the n x m matrix of
+// the selected eigenvectors (stored transposed: Vt is m x n, row k = eigenvector k) and p_j = |V_j|^2,
+//   repeat m times:  item ~ p / sum(p);  v = V[item, :];  f = v - F F'v (F = the orthonormal directions chosen so far);
+//                    f /= |f|;  p_j -= (V_j . f)^2.
+// The uniforms come from the caller (the RNG stays in Julia / numpy); every step is a handful of small kernels plus one pass over Vt,
+// enqueued without host synchronisation (the picked item lives in device memory).
+__global__ void dpp_init_p_kernel(const double* __restrict__ Vt, int64_t m, int64_t n, double* __restrict__ p) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double s0 = 0.0, s1 = 0.0;
+  int64_t k = 0;
+  for (; k + 2 <= m; k += 2) {
+    const double a = Vt[k * n + j], b = Vt[(k + 1) * n + j];
+    s0 = fma(a, a, s0);
+    s1 = fma(b, b, s1);
+  }
+  if (k < m) s0 = fma(Vt[k * n + j], Vt[k * n + j], s0);
+  p[j] = s0 + s1;
+}
+
+// one block: item = the first j with cumsum(p)[j] > u * sum(p) (inverse CDF; deterministic chunked scan)
+__global__ void dpp_pick_kernel(const double* __restrict__ p, int64_t n, const double* __restrict__ uniforms, int64_t step, int64_t* __restrict__ items) {
+  __shared__ double part[1024];
+  __shared__ double total_sh;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int64_t chunk = (n + nt - 1) / nt;
+  const int64_t j0 = (int64_t)tid * chunk, j1 = j0 + chunk < n ? j0 + chunk : n;
+  double s = 0.0;
+  for (int64_t j = j0; j < j1; ++j) s += p[j] > 0.0 ? p[j] : 0.0;
+  part[tid] = s;
+  __syncthreads();
+  if (tid == 0) {  // exclusive prefix over the (<= 1024) chunk sums: sequential, negligible next to the pass over Vt
+    double run = 0.0;
+    for (int k = 0; k < nt; ++k) {
+      const double x = part[k];
+      part[k] = run;
+      run += x;
+    }
+    total_sh = run;
+  }
+  __syncthreads();
+  const double target = uniforms[step] * total_sh;
+  const double lo = part[tid], hi = lo + s;
+  const bool last_nonempty = (hi >= total_sh) && (s > 0.0);  // guards u -> 1 against rounding
+  if ((target >= lo && target < hi) || (last_nonempty && target >= hi)) {
+    double run = lo;
+    int64_t pick = -1;
+    for (int64_t j = j0; j < j1; ++j) {
+      const double x = p[j] > 0.0 ? p[j] : 0.0;
+      if (x > 0.0) pick = j;  // remember the last admissible item of the chunk
+      run += x;
+      if (run > target && x > 0.0) {
+        pick = j;
+        break;
+      }
+    }
+    if (pick >= 0) items[step] = pick;
+  }
+}
+
+// v[k] = Vt[k][item]
+__global__ void dpp_gather_v_kernel(const double* __restrict__ Vt, int64_t m, int64_t n, const int64_t* __restrict__ items, int64_t step, double* __restrict__ v) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < m) v[k] = Vt[k * n + items[step]];
+}
+// c[j] = Ft[j][:] . x for j < rows (one warp per row)
+__global__ void dpp_rowdots_kernel(const double* __restrict__ Ft, int64_t rows, int64_t m, const double* __restrict__ x, double* __restrict__ c) {
+  const int lane = threadIdx.x & 31;
+  const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= rows) return;
+  double acc = 0.0;
+  for (int64_t k = lane; k < m; k += 32) acc = fma(Ft[j * m + k], x[k], acc);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) c[j] = acc;
+}
+// x[k] -= sum_{j < rows} c[j] Ft[j][k]
+__global__ void dpp_subtract_kernel(const double* __restrict__ Ft, int64_t rows, int64_t m, const double* __restrict__ c, double* __restrict__ x) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  double s0 = 0.0, s1 = 0.0;
+  int64_t j = 0;
+  for (; j + 2 <= rows; j += 2) {
+    s0 = fma(c[j], Ft[j * m + k], s0);
+    s1 = fma(c[j + 1], Ft[(j + 1) * m + k], s1);
+  }
+  if (j < rows) s0 = fma(c[j], Ft[j * m + k], s0);
+  x[k] -= s0 + s1;
+}
+// Ft[step][:] = x / |x|  (one block)
+__global__ void dpp_normalise_kernel(const double* __restrict__ x, int64_t m, double* __restrict__ Frow) {
+  __shared__ double sh[1024];
+  double a = 0.0;
+  for (int64_t k = threadIdx.x; k < m; k += blockDim.x) a = fma(x[k], x[k], a);
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  const double inv = sh[0] > 0.0 ? 1.0 / sqrt(sh[0]) : 0.0;
+  for (int64_t k = threadIdx.x; k < m; k += blockDim.x) Frow[k] = x[k] * inv;
+}
+// p_j -= (sum_k Vt[k][j] f[k])^2, the picked item gets exactly 0. blockIdx.y slices the k range; slices > 0 accumulate into `tmp`
+// with a second tiny kernel only when the range is split (nslices > 1).
+__global__ void dpp_update_partial_kernel(const double* __restrict__ Vt, int64_t m, int64_t n, const double* __restrict__ f, int64_t kslice,
+                                          double* __restrict__ tmp) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int64_t k0 = (int64_t)blockIdx.y * kslice;
+  int64_t k1 = k0 + kslice;
+  if (k1 > m) k1 = m;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int64_t k = k0;
+  for (; k + 4 <= k1; k += 4) {
+    s0 = fma(__ldg(Vt + k * n + j), f[k], s0);
+    s1 = fma(__ldg(Vt + (k + 1) * n + j), f[k + 1], s1);
+    s2 = fma(__ldg(Vt + (k + 2) * n + j), f[k + 2], s2);
+    s3 = fma(__ldg(Vt + (k + 3) * n + j), f[k + 3], s3);
+  }
+  for (; k < k1; ++k) s0 = fma(__ldg(Vt + k * n + j), f[k], s0);
+  tmp[(int64_t)blockIdx.y * n + j] = (s0 + s1) + (s2 + s3);
+}
+__global__ void dpp_update_finish_kernel(const double* __restrict__ tmp, int nslices, int64_t n, const int64_t* __restrict__ items, int64_t step,
+                                         double* __restrict__ p) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double t = 0.0;
+  for (int s = 0; s < nslices; ++s) t += tmp[(int64_t)s * n + j];
+  double q = fma(-t, t, p[j]);
+  if (q < 0.0 || j == items[step]) q = 0.0;
+  p[j] = q;
+}
+
 }  // namespace plb

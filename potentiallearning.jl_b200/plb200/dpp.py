@@ -177,7 +177,9 @@ def _log_esp(lam, k):
 
 
 def sample(ell: EllEnsemble, k: int, rng=None):
-    """Determinantal.sample(L, k): exact k-DPP sample (Kulesza & Taskar Alg. 8 + Alg. 1). Returns sorted 0-based indices."""
+    """Determinantal.sample(L, k): exact k-DPP sample (Kulesza & Taskar Alg. 8 + Alg. 1). Returns sorted 0-based indices.
+    Phase 1 (which eigenvectors: elementary symmetric polynomials, O(N k)) runs on the host; phase 2 (projection-DPP sampling over
+    them, O(N k^2)) runs on the device for a resident ensemble (pl_ell_sample) and in numpy otherwise."""
     rng = np.random.default_rng() if rng is None else rng
     lam = np.maximum(ell.α * ell.λ, 0.0)
     N = len(lam)
@@ -195,6 +197,16 @@ def sample(ell: EllEnsemble, k: int, rng=None):
         if np.log(rng.random()) < logp:
             J.append(n - 1)
             l -= 1
+    if ell._resident and _resident_owner is ell and len(J) > 0:
+        # second phase on the device (pl_ell_sample): U stays where it is, the uniforms come from this generator
+        import ctypes
+
+        Jarr = np.ascontiguousarray(J, dtype=np.int64)
+        u = np.ascontiguousarray(rng.random(len(J)))
+        out = np.empty(len(J), dtype=np.int64)
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        _lib.check(_lib.lib().pl_ell_sample(Jarr.ctypes.data_as(i64p), len(J), N, _lib.dptr(u), out.ctypes.data_as(i64p)), "pl_ell_sample")
+        return sorted(int(i) for i in out)
     V = ell.eigvecs(J)
     items = []
     for _ in range(len(J)):

@@ -34,7 +34,7 @@ def timeit(fn, warm=2, reps=5):
     return min(ts), float(np.median(ts))
 
 
-which = sys.argv[1:] or ["feat", "neq", "eig", "proj"]
+which = sys.argv[1:] or ["feat", "neq", "eig", "proj", "dpp"]
 
 if "feat" in which:
     # config-2 shape: 20 000 configurations x 96 atoms x 300 descriptors = 4.6 GB of local descriptors
@@ -131,6 +131,24 @@ if "proj" in which:
         out[f"project_{Rp}x{Kp}_p{pdim}"] = {"ms": best, "read_GBs": Rp * Kp * 8 / best / 1e6, "tflops": 2.0 * Rp * Kp * pdim / best / 1e9,
                                              "max_abs_err_4096_rows": float((Yd[:4096] - ref).abs().max())}
     del Xd
+
+if "dpp" in which:
+    # kDPP end to end at config-2 size: features -> RBF kernel matrix -> eigendecomposition (device) -> rescale -> k-DPP draw
+    n = 20000
+    rng = np.random.default_rng(n)
+    X = rng.standard_normal((n, 300)) / np.sqrt(96) + rng.standard_normal(300)
+    t0 = time.perf_counter()
+    ell = plb200.EllEnsemble.from_features(X, plb200.RBF(plb200.Euclidean(300)), keep_L=False)
+    rec = {"ell_ensemble_ms": (time.perf_counter() - t0) * 1e3}
+    for k in [int(x) for x in os.environ.get("PLB_DPP_K", "500,2000").split(",")]:
+        t0 = time.perf_counter()
+        plb200.rescale_(ell, k)
+        t1 = time.perf_counter()
+        items = plb200.sample(ell, k, rng=np.random.default_rng(1))
+        t2 = time.perf_counter()
+        rec[f"k{k}"] = {"rescale_ms": (t1 - t0) * 1e3, "sample_ms": (t2 - t1) * 1e3, "device_ms": plb200.last_timing()["kernel_ms"],
+                        "distinct": len(set(items)) == k}
+    out["kdpp_n20000"] = rec
 
 out["launches"] = plb200.launch_count()
 print(json.dumps(out))

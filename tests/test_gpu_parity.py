@@ -1261,3 +1261,57 @@ def test_example_workflow_runs_end_to_end(pl):
     assert len(set(r["subset"])) == 40 and abs(r["inclusion_sum"] - 40.0) < 1e-6
     assert r["beta_err"] < 1e-2 and r["e_mae"] < 1e-2 and r["f_mae"] < 1e-2
     assert r["pca_dim"] == 8 and 0.0 < r["var_kept"] <= 1.0
+
+
+def test_device_kdpp_sampler(pl, orc):
+    """pl_ell_sample: projection-DPP sampling over selected eigenvectors of the resident ensemble. (a) With the same eigenvectors and
+    the same uniforms it picks exactly the items of the numpy restatement of the algorithm; (b) the empirical inclusion frequencies of
+    many k-DPP draws match the exact inclusion probabilities of the k-DPP... of the L-ensemble rescaled to expected size k, within
+    sampling error; (c) a draw has k distinct items."""
+    import ctypes
+
+    from plb200 import _lib
+
+    rng = np.random.default_rng(101)
+    n, d = 300, 10
+    X = rng.standard_normal((n, d)) * 0.6 + rng.standard_normal(d)
+    ell = pl.EllEnsemble.from_features(X, pl.RBF(pl.Euclidean(d), ell=2.0))
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    for m in (1, 7, 40):
+        J = np.sort(rng.choice(np.arange(n - 80, n), size=m, replace=False)).astype(np.int64)  # among the 80 largest eigenvalues
+        u = rng.random(m)
+        out = np.empty(m, dtype=np.int64)
+        _lib.check(_lib.lib().pl_ell_sample(J.ctypes.data_as(i64p), m, n, _lib.dptr(u), out.ctypes.data_as(i64p)), "pl_ell_sample")
+        V = ell.eigvecs(J)  # the same device-resident eigenvectors, downloaded
+        ref = orc.sample_projection_dpp(V, u)
+        assert list(out) == ref, (m, list(out), ref)
+        assert len(set(out.tolist())) == m
+    # statistics of full k-DPP draws through the mirror (phase 1 on the host, phase 2 on the device)
+    n2, k = 40, 6
+    X2 = rng.standard_normal((n2, 5)) + 1.0
+    ell2 = pl.EllEnsemble.from_features(X2, pl.RBF(pl.Euclidean(5), ell=1.5))
+    assert ell2._resident
+    r = np.random.default_rng(5)
+    ndraw = 3000
+    cnt = np.zeros(n2)
+    for _ in range(ndraw):
+        s = pl.sample(ell2, k, rng=r)
+        assert len(s) == k and len(set(s)) == k
+        cnt[s] += 1
+    # exact k-DPP inclusion probabilities: P(i in S) = sum_j U_ij^2 * lam_j e_{k-1}(lam without j) / e_k(lam)
+    lam = ell2.λ
+    U = ell2.eigvecs(np.arange(n2))
+
+    def esp(vals, kk):
+        e = np.zeros(kk + 1)
+        e[0] = 1.0
+        for x in vals:
+            e[1:] = e[1:] + x * e[:-1]
+        return e[kk]
+
+    ek = esp(lam, k)
+    w = np.array([lam[j] * esp(np.delete(lam, j), k - 1) / ek for j in range(n2)])
+    pin = (U * U) @ w
+    assert abs(pin.sum() - k) < 1e-8
+    se = np.sqrt(pin * (1 - pin) / ndraw)
+    assert np.all(np.abs(cnt / ndraw - pin) < 5 * se + 1e-3), float(np.max(np.abs(cnt / ndraw - pin) / se))
