@@ -195,6 +195,14 @@ ell_inclusion_prob(α::Real, n::Integer) = (p = zeros(n);
 ell_eigvecs(idx::Vector{Int64}, n::Integer) = (V = zeros(n, length(idx));                # 0-based eigenvector indices; column j = U[:, idx[j]+1]
     check(ccall((:pl_ell_eigvecs, libplb200), Cint, (Ptr{Int64}, Int64, Int64, Ptr{Cdouble}, Int64), idx, length(idx), n, V, n), "pl_ell_eigvecs"); V)
 
+# second phase of a k-DPP draw on the resident ensemble: projection-DPP sampling over the eigenvectors `idx` (0-based) that the first phase
+# (Determinantal's ESP selection) picked; the uniforms come from the caller's RNG: `ell_sample(idx, n, rand(rng, length(idx)))` -> 1-based items
+function ell_sample(idx::Vector{Int64}, n::Integer, uniforms::Vector{Float64})
+    items = zeros(Int64, length(idx))
+    check(ccall((:pl_ell_sample, libplb200), Cint, (Ptr{Int64}, Int64, Int64, Ptr{Cdouble}, Ptr{Int64}), idx, length(idx), n, uniforms, items), "pl_ell_sample")
+    items .+ 1
+end
+
 # ---- GlobalMean / GlobalSum features of a whole DataSet (features.jl:19-34, 76-78) in one segmented reduction ------------------
 function global_features(ds::DataSet, mean::Bool)
     locals = [reduce(hcat, get_values(get_local_descriptors(c))) for c in ds]            # d x natoms_i each == natoms_i rows of d
