@@ -1846,7 +1846,13 @@ int pl_ell_sample(const int64_t* eig_idx, int64_t m, int64_t n, const double* un
       for (int pass = 0; pass < 2; ++pass) {  // classical Gram-Schmidt, twice (keeps F orthonormal to rounding for thousands of steps)
         dpp_rowdots_kernel<<<(unsigned)((i * 32 + 255) / 256), 256, 0, st>>>((const double*)dF, i, m, v, c);
         LAUNCH_CHECK();
-        dpp_subtract_kernel<<<mb, 128, 0, st>>>((const double*)dF, i, m, c, v);
+        int jsl = (int)((i + 255) / 256);  // row slices of >= 256 rows, at most as many as the Vt pass uses (tmp is nslices x n >= jsl x m)
+        if (jsl > nslices) jsl = nslices;
+        if (jsl < 1) jsl = 1;
+        const int64_t jslice = (i + jsl - 1) / jsl;
+        dpp_subtract_partial_kernel<<<dim3(mb, (unsigned)jsl), 128, 0, st>>>((const double*)dF, i, m, c, jslice, (double*)dtmp);
+        LAUNCH_CHECK();
+        dpp_subtract_finish_kernel<<<mb, 128, 0, st>>>((const double*)dtmp, jsl, m, v);
         LAUNCH_CHECK();
       }
     }

@@ -596,18 +596,32 @@ __global__ void dpp_rowdots_kernel(const double* __restrict__ Ft, int64_t rows, 
   for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
   if (lane == 0) c[j] = acc;
 }
-// x[k] -= sum_{j < rows} c[j] Ft[j][k]
-__global__ void dpp_subtract_kernel(const double* __restrict__ Ft, int64_t rows, int64_t m, const double* __restrict__ c, double* __restrict__ x) {
+// x[k] -= sum_{j < rows} c[j] Ft[j][k], in two deterministic stages: blockIdx.y slices the row range (a single stage had only m / 128
+// blocks in flight and ran at a tenth of the HBM rate), partial sums go to tmp[slice][k]
+__global__ void dpp_subtract_partial_kernel(const double* __restrict__ Ft, int64_t rows, int64_t m, const double* __restrict__ c, int64_t jslice,
+                                            double* __restrict__ tmp) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m) return;
-  double s0 = 0.0, s1 = 0.0;
-  int64_t j = 0;
-  for (; j + 2 <= rows; j += 2) {
-    s0 = fma(c[j], Ft[j * m + k], s0);
-    s1 = fma(c[j + 1], Ft[(j + 1) * m + k], s1);
+  const int64_t j0 = (int64_t)blockIdx.y * jslice;
+  int64_t j1 = j0 + jslice;
+  if (j1 > rows) j1 = rows;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int64_t j = j0;
+  for (; j + 4 <= j1; j += 4) {
+    s0 = fma(c[j], __ldg(Ft + j * m + k), s0);
+    s1 = fma(c[j + 1], __ldg(Ft + (j + 1) * m + k), s1);
+    s2 = fma(c[j + 2], __ldg(Ft + (j + 2) * m + k), s2);
+    s3 = fma(c[j + 3], __ldg(Ft + (j + 3) * m + k), s3);
   }
-  if (j < rows) s0 = fma(c[j], Ft[j * m + k], s0);
-  x[k] -= s0 + s1;
+  for (; j < j1; ++j) s0 = fma(c[j], __ldg(Ft + j * m + k), s0);
+  tmp[(int64_t)blockIdx.y * m + k] = (s0 + s1) + (s2 + s3);
+}
+__global__ void dpp_subtract_finish_kernel(const double* __restrict__ tmp, int nslices, int64_t m, double* __restrict__ x) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  double t = 0.0;
+  for (int s = 0; s < nslices; ++s) t += tmp[(int64_t)s * m + k];
+  x[k] -= t;
 }
 // Ft[step][:] = x / |x|  (one block)
 __global__ void dpp_normalise_kernel(const double* __restrict__ x, int64_t m, double* __restrict__ Frow) {
