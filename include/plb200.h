@@ -200,6 +200,11 @@ int pl_ell_eigvecs(const int64_t* idx, int64_t m, int64_t n, double* V, int64_t 
  * items in seconds where the host algorithm needs n x m^2 flops on one core. */
 int pl_ell_sample(const int64_t* eig_idx, int64_t m, int64_t n, const double* uniforms, int64_t* items);
 
+/* Greedy MAP of the resident ensemble (Determinantal.greedy_subset, dpp.jl:60 [external]): k items, each maximising the conditional
+ * variance given the ones before (fast greedy form: one row of K and a rank-t correction per step, O(n k^2) in total). The kernel matrix
+ * is kept on the device next to its eigenvectors for n <= 32768. items[t] = -1 from the step at which the numerical rank is exhausted. */
+int pl_ell_greedy(int64_t k, int64_t n, int64_t* items);
+
 /* ---- predictions of the fitted linear model ("next" row f3 of SURVEY.md 8f) ------------------------------ */
 /* y[r] = A[r,:] . beta + (r < n_energy_rows ? beta0 : 0) over the same packed rows as pl_normal_eq: what
  * get_all_energies(ds, lb) / get_all_forces(ds, lb) (src/Data/utils.jl:42-65) evaluate after learn! (B.beta + beta0, dB.beta). */

@@ -563,3 +563,23 @@ def sample_projection_dpp(V, uniforms):
         p[item] = 0.0
     return items
 
+
+def greedy_map(L, k):
+    """Greedy MAP of an L-ensemble (Determinantal.greedy_subset, called at src/SubsetSelection/dpp.jl:60; external dependency, restated
+    from the published fast greedy algorithm of Chen, Zhang & Zhou 2018): at each step the item with the largest conditional variance."""
+    L = np.asarray(L, dtype=np.float64)
+    n = L.shape[0]
+    d = np.diag(L).copy()
+    C = np.zeros((k, n))
+    chosen = []
+    for t in range(k):
+        j = int(np.argmax(d))
+        if d[j] <= 0:
+            break
+        chosen.append(j)
+        e = (L[j, :] - C[:t, j] @ C[:t, :]) / np.sqrt(d[j])
+        C[t, :] = e
+        d = d - e * e
+        d[chosen] = -np.inf
+    return chosen
+

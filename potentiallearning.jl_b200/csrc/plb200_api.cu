@@ -112,6 +112,7 @@ enum WsSlot {
   WS_DPP_TMP,
   WS_DPP_ITEMS,
   WS_DPP_U,
+  WS_ELL_K,
   WS_NSLOTS
 };
 
@@ -877,6 +878,7 @@ int eigh_dev_impl(double* dA, int64_t n, int64_t lda, int fill, int want_vectors
 struct EllState {
   int64_t n = 0, ld = 0;
   bool valid = false;
+  bool has_kernel = false;  // a full symmetric copy of the kernel matrix is kept next to its eigenvectors (greedy MAP needs rows of K)
 } ell_state;
 
 int inclusion_prob_dev_impl(const double* dV, int64_t nvec, int64_t n, int64_t ldv, const double* dgamma, double* dp, cudaStream_t st) {
@@ -1492,6 +1494,14 @@ int pl_ell_ensemble(int kernel_id, const double* X, int64_t n, int64_t d, int64_
   CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
   // K = KernelMatrix(F, k) (dpp.jl:25,40) in the Symmetric(:U) storage, straight into the eigensolver's buffer
   PL_TRY(gram_dev_impl(kernel_id, dX, n, ld, nullptr, 0, 0, d, alpha, cinv_kind, dc, ell, beta, (double*)dA, ldo, PL_FILL_JULIA_U, 0, 1, 0, g.stream));
+  // a copy of the (triangle) storage is kept for pl_ell_greedy, which needs rows of K, up to n = 32768 (8.6 GB)
+  ell_state.has_kernel = false;
+  if (n <= 32768) {
+    void* dKk;
+    PL_TRY(ws_get(WS_ELL_K, (size_t)n * ldo * 8, &dKk));
+    CUDA_TRY(cudaMemcpyAsync(dKk, dA, (size_t)n * ldo * 8, cudaMemcpyDeviceToDevice, g.stream));
+    ell_state.has_kernel = true;
+  }
   if (Kout) {  // the caller also wants K itself (kDPP keeps it as ell.L): triangle rows, before the solver overwrites the buffer
     for (int64_t r0 = 0; r0 < n; r0 += GRAM_BM) {
       const int64_t r1 = r0 + GRAM_BM < n ? r0 + GRAM_BM : n;
@@ -1870,6 +1880,58 @@ int pl_ell_sample(const int64_t* eig_idx, int64_t m, int64_t n, const double* un
   for (int64_t r = 0; r < m; ++r)
     if (items[r] < 0) return set_err(PL_ECUDA, "k-DPP draw: step %lld found no admissible item (the selected eigenvectors are rank deficient)", (long long)r);
   return PL_OK;
+}
+
+
+int pl_ell_greedy(int64_t k, int64_t n, int64_t* items) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!ell_state.valid) return set_err(PL_EINVAL, "no resident L-ensemble: call pl_ell_ensemble first");
+  if (!ell_state.has_kernel) return set_err(PL_EINVAL, "the kernel matrix of this ensemble was not kept on the device (n > 32768)");
+  if (n != ell_state.n || k < 0 || k > n || (k > 0 && !items)) return set_err(PL_EINVAL, "bad arguments");
+  if (k == 0) return PL_OK;
+  CUDA_TRY(cudaSetDevice(g.device));
+  cudaStream_t st = g.stream;
+  const double* K = (const double*)g.ws[WS_ELL_K];
+  const int64_t ld = ell_state.ld;
+  void *dd, *dC, *dcj, *dtmp, *ditems;
+  PL_TRY(ws_get(WS_DPP_P, (size_t)n * 8, &dd));
+  PL_TRY(ws_get(WS_EIG_SEL, (size_t)k * n * 8, &dC));
+  PL_TRY(ws_get(WS_DPP_VEC, (size_t)2 * (k > n ? k : n) * 8, &dcj));
+  int nslices = (int)((k + 255) / 256);
+  if (nslices > 16) nslices = 16;
+  PL_TRY(ws_get(WS_DPP_TMP, (size_t)nslices * n * 8, &dtmp));
+  PL_TRY(ws_get(WS_DPP_ITEMS, (size_t)k * 8, &ditems));
+  CUDA_TRY(cudaEventRecord(g.ev[0], st));
+  CUDA_TRY(cudaMemsetAsync(ditems, 0xff, (size_t)k * 8, st));
+  CUDA_TRY(cudaEventRecord(g.ev[1], st));
+  const unsigned nb = (unsigned)((n + 127) / 128);
+  greedy_init_kernel<<<nb, 128, 0, st>>>(K, n, ld, (double*)dd);
+  LAUNCH_CHECK();
+  for (int64_t t = 0; t < k; ++t) {
+    greedy_argmax_kernel<<<1, 1024, 0, st>>>((const double*)dd, n, t, (int64_t*)ditems);
+    LAUNCH_CHECK();
+    int sl = 1;
+    if (t > 0) {
+      greedy_gather_kernel<<<(unsigned)((t + 127) / 128), 128, 0, st>>>((const double*)dC, t, n, (const int64_t*)ditems, t, (double*)dcj);
+      LAUNCH_CHECK();
+      sl = (int)((t + 255) / 256);
+      if (sl > nslices) sl = nslices;
+      const int64_t sslice = (t + sl - 1) / sl;
+      greedy_dot_partial_kernel<<<dim3(nb, (unsigned)sl), 128, 0, st>>>((const double*)dC, t, n, (const double*)dcj, sslice, (double*)dtmp);
+      LAUNCH_CHECK();
+    } else {
+      CUDA_TRY(cudaMemsetAsync(dtmp, 0, (size_t)n * 8, st));
+    }
+    greedy_finish_kernel<<<nb, 128, 0, st>>>(K, n, ld, (const double*)dtmp, sl, (const int64_t*)ditems, t, (double*)dC + t * n, (double*)dd);
+    LAUNCH_CHECK();
+    greedy_retire_kernel<<<1, 32, 0, st>>>((const int64_t*)ditems, t, (double*)dd);
+    LAUNCH_CHECK();
+  }
+  CUDA_TRY(cudaEventRecord(g.ev[2], st));
+  CUDA_TRY(cudaMemcpyAsync(items, ditems, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(g.ev[3], st));
+  return finish_timing();  // items[t] == -1 from the step at which the conditional variances are exhausted (numerical rank < k)
 }
 
 }  // extern "C"

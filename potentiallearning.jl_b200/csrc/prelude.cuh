@@ -668,4 +668,83 @@ __global__ void dpp_update_finish_kernel(const double* __restrict__ tmp, int nsl
   p[j] = q;
 }
 
+// ---- greedy MAP of the L-ensemble (Determinantal.greedy_subset, dpp.jl:60 [external]; Chen et al. 2018 fast greedy form) ----
+//   d = diag(K);  repeat k times:  j = argmax d;  e = (K[j,:] - C[:t,j]' C[:t,:]) / sqrt(d_j);  C[t,:] = e;  d -= e.^2
+// K: the kernel matrix kept on the device next to its eigenvectors (row-major lower triangle = Symmetric(:U) storage, leading dimension ld). One block picks the
+// argmax (first index on ties, like argmax); the row update is the same two-stage deterministic reduction as the sampler's.
+__global__ void greedy_init_kernel(const double* __restrict__ K, int64_t n, int64_t ld, double* __restrict__ dg) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) dg[j] = K[j * ld + j];
+}
+__global__ void greedy_argmax_kernel(const double* __restrict__ dg, int64_t n, int64_t step, int64_t* __restrict__ items) {
+  __shared__ double bv[1024];
+  __shared__ int64_t bi[1024];
+  double best = -1.0e308;
+  int64_t arg = -1;
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+    const double x = dg[j];
+    if (x > best) {  // strided scan keeps the smallest index among equal values within a thread
+      best = x;
+      arg = j;
+    }
+  }
+  bv[threadIdx.x] = best;
+  bi[threadIdx.x] = arg;
+  __syncthreads();
+  for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      const double o = bv[threadIdx.x + off];
+      const int64_t oi = bi[threadIdx.x + off];
+      if (o > bv[threadIdx.x] || (o == bv[threadIdx.x] && oi >= 0 && (bi[threadIdx.x] < 0 || oi < bi[threadIdx.x]))) {
+        bv[threadIdx.x] = o;
+        bi[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) items[step] = bv[0] > 0.0 ? bi[0] : -1;  // a non-positive conditional variance: the ensemble's rank is exhausted
+}
+// cj[s] = C[s][item] for s < t
+__global__ void greedy_gather_kernel(const double* __restrict__ C, int64_t t, int64_t n, const int64_t* __restrict__ items, int64_t step, double* __restrict__ cj) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < t && items[step] >= 0) cj[s] = C[s * n + items[step]];
+}
+// tmp[slice][i] = sum_{s in slice} cj[s] C[s][i]
+__global__ void greedy_dot_partial_kernel(const double* __restrict__ C, int64_t t, int64_t n, const double* __restrict__ cj, int64_t sslice, double* __restrict__ tmp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t s0 = (int64_t)blockIdx.y * sslice;
+  int64_t s1 = s0 + sslice;
+  if (s1 > t) s1 = t;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int64_t s = s0;
+  for (; s + 4 <= s1; s += 4) {
+    a0 = fma(cj[s], __ldg(C + s * n + i), a0);
+    a1 = fma(cj[s + 1], __ldg(C + (s + 1) * n + i), a1);
+    a2 = fma(cj[s + 2], __ldg(C + (s + 2) * n + i), a2);
+    a3 = fma(cj[s + 3], __ldg(C + (s + 3) * n + i), a3);
+  }
+  for (; s < s1; ++s) a0 = fma(cj[s], __ldg(C + s * n + i), a0);
+  tmp[(int64_t)blockIdx.y * n + i] = (a0 + a1) + (a2 + a3);
+}
+// e = (K[item][:] - sum of the partial slices) / sqrt(d_item);  C[t][:] = e;  d -= e^2;  the picked item is retired (d = -inf)
+__global__ void greedy_finish_kernel(const double* __restrict__ K, int64_t n, int64_t ld, const double* __restrict__ tmp, int nslices,
+                                     const int64_t* __restrict__ items, int64_t step, double* __restrict__ Crow, double* __restrict__ dg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t item = items[step];
+  if (item < 0) return;
+  double acc = 0.0;
+  for (int s = 0; s < nslices; ++s) acc += tmp[(int64_t)s * n + i];
+  // K is held in the reference's Symmetric(:U) storage (row-major lower triangle): K[item][i] lives at [max][min]
+  const double kji = i <= item ? K[item * ld + i] : K[i * ld + item];
+  const double e = (kji - acc) / sqrt(dg[item]);
+  Crow[i] = e;
+  // (every thread reads dg[item] before any thread may overwrite it: the retire write is done by a separate launch)
+  if (i != item) dg[i] = fma(-e, e, dg[i]);
+}
+__global__ void greedy_retire_kernel(const int64_t* __restrict__ items, int64_t step, double* __restrict__ dg) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && items[step] >= 0) dg[items[step]] = -1.0e308;
+}
+
 }  // namespace plb

@@ -203,6 +203,13 @@ function ell_sample(idx::Vector{Int64}, n::Integer, uniforms::Vector{Float64})
     items .+ 1
 end
 
+# greedy MAP of the resident ensemble (Determinantal.greedy_subset, dpp.jl:60): 1-based items, shorter than k if the rank is exhausted
+function ell_greedy(k::Integer, n::Integer)
+    items = zeros(Int64, k)
+    check(ccall((:pl_ell_greedy, libplb200), Cint, (Int64, Int64, Ptr{Int64}), k, n, items), "pl_ell_greedy")
+    [i + 1 for i in items if i >= 0]
+end
+
 # ---- GlobalMean / GlobalSum features of a whole DataSet (features.jl:19-34, 76-78) in one segmented reduction ------------------
 function global_features(ds::DataSet, mean::Bool)
     locals = [reduce(hcat, get_values(get_local_descriptors(c))) for c in ds]            # d x natoms_i each == natoms_i rows of d

@@ -226,6 +226,12 @@ def sample(ell: EllEnsemble, k: int, rng=None):
 
 def greedy_subset(ell: EllEnsemble, k: int):
     """greedy_subset(L, k): greedy MAP (largest conditional variance first, Cholesky-style updates)."""
+    if ell._resident and _resident_owner is ell and ell.nitems <= 32768:
+        import ctypes
+
+        out = np.empty(k, dtype=np.int64)
+        _lib.check(_lib.lib().pl_ell_greedy(int(k), ell.nitems, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))), "pl_ell_greedy")
+        return [int(i) for i in out if i >= 0]
     L = ell.L
     N = L.shape[0]
     d = np.diag(L).astype(np.float64).copy()

@@ -148,6 +148,10 @@ if "dpp" in which:
         t2 = time.perf_counter()
         rec[f"k{k}"] = {"rescale_ms": (t1 - t0) * 1e3, "sample_ms": (t2 - t1) * 1e3, "device_ms": plb200.last_timing()["kernel_ms"],
                         "distinct": len(set(items)) == k}
+        t0 = time.perf_counter()
+        mode = plb200.greedy_subset(ell, k)
+        rec[f"k{k}"]["greedy_map_ms"] = (time.perf_counter() - t0) * 1e3
+        rec[f"k{k}"]["greedy_items"] = len(set(mode))
     out["kdpp_n20000"] = rec
 
 out["launches"] = plb200.launch_count()

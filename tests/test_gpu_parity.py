@@ -1315,3 +1315,22 @@ def test_device_kdpp_sampler(pl, orc):
     assert abs(pin.sum() - k) < 1e-8
     se = np.sqrt(pin * (1 - pin) / ndraw)
     assert np.all(np.abs(cnt / ndraw - pin) < 5 * se + 1e-3), float(np.max(np.abs(cnt / ndraw - pin) / se))
+
+
+def test_device_greedy_map(pl, orc):
+    """pl_ell_greedy (get_dpp_mode, dpp.jl:59-62): the device greedy MAP picks the items of the numpy restatement on the same kernel
+    matrix, in the same order; a rank-deficient ensemble stops at its numerical rank."""
+    rng = np.random.default_rng(55)
+    n, d = 500, 9
+    X = rng.standard_normal((n, d)) * 0.7 + rng.standard_normal(d)
+    for k in (1, 5, 60):
+        dpp = pl.kDPP(X, pl.RBF(pl.Euclidean(d), ell=1.2), batch_size=k)
+        mode = pl.get_dpp_mode(dpp)
+        ref = orc.greedy_map(dpp.K.L, k)
+        assert mode == ref and len(set(mode)) == k
+    # DotProduct(alpha = 1) of 3-dimensional features has rank 3... (x.y/|x||y|): the greedy stops when the variances are exhausted
+    X3 = rng.standard_normal((200, 3)) + 2.0
+    ell = pl.EllEnsemble.from_features(X3, pl.DotProduct(1))
+    g = pl.greedy_subset(ell, 10)
+    assert 3 <= len(g) <= 10 and len(set(g)) == len(g)
+    assert g[:3] == orc.greedy_map(ell.L, 3)
