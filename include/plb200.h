@@ -205,6 +205,14 @@ int pl_ell_sample(const int64_t* eig_idx, int64_t m, int64_t n, const double* un
  * is kept on the device next to its eigenvectors for n <= 32768. items[t] = -1 from the step at which the numerical rank is exhausted. */
 int pl_ell_greedy(int64_t k, int64_t n, int64_t* items);
 
+/* ---- DBSCAN's distance matrices between configurations (src/SubsetSelection/dbscan.jl:100-170, kabsch.jl; widened row f4) ---------- */
+/* P: n configurations x natoms x 3 atomic positions (row-major; every configuration has natoms atoms). D: n x n, symmetric, zero diagonal.
+ * pl_rmsd_periodic: distance_matrix_periodic / periodic_rmsd (minimum image in an orthorhombic box, box_lengths[3]; same operations in the
+ * same order as the reference: bit-identical). pl_rmsd_kabsch: distance_matrix_kabsch / kabsch_rmsd (centre both, optimal rotation from the
+ * 3 x 3 SVD of the covariance with the reflection check, RMSD of the superposition). One GPU thread per pair. */
+int pl_rmsd_periodic(const double* P, int64_t n, int64_t natoms, const double* box_lengths, double* D, int64_t ldd);
+int pl_rmsd_kabsch(const double* P, int64_t n, int64_t natoms, double* D, int64_t ldd);
+
 /* ---- predictions of the fitted linear model ("next" row f3 of SURVEY.md 8f) ------------------------------ */
 /* y[r] = A[r,:] . beta + (r < n_energy_rows ? beta0 : 0) over the same packed rows as pl_normal_eq: what
  * get_all_energies(ds, lb) / get_all_forces(ds, lb) (src/Data/utils.jl:42-65) evaluate after learn! (B.beta + beta0, dB.beta). */

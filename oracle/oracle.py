@@ -583,3 +583,47 @@ def greedy_map(L, k):
         d[chosen] = -np.inf
     return chosen
 
+
+# ----------------------------------------------------------------------------------------------------------------
+# DBSCAN's distance matrices (src/SubsetSelection/dbscan.jl:100-170, kabsch.jl)
+# ----------------------------------------------------------------------------------------------------------------
+def periodic_rmsd(p1, p2, box_lengths) -> float:
+    """periodic_rmsd (dbscan.jl:110-124), operation by operation: d = p1[i,:] - p2[i,:]; d .- round.(d ./ L) .* L (round half to even,
+    like Julia's round); sum += norm(d)^2 with norm = sqrt of the sequential sum of squares; sqrt(sum / n_atoms)."""
+    p1, p2, L = np.asarray(p1, dtype=np.float64), np.asarray(p2, dtype=np.float64), np.asarray(box_lengths, dtype=np.float64)
+    total = 0.0
+    for i in range(p1.shape[0]):
+        d = p1[i, :] - p2[i, :]
+        d = d - np.rint(d / L) * L
+        ss = d[0] * d[0]
+        ss = ss + d[1] * d[1]
+        ss = ss + d[2] * d[2]
+        nr = np.sqrt(ss)
+        total = total + nr * nr
+    return float(np.sqrt(total / p1.shape[0]))
+
+
+def kabsch_rmsd(P, Q) -> float:
+    """kabsch_rmsd(P, Q) = rmsd(P, kabsch(P, Q)) (kabsch.jl:91-124): centre both, A = Qc' * Pc, (u, d, v) = svd(A),
+    f = sign(det(v) * det(u)), rotated = Qc * u * diag(1, 1, f) * v' + centroid_P, sqrt(sum((P - rotated).^2) / natoms)."""
+    P, Q = np.asarray(P, dtype=np.float64), np.asarray(Q, dtype=np.float64)
+    cp, cq = P.sum(axis=0) / P.shape[0], Q.sum(axis=0) / Q.shape[0]
+    Pc, Qc = P - cp, Q - cq
+    A = Qc.T @ Pc
+    u, _, vt = np.linalg.svd(A)
+    v = vt.T
+    f = int(np.sign(np.linalg.det(v) * np.linalg.det(u)))
+    rotated = Qc @ u @ np.diag([1.0, 1.0, float(f)]) @ v.T + cp
+    return float(np.sqrt(np.sum((P - rotated) ** 2) / P.shape[0]))
+
+
+def distance_matrix(positions, box_lengths=None) -> np.ndarray:
+    """distance_matrix_periodic (dbscan.jl:132-147) if box_lengths is given, else distance_matrix_kabsch (:156-170)."""
+    n = len(positions)
+    D = np.zeros((n, n))
+    for i in range(n):
+        for j in range(i + 1, n):
+            D[i, j] = periodic_rmsd(positions[i], positions[j], box_lengths) if box_lengths is not None else kabsch_rmsd(positions[i], positions[j])
+            D[j, i] = D[i, j]
+    return D
+

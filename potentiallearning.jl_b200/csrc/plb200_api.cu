@@ -113,6 +113,9 @@ enum WsSlot {
   WS_DPP_ITEMS,
   WS_DPP_U,
   WS_ELL_K,
+  WS_POS,
+  WS_POS_C,
+  WS_POS_D,
   WS_NSLOTS
 };
 
@@ -1932,6 +1935,50 @@ int pl_ell_greedy(int64_t k, int64_t n, int64_t* items) {
   CUDA_TRY(cudaMemcpyAsync(items, ditems, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaEventRecord(g.ev[3], st));
   return finish_timing();  // items[t] == -1 from the step at which the conditional variances are exhausted (numerical rank < k)
+}
+
+
+static int rmsd_host(const double* P, int64_t n, int64_t natoms, const double* box, double* D, int64_t ldd) {
+  PL_TRY(need_ready());
+  if (!P || !D || n < 0 || natoms <= 0 || ldd < n) return set_err(PL_EINVAL, "bad arguments");
+  if (n > 65535) return set_err(PL_EINVAL, "at most 65535 configurations");
+  if (box && !(box[0] != 0.0 && box[1] != 0.0 && box[2] != 0.0)) return set_err(PL_EINVAL, "box lengths must be non-zero");
+  if (n == 0) return PL_OK;
+  CUDA_TRY(cudaSetDevice(g.device));
+  cudaStream_t st = g.stream;
+  void *dP, *dPc = nullptr, *dD;
+  const size_t pbytes = (size_t)n * natoms * 3 * 8;
+  PL_TRY(ws_get(WS_POS, pbytes, &dP));
+  PL_TRY(ws_get(WS_POS_D, (size_t)n * n * 8, &dD));
+  CUDA_TRY(cudaEventRecord(g.ev[0], st));
+  CUDA_TRY(cudaMemcpyAsync(dP, P, pbytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(g.ev[1], st));
+  dim3 grid((unsigned)((n + 127) / 128), (unsigned)n);
+  if (box) {
+    rmsd_periodic_kernel<<<grid, 128, 0, st>>>((const double*)dP, n, natoms, box[0], box[1], box[2], (double*)dD, n);
+    LAUNCH_CHECK();
+  } else {
+    PL_TRY(ws_get(WS_POS_C, pbytes, &dPc));
+    centre_positions_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const double*)dP, n, natoms, (double*)dPc);
+    LAUNCH_CHECK();
+    rmsd_kabsch_kernel<<<grid, 128, 0, st>>>((const double*)dPc, n, natoms, (double*)dD, n);
+    LAUNCH_CHECK();
+  }
+  CUDA_TRY(cudaEventRecord(g.ev[2], st));
+  CUDA_TRY(cudaMemcpy2DAsync(D, (size_t)ldd * 8, dD, (size_t)n * 8, (size_t)n * 8, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(g.ev[3], st));
+  return finish_timing();
+}
+
+int pl_rmsd_periodic(const double* P, int64_t n, int64_t natoms, const double* box_lengths, double* D, int64_t ldd) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!box_lengths) return set_err(PL_EINVAL, "box_lengths is NULL");
+  return rmsd_host(P, n, natoms, box_lengths, D, ldd);
+}
+
+int pl_rmsd_kabsch(const double* P, int64_t n, int64_t natoms, double* D, int64_t ldd) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return rmsd_host(P, n, natoms, nullptr, D, ldd);
 }
 
 }  // extern "C"

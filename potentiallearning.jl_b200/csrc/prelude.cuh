@@ -747,4 +747,142 @@ __global__ void greedy_retire_kernel(const int64_t* __restrict__ items, int64_t 
   if (threadIdx.x == 0 && blockIdx.x == 0 && items[step] >= 0) dg[items[step]] = -1.0e308;
 }
 
+// ---- DBSCAN's O(n^2) distance matrices between configurations (src/SubsetSelection/dbscan.jl:100-170, kabsch.jl; row f4) ----
+// P: n configurations x natoms x 3 positions, row-major. One thread per pair i < j; the positions (a few MB) live in L2.
+// periodic_rmsd (dbscan.jl:110-124): d = p1 - p2; d -= round(d / L) * L (minimum image, round half to even); sum += norm(d)^2;
+// sqrt(sum / natoms). Every operation is formed as the reference forms it (no fma contraction, norm then square), so the matrix is
+// bit-identical to the restatement.
+__global__ void rmsd_periodic_kernel(const double* __restrict__ P, int64_t n, int64_t natoms, double Lx, double Ly, double Lz, double* __restrict__ D,
+                                     int64_t ldd) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j >= n || j < i) return;
+  if (j == i) {
+    D[i * ldd + i] = 0.0;  // zeros(n, n): the loop runs over j > i only
+    return;
+  }
+  const double* p1 = P + i * natoms * 3;
+  const double* p2 = P + j * natoms * 3;
+  const double L[3] = {Lx, Ly, Lz};
+  double sum = 0.0;
+  for (int64_t a = 0; a < natoms; ++a) {
+    double ss = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double dd = __dsub_rn(p1[3 * a + c], p2[3 * a + c]);
+      dd = __dsub_rn(dd, __dmul_rn(rint(__ddiv_rn(dd, L[c])), L[c]));
+      ss = c == 0 ? __dmul_rn(dd, dd) : __dadd_rn(ss, __dmul_rn(dd, dd));
+    }
+    const double nr = sqrt(ss);  // norm(d)
+    sum = __dadd_rn(sum, __dmul_rn(nr, nr));
+  }
+  const double r = sqrt(__ddiv_rn(sum, (double)natoms));
+  D[i * ldd + j] = r;
+  D[j * ldd + i] = r;
+}
+
+// centred positions Pc = P - centroid (translate_points, kabsch.jl:60-77), one thread per configuration
+__global__ void centre_positions_kernel(const double* __restrict__ P, int64_t n, int64_t natoms, double* __restrict__ Pc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* p = P + i * natoms * 3;
+  double c[3] = {0.0, 0.0, 0.0};
+  for (int64_t a = 0; a < natoms; ++a)
+    for (int k = 0; k < 3; ++k) c[k] += p[3 * a + k];
+  for (int k = 0; k < 3; ++k) c[k] /= (double)natoms;
+  for (int64_t a = 0; a < natoms; ++a)
+    for (int k = 0; k < 3; ++k) Pc[i * natoms * 3 + 3 * a + k] = p[3 * a + k] - c[k];
+}
+
+// 3 x 3 SVD by one-sided Jacobi (Hestenes): rotates the columns of A until they are orthogonal, A V = U S.
+__device__ __forceinline__ void svd3(const double (&A)[3][3], double (&U)[3][3], double (&S)[3], double (&V)[3][3]) {
+  double B[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      B[r][c] = A[r][c];
+      V[r][c] = r == c ? 1.0 : 0.0;
+    }
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+        for (int r = 0; r < 3; ++r) {
+          alpha += B[r][p] * B[r][p];
+          beta += B[r][q] * B[r][q];
+          gamma += B[r][p] * B[r][q];
+        }
+        if (gamma == 0.0) continue;
+        off = fmax(off, fabs(gamma) / sqrt(alpha * beta + 1e-300));
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+        for (int r = 0; r < 3; ++r) {
+          const double bp = B[r][p], bq = B[r][q];
+          B[r][p] = cs * bp - sn * bq;
+          B[r][q] = sn * bp + cs * bq;
+          const double vp = V[r][p], vq = V[r][q];
+          V[r][p] = cs * vp - sn * vq;
+          V[r][q] = sn * vp + cs * vq;
+        }
+      }
+    if (off < 1e-16) break;
+  }
+  for (int c = 0; c < 3; ++c) S[c] = sqrt(B[0][c] * B[0][c] + B[1][c] * B[1][c] + B[2][c] * B[2][c]);
+  // order the singular values descending (only the completion of a vanishing direction below depends on it)
+  for (int a = 0; a < 2; ++a)
+    for (int b = a + 1; b < 3; ++b)
+      if (S[b] > S[a]) {
+        double tmp = S[a]; S[a] = S[b]; S[b] = tmp;
+        for (int r = 0; r < 3; ++r) {
+          tmp = B[r][a]; B[r][a] = B[r][b]; B[r][b] = tmp;
+          tmp = V[r][a]; V[r][a] = V[r][b]; V[r][b] = tmp;
+        }
+      }
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) U[r][c] = S[c] > 0.0 ? B[r][c] / S[c] : 0.0;
+  if (!(S[2] > 1e-14 * S[0])) {  // rank-deficient covariance (planar / collinear atoms): complete U with the cross product
+    U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+    U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+    U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+  }
+}
+__device__ __forceinline__ double det3(const double (&M)[3][3]) {
+  return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+         M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+}
+// kabsch_rmsd (kabsch.jl:91-124): A = Qc' Pc, (u, s, v) = svd(A), f = sign(det(v) det(u)), R = u diag(1,1,f) v', rmsd of Pc against Qc R.
+__global__ void rmsd_kabsch_kernel(const double* __restrict__ Pc, int64_t n, int64_t natoms, double* __restrict__ D, int64_t ldd) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j >= n || j < i) return;
+  if (j == i) {
+    D[i * ldd + i] = 0.0;
+    return;
+  }
+  const double* p = Pc + i * natoms * 3;  // reference (P)
+  const double* q = Pc + j * natoms * 3;  // coords (Q)
+  double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int64_t a = 0; a < natoms; ++a)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) A[r][c] = fma(q[3 * a + r], p[3 * a + c], A[r][c]);
+  double U[3][3], S[3], V[3][3];
+  svd3(A, U, S, V);
+  const double dd = det3(V) * det3(U);
+  const double f = dd > 0.0 ? 1.0 : (dd < 0.0 ? -1.0 : 0.0);
+  double R[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) R[r][c] = U[r][0] * V[c][0] + U[r][1] * V[c][1] + f * U[r][2] * V[c][2];
+  double sum = 0.0;
+  for (int64_t a = 0; a < natoms; ++a)
+    for (int c = 0; c < 3; ++c) {
+      const double rot = q[3 * a + 0] * R[0][c] + q[3 * a + 1] * R[1][c] + q[3 * a + 2] * R[2][c];
+      const double e = p[3 * a + c] - rot;
+      sum = fma(e, e, sum);
+    }
+  const double r = sqrt(sum / (double)natoms);
+  D[i * ldd + j] = r;
+  D[j * ldd + i] = r;
+}
+
 }  // namespace plb

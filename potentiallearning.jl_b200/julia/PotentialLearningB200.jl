@@ -281,4 +281,15 @@ function PotentialLearning.compute_divergence(x::Vector{Vector{Float64}}, div::P
     out[1]
 end
 
+# ---- DBSCAN's distance matrices (dbscan.jl:132-170): positions as 3 x natoms x n (column-major) == n x natoms x 3 row-major -------------
+function distance_matrix_gpu(P::Array{Float64,3}; box_lengths::Union{Nothing,Vector{Float64}} = nothing)
+    natoms, n = size(P, 2), size(P, 3); D = zeros(n, n)
+    if box_lengths === nothing
+        check(ccall((:pl_rmsd_kabsch, libplb200), Cint, (Ptr{Cdouble}, Int64, Int64, Ptr{Cdouble}, Int64), P, n, natoms, D, n), "pl_rmsd_kabsch")
+    else
+        check(ccall((:pl_rmsd_periodic, libplb200), Cint, (Ptr{Cdouble}, Int64, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Int64), P, n, natoms, box_lengths, D, n), "pl_rmsd_periodic")
+    end
+    D
+end
+
 end # module

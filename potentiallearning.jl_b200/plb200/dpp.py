@@ -293,3 +293,34 @@ def get_dpp_mode(dpp: kDPP, batch_size: int | None = None):
 def get_inclusion_prob(dpp: kDPP):
     """get_inclusion_prob(dpp) (dpp.jl:68-70)."""
     return np.asarray(inclusion_prob(dpp.K)).reshape(-1)
+
+
+# ------------------------------------------------------------------ DBSCAN's distance matrices (dbscan.jl) --------
+def _positions(positions) -> np.ndarray:
+    P = np.ascontiguousarray(np.asarray(positions, dtype=np.float64))
+    if P.ndim != 3 or P.shape[2] != 3:
+        raise ValueError("positions must be n configurations x natoms x 3 (every configuration with the same number of atoms)")
+    return P
+
+
+def distance_matrix_periodic(positions, box_lengths) -> np.ndarray:
+    """distance_matrix_periodic(ds) (dbscan.jl:132-147) on the GPU (pl_rmsd_periodic): periodic_rmsd of every pair of configurations in
+    one orthorhombic box (the reference errors if the boxes differ). positions: n x natoms x 3."""
+    P = _positions(positions)
+    L = _lib.as_f64(box_lengths)
+    if L.shape != (3,):
+        raise ValueError("box_lengths must have 3 entries")
+    n = P.shape[0]
+    D = np.zeros((n, n))
+    _lib.check(_lib.lib().pl_rmsd_periodic(_lib.dptr(P.reshape(-1)), n, P.shape[1], _lib.dptr(L), _lib.dptr(D), n), "pl_rmsd_periodic")
+    return D
+
+
+def distance_matrix_kabsch(positions) -> np.ndarray:
+    """distance_matrix_kabsch(ds) (dbscan.jl:156-170) on the GPU (pl_rmsd_kabsch): RMSD after the optimal superposition."""
+    P = _positions(positions)
+    n = P.shape[0]
+    D = np.zeros((n, n))
+    _lib.check(_lib.lib().pl_rmsd_kabsch(_lib.dptr(P.reshape(-1)), n, P.shape[1], _lib.dptr(D), n), "pl_rmsd_kabsch")
+    return D
+

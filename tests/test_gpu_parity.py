@@ -1334,3 +1334,41 @@ def test_device_greedy_map(pl, orc):
     g = pl.greedy_subset(ell, 10)
     assert 3 <= len(g) <= 10 and len(set(g)) == len(g)
     assert g[:3] == orc.greedy_map(ell.L, 3)
+
+
+def test_dbscan_distance_matrices(pl, orc):
+    """distance_matrix_periodic / distance_matrix_kabsch (dbscan.jl:132-170, kabsch.jl) on the GPU against the literal restatements:
+    the periodic form is bit-identical (same operations in the same order), the Kabsch form agrees to rounding with the LAPACK-SVD
+    evaluation, is invariant under rigid motion of either configuration, and handles planar configurations and reflections."""
+    rng = np.random.default_rng(77)
+    n, natoms = 23, 17
+    box = np.array([7.0, 8.5, 6.25])
+    base = rng.uniform(0, 1, size=(natoms, 3)) * box
+    pos = np.stack([np.mod(base + 0.4 * rng.standard_normal((natoms, 3)) + rng.uniform(-3, 3, size=3), box) for _ in range(n)])
+    D = pl.distance_matrix_periodic(pos, box)
+    Do = orc.distance_matrix(pos, box)
+    assert np.array_equal(D, Do) and np.array_equal(D, D.T) and np.all(np.diag(D) == 0.0)
+    # Kabsch: configurations = rigidly moved, noisy copies of two shapes
+    shapes = [rng.standard_normal((natoms, 3)) * 2.0, rng.standard_normal((natoms, 3)) * 2.0]
+
+    def rigid(X):
+        Q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        if np.linalg.det(Q) < 0:
+            Q[:, 0] = -Q[:, 0]
+        return X @ Q + rng.uniform(-5, 5, size=3)
+
+    pk = np.stack([rigid(shapes[i % 2] + 0.05 * rng.standard_normal((natoms, 3))) for i in range(n)])
+    Dk = pl.distance_matrix_kabsch(pk)
+    Dko = orc.distance_matrix(pk)
+    assert np.max(np.abs(Dk - Dko)) < 1e-10 * np.max(Dko) and np.array_equal(Dk, Dk.T) and np.all(np.diag(Dk) == 0.0)
+    assert Dk[0, 2] < 0.3 and Dk[0, 1] > 1.0  # same shape: only the noise is left; different shapes stay apart
+    pk2 = pk.copy()
+    pk2[5] = rigid(pk[5])
+    assert np.max(np.abs(pl.distance_matrix_kabsch(pk2) - Dk)) < 1e-9
+    # a mirror image needs the reflection guard (f = -1): the RMSD must NOT vanish; planar configurations (rank-2 covariance) work
+    mirrored = shapes[0] * np.array([1.0, 1.0, -1.0])
+    pair = np.stack([shapes[0], mirrored])
+    assert abs(pl.distance_matrix_kabsch(pair)[0, 1] - orc.kabsch_rmsd(pair[0], pair[1])) < 1e-10 and pl.distance_matrix_kabsch(pair)[0, 1] > 0.1
+    planar = rng.standard_normal((2, natoms, 3))
+    planar[:, :, 2] = 0.0
+    assert abs(pl.distance_matrix_kabsch(planar)[0, 1] - orc.kabsch_rmsd(planar[0], planar[1])) < 1e-10
