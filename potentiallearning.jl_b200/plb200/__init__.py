@@ -9,7 +9,7 @@ from .data import (Configuration, DataSet, Energy, ForceDescriptors, Forces, Loc
                    get_forces, get_local_descriptors, get_values)
 from .dimred import (PCA, ActiveSubspace, DimensionReducer, PCAState, compute_eigen, covariance, fit, fit_, project, select_eigendirections,
                      transform_)
-from .dpp import (EllEnsemble, SubsetSelector, distance_matrix_kabsch, distance_matrix_periodic, get_dpp_mode, get_inclusion_prob, get_random_subset, greedy_subset, inclusion_prob, kDPP,
+from .dpp import (DBSCANSelector, EllEnsemble, RandomSelector, SubsetSelector, distance_matrix_kabsch, distance_matrix_periodic, get_dpp_mode, get_inclusion_prob, get_random_subset, greedy_subset, inclusion_prob, kDPP,
                   rescale_, sample)
 from .kernels import (RBF, CorrelationMatrix, Diagonal, Distance, Divergence, DotProduct, KernelSteinDiscrepancy, compute_divergence, Euclidean, Feature, GlobalMean, GlobalSum, InverseMultiquadric, Kernel,
                       KernelMatrix, Symmetric,

@@ -280,8 +280,13 @@ class kDPP(SubsetSelector):
         self.K = ell
 
 
-def get_random_subset(dpp: kDPP, batch_size: int | None = None, rng=None):
-    """get_random_subset(dpp; batch_size) (dpp.jl:50-53)."""
+def get_random_subset(dpp, batch_size: int | None = None, rng=None):
+    """get_random_subset(dpp; batch_size) (dpp.jl:50-53); also dispatches on RandomSelector (random.jl:21-26) and DBSCANSelector
+    (dbscan.jl:49-55) like the generic function of the reference."""
+    if isinstance(dpp, RandomSelector):
+        return _random_subset_random(dpp, batch_size, rng)
+    if isinstance(dpp, DBSCANSelector):
+        return _random_subset_dbscan(dpp, batch_size, rng)
     return sample(dpp.K, dpp.batch_size if batch_size is None else batch_size, rng)
 
 
@@ -323,4 +328,51 @@ def distance_matrix_kabsch(positions) -> np.ndarray:
     D = np.zeros((n, n))
     _lib.check(_lib.lib().pl_rmsd_kabsch(_lib.dptr(P.reshape(-1)), n, P.shape[1], _lib.dptr(D), n), "pl_rmsd_kabsch")
     return D
+
+
+class RandomSelector(SubsetSelector):
+    """RandomSelector(num_configs; batch_size) (random.jl:1-15): a permutation sampler over 1:num_configs."""
+
+    def __init__(self, num_configs: int, batch_size=None):
+        self.num_configs = int(num_configs)
+        self.batch_size = self.num_configs if batch_size is None else int(batch_size)
+
+
+def _random_subset_random(r: RandomSelector, batch_size=None, rng=None):
+    """get_random_subset(r::RandomSelector, batch_size) (random.jl:21-26): randperm(num_configs)[1:batch_size] (0-based here)."""
+    rng = np.random.default_rng() if rng is None else rng
+    bs = r.batch_size if batch_size is None else int(batch_size)
+    if not (bs <= r.num_configs):
+        raise AssertionError("batch_size <= num_configs")
+    return [int(i) for i in rng.permutation(r.num_configs)[:bs]]
+
+
+class DBSCANSelector(SubsetSelector):
+    """DBSCANSelector(ds, eps, minpts, sample_size) (dbscan.jl:14-38). The O(n^2) distance matrix between configurations
+    (get_clusters, :83-98: periodic RMSD if the system is periodic, Kabsch RMSD otherwise) is built on the GPU; the clustering itself is
+    Clustering.jl's `dbscan` in the reference ([external]) and scikit-learn's DBSCAN on the precomputed matrix here.
+    positions: n x natoms x 3; box_lengths: the 3 box edges of a periodic system, or None."""
+
+    def __init__(self, positions, eps, minpts, sample_size, box_lengths=None):
+        from sklearn.cluster import DBSCAN
+
+        D = distance_matrix_periodic(positions, box_lengths) if box_lengths is not None else distance_matrix_kabsch(positions)
+        labels = DBSCAN(eps=float(eps), min_samples=int(minpts), metric="precomputed").fit(D).labels_
+        self.clusters = [np.nonzero(labels == c)[0].tolist() for c in range(int(labels.max()) + 1)]  # noise (label -1) belongs to no cluster
+        self.eps, self.minpts, self.sample_size = eps, minpts, int(sample_size)
+        self.distances = D
+
+
+def _random_subset_dbscan(s: DBSCANSelector, batch_size=None, rng=None):
+    """get_random_subset(s::DBSCANSelector, batch_size) (dbscan.jl:49-55): batch_size ÷ length(clusters) samples WITH replacement from
+    every cluster (`c[rand(1:length(c), batch_size)]`, :66-71)."""
+    rng = np.random.default_rng() if rng is None else rng
+    bs = s.sample_size if batch_size is None else int(batch_size)
+    if not s.clusters:
+        return []
+    per = bs // len(s.clusters)
+    out = []
+    for c in s.clusters:
+        out.extend(int(c[i]) for i in rng.integers(0, len(c), size=per))
+    return out
 

@@ -1372,3 +1372,28 @@ def test_dbscan_distance_matrices(pl, orc):
     planar = rng.standard_normal((2, natoms, 3))
     planar[:, :, 2] = 0.0
     assert abs(pl.distance_matrix_kabsch(planar)[0, 1] - orc.kabsch_rmsd(planar[0], planar[1])) < 1e-10
+
+
+def test_reference_dbscan_selector_tests(pl):
+    """subset_selector_tests.jl:28-39 re-stated on synthetic configurations (the reference loads an xyz file): DBSCANSelector over the
+    GPU-built distance matrix finds the planted clusters, get_random_subset draws sample_size ÷ nclusters indices from each."""
+    rng = np.random.default_rng(8)
+    natoms, box = 12, np.array([9.0, 9.0, 9.0])
+    centres = [rng.uniform(0, 9, size=(natoms, 3)) for _ in range(3)]
+    pos = np.stack([np.mod(centres[i % 3] + 0.01 * rng.standard_normal((natoms, 3)), box) for i in range(45)])
+    sel = pl.DBSCANSelector(pos, 0.05, 5, 6, box_lengths=box)
+    assert isinstance(sel, pl.SubsetSelector)
+    assert len(sel.clusters) == 3 and sorted(len(c) for c in sel.clusters) == [15, 15, 15]
+    for c in sel.clusters:
+        assert len({i % 3 for i in c}) == 1
+    sub = pl.get_random_subset(sel, rng=np.random.default_rng(0))
+    assert len(sub) == 6 and all(isinstance(i, int) for i in sub)
+    assert sorted(sum(1 for i in sub if i in c) for c in sel.clusters) == [2, 2, 2]
+    # non-periodic: Kabsch RMSD separates rigidly moved copies of different shapes
+    shapes = [rng.standard_normal((natoms, 3)) * 2 for _ in range(2)]
+    pk = []
+    for i in range(30):
+        Q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        pk.append((shapes[i % 2] + 0.005 * rng.standard_normal((natoms, 3))) @ Q + rng.uniform(-4, 4, size=3))
+    sel2 = pl.DBSCANSelector(np.stack(pk), 0.1, 5, 4)
+    assert len(sel2.clusters) == 2 and all(len({i % 2 for i in c}) == 1 for c in sel2.clusters)

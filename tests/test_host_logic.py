@@ -133,3 +133,12 @@ def test_kdpp_host_routines_on_oracle_kernel():
     assert abs(cnt.sum() / 300 - 5.0) < 1e-12
     with pytest.raises(ValueError):
         pl.rescale_(ell, 30)  # a degree-2 polynomial kernel of 6-dim features has rank 21 < 30
+
+
+def test_random_selector():
+    """RandomSelector / get_random_subset (random.jl): a prefix of a random permutation."""
+    r = pl.RandomSelector(10, batch_size=2)
+    assert isinstance(r, pl.SubsetSelector)
+    s = pl.get_random_subset(r, rng=np.random.default_rng(0))
+    assert len(s) == 2 and len(set(s)) == 2 and all(isinstance(i, int) and 0 <= i < 10 for i in s)
+    assert sorted(pl.get_random_subset(pl.RandomSelector(7), rng=np.random.default_rng(1))) == list(range(7))
