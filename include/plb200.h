@@ -220,6 +220,12 @@ int pl_predict(const double* A, int64_t R, int64_t Kf, int64_t lda, const double
 int pl_predict_dev(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dbeta, double beta0, int64_t n_energy_rows,
                    double* dy, void* stream);
 
+/* Residual metrics of predictions against reference values (src/Metrics/metrics.jl:11-53): out = [mae, rmse, rsq, mean_cos].
+ * mae = sum|x_pred - x| / n, rmse = sqrt(sum (x_pred - x)^2 / n), rsq = 1 - sum (x_pred - x)^2 / sum (x - mean(x))^2 (two passes),
+ * mean_cos = mean over the 3-vectors (forces, n % 3 == 0) of dot(x, x_pred) / (|x| |x_pred|) with NaNs filtered (NaN otherwise). */
+int pl_metrics(const double* x_pred, const double* x, int64_t n, double* out);
+int pl_metrics_dev(const double* dx_pred, const double* dx, int64_t n, double* dout, void* stream);
+
 /* ---- device-resident entry points (enqueue only; `stream` is a cudaStream_t) ---------------------------- */
 
 /* Kernel matrix on device data. dX2 == NULL -> symmetric (n2/ldx2 ignored, `fill` applies); otherwise rectangular

@@ -116,6 +116,7 @@ enum WsSlot {
   WS_POS,
   WS_POS_C,
   WS_POS_D,
+  WS_MET,
   WS_NSLOTS
 };
 
@@ -920,6 +921,27 @@ int cov_recentre_dev_impl(double* dS, int64_t Kf, const double* drho, const doub
   int blocks = (int)((Kf * Kf + 255) / 256);
   if (blocks > g.num_sms * 8) blocks = g.num_sms * 8;
   cov_recentre_kernel<<<blocks, 256, 0, st>>>(dS, Kf, drho, ddelta, n_rows);
+  LAUNCH_CHECK();
+  return PL_OK;
+}
+
+
+int metrics_dev_impl(const double* dxp, const double* dx, int64_t n, double* dout /*4*/, cudaStream_t st) {
+  PL_TRY(need_ready());
+  if (!dxp || !dx || !dout || n <= 0) return set_err(PL_EINVAL, "bad arguments");
+  int nb = (int)((n + 255) / 256);
+  if (nb > g.num_sms * 4) nb = g.num_sms * 4;
+  void* ws;
+  PL_TRY(ws_get(WS_MET, (size_t)(nb * 6 + 1) * 8, &ws));
+  double* part = (double*)ws;
+  double* mean = part + nb * 6;
+  metrics_partial_kernel<<<nb, 256, 0, st>>>(dxp, dx, n, nullptr, part);
+  LAUNCH_CHECK();
+  metrics_final_kernel<<<1, 32, 0, st>>>(part, nb, n, 0, mean);
+  LAUNCH_CHECK();
+  metrics_partial_kernel<<<nb, 256, 0, st>>>(dxp, dx, n, mean, part);
+  LAUNCH_CHECK();
+  metrics_final_kernel<<<1, 32, 0, st>>>(part, nb, n, 1, dout);
   LAUNCH_CHECK();
   return PL_OK;
 }
@@ -1979,6 +2001,31 @@ int pl_rmsd_periodic(const double* P, int64_t n, int64_t natoms, const double* b
 int pl_rmsd_kabsch(const double* P, int64_t n, int64_t natoms, double* D, int64_t ldd) {
   std::lock_guard<std::mutex> lk(g_mu);
   return rmsd_host(P, n, natoms, nullptr, D, ldd);
+}
+
+
+int pl_metrics_dev(const double* dxp, const double* dx, int64_t n, double* dout, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return metrics_dev_impl(dxp, dx, n, dout, (cudaStream_t)stream);
+}
+
+int pl_metrics(const double* x_pred, const double* x, int64_t n, double* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!x_pred || !x || !out || n <= 0) return set_err(PL_EINVAL, "bad arguments");
+  CUDA_TRY(cudaSetDevice(g.device));
+  CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
+  double *dxp, *dx;
+  PL_TRY(h2d_vector(x_pred, n, WS_H_IN2, &dxp));
+  PL_TRY(h2d_vector(x, n, WS_H_IN3, &dx));
+  void* dout;
+  PL_TRY(ws_get(WS_H_OUT2, 64, &dout));
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  PL_TRY(metrics_dev_impl(dxp, dx, n, (double*)dout, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  CUDA_TRY(cudaMemcpyAsync(out, dout, 32, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
+  return finish_timing();
 }
 
 }  // extern "C"

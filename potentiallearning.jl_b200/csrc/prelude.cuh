@@ -885,4 +885,57 @@ __global__ void rmsd_kabsch_kernel(const double* __restrict__ Pc, int64_t n, int
   D[j * ldd + i] = r;
 }
 
+// ---- residual metrics of the fitted model (src/Metrics/metrics.jl:11-53) ----
+// partial[b][0..6] = sums over block b's strided range of: |d|, d^2, x, (x - xmean)^2 (second pass), cos of 3-vector pairs, count of
+// non-NaN cosines, with d = x_pred - x. Two passes (mean first: rsq needs sum (x - mean(x))^2 without cancellation). Block sums are
+// added in block order by metrics_final_kernel -> deterministic.
+__global__ void metrics_partial_kernel(const double* __restrict__ xp, const double* __restrict__ x, int64_t n, const double* __restrict__ xmean,
+                                       double* __restrict__ partial) {
+  __shared__ double sh[6][256];
+  double a[6] = {0, 0, 0, 0, 0, 0};
+  const double mu = xmean ? xmean[0] : 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double d = xp[i] - x[i];
+    a[0] += fabs(d);
+    a[1] = fma(d, d, a[1]);
+    a[2] += x[i];
+    const double c = x[i] - mu;
+    a[3] = fma(c, c, a[3]);
+  }
+  if (n % 3 == 0) {  // mean_cos over the 3-vectors (forces): dot(x, x_pred) / (|x| |x_pred|), NaNs (zero vectors) filtered
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n / 3; v += (int64_t)gridDim.x * blockDim.x) {
+      const double a0 = x[3 * v], a1 = x[3 * v + 1], a2 = x[3 * v + 2];
+      const double b0 = xp[3 * v], b1 = xp[3 * v + 1], b2 = xp[3 * v + 2];
+      const double cs = (a0 * b0 + a1 * b1 + a2 * b2) / (sqrt(a0 * a0 + a1 * a1 + a2 * a2) * sqrt(b0 * b0 + b1 * b1 + b2 * b2));
+      if (cs == cs) {
+        a[4] += cs;
+        a[5] += 1.0;
+      }
+    }
+  }
+  for (int q = 0; q < 6; ++q) sh[q][threadIdx.x] = a[q];
+  __syncthreads();
+  for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off)
+      for (int q = 0; q < 6; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) partial[(int64_t)blockIdx.x * 6 + threadIdx.x] = sh[threadIdx.x][0];
+}
+// mode 0: out[0] = mean(x) (after the first pass). mode 1: out = [mae, rmse, rsq, mean_cos]
+__global__ void metrics_final_kernel(const double* __restrict__ partial, int nblocks, int64_t n, int mode, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int b = 0; b < nblocks; ++b)
+    for (int q = 0; q < 6; ++q) s[q] += partial[(int64_t)b * 6 + q];
+  if (mode == 0) {
+    out[0] = s[2] / (double)n;
+  } else {
+    out[0] = s[0] / (double)n;
+    out[1] = sqrt(s[1] / (double)n);
+    out[2] = 1.0 - s[1] / s[3];
+    out[3] = s[4] / s[5];  // NaN when n is not a multiple of 3 or every cosine was NaN (mean of an empty collection)
+  }
+}
+
 }  // namespace plb

@@ -15,7 +15,8 @@ from .kernels import (RBF, CorrelationMatrix, Diagonal, Distance, Divergence, Do
                       KernelMatrix, Symmetric,
                       compute_distance, compute_feature, compute_features, compute_kernel, correlation_features, get_parameters, global_features, global_features_dev,
                       gram_tile_coords, kernel_matrix_dev, stack_locals)
-from .learning import (CovariateLinearProblem, LinearBasisPotential, NormalEquationAccumulator, batch_sums, LinearProblem, UnivariateLinearProblem, assemble_matrices,
+from .learning import (CovariateLinearProblem, LinearBasisPotential, NormalEquationAccumulator, batch_sums, calc_all_metrics, get_metrics, mae,
+                       mean_cos, rmse, rsq, LinearProblem, UnivariateLinearProblem, assemble_matrices,
                        get_all_energies, get_all_forces, learn_, learn_potential_, normal_equations, normal_equations_blocks, ols_sums, ooc_learn_, pack_rhs,
                        pack_rows, predict)
 

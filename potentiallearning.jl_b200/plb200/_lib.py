@@ -59,6 +59,8 @@ PROTOTYPES = {
     "pl_ell_greedy": (_int, [_i64, _i64, ctypes.POINTER(_i64)]),
     "pl_rmsd_periodic": (_int, [_dp, _i64, _i64, _dp, _dp, _i64]),
     "pl_rmsd_kabsch": (_int, [_dp, _i64, _i64, _dp, _i64]),
+    "pl_metrics": (_int, [_dp, _dp, _i64, _dp]),
+    "pl_metrics_dev": (_int, [_vp, _vp, _i64, _vp, _vp]),
     "pl_predict": (_int, [_dp, _i64, _i64, _i64, _dp, _dbl, _i64, _dp]),
     "pl_predict_dev": (_int, [_vp, _i64, _i64, _i64, _vp, _dbl, _i64, _vp, _vp]),
     "pl_gram_dev": (_int, [_int, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _int, _vp, _dbl, _dbl, _vp, _i64, _int, _int, _int, _int, _vp]),

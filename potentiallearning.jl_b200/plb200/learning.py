@@ -385,3 +385,44 @@ def get_all_forces(ds: DataSet, lb: LinearBasisPotential | None = None):
         return np.concatenate([get_values(get_forces(c)).reshape(-1) for c in ds])
     dB = np.concatenate([get_values(get_force_descriptors(c)).reshape(-1, len(lb.β)) for c in ds], axis=0)
     return predict(dB, lb.β, 0.0, 0)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Metrics (src/Metrics/metrics.jl:11-53) of the predictions, reduced on the GPU (pl_metrics)
+# ----------------------------------------------------------------------------------------------------------------
+def calc_all_metrics(x_pred, x):
+    """[mae, rmse, rsq, mean_cos] in one device pass pair (pl_metrics)."""
+    xp, xr = _lib.as_f64(x_pred).reshape(-1), _lib.as_f64(x).reshape(-1)
+    if xp.shape != xr.shape or xp.size == 0:
+        raise ValueError("DimensionMismatch: x_pred and x must have the same non-zero length")
+    out = np.empty(4)
+    _lib.check(_lib.lib().pl_metrics(_lib.dptr(xp), _lib.dptr(xr), xp.size, _lib.dptr(out)), "pl_metrics")
+    return out
+
+
+def mae(x_pred, x):
+    """mae(x_pred, x) (metrics.jl:11-13)."""
+    return float(calc_all_metrics(x_pred, x)[0])
+
+
+def rmse(x_pred, x):
+    """rmse(x_pred, x) (metrics.jl:23-25)."""
+    return float(calc_all_metrics(x_pred, x)[1])
+
+
+def rsq(x_pred, x):
+    """rsq(x_pred, x) (metrics.jl:35-37)."""
+    return float(calc_all_metrics(x_pred, x)[2])
+
+
+def mean_cos(x_pred, x):
+    """mean_cos(x_pred, x) (metrics.jl:47-53): mean cosine between predicted and true force 3-vectors, NaNs filtered."""
+    return float(calc_all_metrics(x_pred, x)[3])
+
+
+def get_metrics(x_pred, x, metrics=(mae, rmse, rsq), label="x"):
+    """get_metrics(x_pred, x; metrics, label) (metrics.jl:67-75): {"<label>_<metric>": value} in the given order."""
+    vals = calc_all_metrics(x_pred, x)
+    idx = {"mae": 0, "rmse": 1, "rsq": 2, "mean_cos": 3}
+    return {f"{label}_{m.__name__}": float(vals[idx[m.__name__]]) for m in metrics}
+

@@ -1397,3 +1397,28 @@ def test_reference_dbscan_selector_tests(pl):
         pk.append((shapes[i % 2] + 0.005 * rng.standard_normal((natoms, 3))) @ Q + rng.uniform(-4, 4, size=3))
     sel2 = pl.DBSCANSelector(np.stack(pk), 0.1, 5, 4)
     assert len(sel2.clusters) == 2 and all(len({i % 2 for i in c}) == 1 for c in sel2.clusters)
+
+
+def test_metrics(pl):
+    """mae / rmse / rsq / mean_cos / get_metrics (src/Metrics/metrics.jl:11-75) against the definitions evaluated in numpy."""
+    rng = np.random.default_rng(6)
+    for n in (3, 999, 300_000):
+        x = rng.standard_normal(n) * 2.0 + 5.0
+        xp = x + 0.1 * rng.standard_normal(n)
+        if n >= 999:
+            x[3:6] = 0.0  # a zero force vector: its cosine is NaN and must be filtered (metrics.jl:51)
+        d = xp - x
+        ref = {"mae": np.sum(np.abs(d)) / n, "rmse": np.sqrt(np.sum(d ** 2) / n), "rsq": 1 - np.sum(d ** 2) / np.sum((x - np.mean(x)) ** 2)}
+        xv, pv = x.reshape(-1, 3), xp.reshape(-1, 3)
+        with np.errstate(all="ignore"):
+            cs = np.sum(xv * pv, axis=1) / (np.linalg.norm(xv, axis=1) * np.linalg.norm(pv, axis=1))
+        ref["mean_cos"] = np.mean(cs[~np.isnan(cs)])
+        assert abs(pl.mae(xp, x) - ref["mae"]) < 1e-12 * ref["mae"]
+        assert abs(pl.rmse(xp, x) - ref["rmse"]) < 1e-12 * ref["rmse"]
+        assert abs(pl.rsq(xp, x) - ref["rsq"]) < 1e-12
+        assert abs(pl.mean_cos(xp, x) - ref["mean_cos"]) < 1e-12
+        m = pl.get_metrics(xp, x, metrics=[pl.mae, pl.rmse, pl.rsq], label="e")
+        assert list(m) == ["e_mae", "e_rmse", "e_rsq"] and abs(m["e_rmse"] - ref["rmse"]) < 1e-12 * ref["rmse"]
+    assert np.isnan(pl.mean_cos(np.ones(4), np.ones(4)))  # not a multiple of 3: no 3-vectors
+    with pytest.raises(ValueError):
+        pl.mae(np.ones(3), np.ones(4))
