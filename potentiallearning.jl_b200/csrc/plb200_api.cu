@@ -200,7 +200,7 @@ int tma_operand(const double* src, int64_t rows, int64_t cols, int64_t ld, int s
     return PL_OK;
   }
   const int64_t ldp = (cols + 1) & ~(int64_t)1;
-  void* buf;
+  void* buf = nullptr;
   PL_TRY(ws_get(slot, (size_t)rows * ldp * 8, &buf));
   const int64_t total = rows * cols;
   int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
@@ -224,7 +224,7 @@ int64_t colsum_rows_per_block(int64_t R, int64_t Kf) {
 int colsum(const double* dA, int64_t R, int64_t Kf, int64_t lda, double denom, double* dout, cudaStream_t st, const double* dshift = nullptr) {
   const int64_t rpb = colsum_rows_per_block(R, Kf);
   const int64_t nblk = (R + rpb - 1) / rpb;
-  void* part;
+  void* part = nullptr;
   PL_TRY(ws_get(WS_COLSUM_PARTIAL, (size_t)(nblk > 0 ? nblk : 1) * Kf * 8, &part));
   if (nblk > 0) {
     const int64_t pairs = (Kf + 1) / 2;
@@ -244,7 +244,7 @@ int moment_vectors(const double* dA, int64_t R, int64_t Kf, int64_t lda, const d
   const int64_t Rv = db ? R : ne;
   const int64_t rpb = colsum_rows_per_block(Rv, Kf);
   const int64_t nblk = (Rv + rpb - 1) / rpb;
-  void* part;
+  void* part = nullptr;
   PL_TRY(ws_get(WS_COLSUM_PARTIAL, (size_t)(nblk > 0 ? nblk : 1) * Kf * 8 * 2, &part));
   double* pv = (double*)part;
   double* pc = pv + (nblk > 0 ? nblk : 1) * Kf;
@@ -655,7 +655,7 @@ int finish_dev_impl(const double* dS, const double* dvec, int64_t Kf, int ic, do
 // host <-> device helpers for the host-pointer entry points
 int h2d_matrix(const double* h, int64_t rows, int64_t cols, int64_t ldh, int slot, double** dptr, int64_t* ldd) {
   const int64_t ldp = (cols + 1) & ~(int64_t)1;
-  void* buf;
+  void* buf = nullptr;
   PL_TRY(ws_get(slot, (size_t)(rows > 0 ? rows : 1) * ldp * 8, &buf));
   if (rows > 0) {
     if (ldp == ldh && ldh == cols)  // dense on both sides: one linear copy (faster than the pitched path)
@@ -668,7 +668,7 @@ int h2d_matrix(const double* h, int64_t rows, int64_t cols, int64_t ldh, int slo
   return PL_OK;
 }
 int h2d_vector(const double* h, int64_t count, int slot, double** dptr) {
-  void* buf;
+  void* buf = nullptr;
   PL_TRY(ws_get(slot, (size_t)(count > 0 ? count : 1) * 8, &buf));
   if (count > 0) CUDA_TRY(cudaMemcpyAsync(buf, h, (size_t)count * 8, cudaMemcpyHostToDevice, g.stream));
   *dptr = (double*)buf;
@@ -889,7 +889,7 @@ int inclusion_prob_dev_impl(const double* dV, int64_t nvec, int64_t n, int64_t l
   int64_t rpb = nvec / 64;
   rpb = rpb < 16 ? 16 : (rpb + 1) / 2 * 2;
   const int64_t nblk = (nvec + rpb - 1) / rpb;
-  void* part;
+  void* part = nullptr;
   PL_TRY(ws_get(WS_COLSUM_PARTIAL, (size_t)nblk * n * 8, &part));
   dim3 grid((unsigned)((n + 127) / 128), (unsigned)nblk);
   weighted_colsumsq_partial_kernel<<<grid, 128, 0, st>>>(dV, nvec, n, ldv, dgamma, (int)rpb, (double*)part);
