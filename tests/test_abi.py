@@ -91,3 +91,25 @@ def test_tile_enumeration_helpers_run_on_host():
         assert len(seen) == T * (T + 1) // 2
         counts = [int(lib.pl_gram_tile_count(n, 0, p, nparts)) for p in range(nparts)]
         assert max(counts) - min(counts) <= 1, "tiles are dealt evenly"
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under potentiallearning.jl_b200/ (the product) may import, load or execute it, and the
+    library has no CPU code path to fall back to (every compute entry point starts with need_ready())."""
+    pkg = os.path.join(ROOT, "potentiallearning.jl_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".jl")):
+                txt = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|libploracle|pl_oracle", txt, flags=re.M):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+    api = open(os.path.join(pkg, "csrc", "plb200_api.cu")).read()
+    body = api[api.index('extern "C" {'):]
+    # every exported compute entry point (everything but lifetime / bookkeeping helpers) checks for an initialised sm_100 device
+    for m in re.finditer(r"\n(?:int|void\*)\s+(pl_\w+)\s*\([^)]*\)\s*\{(.*?)\n\}\n", body, flags=re.S):
+        name, code = m.group(1), m.group(2)
+        if name in ("pl_init", "pl_last_timing", "pl_set_profiling", "pl_host_free", "pl_gram_tile_coords"):
+            continue
+        assert ("need_ready()" in code) or re.search(r"return \w+_impl\(|return gram_host\(|return rmsd_host\(|return normal_eq_stream\(", code), name
