@@ -75,8 +75,9 @@ int pl_set_profiling(int on);
 int pl_last_main_kernel_ms(double* ms);
 
 /* Pinned, zero-filled host memory for result arrays (the shim wraps it as a Julia Array with a finalizer). The host entry points accept
- * any host pointer, but device-to-host copies reach the PCIe rate only into pinned memory: config 2 end to end takes 36 ms into a
- * pinned K, 105 ms into pageable memory, 510 ms into freshly calloc'ed (never touched) pages. NULL on failure (pl_last_error). */
+ * any host pointer (pageable memory is staged through the library's own pinned ring and host threads), but only pinned memory is copied at
+ * the PCIe rate: config 2 end to end takes 37 ms into a pinned K, 63 ms into pageable memory, 120-180 ms into freshly calloc'ed pages.
+ * NULL on failure (pl_last_error). */
 void* pl_host_alloc(int64_t bytes);
 int pl_host_free(void* p);
 

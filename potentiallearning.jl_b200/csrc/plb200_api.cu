@@ -16,6 +16,7 @@
 
 #include "../../include/plb200.h"
 #include "gram.cuh"
+#include "hoststage.h"
 #include "prelude.cuh"
 #include "syrk.cuh"
 
@@ -24,6 +25,10 @@ using namespace plb;
 namespace {
 
 thread_local char g_err[1024] = "";
+HostStager g_stager;  // pinned staging ring + host threads for pageable host memory (hoststage.h)
+bool staging_for(const void* host_ptr, size_t bytes) {
+  return bytes >= ((size_t)4 << 20) && !getenv("PLB200_NO_STAGING") && HostStager::is_pageable(host_ptr);
+}
 std::mutex g_mu;
 std::atomic<int64_t> g_launches{0};
 
@@ -658,7 +663,9 @@ int h2d_matrix(const double* h, int64_t rows, int64_t cols, int64_t ldh, int slo
   void* buf = nullptr;
   PL_TRY(ws_get(slot, (size_t)(rows > 0 ? rows : 1) * ldp * 8, &buf));
   if (rows > 0) {
-    if (ldp == ldh && ldh == cols)  // dense on both sides: one linear copy (faster than the pitched path)
+    if (staging_for(h, (size_t)rows * cols * 8))  // pageable source: our own pinned staging ring + host threads
+      CUDA_TRY(g_stager.h2d_2d(buf, (size_t)ldp * 8, h, (size_t)ldh * 8, (size_t)cols * 8, (size_t)rows, g.stream));
+    else if (ldp == ldh && ldh == cols)  // dense on both sides: one linear copy (faster than the pitched path)
       CUDA_TRY(cudaMemcpyAsync(buf, h, (size_t)rows * cols * 8, cudaMemcpyHostToDevice, g.stream));
     else
       CUDA_TRY(cudaMemcpy2DAsync(buf, (size_t)ldp * 8, h, (size_t)ldh * 8, (size_t)cols * 8, (size_t)rows, cudaMemcpyHostToDevice, g.stream));
@@ -746,6 +753,8 @@ int normal_eq_stream(const double* const* blocks, const int64_t* rows, const int
   CUDA_TRY(cudaStreamWaitEvent(g.copy_stream, g.chunk_ev[4], 0));
   int64_t blk = 0, blk_row = 0;  // cursor into the block list
   int64_t r0 = 0;
+  const bool stage_blocks = !getenv("PLB200_NO_STAGING") && (double)R * (double)Kf * 8.0 >= 4.0 * 1048576.0;
+  bool staged = false;
   for (int64_t c = 0; r0 < R; ++c) {
     const int bi = (int)(c & 1);
     const int64_t nr = R - r0 < chunk_rows ? R - r0 : chunk_rows;
@@ -760,13 +769,17 @@ int normal_eq_stream(const double* const* blocks, const int64_t* rows, const int
       if (take > nr - filled) take = nr - filled;
       const double* src = blocks[blk] + blk_row * lds[blk];
       double* dst = (double*)buf[bi] + filled * ldp;
-      if (lds[blk] == Kf && ldp == Kf)
+      if (stage_blocks && HostStager::is_pageable(src)) {
+        CUDA_TRY(g_stager.h2d_2d(dst, (size_t)ldp * 8, src, (size_t)lds[blk] * 8, (size_t)Kf * 8, (size_t)take, g.copy_stream, false));
+        staged = true;
+      } else if (lds[blk] == Kf && ldp == Kf)
         CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)take * Kf * 8, cudaMemcpyHostToDevice, g.copy_stream));
       else
         CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ldp * 8, src, (size_t)lds[blk] * 8, (size_t)Kf * 8, (size_t)take, cudaMemcpyHostToDevice, g.copy_stream));
       filled += take;
       blk_row += take;
     }
+    if (staged) CUDA_TRY(g_stager.finish());  // every DMA of this chunk has been enqueued on the copy stream
     CUDA_TRY(cudaEventRecord(g.chunk_ev[bi], g.copy_stream));
     CUDA_TRY(cudaStreamWaitEvent(g.stream, g.chunk_ev[bi], 0));
     int64_t ne_c = ne - r0;
@@ -1015,6 +1028,7 @@ void pl_finalize(void) {
     cs.h = nullptr;
     cs.params = nullptr;
   }
+  g_stager.shutdown();
   ell_state.valid = false;
   neq_state.open = false;
   if (g.stream) cudaStreamDestroy(g.stream);
@@ -1233,14 +1247,19 @@ static int gram_host(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, 
       CUDA_TRY(cudaEventRecord(g.chunk_ev[c], g.stream));
     }
     CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+    const bool stage_out = staging_for(K, (size_t)n1 * n1 * 4);
     for (int c = 0; c < NCHUNK; ++c) {
       CUDA_TRY(cudaStreamWaitEvent(g.copy_stream, g.chunk_ev[c], 0));
       for (int tb = bounds[c]; tb < bounds[c + 1]; ++tb) {
         const int64_t r0 = (int64_t)tb * GRAM_BM;
         const int64_t r1 = r0 + GRAM_BM < n1 ? r0 + GRAM_BM : n1;
-        CUDA_TRY(cudaMemcpy2DAsync(K + r0 * ldk, (size_t)ldk * 8, dK + r0 * ldo, (size_t)ldo * 8, (size_t)r1 * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, g.copy_stream));
+        if (stage_out)
+          CUDA_TRY(g_stager.d2h_2d(K + r0 * ldk, (size_t)ldk * 8, dK + r0 * ldo, (size_t)ldo * 8, (size_t)r1 * 8, (size_t)(r1 - r0), g.copy_stream, false));
+        else
+          CUDA_TRY(cudaMemcpy2DAsync(K + r0 * ldk, (size_t)ldk * 8, dK + r0 * ldo, (size_t)ldo * 8, (size_t)r1 * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, g.copy_stream));
       }
     }
+    if (stage_out) CUDA_TRY(g_stager.finish());
     CUDA_TRY(cudaEventRecord(g.ev[3], g.copy_stream));
     CUDA_TRY(cudaStreamSynchronize(g.copy_stream));
     return finish_timing();
@@ -1248,7 +1267,10 @@ static int gram_host(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, 
   PL_TRY(gram_dev_impl(kernel_id, d1, n1, l1, d2, n2, l2, d, alpha, cinv_kind, dc, ell, beta, dK, ldo, fill, 0, 1, 0, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
   if (!sym || fill == PL_FILL_FULL) {
-    CUDA_TRY(cudaMemcpy2DAsync(K, (size_t)ldk * 8, dK, (size_t)ldo * 8, (size_t)n2 * 8, (size_t)n1, cudaMemcpyDeviceToHost, g.stream));
+    if (staging_for(K, (size_t)n1 * n2 * 8))
+      CUDA_TRY(g_stager.d2h_2d(K, (size_t)ldk * 8, dK, (size_t)ldo * 8, (size_t)n2 * 8, (size_t)n1, g.stream));
+    else
+      CUDA_TRY(cudaMemcpy2DAsync(K, (size_t)ldk * 8, dK, (size_t)ldo * 8, (size_t)n2 * 8, (size_t)n1, cudaMemcpyDeviceToHost, g.stream));
   } else {
     // one triangle only: copy the staircase of 128-row blocks (half the PCIe traffic). Inside diagonal tiles the
     // unused half was written as zeros by the kernel, matching the reference's zeros(n,n) storage.

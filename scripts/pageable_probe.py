@@ -34,6 +34,7 @@ Kp = plb200.pinned_zeros((N, N))  # pl_host_alloc
 out["pinned_alloc_ms"] = (time.perf_counter() - t0) * 1e3
 run(Kp)
 out["pinned_ms"] = min(run(Kp) for _ in range(3))
+out["pinned_timing"] = plb200.last_timing()
 t = []
 for _ in range(3):
     K = np.zeros((N, N))  # fresh calloc'ed pages, like Julia's zeros(n, n)
@@ -42,4 +43,5 @@ out["pageable_fresh_zeros_ms"] = t
 K = np.zeros((N, N))
 K[:] = 0.0  # touched once: pages exist
 out["pageable_touched_ms"] = [run(K) for _ in range(3)]
+out["pageable_timing"] = plb200.last_timing()
 print(json.dumps(out))

@@ -1422,3 +1422,34 @@ def test_metrics(pl):
     assert np.isnan(pl.mean_cos(np.ones(4), np.ones(4)))  # not a multiple of 3: no 3-vectors
     with pytest.raises(ValueError):
         pl.mae(np.ones(3), np.ones(4))
+
+
+def test_pageable_staging_paths(pl, orc):
+    """Pageable host memory goes through the library's pinned staging ring + host threads (hoststage.h): same results as the direct
+    path (PLB200_NO_STAGING=1), for the streamed kernel-matrix download, the pitched matrix upload and the block-list upload."""
+    import os
+
+    rng = np.random.default_rng(12)
+    X = rng.standard_normal((2500, 40)) * 0.5 + 1.0  # 2500^2 * 8 = 50 MB result: staged (>= 4 MB), T = 20 >= 16: the streamed path
+    k = pl.RBF(pl.Euclidean(40), ell=2.0)
+    K1 = np.asarray(pl.KernelMatrix(X, k, fill="U"))
+    K1f = np.asarray(pl.KernelMatrix(X, k))
+    Kx1 = pl.KernelMatrix(X, X[:700], k)  # rectangular 2500 x 700 = 14 MB
+    A = rng.standard_normal((120_000, 37))  # 35 MB, odd K: pitched upload
+    b = rng.standard_normal(120_000)
+    M1, v1 = pl.normal_equations(A, b, None, 500, 30.0, 1.0, True, 0.01)
+    blocks = [rng.standard_normal(64) for _ in range(50)] + [np.asfortranarray(rng.standard_normal((64, 3 * n))) for n in rng.integers(20, 200, size=150)]
+    bb = rng.standard_normal(sum(1 if m.ndim == 1 else m.shape[1] for m in blocks))
+    M3, v3 = pl.normal_equations_blocks(blocks, bb, None, 50, 100.0, 1.0, True, 0.0, chunk_rows=4096)
+    os.environ["PLB200_NO_STAGING"] = "1"
+    try:
+        K2 = np.asarray(pl.KernelMatrix(X, k, fill="U"))
+        K2f = np.asarray(pl.KernelMatrix(X, k))
+        Kx2 = pl.KernelMatrix(X, X[:700], k)
+        M2, v2 = pl.normal_equations(A, b, None, 500, 30.0, 1.0, True, 0.01)
+        M4, v4 = pl.normal_equations_blocks(blocks, bb, None, 50, 100.0, 1.0, True, 0.0, chunk_rows=4096)
+    finally:
+        del os.environ["PLB200_NO_STAGING"]
+    assert np.array_equal(K1, K2) and np.array_equal(K1f, K2f) and np.array_equal(Kx1, Kx2)
+    assert np.array_equal(M1, M2) and np.array_equal(v1, v2) and np.array_equal(M3, M4) and np.array_equal(v3, v4)
+    assert relerr(K1f[:200, :200], orc.symmetric(orc.kernel_matrix(X[:200], orc.RBF(orc.Euclidean(40), ell=2.0)))) < RTOL
