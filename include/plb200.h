@@ -76,7 +76,7 @@ int pl_last_main_kernel_ms(double* ms);
 
 /* Pinned, zero-filled host memory for result arrays (the shim wraps it as a Julia Array with a finalizer). The host entry points accept
  * any host pointer (pageable memory is staged through the library's own pinned ring and host threads), but only pinned memory is copied at
- * the PCIe rate: config 2 end to end takes 37 ms into a pinned K, 63 ms into pageable memory, 120-180 ms into freshly calloc'ed pages.
+ * the PCIe rate: config 2 end to end takes 37 ms into a pinned K, 45 ms into pageable memory, ~100 ms into freshly calloc'ed pages.
  * NULL on failure (pl_last_error). */
 void* pl_host_alloc(int64_t bytes);
 int pl_host_free(void* p);

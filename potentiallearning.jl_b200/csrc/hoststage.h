@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -21,8 +22,8 @@ namespace plb {
 class HostStager {
  public:
   static constexpr size_t kSlotBytes = 16u << 20;
-  static constexpr int kSlots = 6;
-  static constexpr int kThreads = 6;
+  static constexpr int kSlots = 16;     // ring capacity (only nthreads_ + 2 of them are allocated)
+  static constexpr int kDefaultThreads = 8;
 
   ~HostStager() { shutdown(); }
 
@@ -141,7 +142,15 @@ class HostStager {
   cudaError_t ensure() {
     std::unique_lock<std::mutex> lk(mu_);
     if (started_) return cudaSuccess;
-    for (int s = 0; s < kSlots; ++s) {
+    {
+      const char* env = getenv("PLB200_STAGE_THREADS");
+      int t = env ? atoi(env) : kDefaultThreads;
+      const int hw = (int)std::thread::hardware_concurrency();
+      if (hw > 0 && t > hw) t = hw;
+      nthreads_ = t < 1 ? 1 : (t > kSlots - 2 ? kSlots - 2 : t);
+      nslots_ = nthreads_ + 2;
+    }
+    for (int s = 0; s < nslots_; ++s) {
       cudaError_t e = cudaHostAlloc(&slot_[s], kSlotBytes, cudaHostAllocDefault);
       if (e != cudaSuccess) return e;
       e = cudaEventCreateWithFlags(&ev_[s], cudaEventDisableTiming);
@@ -151,7 +160,7 @@ class HostStager {
     }
     int dev = 0;
     cudaGetDevice(&dev);
-    for (int t = 0; t < kThreads; ++t)
+    for (int t = 0; t < nthreads_; ++t)
       threads_.emplace_back([this, dev]() {
         cudaSetDevice(dev);
         for (;;) {
@@ -187,7 +196,7 @@ class HostStager {
   // round-robin slot whose previous job has completed
   int next_slot() {
     const int s = cursor_;
-    cursor_ = (cursor_ + 1) % kSlots;
+    cursor_ = (cursor_ + 1) % nslots_;
     std::unique_lock<std::mutex> lk(mu_);
     done_cv_.wait(lk, [this, s]() { return !busy_[s]; });
     return s;
@@ -202,6 +211,7 @@ class HostStager {
   bool busy_[kSlots] = {};
   bool h2d_used_[kSlots] = {};  // the slot's event marks an H2D DMA that may still be reading it
   int cursor_ = 0;
+  int nthreads_ = kDefaultThreads, nslots_ = kDefaultThreads + 2;
   cudaError_t async_error_ = cudaSuccess;
   int pending_ = 0;
   bool started_ = false, stop_ = false;

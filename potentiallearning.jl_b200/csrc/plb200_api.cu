@@ -1827,7 +1827,7 @@ int pl_cov_recentre_dev(double* dS, int64_t Kf, const double* drho, const double
 
 
 // Pinned (page-locked), zero-filled host memory for result arrays: D2H into pinned memory runs at the PCIe rate (config 2: 37 ms end to
-// end); pageable memory goes through the staging ring (63 ms; 120-180 ms when the pages have never been touched).
+// end); pageable memory goes through the staging ring (45 ms; ~100 ms when the pages have never been touched).
 void* pl_host_alloc(int64_t bytes) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (need_ready() != PL_OK || bytes <= 0) return nullptr;

@@ -85,7 +85,27 @@ if "neq" in which:
     M2, v2 = plb200.normal_equations_blocks(blocks, b.numpy(), None, ncfg, 100.0, 1.0, True, 0.01)
     out["neq_blocks_pinned"] = {"nblocks": len(blocks), "ms": (time.perf_counter() - t0) * 1e3,
                                 "max_rel_vs_contiguous": float(np.max(np.abs(M2 - M.numpy())) / np.max(np.abs(M.numpy())))}
-    del A
+    # the same rows in PAGEABLE memory (a plain numpy / Julia array): staged by the library (hoststage.h) vs the driver's bounce buffer
+    Apg = np.array(An, copy=True)
+    bpg = np.array(b.numpy(), copy=True)
+    Mpg, vpg = np.empty((n, n)), np.empty(n)
+    PP = lambda a: a.ctypes.data_as(dp)
+
+    def run_pg():
+        _lib.check(lib.pl_normal_eq(PP(Apg), R, K, K, None, ncfg, 100.0, 1.0, PP(bpg), 1, 0.01, PP(Mpg), PP(vpg)), "pl_normal_eq")
+
+    for label, env in (("staged", None), ("unstaged", "1")):
+        if env:
+            os.environ["PLB200_NO_STAGING"] = env
+        ts = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            run_pg()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        os.environ.pop("PLB200_NO_STAGING", None)
+        out[f"neq_stream_pageable_{label}"] = {"ms_best": min(ts), "h2d_GBs": R * K * 8 / (min(ts) / 1e3) / 1e9,
+                                               "bitwise_equal_to_pinned": bool(np.array_equal(Mpg, M.numpy()))}
+    del A, Apg
 
 if "eig" in which:
 
