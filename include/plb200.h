@@ -194,11 +194,19 @@ int pl_ell_inclusion_prob(double alpha_scale, int64_t n, double* p);
  * cross PCIe instead of n*n. */
 int pl_ell_eigvecs(const int64_t* idx, int64_t m, int64_t n, double* V, int64_t ldv);
 
-/* Second phase of a k-DPP draw on the resident ensemble (Determinantal.sample, dpp.jl:51 [external]; Kulesza & Taskar 2012 Alg. 1 in its
- * O(n m^2) Gram-Schmidt form): projection-DPP sampling over the m eigenvectors eig_idx selected by the first phase (elementary symmetric
- * polynomials, on the host). uniforms: m numbers in [0, 1) from the CALLER's generator (the RNG stays in Julia / numpy), one per step.
- * items: the m selected item indices (0-based, in draw order). U never leaves the device; config-2 size (n = 20 000) draws thousands of
- * items in seconds where the host algorithm needs n x m^2 flops on one core. */
+/* First phase of a k-DPP draw (Determinantal.sample, dpp.jl:51 [external]; Kulesza & Taskar 2012 Alg. 7 + Alg. 8): which eigenvectors.
+ * lam: the n eigenvalues already scaled by rescale!'s alpha (>= 0); uniforms: n numbers in [0, 1) from the CALLER's generator, uniforms[i]
+ * decides eigenvalue n-1-i (visited from the largest index down, unused once k eigenvectors are taken). idx (capacity k): the selected
+ * eigenvector indices (0-based, descending); *count: how many (k unless the table underflows). The (n+1) x (k+1) table of log elementary
+ * symmetric polynomials is built on the device by one thread-block cluster (a cluster barrier per eigenvalue) and never leaves it. */
+int pl_esp_select(const double* lam, int64_t n, int64_t k, const double* uniforms, int64_t* idx, int64_t* count);
+
+/* Second phase of a k-DPP draw on the resident ensemble (Determinantal.sample, dpp.jl:51 [external]; Kulesza & Taskar 2012 Alg. 1):
+ * projection-DPP sampling over the m eigenvectors eig_idx selected by the first phase. uniforms: m numbers in [0, 1) from the CALLER's
+ * generator (the RNG stays in Julia / numpy), one per step; items: the m selected item indices (0-based, in draw order). U never leaves
+ * the device. For n <= 32768 the conditioning runs in its kernel-row (pivoted Cholesky) form on P = V V', built once by the Gram engine:
+ * a step reads t rows of an m x n factor; larger n use the O(n m^2) Gram-Schmidt form on V alone (PLB200_DPP_GS=1 forces it). Both pick
+ * item t from the same conditional distribution by inverse CDF. */
 int pl_ell_sample(const int64_t* eig_idx, int64_t m, int64_t n, const double* uniforms, int64_t* items);
 
 /* Greedy MAP of the resident ensemble (Determinantal.greedy_subset, dpp.jl:60 [external]): k items, each maximising the conditional

@@ -535,6 +535,43 @@ def compute_divergence_ksd(x, score, k: RBF) -> float:
     return float(ksd)
 
 
+def select_eigenvectors_kdpp(lam, k, uniforms):
+    """First phase of a k-DPP draw — which eigenvectors (Kulesza & Taskar 2012, Alg. 7 + Alg. 8; what Determinantal.sample(L, k), called
+    at src/SubsetSelection/dpp.jl:51, does before its projection-DPP phase; external dependency, restated from the published algorithm).
+    Elementary symmetric polynomials e_l(lam_1..lam_n) in exact rational-free form: scaled floating point per column would do, here
+    they are kept as Python floats in the log domain with math.log / log1p (independent of the product's numpy / CUDA forms).
+    uniforms[i] decides eigenvalue n = N - i (visited from the last one down). Returns the selected 0-based indices, descending."""
+    import math
+
+    lam = [float(x) for x in lam]
+    N = len(lam)
+    NEG = float("-inf")
+    loglam = [math.log(x) if x > 0.0 else NEG for x in lam]
+
+    def lae(a, b):
+        mx = max(a, b)
+        return mx if mx == NEG else mx + math.log1p(math.exp(-abs(a - b)))
+
+    E = [[NEG] * (N + 1) for _ in range(k + 1)]
+    E[0] = [0.0] * (N + 1)
+    for n in range(1, N + 1):
+        for l in range(1, min(n, k) + 1):
+            E[l][n] = lae(E[l][n - 1], loglam[n - 1] + E[l - 1][n - 1])
+    J, l = [], k
+    for n in range(N, 0, -1):
+        if l == 0:
+            break
+        if l == n:
+            J.extend(range(n - 1, -1, -1))
+            break
+        logp = loglam[n - 1] + E[l - 1][n - 1] - E[l][n]
+        u = uniforms[N - n]
+        if (math.log(u) if u > 0.0 else NEG) < logp:
+            J.append(n - 1)
+            l -= 1
+    return J
+
+
 def sample_projection_dpp(V, uniforms):
     """Projection-DPP sampling over the orthonormal columns of V (n x m) with caller-supplied uniforms, one per step — the O(n m^2)
     Gram-Schmidt form of Kulesza & Taskar (2012) Alg. 1 that Determinantal.jl's sample_pdpp implements (Determinantal.jl is an external

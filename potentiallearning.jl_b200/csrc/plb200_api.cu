@@ -117,6 +117,10 @@ enum WsSlot {
   WS_DPP_TMP,
   WS_DPP_ITEMS,
   WS_DPP_U,
+  WS_DPP_K,
+  WS_DPP_C,
+  WS_ESP_T,
+  WS_ESP_AUX,
   WS_ELL_K,
   WS_POS,
   WS_POS_C,
@@ -1849,6 +1853,121 @@ int pl_host_free(void* p) {
 }
 
 
+// First phase of a k-DPP draw (Kulesza & Taskar 2012 Alg. 8; Determinantal.sample, dpp.jl:51 [external]): which eigenvectors.
+int pl_esp_select(const double* lam, int64_t n, int64_t k, const double* uniforms, int64_t* idx, int64_t* count) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  if (!lam || !uniforms || !idx || !count || n <= 0 || k < 0 || k > n) return set_err(PL_EINVAL, "bad arguments");
+  *count = 0;
+  if (k == 0) return PL_OK;
+  int64_t positive = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (!(lam[i] >= 0.0) || !std::isfinite(lam[i])) return set_err(PL_EINVAL, "eigenvalue %lld is negative or not finite", (long long)i);
+    if (!(uniforms[i] >= 0.0 && uniforms[i] < 1.0)) return set_err(PL_EINVAL, "uniforms must lie in [0, 1)");
+    positive += lam[i] > 0.0;
+  }
+  if (k > positive) return set_err(PL_EINVAL, "k = %lld exceeds the number of positive eigenvalues (%lld)", (long long)k, (long long)positive);
+  const int64_t ldt = (k + 2) & ~(int64_t)1;
+  const double table_gib = (double)(n + 1) * (double)ldt * 8.0 / 1073741824.0;
+  if (table_gib > 24.0) return set_err(PL_ENOMEM, "the (n+1) x (k+1) table of elementary symmetric polynomials needs %.1f GiB (limit 24)", table_gib);
+  CUDA_TRY(cudaSetDevice(g.device));
+  cudaStream_t st = g.stream;
+  void *dT, *daux;
+  PL_TRY(ws_get(WS_ESP_T, (size_t)(n + 1) * ldt * 8, &dT));
+  PL_TRY(ws_get(WS_ESP_AUX, (size_t)(3 * n + k + 2) * 8, &daux));
+  double* dlam = (double*)daux;
+  double* dll = dlam + n;
+  double* du = dll + n;
+  int64_t* didx = (int64_t*)(du + n);
+  int64_t* dcnt = didx + k;
+  CUDA_TRY(cudaEventRecord(g.ev[0], st));
+  CUDA_TRY(cudaMemcpyAsync(dlam, lam, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(du, uniforms, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(g.ev[1], st));
+  esp_loglam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dlam, n, dll);
+  LAUNCH_CHECK();
+  esp_forward_kernel<<<ESP_CLUSTER, 1024, 0, st>>>(dll, n, k, (double*)dT, ldt);
+  LAUNCH_CHECK();
+  esp_select_kernel<<<1, 32, 0, st>>>((const double*)dT, ldt, dll, n, k, du, didx, dcnt);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaEventRecord(g.ev[2], st));
+  int64_t cnt = 0;
+  CUDA_TRY(cudaMemcpyAsync(&cnt, dcnt, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(g.ev[3], st));
+  PL_TRY(finish_timing());
+  if (cnt < 0 || cnt > k) return set_err(PL_ECUDA, "selection pass returned %lld eigenvectors for k = %lld", (long long)cnt, (long long)k);
+  if (cnt > 0) CUDA_TRY(cudaMemcpy(idx, didx, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
+  *count = cnt;
+  return PL_OK;
+}
+
+// pl_ell_sample in its kernel-row (Cholesky) form, see prelude.cuh: P = V V' once on the DMMA engine, then per step
+// pick -> gather C[:t,item] -> C[:t,:]'cj (two-stage, deterministic) -> row update.
+static int ell_sample_chol(const int64_t* eig_idx, int64_t m, int64_t n, const double* uniforms, int64_t* items, cudaStream_t st) {
+  const int64_t ldv = (m + 1) & ~(int64_t)1, ldp = (n + 1) & ~(int64_t)1;
+  void *didx, *dV, *dP, *dC, *dp, *dvec, *dtmp, *ditems, *du;
+  PL_TRY(ws_get(WS_EIG_IDX, (size_t)m * 8, &didx));
+  PL_TRY(ws_get(WS_EIG_SEL, (size_t)n * ldv * 8, &dV));
+  PL_TRY(ws_get(WS_DPP_K, (size_t)n * ldp * 8, &dP));
+  PL_TRY(ws_get(WS_DPP_C, (size_t)m * n * 8, &dC));
+  PL_TRY(ws_get(WS_DPP_P, (size_t)n * 8, &dp));
+  PL_TRY(ws_get(WS_DPP_VEC, (size_t)(m + 2) * 8, &dvec));
+  int nslices = (int)((m + 255) / 256);
+  if (nslices > 16) nslices = 16;
+  PL_TRY(ws_get(WS_DPP_TMP, (size_t)nslices * n * 8, &dtmp));
+  PL_TRY(ws_get(WS_DPP_ITEMS, (size_t)m * 8, &ditems));
+  PL_TRY(ws_get(WS_DPP_U, (size_t)m * 8, &du));
+  double* cj = (double*)dvec;
+  double* pivot = cj + m;
+  CUDA_TRY(cudaEventRecord(g.ev[0], st));
+  CUDA_TRY(cudaMemcpyAsync(didx, eig_idx, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(du, uniforms, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(ditems, 0xff, (size_t)m * 8, st));  // -1: "no item picked" stays visible
+  CUDA_TRY(cudaEventRecord(g.ev[1], st));
+  {
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((ldv + 31) / 32));
+    gather_cols_kernel<<<grid, dim3(32, 8), 0, st>>>((const double*)g.ws[WS_EIG_A], n, ell_state.ld, (const int64_t*)didx, m, (double*)dV, ldv);
+    LAUNCH_CHECK();
+    GramLaunch L{};
+    L.epi = EPI_LINEAR;
+    L.A = (const double*)dV; L.nA = n; L.ldA = ldv;
+    L.B = (const double*)dV; L.nB = n; L.ldB = ldv;
+    L.d = m;
+    L.out = (double*)dP; L.ldo = ldp;
+    L.symmetric = 1;
+    L.same_operand = 1;
+    L.fill = PL_FILL_FULL;
+    L.nparts = 1;
+    PL_TRY(launch_gram(L, st));
+  }
+  const unsigned nb = (unsigned)((n + 127) / 128);
+  greedy_init_kernel<<<nb, 128, 0, st>>>((const double*)dP, n, ldp, (double*)dp);
+  LAUNCH_CHECK();
+  for (int64_t t = 0; t < m; ++t) {
+    dpp_pick_kernel<<<1, 1024, 0, st>>>((const double*)dp, n, (const double*)du, t, (int64_t*)ditems);
+    LAUNCH_CHECK();
+    dpp_chol_gather_kernel<<<(unsigned)(t > 0 ? (t + 127) / 128 : 1), 128, 0, st>>>((const double*)dC, t, n, (const int64_t*)ditems, t, (const double*)dp, cj, pivot);
+    LAUNCH_CHECK();
+    int sl = 0;
+    if (t > 0) {
+      sl = (int)((t + 255) / 256);
+      if (sl > nslices) sl = nslices;
+      const int64_t sslice = (t + sl - 1) / sl;
+      greedy_dot_partial_kernel<<<dim3(nb, (unsigned)sl), 128, 0, st>>>((const double*)dC, t, n, cj, sslice, (double*)dtmp);
+      LAUNCH_CHECK();
+    }
+    dpp_chol_finish_kernel<<<nb, 128, 0, st>>>((const double*)dP, n, ldp, (const double*)dtmp, sl, (const int64_t*)ditems, t, pivot, (double*)dC + t * n, (double*)dp);
+    LAUNCH_CHECK();
+  }
+  CUDA_TRY(cudaEventRecord(g.ev[2], st));
+  CUDA_TRY(cudaMemcpyAsync(items, ditems, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(g.ev[3], st));
+  PL_TRY(finish_timing());
+  for (int64_t r = 0; r < m; ++r)
+    if (items[r] < 0) return set_err(PL_ECUDA, "k-DPP draw: step %lld found no admissible item (the selected eigenvectors are rank deficient)", (long long)r);
+  return PL_OK;
+}
+
 int pl_ell_sample(const int64_t* eig_idx, int64_t m, int64_t n, const double* uniforms, int64_t* items) {
   std::lock_guard<std::mutex> lk(g_mu);
   PL_TRY(need_ready());
@@ -1861,6 +1980,8 @@ int pl_ell_sample(const int64_t* eig_idx, int64_t m, int64_t n, const double* un
   }
   CUDA_TRY(cudaSetDevice(g.device));
   cudaStream_t st = g.stream;
+  // n x n projection kernel affordable (<= 8.6 GB): the kernel-row form, one pass over the rows of C per step
+  if (n <= 32768 && !getenv("PLB200_DPP_GS")) return ell_sample_chol(eig_idx, m, n, uniforms, items, st);
   void *didx, *dVt, *dp, *dF, *dvec, *dtmp, *ditems, *du;
   PL_TRY(ws_get(WS_EIG_IDX, (size_t)m * 8, &didx));
   PL_TRY(ws_get(WS_EIG_SEL, (size_t)m * n * 8, &dVt));

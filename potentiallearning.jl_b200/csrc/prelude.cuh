@@ -5,6 +5,7 @@
 // Reference sites: dot(A,A), dot(B,B) recomputed per pair (src/Kernels/kernels.jl:35); (B1-B2)'*Cinv*(B1-B2)
 // (src/Kernels/distances.jl:58-60); pca.m = sum(d)/length(d) (src/DimensionReduction/pca_state.jl:35).
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -519,6 +520,63 @@ __global__ void axpy1_kernel(const double* __restrict__ a, const double* __restr
   if (i < count) out[i] = a[i] + b[i];
 }
 
+// ---- first phase of a k-DPP draw: which eigenvectors (Kulesza & Taskar 2012, Alg. 7 + Alg. 8), in the log domain ----
+// T[n][l] = log e_l(lam_1..lam_n): T[n][l] = logaddexp(T[n-1][l], log lam_n + T[n-1][l-1]). Row n depends on row n-1 only, so one
+// thread-block CLUSTER (8 CTAs x 1024 threads) walks the rows with a cluster barrier per row; the l range is spread over the cluster.
+// Rows are exchanged through global memory (L2 loads: another SM's L1 is not coherent); the table is kept for the selection pass.
+constexpr int ESP_CLUSTER = 8;
+__global__ void esp_loglam_kernel(const double* __restrict__ lam, int64_t N, double* __restrict__ loglam) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) loglam[i] = lam[i] > 0.0 ? log(lam[i]) : -INFINITY;
+}
+__global__ void __cluster_dims__(ESP_CLUSTER, 1, 1) __launch_bounds__(1024) esp_forward_kernel(const double* __restrict__ loglam, int64_t N, int64_t k, double* T, int64_t ldt) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int64_t gtid = (int64_t)cluster.block_rank() * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)ESP_CLUSTER * blockDim.x;
+  for (int64_t l = gtid; l <= k; l += nth) T[l] = l == 0 ? 0.0 : -INFINITY;
+  cluster.sync();
+  for (int64_t n = 1; n <= N; ++n) {
+    const double ll = loglam[n - 1];
+    const double* prev = T + (n - 1) * ldt;
+    double* cur = T + n * ldt;
+    for (int64_t l = gtid; l <= k; l += nth) {
+      double v;
+      if (l == 0) {
+        v = 0.0;
+      } else if (l > n) {
+        v = -INFINITY;  // e_l of fewer than l values
+      } else {
+        const double a = __ldcg(prev + l), b = ll + __ldcg(prev + l - 1);
+        const double mx = fmax(a, b);
+        v = (mx == -INFINITY) ? mx : mx + log1p(exp(-fabs(a - b)));
+      }
+      cur[l] = v;
+    }
+    cluster.sync();
+  }
+}
+// Alg. 8, backwards over the eigenvalues with one uniform per visited eigenvalue (uniforms[N - n] for eigenvalue n): eigenvector n-1 is
+// taken with probability lam_n e_{l-1}^{n-1} / e_l^n. idx: the taken eigenvectors in visiting order (descending); count[0] = how many.
+__global__ void esp_select_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ loglam, int64_t N, int64_t k,
+                                  const double* __restrict__ uniforms, int64_t* __restrict__ idx, int64_t* __restrict__ count) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int64_t l = k, cnt = 0;
+  for (int64_t n = N; n >= 1 && l > 0; --n) {
+    if (l == n) {  // every remaining eigenvector is needed
+      for (int64_t r = n - 1; r >= 0; --r) idx[cnt++] = r;
+      l = 0;
+      break;
+    }
+    const double logp = loglam[n - 1] + T[(n - 1) * ldt + l - 1] - T[n * ldt + l];
+    if (log(uniforms[N - n]) < logp) {
+      idx[cnt++] = n - 1;
+      --l;
+    }
+  }
+  count[0] = cnt;
+}
+
 // ---- projection-DPP sampling over the selected eigenvectors of the resident L-ensemble (second phase of a k-DPP draw) ----
 // Kulesza & Taskar 2012, Alg. 1 in its O(n m^2) Gram-Schmidt form (what Determinantal.jl's sample_pdpp does): with V the n x m matrix of
 // the selected eigenvectors (stored transposed: Vt is m x n, row k = eigenvector k) and p_j = |V_j|^2,
@@ -666,6 +724,55 @@ __global__ void dpp_update_finish_kernel(const double* __restrict__ tmp, int nsl
   double q = fma(-t, t, p[j]);
   if (q < 0.0 || j == items[step]) q = 0.0;
   p[j] = q;
+}
+
+// ---- the same draw in its kernel-row (Cholesky) form: used when the n x n projection kernel P = V V' fits on the device ----
+// Conditioning on the picked items is the pivoted Cholesky recursion on P (Poulson 2019; Launay, Galerne & Desolneux 2018) — the
+// same conditional distribution as the Gram-Schmidt form, item by item:
+//   p = diag(P);  repeat m times:  item ~ p / sum(p);  c = (P[item,:] - C[:t,item]' C[:t,:]) / sqrt(p_item);  C[t,:] = c;  p -= c.^2.
+// P comes out of the Gram engine (DMMA) once; a step then reads t rows of C instead of all of Vt plus four passes over F, and is three
+// launches after the pick. V is the n x m matrix of the selected eigenvectors (row-major, leading dimension ldv, pad column zeroed).
+__global__ void gather_cols_kernel(const double* __restrict__ U, int64_t n, int64_t ldu, const int64_t* __restrict__ idx, int64_t m, double* __restrict__ V,
+                                   int64_t ldv) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const int64_t j0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 32;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t k = k0 + ty + 8 * r, j = j0 + tx;
+    tile[ty + 8 * r][tx] = (k < m && j < n) ? U[idx[k] * ldu + j] : 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t j = j0 + ty + 8 * r, k = k0 + tx;
+    if (j < n && k < ldv) V[j * ldv + k] = tile[tx][ty + 8 * r];
+  }
+}
+// cj[s] = C[s][item] for s < t, and the pivot p_item (read here so that the row update may overwrite p in place)
+__global__ void dpp_chol_gather_kernel(const double* __restrict__ C, int64_t t, int64_t n, const int64_t* __restrict__ items, int64_t step,
+                                       const double* __restrict__ p, double* __restrict__ cj, double* __restrict__ pivot) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t item = items[step];
+  if (item < 0) return;
+  if (s < t) cj[s] = C[s * n + item];
+  if (s == 0) pivot[0] = p[item];
+}
+// c = (P[item][:] - sum of the partial slices) / sqrt(pivot);  C[t][:] = c;  p -= c^2 (clamped at 0; the picked item gets exactly 0)
+__global__ void dpp_chol_finish_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ tmp, int nslices,
+                                       const int64_t* __restrict__ items, int64_t step, const double* __restrict__ pivot, double* __restrict__ Crow,
+                                       double* __restrict__ p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t item = items[step];
+  if (item < 0) return;
+  double acc = 0.0;
+  for (int s = 0; s < nslices; ++s) acc += tmp[(int64_t)s * n + i];
+  const double c = (P[item * ld + i] - acc) / sqrt(pivot[0]);
+  Crow[i] = c;
+  double q = fma(-c, c, p[i]);
+  if (q < 0.0 || i == item) q = 0.0;
+  p[i] = q;
 }
 
 // ---- greedy MAP of the L-ensemble (Determinantal.greedy_subset, dpp.jl:60 [external]; Chen et al. 2018 fast greedy form) ----

@@ -195,6 +195,14 @@ ell_inclusion_prob(α::Real, n::Integer) = (p = zeros(n);
 ell_eigvecs(idx::Vector{Int64}, n::Integer) = (V = zeros(n, length(idx));                # 0-based eigenvector indices; column j = U[:, idx[j]+1]
     check(ccall((:pl_ell_eigvecs, libplb200), Cint, (Ptr{Int64}, Int64, Int64, Ptr{Cdouble}, Int64), idx, length(idx), n, V, n), "pl_ell_eigvecs"); V)
 
+# first phase of a k-DPP draw (which eigenvectors; Kulesza & Taskar Alg. 8) on the device: `αλ` the rescaled eigenvalues,
+# `esp_select(αλ, k, rand(rng, length(αλ)))` -> 0-based eigenvector indices for `ell_sample`
+function esp_select(αλ::Vector{Float64}, k::Integer, uniforms::Vector{Float64})
+    idx = zeros(Int64, k); count = Ref{Int64}(0)
+    check(ccall((:pl_esp_select, libplb200), Cint, (Ptr{Cdouble}, Int64, Int64, Ptr{Cdouble}, Ptr{Int64}, Ptr{Int64}), αλ, length(αλ), k, uniforms, idx, count), "pl_esp_select")
+    idx[1:count[]]
+end
+
 # second phase of a k-DPP draw on the resident ensemble: projection-DPP sampling over the eigenvectors `idx` (0-based) that the first phase
 # (Determinantal's ESP selection) picked; the uniforms come from the caller's RNG: `ell_sample(idx, n, rand(rng, length(idx)))` -> 1-based items
 function ell_sample(idx::Vector{Int64}, n::Integer, uniforms::Vector{Float64})

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "pl_ell_eigvecs": (_int, [ctypes.POINTER(_i64), _i64, _i64, _dp, _i64]),
     "pl_ell_sample": (_int, [ctypes.POINTER(_i64), _i64, _i64, _dp, ctypes.POINTER(_i64)]),
     "pl_ell_greedy": (_int, [_i64, _i64, ctypes.POINTER(_i64)]),
+    "pl_esp_select": (_int, [_dp, _i64, _i64, _dp, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
     "pl_rmsd_periodic": (_int, [_dp, _i64, _i64, _dp, _dp, _i64]),
     "pl_rmsd_kabsch": (_int, [_dp, _i64, _i64, _dp, _i64]),
     "pl_metrics": (_int, [_dp, _dp, _i64, _dp]),

@@ -15,6 +15,8 @@ PARITY UNPINNED for these host routines: they use numpy's RNG, not Julia's, so i
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .data import DataSet, LocalDescriptors
@@ -176,16 +178,14 @@ def _log_esp(lam, k):
     return E, loglam
 
 
-def sample(ell: EllEnsemble, k: int, rng=None):
-    """Determinantal.sample(L, k): exact k-DPP sample (Kulesza & Taskar Alg. 8 + Alg. 1). Returns sorted 0-based indices.
-    Phase 1 (which eigenvectors: elementary symmetric polynomials, O(N k)) runs on the host; phase 2 (projection-DPP sampling over
-    them, O(N k^2)) runs on the device for a resident ensemble (pl_ell_sample) and in numpy otherwise."""
-    rng = np.random.default_rng() if rng is None else rng
-    lam = np.maximum(ell.α * ell.λ, 0.0)
+def _esp_select_host(lam, k, u1):
+    """Kulesza & Taskar Alg. 8 on the host (ensembles that are not device-resident)."""
     N = len(lam)
     E, loglam = _log_esp(lam, k)
     J = []
     l = k
+    with np.errstate(divide="ignore"):
+        logu = np.log(u1)
     for n in range(N, 0, -1):
         if l == 0:
             break
@@ -194,10 +194,40 @@ def sample(ell: EllEnsemble, k: int, rng=None):
             l = 0
             break
         logp = loglam[n - 1] + E[l - 1, n - 1] - E[l, n]
-        if np.log(rng.random()) < logp:
+        if logu[N - n] < logp:
             J.append(n - 1)
             l -= 1
-    if ell._resident and _resident_owner is ell and len(J) > 0:
+    return J
+
+
+def _esp_select_device(lam, k, u1):
+    """the same selection by pl_esp_select: the (N+1) x (k+1) table is built and walked on the device"""
+    import ctypes
+
+    lam = np.ascontiguousarray(lam, dtype=np.float64)
+    u1 = np.ascontiguousarray(u1, dtype=np.float64)
+    idx = np.empty(max(k, 1), dtype=np.int64)
+    cnt = ctypes.c_int64(0)
+    _lib.check(_lib.lib().pl_esp_select(_lib.dptr(lam), len(lam), int(k), _lib.dptr(u1), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                        ctypes.byref(cnt)), "pl_esp_select")
+    return [int(i) for i in idx[: cnt.value]]
+
+
+def sample(ell: EllEnsemble, k: int, rng=None):
+    """Determinantal.sample(L, k): exact k-DPP sample (Kulesza & Taskar Alg. 8 + Alg. 1). Returns sorted 0-based indices.
+    For a device-resident ensemble both phases run on the GPU: phase 1 (which eigenvectors: elementary symmetric polynomials, O(N k),
+    pl_esp_select) and phase 2 (projection-DPP sampling over them, pl_ell_sample); the uniforms of both come from `rng`. Ensembles that
+    are not resident (built from host eigenpairs) use the numpy forms of the same two phases."""
+    rng = np.random.default_rng() if rng is None else rng
+    lam = np.maximum(ell.α * ell.λ, 0.0)
+    N = len(lam)
+    u1 = rng.random(N)  # one uniform per eigenvalue, visited from the last one down (u1[N - n] decides eigenvalue n)
+    on_device = ell._resident and _resident_owner is ell
+    if on_device and not os.environ.get("PLB200_ESP_HOST") and (N + 1) * (k + 2) * 8 <= 24 * 2**30:
+        J = _esp_select_device(lam, k, u1)
+    else:
+        J = _esp_select_host(lam, k, u1)
+    if on_device and len(J) > 0:
         # second phase on the device (pl_ell_sample): U stays where it is, the uniforms come from this generator
         import ctypes
 

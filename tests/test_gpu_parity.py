@@ -5,6 +5,8 @@ regressions show long before the contract is at risk). Kernel matrices are compa
 are > 0), SYRK-type results norm-wise (max |diff| / max |ref|) plus element-wise where |ref| > 1e-3 max.
 The first blocks re-state the reference's own tests (shapes d=8, 20 atoms, 10/8/100 configs).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -1281,11 +1283,18 @@ def test_device_kdpp_sampler(pl, orc):
         J = np.sort(rng.choice(np.arange(n - 80, n), size=m, replace=False)).astype(np.int64)  # among the 80 largest eigenvalues
         u = rng.random(m)
         out = np.empty(m, dtype=np.int64)
-        _lib.check(_lib.lib().pl_ell_sample(J.ctypes.data_as(i64p), m, n, _lib.dptr(u), out.ctypes.data_as(i64p)), "pl_ell_sample")
         V = ell.eigvecs(J)  # the same device-resident eigenvectors, downloaded
         ref = orc.sample_projection_dpp(V, u)
-        assert list(out) == ref, (m, list(out), ref)
-        assert len(set(out.tolist())) == m
+        for form in ("kernel-row", "gram-schmidt"):  # n <= 32768 takes the kernel-row (Cholesky) form; PLB200_DPP_GS forces the other
+            if form == "gram-schmidt":
+                os.environ["PLB200_DPP_GS"] = "1"
+            try:
+                out[:] = -7
+                _lib.check(_lib.lib().pl_ell_sample(J.ctypes.data_as(i64p), m, n, _lib.dptr(u), out.ctypes.data_as(i64p)), "pl_ell_sample")
+            finally:
+                os.environ.pop("PLB200_DPP_GS", None)
+            assert list(out) == ref, (form, m, list(out), ref)
+            assert len(set(out.tolist())) == m
     # statistics of full k-DPP draws through the mirror (phase 1 on the host, phase 2 on the device)
     n2, k = 40, 6
     X2 = rng.standard_normal((n2, 5)) + 1.0
@@ -1315,6 +1324,55 @@ def test_device_kdpp_sampler(pl, orc):
     assert abs(pin.sum() - k) < 1e-8
     se = np.sqrt(pin * (1 - pin) / ndraw)
     assert np.all(np.abs(cnt / ndraw - pin) < 5 * se + 1e-3), float(np.max(np.abs(cnt / ndraw - pin) / se))
+
+
+def test_device_esp_selection(pl, orc):
+    """pl_esp_select (first phase of a k-DPP draw, Kulesza & Taskar Alg. 8, built by one thread-block cluster): the eigenvectors of the
+    oracle's restatement for the same eigenvalues and uniforms — spread-out spectra (hundreds of orders of magnitude in e_k), zero
+    eigenvalues, k = 1, k = n - 1, k = number of positive eigenvalues; through the mirror, a draw with the table on the device equals the
+    draw with the table on the host for the same generator."""
+    import ctypes
+
+    from plb200 import _lib
+
+    rng = np.random.default_rng(404)
+    i64p = ctypes.POINTER(ctypes.c_int64)
+
+    def dev(lam, k, u):
+        idx = np.full(max(k, 1), -5, dtype=np.int64)
+        cnt = ctypes.c_int64(-1)
+        _lib.check(_lib.lib().pl_esp_select(_lib.dptr(lam), len(lam), k, _lib.dptr(u), idx.ctypes.data_as(i64p), ctypes.byref(cnt)), "pl_esp_select")
+        return [int(i) for i in idx[: cnt.value]]
+
+    cases = []
+    for N, k in [(40, 6), (257, 31), (300, 1), (64, 63), (1000, 400), (9000, 20)]:
+        cases.append((np.sort(rng.random(N) ** 4 * 50.0), k))
+    lamz = np.sort(rng.random(120) * 2.0)
+    lamz[:70] = 0.0
+    cases += [(lamz, 50), (lamz, 17), (np.sort(10.0 ** rng.uniform(-30, 30, 500)), 120)]
+    for lam, k in cases:
+        lam = np.ascontiguousarray(lam)
+        u = rng.random(len(lam))
+        got = dev(lam, k, u)
+        ref = orc.select_eigenvectors_kdpp(lam, k, u)
+        assert got == ref, (len(lam), k, got[:10], ref[:10])
+        assert len(got) == k
+    assert dev(lamz, 0, rng.random(120)) == []
+    with pytest.raises(_lib.PLB200Error):
+        dev(lamz, 51, rng.random(120))  # only 50 positive eigenvalues
+    with pytest.raises(_lib.PLB200Error):
+        dev(np.array([1.0, -1.0, 2.0]), 1, rng.random(3))
+    # through the mirror
+    X = rng.standard_normal((200, 6)) * 0.5 + 1.0
+    ell = pl.EllEnsemble.from_features(X, pl.RBF(pl.Euclidean(6), ell=1.2))
+    pl.rescale_(ell, 30)
+    a = pl.sample(ell, 30, rng=np.random.default_rng(9))
+    os.environ["PLB200_ESP_HOST"] = "1"
+    try:
+        b = pl.sample(ell, 30, rng=np.random.default_rng(9))
+    finally:
+        os.environ.pop("PLB200_ESP_HOST", None)
+    assert a == b and len(set(a)) == 30
 
 
 def test_device_greedy_map(pl, orc):

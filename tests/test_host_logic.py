@@ -142,3 +142,34 @@ def test_random_selector():
     s = pl.get_random_subset(r, rng=np.random.default_rng(0))
     assert len(s) == 2 and len(set(s)) == 2 and all(isinstance(i, int) and 0 <= i < 10 for i in s)
     assert sorted(pl.get_random_subset(pl.RandomSelector(7), rng=np.random.default_rng(1))) == list(range(7))
+
+
+def test_kdpp_eigenvector_selection_host_vs_oracle():
+    """phase 1 of a k-DPP draw (Kulesza & Taskar Alg. 8): the mirror's numpy form picks the oracle's eigenvectors for the same uniforms,
+    and the oracle's selection frequencies match the exact probabilities lam_j e_{k-1}(lam \\ j) / e_k(lam)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle as orc
+    from plb200 import dpp
+
+    rng = np.random.default_rng(0)
+    for N, k in [(40, 6), (200, 50), (300, 1), (50, 50), (60, 59)]:
+        lam = np.sort(rng.random(N) ** 3 * 5)
+        u = rng.random(N)
+        a = orc.select_eigenvectors_kdpp(lam, k, u)
+        assert a == dpp._esp_select_host(lam, k, u) and len(a) == k and sorted(a, reverse=True) == a
+    N, k, nd = 12, 4, 6000
+    lam = rng.random(N) * 3
+
+    def esp(v, kk):
+        e = np.zeros(kk + 1)
+        e[0] = 1
+        for x in v:
+            e[1:] = e[1:] + x * e[:-1]
+        return e[kk]
+
+    w = np.array([lam[j] * esp(np.delete(lam, j), k - 1) / esp(lam, k) for j in range(N)])
+    cnt = np.zeros(N)
+    for _ in range(nd):
+        cnt[orc.select_eigenvectors_kdpp(lam, k, rng.random(N))] += 1
+    assert np.max(np.abs(cnt / nd - w) / np.sqrt(w * (1 - w) / nd)) < 5.0
