@@ -69,6 +69,9 @@ int pl_last_timing(double* kernel_ms, double* h2d_ms, double* d2h_ms);
 int64_t pl_launch_count(void);
 /* bytes of device workspace currently held by the library. */
 int64_t pl_workspace_bytes(void);
+/* Frees the library's device scratch (it is grown lazily and otherwise kept until pl_finalize). keep_resident != 0 keeps the resident
+ * L-ensemble (pl_ell_*) and an open normal-equation accumulator (pl_neq_*); 0 drops them as well. */
+int pl_workspace_trim(int keep_resident);
 /* on != 0: the dominant DMMA kernel (Gram or SYRK) of every following operation is bracketed by CUDA events on the
  * stream it is launched on; pl_last_main_kernel_ms waits for it and returns its duration (roofline measurements). */
 int pl_set_profiling(int on);

@@ -1077,6 +1077,31 @@ int64_t pl_workspace_bytes(void) {
   return tot;
 }
 
+// Hands the library's device scratch back to the driver (it only ever grows otherwise: a k = 10 000 draw at n = 20 000 leaves 6.4 GB of
+// factors behind). keep_resident != 0 keeps what later calls depend on: the resident L-ensemble (eigenvectors, eigenvalues, kernel
+// matrix) and an open normal-equation accumulator; 0 drops those too (pl_ell_* then ask for a new pl_ell_ensemble, pl_neq_add for a
+// new pl_neq_begin).
+int pl_workspace_trim(int keep_resident) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PL_TRY(need_ready());
+  CUDA_TRY(cudaSetDevice(g.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (int i = 0; i < WS_NSLOTS; ++i) {
+    if (keep_resident) {
+      if (ell_state.valid && (i == WS_EIG_A || i == WS_EIG_W || i == WS_ELL_K)) continue;
+      if (neq_state.open && (i == WS_ACC_S || i == WS_ACC_V)) continue;
+    }
+    if (g.ws[i]) CUDA_TRY(cudaFree(g.ws[i]));
+    g.ws[i] = nullptr;
+    g.ws_bytes[i] = 0;
+  }
+  if (!keep_resident) {
+    ell_state.valid = false;
+    neq_state.open = false;
+  }
+  return PL_OK;
+}
+
 int pl_gram_dev(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, const double* dX2, int64_t n2, int64_t ldx2, int64_t d, int alpha,
                 int cinv_kind, const double* dcinv, double ell, double beta, double* dOut, int64_t ldo, int fill, int part, int nparts, int packed,
                 void* stream) {

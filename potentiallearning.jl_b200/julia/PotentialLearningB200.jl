@@ -195,6 +195,10 @@ ell_inclusion_prob(α::Real, n::Integer) = (p = zeros(n);
 ell_eigvecs(idx::Vector{Int64}, n::Integer) = (V = zeros(n, length(idx));                # 0-based eigenvector indices; column j = U[:, idx[j]+1]
     check(ccall((:pl_ell_eigvecs, libplb200), Cint, (Ptr{Int64}, Int64, Int64, Ptr{Cdouble}, Int64), idx, length(idx), n, V, n), "pl_ell_eigvecs"); V)
 
+# device scratch held by the library / hand it back (keep_resident = false also drops the resident L-ensemble and an open accumulator)
+workspace_bytes() = ccall((:pl_workspace_bytes, libplb200), Int64, ())
+workspace_trim(keep_resident::Bool = true) = check(ccall((:pl_workspace_trim, libplb200), Cint, (Cint,), keep_resident ? 1 : 0), "pl_workspace_trim")
+
 # first phase of a k-DPP draw (which eigenvectors; Kulesza & Taskar Alg. 8) on the device: `αλ` the rescaled eigenvalues,
 # `esp_select(αλ, k, rand(rng, length(αλ)))` -> 0-based eigenvector indices for `ell_sample`
 function esp_select(αλ::Vector{Float64}, k::Integer, uniforms::Vector{Float64})

@@ -4,13 +4,13 @@ Layout: csrc/ (sm_100a CUDA + C ABI -> plb200/libplb200.so), plb200/ (this packa
 operator interface for the path), julia/ (the ccall shim a Julia deployment loads). See DESIGN.md / INTEGRATION.md.
 """
 from . import _lib
-from ._lib import PLB200Error, finalize, init, last_timing, launch_count, pinned_zeros
+from ._lib import PLB200Error, finalize, init, last_timing, launch_count, pinned_zeros, workspace_bytes
 from .data import (Configuration, DataSet, Energy, ForceDescriptors, Forces, LocalDescriptors, get_energy, get_force_descriptors,
                    get_forces, get_local_descriptors, get_values)
 from .dimred import (PCA, ActiveSubspace, DimensionReducer, PCAState, compute_eigen, covariance, fit, fit_, project, select_eigendirections,
                      transform_)
 from .dpp import (DBSCANSelector, EllEnsemble, RandomSelector, SubsetSelector, distance_matrix_kabsch, distance_matrix_periodic, get_dpp_mode, get_inclusion_prob, get_random_subset, greedy_subset, inclusion_prob, kDPP,
-                  rescale_, sample)
+                  rescale_, sample, workspace_trim)
 from .kernels import (RBF, CorrelationMatrix, Diagonal, Distance, Divergence, DotProduct, KernelSteinDiscrepancy, compute_divergence, Euclidean, Feature, GlobalMean, GlobalSum, InverseMultiquadric, Kernel,
                       KernelMatrix, Symmetric,
                       compute_distance, compute_feature, compute_features, compute_kernel, correlation_features, get_parameters, global_features, global_features_dev,

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "pl_last_timing": (_int, [_dp, _dp, _dp]),
     "pl_launch_count": (_i64, []),
     "pl_workspace_bytes": (_i64, []),
+    "pl_workspace_trim": (_int, [_int]),
     "pl_set_profiling": (_int, [_int]),
     "pl_last_main_kernel_ms": (_int, [_dp]),
     "pl_host_alloc": (_vp, [_i64]),
@@ -151,6 +152,11 @@ def last_main_kernel_ms() -> float:
 
 def launch_count() -> int:
     return int(load().pl_launch_count())
+
+
+def workspace_bytes() -> int:
+    """device scratch currently held by the library"""
+    return int(load().pl_workspace_bytes())
 
 
 def dptr(a: np.ndarray | None):

@@ -144,6 +144,14 @@ class EllEnsemble:
         _resident_owner = None
 
 
+def workspace_trim(keep_resident: bool = True):
+    """pl_workspace_trim: hand the library's device scratch back (it only grows otherwise). keep_resident=False also drops the resident
+    L-ensemble (small ones are downloaded first, like any eviction) and an open normal-equation accumulator."""
+    if not keep_resident and _resident_owner is not None:
+        _resident_owner._evict()
+    _lib.check(_lib.lib().pl_workspace_trim(1 if keep_resident else 0), "pl_workspace_trim")
+
+
 def rescale_(ell: EllEnsemble, k: int):
     """rescale!(L, k): pick α so that the expected cardinality sum(αλ/(1+αλ)) equals k (bisection in log α)."""
     lam = ell.λ

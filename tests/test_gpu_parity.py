@@ -1511,3 +1511,33 @@ def test_pageable_staging_paths(pl, orc):
     assert np.array_equal(K1, K2) and np.array_equal(K1f, K2f) and np.array_equal(Kx1, Kx2)
     assert np.array_equal(M1, M2) and np.array_equal(v1, v2) and np.array_equal(M3, M4) and np.array_equal(v3, v4)
     assert relerr(K1f[:200, :200], orc.symmetric(orc.kernel_matrix(X[:200], orc.RBF(orc.Euclidean(40), ell=2.0)))) < RTOL
+
+
+def test_workspace_trim(pl, orc):
+    """pl_workspace_trim: scratch goes back to the driver; with keep_resident the resident L-ensemble keeps answering (same inclusion
+    probabilities, same draw), without it the pl_ell_* entries ask for a new ensemble; everything regrows on demand."""
+    rng = np.random.default_rng(77)
+    X = rng.standard_normal((700, 12)) * 0.5 + 1.0
+    k = pl.RBF(pl.Euclidean(12), ell=1.5)
+    ell = pl.EllEnsemble.from_features(X, k)
+    pl.rescale_(ell, 60)
+    p0 = pl.inclusion_prob(ell)
+    s0 = pl.sample(ell, 60, rng=np.random.default_rng(3))
+    before = pl.workspace_bytes()
+    pl.workspace_trim(True)
+    mid = pl.workspace_bytes()
+    assert 0 < mid < before
+    assert np.array_equal(pl.inclusion_prob(ell), p0)
+    assert pl.sample(ell, 60, rng=np.random.default_rng(3)) == s0
+    K1 = np.asarray(pl.KernelMatrix(list(X), k))
+    pl.workspace_trim(False)
+    assert pl.workspace_bytes() == 0
+    assert not ell._resident
+    import ctypes
+
+    from plb200 import _lib
+
+    out = np.empty(700)
+    assert _lib.lib().pl_ell_inclusion_prob(1.0, 700, _lib.dptr(out)) != 0  # no resident ensemble any more
+    assert np.allclose(pl.inclusion_prob(ell), p0, rtol=0, atol=1e-12)  # the mirror downloaded U before the eviction (n <= 4096)
+    assert np.array_equal(np.asarray(pl.KernelMatrix(list(X), k)), K1)
