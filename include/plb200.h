@@ -252,6 +252,14 @@ int64_t pl_gram_tile_count(int64_t n1, int64_t n2, int part, int nparts);
 /* tile-row / tile-column (units of 128) of the k-th tile owned by `part`; returns 0 or PL_EINVAL */
 int pl_gram_tile_coords(int64_t n1, int64_t n2, int part, int nparts, int64_t k, int64_t* ti, int64_t* tj);
 
+/* The schedule pl_syrk_dev would use for an R x Kf matrix on a device with num_sms SMs, as a table (host arithmetic only; no device
+ * needed): rows (cta, unit, first_stage, nstages, slot) — CTA `cta` streams `nstages` stages of 16 rows of work unit `unit` from stage
+ * `first_stage` and writes its partial to workspace slot `slot`. mode 0: "waves" (one piece per CTA, ~20 short CTAs per SM);
+ * mode 1: "streamk" (the cost-weighted work cut into num_sms x waves equal intervals, a CTA crossing unit boundaries without refilling
+ * its pipeline). waves <= 0 / diag_cost <= 0: library defaults. table may be NULL (counts only). For tests and tools. */
+int pl_syrk_schedule(int64_t R, int64_t Kf, int num_sms, int mode, int waves, double diag_cost, int64_t capacity, int* table, int64_t* npieces,
+                     int64_t* nctas);
+
 /* Partial weighted SYRK of a row shard: S = sum_r w_r (a_r-m)(a_r-m)' and, if dvec != NULL,
  * v = sum_r w_r b_r a_r, c = sum_{r<n_energy_rows} w_r a_r, s = [sum_{r<ne} w_r, sum_{r<ne} w_r b_r].
  * dmean == NULL -> no centring. Outputs are UNSCALED sums so shards can be all-reduced:

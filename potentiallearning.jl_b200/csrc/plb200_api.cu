@@ -8,11 +8,13 @@
 #include <dlfcn.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/plb200.h"
 #include "gram.cuh"
@@ -99,6 +101,7 @@ enum WsSlot {
   WS_EIG_IDX,
   WS_EIG_SEL,
   WS_TRACE,
+  WS_SYRK_SCHED,
   WS_SYRK_AUX,
   WS_ACC_S,
   WS_ACC_V,
@@ -510,29 +513,139 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
   return launch_gram(L, st);
 }
 
-void choose_splits(int64_t R, int nunits, int* splits, int64_t* rows_per_split) {
-  // One CTA per (work unit, row split), one CTA resident per SM. Work units are not equal (a diagonal unit costs ~1.06-1.19 x an
-  // off-diagonal one) and the hardware hands CTAs to SMs as they free up, so the makespan is total/148 plus about one CTA: keep CTAs
-  // SHORT — ~20 per SM (measured with the trace hook: 5-6 long CTAs per SM left 9 % of the machine idle at the tail) — while each
-  // still streams >= 1024 rows (64 pipeline stages) so that pipeline fill and the 160 KB partial it writes stay below 1 %.
-  static const int waves = [] {
-    const char* e = getenv("PLB200_SYRK_WAVES");
-    const int v = e ? atoi(e) : 0;
-    return v > 0 ? v : 20;
+// ---- SYRK schedule: which CTA runs which (work unit, row range) pieces ----
+// One CTA is resident per SM. Work units are not equal (a diagonal unit costs ~1.06-1.19 x an off-diagonal one) and SMs do not all run
+// at the same speed, so two schedules are built here as plain tables the kernel walks (syrk.cuh: SyrkPiece):
+//   * "waves" (PLB200_SYRK_SCHED=waves): one piece per CTA, ~20 short CTAs per SM dealt out by the hardware as SMs free up (measured
+//     with the trace hook: 5-6 long CTAs per SM left 9 % of the machine idle at the tail), each streaming >= 1024 rows;
+//   * "streamk" (default; PLB200_SYRK_SCHED=sk<w>, w = 4): the linearised work (unit-major, costs weighted) is cut into 148 x w
+//     equal-cost intervals; a CTA runs its interval through ONE pipeline (no refill at a unit boundary) and writes one partial per unit
+//     it touches. Fewer partials (148 w + units instead of ~3000 x 160 KB), w pipeline fills per SM instead of 20, and the w-fold
+//     over-decomposition still lets the hardware even out SM speed differences. Measured (profiles/r01_syrk_schedules.json): config 3
+//     22.5 -> 22.15 ms, a per-GPU eighth of it 2.95 -> 2.81 ms, config 4 quarter 80.3 -> 77.5 ms; w = 4..8 and cost 1.12..1.16 are flat.
+// Either way the partial slots of a unit are contiguous and in row order, so the second-stage sum is deterministic.
+struct SyrkSchedule {
+  std::vector<int> cta_first, unit_first;
+  std::vector<SyrkPiece> pieces;
+  int nctas = 0, nslots = 0;
+};
+
+struct SyrkSchedConfig {
+  int mode;        // 0 waves, 1 streamk
+  int waves;       // CTAs per SM
+  double diag_cost;
+};
+
+const SyrkSchedConfig& syrk_sched_config() {
+  static const SyrkSchedConfig cfg = [] {
+    SyrkSchedConfig c;
+    c.mode = 1;
+    c.waves = 0;
+    c.diag_cost = 1.15;  // measured optimum 1.12-1.16 (flat); the DMMA count alone says 1.125
+    const char* e = getenv("PLB200_SYRK_SCHED");
+    if (e && !strncmp(e, "waves", 5)) c.mode = 0;
+    else if (e && !strncmp(e, "sk", 2)) c.waves = atoi(e + 2);
+    const char* w = getenv("PLB200_SYRK_WAVES");
+    if (w && atoi(w) > 0) c.waves = atoi(w);
+    if (c.waves <= 0) c.waves = c.mode == 0 ? 20 : 4;
+    const char* dc = getenv("PLB200_SYRK_DIAG_COST");
+    if (dc && atof(dc) > 0.0) c.diag_cost = atof(dc);
+    return c;
   }();
-  int64_t s = ((int64_t)g.num_sms * waves + nunits - 1) / nunits;
-  int64_t max_by_rows = R / 1024;
-  if (max_by_rows < 1) max_by_rows = 1;
-  if (s > max_by_rows) s = max_by_rows;
-  if (s < 1) s = 1;
-  int64_t rps = (R + s - 1) / s;
-  rps = (rps + SYRK_BK - 1) / SYRK_BK * SYRK_BK;
-  if (rps < SYRK_BK) rps = SYRK_BK;
-  s = (R + rps - 1) / rps;
-  if (s < 1) s = 1;
-  *splits = (int)s;
-  *rows_per_split = rps;
+  return cfg;
 }
+
+void build_syrk_schedule(int64_t R, int T, int nunits, int num_sms, const SyrkSchedConfig& cfg, SyrkSchedule* out) {
+  out->pieces.clear();
+  out->cta_first.clear();
+  out->unit_first.assign(nunits + 1, 0);
+  const int64_t nst = (R + SYRK_BK - 1) / SYRK_BK;  // pipeline stages per unit
+  if (nst == 0) {
+    out->nctas = 1;
+    out->nslots = 0;
+    out->cta_first.assign(2, 0);
+    return;
+  }
+  if (cfg.mode == 0) {
+    int64_t s = ((int64_t)num_sms * cfg.waves + nunits - 1) / nunits;
+    int64_t max_by_rows = R / 1024;
+    if (max_by_rows < 1) max_by_rows = 1;
+    if (s > max_by_rows) s = max_by_rows;
+    if (s < 1) s = 1;
+    int64_t sps = (nst + s - 1) / s;  // stages per split
+    s = (nst + sps - 1) / sps;
+    for (int64_t sp = 0; sp < s; ++sp)
+      for (int u = 0; u < nunits; ++u) {  // unit fastest: the dispatch order of the (unit, split) grid
+        const int64_t f = sp * sps;
+        const int64_t n = f + sps <= nst ? sps : nst - f;
+        out->cta_first.push_back((int)out->pieces.size());
+        out->pieces.push_back(SyrkPiece{u, (int)f, (int)n, (int)(u * s + sp)});
+      }
+    out->cta_first.push_back((int)out->pieces.size());
+    for (int u = 0; u <= nunits; ++u) out->unit_first[u] = (int)(u * s);
+    out->nctas = (int)(s * nunits);
+    out->nslots = (int)(s * nunits);
+    return;
+  }
+  // streamk: positions are (unit, stage) linearised as unit * nst + stage; boundaries at equal cumulative cost
+  const int noff = T * (T - 1) / 2;
+  std::vector<double> cum(nunits + 1, 0.0);
+  for (int u = 0; u < nunits; ++u) cum[u + 1] = cum[u] + (u < noff ? 1.0 : cfg.diag_cost) * (double)nst;
+  const double total = cum[nunits];
+  int64_t G = (int64_t)num_sms * cfg.waves;
+  const int64_t max_ctas = ((int64_t)nunits * nst + 63) / 64;  // a CTA should stream >= 64 stages (1024 rows)
+  if (G > max_ctas) G = max_ctas;
+  if (G < 1) G = 1;
+  const int64_t snap = nst < 64 ? nst : 16;  // boundaries this close to a unit edge move onto it (no tiny pieces)
+  std::vector<int64_t> pos(G + 1);
+  int u = 0;
+  for (int64_t q = 0; q <= G; ++q) {
+    const double target = total * (double)q / (double)G;
+    while (u < nunits - 1 && cum[u + 1] <= target) ++u;
+    const double c = (u < noff ? 1.0 : cfg.diag_cost);
+    int64_t st = (int64_t)llround((target - cum[u]) / c);
+    if (st < 0) st = 0;
+    if (st > nst) st = nst;
+    if (st < snap) st = 0;
+    else if (nst - st < snap) st = nst;
+    pos[q] = (int64_t)u * nst + st;
+  }
+  pos[0] = 0;
+  pos[G] = (int64_t)nunits * nst;
+  for (int64_t q = 1; q <= G; ++q)
+    if (pos[q] < pos[q - 1]) pos[q] = pos[q - 1];
+  int last_unit = -1;
+  for (int64_t q = 0; q < G; ++q) {
+    out->cta_first.push_back((int)out->pieces.size());
+    int64_t a0 = pos[q];
+    const int64_t a1 = pos[q + 1];
+    while (a0 < a1) {
+      const int un = (int)(a0 / nst);
+      const int64_t f = a0 % nst;
+      int64_t e = (int64_t)(un + 1) * nst;
+      if (e > a1) e = a1;
+      const int slot = (int)out->pieces.size();
+      if (un != last_unit) {
+        for (int v = last_unit + 1; v <= un; ++v) out->unit_first[v] = slot;
+        last_unit = un;
+      }
+      out->pieces.push_back(SyrkPiece{un, (int)f, (int)(e - a0), slot});
+      a0 = e;
+    }
+  }
+  out->cta_first.push_back((int)out->pieces.size());
+  for (int v = last_unit + 1; v <= nunits; ++v) out->unit_first[v] = (int)out->pieces.size();
+  out->nctas = (int)G;
+  out->nslots = (int)out->pieces.size();
+}
+
+// the schedule of the last shape stays on the device (same shape again: no rebuild, no upload)
+struct SyrkSchedCache {
+  int64_t R = -1;
+  int T = -1;
+  const void* dev = nullptr;
+  SyrkSchedule sch;
+} g_sched;
 
 // drho_out (centred mode, optional): rho = sum_r (a_r - mean) of this shard, the by-product of the one-sided centring
 int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dw, int64_t ne, double w_e, double w_f, const double* db,
@@ -558,9 +671,31 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
   p.mean = dmean;
   p.T = (int)((Kf + SYRK_BT - 1) / SYRK_BT);
   p.ntiles = syrk_num_units(p.T);
-  choose_splits(R, p.ntiles, &p.splits, &p.rows_per_split);
+  if (g_sched.R != R || g_sched.T != p.T || g_sched.dev == nullptr || g_sched.dev != g.ws[WS_SYRK_SCHED]) {
+    build_syrk_schedule(R, p.T, p.ntiles, g.num_sms, syrk_sched_config(), &g_sched.sch);
+    const SyrkSchedule& sc = g_sched.sch;
+    const size_t n1 = sc.cta_first.size(), n2 = sc.unit_first.size(), n3 = sc.pieces.size() * 4;
+    void* dsch;
+    PL_TRY(ws_get(WS_SYRK_SCHED, (n1 + n2 + n3 + 4) * sizeof(int), &dsch));
+    int* di = (int*)dsch;
+    // pageable sources: the copies are staged before the calls return, so the vectors may change afterwards
+    CUDA_TRY(cudaMemcpyAsync(di, sc.cta_first.data(), n1 * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(di + n1, sc.unit_first.data(), n2 * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (n3) CUDA_TRY(cudaMemcpyAsync(di + ((n1 + n2 + 3) & ~(size_t)3), sc.pieces.data(), n3 * sizeof(int), cudaMemcpyHostToDevice, st));
+    g_sched.R = R;
+    g_sched.T = p.T;
+    g_sched.dev = dsch;
+  }
+  const SyrkSchedule& sc = g_sched.sch;
+  {
+    const size_t n1 = sc.cta_first.size(), n2 = sc.unit_first.size();
+    const int* di = (const int*)g_sched.dev;
+    p.cta_first = di;
+    p.pieces = (const SyrkPiece*)(di + ((n1 + n2 + 3) & ~(size_t)3));  // 16-byte aligned
+  }
+  const int* d_unit_first = (const int*)g_sched.dev + sc.cta_first.size();
   void* wst;
-  PL_TRY(ws_get(WS_SYRK_TILES, (size_t)p.splits * p.ntiles * SYRK_TILE_ELEMS * 8, &wst));
+  PL_TRY(ws_get(WS_SYRK_TILES, (size_t)(sc.nslots > 0 ? sc.nslots : 1) * SYRK_TILE_ELEMS * 8, &wst));
   void* rho = nullptr;
   if (dmean) PL_TRY(ws_get(WS_SYRK_RHO, (size_t)Kf * 8, &rho));
   p.ws_tiles = (double*)wst;
@@ -570,8 +705,8 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
   p.trace = nullptr;
   if (trace_path && *trace_path) {
     void* tr;
-    PL_TRY(ws_get(WS_TRACE, (size_t)p.ntiles * p.splits * 10 * 8, &tr));
-    CUDA_TRY(cudaMemsetAsync(tr, 0, (size_t)p.ntiles * p.splits * 10 * 8, st));
+    PL_TRY(ws_get(WS_TRACE, (size_t)sc.nctas * 10 * 8, &tr));
+    CUDA_TRY(cudaMemsetAsync(tr, 0, (size_t)sc.nctas * 10 * 8, st));
     p.trace = (long long*)tr;
   }
 
@@ -592,7 +727,7 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
     PL_TRY(make_tmap_2d(&tmx, (const double*)aux, 16, R, 16, 16, SYRK_BK));
     p.aux_box = (int)(Kf / 16);
   }
-  dim3 grid((unsigned)p.ntiles, (unsigned)p.splits);
+  dim3 grid((unsigned)sc.nctas);
   MAIN_KERNEL_BEGIN(st);
   if (dmean)
     syrk_kernel<true><<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, st>>>(tm, tmx, p);
@@ -601,21 +736,23 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
   LAUNCH_CHECK();
   MAIN_KERNEL_END(st);
   if (p.trace) {
-    const size_t cnt = (size_t)p.ntiles * p.splits * 10;
+    const size_t cnt = (size_t)sc.nctas * 10;
     long long* h = (long long*)malloc(cnt * 8);
     if (h) {
       CUDA_TRY(cudaMemcpyAsync(h, p.trace, cnt * 8, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
       FILE* f = fopen(trace_path, "w");
       if (f) {
-        fprintf(f, "# units %d splits %d T %d R %lld Kf %lld\n", p.ntiles, p.splits, p.T, (long long)R, (long long)Kf);
-        for (int sp = 0; sp < p.splits; ++sp)
-          for (int u = 0; u < p.ntiles; ++u) {
-            const long long* e = h + ((size_t)sp * p.ntiles + u) * 10;
-            fprintf(f, "%d %d %lld %lld", u, sp, e[0], e[1]);
-            for (int w = 0; w < 8; ++w) fprintf(f, " %lld", e[2 + w]);
-            fprintf(f, "\n");
-          }
+        fprintf(f, "# units %d ctas %d T %d R %lld Kf %lld slots %d\n", p.ntiles, sc.nctas, p.T, (long long)R, (long long)Kf, sc.nslots);
+        for (int q = 0; q < sc.nctas; ++q) {  // first unit of the CTA, CTA index, start, SM, end of the 8 consumer warps, stages
+          const long long* e = h + (size_t)q * 10;
+          const int pc0 = sc.cta_first[q], pc1 = sc.cta_first[q + 1];
+          long long stages = 0;
+          for (int pc = pc0; pc < pc1; ++pc) stages += sc.pieces[pc].nstages;
+          fprintf(f, "%d %d %lld %lld", pc1 > pc0 ? sc.pieces[pc0].unit : -1, q, e[0], e[1]);
+          for (int w = 0; w < 8; ++w) fprintf(f, " %lld", e[2 + w]);
+          fprintf(f, " %lld %d\n", stages, pc1 - pc0);
+        }
         fclose(f);
       }
       free(h);
@@ -630,7 +767,7 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
     // rho_i = sum_r (a_ri - m_i) closes the one-sided centring (S_ij = S'_ij - rho_i m_j): one HBM-rate pass, differences first
     PL_TRY(colsum(A, R, Kf, ld, 0.0, (double*)rho, st, dmean));
   }
-  syrk_reduce_kernel<<<dim3((unsigned)p.ntiles, SYRK_TILE_ELEMS / 256), 256, 0, st>>>(p.ws_tiles, p.T, p.ntiles, p.splits, Kf, dS, (dmean && !aug) ? dmean : nullptr,
+  syrk_reduce_kernel<<<dim3((unsigned)p.ntiles, SYRK_TILE_ELEMS / 256), 256, 0, st>>>(p.ws_tiles, p.T, d_unit_first, Kf, dS, (dmean && !aug) ? dmean : nullptr,
                                                                                    (const double*)rho, augvec);
   LAUNCH_CHECK();
   if (dmean && aug) {
@@ -1131,6 +1268,34 @@ int pl_gram_tile_coords(int64_t n1, int64_t n2, int part, int nparts, int64_t k,
   if (!gram_slot_to_tile(T1, T2, sym, k * nparts + part, a, b)) a = b = -1;
   if (ti) *ti = a;
   if (tj) *tj = b;
+  return PL_OK;
+}
+
+// The SYRK schedule as a table (host arithmetic only, no device needed): which CTA runs which (unit, stage range) piece and where its
+// partial goes. mode 0 = waves, 1 = streamk; waves <= 0 / diag_cost <= 0 take the library defaults. Rows of `table`: (cta, unit,
+// first_stage, nstages, slot). Used by the CPU tests of the scheduling invariants and by tools.
+int pl_syrk_schedule(int64_t R, int64_t Kf, int num_sms, int mode, int waves, double diag_cost, int64_t capacity, int* table, int64_t* npieces,
+                     int64_t* nctas) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (R < 0 || Kf <= 0 || num_sms <= 0 || (mode != 0 && mode != 1)) return set_err(PL_EINVAL, "bad arguments");
+  SyrkSchedConfig cfg = syrk_sched_config();
+  cfg.mode = mode;
+  cfg.waves = waves > 0 ? waves : (mode == 0 ? 20 : 4);
+  if (diag_cost > 0.0) cfg.diag_cost = diag_cost;
+  const int T = (int)((Kf + SYRK_BT - 1) / SYRK_BT);
+  SyrkSchedule sc;
+  build_syrk_schedule(R, T, syrk_num_units(T), num_sms, cfg, &sc);
+  if (npieces) *npieces = (int64_t)sc.pieces.size();
+  if (nctas) *nctas = sc.nctas;
+  if (table) {
+    if (capacity < (int64_t)sc.pieces.size()) return set_err(PL_EINVAL, "table holds %lld rows, the schedule has %zu", (long long)capacity, sc.pieces.size());
+    for (int q = 0; q < sc.nctas; ++q)
+      for (int pc = sc.cta_first[q]; pc < sc.cta_first[q + 1]; ++pc) {
+        const SyrkPiece& x = sc.pieces[pc];
+        int* row = table + (size_t)pc * 5;
+        row[0] = q; row[1] = x.unit; row[2] = x.first_stage; row[3] = x.nstages; row[4] = x.slot;
+      }
+  }
   return PL_OK;
 }
 

@@ -7,11 +7,12 @@
 //
 // Geometry: the contraction runs over ROWS of one row-major R x Kf matrix, so both MMA operands are "MN-major"
 // (the output index is contiguous in memory) — the transpose of the Gram kernel's geometry:
-//   * CTA (unit, split): a work unit is 8 warp jobs x a contiguous row range. Off-diagonal 128 x 128 tiles are one unit
-//     each (4 x 2 warp blocks of 32 x 64). Diagonal tiles are packed two per unit as four 64 x 64 diagonal squares (one warp
-//     each, only the 10 upper box pairs of the 4 x 4 grid of 16-column fragment boxes) plus their four upper-right 32 x 64
-//     blocks — see syrk_warp_block. Partials go to a workspace in fragment order (perfectly coalesced) and a
-//     deterministic second-stage kernel sums the splits in fixed order, mirrors, and applies scale / ridge / intercept;
+//   * a work unit is 8 warp jobs x all rows. Off-diagonal 128 x 128 tiles are one unit each (4 x 2 warp blocks of 32 x 64).
+//     Diagonal tiles are packed two per unit as four 64 x 64 diagonal squares (one warp each, only the 10 upper box pairs of the
+//     4 x 4 grid of 16-column fragment boxes) plus their four upper-right 32 x 64 blocks — see syrk_warp_block. A CTA runs a
+//     host-built list of PIECES (unit, row range) through one pipeline (SyrkPiece; the schedule is a table, plb200_api.cu).
+//     Partials go to a workspace in fragment order (perfectly coalesced) and a deterministic second-stage kernel sums each unit's
+//     partials in fixed order, mirrors, and applies scale / ridge / intercept;
 //   * stage = 16 rows x 128 columns per operand, brought in as 8 TMA boxes of 16 rows x 16 columns (128 bytes wide,
 //     128B swizzle); diagonal tiles load one operand only;
 //   * fragment loads are 128-bit: lane (g,t) reads columns (2g, 2g+1) of row 2t+par(+8h) of a box — two m-tiles of
@@ -41,6 +42,13 @@ constexpr int SYRK_SMEM_BYTES = SYRK_STAGES * 2 * SYRK_OP_BYTES + 1024 + 256;
 constexpr int SYRK_UNIT_ACC = 80;                        // accumulator slots per thread in a unit's partial (squares: 80, blocks: 64)
 constexpr int SYRK_TILE_ELEMS = SYRK_UNIT_ACC * 256;     // doubles per (split, unit) partial
 
+// One piece of work: `nstages` pipeline stages (16 rows each) of work unit `unit`, starting at stage `first_stage`; its partial goes to
+// workspace slot `slot`. The slots of one unit are contiguous and ordered by row position, so the second-stage sum has a fixed order
+// whatever the schedule. A CTA runs a short list of pieces back to back through one TMA/mbarrier pipeline (no refill between pieces).
+struct SyrkPiece {
+  int unit, first_stage, nstages, slot;
+};
+
 struct SyrkParams {
   int64_t R, Kf;
   const double* w;        // per-row weights or NULL
@@ -50,9 +58,9 @@ struct SyrkParams {
   const double* mean;     // column means (centred mode) or NULL
   int T;                  // column blocks = ceil(Kf / 128)
   int ntiles;             // work units: T (T-1) / 2 off-diagonal tiles + ceil(T / 2) diagonal units
-  int splits;             // row splits
-  int64_t rows_per_split; // multiple of SYRK_BK
-  double* ws_tiles;       // [split][unit][80 acc][256 threads]
+  const SyrkPiece* pieces;  // the work list (built on the host, see SyrkPiece): CTA q runs pieces [cta_first[q], cta_first[q + 1])
+  const int* cta_first;
+  double* ws_tiles;       // [partial slot][80 acc][256 threads]
   int aux_box;            // >= 0: the 16-column box (global index) that is loaded from the auxiliary tensor instead of A (see
                           // syrk_aux_box_kernel: the moment vectors ride along as two extra columns); -1: none
   long long* trace;       // NULL, or 10 int64 per CTA: [globaltimer at start, SM id, end time of consumer warps 0..7] (PLB200_SYRK_TRACE)
@@ -135,7 +143,7 @@ __host__ __device__ __forceinline__ void syrk_square_pair(int p, int& bi, int& b
 //     (wcolsum_partial_kernel, prelude.cuh), and the rho of the one-sided centring is the centred column sum (colsum with a shift).
 template <bool CENTER, bool SQUARE>
 __device__ __forceinline__ void syrk_consume(const SyrkParams& p, const SyrkWarpBlock& WB, const uint32_t smem_base, const uint32_t bar_base,
-                                             const int KT, const int64_t r_begin, const int64_t r_end, const int tile, const int split, const int lane) {
+                                             const uint32_t it0, const int KT, const int64_t r_begin, const int64_t r_end, const int slot, const int lane) {
   constexpr int NA = SQUARE ? 4 : 2;       // fragment boxes of the A operand
   constexpr int NT = SQUARE ? 40 : 32;     // DMMA tiles = accumulator pairs
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -252,8 +260,9 @@ __device__ __forceinline__ void syrk_consume(const SyrkParams& p, const SyrkWarp
   };
 
   for (int kt = 0; kt < KT; ++kt) {
-    const int s = kt % SYRK_STAGES;
-    const uint32_t ph = (kt / SYRK_STAGES) & 1u;
+    const uint32_t it = it0 + (uint32_t)kt;  // pipeline position: runs on across the pieces of a CTA
+    const int s = it % SYRK_STAGES;
+    const uint32_t ph = (it / SYRK_STAGES) & 1u;
     const int64_t r0 = r_begin + (int64_t)kt * SYRK_BK;
     const bool need_w = !uniform || (CENTER && r0 >= r_full_end);
     const uint32_t sA = smem_base + s * 2 * SYRK_OP_BYTES + offA;
@@ -284,7 +293,7 @@ __device__ __forceinline__ void syrk_consume(const SyrkParams& p, const SyrkWarp
   }
 
   // ---- partial to the workspace in fragment order: [acc index][consumer thread] (coalesced) ----
-  double* wst = p.ws_tiles + ((int64_t)split * p.ntiles + tile) * SYRK_TILE_ELEMS;
+  double* wst = p.ws_tiles + (int64_t)slot * SYRK_TILE_ELEMS;
   const int ctid = threadIdx.x;  // 0..255
 #pragma unroll
   for (int i = 0; i < NT; ++i)
@@ -296,11 +305,7 @@ template <bool CENTER>
 __global__ void __launch_bounds__(SYRK_THREADS, 1)
 syrk_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmx, const SyrkParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const int tile = blockIdx.x;  // work unit
-  const int split = blockIdx.y;
-  const int64_t r_begin = (int64_t)split * p.rows_per_split;
-  int64_t r_end = r_begin + p.rows_per_split;
-  if (r_end > p.R) r_end = p.R;
+  const int pc0 = p.cta_first[blockIdx.x], pc1 = p.cta_first[blockIdx.x + 1];  // this CTA's pieces
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + SYRK_STAGES * 2 * SYRK_OP_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -308,10 +313,6 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  int cb0, cb1;
-  const SyrkWarpBlock WB = syrk_warp_block(p.T, tile, warp < SYRK_CONSUMER_WARPS ? warp : 0, cb0, cb1);
-  const bool one_buf = (cb0 == cb1);
-  const int KT = r_end > r_begin ? (int)((r_end - r_begin + SYRK_BK - 1) / SYRK_BK) : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SYRK_STAGES; ++s) {
@@ -320,7 +321,7 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
     }
     fence_barrier_init();
     if (p.trace) {
-      long long* tr = p.trace + ((int64_t)blockIdx.y * p.ntiles + blockIdx.x) * 10;
+      long long* tr = p.trace + (int64_t)blockIdx.x * 10;
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       long long t0;
@@ -336,25 +337,31 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
     if (warp == SYRK_CONSUMER_WARPS && lane == 0) {
       tma_prefetch_desc(&tm);
       if (p.aux_box >= 0) tma_prefetch_desc(&tmx);
-      const uint32_t bytes = one_buf ? SYRK_OP_BYTES : 2 * SYRK_OP_BYTES;
-      for (int kt = 0; kt < KT; ++kt) {
-        const int s = kt % SYRK_STAGES;
-        const uint32_t ph = (kt / SYRK_STAGES) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_arrive_expect_tx(full_bar(s), bytes);
-        const uint32_t dst = smem_base + s * 2 * SYRK_OP_BYTES;
-        const int r0 = (int)(r_begin + (int64_t)kt * SYRK_BK);
-        // NOTE: the last stage of a split may read rows of the next split (r >= r_end); they are zero-weighted below.
-#pragma unroll
-        for (int bx = 0; bx < 8; ++bx) {
-          if (cb0 * 8 + bx == p.aux_box) tma_load_2d(dst + bx * SYRK_BOX_BYTES, &tmx, full_bar(s), 0, r0);
-          else tma_load_2d(dst + bx * SYRK_BOX_BYTES, &tm, full_bar(s), cb0 * SYRK_BT + 16 * bx, r0);
-        }
-        if (!one_buf) {
+      uint32_t it = 0;
+      for (int pc = pc0; pc < pc1; ++pc) {
+        const SyrkPiece pcx = p.pieces[pc];
+        int cb0, cb1;
+        (void)syrk_warp_block(p.T, pcx.unit, 0, cb0, cb1);
+        const bool one_buf = (cb0 == cb1);
+        const uint32_t bytes = one_buf ? SYRK_OP_BYTES : 2 * SYRK_OP_BYTES;
+        for (int kt = 0; kt < pcx.nstages; ++kt, ++it) {
+          const int s = it % SYRK_STAGES;
+          const uint32_t ph = (it / SYRK_STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), bytes);
+          const uint32_t dst = smem_base + s * 2 * SYRK_OP_BYTES;
+          const int r0 = (pcx.first_stage + kt) * SYRK_BK;  // rows beyond R are zero-filled by TMA
 #pragma unroll
           for (int bx = 0; bx < 8; ++bx) {
-            if (cb1 * 8 + bx == p.aux_box) tma_load_2d(dst + SYRK_OP_BYTES + bx * SYRK_BOX_BYTES, &tmx, full_bar(s), 0, r0);
-            else tma_load_2d(dst + SYRK_OP_BYTES + bx * SYRK_BOX_BYTES, &tm, full_bar(s), cb1 * SYRK_BT + 16 * bx, r0);
+            if (cb0 * 8 + bx == p.aux_box) tma_load_2d(dst + bx * SYRK_BOX_BYTES, &tmx, full_bar(s), 0, r0);
+            else tma_load_2d(dst + bx * SYRK_BOX_BYTES, &tm, full_bar(s), cb0 * SYRK_BT + 16 * bx, r0);
+          }
+          if (!one_buf) {
+#pragma unroll
+            for (int bx = 0; bx < 8; ++bx) {
+              if (cb1 * 8 + bx == p.aux_box) tma_load_2d(dst + SYRK_OP_BYTES + bx * SYRK_BOX_BYTES, &tmx, full_bar(s), 0, r0);
+              else tma_load_2d(dst + SYRK_OP_BYTES + bx * SYRK_BOX_BYTES, &tm, full_bar(s), cb1 * SYRK_BT + 16 * bx, r0);
+            }
           }
         }
       }
@@ -364,16 +371,26 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
 
   // ------------------------------ consumers ------------------------------
   setmaxnreg_inc<240>();
-  if (WB.kind == 1) syrk_consume<CENTER, true>(p, WB, smem_base, bar_base, KT, r_begin, r_end, tile, split, lane);
-  else syrk_consume<CENTER, false>(p, WB, smem_base, bar_base, KT, r_begin, r_end, tile, split, lane);
+  uint32_t it = 0;
+  for (int pc = pc0; pc < pc1; ++pc) {
+    const SyrkPiece pcx = p.pieces[pc];
+    int cb0, cb1;
+    const SyrkWarpBlock WB = syrk_warp_block(p.T, pcx.unit, warp, cb0, cb1);
+    const int64_t r_begin = (int64_t)pcx.first_stage * SYRK_BK;
+    int64_t r_end = r_begin + (int64_t)pcx.nstages * SYRK_BK;
+    if (r_end > p.R) r_end = p.R;
+    if (WB.kind == 1) syrk_consume<CENTER, true>(p, WB, smem_base, bar_base, it, pcx.nstages, r_begin, r_end, pcx.slot, lane);
+    else syrk_consume<CENTER, false>(p, WB, smem_base, bar_base, it, pcx.nstages, r_begin, r_end, pcx.slot, lane);
+    it += (uint32_t)pcx.nstages;
+  }
   if (p.trace && lane == 0) {
     long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    p.trace[((int64_t)blockIdx.y * p.ntiles + blockIdx.x) * 10 + 2 + warp] = t1;
+    p.trace[(int64_t)blockIdx.x * 10 + 2 + warp] = t1;
   }
 }
 
-// Second stage: S[i][j] = S[j][i] = sum over splits (fixed order) of the partial blocks; v, c likewise.
+// Second stage: S[i][j] = S[j][i] = sum over the unit's partial slots (fixed order) of the partial blocks; v, c likewise.
 // Element (acc index a, consumer thread tid) of work unit u:
 //   warp = tid>>5 -> block (cb_a, wm, cb_b, wn) = syrk_warp_block(T, u, warp); g = (tid&31)>>2, t = tid&3
 //   mt = a>>4, nt = (a>>1)&7, c = a&1
@@ -383,7 +400,7 @@ syrk_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
 // one-sided centring: S_ij = S'_ij - rho_i * m_j.
 // vec != NULL ("augmented" mode): columns Kf and Kf+1 of the contraction held (b_r) and ([r < ne]) — see syrk_aux_box_kernel — so
 //   S_aug[i][Kf] = v_i, S_aug[i][Kf+1] = c_i (i < Kf), S_aug[Kf+1][Kf+1] = s_0, S_aug[Kf][Kf+1] = s_1   ->   vec = [v ; c ; s].
-__global__ void syrk_reduce_kernel(const double* __restrict__ ws_tiles, int T, int ntiles, int splits, int64_t Kf, double* __restrict__ S,
+__global__ void syrk_reduce_kernel(const double* __restrict__ ws_tiles, int T, const int* __restrict__ unit_first, int64_t Kf, double* __restrict__ S,
                                    const double* __restrict__ mean, const double* __restrict__ rho, double* __restrict__ vec) {
   const int unit = blockIdx.x;
   const int e = blockIdx.y * blockDim.x + threadIdx.x;  // one partial element per thread: grid = (units, SYRK_TILE_ELEMS / 256)
@@ -412,8 +429,9 @@ __global__ void syrk_reduce_kernel(const double* __restrict__ ws_tiles, int T, i
   const int64_t Ka = vec ? Kf + 2 : Kf;
   if (j >= Ka) return;  // (i <= j)
   // four interleaved partial sums (splits sp, sp+1, sp+2, sp+3 mod 4) keep 4 loads in flight; the order is fixed -> deterministic
-  const double* src = ws_tiles + (int64_t)unit * SYRK_TILE_ELEMS + e;
-  const int64_t stride = (int64_t)ntiles * SYRK_TILE_ELEMS;
+  const int slot0 = unit_first[unit], splits = unit_first[unit + 1] - slot0;  // this unit's partials: contiguous slots, in row order
+  const double* src = ws_tiles + (int64_t)slot0 * SYRK_TILE_ELEMS + e;
+  const int64_t stride = SYRK_TILE_ELEMS;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   int sp = 0;
   for (; sp + 4 <= splits; sp += 4) {

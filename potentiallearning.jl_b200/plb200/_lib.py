@@ -32,6 +32,7 @@ PROTOTYPES = {
     "pl_launch_count": (_i64, []),
     "pl_workspace_bytes": (_i64, []),
     "pl_workspace_trim": (_int, [_int]),
+    "pl_syrk_schedule": (_int, [_i64, _i64, _int, _int, _int, ctypes.c_double, _i64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
     "pl_set_profiling": (_int, [_int]),
     "pl_last_main_kernel_ms": (_int, [_dp]),
     "pl_host_alloc": (_vp, [_i64]),

@@ -50,7 +50,7 @@ start = (d[:, 2] - t0) / 1e3
 ends = (d[:, 4:12] - t0) / 1e3
 dur = ends.max(1) - start
 off, dg = d[:, 0] < noff, d[:, 0] >= noff
-print(f"units {units} splits {splits} T {T}; kernel span {ends.max():.0f} us")
+print(f"units {units} CTAs {splits} T {T}; kernel span {ends.max():.0f} us (column 0 = first unit of the CTA's piece list)")
 print(f"off-diagonal units: n={off.sum()} mean {dur[off].mean():.1f} us (min {dur[off].min():.1f} max {dur[off].max():.1f})")
 if dg.any():
     print(f"diagonal units:     n={dg.sum()} mean {dur[dg].mean():.1f} us (min {dur[dg].min():.1f} max {dur[dg].max():.1f})  ratio {dur[dg].mean() / dur[off].mean():.3f}")

@@ -110,6 +110,51 @@ def test_product_never_imports_the_oracle():
     # every exported compute entry point (everything but lifetime / bookkeeping helpers) checks for an initialised sm_100 device
     for m in re.finditer(r"\n(?:int|void\*)\s+(pl_\w+)\s*\([^)]*\)\s*\{(.*?)\n\}\n", body, flags=re.S):
         name, code = m.group(1), m.group(2)
-        if name in ("pl_init", "pl_last_timing", "pl_set_profiling", "pl_host_free", "pl_gram_tile_coords"):
+        if name in ("pl_init", "pl_last_timing", "pl_set_profiling", "pl_host_free", "pl_gram_tile_coords", "pl_syrk_schedule"):
             continue
         assert ("need_ready()" in code) or re.search(r"return \w+_impl\(|return gram_host\(|return rmsd_host\(|return normal_eq_stream\(", code), name
+
+
+def _syrk_schedule(R, K, sms, mode, waves=0, diag=0.0):
+    import ctypes
+
+    lib = _lib.load()
+    npc, ncta = ctypes.c_int64(0), ctypes.c_int64(0)
+    assert lib.pl_syrk_schedule(R, K, sms, mode, waves, diag, 0, None, ctypes.byref(npc), ctypes.byref(ncta)) == 0
+    tab = np.zeros((max(npc.value, 1), 5), dtype=np.int32)
+    assert lib.pl_syrk_schedule(R, K, sms, mode, waves, diag, npc.value, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), ctypes.byref(npc),
+                                ctypes.byref(ncta)) == 0
+    return tab[: npc.value], int(ncta.value)
+
+
+def test_syrk_schedules_cover_every_stage_once():
+    """Both SYRK schedules (host tables the kernel walks) give every pipeline stage of every work unit to exactly one CTA; the partial
+    slots of a unit are contiguous and in row order (the second-stage sum is a fixed-order walk over them); CTA piece lists are
+    contiguous; the stream-K cut is balanced in cost to within one snapping distance."""
+    for R, K in [(0, 500), (1, 8), (15, 128), (16, 129), (1000, 500), (5000, 257), (361_250, 500), (2_890_000, 500), (1_250_000, 1000), (100_000, 1500)]:
+        T = (K + 127) // 128
+        nunits = T * (T - 1) // 2 + (T + 1) // 2
+        noff = T * (T - 1) // 2
+        nst = (R + 15) // 16
+        for mode, waves in [(0, 0), (0, 7), (1, 1), (1, 2), (1, 3), (1, 5)]:
+            tab, nctas = _syrk_schedule(R, K, 148, mode, waves, 1.125)
+            if nst == 0:
+                assert len(tab) == 0
+                continue
+            assert np.all(tab[:, 3] > 0) and tab[:, 0].max() < nctas
+            assert np.all(np.diff(tab[:, 0]) >= 0), "a CTA's pieces are adjacent rows of the table"
+            slots = np.sort(tab[:, 4])
+            assert np.array_equal(slots, np.arange(len(tab))), "slots are a permutation of 0..npieces-1"
+            by_slot = tab[np.argsort(tab[:, 4])]
+            assert np.all(np.diff(by_slot[:, 1]) >= 0), "slots are unit-major"
+            for u in range(nunits):
+                rows = by_slot[by_slot[:, 1] == u]
+                assert len(rows) >= 1 and rows[0, 2] == 0
+                assert np.array_equal(rows[1:, 2], (rows[:, 2] + rows[:, 3])[:-1]), "row order, no gap, no overlap"
+                assert rows[-1, 2] + rows[-1, 3] == nst
+            if mode == 1 and nst >= 4096:
+                cost = np.where(tab[:, 1] < noff, 1.0, 1.125) * tab[:, 3]
+                per_cta = np.bincount(tab[:, 0], weights=cost, minlength=nctas)
+                assert nctas == 148 * waves
+                assert per_cta.max() - per_cta.min() <= 2 * 16 * 1.125 + 2, (R, K, waves, per_cta.min(), per_cta.max())
+                assert len(tab) <= nctas + nunits
