@@ -7,6 +7,7 @@
 #include <cusolverDn.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -518,11 +519,12 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
 // at the same speed, so two schedules are built here as plain tables the kernel walks (syrk.cuh: SyrkPiece):
 //   * "waves" (PLB200_SYRK_SCHED=waves): one piece per CTA, ~20 short CTAs per SM dealt out by the hardware as SMs free up (measured
 //     with the trace hook: 5-6 long CTAs per SM left 9 % of the machine idle at the tail), each streaming >= 1024 rows;
-//   * "streamk" (default; PLB200_SYRK_SCHED=sk<w>, w = 4): the linearised work (unit-major, costs weighted) is cut into 148 x w
-//     equal-cost intervals; a CTA runs its interval through ONE pipeline (no refill at a unit boundary) and writes one partial per unit
-//     it touches. Fewer partials (148 w + units instead of ~3000 x 160 KB), w pipeline fills per SM instead of 20, and the w-fold
-//     over-decomposition still lets the hardware even out SM speed differences. Measured (profiles/r01_syrk_schedules.json): config 3
-//     22.5 -> 22.15 ms, a per-GPU eighth of it 2.95 -> 2.81 ms, config 4 quarter 80.3 -> 77.5 ms; w = 4..8 and cost 1.12..1.16 are flat.
+//   * "streamk" (default; PLB200_SYRK_SCHED=sk<w> caps the rounds at w): ~148 x 4 CTAs of equal COST — a unit is cut into N0
+//     (off-diagonal) or ceil(1.15 N0) (diagonal) long row chunks, cuts aligned across units, CTAs issued in row order, N0 chosen so
+//     that the last round of CTAs is full. ~4 pipeline fills per SM instead
+//     of 20, ~600 partials of 160 KB instead of ~3000, and the w-fold over-decomposition still lets the hardware even out SM speed
+//     differences. Measured (profiles/r01_syrk_schedules.json): config 3 22.5 -> 22.2 ms, a per-GPU eighth of it 2.95 -> 2.81 ms,
+//     a quarter of config 4 80.3 -> 77.5 ms; w = 4..8 and cost 1.12..1.16 are flat.
 // Either way the partial slots of a unit are contiguous and in row order, so the second-stage sum is deterministic.
 struct SyrkSchedule {
   std::vector<int> cta_first, unit_first;
@@ -547,7 +549,7 @@ const SyrkSchedConfig& syrk_sched_config() {
     else if (e && !strncmp(e, "sk", 2)) c.waves = atoi(e + 2);
     const char* w = getenv("PLB200_SYRK_WAVES");
     if (w && atoi(w) > 0) c.waves = atoi(w);
-    if (c.waves <= 0) c.waves = c.mode == 0 ? 20 : 4;
+    if (c.waves <= 0) c.waves = 20;  // waves: CTAs per SM; streamk: the most rounds the chunk-count search may use
     const char* dc = getenv("PLB200_SYRK_DIAG_COST");
     if (dc && atof(dc) > 0.0) c.diag_cost = atof(dc);
     return c;
@@ -587,57 +589,66 @@ void build_syrk_schedule(int64_t R, int T, int nunits, int num_sms, const SyrkSc
     out->nslots = (int)(s * nunits);
     return;
   }
-  // streamk: positions are (unit, stage) linearised as unit * nst + stage; boundaries at equal cumulative cost
-  const int noff = T * (T - 1) / 2;
-  std::vector<double> cum(nunits + 1, 0.0);
-  for (int u = 0; u < nunits; ++u) cum[u + 1] = cum[u] + (u < noff ? 1.0 : cfg.diag_cost) * (double)nst;
-  const double total = cum[nunits];
-  int64_t G = (int64_t)num_sms * cfg.waves;
-  const int64_t max_ctas = ((int64_t)nunits * nst + 63) / 64;  // a CTA should stream >= 64 stages (1024 rows)
-  if (G > max_ctas) G = max_ctas;
-  if (G < 1) G = 1;
-  const int64_t snap = nst < 64 ? nst : 16;  // boundaries this close to a unit edge move onto it (no tiny pieces)
-  std::vector<int64_t> pos(G + 1);
-  int u = 0;
-  for (int64_t q = 0; q <= G; ++q) {
-    const double target = total * (double)q / (double)G;
-    while (u < nunits - 1 && cum[u + 1] <= target) ++u;
-    const double c = (u < noff ? 1.0 : cfg.diag_cost);
-    int64_t st = (int64_t)llround((target - cum[u]) / c);
-    if (st < 0) st = 0;
-    if (st > nst) st = nst;
-    if (st < snap) st = 0;
-    else if (nst - st < snap) st = nst;
-    pos[q] = (int64_t)u * nst + st;
-  }
-  pos[0] = 0;
-  pos[G] = (int64_t)nunits * nst;
-  for (int64_t q = 1; q <= G; ++q)
-    if (pos[q] < pos[q - 1]) pos[q] = pos[q - 1];
-  int last_unit = -1;
-  for (int64_t q = 0; q < G; ++q) {
-    out->cta_first.push_back((int)out->pieces.size());
-    int64_t a0 = pos[q];
-    const int64_t a1 = pos[q + 1];
-    while (a0 < a1) {
-      const int un = (int)(a0 / nst);
-      const int64_t f = a0 % nst;
-      int64_t e = (int64_t)(un + 1) * nst;
-      if (e > a1) e = a1;
-      const int slot = (int)out->pieces.size();
-      if (un != last_unit) {
-        for (int v = last_unit + 1; v <= un; ++v) out->unit_first[v] = slot;
-        last_unit = un;
-      }
-      out->pieces.push_back(SyrkPiece{un, (int)f, (int)(e - a0), slot});
-      a0 = e;
+  // streamk: every unit is cut into equal row chunks — N0 chunks for an off-diagonal unit, ceil(diag_cost * N0) for a diagonal one
+  // (equal cost per CTA to within rounding, the diagonal CTAs never the longer ones), N0 the largest count that keeps the total at
+  // or below 148 x waves CTAs. Units of the same kind get IDENTICAL cuts, and CTAs are issued in order of their first row: the CTAs
+  // that run at the same time then read the same rows for different units, so a row range is fetched from HBM once and shared
+  // through L2 (cutting the unit-major linearised work into equal-cost intervals instead left every unit streaming its own rows
+  // alone: ncu showed 13.0 GB of DRAM reads for a 2.9 GB shard).
+  const int noff = T * (T - 1) / 2, ndiag = nunits - noff;
+  int64_t cap = nst / 64;  // a CTA should stream >= 64 stages (1024 rows)
+  if (cap < 1) cap = 1;
+  auto ndg = [&](int64_t n0) { return (int64_t)ceil(cfg.diag_cost * (double)n0 - 1e-9); };
+  // N0 is chosen by a small model: CTAs of cost c run in ceil(nctas / SMs) rounds, so the efficiency is total cost / (SMs x rounds x c);
+  // every extra wave costs ~0.15 % (one more pipeline fill and 160 KB partial per SM; measured: 4..8 waves flat, 20 waves 2 % slower).
+  // With few units (the BASELINE shapes: 8 at K = 500, 32 at K = 1000) this lands on ~4 waves that fill the last round to > 99 %; with
+  // more units than SMs it takes as many waves as the fill needs, up to cfg.waves.
+  const double total_cost = (double)noff + cfg.diag_cost * (double)ndiag;
+  int64_t N0 = noff ? 1 : 0, ND = 1;
+  double best = -1.0;
+  for (int64_t n = 1; n <= cap; ++n) {
+    const int64_t nd = noff ? (ndg(n) < cap ? ndg(n) : cap) : n;
+    const int64_t nctas = noff ? noff * n + ndiag * nd : ndiag * nd;
+    const int64_t rounds = (nctas + num_sms - 1) / num_sms;
+    if (rounds > cfg.waves && best >= 0.0) break;
+    const double c = noff ? std::max(1.0 / (double)n, cfg.diag_cost / (double)nd) : cfg.diag_cost / (double)nd;
+    // fewer than 4 rounds leave the hardware too little to even out SM speed differences with (measured: 1 round -2.7 %, 2 rounds
+    // -0.2..-1.1 %, 3 rounds -0.1..-0.9 % against 4)
+    const double few = rounds == 1 ? 0.025 : (rounds == 2 ? 0.008 : (rounds == 3 ? 0.004 : 0.0));
+    const double score = total_cost / ((double)num_sms * (double)rounds * c) - 0.0015 * (double)rounds - few;
+    if (score > best + 1e-12) {
+      best = score;
+      N0 = noff ? n : 0;
+      ND = nd;
     }
   }
+  struct Cta {
+    int64_t key;
+    SyrkPiece pc;
+  };
+  std::vector<Cta> ctas;
+  int slot = 0;
+  for (int u = 0; u < nunits; ++u) {
+    const int64_t n = u < noff ? N0 : ND;
+    out->unit_first[u] = slot;
+    for (int64_t j = 0; j < n; ++j) {
+      const int64_t f = (nst * j) / n, e = (nst * (j + 1)) / n;
+      if (e <= f) continue;
+      ctas.push_back(Cta{f * nunits + u, SyrkPiece{u, (int)f, (int)(e - f), slot}});
+      ++slot;
+    }
+  }
+  out->unit_first[nunits] = slot;
+  std::sort(ctas.begin(), ctas.end(), [](const Cta& x, const Cta& y) { return x.key < y.key; });
+  for (const Cta& c : ctas) {
+    out->cta_first.push_back((int)out->pieces.size());
+    out->pieces.push_back(c.pc);
+  }
   out->cta_first.push_back((int)out->pieces.size());
-  for (int v = last_unit + 1; v <= nunits; ++v) out->unit_first[v] = (int)out->pieces.size();
-  out->nctas = (int)G;
-  out->nslots = (int)out->pieces.size();
+  out->nctas = (int)ctas.size();
+  out->nslots = slot;
 }
+
 
 // the schedule of the last shape stays on the device (same shape again: no rebuild, no upload)
 struct SyrkSchedCache {
@@ -1280,7 +1291,7 @@ int pl_syrk_schedule(int64_t R, int64_t Kf, int num_sms, int mode, int waves, do
   if (R < 0 || Kf <= 0 || num_sms <= 0 || (mode != 0 && mode != 1)) return set_err(PL_EINVAL, "bad arguments");
   SyrkSchedConfig cfg = syrk_sched_config();
   cfg.mode = mode;
-  cfg.waves = waves > 0 ? waves : (mode == 0 ? 20 : 4);
+  cfg.waves = waves > 0 ? waves : 20;
   if (diag_cost > 0.0) cfg.diag_cost = diag_cost;
   const int T = (int)((Kf + SYRK_BT - 1) / SYRK_BT);
   SyrkSchedule sc;
