@@ -523,8 +523,8 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
 //     (off-diagonal) or ceil(1.15 N0) (diagonal) long row chunks, cuts aligned across units, CTAs issued in row order, N0 chosen so
 //     that the last round of CTAs is full. ~4 pipeline fills per SM instead
 //     of 20, ~600 partials of 160 KB instead of ~3000, and the w-fold over-decomposition still lets the hardware even out SM speed
-//     differences. Measured (profiles/r01_syrk_schedules.json): config 3 22.5 -> 22.2 ms, a per-GPU eighth of it 2.95 -> 2.81 ms,
-//     a quarter of config 4 80.3 -> 77.5 ms; w = 4..8 and cost 1.12..1.16 are flat.
+//     differences. Measured (profiles/r01_syrk_schedules.json): config 3 22.5 -> 22.2 ms, a per-GPU eighth of it 2.95 -> 2.82 ms,
+//     a quarter of config 4 80.3 -> 78.2 ms; 4..8 rounds and cost 1.12..1.16 are flat.
 // Either way the partial slots of a unit are contiguous and in row order, so the second-stage sum is deterministic.
 struct SyrkSchedule {
   std::vector<int> cta_first, unit_first;
