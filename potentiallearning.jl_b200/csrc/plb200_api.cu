@@ -655,6 +655,8 @@ struct SyrkSchedCache {
   int64_t R = -1;
   int T = -1;
   const void* dev = nullptr;
+  cudaStream_t up_stream = nullptr;  // the stream the table was uploaded on; other streams wait for `ready` before using it
+  cudaEvent_t ready = nullptr;
   SyrkSchedule sch;
 } g_sched;
 
@@ -693,9 +695,14 @@ int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const do
     CUDA_TRY(cudaMemcpyAsync(di, sc.cta_first.data(), n1 * sizeof(int), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(di + n1, sc.unit_first.data(), n2 * sizeof(int), cudaMemcpyHostToDevice, st));
     if (n3) CUDA_TRY(cudaMemcpyAsync(di + ((n1 + n2 + 3) & ~(size_t)3), sc.pieces.data(), n3 * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (!g_sched.ready) CUDA_TRY(cudaEventCreateWithFlags(&g_sched.ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(g_sched.ready, st));
+    g_sched.up_stream = st;
     g_sched.R = R;
     g_sched.T = p.T;
     g_sched.dev = dsch;
+  } else if (st != g_sched.up_stream) {
+    CUDA_TRY(cudaStreamWaitEvent(st, g_sched.ready, 0));
   }
   const SyrkSchedule& sc = g_sched.sch;
   {
@@ -1181,6 +1188,10 @@ void pl_finalize(void) {
     cs.params = nullptr;
   }
   g_stager.shutdown();
+  if (g_sched.ready) cudaEventDestroy(g_sched.ready);
+  g_sched.ready = nullptr;
+  g_sched.dev = nullptr;
+  g_sched.R = -1;
   ell_state.valid = false;
   neq_state.open = false;
   if (g.stream) cudaStreamDestroy(g.stream);

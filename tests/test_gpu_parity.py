@@ -1541,3 +1541,34 @@ def test_workspace_trim(pl, orc):
     assert _lib.lib().pl_ell_inclusion_prob(1.0, 700, _lib.dptr(out)) != 0  # no resident ensemble any more
     assert np.allclose(pl.inclusion_prob(ell), p0, rtol=0, atol=1e-12)  # the mirror downloaded U before the eviction (n <= 4096)
     assert np.array_equal(np.asarray(pl.KernelMatrix(list(X), k)), K1)
+
+
+def test_syrk_schedule_modes_and_streams(pl, orc):
+    """The SYRK work table is cached on the device per shape: a second stream using the cached table, a shape change and a trim in
+    between all give the bits of the first result (fixed-order second stage), and the result matches the oracle."""
+    import torch
+
+    from plb200.device import DeviceEngine
+
+    eng = DeviceEngine()
+    rng = np.random.default_rng(31)
+    R, K, ne = 5000, 200, 40
+    A = rng.standard_normal((R, K))
+    b = rng.standard_normal(R)
+    Ad, bd = torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda()
+    S0, v0 = eng.syrk_partial(Ad, None, ne, 3.0, 0.5, bd, None, True)
+    torch.cuda.synchronize()
+    s2 = torch.cuda.Stream()
+    with torch.cuda.stream(s2):
+        S1, v1 = eng.syrk_partial(Ad, None, ne, 3.0, 0.5, bd, None, True)  # cached table, other stream
+    s2.synchronize()
+    assert torch.equal(S0, S1) and torch.equal(v0, v1)
+    eng.syrk_partial(Ad[:3333], None, ne, 3.0, 0.5, bd[:3333], None, True)  # another shape replaces the table
+    pl.workspace_trim(True)
+    S2, v2 = eng.syrk_partial(Ad, None, ne, 3.0, 0.5, bd, None, True)
+    torch.cuda.synchronize()
+    assert torch.equal(S0, S2) and torch.equal(v0, v2)
+    w = np.where(np.arange(R) < ne, 3.0, 0.5)
+    Sref = (A * w[:, None]).T @ A
+    assert normerr(S0.cpu().numpy(), Sref) < RTOL
+    assert np.allclose(v0.cpu().numpy()[:K], A.T @ (w * b), rtol=0, atol=1e-9 * np.abs(A.T @ (w * b)).max())
