@@ -190,61 +190,165 @@ def cpu_strong_blas_rate(X, n_sub=6000):
     return n * (n + 1) * d / dt / 1e9, dt
 
 
-def other_configs(dev, peak_tflops):
-    """BASELINE configs[2] (normal equations, full size) and configs[3] (PCA covariance, a 2.5 M-row slice of the 10 M rows) on one GPU,
-    inputs resident in HBM, CUDA events, best of 5 after 2 warm-ups. Reported next to the headline metric, not instead of it."""
+def other_configs(dev, peak_tflops, rank, world, sync):
+    """The other BASELINE shapes at this N, inputs resident in HBM, CUDA events on the launching stream, best of `reps` after warm-ups,
+    max over ranks per repetition. Every rank calls this (the sharded entries are collective); rank 0 reports.
+      configs[2] normal equations: rows sharded (whole configurations per rank), fused SYRK -> ONE ncclAllReduce of the bucket
+                 [S ; v ; c ; s] issued by libplb200 itself (pl_normal_eq_sharded_dev) -> finish kernel; rows/s over ALL ranks;
+      configs[3] PCA covariance of 10^7 x 1000 rows (80 GB over the ranks; fewer rows if one GPU cannot hold its share): one pass,
+                 two all-reduces (K column sums, K x K) inside pl_cov_sharded_dev;
+      configs[4] DotProduct Gram N = 200 000 x 500, tile-packed shards (tiles round-robin over ranks, no collective);
+      configs[0] DotProduct Gram N = 1000 x 26 (the kDPP example shape), rank 0 only: HBM-bound, reported against the copy peak.
+    Reported next to the headline metric, not instead of it."""
     import torch
+    import torch.distributed as dist
 
-    from plb200.device import DeviceEngine
+    from plb200 import _lib
 
-    eng = DeviceEngine()
+    lib = _lib.lib()
     res = {}
+    stream = lambda: torch.cuda.current_stream(dev).cuda_stream
 
-    def best_ms(fn, warm=2, reps=5):
+    def timed(fn, warm=2, reps=4):
         for _ in range(warm):
             fn()
-        torch.cuda.synchronize()
-        ts = []
+        sync()
+        ts, main, coll = [], [], []
+        _lib.set_profiling(True)
         for _ in range(reps):
+            sync()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
             e1.record()
             e1.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        return min(ts)
+            t = torch.tensor([e0.elapsed_time(e1), _lib.last_main_kernel_ms(), _lib.last_coll_ms() if world > 1 else 0.0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t[0]))
+            main.append(float(t[1]))
+            coll.append(float(t[2]))
+        _lib.set_profiling(False)
+        i = int(np.argmin(ts))
+        return ts[i], main[i], coll[i]
+
+    def free_gb():
+        torch.cuda.empty_cache()
+        return torch.cuda.mem_get_info(dev)[0] / 1e9
 
     try:
-        g = torch.Generator(device=dev).manual_seed(1003)
+        # ---- configs[2]: learn! normal equations, 10 000 configurations x 96 atoms, K = 500 ----
+        g = torch.Generator(device=dev).manual_seed(1003 + rank)
         ncfg, nat, K = 10_000, 96, 500
+        lo, hi = rank * ncfg // world, (rank + 1) * ncfg // world
+        ne_l = hi - lo
+        R_l = ne_l * (1 + 3 * nat)
         R = ncfg * (1 + 3 * nat)
-        A = torch.randn((R, K), device=dev, dtype=torch.float64, generator=g)
-        b = torch.randn(R, device=dev, dtype=torch.float64, generator=g)
+        A = torch.empty((R_l, K), device=dev, dtype=torch.float64)
+        for r0 in range(0, R_l, 1 << 19):
+            A[r0:r0 + (1 << 19)].normal_(generator=g)
+        b = torch.randn(R_l, device=dev, dtype=torch.float64, generator=g)
+        M = torch.empty((K + 1, K + 1), device=dev, dtype=torch.float64)
+        v = torch.empty(K + 1, device=dev, dtype=torch.float64)
 
         def neq():
-            S, vec = eng.syrk_partial(A, None, ncfg, 100.0, 1.0, b, None, True)
-            eng.normal_eq_finish(S, vec, True, 0.01)
+            _lib.check(lib.pl_normal_eq_sharded_dev(A.data_ptr(), R_l, K, K, None, ne_l, 100.0, 1.0, b.data_ptr(), 1, 0.01, M.data_ptr(), v.data_ptr(),
+                                                    stream()), "pl_normal_eq_sharded_dev")
 
-        ms = best_ms(neq)
+        ms, main_ms, coll_ms = timed(neq)
         tf = R * K * (K + 1.0) / (ms * 1e-3) / 1e12
-        res["normal_equations_c3"] = {"workload": f"learn! energy+force normal equations R={R} K={K}, ws=[100,1], intercept, lambda=0.01 (BASELINE configs[2])",
-                                      "ms": ms, "rows_per_s": R / (ms * 1e-3), "tflops_RK(K+1)": tf, "frac_of_measured_dgemm": tf / peak_tflops}
-        del A, b
-        n, K = 2_500_000, 1000
-        X = torch.randn((n, K), device=dev, dtype=torch.float64, generator=g) + 10.0 * torch.randn(K, device=dev, dtype=torch.float64, generator=g)
+        res["normal_equations_c3"] = {
+            "workload": f"learn! energy+force normal equations R={R} K={K}, ws=[100,1], intercept, lambda=0.01 (BASELINE configs[2]); rows sharded over {world} GPU(s), one ncclAllReduce of K^2+2K+2 doubles inside libplb200",
+            "ms": ms, "rows_per_s": R / (ms * 1e-3), "tflops_RK(K+1)": tf, "frac_of_measured_dgemm_per_gpu": tf / world / peak_tflops,
+            "syrk_kernel_ms_max_rank": main_ms, "allreduce_ms_max_rank": coll_ms, "rows_per_rank": R_l}
+        del A, b, M, v
 
-        from plb200.distributed import covariance_sharded
+        # ---- configs[3]: PCAState covariance, 10^7 rows x 1000 features ----
+        n_total, K = 10_000_000, 1000
+        n_l = n_total // world
+        room = free_gb() - 8.0
+        full = n_l * K * 8 / 1e9 <= room
+        if not full:
+            n_l = int(room * 1e9 / (K * 8)) // 65536 * 65536
+            n_total = n_l * world
+        g = torch.Generator(device=dev).manual_seed(1004)  # the same feature means on every rank
+        shift = 10.0 * torch.randn(K, device=dev, dtype=torch.float64, generator=g)
+        g = torch.Generator(device=dev).manual_seed(2004 + rank)
+        X = torch.empty((n_l, K), device=dev, dtype=torch.float64)
+        for r0 in range(0, n_l, 1 << 18):
+            X[r0:r0 + (1 << 18)].normal_(generator=g)
+            X[r0:r0 + (1 << 18)] += shift
+        C = torch.empty((K, K), device=dev, dtype=torch.float64)
+        m = torch.empty(K, device=dev, dtype=torch.float64)
 
         def cov():
-            covariance_sharded(X, n, engine=eng)  # prefix mean -> shifted SYRK (one pass over the rows) -> re-centre -> 1/n
+            _lib.check(lib.pl_cov_sharded_dev(X.data_ptr(), n_l, n_total, K, K, m.data_ptr(), 0, 1, C.data_ptr(), stream()), "pl_cov_sharded_dev")
 
-        ms = best_ms(cov, reps=3)
-        tf = n * K * (K + 1.0) / (ms * 1e-3) / 1e12
-        res["pca_covariance_c4_slice"] = {"workload": f"PCAState fit! centred covariance, {n} of the 10^7 rows x K={K} (BASELINE configs[3]; 20 of 80 GB)",
-                                          "ms": ms, "rows_per_s": n / (ms * 1e-3), "tflops_nK(K+1)": tf, "frac_of_measured_dgemm": tf / peak_tflops}
-        del X
+        ms, main_ms, coll_ms = timed(cov, warm=1, reps=3)
+        tf = n_total * K * (K + 1.0) / (ms * 1e-3) / 1e12
+        res["pca_covariance_c4"] = {
+            "workload": f"PCAState fit! centred covariance, n={n_total} rows x K={K} (BASELINE configs[3]" + ("" if full else f"; REDUCED from 10^7 rows: {room:.0f} GB free per GPU") + f"); rows sharded over {world} GPU(s), one pass, all-reduces of K and K^2 doubles inside libplb200",
+            "ms": ms, "rows_per_s": n_total / (ms * 1e-3), "tflops_nK(K+1)": tf, "frac_of_measured_dgemm_per_gpu": tf / world / peak_tflops,
+            "syrk_kernel_ms_max_rank": main_ms, "last_allreduce_ms_max_rank": coll_ms, "rows_per_rank": n_l, "full_size": bool(full)}
+        del X, C, m, shift
+
+        # ---- configs[4]: DotProduct Gram for hierarchical kDPP, N = 200 000 x 500, tile-packed shards ----
+        n5, d5 = 200_000, 500
+        rng = np.random.default_rng(1005)
+        mu = torch.as_tensor(2.0 * rng.standard_normal(d5), device=dev)
+        g = torch.Generator(device=dev).manual_seed(1005)  # X is replicated: the same rows on every rank
+        X5 = mu + torch.randn((n5, d5), device=dev, dtype=torch.float64, generator=g) / np.sqrt(96.0)
+        passes = 1
+        while int(lib.pl_gram_tile_count(n5, 0, rank, world * passes)) * 131072 / 1e9 > free_gb() - 6.0 and passes < 64:
+            passes *= 2
+        nt = int(lib.pl_gram_tile_count(n5, 0, 0, world * passes))  # part 0 owns the most tiles
+        tiles = torch.empty((nt, 128, 128), device=dev, dtype=torch.float64)
+
+        def gram5():
+            for ps in range(passes):  # passes > 1 only when one GPU cannot hold its whole shard: later passes overwrite the buffer
+                _lib.check(lib.pl_gram_dev(_lib.PL_KERNEL_DOT, X5.data_ptr(), n5, d5, None, 0, 0, d5, 2, 0, None, 1.0, 1.0, tiles.data_ptr(), 128,
+                                           _lib.PL_FILL_FULL, rank * passes + ps, world * passes, 1, stream()), "pl_gram_dev")
+
+        ms, main_ms, _ = timed(gram5, warm=1, reps=3)
+        fl = float(n5) * (n5 + 1) * d5
+        tf = fl / (ms * 1e-3) / 1e12
+        res["gram_dot_c5"] = {
+            "workload": f"KernelMatrix DotProduct N={n5} d={d5} (BASELINE configs[4]); 128x128 tiles of the upper triangle round-robin over {world} GPU(s), tile-packed shards resident ({nt * 131072 / 1e9:.1f} GB per GPU" + (f", computed in {passes} passes over one buffer" if passes > 1 else "") + "), no collective",
+            "ms": ms, "gflops_N(N+1)d": fl / (ms * 1e-3) / 1e9, "tflops": tf, "frac_of_measured_dgemm_per_gpu": tf / world / peak_tflops, "passes": passes}
+        del X5, tiles
+
+        # ---- configs[0]: the kDPP example shape, N = 1000 x 26 DotProduct (HBM / launch bound), rank 0 ----
+        if rank == 0:
+            n1, d1 = 1000, 26
+            X1 = torch.as_tensor(rng.standard_normal((n1, d1)) + 2.0 * rng.standard_normal(d1), device=dev)
+            K1 = torch.zeros((n1, n1), device=dev, dtype=torch.float64)
+
+            def gram1():
+                _lib.check(lib.pl_gram_dev(_lib.PL_KERNEL_DOT, X1.data_ptr(), n1, d1, None, 0, 0, d1, 2, 0, None, 1.0, 1.0, K1.data_ptr(), n1,
+                                           _lib.PL_FILL_JULIA_U, 0, 1, 0, stream()), "pl_gram_dev")
+
+            for _ in range(5):
+                gram1()
+            torch.cuda.synchronize()
+            reps = 200
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                gram1()
+            e1.record()
+            e1.synchronize()
+            us = e0.elapsed_time(e1) / reps * 1e3
+            wbytes = n1 * (n1 + 1) / 2 * 8 + n1 * d1 * 8
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            hbm = float(peaks.get("hbm_gbs", 6545.0))
+            res["gram_dot_c1"] = {"workload": f"kDPP kernel build: KernelMatrix DotProduct N={n1} d={d1} (BASELINE configs[0]), Symmetric(:U) storage, back-to-back launches (L2-resident: 8 MB result)",
+                                  "us_per_matrix": us, "algorithmic_GBps": wbytes / (us * 1e-6) / 1e9, "hbm_peak_GBps": hbm,
+                                  "frac_of_hbm_copy_peak": wbytes / (us * 1e-6) / 1e9 / hbm}
+            del X1, K1
     except Exception as e:  # never let the side measurements take the headline line down
-        res["error"] = repr(e)
+        import traceback
+
+        res["error"] = repr(e) + " | " + traceback.format_exc(limit=2).replace("\n", " / ")
     torch.cuda.empty_cache()
     return res
 
@@ -304,13 +408,15 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL logs to stdout; keep stdout to the one JSON line
+        # (NCCL's log goes to fd 1, which claim_stdout() has already pointed at stderr: NCCL_DEBUG stays whatever the launcher set)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
         torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     plb200.init(local_rank)
+    if world > 1:
+        _lib.comm_init_from_torch()  # the library's own NCCL communicator: the data-path all-reduces are issued inside libplb200
     W = max(args.warmup, 3)
     K = args.steps
 
@@ -401,16 +507,43 @@ def main():
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         tm = _lib.last_timing()
         e2e = {"value": flops / float(t_e2e.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": N_CFG * D_CFG * 8, "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": float(t_e2e.item()) * 1e3, "steps": n_e2e, "last_call_ms": tm,
+               "ms_per_step": float(t_e2e.item()) * 1e3, "steps": n_e2e, "last_call_ms": tm, "host_buffers": "pinned",
                "api": "pl_gram_part (tile-packed shard)" if packed else "pl_gram_rbf fill=PL_FILL_JULIA_U (Symmetric uplo=:U storage)"}
-        del Kp
-
-    if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
-        return 0
+            # where the slowest rank's time goes: kernel / H2D / D2H of every rank's last call (GPUs behind one PCIe switch share its uplink)
+            mine = torch.tensor([tm["kernel_ms"], tm["h2d_ms"], tm["d2h_ms"]], device=dev, dtype=torch.float64)
+            allr = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            e2e["last_call_ms_per_rank"] = [[round(float(x), 3) for x in t] for t in allr]
+        del Kp
+        if world == 1:
+            # What the Julia shim does by default: the result is an ordinary (pageable) zeros(n, n). The library stages it through its own
+            # pinned ring + host threads. "touched": the same array again (pages resident); "fresh": a new np.zeros each call (first touch).
+            Xg = np.array(Xh)
+            Kg = np.zeros((N_CFG, N_CFG))
 
-    # ---------------- roofline denominator: fp64 tensor peak = cuBLAS DGEMM measured here ----------------
+            def pageable_step(Kdst):
+                _lib.check(lib.pl_gram_rbf(_lib.dptr(Xg), N_CFG, D_CFG, D_CFG, 0, None, ELL, BETA, _lib.dptr(Kdst.reshape(-1)), N_CFG,
+                                           _lib.PL_FILL_JULIA_U), "pl_gram_rbf")
+
+            pageable_step(Kg)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                pageable_step(Kg)
+            t_touched = (time.perf_counter() - t0) / 3
+            t_fresh = []
+            for _ in range(2):
+                Kf = np.zeros((N_CFG, N_CFG))
+                t0 = time.perf_counter()
+                pageable_step(Kf)
+                t_fresh.append(time.perf_counter() - t0)
+                del Kf
+            e2e["pageable"] = {"touched_ms_per_step": t_touched * 1e3, "touched_value": flops / t_touched / 1e9, "fresh_zeros_ms_per_step": min(t_fresh) * 1e3,
+                               "fresh_zeros_value": flops / min(t_fresh) / 1e9,
+                               "note": "pageable numpy result (what Julia's zeros(n,n) is): staged by libplb200's pinned ring + host threads"}
+            del Kg, Xg
+
+    # ---------------- roofline denominator: fp64 tensor peak = cuBLAS DGEMM measured here (every rank: `also` reports against it) ----------
     del out
     torch.cuda.empty_cache()
     a = torch.randn((8192, 8192), device=dev, dtype=torch.float64)
@@ -429,17 +562,35 @@ def main():
         best = min(best, e0.elapsed_time(e1))
     peak_tflops = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
     del a, b, c
+
+    # ---------------- the other BASELINE shapes at this N, device-resident, collectives inside the library (every rank takes part) ----------
+    also = None
+    if not args.no_also:
+        _lib.check(_lib.lib().pl_workspace_trim(0), "pl_workspace_trim")
+        del flush
+        torch.cuda.empty_cache()
+        also = other_configs(dev, peak_tflops, rank, world, barrier)
+
+    if rank != 0:
+        if world > 1:
+            _lib.comm_destroy()
+            dist.destroy_process_group()
+        return 0
+
     flops_launch = flops / world  # tiles are dealt evenly; per-launch algorithmic flops of this rank
     achieved = flops_launch / (main_ms_per_step * 1e-3) / 1e12
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_gram_rbf_ncu_summary.json")
-    if os.path.exists(prof):
-        try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    traffic, traffic_source = None, None
+    for name in ("r02_gram_rbf_ncu_summary.json", "r01_gram_rbf_ncu_summary.json"):
+        prof = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+                traffic_source = f"static: one ncu --set full capture of this kernel at this shape, committed as profiles/{name} (not measured in this run)"
+                break
+            except Exception:
+                traffic = None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic,
-                "kernel": "plb::gram_kernel<EPI_RBF>", "kernel_ms": main_ms_per_step,
+                "traffic_source": traffic_source, "kernel": "plb::gram_kernel<EPI_RBF>", "kernel_ms": main_ms_per_step,
                 "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; MEASURED_PEAKS.json has no fp64 figure; nominal 37 TFLOP/s (HGX B200)",
                 "algorithmic_flops_per_launch": flops_launch}
 
@@ -460,11 +611,6 @@ def main():
         except Exception as e:  # scipy missing on the box: the faithful port above is the baseline
             cpu["strong_blas_context"] = {"unavailable": str(e)}
 
-    # ---------------- the other single-GPU BASELINE shapes, device-resident (N = 1 only; a few hundred ms in total) ----------------
-    also = None
-    if world == 1 and not args.no_also:
-        also = other_configs(dev, peak_tflops)
-
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config({"parallelism": f"tiles round-robin over {world} GPU(s), no collective", "output": "tile-packed shards" if packed else "dense N x N storage, Symmetric uplo=:U triangle written (reference contract, kernels.jl:216-222)"}),
@@ -472,6 +618,7 @@ def main():
             "wall_s_timed_region": t_wall, "also": also}
     emit(line)
     if world > 1:
+        _lib.comm_destroy()
         dist.destroy_process_group()
     return 0
 

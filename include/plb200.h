@@ -57,11 +57,31 @@ extern "C" {
 #define PL_FILL_JULIA_U PL_FILL_RM_LOWER
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */
-/* Bind the library to one CUDA device (-1: the current device). One process drives one GPU; multi-GPU jobs run
- * one process per GPU and combine partials with one all-reduce. Fails with PL_ENODEV unless the
- * device is compute capability 10.x. Idempotent. */
+/* Bind the library to one CUDA device (-1: the current device): one process per GPU. Multi-GPU jobs of that kind create a
+ * communicator with pl_comm_init_rank and use the *_sharded entry points. Fails with PL_ENODEV unless the device is compute
+ * capability 10.x. Idempotent. */
 int pl_init(int device);
+/* ONE process drives ndev GPUs (what a Julia session does): a context (streams, workspace) per device and one NCCL
+ * communicator per device from ncclCommInitAll inside the library. device_ids == NULL: devices 0..ndev-1; ndev <= 0: every visible
+ * device. Afterwards the HOST entry points shard large inputs over the devices transparently — pl_normal_eq / pl_normal_eq_blocks /
+ * pl_cov shard rows (each device streams its shard over its own PCIe link, one all-reduce of K^2+2K+2 doubles adds the partials:
+ * learn! linear-learn.jl:253, compute_eigen dimension_reduction.jl:12), pl_gram_dot / pl_gram_rbf / pl_gram_imq with PL_FILL_JULIA_U
+ * shard tile columns (no collective, parallel D2H: KernelMatrix kernels.jl:211-223) — results identical in meaning and layout to one
+ * device. The _dev entry points and everything else run on device_ids[0]. */
+int pl_init_all(int ndev, const int* device_ids);
+/* devices driven by this process (0 before pl_init / pl_init_all) */
+int pl_device_count(void);
 void pl_finalize(void);
+
+/* ---- one process per GPU: the communicator (NCCL, loaded with dlopen; PLB200_NCCL overrides the library path) --------------- */
+/* rank 0 calls pl_comm_unique_id and distributes the 128 bytes by any means (torch.distributed store, MPI, a file); then EVERY rank
+ * calls pl_comm_init_rank (collective). nranks / rank as in ncclCommInitRank. */
+int pl_comm_unique_id(void* out128);
+int pl_comm_init_rank(int nranks, int rank, const void* id128);
+int pl_comm_info(int* nranks, int* rank, int* nccl_version);
+int pl_comm_destroy(void);
+/* milliseconds of the last all-reduce enqueued by the library on this process's first device (CUDA events around it) */
+int pl_last_coll_ms(double* ms);
 const char* pl_last_error(void);
 /* milliseconds spent by the last host entry point: kernels (CUDA events), H2D and D2H copies. */
 int pl_last_timing(double* kernel_ms, double* h2d_ms, double* d2h_ms);
@@ -116,6 +136,21 @@ int pl_gram_cross(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, con
 int pl_gram_part(int kernel_id, const double* X, int64_t n, int64_t d, int64_t ldx, int alpha, int cinv_kind, const double* cinv,
                  double ell, double beta, int part, int nparts, double* tiles);
 
+/* ---- resident kernel matrix: KernelMatrix(F, k) (kernels.jl:211-223) too large for one host matrix -------------------------------------
+ * N = 200 000 (BASELINE configs[4], hierarchical kDPP) has a 160 GB upper triangle: it only exists as tile-packed shards on the GPUs.
+ * pl_gram_resident computes the 128 x 128 tiles of the upper triangle and LEAVES them on the devices: dealt round-robin over the devices
+ * of pl_init_all, or (one process per GPU, collective) this rank's tiles t % nranks == rank. X is replicated; no collective on the result.
+ * pl_gram_fetch_block gathers any block K[i0:i1, j0:j1] (row-major (i1-i0) x (j1-j0), both triangles by mirroring, <= 2 GB) to the host:
+ * every shard writes the elements it owns into a zeroed staging block, one all-reduce assembles it (collective in the process-per-GPU
+ * mode; every rank receives the block). pl_gram_resident_shard exposes a shard's device pointer (tile k of shard `part` is tile
+ * pl_gram_tile_coords(n, 0, part, nparts, k)). The handle owns the device memory until pl_gram_free. */
+int pl_gram_resident(int kernel_id, const double* X, int64_t n, int64_t d, int64_t ldx, int alpha, int cinv_kind, const double* cinv, double ell,
+                     double beta, void** handle);
+int pl_gram_resident_info(void* handle, int64_t* n, int* nparts, int64_t* tiles_local, int64_t* bytes_local);
+int pl_gram_resident_shard(void* handle, int local_index, int* part, int64_t* ntiles, void** dtiles);
+int pl_gram_fetch_block(void* handle, int64_t i0, int64_t i1, int64_t j0, int64_t j1, double* out, int64_t ldo);
+int pl_gram_free(void* handle);
+
 /* ---- weighted normal equations: replaces every A'WA / A'Wb site of src/Learning/linear-learn.jl ------- */
 /* A: row-major R x Kf (rows = [n_energy_rows energy rows ; force rows], linear-learn.jl:232-245).
  * Row weights: w != NULL -> w[r] (ooc_learn! per-configuration weights, linear-learn.jl:341-352);
@@ -147,6 +182,16 @@ int pl_neq_begin(int64_t Kf);
 int pl_neq_add(const double* A, int64_t R, int64_t lda, const double* w, int64_t n_energy_rows, double w_e, double w_f, const double* b);
 int pl_neq_finish(int add_intercept, double lambda, double* AtWA, double* AtWb);
 
+/* One process per GPU (after pl_comm_init_rank; collective: every rank calls it): A_local is THIS rank's shard, laid out [its energy rows ;
+ * its force rows]; the result is the normal equations of the row-wise union of all shards, identical on every rank. SYRK of the shard ->
+ * ONE ncclAllReduce of the bucket [S ; v ; c ; s] (Kf^2 + 2 Kf + 2 doubles) -> finish, all on the library's stream. Other arguments as
+ * pl_normal_eq. Without a communicator it equals pl_normal_eq. */
+int pl_normal_eq_sharded(const double* A_local, int64_t R_local, int64_t Kf, int64_t lda, const double* w, int64_t n_energy_rows_local, double w_e,
+                         double w_f, const double* b, int add_intercept, double lambda, double* AtWA, double* AtWb);
+/* the same on DEVICE data, enqueue only (stream is a cudaStream_t): what the multi-GPU benchmark times */
+int pl_normal_eq_sharded_dev(const double* dA, int64_t R_local, int64_t Kf, int64_t lda, const double* dw, int64_t n_energy_rows_local, double w_e,
+                             double w_f, const double* db, int add_intercept, double lambda, double* dAtWA, double* dAtWb, void* stream);
+
 /* ---- GlobalSum / GlobalMean features on the device ("next" row f2 of SURVEY.md 8f) ------------------------ */
 /* locals: the local descriptors of all N configurations stacked, row-major (offsets[N]) x d, leading dimension ldl; configuration i owns
  * rows [offsets[i], offsets[i+1]) (offsets[0] == 0, strictly increasing). X[i,:] = sum of its rows (mean == 0: compute_feature(B,
@@ -174,6 +219,16 @@ int pl_ksd_rbf(const double* X, const double* S, int64_t n, int64_t d, int64_t l
  * center != 0: if mean_given == 0, mean_inout <- sum_r x_r / n (pca_state.jl:35), else mean_inout is used as is
  * (pca.m persists, pca_state.jl:34); C = (1/n) sum_r (x_r-m)(x_r-m)'. C: Kf x Kf full, exactly symmetric. */
 int pl_cov(const double* X, int64_t n, int64_t Kf, int64_t ldx, double* mean_inout, int mean_given, int center, double* C);
+
+/* One process per GPU (collective): X_local is this rank's n_local of the n_total rows. center != 0 and mean_given == 0: ONE pass over the rows
+ * per rank (shifted second moment about the mean of a prefix of the shard), an all-reduce of the K column sums for the global mean
+ * (returned in mean_inout on every rank), re-centring, ONE all-reduce of K x K. C = (1/n_total) sum over all ranks, exactly symmetric. */
+int pl_cov_sharded(const double* X_local, int64_t n_local, int64_t n_total, int64_t Kf, int64_t ldx, double* mean_inout, int mean_given, int center,
+                   double* C);
+int pl_cov_sharded_dev(const double* dX, int64_t n_local, int64_t n_total, int64_t Kf, int64_t ldx, double* dmean_inout, int mean_given, int center,
+                       double* dC, void* stream);
+/* sum-all-reduce count doubles in place over the library's communicator, enqueued on stream (a no-op without a communicator) */
+int pl_allreduce_dev(double* dbuf, int64_t count, void* stream);
 
 /* ---- symmetric eigendecomposition and the L-ensemble on the device ("next" row f1 of SURVEY.md 8f) ----------- */
 /* eigen(Symmetric(Q)) (dimension_reduction.jl:13; LAPACK in the reference) and the eigendecomposition inside EllEnsemble(K)

@@ -27,6 +27,17 @@ class HostStager {
 
   ~HostStager() { shutdown(); }
 
+  // Start the ring and the worker threads now (otherwise at first use) with at most `max_threads` workers. A library driving several
+  // GPUs from one process starts every device's stager up front: pinned allocations may synchronise all devices, which must not
+  // happen while another device already waits inside a collective.
+  cudaError_t start(int max_threads) {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      if (!started_ && max_threads > 0) thread_cap_ = max_threads;
+    }
+    return ensure();
+  }
+
   static bool is_pageable(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -147,6 +158,7 @@ class HostStager {
       int t = env ? atoi(env) : kDefaultThreads;
       const int hw = (int)std::thread::hardware_concurrency();
       if (hw > 0 && t > hw) t = hw;
+      if (thread_cap_ > 0 && t > thread_cap_) t = thread_cap_;
       nthreads_ = t < 1 ? 1 : (t > kSlots - 2 ? kSlots - 2 : t);
       nslots_ = nthreads_ + 2;
     }
@@ -212,6 +224,7 @@ class HostStager {
   bool h2d_used_[kSlots] = {};  // the slot's event marks an H2D DMA that may still be reading it
   int cursor_ = 0;
   int nthreads_ = kDefaultThreads, nslots_ = kDefaultThreads + 2;
+  int thread_cap_ = 0;
   cudaError_t async_error_ = cudaSuccess;
   int pending_ = 0;
   bool started_ = false, stop_ = false;

@@ -28,7 +28,6 @@ using namespace plb;
 namespace {
 
 thread_local char g_err[1024] = "";
-HostStager g_stager;  // pinned staging ring + host threads for pageable host memory (hoststage.h)
 bool staging_for(const void* host_ptr, size_t bytes) {
   return bytes >= ((size_t)4 << 20) && !getenv("PLB200_NO_STAGING") && HostStager::is_pageable(host_ptr);
 }
@@ -133,9 +132,30 @@ enum WsSlot {
   WS_NSLOTS
 };
 
+// the SYRK schedule of the last shape stays on the device (same shape again: no rebuild, no upload); see build_syrk_schedule
+struct SyrkSchedule {
+  std::vector<int> cta_first, unit_first;
+  std::vector<SyrkPiece> pieces;
+  int nctas = 0, nslots = 0;
+};
+struct SyrkSchedCache {
+  int64_t R = -1;
+  int T = -1;
+  const void* dev = nullptr;
+  cudaStream_t up_stream = nullptr;  // the stream the table was uploaded on; other streams wait for `ready` before using it
+  cudaEvent_t ready = nullptr;
+  SyrkSchedule sch;
+};
+
+// One context per GPU the library drives. pl_init binds context 0 to one device (one process per GPU); pl_init_all creates one per
+// device of the box (single process, what a Julia session uses). Every internal routine works on the calling thread's CURRENT
+// context `g`: the entry points run on context 0, the multi-GPU entry points hand each device's share to a host thread whose
+// current context is that device's.
+constexpr int PL_MAX_DEV = 16;
 struct Ctx {
   bool ready = false;
   int device = -1;
+  int index = 0;  // position in g_ctx
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // D2H of finished row blocks overlaps the remaining Gram launches
@@ -144,10 +164,19 @@ struct Ctx {
   PFN_cuTensorMapEncodeTiled encode = nullptr;
   void* ws[WS_NSLOTS] = {};
   size_t ws_bytes[WS_NSLOTS] = {};
-  double t_kernel = 0, t_h2d = 0, t_d2h = 0;
+  double t_kernel = 0, t_h2d = 0, t_d2h = 0, t_coll = 0;
   bool profiling = false;
   bool main_timed = false;
-} g;
+  HostStager stager;  // pinned staging ring + host threads for pageable host memory (hoststage.h)
+  SyrkSchedCache sched;
+  void* comm = nullptr;  // ncclComm_t of this device (pl_init_all: one per context; pl_comm_init_rank: context 0)
+};
+Ctx g_ctx[PL_MAX_DEV];
+int g_ndev = 0;  // contexts in use (0 before pl_init)
+thread_local Ctx* tl_ctx = &g_ctx[0];
+#define g (*tl_ctx)
+#define g_stager (g.stager)
+#define g_sched (g.sched)
 
 // ev[4], ev[5] bracket the dominant (DMMA) kernel of the last operation when profiling is on
 #define MAIN_KERNEL_BEGIN(st) do { if (g.profiling) CUDA_TRY(cudaEventRecord(g.ev[4], st)); } while (0)
@@ -182,6 +211,9 @@ int ws_get(int slot, size_t bytes, void** out) {
 
 int need_ready() {
   if (!g.ready) return set_err(PL_ENODEV, "plb200 is not initialised: call pl_init (needs an sm_100 GPU; there is no CPU fallback)");
+  // every entry point (host and _dev) works on the device of the calling thread's context, whatever device the caller had current
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != g.device) CUDA_TRY(cudaSetDevice(g.device));
   return PL_OK;
 }
 
@@ -526,12 +558,6 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
 //     differences. Measured (profiles/r01_syrk_schedules.json): config 3 22.5 -> 22.2 ms, a per-GPU eighth of it 2.95 -> 2.82 ms,
 //     a quarter of config 4 80.3 -> 78.2 ms; 4..8 rounds and cost 1.12..1.16 are flat.
 // Either way the partial slots of a unit are contiguous and in row order, so the second-stage sum is deterministic.
-struct SyrkSchedule {
-  std::vector<int> cta_first, unit_first;
-  std::vector<SyrkPiece> pieces;
-  int nctas = 0, nslots = 0;
-};
-
 struct SyrkSchedConfig {
   int mode;        // 0 waves, 1 streamk
   int waves;       // CTAs per SM
@@ -649,16 +675,6 @@ void build_syrk_schedule(int64_t R, int T, int nunits, int num_sms, const SyrkSc
   out->nslots = slot;
 }
 
-
-// the schedule of the last shape stays on the device (same shape again: no rebuild, no upload)
-struct SyrkSchedCache {
-  int64_t R = -1;
-  int T = -1;
-  const void* dev = nullptr;
-  cudaStream_t up_stream = nullptr;  // the stream the table was uploaded on; other streams wait for `ready` before using it
-  cudaEvent_t ready = nullptr;
-  SyrkSchedule sch;
-} g_sched;
 
 // drho_out (centred mode, optional): rho = sum_r (a_r - mean) of this shard, the by-product of the one-sided centring
 int syrk_dev_impl(const double* dA, int64_t R, int64_t Kf, int64_t lda, const double* dw, int64_t ne, double w_e, double w_f, const double* db,
@@ -879,33 +895,26 @@ int check_offsets(const int64_t* off, int64_t N) {
   return PL_OK;
 }
 
-// Streamed weighted normal equations over a list of host row blocks: chunks of rows are copied on the copy stream into two
-// alternating device buffers while the SYRK of the previous chunk runs on the compute stream; the unscaled chunk partials are
-// accumulated in chunk order (deterministic), then finished exactly like the resident path.
-int normal_eq_stream(const double* const* blocks, const int64_t* rows, const int64_t* lds, int64_t nblocks, int64_t R, int64_t Kf, const double* w,
-                     int64_t ne, double w_e, double w_f, const double* b, int ic, double lambda, double* AtWA, double* AtWb, int64_t chunk_rows) {
+// First half: leaves the UNSCALED sums of these rows on the device as one bucket [S (Kf x Kf) ; vec = v, c, s (2 Kf + 2)] — what a
+// multi-GPU caller all-reduces — and returns after enqueueing (g.ev[0], g.ev[1] recorded around the vector uploads).
+int normal_eq_stream_partial(const double* const* blocks, const int64_t* rows, const int64_t* lds, int64_t nblocks, int64_t R, int64_t Kf,
+                             const double* w, int64_t ne, double w_e, double w_f, const double* b, bool want_vec, int64_t chunk_rows,
+                             double** bucket_out) {
   const int64_t ldp = (Kf + 1) & ~(int64_t)1;
-  const int64_t n = Kf + ic;
-  const bool want_vec = ic || b;
   if (chunk_rows > R) chunk_rows = R;
   if (chunk_rows < 1) chunk_rows = 1;
-  void *buf[2], *dS, *dvec = nullptr, *dSacc, *dVacc = nullptr, *dM, *dv = nullptr;
-  double *dw = nullptr, *db = nullptr;
+  void *buf[2], *dS, *dvec = nullptr, *dSacc;
+  double *dVacc, *dw = nullptr, *db = nullptr;
   PL_TRY(ws_get(WS_NE_BUF0, (size_t)chunk_rows * ldp * 8, &buf[0]));
   PL_TRY(ws_get(WS_NE_BUF1, (size_t)(R > chunk_rows ? chunk_rows : 1) * ldp * 8, &buf[1]));
   PL_TRY(ws_get(WS_H_S, (size_t)Kf * Kf * 8, &dS));
-  PL_TRY(ws_get(WS_NE_SACC, (size_t)Kf * Kf * 8, &dSacc));
-  if (want_vec) {
-    PL_TRY(ws_get(WS_H_VEC, (size_t)(2 * Kf + 2) * 8, &dvec));
-    PL_TRY(ws_get(WS_NE_VACC, (size_t)(2 * Kf + 2) * 8, &dVacc));
-  }
-  PL_TRY(ws_get(WS_H_OUT1, (size_t)n * n * 8, &dM));
-  if (AtWb) PL_TRY(ws_get(WS_H_OUT2, (size_t)n * 8, &dv));
+  PL_TRY(ws_get(WS_NE_SACC, (size_t)(Kf * Kf + 2 * Kf + 2) * 8, &dSacc));
+  dVacc = (double*)dSacc + Kf * Kf;
+  if (want_vec) PL_TRY(ws_get(WS_H_VEC, (size_t)(2 * Kf + 2) * 8, &dvec));
   CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
   if (w) PL_TRY(h2d_vector(w, R, WS_H_IN2, &dw));
   if (b) PL_TRY(h2d_vector(b, R, WS_H_IN3, &db));
-  CUDA_TRY(cudaMemsetAsync(dSacc, 0, (size_t)Kf * Kf * 8, g.stream));
-  if (want_vec) CUDA_TRY(cudaMemsetAsync(dVacc, 0, (size_t)(2 * Kf + 2) * 8, g.stream));
+  CUDA_TRY(cudaMemsetAsync(dSacc, 0, (size_t)(Kf * Kf + 2 * Kf + 2) * 8, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
   // the copy stream must not overwrite buffers an earlier call's kernels may still be reading
   CUDA_TRY(cudaEventRecord(g.chunk_ev[4], g.stream));
@@ -948,18 +957,39 @@ int normal_eq_stream(const double* const* blocks, const int64_t* rows, const int
     accumulate_kernel<<<g.num_sms * 4, 256, 0, g.stream>>>((const double*)dS, Kf * Kf, (double*)dSacc);
     LAUNCH_CHECK();
     if (want_vec) {
-      accumulate_kernel<<<8, 256, 0, g.stream>>>((const double*)dvec, 2 * Kf + 2, (double*)dVacc);
+      accumulate_kernel<<<8, 256, 0, g.stream>>>((const double*)dvec, 2 * Kf + 2, dVacc);
       LAUNCH_CHECK();
     }
     CUDA_TRY(cudaEventRecord(g.chunk_ev[2 + bi], g.stream));
     r0 += nr;
   }
-  PL_TRY(finish_dev_impl((double*)dSacc, (double*)dVacc, Kf, ic, lambda, (double*)dM, (double*)dv, g.stream));
+  *bucket_out = (double*)dSacc;
+  return PL_OK;
+}
+
+// Second half on the (possibly all-reduced) bucket: finish kernel, D2H, timing.
+int normal_eq_bucket_finish(const double* bucket, int64_t Kf, bool want_vec, int ic, double lambda, double* AtWA, double* AtWb) {
+  const int64_t n = Kf + ic;
+  void *dM, *dv = nullptr;
+  PL_TRY(ws_get(WS_H_OUT1, (size_t)n * n * 8, &dM));
+  if (AtWb) PL_TRY(ws_get(WS_H_OUT2, (size_t)n * 8, &dv));
+  PL_TRY(finish_dev_impl(bucket, want_vec ? bucket + Kf * Kf : nullptr, Kf, ic, lambda, (double*)dM, (double*)dv, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
   CUDA_TRY(cudaMemcpyAsync(AtWA, dM, (size_t)n * n * 8, cudaMemcpyDeviceToHost, g.stream));
   if (AtWb) CUDA_TRY(cudaMemcpyAsync(AtWb, dv, (size_t)n * 8, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev[3], g.stream));
   return finish_timing();
+}
+
+// Streamed weighted normal equations over a list of host row blocks: chunks of rows are copied on the copy stream into two
+// alternating device buffers while the SYRK of the previous chunk runs on the compute stream; the unscaled chunk partials are
+// accumulated in chunk order (deterministic), then finished exactly like the resident path.
+int normal_eq_stream(const double* const* blocks, const int64_t* rows, const int64_t* lds, int64_t nblocks, int64_t R, int64_t Kf, const double* w,
+                     int64_t ne, double w_e, double w_f, const double* b, int ic, double lambda, double* AtWA, double* AtWb, int64_t chunk_rows) {
+  const bool want_vec = ic || b;
+  double* bucket = nullptr;
+  PL_TRY(normal_eq_stream_partial(blocks, rows, lds, nblocks, R, Kf, w, ne, w_e, w_f, b, want_vec, chunk_rows, &bucket));
+  return normal_eq_bucket_finish(bucket, Kf, want_vec, ic, lambda, AtWA, AtWb);
 }
 
 
@@ -1120,34 +1150,90 @@ int metrics_dev_impl(const double* dxp, const double* dx, int64_t n, double* dou
 
 }  // namespace
 
-extern "C" {
+namespace {
 
-int pl_init(int device) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (g.ready) return PL_OK;
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0) {
-    cudaGetLastError();
-    return set_err(PL_ENODEV, "no CUDA device available (%s); plb200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+// defined in multi.inl (included at the end of this file): single-process multi-GPU forms of the host entry points
+void multi_shutdown();
+int normal_eq_multi(const double* const* blocks, const int64_t* rows, const int64_t* lds, int64_t nblocks, int64_t R, int64_t Kf, const double* w,
+                    int64_t ne, double w_e, double w_f, const double* b, int ic, double lambda, double* AtWA, double* AtWb, int64_t chunk_rows);
+int cov_multi(const double* X, int64_t n, int64_t Kf, int64_t ldx, double* mean_inout, int mean_given, int center, double* C);
+int gram_sym_multi(int kernel_id, const double* X, int64_t n, int64_t d, int64_t ldx, int alpha, int cinv_kind, const double* cinv, double ell,
+                   double beta, double* K, int64_t ldk);
+// inputs below these sizes stay on device 0 even when the library drives several GPUs
+constexpr double MULTI_MIN_ROW_BYTES = 256.0 * 1048576.0;  // normal equations / covariance: bytes of the row matrix
+constexpr int64_t MULTI_MIN_GRAM_N = 8192;                 // symmetric kernel matrices: number of features
+
+// Symmetric(K) uplo = :U storage (kernels.jl:217-222) streamed to the host: row block jb of the row-major view is complete as soon as
+// tile column jb is. The T tile columns are cut into `nchunk_total` ranges of equal work; this call computes ranges [c_lo, c_hi) — all of
+// them on one GPU, one contiguous share per device when several GPUs work on one matrix — launching the Gram kernel once per range and
+// copying each finished range to the host on the copy stream while the next ranges compute: the PCIe copy (the e2e bottleneck)
+// starts at once. Only rows [128 bounds[c_lo], 128 bounds[c_hi]) of the result exist on this device. Records g.ev[1..3].
+int gram_sym_stream(int kernel_id, const double* d1, int64_t n1, int64_t l1, int64_t d, int alpha, int cinv_kind, const double* dc, double ell,
+                    double beta, double* K, int64_t ldk, int c_lo, int c_hi, int nchunk_total) {
+  const int T = (int)((n1 + GRAM_BM - 1) / GRAM_BM);
+  const int64_t ldo = (n1 + 1) & ~(int64_t)1;
+  std::vector<int> bounds(nchunk_total + 1);
+  for (int c = 0; c <= nchunk_total; ++c) bounds[c] = (int)(T * sqrt((double)c / nchunk_total) + 0.5);
+  bounds[0] = 0;
+  bounds[nchunk_total] = T;
+  const int64_t row_lo = (int64_t)bounds[c_lo] * GRAM_BM;
+  int64_t row_hi = (int64_t)bounds[c_hi] * GRAM_BM;
+  if (row_hi > n1) row_hi = n1;
+  void* outbuf;
+  PL_TRY(ws_get(WS_H_OUT1, (size_t)(row_hi > row_lo ? row_hi - row_lo : 1) * ldo * 8, &outbuf));
+  double* dK = (double*)outbuf - row_lo * ldo;  // rows below row_lo are never addressed
+  CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
+  GramLaunch L;
+  PL_TRY(gram_dev_impl(kernel_id, d1, n1, l1, nullptr, n1, 0, d, alpha, cinv_kind, dc, ell, beta, dK, ldo, PL_FILL_RM_LOWER, 0, 1, 0, g.stream, &L));
+  const int nch = c_hi - c_lo;
+  if (nch > 12) return set_err(PL_EINVAL, "too many chunks per device");
+  for (int c = 0; c < nch; ++c) {
+    if (bounds[c_lo + c + 1] > bounds[c_lo + c]) {
+      L.tcol_begin = bounds[c_lo + c];
+      L.tcol_end = bounds[c_lo + c + 1];
+      PL_TRY(launch_gram(L, g.stream));
+    }
+    CUDA_TRY(cudaEventRecord(g.chunk_ev[c], g.stream));
   }
-  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
-  if (device >= count) return set_err(PL_EINVAL, "device %d out of range (%d devices)", device, count);
+  CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
+  const bool stage_out = staging_for(K, (size_t)n1 * n1 * 4);
+  for (int c = 0; c < nch; ++c) {
+    CUDA_TRY(cudaStreamWaitEvent(g.copy_stream, g.chunk_ev[c], 0));
+    for (int tb = bounds[c_lo + c]; tb < bounds[c_lo + c + 1]; ++tb) {
+      const int64_t r0 = (int64_t)tb * GRAM_BM;
+      const int64_t r1 = r0 + GRAM_BM < n1 ? r0 + GRAM_BM : n1;
+      if (stage_out)
+        CUDA_TRY(g_stager.d2h_2d(K + r0 * ldk, (size_t)ldk * 8, dK + r0 * ldo, (size_t)ldo * 8, (size_t)r1 * 8, (size_t)(r1 - r0), g.copy_stream, false));
+      else
+        CUDA_TRY(cudaMemcpy2DAsync(K + r0 * ldk, (size_t)ldk * 8, dK + r0 * ldo, (size_t)ldo * 8, (size_t)r1 * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, g.copy_stream));
+    }
+  }
+  if (stage_out) CUDA_TRY(g_stager.finish());
+  CUDA_TRY(cudaEventRecord(g.ev[3], g.copy_stream));
+  CUDA_TRY(cudaStreamSynchronize(g.copy_stream));
+  return finish_timing();
+}
+
+// create context `idx` on CUDA device `device`: streams, events, kernel attributes. Leaves the calling thread on that device.
+int ctx_create(int idx, int device) {
+  Ctx& c = g_ctx[idx];
+  if (c.ready) return PL_OK;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return set_err(PL_ENODEV, "device %d is sm_%d%d; libplb200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
   CUDA_TRY(cudaSetDevice(device));
-  g.device = device;
-  g.num_sms = prop.multiProcessorCount;
+  c.device = device;
+  c.index = idx;
+  c.num_sms = prop.multiProcessorCount;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) return set_err(PL_ECUDA, "cuTensorMapEncodeTiled entry point not found");
-  g.encode = (PFN_cuTensorMapEncodeTiled)fn;
-  CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
-  for (auto& ev : g.ev) CUDA_TRY(cudaEventCreate(&ev));
-  for (auto& ev : g.chunk_ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  c.encode = (PFN_cuTensorMapEncodeTiled)fn;
+  CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  for (auto& ev : c.ev) CUDA_TRY(cudaEventCreate(&ev));
+  for (auto& ev : c.chunk_ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 #define GRAM_ATTR(EPI_)                                                                                                                  \
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));                 \
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));                 \
@@ -1159,46 +1245,83 @@ int pl_init(int device) {
 #undef GRAM_ATTR
   CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
-  g.ready = true;
+  c.ready = true;
+  return PL_OK;
+}
+
+void ctx_destroy(int idx) {
+  Ctx& c = g_ctx[idx];
+  if (!c.ready) return;
+  cudaSetDevice(c.device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < WS_NSLOTS; ++i) {
+    if (c.ws[i]) cudaFree(c.ws[i]);
+    c.ws[i] = nullptr;
+    c.ws_bytes[i] = 0;
+  }
+  for (auto& ev : c.ev) {
+    if (ev) cudaEventDestroy(ev);
+    ev = nullptr;
+  }
+  for (auto& ev : c.chunk_ev) {
+    if (ev) cudaEventDestroy(ev);
+    ev = nullptr;
+  }
+  c.stager.shutdown();
+  if (c.sched.ready) cudaEventDestroy(c.sched.ready);
+  c.sched.ready = nullptr;
+  c.sched.dev = nullptr;
+  c.sched.R = -1;
+  if (c.stream) cudaStreamDestroy(c.stream);
+  if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+  c.stream = nullptr;
+  c.copy_stream = nullptr;
+  c.ready = false;
+}
+
+int device_count_checked(int* count) {
+  *count = 0;
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess || *count == 0) {
+    cudaGetLastError();
+    return set_err(PL_ENODEV, "no CUDA device available (%s); plb200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  return PL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pl_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_ctx[0].ready) return PL_OK;
+  int count = 0;
+  PL_TRY(device_count_checked(&count));
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  if (device >= count) return set_err(PL_EINVAL, "device %d out of range (%d devices)", device, count);
+  tl_ctx = &g_ctx[0];
+  PL_TRY(ctx_create(0, device));
+  g_ndev = 1;
   return PL_OK;
 }
 
 void pl_finalize(void) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (!g.ready) return;
-  cudaSetDevice(g.device);
-  cudaDeviceSynchronize();
-  for (int i = 0; i < WS_NSLOTS; ++i) {
-    if (g.ws[i]) cudaFree(g.ws[i]);
-    g.ws[i] = nullptr;
-    g.ws_bytes[i] = 0;
-  }
-  for (auto& ev : g.ev) {
-    if (ev) cudaEventDestroy(ev);
-    ev = nullptr;
-  }
-  for (auto& ev : g.chunk_ev) {
-    if (ev) cudaEventDestroy(ev);
-    ev = nullptr;
-  }
+  if (!g_ctx[0].ready) return;
+  multi_shutdown();
   if (cs.h) {
+    cudaSetDevice(g_ctx[0].device);
     if (cs.params) cs.DestroyParams(cs.params);
     cs.Destroy(cs.h);
     cs.h = nullptr;
     cs.params = nullptr;
   }
-  g_stager.shutdown();
-  if (g_sched.ready) cudaEventDestroy(g_sched.ready);
-  g_sched.ready = nullptr;
-  g_sched.dev = nullptr;
-  g_sched.R = -1;
   ell_state.valid = false;
   neq_state.open = false;
-  if (g.stream) cudaStreamDestroy(g.stream);
-  if (g.copy_stream) cudaStreamDestroy(g.copy_stream);
-  g.stream = nullptr;
-  g.copy_stream = nullptr;
-  g.ready = false;
+  for (int i = PL_MAX_DEV - 1; i >= 0; --i) ctx_destroy(i);
+  g_ndev = 0;
+  tl_ctx = &g_ctx[0];
 }
 
 const char* pl_last_error(void) { return g_err; }
@@ -1232,7 +1355,8 @@ int pl_last_main_kernel_ms(double* ms) {
 
 int64_t pl_workspace_bytes(void) {
   int64_t tot = 0;
-  for (int i = 0; i < WS_NSLOTS; ++i) tot += (int64_t)g.ws_bytes[i];
+  for (int c = 0; c < PL_MAX_DEV; ++c)
+    for (int i = 0; i < WS_NSLOTS; ++i) tot += (int64_t)g_ctx[c].ws_bytes[i];
   return tot;
 }
 
@@ -1254,6 +1378,19 @@ int pl_workspace_trim(int keep_resident) {
     g.ws[i] = nullptr;
     g.ws_bytes[i] = 0;
   }
+  g.sched.dev = nullptr;
+  for (int c = 1; c < g_ndev; ++c) {  // the other devices of a pl_init_all session hold scratch only
+    Ctx& x = g_ctx[c];
+    CUDA_TRY(cudaSetDevice(x.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < WS_NSLOTS; ++i) {
+      if (x.ws[i]) CUDA_TRY(cudaFree(x.ws[i]));
+      x.ws[i] = nullptr;
+      x.ws_bytes[i] = 0;
+    }
+    x.sched.dev = nullptr;
+  }
+  CUDA_TRY(cudaSetDevice(g.device));
   if (!keep_resident) {
     ell_state.valid = false;
     neq_state.open = false;
@@ -1423,6 +1560,8 @@ static int gram_host(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, 
   if (ldk < n2) return set_err(PL_EINVAL, "ldk smaller than the number of columns");
   if (sym && (fill < 1 || fill > 3)) return set_err(PL_EINVAL, "bad fill");
   if (n1 == 0 || n2 == 0) return PL_OK;
+  if (sym && fill == PL_FILL_RM_LOWER && g_ndev > 1 && n1 >= MULTI_MIN_GRAM_N)  // several GPUs: tile-column ranges per device, parallel D2H
+    return gram_sym_multi(kernel_id, X1, n1, d, ldx1, alpha, cinv_kind, cinv, ell, beta, K, ldk);
   CUDA_TRY(cudaSetDevice(g.device));
   CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
   double *d1, *d2 = nullptr, *dc = nullptr, *dK;
@@ -1437,49 +1576,14 @@ static int gram_host(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, 
     if (!cinv) return set_err(PL_EINVAL, "cinv is NULL");
     PL_TRY(h2d_vector(cinv, d * d, WS_H_IN3, &dc));  // dense d x d; gram_dev_impl pads it if d is odd
   }
+  const int T = (int)((n1 + GRAM_BM - 1) / GRAM_BM);
+  if (sym && fill == PL_FILL_RM_LOWER && T >= 16)  // the reference's storage contract at scale: computed and copied out in overlapped column ranges
+    return gram_sym_stream(kernel_id, d1, n1, l1, d, alpha, cinv_kind, dc, ell, beta, K, ldk, 0, 8, 8);
   const int64_t ldo = (n2 + 1) & ~(int64_t)1;
   void* outbuf;
   PL_TRY(ws_get(WS_H_OUT1, (size_t)n1 * ldo * 8, &outbuf));
   dK = (double*)outbuf;
   CUDA_TRY(cudaEventRecord(g.ev[1], g.stream));
-  const int T = (int)((n1 + GRAM_BM - 1) / GRAM_BM);
-  if (sym && fill == PL_FILL_RM_LOWER && T >= 16) {
-    // Symmetric(K) uplo = :U storage (kernels.jl:217-222): row block jb of the row-major view is complete as soon as tile
-    // column jb is. Launch the Gram kernel over NCHUNK tile-column ranges of equal work and stream each finished range
-    // to the host on a second stream while the next ranges compute: the PCIe copy (the e2e bottleneck) starts at once.
-    constexpr int NCHUNK = 8;
-    GramLaunch L;
-    PL_TRY(gram_dev_impl(kernel_id, d1, n1, l1, nullptr, n2, 0, d, alpha, cinv_kind, dc, ell, beta, dK, ldo, fill, 0, 1, 0, g.stream, &L));
-    int bounds[NCHUNK + 1];
-    for (int c = 0; c <= NCHUNK; ++c) bounds[c] = (int)(T * sqrt((double)c / NCHUNK) + 0.5);
-    bounds[0] = 0;
-    bounds[NCHUNK] = T;
-    for (int c = 0; c < NCHUNK; ++c) {
-      if (bounds[c + 1] > bounds[c]) {
-        L.tcol_begin = bounds[c];
-        L.tcol_end = bounds[c + 1];
-        PL_TRY(launch_gram(L, g.stream));
-      }
-      CUDA_TRY(cudaEventRecord(g.chunk_ev[c], g.stream));
-    }
-    CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
-    const bool stage_out = staging_for(K, (size_t)n1 * n1 * 4);
-    for (int c = 0; c < NCHUNK; ++c) {
-      CUDA_TRY(cudaStreamWaitEvent(g.copy_stream, g.chunk_ev[c], 0));
-      for (int tb = bounds[c]; tb < bounds[c + 1]; ++tb) {
-        const int64_t r0 = (int64_t)tb * GRAM_BM;
-        const int64_t r1 = r0 + GRAM_BM < n1 ? r0 + GRAM_BM : n1;
-        if (stage_out)
-          CUDA_TRY(g_stager.d2h_2d(K + r0 * ldk, (size_t)ldk * 8, dK + r0 * ldo, (size_t)ldo * 8, (size_t)r1 * 8, (size_t)(r1 - r0), g.copy_stream, false));
-        else
-          CUDA_TRY(cudaMemcpy2DAsync(K + r0 * ldk, (size_t)ldk * 8, dK + r0 * ldo, (size_t)ldo * 8, (size_t)r1 * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, g.copy_stream));
-      }
-    }
-    if (stage_out) CUDA_TRY(g_stager.finish());
-    CUDA_TRY(cudaEventRecord(g.ev[3], g.copy_stream));
-    CUDA_TRY(cudaStreamSynchronize(g.copy_stream));
-    return finish_timing();
-  }
   PL_TRY(gram_dev_impl(kernel_id, d1, n1, l1, d2, n2, l2, d, alpha, cinv_kind, dc, ell, beta, dK, ldo, fill, 0, 1, 0, g.stream));
   CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
   if (!sym || fill == PL_FILL_FULL) {
@@ -1562,6 +1666,13 @@ int pl_normal_eq(const double* A, int64_t R, int64_t Kf, int64_t lda, const doub
   if (!A || !AtWA || R < 0 || Kf <= 0 || lda < Kf) return set_err(PL_EINVAL, "bad arguments");
   if (AtWb && !b) return set_err(PL_EINVAL, "AtWb requested without b");
   CUDA_TRY(cudaSetDevice(g.device));
+  if (g_ndev > 1 && (double)R * (double)Kf * 8.0 >= MULTI_MIN_ROW_BYTES) {
+    // several GPUs (pl_init_all): rows sharded over the devices, every device streams its own shard over its own PCIe link, one all-reduce
+    const double* blk[1] = {A};
+    const int64_t rows[1] = {R}, lds[1] = {lda};
+    const int64_t ne = n_energy_rows < 0 ? 0 : (n_energy_rows > R ? R : n_energy_rows);
+    return normal_eq_multi(blk, rows, lds, 1, R, Kf, w, ne, w_e, w_f, b, add_intercept ? 1 : 0, lambda, AtWA, AtWb, 0);
+  }
   if ((double)R * (double)Kf * 8.0 > 768.0 * 1048576.0) {
     // large inputs: stream row chunks through two device buffers, H2D overlapped with the SYRK (same code as pl_normal_eq_blocks)
     int64_t chunk_rows = (((int64_t)512 << 20) / (Kf * 8) + 15) / 16 * 16;
@@ -1600,6 +1711,7 @@ int pl_cov(const double* X, int64_t n, int64_t Kf, int64_t ldx, double* mean_ino
   if (!X || !C || n <= 0 || Kf <= 0 || ldx < Kf) return set_err(PL_EINVAL, "bad arguments");
   if (center && !mean_inout) return set_err(PL_EINVAL, "centred covariance needs mean_inout");
   CUDA_TRY(cudaSetDevice(g.device));
+  if (g_ndev > 1 && (double)n * (double)Kf * 8.0 >= MULTI_MIN_ROW_BYTES) return cov_multi(X, n, Kf, ldx, mean_inout, mean_given, center, C);
   CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
   double* dX;
   int64_t ld;
@@ -1705,7 +1817,9 @@ int pl_normal_eq_blocks(const double* const* blocks, const int64_t* rows, int64_
   if (!lds) return set_err(PL_ENOMEM, "host allocation failed");
   for (int64_t k = 0; k < nblocks; ++k) lds[k] = Kf;
   int64_t ne = n_energy_rows < 0 ? 0 : (n_energy_rows > R ? R : n_energy_rows);
-  const int rc = normal_eq_stream(blocks, rows, lds, nblocks, R, Kf, w, ne, w_e, w_f, b, add_intercept ? 1 : 0, lambda, AtWA, AtWb, chunk_rows);
+  const int rc = (g_ndev > 1 && (double)R * (double)Kf * 8.0 >= MULTI_MIN_ROW_BYTES)
+                     ? normal_eq_multi(blocks, rows, lds, nblocks, R, Kf, w, ne, w_e, w_f, b, add_intercept ? 1 : 0, lambda, AtWA, AtWb, chunk_rows)
+                     : normal_eq_stream(blocks, rows, lds, nblocks, R, Kf, w, ne, w_e, w_f, b, add_intercept ? 1 : 0, lambda, AtWA, AtWb, chunk_rows);
   free(lds);
   return rc;
 }
@@ -2384,3 +2498,5 @@ int pl_metrics(const double* x_pred, const double* x, int64_t n, double* out) {
 }
 
 }  // extern "C"
+
+#include "multi.inl"  // NCCL (dlopen), pl_init_all / pl_comm_*, the sharded entry points and the resident Gram handle

@@ -26,6 +26,23 @@ _vp = ctypes.c_void_p
 # name -> (restype, argtypes); mirrors include/plb200.h one to one (tests/test_abi.py checks the header against this)
 PROTOTYPES = {
     "pl_init": (_int, [_int]),
+    "pl_init_all": (_int, [_int, ctypes.POINTER(ctypes.c_int)]),
+    "pl_device_count": (_int, []),
+    "pl_comm_unique_id": (_int, [_vp]),
+    "pl_comm_init_rank": (_int, [_int, _int, _vp]),
+    "pl_comm_info": (_int, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "pl_comm_destroy": (_int, []),
+    "pl_last_coll_ms": (_int, [_dp]),
+    "pl_normal_eq_sharded": (_int, [_dp, _i64, _i64, _i64, _dp, _i64, _dbl, _dbl, _dp, _int, _dbl, _dp, _dp]),
+    "pl_normal_eq_sharded_dev": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _dbl, _dbl, _vp, _int, _dbl, _vp, _vp, _vp]),
+    "pl_cov_sharded": (_int, [_dp, _i64, _i64, _i64, _i64, _dp, _int, _int, _dp]),
+    "pl_cov_sharded_dev": (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _int, _int, _vp, _vp]),
+    "pl_allreduce_dev": (_int, [_vp, _i64, _vp]),
+    "pl_gram_resident": (_int, [_int, _dp, _i64, _i64, _i64, _int, _int, _dp, _dbl, _dbl, ctypes.POINTER(_vp)]),
+    "pl_gram_resident_info": (_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "pl_gram_resident_shard": (_int, [_vp, _int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_i64), ctypes.POINTER(_vp)]),
+    "pl_gram_fetch_block": (_int, [_vp, _i64, _i64, _i64, _i64, _dp, _i64]),
+    "pl_gram_free": (_int, [_vp]),
     "pl_finalize": (None, []),
     "pl_last_error": (ctypes.c_char_p, []),
     "pl_last_timing": (_int, [_dp, _dp, _dp]),
@@ -122,6 +139,61 @@ def init(device: int = -1):
         check(lib.pl_init(int(device)), "pl_init")
         _inited = True
     return lib
+
+
+def init_all(ndev: int = 0, device_ids=None):
+    """pl_init_all: ONE process drives `ndev` GPUs (0: all visible); the host entry points then shard large inputs over them."""
+    global _inited
+    lib = load()
+    if not _inited:
+        ids = None if device_ids is None else (ctypes.c_int * len(device_ids))(*device_ids)
+        check(lib.pl_init_all(int(ndev if device_ids is None else len(device_ids)), ids), "pl_init_all")
+        _inited = True
+    return lib
+
+
+def device_count() -> int:
+    return int(load().pl_device_count())
+
+
+def comm_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    check(load().pl_comm_unique_id(buf), "pl_comm_unique_id")
+    return buf.raw
+
+
+def comm_init_rank(nranks: int, rank: int, uid: bytes):
+    """collective: every rank of a one-process-per-GPU job calls it with rank 0's pl_comm_unique_id bytes"""
+    assert len(uid) == 128
+    check(lib().pl_comm_init_rank(int(nranks), int(rank), ctypes.create_string_buffer(uid, 128)), "pl_comm_init_rank")
+
+
+def comm_init_from_torch(group=None):
+    """Create the library's NCCL communicator over the ranks of an initialised torch.distributed job: rank 0's unique id travels
+    through torch's object broadcast (control plane only); the data-path collectives are then issued by libplb200 itself."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    box = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    comm_init_rank(world, rank, box[0])
+    return world, rank
+
+
+def comm_info():
+    n, r, v = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    load().pl_comm_info(ctypes.byref(n), ctypes.byref(r), ctypes.byref(v))
+    return {"nranks": n.value, "rank": r.value, "nccl_version": v.value}
+
+
+def comm_destroy():
+    check(load().pl_comm_destroy(), "pl_comm_destroy")
+
+
+def last_coll_ms() -> float:
+    ms = _dbl()
+    check(load().pl_last_coll_ms(ctypes.byref(ms)), "pl_last_coll_ms")
+    return ms.value
 
 
 def lib():

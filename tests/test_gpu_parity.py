@@ -735,6 +735,118 @@ def test_config4_slice_checksums(pl):
     del X
 
 
+def test_config4_full_size_checksums(pl):
+    """BASELINE config 4 at FULL size (10^7 rows x K = 1000, 80 GB resident, mean/sigma = 10) through pl_cov_sharded_dev (one rank: no
+    communicator, same code path as the 8-GPU run): mean, trace of the centred covariance and a random 64 x 64 sub-block against
+    independent chunked fp64 torch reductions; exact symmetry. Skipped when the GPU cannot hold 80 GB + scratch."""
+    import torch
+
+    from plb200 import _lib
+
+    torch.cuda.empty_cache()
+    _lib.check(_lib.lib().pl_workspace_trim(1), "trim")
+    n, K = 10_000_000, 1000
+    if torch.cuda.mem_get_info()[0] < (n * K * 8 + 12e9):
+        pytest.skip("needs 92 GB of free HBM")
+    g = torch.Generator(device="cuda").manual_seed(1004)
+    shift = 10.0 * torch.randn(K, device="cuda", dtype=torch.float64, generator=g)
+    X = torch.empty((n, K), device="cuda", dtype=torch.float64)
+    step = 1 << 18
+    for r0 in range(0, n, step):
+        X[r0:r0 + step].normal_(generator=g)
+        X[r0:r0 + step] += shift
+    C = torch.empty((K, K), device="cuda", dtype=torch.float64)
+    m = torch.empty(K, device="cuda", dtype=torch.float64)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib().pl_cov_sharded_dev(X.data_ptr(), n, n, K, K, m.data_ptr(), 0, 1, C.data_ptr(), st), "pl_cov_sharded_dev")
+    torch.cuda.synchronize()
+    # independent reference: chunked sums in fp64 (pairwise inside torch, sequential over 39 chunks)
+    s = torch.zeros(K, device="cuda", dtype=torch.float64)
+    for r0 in range(0, n, step):
+        s += X[r0:r0 + step].sum(0)
+    m_ref = s / n
+    assert float(((m - m_ref).abs() / m_ref.abs()).max()) < 1e-12
+    assert bool(torch.equal(C, C.T))
+    idx = torch.randperm(K, device="cuda", generator=g)[:64]
+    blk_ref = torch.zeros((64, 64), device="cuda", dtype=torch.float64)
+    tr_ref = 0.0
+    for r0 in range(0, n, step):
+        Y = X[r0:r0 + step] - m_ref
+        tr_ref += float((Y * Y).sum())
+        Ys = Y[:, idx]
+        blk_ref += Ys.T @ Ys
+        del Y, Ys
+    blk_ref /= n
+    blk = C[idx][:, idx]
+    assert float((blk - blk_ref).abs().max() / blk_ref.abs().max()) < 1e-11
+    assert abs(float(torch.trace(C)) - tr_ref / n) / (tr_ref / n) < 1e-12
+    del X
+    torch.cuda.empty_cache()
+
+
+def test_config5_shard_sampled_tiles(pl, orc):
+    """BASELINE config 5 (DotProduct Gram, N = 200 000, d = 500): shard 0 of 8 (12 214 packed 128 x 128 tiles, 20 GB) exactly as one of the 8
+    GPUs computes it. 64 sampled tiles against the ORACLE's C pair loop (kernels.jl:30-36 restated), every diagonal element == 1, and
+    2 000 more tiles against an independent torch fp64 evaluation."""
+    import ctypes
+
+    import torch
+
+    from plb200 import _lib
+
+    lib = _lib.lib()
+    torch.cuda.empty_cache()
+    _lib.check(lib.pl_workspace_trim(1), "trim")
+    n, d, nparts, part = 200_000, 500, 8, 0
+    ntiles = int(lib.pl_gram_tile_count(n, 0, part, nparts))
+    if torch.cuda.mem_get_info()[0] < ntiles * 131072 + 4e9:
+        pytest.skip("needs 24 GB of free HBM")
+    rng = np.random.default_rng(1005)
+    mu = torch.as_tensor(2.0 * rng.standard_normal(d), device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(1005)
+    X = mu + torch.randn((n, d), device="cuda", dtype=torch.float64, generator=g) / np.sqrt(96.0)
+    tiles = torch.empty((ntiles, 128, 128), device="cuda", dtype=torch.float64)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.pl_gram_dev(_lib.PL_KERNEL_DOT, X.data_ptr(), n, d, None, 0, 0, d, 2, 0, None, 1.0, 1.0, tiles.data_ptr(), 128, _lib.PL_FILL_FULL, part, nparts, 1,
+                               st), "pl_gram_dev")
+    torch.cuda.synchronize()
+    Xh = X.cpu().numpy()
+    T = (n + 127) // 128
+
+    def coords(k):
+        ti, tj = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(lib.pl_gram_tile_coords(n, 0, part, nparts, int(k), ctypes.byref(ti), ctypes.byref(tj)), "coords")
+        return ti.value, tj.value
+
+    ks = rng.choice(ntiles, 64, replace=False).tolist() + [0, ntiles - 1]
+    checked = 0
+    for k in ks:
+        ti, tj = coords(k)
+        if ti < 0:
+            continue  # an unused slot of the folded enumeration (odd T)
+        r0, r1, c0, c1 = ti * 128, min(ti * 128 + 128, n), tj * 128, min(tj * 128 + 128, n)
+        ref = orc.kernel_matrix_cross(Xh[r0:r1], Xh[c0:c1], orc.DotProduct())
+        got = tiles[k, : r1 - r0, : c1 - c0].cpu().numpy()
+        if ti == tj:  # both triangles of a packed diagonal tile are written; diagonal forced to 1 (n/sqrt(n*n))
+            assert np.array_equal(np.diag(got), np.ones(r1 - r0))
+            np.fill_diagonal(ref, 1.0)
+        assert relerr(got, ref) < RTOL, (k, ti, tj)
+        checked += 1
+    assert checked >= 60
+    # 2 000 further tiles against torch fp64 (normalised rows, DGEMM, square)
+    Xn = X / X.norm(dim=1, keepdim=True)
+    worst = 0.0
+    for k in rng.choice(ntiles, 2000, replace=False).tolist():
+        ti, tj = coords(k)
+        if ti < 0 or ti == tj or ti == T - 1 or tj == T - 1:
+            continue
+        ref = (Xn[ti * 128:(ti + 1) * 128] @ Xn[tj * 128:(tj + 1) * 128].T) ** 2
+        worst = max(worst, float(((tiles[k] - ref).abs() / ref).max()))
+    assert worst < 1e-11, worst
+    del tiles, X, Xn
+    torch.cuda.empty_cache()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # SURVEY.md 8f row f2: feature / row packing on the device
 # ---------------------------------------------------------------------------------------------------------------
