@@ -152,7 +152,7 @@ def run_single(ndev):
     nn, npart, tl, bl = ctypes.c_int64(), ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
     _lib.check(lib.pl_gram_resident_info(h, ctypes.byref(nn), ctypes.byref(npart), ctypes.byref(tl), ctypes.byref(bl)), "info")
     T = (N + 127) // 128
-    assert nn.value == N and npart.value == nd and tl.value == T * (T + 1) // 2, (nn.value, npart.value, tl.value)
+    assert nn.value == N and npart.value == nd and T * (T + 1) // 2 <= tl.value <= (T + 1) // 2 * (T + 1), (nn.value, npart.value, tl.value)  # slots of the folded enumeration
     full = np.tril(Kdot) + np.tril(Kdot, -1).T  # symmetric matrix from the :U storage
     worst = 0.0
     for (i0, i1, j0, j1) in [(0, 300, 0, 300), (100, 400, 5000, 5700), (8000, 9000, 200, 260), (8873, 9000, 8873, 9000), (4000, 4129, 3900, 4300), (17, 18, 0, 9000)]:
