@@ -14,7 +14,10 @@
  *    duration of a ccall).
  *  - "_dev" entry points take DEVICE pointers (16-byte aligned, leading dimension even) plus a
  *    cudaStream_t passed as void*; they only enqueue work on that stream (no sync) and are what
- *    the multi-GPU host code and the benchmarks use.
+ *    the multi-GPU host code and the benchmarks use. They run on the library's device whatever device
+ *    the caller has current, and they SHARE the library's scratch buffers (SYRK partials, schedule table,
+ *    centred copies, row statistics): enqueue them on ONE stream at a time — calls on two streams must be
+ *    ordered by the caller (event / synchronise), also across different entry points.
  *  - Matrices of descriptors are ROW-MAJOR n x d with leading dimension ld (elements). This is
  *    byte-identical to Julia's column-major d x n produced by reduce(hcat, F).
  *  - There is NO CPU fallback: without an sm_100 device pl_init fails and every entry errors.

@@ -398,6 +398,25 @@ def ols_sums(iv_data, dv_data):
     return AtA, Atb
 
 
+def pinv_julia(M, tol: float):
+    """pinv(M, tol) as linear-learn.jl:19 calls it. In Julia's LinearAlgebra [external, stdlib] the positional form is
+    pinv(M; rtol = tol): with the SVD M = U S V', singular values S .> max(rtol * maximum(S), atol = 0) are inverted, the others zeroed."""
+    M = np.asarray(M, dtype=np.float64)
+    U, S, Vt = np.linalg.svd(M)
+    cut = max(tol * (S.max() if S.size else 0.0), 0.0)
+    Sinv = np.array([1.0 / x if x > cut else 0.0 for x in S])
+    return (Vt.T * Sinv) @ U.T
+
+
+def learn_ols(iv_data, dv_data, alpha: float):
+    """learn!(lp::UnivariateLinearProblem, α) (linear-learn.jl:11-23): returns (β, σ, Σ)."""
+    AtA, Atb = ols_sums(iv_data, dv_data)  # :16-17
+    Q = pinv_julia(AtA, alpha)  # :19
+    beta = Q @ Atb  # :20
+    sigma = np.std(Atb - AtA @ beta, ddof=1)  # :21  (Statistics.std is the corrected sample deviation)
+    return beta, sigma, sigma ** 2 * Q  # :22
+
+
 def ooc_accumulate(configs, ws=(30.0, 1.0), eweight_normalized="squared"):
     """AtWA .+= A'*W*A; AtWb .+= A'*W*b per configuration (linear-learn.jl:328-357).
     configs: iterable of (global_descr K, force_descrs 3natoms x K, ref_energy, ref_forces 3natoms)."""

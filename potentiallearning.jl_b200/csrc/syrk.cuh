@@ -274,8 +274,10 @@ __device__ __forceinline__ void syrk_consume(const SyrkParams& p, const SyrkWarp
 #pragma unroll
       for (int par = 0; par < 2; ++par) {
         const int64_t r = r0 + 8 * h + 2 * t + par;
+        // uniform CTAs apply their one weight to the accumulators at the end (wscale): on the ragged last stage of the centred mode
+        // the per-row factor is then only the 1 / 0 mask of the zero-filled rows, not the weight a second time
         double w = 0.0;
-        if (need_w && r < r_end) w = p.w ? __ldg(p.w + r) : (r < p.ne ? p.w_e : p.w_f);
+        if (need_w && r < r_end) w = uniform ? 1.0 : (p.w ? __ldg(p.w + r) : (r < p.ne ? p.w_e : p.w_f));
         wv[h][par] = w;
       }
     mbar_wait(full_bar(s), ph);

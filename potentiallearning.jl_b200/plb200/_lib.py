@@ -102,6 +102,7 @@ class PLB200Error(RuntimeError):
 
 _lib = None
 _inited = False
+_device = None  # CUDA device index the library's first context is bound to (None: whatever was current at pl_init(-1))
 
 
 def load():
@@ -133,22 +134,27 @@ def check(rc: int, what: str):
 
 def init(device: int = -1):
     """pl_init: bind to one B200. Raises PLB200Error when there is no sm_100 device."""
-    global _inited
+    global _inited, _device
     lib = load()
     if not _inited:
         check(lib.pl_init(int(device)), "pl_init")
         _inited = True
+        _device = int(device) if device is not None and int(device) >= 0 else None
+    elif device is not None and int(device) >= 0 and _device is not None and int(device) != _device:
+        raise PLB200Error(f"libplb200 is bound to CUDA device {_device}; cannot re-bind it to device {device} (one process drives one GPU, "
+                          "or use init_all)")
     return lib
 
 
 def init_all(ndev: int = 0, device_ids=None):
     """pl_init_all: ONE process drives `ndev` GPUs (0: all visible); the host entry points then shard large inputs over them."""
-    global _inited
+    global _inited, _device
     lib = load()
     if not _inited:
         ids = None if device_ids is None else (ctypes.c_int * len(device_ids))(*device_ids)
         check(lib.pl_init_all(int(ndev if device_ids is None else len(device_ids)), ids), "pl_init_all")
         _inited = True
+        _device = 0 if device_ids is None else int(device_ids[0])
     return lib
 
 
@@ -202,9 +208,11 @@ def lib():
 
 def finalize():
     global _inited
+    global _device
     if _lib is not None and _inited:
         _lib.pl_finalize()
         _inited = False
+        _device = None
 
 
 def last_timing():

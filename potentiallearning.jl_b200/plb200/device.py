@@ -16,6 +16,8 @@ def _check_mat(t, name):
 
     if not (t.is_cuda and t.dtype == torch.float64 and t.dim() == 2 and t.stride(1) == 1):
         raise ValueError(f"{name} must be a CUDA float64 row-major matrix")
+    # the library's workspace lives on ONE device: bind it to the tensor's device at first use, refuse tensors of any other device
+    _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
 
 
 class DeviceEngine:

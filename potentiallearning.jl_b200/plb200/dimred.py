@@ -38,10 +38,20 @@ def covariance(rows, mean=None, center: bool = False):
 
 def compute_eigen(d, _precentered_mean=None):
     """compute_eigen(d) (dimension_reduction.jl:11-14): Q = Symmetric(mean(di*di')), eigen(Symmetric(Q)) -> (λ ascending, ϕ)."""
-    from .dpp import eigh
-
     Q, _ = covariance(d)
-    lam, phi = eigh(Q)  # eigen(Symmetric(Q)) on the GPU (pl_eigh); Q is exactly symmetric by construction
+    return eigen_symmetric(Q)
+
+
+def eigen_symmetric(Q):
+    """eigen(Symmetric(Q)) (dimension_reduction.jl:13). LAPACK on the host by default, exactly as the reference (signs and the basis of
+    degenerate clusters are solver-specific, so the default must not change solver); PLB200_EIGEN=gpu opts into pl_eigh (cuSOLVER)."""
+    import os
+
+    if os.environ.get("PLB200_EIGEN", "lapack") == "gpu":
+        from .dpp import eigh
+
+        return eigh(Q)
+    lam, phi = np.linalg.eigh(np.asarray(Q, dtype=np.float64), UPLO="U")  # Q is exactly symmetric by construction
     return lam, phi
 
 
@@ -121,9 +131,7 @@ def fit_(ds: DataSet, pca: PCAState, use_force_descriptors: bool = False):
     Q, m = covariance(rows, mean=pca.m if mean_given else None, center=True)
     if not mean_given:
         pca.m = m
-    from .dpp import eigh
-
-    lam, phi = eigh(Q)
+    lam, phi = eigen_symmetric(Q)  # LAPACK like the reference; PLB200_EIGEN=gpu opts into pl_eigh
     pca.λ, pca.W = _select(lam, phi, pca.tol)
     return None
 

@@ -111,10 +111,12 @@ def normal_equations(A, b=None, w=None, n_energy_rows=0, w_e=1.0, w_f=1.0, inter
     return M, v
 
 
-def normal_equations_blocks(blocks, b=None, w=None, n_energy_rows=0, w_e=1.0, w_f=1.0, intercept=False, lam=0.0, chunk_rows=0):
-    """Streamed GPU assembly over a LIST of row blocks (pl_normal_eq_blocks): no host-side concatenation. Each block is either a
-    K-vector (one row), a rows x K C-contiguous array, or a K x m Fortran-ordered / transposed view (Julia's column-major K x 3natoms
-    force-descriptor block, linear-learning-problem.jl:127) whose memory already is m rows of K."""
+def normal_equations_blocks(blocks, b=None, w=None, n_energy_rows=0, w_e=1.0, w_f=1.0, intercept=False, lam=0.0, chunk_rows=0, layout="julia"):
+    """Streamed GPU assembly over a LIST of row blocks (pl_normal_eq_blocks): no host-side concatenation. Orientation follows the
+    reference's containers and is decided by SHAPE, exactly as pack_rows does: a 1-D entry is a K-vector (one row: lp.B[i], iv_data[i]);
+    a 2-D entry is K x m (lp.dB[i], linear-learning-problem.jl:127) and contributes its m columns as rows — a Fortran-ordered / transposed
+    view (Julia's column-major block) is used as it lies in memory, a C-ordered K x m array is copied once. layout="rows" declares
+    2-D entries to be rows x K instead (already packed row blocks)."""
     import ctypes
 
     keep, ptrs, rows = [], [], []
@@ -123,8 +125,8 @@ def normal_equations_blocks(blocks, b=None, w=None, n_energy_rows=0, w_e=1.0, w_
         a = np.asarray(blk, dtype=np.float64)
         if a.ndim == 1:
             a = a[None, :]
-        elif not a.flags.c_contiguous and a.T.flags.c_contiguous:
-            a = a.T  # K x m column-major == m x K row-major: the bytes are used as they are
+        elif layout != "rows":
+            a = a.T  # K x m -> m rows of K; free when the block is column-major like Julia's
         a = np.ascontiguousarray(a)
         if K is None:
             K = a.shape[1]
@@ -270,7 +272,7 @@ def batch_sums(lp: LinearProblem, inds):
 def _learn_ols(lp, α: float):
     if isinstance(lp, UnivariateLinearProblem):
         AtA, Atb = ols_sums(lp.iv_data, lp.dv_data)  # :16-17 on the GPU
-        Q = np.linalg.pinv(AtA, rcond=0.0, hermitian=False) if α == 0 else _pinv_atol(AtA, α)  # pinv(AtA, α): atol
+        Q = _pinv_rtol(AtA, α)  # pinv(AtA, α) == pinv(AtA; rtol = α) (:19)
         lp.β[:] = Q @ Atb
         lp.σ[:] = np.std(Atb - AtA @ lp.β, ddof=1)
         lp.Σ[:, :] = lp.σ[0] ** 2 * Q
@@ -281,10 +283,13 @@ def _learn_ols(lp, α: float):
     return AtAe, Atbe, AtAf, Atbf
 
 
-def _pinv_atol(M, atol):
-    """Julia pinv(M, atol): singular values <= atol are dropped (linear-learn.jl:19)."""
+def _pinv_rtol(M, rtol):
+    """Julia's positional `pinv(M, tol)` (linear-learn.jl:19, :108, :61-66) is `pinv(M; rtol = tol)` [LinearAlgebra, external]: singular values
+    s with s <= rtol * maximum(s) are dropped (strict `>` keeps the rest); atol = 0. rtol = 0 keeps every non-zero singular value."""
     U, s, Vt = np.linalg.svd(M)
-    sinv = np.where(s > atol, 1.0 / np.where(s > atol, s, 1.0), 0.0)
+    tol = float(rtol) * (s.max() if s.size else 0.0)
+    keep = s > tol
+    sinv = np.where(keep, 1.0 / np.where(keep, s, 1.0), 0.0)
     return (Vt.T * sinv) @ U.T
 
 

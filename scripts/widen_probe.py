@@ -82,7 +82,7 @@ if "neq" in which:
     An = A.numpy()
     blocks = [An[:ncfg]] + [An[ncfg + i * 3 * nat: ncfg + (i + 1) * 3 * nat] for i in range(ncfg)]
     t0 = time.perf_counter()
-    M2, v2 = plb200.normal_equations_blocks(blocks, b.numpy(), None, ncfg, 100.0, 1.0, True, 0.01)
+    M2, v2 = plb200.normal_equations_blocks(blocks, b.numpy(), None, ncfg, 100.0, 1.0, True, 0.01, layout="rows")
     out["neq_blocks_pinned"] = {"nblocks": len(blocks), "ms": (time.perf_counter() - t0) * 1e3,
                                 "max_rel_vs_contiguous": float(np.max(np.abs(M2 - M.numpy())) / np.max(np.abs(M.numpy())))}
     # the same rows in PAGEABLE memory (a plain numpy / Julia array): staged by the library (hoststage.h) vs the driver's bounce buffer

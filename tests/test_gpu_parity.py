@@ -286,6 +286,47 @@ def test_reference_univariate_linear_tests(pl, orc):
     assert np.max(np.abs(A @ lp4.β - e)) < 1e-4  # :64
 
 
+def test_ols_pinv_cutoff_is_relative_like_julia(pl, orc):
+    """learn!(lp, α) uses pinv(AtA, α) (linear-learn.jl:19) — in Julia that is rtol = α: the cutoff is α * σ_max, not α. A spectrum that
+    straddles both readings (σ = 400, 25, 1, 0.04 ... with α = 0.01: the relative cutoff 4 drops what an absolute 0.01 would keep)."""
+    rng = np.random.default_rng(77)
+    K, n = 6, 40
+    Qm, _ = np.linalg.qr(rng.standard_normal((K, K)))
+    scales = np.array([20.0, 5.0, 1.0, 0.2, 0.05, 0.01])  # AtA singular values ~ n * scales^2
+    iv = [Qm @ (scales * rng.standard_normal(K)) for _ in range(n)]
+    dv = [float(rng.standard_normal()) for _ in range(n)]
+    alpha = 0.01
+    AtA, _ = orc.ols_sums(iv, dv)
+    s = np.linalg.svd(AtA, compute_uv=False)
+    assert (s > alpha).sum() > (s > alpha * s.max()).sum() >= 1, "the two cutoffs must select different ranks for this test to mean anything"
+    lp = pl.UnivariateLinearProblem(iv, dv, np.zeros(K), np.zeros(1), np.ones(1), np.zeros((K, K)))
+    pl.learn_(lp, alpha)
+    beta, sigma, Sigma = orc.learn_ols(iv, dv, alpha)
+    assert np.allclose(lp.β, beta, rtol=1e-9, atol=1e-12 * np.abs(beta).max())
+    assert abs(lp.σ[0] - sigma) < 1e-9 * sigma and np.allclose(lp.Σ, Sigma, rtol=1e-8, atol=1e-10 * np.abs(Sigma).max())
+    import scipy.linalg
+
+    assert np.allclose(pl.learning._pinv_rtol(AtA, alpha), scipy.linalg.pinv(AtA, atol=0.0, rtol=alpha), rtol=1e-9, atol=1e-14)
+
+
+def test_blocks_orientation_follows_shape(pl, orc):
+    """entries of lp.dB are K x m whatever their memory order (Fortran like Julia's, C after a numpy copy), entries of lp.B K-vectors —
+    including K == 1 and 3 natoms == K, where memory order says nothing."""
+    rng = np.random.default_rng(78)
+    for K, ms in ((5, (5, 3, 5)), (1, (4, 1, 2)), (7, (2, 9))):
+        B = [rng.standard_normal(K) for _ in ms]
+        dBf = [np.asfortranarray(rng.standard_normal((K, m))) for m in ms]
+        dBc = [np.ascontiguousarray(x) for x in dBf]
+        A = np.concatenate([np.stack(B)] + [x.T for x in dBf], axis=0)
+        b = rng.standard_normal(A.shape[0])
+        Mo, vo = orc.normal_equations(A, b, np.ones(A.shape[0]), 0.0)
+        for dB in (dBf, dBc):
+            M, v = pl.normal_equations_blocks(B + dB, b)
+            assert normerr(M, Mo) < RTOL and normerr(v, vo) < RTOL
+        M, v = pl.normal_equations_blocks([np.stack(B)] + [x.T.copy() for x in dBf], b, layout="rows")
+        assert normerr(M, Mo) < RTOL and normerr(v, vo) < RTOL
+
+
 def test_reference_covariate_linear_tests(pl, orc):
     rng = np.random.default_rng(1)
     d, num_atoms, num_configs = 8, 20, 100  # :71-73
@@ -999,15 +1040,44 @@ def test_ell_ensemble_resident_pipeline(pl, orc):
     assert pl.sample(ell, 50, rng=np.random.default_rng(3)) == s1
 
 
-def test_compute_eigen_and_pca_on_device(pl, orc):
-    """compute_eigen (dimension_reduction.jl:11-14): covariance and eigen both on the GPU; eigenvalues against the oracle."""
+def test_compute_eigen_and_pca_on_device(pl, orc, monkeypatch):
+    """compute_eigen (dimension_reduction.jl:11-14): Q on the GPU; eigen(Symmetric(Q)) stays LAPACK by default (same solver as the reference:
+    identical vectors for an identical Q), the device eigensolver is opt-in (PLB200_EIGEN=gpu). Eigenvalues against the oracle."""
     rng = np.random.default_rng(4)
     rows = rng.standard_normal((500, 30)) @ np.diag(np.linspace(0.1, 3, 30))
-    lam, phi = pl.compute_eigen(rows)
     lo, _ = orc.compute_eigen(list(rows))
-    assert np.max(np.abs(lam - lo)) / lo.max() < 1e-12
     Q = rows.T @ rows / 500
-    assert np.max(np.abs(Q @ phi - phi * lam[None, :])) / lo.max() < 1e-12
+    launches = pl.launch_count()
+    lam, phi = pl.compute_eigen(rows)
+    Qg, _ = pl.covariance(rows)
+    lam_l, phi_l = np.linalg.eigh(Qg, UPLO="U")
+    assert np.array_equal(lam, lam_l) and np.array_equal(phi, phi_l), "default: LAPACK on the GPU-built Q"
+    monkeypatch.setenv("PLB200_EIGEN", "gpu")
+    lam_g, phi_g = pl.compute_eigen(rows)
+    for l, p in ((lam, phi), (lam_g, phi_g)):
+        assert np.max(np.abs(l - lo)) / lo.max() < 1e-12
+        assert np.max(np.abs(Q @ p - p * l[None, :])) / lo.max() < 1e-12
+    assert pl.launch_count() > launches
+
+
+def test_centred_syrk_with_uniform_weight_and_ragged_rows(pl):
+    """pl_syrk_dev documents S = sum_r w_r (a_r - m)(a_r - m)'. With a uniform weight != 1 and R % 16 != 0 the ragged last stage must mask the
+    zero-filled rows without applying the weight a second time."""
+    import torch
+
+    from plb200.device import DeviceEngine
+
+    eng = DeviceEngine()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for R, K in ((1000 + 7, 40), (16 * 70 + 1, 130), (33, 8)):
+        A = torch.randn((R, K), device="cuda", dtype=torch.float64, generator=g) + 3.0
+        m = A.mean(0)
+        for (ne, we, wf) in ((0, 1.0, 2.5), (R, 0.3, 1.0), (R // 2, 2.0, 2.0)):
+            S, _ = eng.syrk_partial(A, None, ne, we, wf, None, m, False)
+            w = torch.where(torch.arange(R, device="cuda") < ne, we, wf).to(torch.float64)
+            Ac = A - m
+            ref = Ac.T @ (Ac * w[:, None])
+            assert float((S - ref).abs().max() / ref.abs().max()) < 1e-12, (R, K, ne, we, wf)
 
 
 def test_normal_equations_aug_and_fallback_agree(pl, orc, monkeypatch):
