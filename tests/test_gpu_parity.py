@@ -1074,7 +1074,8 @@ def test_centred_syrk_with_uniform_weight_and_ragged_rows(pl):
         m = A.mean(0)
         for (ne, we, wf) in ((0, 1.0, 2.5), (R, 0.3, 1.0), (R // 2, 2.0, 2.0)):
             S, _ = eng.syrk_partial(A, None, ne, we, wf, None, m, False)
-            w = torch.where(torch.arange(R, device="cuda") < ne, we, wf).to(torch.float64)
+            w = torch.full((R,), wf, device="cuda", dtype=torch.float64)
+            w[:ne] = we
             Ac = A - m
             ref = Ac.T @ (Ac * w[:, None])
             assert float((S - ref).abs().max() / ref.abs().max()) < 1e-12, (R, K, ne, we, wf)
