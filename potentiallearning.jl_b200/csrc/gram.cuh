@@ -59,6 +59,7 @@ struct GramParams {
   int part, nparts;     // tile sharding across GPUs: slot l is ours iff l % nparts == part
   int tcol_begin;       // >= 0: "column range" enumeration (symmetric only): tiles (ti <= tj) of tile columns
   int tma_out;          // TMAST variant: the output matrix is described by the third tensor map (dense, 16-byte aligned, even ldo)
+  int pdl;              // launched as a programmatic dependent of the prelude kernel: see pdl_wait() in the kernel
   int tcol_end;         //       [tcol_begin, tcol_end), column by column — lets the host stream finished rows of the
                         //       Symmetric(:U) storage to the host while later columns are still being computed
 };
@@ -311,7 +312,10 @@ __device__ __forceinline__ void gram_epilogue_staged(double (&acc)[4][8][2], con
   }
 }
 
+// NARROW is the tile SHAPE:
 // NARROW = 0: 128 x 128 output tile, warps 4 (m) x 2 (n), warp tile 32 x 64.
+// NARROW = 2: 64 x 64 output tile, warps 4 (m) x 2 (n), warp tile 16 x 32: small matrices whose 128 x 128 tiles would not fill the machine
+//             (config 1, the kDPP example shape N = 1000: 36 tiles of 128 on 148 SMs, 136 tiles of 64).
 // NARROW = 1: 128 x 32 output tile for rectangular results with few columns (projections W'(x - m) of transform!, pca_state.jl:42-62;
 //             KernelMatrix(F1, F2, k) against a handful of reference points): warps 8 (m) x 1, warp tile 16 x 32. A 128-wide tile
 //             would spend 128 / n2 times the DMMAs such a result needs; at n2 <= 32 the narrow tile is within 1.4 x of the HBM time of
@@ -322,9 +326,11 @@ template <int EPI, int NARROW, int TMAST>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const GramParams p) {
   constexpr int NSTAGE = TMAST ? GRAM_STAGES_TMAST : GRAM_STAGES;
-  constexpr int BN = NARROW ? 32 : GRAM_BN;
+  constexpr int BM = NARROW == 2 ? 64 : GRAM_BM;
+  constexpr int BN = NARROW == 1 ? 32 : (NARROW == 2 ? 64 : GRAM_BN);
   constexpr int MT = NARROW ? 2 : 4;   // 8-row DMMA m-tiles per warp
   constexpr int NT = NARROW ? 4 : 8;   // 8-column DMMA n-tiles per warp
+  constexpr uint32_t A_TILE_BYTES = BM * GRAM_BK * 8;
   constexpr uint32_t B_TILE_BYTES = BN * GRAM_BK * 8;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles
@@ -344,6 +350,9 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     fence_barrier_init();
   }
   __syncthreads();
+  // Launched as a programmatic dependent of the prelude kernel (row statistics / centred copy): everything above overlaps its tail.
+  // DotProduct contracts the caller's X itself, so only the epilogue (row statistics) has to wait; the others read the prelude's output.
+  if (p.pdl && EPI != EPI_DOT) pdl_wait();
 
   const int KT = (int)((p.d + GRAM_BK - 1) / GRAM_BK);
   const int64_t slot0 = (int64_t)blockIdx.x * p.nparts + p.part;
@@ -361,14 +370,14 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (p.tcol_begin >= 0) gram_colrange_slot_to_tile(p.tcol_begin, l, ti, tj);
         else if (!gram_slot_to_tile(p.T1, p.T2, p.symmetric, l, ti, tj)) continue;
         const bool one_tile = p.same_operand && (ti == tj);
-        const uint32_t bytes = one_tile ? GRAM_TILE_BYTES : GRAM_TILE_BYTES + B_TILE_BYTES;
+        const uint32_t bytes = one_tile ? A_TILE_BYTES : A_TILE_BYTES + B_TILE_BYTES;
         for (int kt = 0; kt < KT; ++kt, ++it) {
           const int s = it % NSTAGE;
           const uint32_t ph = (it / NSTAGE) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_arrive_expect_tx(full_bar(s), bytes);
           const uint32_t dstA = smem_base + s * 2 * GRAM_TILE_BYTES;
-          tma_load_2d(dstA, &tmA, full_bar(s), kt * GRAM_BK, ti * GRAM_BM);
+          tma_load_2d(dstA, &tmA, full_bar(s), kt * GRAM_BK, ti * BM);
           if (!one_tile) tma_load_2d(dstA + GRAM_TILE_BYTES, &tmB, full_bar(s), kt * GRAM_BK, tj * BN);
         }
       }
@@ -378,8 +387,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   // ------------------------------ DMMA consumers ------------------------------
   setmaxnreg_inc<CONSUMER_REGS>();
-  const int wm = NARROW ? warp : warp >> 1;  // 8*MT-row slab
-  const int wn = NARROW ? 0 : warp & 1;      // 8*NT-col slab
+  const int wm = NARROW == 1 ? warp : warp >> 1;  // 8*MT-row slab
+  const int wn = NARROW == 1 ? 0 : warp & 1;      // 8*NT-col slab
   const int g = lane >> 2;
   const int t = lane & 3;
   const int pg = ((g & 1) << 2) | (g >> 1);  // tile row (within an 8-row group) served by fragment row g
@@ -460,7 +469,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     //   i = 128*ti + 32*wm + 8*mt + perm(g),   j = 128*tj + 64*wn + 8*nt + perm(2t + c) = ... + t + 4c
     const int il0 = 8 * MT * wm + pg;  // local row of mt = 0
     const int jl0 = 8 * NT * wn + t;   // local col of (nt = 0, c = 0)
-    const int64_t i0 = (int64_t)ti * GRAM_BM + il0;
+    if (p.pdl && EPI == EPI_DOT) pdl_wait();  // the row statistics come from the prelude kernel this launch depends on
+    const int64_t i0 = (int64_t)ti * BM + il0;
     const int64_t j0 = (int64_t)tj * BN + jl0;
     const bool diag_tile = p.symmetric && (ti == tj);
     const bool f1 = p.packed || !p.symmetric || (p.fill & 1);            // write [i][j]
@@ -468,7 +478,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     double* base;
     int64_t ldo, ib, jb;
     if (p.packed) {  // tile k = (l - part) / nparts of this part, 128 x 128 row-major
-      base = p.out + ((l - p.part) / p.nparts) * (int64_t)(GRAM_BM * BN);
+      base = p.out + ((l - p.part) / p.nparts) * (int64_t)(BM * BN);
       ldo = BN;
       ib = il0;
       jb = jl0;
@@ -480,7 +490,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     double* const prow = base + ib * ldo + jb;  // direct:  prow[8*mt*ldo + 8*nt + 4*c]
     double* const pcol = base + jb * ldo + ib;  // mirror:  pcol[(8*nt + 4*c)*ldo + 8*mt]
-    const bool interior = ((int64_t)(ti + 1) * GRAM_BM <= p.n1) && ((int64_t)(tj + 1) * BN <= p.n2);
+    const bool interior = ((int64_t)(ti + 1) * BM <= p.n1) && ((int64_t)(tj + 1) * BN <= p.n2);
     const int rel0 = diag_tile ? (jl0 - il0) : 4096;
     const bool w1 = f1 || diag_tile, w2 = diag_tile ? true : f2;
     // ALPHA doubles as the "uncommon parameters" switch: DotProduct power != 2, or an RBF scale beta <= 0 that cannot be

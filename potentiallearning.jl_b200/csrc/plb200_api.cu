@@ -322,15 +322,43 @@ struct GramLaunch {
   int symmetric, same_operand, fill, packed, part, nparts, alpha;
   double s, beta;
   int tcol_begin = -1, tcol_end = -1;  // column-range enumeration (host streaming path)
+  int pdl = 0;                         // the launch directly follows the prelude kernel it depends on: programmatic dependent launch
 };
+
+// <<<>>> with the programmatic-dependent-launch attribute when pdl is set (the kernel then calls pdl_wait() before it touches what its
+// predecessor in the stream produces)
+template <class... KArgs, class... Args>
+cudaError_t launch_ex(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 int launch_gram(const GramLaunch& L, cudaStream_t st) {
   if (L.nA == 0 || L.nB == 0) return PL_OK;
   // rectangular results with few columns (projections, cross kernels against a handful of points): the 128 x 32 tile
   const bool narrow = !L.symmetric && !L.packed && L.nB <= 96;
-  const int BN = narrow ? 32 : GRAM_BN;
+  // small matrices: when the 128 x 128 tiles of a dense result would leave SMs idle, 64 x 64 tiles (4 x as many CTAs). N = 1000
+  // (config 1, the kDPP example shape) has 36 upper-triangle tiles of 128 for 148 SMs, 136 of 64.
+  bool small = false;
+  if (!narrow && !L.packed && L.tcol_begin < 0) {
+    const int T1 = (int)((L.nA + GRAM_BM - 1) / GRAM_BM), T2 = (int)((L.nB + GRAM_BN - 1) / GRAM_BN);
+    const int64_t t128 = L.symmetric ? (int64_t)T1 * (T1 + 1) / 2 : (int64_t)T1 * T2;
+    small = (t128 + L.nparts - 1) / L.nparts < g.num_sms;
+    if (const char* e = getenv("PLB200_GRAM_SMALL")) small = e[0] == '1' ? true : (e[0] == '0' ? false : small);
+  }
+  const int BM = small ? 64 : GRAM_BM;
+  const int BN = narrow ? 32 : (small ? 64 : GRAM_BN);
   CUtensorMap tmA, tmB;
-  PL_TRY(make_tmap_2d(&tmA, L.A, L.d, L.nA, L.ldA, GRAM_BK, GRAM_BM));
+  PL_TRY(make_tmap_2d(&tmA, L.A, L.d, L.nA, L.ldA, GRAM_BK, BM));
   PL_TRY(make_tmap_2d(&tmB, L.B, L.d, L.nB, L.ldB, GRAM_BK, BN));
   GramParams p;
   p.n1 = L.nA;
@@ -350,13 +378,15 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   p.beta = L.beta;
   p.lnbeta = (L.epi == EPI_RBF && L.beta > 0.0) ? log(L.beta) : 0.0;
   p.bmul = (L.epi == EPI_RBF && L.beta > 0.0) ? 1.0 : L.beta;
-  p.T1 = (int)((L.nA + GRAM_BM - 1) / GRAM_BM);
+  p.T1 = (int)((L.nA + BM - 1) / BM);
   p.T2 = (int)((L.nB + BN - 1) / BN);
   p.tcol_begin = L.tcol_begin;
   p.tcol_end = L.tcol_end;
   p.ntiles_total = L.tcol_begin >= 0 ? gram_colrange_num_slots(L.tcol_begin, L.tcol_end) : gram_num_slots(p.T1, p.T2, p.symmetric);
   p.part = L.part;
   p.nparts = L.nparts;
+  const bool pdl = L.pdl && !getenv("PLB200_NO_PDL");
+  p.pdl = pdl ? 1 : 0;
   const int64_t mine = (p.ntiles_total - L.part + L.nparts - 1) / L.nparts;
   if (mine <= 0) return PL_OK;
   const int grid = (int)(mine < g.num_sms ? mine : g.num_sms);
@@ -364,10 +394,10 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   // the contraction is shallow and the kernel is bound by writing K, still 1-2 % at d = 300. Needs an output the TMA unit can address
   // (16-byte aligned, even leading dimension). PLB200_GRAM_TMAST=0/1 overrides the rule (experiments).
   // (not for RBF: its exp epilogue is tuned in groups of 8 interleaved chains in gram_epilogue and measured 3-6 % slower staged)
-  bool tmast = !narrow && !L.packed && L.epi != EPI_RBF && !(reinterpret_cast<uintptr_t>(L.out) & 15u) && !(L.ldo & 1);
+  bool tmast = !narrow && !small && !L.packed && L.epi != EPI_RBF && !(reinterpret_cast<uintptr_t>(L.out) & 15u) && !(L.ldo & 1);
   if (const char* e = getenv("PLB200_GRAM_TMAST")) {
     if (e[0] == '0') tmast = false;
-    else if (e[0] == '1') tmast = !narrow && !L.packed && !(reinterpret_cast<uintptr_t>(L.out) & 15u) && !(L.ldo & 1);
+    else if (e[0] == '1') tmast = !narrow && !small && !L.packed && !(reinterpret_cast<uintptr_t>(L.out) & 15u) && !(L.ldo & 1);
   }
   CUtensorMap tmO = tmA;
   p.tma_out = 0;
@@ -376,22 +406,26 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
     p.tma_out = 1;
   }
   if (L.epi != EPI_LINEAR || L.packed || L.symmetric) MAIN_KERNEL_BEGIN(st);
-#define GRAM_LAUNCH(NARROW_, TMAST_, SMEM_)                                                                                       \
-  switch (L.epi) {                                                                                                                \
-    case EPI_LINEAR: gram_kernel<EPI_LINEAR, NARROW_, TMAST_><<<grid, GRAM_THREADS, SMEM_, st>>>(tmA, tmB, tmO, p); break;        \
-    case EPI_DOT: gram_kernel<EPI_DOT, NARROW_, TMAST_><<<grid, GRAM_THREADS, SMEM_, st>>>(tmA, tmB, tmO, p); break;              \
-    case EPI_RBF: gram_kernel<EPI_RBF, NARROW_, TMAST_><<<grid, GRAM_THREADS, SMEM_, st>>>(tmA, tmB, tmO, p); break;              \
-    case EPI_IMQ: gram_kernel<EPI_IMQ, NARROW_, TMAST_><<<grid, GRAM_THREADS, SMEM_, st>>>(tmA, tmB, tmO, p); break;              \
-    default: return set_err(PL_EINVAL, "unknown epilogue %d", L.epi);                                                            \
+  cudaError_t le = cudaSuccess;
+#define GRAM_LAUNCH(NARROW_, TMAST_, SMEM_)                                                                                                   \
+  switch (L.epi) {                                                                                                                            \
+    case EPI_LINEAR: le = launch_ex(gram_kernel<EPI_LINEAR, NARROW_, TMAST_>, grid, GRAM_THREADS, SMEM_, st, pdl, tmA, tmB, tmO, p); break;   \
+    case EPI_DOT: le = launch_ex(gram_kernel<EPI_DOT, NARROW_, TMAST_>, grid, GRAM_THREADS, SMEM_, st, pdl, tmA, tmB, tmO, p); break;         \
+    case EPI_RBF: le = launch_ex(gram_kernel<EPI_RBF, NARROW_, TMAST_>, grid, GRAM_THREADS, SMEM_, st, pdl, tmA, tmB, tmO, p); break;         \
+    case EPI_IMQ: le = launch_ex(gram_kernel<EPI_IMQ, NARROW_, TMAST_>, grid, GRAM_THREADS, SMEM_, st, pdl, tmA, tmB, tmO, p); break;         \
+    default: return set_err(PL_EINVAL, "unknown epilogue %d", L.epi);                                                                        \
   }
   if (narrow) {
     GRAM_LAUNCH(1, 0, GRAM_SMEM_BYTES)
+  } else if (small) {
+    GRAM_LAUNCH(2, 0, GRAM_SMEM_BYTES)
   } else if (tmast) {
     GRAM_LAUNCH(0, 1, GRAM_SMEM_BYTES_TMAST)
   } else {
     GRAM_LAUNCH(0, 0, GRAM_SMEM_BYTES)
   }
 #undef GRAM_LAUNCH
+  CUDA_TRY(le);
   LAUNCH_CHECK();
   if (L.epi != EPI_LINEAR || L.packed || L.symmetric) MAIN_KERNEL_END(st);
   return PL_OK;
@@ -460,6 +494,7 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
       PL_TRY(launch_prep<PREP_DOT>(X2, n2, d, l2, nullptr, nullptr, nullptr, nullptr, 0, (double*)s2, st));
     }
     L.epi = EPI_DOT;
+    L.pdl = 1;  // follows prep_rows: the main loop overlaps it, the epilogue waits for the row statistics
     L.A = X1; L.ldA = l1;
     L.B = sym ? X1 : X2; L.ldB = sym ? l1 : l2;
     L.ra = (double*)s1;
@@ -493,6 +528,7 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
     PL_TRY(ws_get(WS_STAT2, (size_t)n2 * 8, &s2));
   }
   L.epi = kernel_id == PL_KERNEL_IMQ ? EPI_IMQ : EPI_RBF;
+  L.pdl = 1;  // follows prep_rows / rowdot: barrier set-up and descriptor prefetch overlap its tail
   L.s = kernel_id == PL_KERNEL_IMQ ? 1.0 / (ell * ell) : -0.5 / (ell * ell);
   L.beta = beta;  // RBF: beta ; IMQ: c2
   L.ra = (double*)s1;
@@ -1237,6 +1273,7 @@ int ctx_create(int idx, int device) {
 #define GRAM_ATTR(EPI_)                                                                                                                  \
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));                 \
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));                 \
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));                 \
   CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES_TMAST));
   GRAM_ATTR(EPI_LINEAR)
   GRAM_ATTR(EPI_DOT)

@@ -96,6 +96,7 @@ template <int MODE>
 __global__ void prep_rows_kernel(const double* __restrict__ X, int64_t n, int64_t d, int64_t ldx, const double* __restrict__ mean,
                                  const double* __restrict__ cdiag, double* __restrict__ Xc, double* __restrict__ Y, int64_t ldc,
                                  double* __restrict__ stat) {
+  pdl_launch_dependents();  // the Gram kernel that follows may start its prologue (and, for DotProduct, its main loop) now
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
