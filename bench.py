@@ -206,7 +206,10 @@ def other_configs(dev, peak_tflops, rank, world, sync):
     from plb200 import _lib
 
     lib = _lib.lib()
-    res = {}
+    res = {"comm": _lib.comm_info() if world > 1 else None}
+    if world > 1:
+        res["comm"]["exchange"] = ("peer memory: reduce-scatter + all-gather over NVLink loads/stores in one libplb200 kernel behind the SYRK's reduce kernel"
+                                   if res["comm"]["peer_exchange"] else "ncclAllReduce issued by libplb200")
     stream = lambda: torch.cuda.current_stream(dev).cuda_stream
 
     def timed(fn, warm=2, reps=4):
@@ -258,9 +261,9 @@ def other_configs(dev, peak_tflops, rank, world, sync):
         ms, main_ms, coll_ms = timed(neq)
         tf = R * K * (K + 1.0) / (ms * 1e-3) / 1e12
         res["normal_equations_c3"] = {
-            "workload": f"learn! energy+force normal equations R={R} K={K}, ws=[100,1], intercept, lambda=0.01 (BASELINE configs[2]); rows sharded over {world} GPU(s), one ncclAllReduce of K^2+2K+2 doubles inside libplb200",
+            "workload": f"learn! energy+force normal equations R={R} K={K}, ws=[100,1], intercept, lambda=0.01 (BASELINE configs[2]); rows sharded over {world} GPU(s), ONE exchange of K^2+2K+2 doubles inside libplb200 (see comm.exchange)",
             "ms": ms, "rows_per_s": R / (ms * 1e-3), "tflops_RK(K+1)": tf, "frac_of_measured_dgemm_per_gpu": tf / world / peak_tflops,
-            "syrk_kernel_ms_max_rank": main_ms, "allreduce_ms_max_rank": coll_ms, "rows_per_rank": R_l}
+            "syrk_kernel_ms_max_rank": main_ms, "exchange_ms_max_rank": coll_ms, "rows_per_rank": R_l}
         del A, b, M, v
 
         # ---- configs[3]: PCAState covariance, 10^7 rows x 1000 features ----
@@ -287,9 +290,9 @@ def other_configs(dev, peak_tflops, rank, world, sync):
         ms, main_ms, coll_ms = timed(cov, warm=1, reps=3)
         tf = n_total * K * (K + 1.0) / (ms * 1e-3) / 1e12
         res["pca_covariance_c4"] = {
-            "workload": f"PCAState fit! centred covariance, n={n_total} rows x K={K} (BASELINE configs[3]" + ("" if full else f"; REDUCED from 10^7 rows: {room:.0f} GB free per GPU") + f"); rows sharded over {world} GPU(s), one pass, all-reduces of K and K^2 doubles inside libplb200",
+            "workload": f"PCAState fit! centred covariance, n={n_total} rows x K={K} (BASELINE configs[3]" + ("" if full else f"; REDUCED from 10^7 rows: {room:.0f} GB free per GPU") + f"); rows sharded over {world} GPU(s), one pass, exchanges of K and K^2 doubles inside libplb200",
             "ms": ms, "rows_per_s": n_total / (ms * 1e-3), "tflops_nK(K+1)": tf, "frac_of_measured_dgemm_per_gpu": tf / world / peak_tflops,
-            "syrk_kernel_ms_max_rank": main_ms, "last_allreduce_ms_max_rank": coll_ms, "rows_per_rank": n_l, "full_size": bool(full)}
+            "syrk_kernel_ms_max_rank": main_ms, "last_exchange_ms_max_rank": coll_ms, "rows_per_rank": n_l, "full_size": bool(full)}
         del X, C, m, shift
 
         # ---- configs[4]: DotProduct Gram for hierarchical kDPP, N = 200 000 x 500, tile-packed shards ----

@@ -82,6 +82,11 @@ void pl_finalize(void);
 int pl_comm_unique_id(void* out128);
 int pl_comm_init_rank(int nranks, int rank, const void* id128);
 int pl_comm_info(int* nranks, int* rank, int* nccl_version);
+/* 1 when the K x K exchange of the sharded entry points runs over PEER MEMORY (every rank maps every other rank's exchange window:
+ * cudaIpc between processes, peer access inside one process): the SYRK's second-stage kernel writes into the window, one kernel does
+ * reduce-scatter + all-gather with NVLink loads / stores between two flag barriers, every rank ends with identical bits. 0: NCCL
+ * (no peer access, bucket above the 32 MB window, or PLB200_PEER_ALLREDUCE=0). */
+int pl_comm_peer_enabled(void);
 int pl_comm_destroy(void);
 /* milliseconds of the last all-reduce enqueued by the library on this process's first device (CUDA events around it) */
 int pl_last_coll_ms(double* ms);

@@ -32,6 +32,7 @@ struct Nccl {
   int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -59,6 +60,7 @@ int nccl_ready() {
   NC_SYM(CommInitAll, "ncclCommInitAll");
   NC_SYM(CommDestroy, "ncclCommDestroy");
   NC_SYM(AllReduce, "ncclAllReduce");
+  NC_SYM(AllGather, "ncclAllGather");
   NC_SYM(GroupStart, "ncclGroupStart");
   NC_SYM(GroupEnd, "ncclGroupEnd");
   NC_SYM(GetErrorString, "ncclGetErrorString");
@@ -78,8 +80,102 @@ int nccl_ready() {
 int g_nranks = 1, g_rank = 0;
 cudaEvent_t g_coll_ev[PL_MAX_DEV][2] = {};
 
-// sum-all-reduce `count` doubles in place on the current context's communicator, enqueued on `st`; a no-op without a communicator
-int comm_allreduce(double* buf, size_t count, cudaStream_t st) {
+// ---- the exchange step over PEER MEMORY (NVLink / NVSwitch loads and stores), fused behind the SYRK's own reduce kernel ---------------------
+// Every rank owns a WINDOW [flags | bucket | result] that all other ranks map (cudaDeviceEnablePeerAccess inside one process,
+// cudaIpc handles between processes). The second-stage kernel of the SYRK (syrk_reduce_kernel) writes its K x K sums straight into the
+// bucket; then ONE kernel per rank does reduce-scatter + all-gather: after a flag barrier it loads its 1/n slice of every rank's bucket,
+// adds them in rank order 0..n-1 and stores the sums into every rank's result buffer; a second flag barrier (peer_wait_kernel) releases
+// the finish kernel, which reads the local result. 2 (n-1)/n x 8 K^2 bytes cross NVLink per rank (3.5 MB at K = 500, n = 8) instead of
+// a ring's latency chain, and every element is summed by exactly one rank in a fixed order: all ranks hold IDENTICAL bits and the result
+// is exactly symmetric. NCCL stays the fallback (no peer access, buckets above the window, PLB200_PEER_ALLREDUCE=0) and the transport
+// of the large block fetches.
+constexpr size_t PEER_CAP = (size_t)4 << 20;   // doubles per bucket / result region (32 MB: K up to ~2000)
+constexpr size_t PEER_FLAG_BYTES = 4096;
+struct PeerArgs {
+  char* win[PL_MAX_DEV];  // window base of every rank as mapped in THIS process / device
+  int n, me;
+  unsigned long long epoch;
+};
+struct PeerWin {
+  bool on = false, ipc = false;
+  PeerArgs a = {};
+};
+PeerWin g_peer[PL_MAX_DEV];  // per context
+
+__device__ __forceinline__ unsigned long long* peer_flag(char* win, int which, int rank) {
+  return reinterpret_cast<unsigned long long*>(win) + which * PL_MAX_DEV + rank;
+}
+__device__ __forceinline__ double* peer_bucket(char* win) { return reinterpret_cast<double*>(win + PEER_FLAG_BYTES); }
+__device__ __forceinline__ double* peer_result(char* win) { return reinterpret_cast<double*>(win + PEER_FLAG_BYTES) + PEER_CAP; }
+
+// flag barrier `which` of this epoch: block 0 tells every rank "I am here" (release, system scope), every block waits until all
+// ranks have said so in OUR window (acquire). A rank that never arrives (a crashed peer) traps after 30 s instead of hanging the GPU.
+__device__ __forceinline__ void peer_barrier(const PeerArgs& a, int which) {
+  if (blockIdx.x == 0 && threadIdx.x < a.n) {
+    __threadfence_system();
+    unsigned long long* f = peer_flag(a.win[threadIdx.x], which, a.me);
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.epoch) : "memory");
+  }
+  if (threadIdx.x < a.n) {
+    const unsigned long long* f = peer_flag(a.win[a.me], which, threadIdx.x);
+    unsigned long long v, t0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= a.epoch) break;
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 30000000000ull) {
+        printf("plb200: rank %d waited 30 s for rank %d at the peer-memory barrier (epoch %llu)\n", a.me, (int)threadIdx.x, a.epoch);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// reduce-scatter + all-gather of doubles [off, off + count) of the buckets (off even): see the block comment above
+__global__ void peer_rsag_kernel(const PeerArgs a, size_t off, size_t count) {
+  peer_barrier(a, 0);  // every rank's bucket is complete
+  const size_t pairs = (count + 1) / 2, per = (pairs + a.n - 1) / a.n;
+  const size_t lo = (size_t)a.me * per, hi = lo + per < pairs ? lo + per : pairs;
+  for (size_t q = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < hi; q += (size_t)gridDim.x * blockDim.x) {
+    double2 sum;
+    {
+      const double2* src = reinterpret_cast<const double2*>(peer_bucket(a.win[0]) + off) + q;
+      asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%2];" : "=d"(sum.x), "=d"(sum.y) : "l"(src) : "memory");
+    }
+    for (int r = 1; r < a.n; ++r) {
+      const double2* src = reinterpret_cast<const double2*>(peer_bucket(a.win[r]) + off) + q;
+      double2 v;
+      asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(src) : "memory");
+      sum.x += v.x;
+      sum.y += v.y;
+    }
+    for (int r = 0; r < a.n; ++r) reinterpret_cast<double2*>(peer_result(a.win[r]) + off)[q] = sum;
+  }
+  __threadfence_system();
+}
+// second barrier: every rank has stored its slices everywhere; what follows in the stream may read the local result
+__global__ void peer_wait_kernel(const PeerArgs a) { peer_barrier(a, 1); }
+
+// the bucket an operation should accumulate into: the peer window's when the exchange will run over peer memory, else workspace `slot`
+int bucket_get(size_t count, int slot, double** out) {
+  PeerWin& w = g_peer[g.index];
+  if (w.on && count <= PEER_CAP) {
+    *out = reinterpret_cast<double*>(w.a.win[w.a.me] + PEER_FLAG_BYTES);
+    return PL_OK;
+  }
+  void* p;
+  PL_TRY(ws_get(slot, count * 8, &p));
+  *out = (double*)p;
+  return PL_OK;
+}
+
+// Sum-all-reduce of `count` doubles over the ranks, enqueued on `st`. buf inside the peer window's bucket region: the peer-memory exchange,
+// *out = the window's result region (same offset). Otherwise NCCL in place, *out = buf. Without a communicator: nothing, *out = buf.
+int comm_allreduce(double* buf, size_t count, cudaStream_t st, double** out = nullptr) {
+  if (out) *out = buf;
   if (!g.comm || count == 0) return PL_OK;
   cudaEvent_t* ev = g_coll_ev[g.index];
   if (!ev[0]) {
@@ -87,9 +183,156 @@ int comm_allreduce(double* buf, size_t count, cudaStream_t st) {
     CUDA_TRY(cudaEventCreate(&ev[1]));
   }
   CUDA_TRY(cudaEventRecord(ev[0], st));
-  NCCL_TRY(nc.AllReduce(buf, buf, count, NCCL_DOUBLE, NCCL_SUM, (ncclComm_t)g.comm, st));
+  PeerWin& w = g_peer[g.index];
+  double* mine = w.on ? reinterpret_cast<double*>(w.a.win[w.a.me] + PEER_FLAG_BYTES) : nullptr;
+  if (w.on && buf >= mine && buf + count <= mine + PEER_CAP && (((size_t)(buf - mine)) & 1) == 0) {
+    const size_t off = (size_t)(buf - mine);
+    ++w.a.epoch;
+    const size_t per = ((count + 1) / 2 + w.a.n - 1) / w.a.n;
+    int grid = (int)((per + 255) / 256);
+    if (grid > 2 * g.num_sms) grid = 2 * g.num_sms;
+    if (grid < 1) grid = 1;
+    peer_rsag_kernel<<<grid, 256, 0, st>>>(w.a, off, count);
+    LAUNCH_CHECK();
+    peer_wait_kernel<<<1, 32, 0, st>>>(w.a);
+    LAUNCH_CHECK();
+    if (out) *out = mine + PEER_CAP + off;
+    else  // in-place contract of the generic entry: bring the sums back
+      CUDA_TRY(cudaMemcpyAsync(buf, mine + PEER_CAP + off, count * 8, cudaMemcpyDeviceToDevice, st));
+  } else {
+    NCCL_TRY(nc.AllReduce(buf, buf, count, NCCL_DOUBLE, NCCL_SUM, (ncclComm_t)g.comm, st));
+  }
   CUDA_TRY(cudaEventRecord(ev[1], st));
   return PL_OK;
+}
+
+bool peer_wanted() {
+  const char* e = getenv("PLB200_PEER_ALLREDUCE");
+  return !(e && e[0] == '0');
+}
+
+// single process: windows on every device, every pair peer-enabled. Any failure leaves NCCL as the exchange (not an error).
+void peer_setup_single(int ndev) {
+  if (!peer_wanted() || ndev < 2) return;
+  for (int i = 0; i < ndev; ++i)
+    for (int j = 0; j < ndev; ++j) {
+      if (i == j) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, g_ctx[i].device, g_ctx[j].device) != cudaSuccess || !can) {
+        cudaGetLastError();
+        return;
+      }
+    }
+  char* win[PL_MAX_DEV] = {};
+  bool ok = true;
+  for (int i = 0; i < ndev && ok; ++i) {
+    ok = cudaSetDevice(g_ctx[i].device) == cudaSuccess;
+    for (int j = 0; j < ndev && ok; ++j) {
+      if (i == j) continue;
+      const cudaError_t e = cudaDeviceEnablePeerAccess(g_ctx[j].device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+      cudaGetLastError();
+    }
+    const size_t bytes = PEER_FLAG_BYTES + 2 * PEER_CAP * 8;
+    if (ok) ok = cudaMalloc((void**)&win[i], bytes) == cudaSuccess && cudaMemset(win[i], 0, bytes) == cudaSuccess;
+  }
+  if (ok)
+    for (int i = 0; i < ndev; ++i) ok = ok && cudaSetDevice(g_ctx[i].device) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    for (int i = 0; i < ndev; ++i)
+      if (win[i]) {
+        cudaSetDevice(g_ctx[i].device);
+        cudaFree(win[i]);
+      }
+    return;
+  }
+  for (int i = 0; i < ndev; ++i) {
+    PeerWin& w = g_peer[i];
+    w = PeerWin();
+    for (int j = 0; j < ndev; ++j) w.a.win[j] = win[j];
+    w.a.n = ndev;
+    w.a.me = i;
+    w.on = true;
+  }
+}
+
+// one process per GPU: the windows are exchanged as CUDA IPC handles through the communicator itself (collective: every rank calls it).
+// All ranks agree on the outcome: the peer exchange is used only if EVERY rank mapped every window.
+int peer_setup_ranks(int nranks, int rank, cudaStream_t st) {
+  PeerWin& w = g_peer[0];
+  w = PeerWin();
+  if (nranks < 2 || nranks > PL_MAX_DEV) return PL_OK;
+  const bool want = peer_wanted();
+  const size_t bytes = PEER_FLAG_BYTES + 2 * PEER_CAP * 8;
+  char* mine = nullptr;
+  cudaIpcMemHandle_t hd;
+  memset(&hd, 0, sizeof(hd));
+  double okflag = 0.0;
+  if (want && cudaMalloc((void**)&mine, bytes) == cudaSuccess && cudaMemset(mine, 0, bytes) == cudaSuccess && cudaIpcGetMemHandle(&hd, mine) == cudaSuccess)
+    okflag = 1.0;
+  cudaGetLastError();
+  // gather the handles and count the ranks that got this far
+  void* dbuf;
+  PL_TRY(ws_get(WS_PADC, (size_t)(nranks + 1) * sizeof(hd) + 64, &dbuf));
+  char* dh = (char*)dbuf;
+  double* dok = (double*)(dh + (((size_t)(nranks + 1) * sizeof(hd) + 15) & ~(size_t)15));
+  CUDA_TRY(cudaMemcpyAsync(dh + (size_t)nranks * sizeof(hd), &hd, sizeof(hd), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dok, &okflag, 8, cudaMemcpyHostToDevice, st));
+  NCCL_TRY(nc.AllGather(dh + (size_t)nranks * sizeof(hd), dh, sizeof(hd), 0 /* ncclChar */, (ncclComm_t)g.comm, st));
+  NCCL_TRY(nc.AllReduce(dok, dok, 1, NCCL_DOUBLE, NCCL_SUM, (ncclComm_t)g.comm, st));
+  std::vector<cudaIpcMemHandle_t> all(nranks);
+  double nok = 0.0;
+  CUDA_TRY(cudaMemcpyAsync(all.data(), dh, (size_t)nranks * sizeof(hd), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&nok, dok, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  double mapped = 0.0;
+  if (nok == (double)nranks) {
+    mapped = 1.0;
+    w.a.win[rank] = mine;
+    for (int r = 0; r < nranks; ++r) {
+      if (r == rank) continue;
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        mapped = 0.0;
+        break;
+      }
+      w.a.win[r] = (char*)p;
+    }
+  }
+  CUDA_TRY(cudaMemcpyAsync(dok, &mapped, 8, cudaMemcpyHostToDevice, st));
+  NCCL_TRY(nc.AllReduce(dok, dok, 1, NCCL_DOUBLE, NCCL_SUM, (ncclComm_t)g.comm, st));
+  CUDA_TRY(cudaMemcpyAsync(&nok, dok, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (nok == (double)nranks) {
+    w.a.n = nranks;
+    w.a.me = rank;
+    w.ipc = true;
+    w.on = true;
+  } else {
+    for (int r = 0; r < nranks; ++r)
+      if (r != rank && w.a.win[r]) cudaIpcCloseMemHandle(w.a.win[r]);
+    if (mine) cudaFree(mine);
+    cudaGetLastError();
+    w = PeerWin();
+  }
+  return PL_OK;
+}
+
+void peer_teardown() {
+  for (int i = 0; i < PL_MAX_DEV; ++i) {
+    PeerWin& w = g_peer[i];
+    if (!w.on) continue;
+    if (g_ctx[i].ready) cudaSetDevice(g_ctx[i].device);
+    if (w.ipc) {
+      for (int r = 0; r < w.a.n; ++r)
+        if (r != w.a.me && w.a.win[r]) cudaIpcCloseMemHandle(w.a.win[r]);
+    }
+    if (w.a.win[w.a.me]) cudaFree(w.a.win[w.a.me]);
+    cudaGetLastError();
+    w = PeerWin();
+  }
 }
 
 // out = a * x + b * y (K-length glue of the sharded covariance: column sums n_r z + rho, delta = m - z)
@@ -132,6 +375,12 @@ int for_each_device(F&& fn) {
 }
 
 void multi_shutdown() {
+  for (int i = 0; i < PL_MAX_DEV; ++i)
+    if (g_ctx[i].ready) {
+      cudaSetDevice(g_ctx[i].device);
+      cudaDeviceSynchronize();
+    }
+  peer_teardown();
   for (int i = 0; i < PL_MAX_DEV; ++i) {
     if (g_ctx[i].comm && nc.CommDestroy) {
       cudaSetDevice(g_ctx[i].device);
@@ -205,8 +454,9 @@ int normal_eq_multi(const double* const* blocks, const int64_t* rows, const int6
     double* bucket = nullptr;
     PL_TRY(normal_eq_stream_partial(sb.data(), srows.data(), slds.data(), (int64_t)sb.size() - 1, R_i, Kf, w ? wv.data() : nullptr, ne_i, w_e, w_f,
                                     b ? bv.data() : nullptr, want_vec, chunk_rows, &bucket));
-    PL_TRY(comm_allreduce(bucket, (size_t)(Kf * Kf + (want_vec ? 2 * Kf + 2 : 0)), g.stream));
-    if (i == 0) return normal_eq_bucket_finish(bucket, Kf, want_vec, ic, lambda, AtWA, AtWb);
+    double* sums = nullptr;
+    PL_TRY(comm_allreduce(bucket, (size_t)(Kf * Kf + (want_vec ? 2 * Kf + 2 : 0)), g.stream, &sums));
+    if (i == 0) return normal_eq_bucket_finish(sums, Kf, want_vec, ic, lambda, AtWA, AtWb);
     CUDA_TRY(cudaStreamSynchronize(g.stream));
     return PL_OK;
   });
@@ -217,16 +467,19 @@ int normal_eq_multi(const double* const* blocks, const int64_t* rows, const int6
 // global mean). dC receives (1/n_total) sum over ALL shards, exactly symmetric. Everything is enqueued on st.
 int cov_shard_dev(const double* dX, int64_t n_local, int64_t n_total, int64_t Kf, int64_t ld, double* dmean, int mean_given, int center, double* dC,
                   cudaStream_t st) {
-  void* dS;
-  PL_TRY(ws_get(WS_H_S, (size_t)Kf * Kf * 8, &dS));
+  // S (K x K) and, behind it, the K column sums share one bucket: both exchanges can run over the peer window
+  const size_t soff = ((size_t)(Kf * Kf) + 1) & ~(size_t)1;
+  double* dS;
+  PL_TRY(bucket_get(soff + (size_t)Kf, WS_H_S, &dS));
+  double* sums = dS;
   if (center && !mean_given) {
     // one pass over the rows: shift z = mean of a prefix of THIS shard, S_z and rho from the SYRK; the column sums n_r z + rho are
     // all-reduced for the global mean (pca.m = sum(d)/length(d), pca_state.jl:35), every shard re-centres about it, one all-reduce adds
-    void *z, *rho, *delta, *csum;
+    void *z, *rho, *delta;
     PL_TRY(ws_get(WS_COV_Z, (size_t)Kf * 8, &z));
     PL_TRY(ws_get(WS_COV_RHO, (size_t)Kf * 8, &rho));
-    PL_TRY(ws_get(WS_COV_DELTA, (size_t)2 * Kf * 8, &delta));
-    csum = (double*)delta + Kf;
+    PL_TRY(ws_get(WS_COV_DELTA, (size_t)Kf * 8, &delta));
+    double* csum = dS + soff;
     const unsigned kb = (unsigned)((Kf + 255) / 256);
     if (n_local > 0) {
       const int64_t prefix = n_local < 65536 ? n_local : 65536;
@@ -239,8 +492,9 @@ int cov_shard_dev(const double* dX, int64_t n_local, int64_t n_total, int64_t Kf
     }
     axpby_kernel<<<kb, 256, 0, st>>>((double)n_local, (const double*)z, 1.0, (const double*)rho, Kf, (double*)csum);
     LAUNCH_CHECK();
-    PL_TRY(comm_allreduce((double*)csum, (size_t)Kf, st));
-    scale_div_kernel<<<kb, 256, 0, st>>>((const double*)csum, (double)n_total, Kf, dmean);
+    double* csum_all = nullptr;
+    PL_TRY(comm_allreduce(csum, (size_t)Kf, st, &csum_all));
+    scale_div_kernel<<<kb, 256, 0, st>>>((const double*)csum_all, (double)n_total, Kf, dmean);
     LAUNCH_CHECK();
     axpby_kernel<<<kb, 256, 0, st>>>(1.0, (const double*)dmean, -1.0, (const double*)z, Kf, (double*)delta);
     LAUNCH_CHECK();
@@ -248,11 +502,11 @@ int cov_shard_dev(const double* dX, int64_t n_local, int64_t n_total, int64_t Kf
   } else {
     PL_TRY(syrk_dev_impl(dX, n_local, Kf, ld, nullptr, 0, 1.0, 1.0, nullptr, center ? dmean : nullptr, (double*)dS, nullptr, st));
   }
-  PL_TRY(comm_allreduce((double*)dS, (size_t)(Kf * Kf), st));
+  PL_TRY(comm_allreduce(dS, (size_t)(Kf * Kf), st, &sums));
   int blocks = (int)((Kf * Kf + 255) / 256);
   if (blocks > g.num_sms * 8) blocks = g.num_sms * 8;
   // mean(di*di') = sum / n from the j >= i triangle: exactly symmetric whatever order the all-reduce summed in
-  sym_scale_div_kernel<<<blocks, 256, 0, st>>>((const double*)dS, Kf, (double)n_total, dC);
+  sym_scale_div_kernel<<<blocks, 256, 0, st>>>((const double*)sums, Kf, (double)n_total, dC);
   LAUNCH_CHECK();
   return PL_OK;
 }
@@ -391,6 +645,7 @@ int pl_init_all(int ndev, const int* device_ids) {
       return rc;
     }
     for (int i = 0; i < ndev; ++i) g_ctx[i].comm = comms[i];
+    peer_setup_single(ndev);  // peer windows for the exchange over NVLink; NCCL remains the fallback
     // pinned staging rings up front (see HostStager::start): 16 host threads over all devices
     const int per = 16 / ndev < 2 ? 2 : 16 / ndev;
     for (int i = 0; i < ndev; ++i) {
@@ -430,7 +685,11 @@ int pl_comm_init_rank(int nranks, int rank, const void* id128) {
   g.comm = c;
   g_nranks = nranks;
   g_rank = rank;
-  return PL_OK;
+  return peer_setup_ranks(nranks, rank, g.stream);  // collective: IPC-mapped peer windows (falls back to NCCL on every rank alike)
+}
+
+int pl_comm_peer_enabled(void) {
+  return g_peer[0].on ? 1 : 0;
 }
 
 int pl_comm_info(int* nranks, int* rank, int* nccl_version) {
@@ -445,7 +704,8 @@ int pl_comm_destroy(void) {
   if (g_ndev > 1) return set_err(PL_EINVAL, "the communicators of pl_init_all live until pl_finalize");
   if (g_ctx[0].comm) {
     CUDA_TRY(cudaSetDevice(g_ctx[0].device));
-    CUDA_TRY(cudaStreamSynchronize(g_ctx[0].stream));
+    CUDA_TRY(cudaDeviceSynchronize());
+    peer_teardown();
     nc.CommDestroy((ncclComm_t)g_ctx[0].comm);
     g_ctx[0].comm = nullptr;
   }
@@ -482,13 +742,14 @@ int pl_normal_eq_sharded_dev(const double* dA, int64_t R_local, int64_t Kf, int6
   const int ic = add_intercept ? 1 : 0;
   const bool want_vec = ic || db;
   cudaStream_t st = (cudaStream_t)stream;
-  void* bucket;
-  PL_TRY(ws_get(WS_NE_SACC, (size_t)(Kf * Kf + 2 * Kf + 2) * 8, &bucket));
-  double* dS = (double*)bucket;
+  // the SYRK's second-stage kernel writes its sums straight into the exchange bucket (the peer window when it is mapped)
+  double* dS;
+  PL_TRY(bucket_get((size_t)(Kf * Kf + 2 * Kf + 2), WS_NE_SACC, &dS));
   double* dvec = want_vec ? dS + Kf * Kf : nullptr;
   PL_TRY(syrk_dev_impl(dA, R_local, Kf, lda, dw, n_energy_rows_local, w_e, w_f, db, nullptr, dS, dvec, st));
-  PL_TRY(comm_allreduce(dS, (size_t)(Kf * Kf + (want_vec ? 2 * Kf + 2 : 0)), st));
-  return finish_dev_impl(dS, dvec, Kf, ic, lambda, dAtWA, dAtWb, st);
+  double* sums = nullptr;
+  PL_TRY(comm_allreduce(dS, (size_t)(Kf * Kf + (want_vec ? 2 * Kf + 2 : 0)), st, &sums));
+  return finish_dev_impl(sums, want_vec ? sums + Kf * Kf : nullptr, Kf, ic, lambda, dAtWA, dAtWb, st);
 }
 
 int pl_cov_sharded_dev(const double* dX, int64_t n_local, int64_t n_total, int64_t Kf, int64_t ldx, double* dmean_inout, int mean_given, int center,
@@ -519,8 +780,9 @@ int pl_normal_eq_sharded(const double* A_local, int64_t R_local, int64_t Kf, int
   int64_t ne = n_energy_rows_local < 0 ? 0 : (n_energy_rows_local > R_local ? R_local : n_energy_rows_local);
   double* bucket = nullptr;
   PL_TRY(normal_eq_stream_partial(blk, rows, lds, 1, R_local, Kf, w, ne, w_e, w_f, b, want_vec, chunk_rows, &bucket));
-  PL_TRY(comm_allreduce(bucket, (size_t)(Kf * Kf + (want_vec ? 2 * Kf + 2 : 0)), g.stream));
-  return normal_eq_bucket_finish(bucket, Kf, want_vec, ic, lambda, AtWA, AtWb);
+  double* sums = nullptr;
+  PL_TRY(comm_allreduce(bucket, (size_t)(Kf * Kf + (want_vec ? 2 * Kf + 2 : 0)), g.stream, &sums));
+  return normal_eq_bucket_finish(sums, Kf, want_vec, ic, lambda, AtWA, AtWb);
 }
 
 int pl_cov_sharded(const double* X_local, int64_t n_local, int64_t n_total, int64_t Kf, int64_t ldx, double* mean_inout, int mean_given, int center,

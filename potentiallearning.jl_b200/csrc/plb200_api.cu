@@ -209,6 +209,9 @@ int ws_get(int slot, size_t bytes, void** out) {
   return PL_OK;
 }
 
+// (multi.inl) the bucket an operation accumulates into: the peer window's when the exchange runs over peer memory, else workspace `slot`
+int bucket_get(size_t count, int slot, double** out);
+
 int need_ready() {
   if (!g.ready) return set_err(PL_ENODEV, "plb200 is not initialised: call pl_init (needs an sm_100 GPU; there is no CPU fallback)");
   // every entry point (host and _dev) works on the device of the calling thread's context, whatever device the caller had current
@@ -342,19 +345,28 @@ cudaError_t launch_ex(void (*kernel)(KArgs...), int grid, int block, size_t smem
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Tile shape of a dense (not tile-packed, not column-range) Gram launch: 64 x 64 tiles when the 128 x 128 tiles of the result would
+// leave SMs idle or give too few waves to hide the tail (4 x as many CTAs): N = 1000 (config 1, the kDPP example shape) has 36
+// upper-triangle tiles of 128 for 148 SMs, 136 of 64. Measured (profiles/r02_small_gram_probe.json, CUDA-graph replay; r02_skinny_tile_probe.json):
+// N = 1000, d = 26 DotProduct 15.1 -> 6.0 us, RBF 30.2 -> 13.9 us; N = 4000, d = 26 38 -> 33 us / 72 -> 52 us; N = 8000 RBF 0.187 -> 0.161 ms
+// but DotProduct 0.103 -> 0.111 ms (the TMA-store epilogue of the 128 tile wins once the machine is full); N >= 20 000: 128 x 128 always.
+// Hence: 64 x 64 below 4 waves of 128-tiles, below 16 waves for the exp epilogue.
+// The host paths that copy a triangle back as a staircase of row blocks use the same edge (the unused half of a DIAGONAL tile is
+// written as zeros by the kernel, off-diagonal tiles of the other triangle are not touched).
+bool gram_small_tiles(int64_t nA, int64_t nB, bool symmetric, int nparts, int kernel_id) {
+  const int T1 = (int)((nA + GRAM_BM - 1) / GRAM_BM), T2 = (int)((nB + GRAM_BN - 1) / GRAM_BN);
+  const int64_t t128 = symmetric ? (int64_t)T1 * (T1 + 1) / 2 : (int64_t)T1 * T2;
+  const int64_t waves = kernel_id == PL_KERNEL_RBF ? 16 : 4;
+  bool small = (t128 + nparts - 1) / nparts < waves * g.num_sms;
+  if (const char* e = getenv("PLB200_GRAM_SMALL")) small = e[0] == '1' ? true : (e[0] == '0' ? false : small);
+  return small;
+}
+
 int launch_gram(const GramLaunch& L, cudaStream_t st) {
   if (L.nA == 0 || L.nB == 0) return PL_OK;
   // rectangular results with few columns (projections, cross kernels against a handful of points): the 128 x 32 tile
   const bool narrow = !L.symmetric && !L.packed && L.nB <= 96;
-  // small matrices: when the 128 x 128 tiles of a dense result would leave SMs idle, 64 x 64 tiles (4 x as many CTAs). N = 1000
-  // (config 1, the kDPP example shape) has 36 upper-triangle tiles of 128 for 148 SMs, 136 of 64.
-  bool small = false;
-  if (!narrow && !L.packed && L.tcol_begin < 0) {
-    const int T1 = (int)((L.nA + GRAM_BM - 1) / GRAM_BM), T2 = (int)((L.nB + GRAM_BN - 1) / GRAM_BN);
-    const int64_t t128 = L.symmetric ? (int64_t)T1 * (T1 + 1) / 2 : (int64_t)T1 * T2;
-    small = (t128 + L.nparts - 1) / L.nparts < g.num_sms;
-    if (const char* e = getenv("PLB200_GRAM_SMALL")) small = e[0] == '1' ? true : (e[0] == '0' ? false : small);
-  }
+  const bool small = !narrow && !L.packed && L.tcol_begin < 0 && gram_small_tiles(L.nA, L.nB, L.symmetric, L.nparts, L.epi == EPI_RBF ? PL_KERNEL_RBF : PL_KERNEL_DOT);
   const int BM = small ? 64 : GRAM_BM;
   const int BN = narrow ? 32 : (small ? 64 : GRAM_BN);
   CUtensorMap tmA, tmB;
@@ -944,7 +956,11 @@ int normal_eq_stream_partial(const double* const* blocks, const int64_t* rows, c
   PL_TRY(ws_get(WS_NE_BUF0, (size_t)chunk_rows * ldp * 8, &buf[0]));
   PL_TRY(ws_get(WS_NE_BUF1, (size_t)(R > chunk_rows ? chunk_rows : 1) * ldp * 8, &buf[1]));
   PL_TRY(ws_get(WS_H_S, (size_t)Kf * Kf * 8, &dS));
-  PL_TRY(ws_get(WS_NE_SACC, (size_t)(Kf * Kf + 2 * Kf + 2) * 8, &dSacc));
+  {
+    double* bk;
+    PL_TRY(bucket_get((size_t)(Kf * Kf + 2 * Kf + 2), WS_NE_SACC, &bk));
+    dSacc = bk;
+  }
   dVacc = (double*)dSacc + Kf * Kf;
   if (want_vec) PL_TRY(ws_get(WS_H_VEC, (size_t)(2 * Kf + 2) * 8, &dvec));
   CUDA_TRY(cudaEventRecord(g.ev[0], g.stream));
@@ -1629,10 +1645,11 @@ static int gram_host(int kernel_id, const double* X1, int64_t n1, int64_t ldx1, 
     else
       CUDA_TRY(cudaMemcpy2DAsync(K, (size_t)ldk * 8, dK, (size_t)ldo * 8, (size_t)n2 * 8, (size_t)n1, cudaMemcpyDeviceToHost, g.stream));
   } else {
-    // one triangle only: copy the staircase of 128-row blocks (half the PCIe traffic). Inside diagonal tiles the
+    // one triangle only: copy the staircase of tile-row blocks (half the PCIe traffic). Inside diagonal tiles the
     // unused half was written as zeros by the kernel, matching the reference's zeros(n,n) storage.
-    for (int64_t r0 = 0; r0 < n1; r0 += GRAM_BM) {
-      const int64_t r1 = r0 + GRAM_BM < n1 ? r0 + GRAM_BM : n1;
+    const int64_t edge = gram_small_tiles(n1, n2, true, 1, kernel_id) ? 64 : GRAM_BM;
+    for (int64_t r0 = 0; r0 < n1; r0 += edge) {
+      const int64_t r1 = r0 + edge < n1 ? r0 + edge : n1;
       if (fill == PL_FILL_RM_LOWER) {
         CUDA_TRY(cudaMemcpy2DAsync(K + r0 * ldk, (size_t)ldk * 8, dK + r0 * ldo, (size_t)ldo * 8, (size_t)r1 * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, g.stream));
       } else {
@@ -1917,8 +1934,9 @@ int pl_ell_ensemble(int kernel_id, const double* X, int64_t n, int64_t d, int64_
     ell_state.has_kernel = true;
   }
   if (Kout) {  // the caller also wants K itself (kDPP keeps it as ell.L): triangle rows, before the solver overwrites the buffer
-    for (int64_t r0 = 0; r0 < n; r0 += GRAM_BM) {
-      const int64_t r1 = r0 + GRAM_BM < n ? r0 + GRAM_BM : n;
+    const int64_t edge = gram_small_tiles(n, n, true, 1, kernel_id) ? 64 : GRAM_BM;
+    for (int64_t r0 = 0; r0 < n; r0 += edge) {
+      const int64_t r1 = r0 + edge < n ? r0 + edge : n;
       CUDA_TRY(cudaMemcpy2DAsync(Kout + r0 * ldk, (size_t)ldk * 8, (double*)dA + r0 * ldo, (size_t)ldo * 8, (size_t)r1 * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, g.stream));
     }
   }

@@ -32,6 +32,7 @@ PROTOTYPES = {
     "pl_comm_init_rank": (_int, [_int, _int, _vp]),
     "pl_comm_info": (_int, [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "pl_comm_destroy": (_int, []),
+    "pl_comm_peer_enabled": (_int, []),
     "pl_last_coll_ms": (_int, [_dp]),
     "pl_normal_eq_sharded": (_int, [_dp, _i64, _i64, _i64, _dp, _i64, _dbl, _dbl, _dp, _int, _dbl, _dp, _dp]),
     "pl_normal_eq_sharded_dev": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _dbl, _dbl, _vp, _int, _dbl, _vp, _vp, _vp]),
@@ -189,7 +190,7 @@ def comm_init_from_torch(group=None):
 def comm_info():
     n, r, v = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
     load().pl_comm_info(ctypes.byref(n), ctypes.byref(r), ctypes.byref(v))
-    return {"nranks": n.value, "rank": r.value, "nccl_version": v.value}
+    return {"nranks": n.value, "rank": r.value, "nccl_version": v.value, "peer_exchange": bool(load().pl_comm_peer_enabled())}
 
 
 def comm_destroy():

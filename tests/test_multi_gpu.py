@@ -21,9 +21,10 @@ def ngpus():
     return torch.cuda.device_count()
 
 
-def run(cmd, timeout=900):
+def run(cmd, timeout=900, extra_env=None):
     env = dict(os.environ)
     env.setdefault("MASTER_ADDR", "127.0.0.1")
+    env.update(extra_env or {})
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
     assert p.returncode == 0, f"{' '.join(cmd)}\nSTDOUT:\n{p.stdout[-3000:]}\nSTDERR:\n{p.stderr[-3000:]}"
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
@@ -36,16 +37,23 @@ def test_init_all_with_one_device_is_the_plain_path():
     assert out["ok"] and out["devices"] == 1
 
 
+# peer = "1": the K x K exchange over peer memory (NVLink loads / stores fused behind the SYRK's reduce kernel); "0": NCCL all-reduce
 @pytest.mark.skipif("ngpus() < 2")
-def test_single_process_drives_all_gpus():
+@pytest.mark.parametrize("peer", ["1", "0"])
+def test_single_process_drives_all_gpus(peer):
     n = min(ngpus(), 8)
-    out = run([sys.executable, SCRIPT, "single", str(n)])
+    out = run([sys.executable, SCRIPT, "single", str(n)], extra_env={"PLB200_PEER_ALLREDUCE": peer})
     assert out["ok"] and out["devices"] == n and out["nccl"]["nranks"] == n
+    if peer == "0":
+        assert not out["nccl"]["peer_exchange"]
 
 
 @pytest.mark.skipif("ngpus() < 2")
-def test_one_process_per_gpu_sharded_entry_points():
+@pytest.mark.parametrize("peer", ["1", "0"])
+def test_one_process_per_gpu_sharded_entry_points(peer):
     n = min(ngpus(), 8)
-    out = run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", "29613",
-               SCRIPT, "ranks"])
+    out = run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port",
+               "29613" if peer == "1" else "29614", SCRIPT, "ranks"], extra_env={"PLB200_PEER_ALLREDUCE": peer})
     assert out["ok"] and out["world"] == n
+    if peer == "0":
+        assert not out["nccl"]["peer_exchange"]
