@@ -502,8 +502,12 @@ def main():
         barrier()
         n_e2e = max(3, min(K, 10))
         t0 = time.perf_counter()
+        per_call = []
         for _ in range(n_e2e):
+            tc = time.perf_counter()
             e2e_step()  # synchronous: returns after the D2H has completed
+            per_call.append((time.perf_counter() - tc) * 1e3)
+        t_loop = time.perf_counter() - t0
         barrier()
         t_e2e = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
         if world > 1:
@@ -511,10 +515,11 @@ def main():
         tm = _lib.last_timing()
         e2e = {"value": flops / float(t_e2e.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": N_CFG * D_CFG * 8, "d2h_bytes_per_step": int(d2h),
                "ms_per_step": float(t_e2e.item()) * 1e3, "steps": n_e2e, "last_call_ms": tm, "host_buffers": "pinned",
+               "rank0_wall_ms_per_call": [round(x, 3) for x in per_call], "rank0_loop_ms_per_call": t_loop / n_e2e * 1e3,
                "api": "pl_gram_part (tile-packed shard)" if packed else "pl_gram_rbf fill=PL_FILL_JULIA_U (Symmetric uplo=:U storage)"}
         if world > 1:
             # where the slowest rank's time goes: kernel / H2D / D2H of every rank's last call (GPUs behind one PCIe switch share its uplink)
-            mine = torch.tensor([tm["kernel_ms"], tm["h2d_ms"], tm["d2h_ms"]], device=dev, dtype=torch.float64)
+            mine = torch.tensor([tm["kernel_ms"], tm["h2d_ms"], tm["d2h_ms"], tm["host_wall_ms"]], device=dev, dtype=torch.float64)
             allr = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(allr, mine)
             e2e["last_call_ms_per_rank"] = [[round(float(x), 3) for x in t] for t in allr]

@@ -93,6 +93,8 @@ int pl_last_coll_ms(double* ms);
 const char* pl_last_error(void);
 /* milliseconds spent by the last host entry point: kernels (CUDA events), H2D and D2H copies. */
 int pl_last_timing(double* kernel_ms, double* h2d_ms, double* d2h_ms);
+/* wall-clock milliseconds the last host entry point spent inside the library, entry to return (>= the three above: the rest is host work) */
+int pl_last_host_ms(double* ms);
 /* number of plb200 CUDA kernels launched by this process so far (benchmarks report it as gpu_launches). */
 int64_t pl_launch_count(void);
 /* bytes of device workspace currently held by the library. */

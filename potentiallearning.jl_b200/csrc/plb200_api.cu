@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -164,9 +165,11 @@ struct Ctx {
   PFN_cuTensorMapEncodeTiled encode = nullptr;
   void* ws[WS_NSLOTS] = {};
   size_t ws_bytes[WS_NSLOTS] = {};
-  double t_kernel = 0, t_h2d = 0, t_d2h = 0, t_coll = 0;
+  double t_kernel = 0, t_h2d = 0, t_d2h = 0, t_coll = 0, t_host = 0;
+  std::chrono::steady_clock::time_point t_entry;  // when the current host entry point started (need_ready)
   bool profiling = false;
   bool main_timed = false;
+  uint64_t ws_gen = 0;  // bumped whenever a workspace slot is (re)allocated or freed: cached CUDA graphs hold workspace pointers
   HostStager stager;  // pinned staging ring + host threads for pageable host memory (hoststage.h)
   SyrkSchedCache sched;
   void* comm = nullptr;  // ncclComm_t of this device (pl_init_all: one per context; pl_comm_init_rank: context 0)
@@ -204,6 +207,7 @@ int ws_get(int slot, size_t bytes, void** out) {
       return set_err(PL_ENOMEM, "device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
     }
     g.ws_bytes[slot] = want;
+    ++g.ws_gen;
   }
   *out = g.ws[slot];
   return PL_OK;
@@ -217,6 +221,7 @@ int need_ready() {
   // every entry point (host and _dev) works on the device of the calling thread's context, whatever device the caller had current
   int cur = -1;
   if (cudaGetDevice(&cur) != cudaSuccess || cur != g.device) CUDA_TRY(cudaSetDevice(g.device));
+  g.t_entry = std::chrono::steady_clock::now();
   return PL_OK;
 }
 
@@ -914,6 +919,7 @@ int finish_timing() {
   g.t_h2d = a;
   g.t_kernel = b;
   g.t_d2h = c;
+  g.t_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g.t_entry).count();
   return PL_OK;
 }
 
@@ -1206,6 +1212,7 @@ namespace {
 
 // defined in multi.inl (included at the end of this file): single-process multi-GPU forms of the host entry points
 void multi_shutdown();
+void gram_graphs_clear(int ctx_index);  // cached CUDA graphs of pl_gram_dev (defined next to it)
 int normal_eq_multi(const double* const* blocks, const int64_t* rows, const int64_t* lds, int64_t nblocks, int64_t R, int64_t Kf, const double* w,
                     int64_t ne, double w_e, double w_f, const double* b, int ic, double lambda, double* AtWA, double* AtWb, int64_t chunk_rows);
 int cov_multi(const double* X, int64_t n, int64_t Kf, int64_t ldx, double* mean_inout, int mean_given, int center, double* C);
@@ -1321,6 +1328,7 @@ void ctx_destroy(int idx) {
     ev = nullptr;
   }
   c.stager.shutdown();
+  gram_graphs_clear(idx);
   if (c.sched.ready) cudaEventDestroy(c.sched.ready);
   c.sched.ready = nullptr;
   c.sched.dev = nullptr;
@@ -1386,6 +1394,11 @@ int pl_last_timing(double* kernel_ms, double* h2d_ms, double* d2h_ms) {
   return PL_OK;
 }
 
+int pl_last_host_ms(double* ms) {
+  if (ms) *ms = g.t_host;
+  return PL_OK;
+}
+
 int64_t pl_launch_count(void) { return g_launches.load(); }
 
 int pl_set_profiling(int on) {
@@ -1431,6 +1444,7 @@ int pl_workspace_trim(int keep_resident) {
     g.ws[i] = nullptr;
     g.ws_bytes[i] = 0;
   }
+  ++g.ws_gen;
   g.sched.dev = nullptr;
   for (int c = 1; c < g_ndev; ++c) {  // the other devices of a pl_init_all session hold scratch only
     Ctx& x = g_ctx[c];
@@ -1451,12 +1465,125 @@ int pl_workspace_trim(int keep_resident) {
   return PL_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// pl_gram_dev is launch bound on small problems (config 1: four launches and three tensor-map encodes for 6 us of GPU work; a config-2
+// shard on 8 GPUs: 48 us of preludes and launch gaps around a 540 us kernel). The launches of a call are therefore captured into a CUDA
+// graph the SECOND time the identical call is made (same pointers, shapes, parameters, workspace generation) and replayed from then on:
+// one cudaGraphLaunch instead of the launch sequence. The kernels read whatever the buffers hold at replay time, exactly like the
+// plain launches. PLB200_NO_GRAPH=1 disables it; profiling (pl_set_profiling) bypasses it.
+struct GramGraphKey {
+  int kernel_id, alpha, cinv_kind, fill, part, nparts, packed;
+  const void *dX1, *dX2, *dcinv, *dOut;
+  int64_t n1, ldx1, n2, ldx2, d, ldo;
+  double ell, beta;
+  uint64_t ws_gen;
+  unsigned env;
+  bool operator==(const GramGraphKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
+};
+struct GramGraphEntry {
+  GramGraphKey key;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+  uint64_t last_use = 0;
+  bool uncacheable = false;
+};
+constexpr int GRAM_GRAPH_SLOTS = 8;
+GramGraphEntry g_gram_graphs[PL_MAX_DEV][GRAM_GRAPH_SLOTS];
+uint64_t g_gram_graph_clock = 0;
+
+unsigned env_bits() {
+  unsigned h = 0;
+  const char* names[] = {"PLB200_GRAM_SMALL", "PLB200_NO_PDL", "PLB200_GRAM_TMAST", "PLB200_GRAM_NOSTORE"};
+  for (const char* nm : names) {
+    const char* e = getenv(nm);
+    h = h * 31u + (e ? (unsigned)(unsigned char)e[0] + 1u : 0u);
+  }
+  return h;
+}
+
+void gram_graphs_clear(int ctx_index) {
+  for (auto& e : g_gram_graphs[ctx_index]) {
+    if (e.exec) cudaGraphExecDestroy(e.exec);
+    e = GramGraphEntry();
+  }
+}
+}  // namespace
+
+extern "C" {
+
 int pl_gram_dev(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, const double* dX2, int64_t n2, int64_t ldx2, int64_t d, int alpha,
                 int cinv_kind, const double* dcinv, double ell, double beta, double* dOut, int64_t ldo, int fill, int part, int nparts, int packed,
                 void* stream) {
   std::lock_guard<std::mutex> lk(g_mu);
-  return gram_dev_impl(kernel_id, dX1, n1, ldx1, dX2, n2, ldx2, d, alpha, cinv_kind, dcinv, ell, beta, dOut, ldo, fill, part, nparts, packed,
-                       (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool plain = !g.ready || g.profiling || getenv("PLB200_NO_GRAPH") || cudaStreamIsCapturing(st, &cap) != cudaSuccess ||
+                     cap != cudaStreamCaptureStatusNone;  // (a caller that is capturing itself gets the plain launches in ITS graph)
+  if (plain) {
+    cudaGetLastError();
+    return gram_dev_impl(kernel_id, dX1, n1, ldx1, dX2, n2, ldx2, d, alpha, cinv_kind, dcinv, ell, beta, dOut, ldo, fill, part, nparts, packed, st);
+  }
+  GramGraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.kernel_id = kernel_id; key.alpha = alpha; key.cinv_kind = cinv_kind; key.fill = fill; key.part = part; key.nparts = nparts; key.packed = packed;
+  key.dX1 = dX1; key.dX2 = dX2; key.dcinv = dcinv; key.dOut = dOut;
+  key.n1 = n1; key.ldx1 = ldx1; key.n2 = n2; key.ldx2 = ldx2; key.d = d; key.ldo = ldo;
+  key.ell = ell; key.beta = beta;
+  key.ws_gen = g.ws_gen;
+  key.env = env_bits();
+  GramGraphEntry* tab = g_gram_graphs[g.index];
+  GramGraphEntry* hit = nullptr;
+  GramGraphEntry* victim = &tab[0];
+  for (int i = 0; i < GRAM_GRAPH_SLOTS; ++i) {
+    if (tab[i].last_use && tab[i].key == key) hit = &tab[i];
+    if (tab[i].last_use < victim->last_use) victim = &tab[i];
+  }
+  if (hit && hit->exec) {  // third and later identical calls: replay
+    hit->last_use = ++g_gram_graph_clock;
+    PL_TRY(need_ready());
+    CUDA_TRY(cudaGraphLaunch(hit->exec, st));
+    g_launches.fetch_add(hit->launches);
+    return PL_OK;
+  }
+  if (!hit || hit->uncacheable) {  // first sight: plain launches (this is also where the workspace grows), remember the call
+    const int rc = gram_dev_impl(kernel_id, dX1, n1, ldx1, dX2, n2, ldx2, d, alpha, cinv_kind, dcinv, ell, beta, dOut, ldo, fill, part, nparts, packed, st);
+    if (!hit && rc == PL_OK) {
+      if (victim->exec) cudaGraphExecDestroy(victim->exec);
+      *victim = GramGraphEntry();
+      key.ws_gen = g.ws_gen;  // (the call itself may have grown the workspace)
+      victim->key = key;
+      victim->last_use = ++g_gram_graph_clock;
+    }
+    return rc;
+  }
+  // second identical call: capture the launches on the library's stream, instantiate, and run the graph on the caller's stream
+  hit->last_use = ++g_gram_graph_clock;
+  PL_TRY(need_ready());
+  const int64_t l0 = g_launches.load();
+  cudaGraph_t graph = nullptr;
+  int rc = PL_OK;
+  if (cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+    rc = gram_dev_impl(kernel_id, dX1, n1, ldx1, dX2, n2, ldx2, d, alpha, cinv_kind, dcinv, ell, beta, dOut, ldo, fill, part, nparts, packed, g.stream);
+    const cudaError_t ee = cudaStreamEndCapture(g.stream, &graph);
+    if (rc == PL_OK && ee == cudaSuccess && graph && g.ws_gen == key.ws_gen && cudaGraphInstantiate(&hit->exec, graph, 0) == cudaSuccess) {
+      hit->launches = g_launches.load() - l0;
+    } else {
+      hit->exec = nullptr;
+      hit->uncacheable = true;
+    }
+    if (graph) cudaGraphDestroy(graph);
+  } else {
+    hit->uncacheable = true;
+  }
+  cudaGetLastError();
+  if (hit->exec) {
+    CUDA_TRY(cudaGraphLaunch(hit->exec, st));
+    return PL_OK;
+  }
+  g_launches.store(l0);
+  return gram_dev_impl(kernel_id, dX1, n1, ldx1, dX2, n2, ldx2, d, alpha, cinv_kind, dcinv, ell, beta, dOut, ldo, fill, part, nparts, packed, st);
 }
 
 int64_t pl_gram_tile_count(int64_t n1, int64_t n2, int part, int nparts) {

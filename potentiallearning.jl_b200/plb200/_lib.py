@@ -47,6 +47,7 @@ PROTOTYPES = {
     "pl_finalize": (None, []),
     "pl_last_error": (ctypes.c_char_p, []),
     "pl_last_timing": (_int, [_dp, _dp, _dp]),
+    "pl_last_host_ms": (_int, [_dp]),
     "pl_launch_count": (_i64, []),
     "pl_workspace_bytes": (_i64, []),
     "pl_workspace_trim": (_int, [_int]),
@@ -219,7 +220,9 @@ def finalize():
 def last_timing():
     k, h, d = _dbl(), _dbl(), _dbl()
     load().pl_last_timing(ctypes.byref(k), ctypes.byref(h), ctypes.byref(d))
-    return {"kernel_ms": k.value, "h2d_ms": h.value, "d2h_ms": d.value}
+    w = _dbl()
+    load().pl_last_host_ms(ctypes.byref(w))
+    return {"kernel_ms": k.value, "h2d_ms": h.value, "d2h_ms": d.value, "host_wall_ms": w.value}
 
 
 def set_profiling(on: bool):

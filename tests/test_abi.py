@@ -111,7 +111,7 @@ def test_product_never_imports_the_oracle():
     # every exported compute entry point (everything but lifetime / bookkeeping helpers) checks for an initialised sm_100 device
     for m in re.finditer(r"\n(?:int|void\*)\s+(pl_\w+)\s*\([^)]*\)\s*\{(.*?)\n\}\n", body, flags=re.S):
         name, code = m.group(1), m.group(2)
-        if name in ("pl_init", "pl_init_all", "pl_device_count", "pl_last_timing", "pl_set_profiling", "pl_host_free", "pl_gram_tile_coords", "pl_syrk_schedule",
+        if name in ("pl_init", "pl_init_all", "pl_device_count", "pl_last_timing", "pl_last_host_ms", "pl_set_profiling", "pl_host_free", "pl_gram_tile_coords", "pl_syrk_schedule",
                     "pl_comm_unique_id", "pl_comm_info", "pl_comm_destroy", "pl_comm_peer_enabled", "pl_gram_resident_info", "pl_gram_resident_shard", "pl_gram_free"):
             continue  # lifetime / bookkeeping: no compute
         assert ("need_ready()" in code) or re.search(r"return \w+_impl\(|return gram_host\(|return rmsd_host\(|return normal_eq_stream\(", code), name

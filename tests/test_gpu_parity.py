@@ -1755,3 +1755,65 @@ def test_syrk_schedule_modes_and_streams(pl, orc):
     Sref = (A * w[:, None]).T @ A
     assert normerr(S0.cpu().numpy(), Sref) < RTOL
     assert np.allclose(v0.cpu().numpy()[:K], A.T @ (w * b), rtol=0, atol=1e-9 * np.abs(A.T @ (w * b)).max())
+
+
+def test_gram_dev_graph_replay_tracks_buffer_contents(pl, orc, monkeypatch):
+    """pl_gram_dev replays a cached CUDA graph from the third identical call on (same pointers / shapes / parameters): the replay must read the
+    buffers as they are NOW, survive a workspace trim (new workspace pointers -> new graph), count its launches, and equal the plain launches
+    bit for bit; both tile shapes are exercised."""
+    import torch
+
+    from plb200 import _lib
+
+    lib = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for n, d, kid, k_or in ((700, 26, _lib.PL_KERNEL_DOT, orc.DotProduct()), (2300, 40, _lib.PL_KERNEL_RBF, orc.RBF(orc.Euclidean(40)))):
+        X = torch.empty((n, d), device="cuda", dtype=torch.float64)
+        K = torch.zeros((n, n), device="cuda", dtype=torch.float64)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def call():
+            _lib.check(lib.pl_gram_dev(kid, X.data_ptr(), n, d, None, 0, 0, d, 2, 0, None, 1.0, 1.0, K.data_ptr(), n, _lib.PL_FILL_FULL, 0, 1, 0, st), "pl_gram_dev")
+
+        per_call = None
+        for it in range(6):
+            X.copy_(torch.randn((n, d), device="cuda", dtype=torch.float64, generator=g) * 0.3 + 1.0 + it)
+            if it == 4:
+                _lib.check(lib.pl_workspace_trim(1), "trim")  # workspace pointers change: the cached graph must not be replayed
+            l0 = pl.launch_count()
+            call()
+            torch.cuda.synchronize()
+            nl = pl.launch_count() - l0
+            per_call = per_call or nl
+            assert nl == per_call, "a replay accounts for the same number of kernel launches"
+            got = K.cpu().numpy()
+            monkeypatch.setenv("PLB200_NO_GRAPH", "1")
+            K.zero_()
+            call()
+            torch.cuda.synchronize()
+            monkeypatch.delenv("PLB200_NO_GRAPH")
+            assert np.array_equal(got, K.cpu().numpy()), (n, it)
+            if it in (0, 5):
+                rows = [0, n // 2, n - 1]
+                Xh = X.cpu().numpy()
+                ref = orc.kernel_matrix_cross(Xh[rows], Xh, k_or)
+                gr = got[rows]
+                for q, i in enumerate(rows):
+                    gr[q, i] = ref[q, i]  # the diagonal is forced (k(x,x)), the oracle rounds it
+                assert relerr(gr, ref) < RTOL
+
+
+def test_tile_shapes_agree_bitwise(pl, monkeypatch):
+    """64 x 64 and 128 x 128 tiles run the same contraction order and the same epilogue arithmetic: identical bits, symmetric and rectangular,
+    with ragged edges."""
+    rng = np.random.default_rng(91)
+    for n, m, d in ((333, 0, 26), (1000, 0, 7), (257, 190, 33), (129, 640, 8)):
+        X = rng.standard_normal((n, d)) * 0.3 + 1.0
+        Y = rng.standard_normal((m, d)) * 0.3 + 1.0 if m else None
+        for k in (pl.DotProduct(), pl.RBF(pl.Euclidean(d), ell=1.3, beta=0.8), pl.InverseMultiquadric(pl.Euclidean(d))):
+            res = []
+            for small in ("0", "1"):
+                monkeypatch.setenv("PLB200_GRAM_SMALL", small)
+                res.append(np.asarray(pl.KernelMatrix(X, k)) if Y is None else pl.KernelMatrix(X, Y, k))
+            monkeypatch.delenv("PLB200_GRAM_SMALL")
+            assert np.array_equal(res[0], res[1]), (n, m, d, type(k).__name__)
