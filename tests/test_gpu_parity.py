@@ -637,7 +637,7 @@ def test_c_abi_layouts_and_errors(pl, orc):
     # empty input is a no-op, not an error
     assert lib.pl_gram_dot(_lib.dptr(X), 0, d, d, 2, _lib.dptr(K0), 4, 3) == 0
     t = pl.last_timing()
-    assert set(t) == {"kernel_ms", "h2d_ms", "d2h_ms"} and pl.launch_count() > 0
+    assert set(t) == {"kernel_ms", "h2d_ms", "d2h_ms", "host_wall_ms"} and pl.launch_count() > 0
 
 
 # ---------------------------------------------------------------------------------------------------------------
