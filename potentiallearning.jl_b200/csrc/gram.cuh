@@ -60,6 +60,9 @@ struct GramParams {
   int tcol_begin;       // >= 0: "column range" enumeration (symmetric only): tiles (ti <= tj) of tile columns
   int tma_out;          // TMAST variant: the output matrix is described by the third tensor map (dense, 16-byte aligned, even ldo)
   int pdl;              // launched as a programmatic dependent of the prelude kernel: see pdl_wait() in the kernel
+  int64_t tail_first;   // >= 0 (64 x 64 kernel only): TAIL mode. The last tail_count 128 x 128 tiles of this part (slots tail_first,
+  int tail_count;       //   tail_first + nparts, ...) are computed as up to four 64 x 64 sub-tiles each, written into the parent tile's
+  int T1p, T2p;         //   place (tile-packed output: inside the 128 x 128 packed tile). T1p / T2p: the 128-tile grid of the slots.
   int tcol_end;         //       [tcol_begin, tcol_end), column by column — lets the host stream finished rows of the
                         //       Symmetric(:U) storage to the host while later columns are still being computed
 };
@@ -102,6 +105,38 @@ __host__ __device__ __forceinline__ int64_t gram_colrange_num_slots(int c0, int 
 __host__ __device__ __forceinline__ int64_t gram_num_slots(int T1, int T2, int symmetric) {
   if (!symmetric) return (int64_t)T1 * T2;
   return (int64_t)((T1 + 1) / 2) * (T1 + 1);
+}
+
+// One unit of work of a CTA: the output tile (ti, tj) in units of the kernel's own tile edge, the packed tile it lands in (pk) and, in TAIL
+// mode, its offset (oi, oj) inside that 128 x 128 parent and whether the parent is a diagonal tile (its (0, 1) sub-tile is mirrored into it).
+struct GramTile {
+  int ti, tj, oi, oj;
+  int64_t pk;
+  bool diag_parent;
+};
+template <int NARROW>
+__device__ __forceinline__ bool gram_tile_of(const GramParams& p, int64_t l, GramTile& t) {
+  t.oi = t.oj = 0;
+  t.diag_parent = false;
+  if (NARROW == 2 && p.tail_first >= 0) {
+    const int64_t slot = p.tail_first + (l >> 2) * p.nparts;
+    int pi, pj;
+    if (!gram_slot_to_tile(p.T1p, p.T2p, p.symmetric, slot, pi, pj)) return false;
+    const int a = (int)((l >> 1) & 1), b = (int)(l & 1);
+    if (p.symmetric && pi == pj && a > b) return false;  // produced by mirroring sub-tile (0, 1): never computed independently
+    t.ti = 2 * pi + a;
+    t.tj = 2 * pj + b;
+    if ((int64_t)t.ti * 64 >= p.n1 || (int64_t)t.tj * 64 >= p.n2) return false;
+    t.pk = (slot - p.part) / p.nparts;
+    t.oi = 64 * a;
+    t.oj = 64 * b;
+    t.diag_parent = p.symmetric && pi == pj;
+    return true;
+  }
+  if (p.tcol_begin >= 0) gram_colrange_slot_to_tile(p.tcol_begin, l, t.ti, t.tj);
+  else if (!gram_slot_to_tile(p.T1, p.T2, p.symmetric, l, t.ti, t.tj)) return false;
+  t.pk = (l - p.part) / p.nparts;
+  return true;
 }
 
 // Integer power by squaring for a general DotProduct alpha (kernels.jl:35 `^d.α`); alpha = 1, 2 are inlined in the epilogue.
@@ -355,8 +390,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (p.pdl && EPI != EPI_DOT) pdl_wait();
 
   const int KT = (int)((p.d + GRAM_BK - 1) / GRAM_BK);
-  const int64_t slot0 = (int64_t)blockIdx.x * p.nparts + p.part;
-  const int64_t slot_stride = (int64_t)gridDim.x * p.nparts;
+  const bool tail = NARROW == 2 && p.tail_first >= 0;
+  const int64_t slot0 = tail ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * p.nparts + p.part;
+  const int64_t slot_stride = tail ? (int64_t)gridDim.x : (int64_t)gridDim.x * p.nparts;
+  const int64_t slot_end = tail ? (int64_t)4 * p.tail_count : p.ntiles_total;
 
   if (warp >= GRAM_CONSUMER_WARPS) {
     // ------------------------------ TMA producer warpgroup (one elected lane works) ------------------------------
@@ -365,10 +402,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       uint32_t it = 0;
-      for (int64_t l = slot0; l < p.ntiles_total; l += slot_stride) {
-        int ti, tj;
-        if (p.tcol_begin >= 0) gram_colrange_slot_to_tile(p.tcol_begin, l, ti, tj);
-        else if (!gram_slot_to_tile(p.T1, p.T2, p.symmetric, l, ti, tj)) continue;
+      for (int64_t l = slot0; l < slot_end; l += slot_stride) {
+        GramTile tl;
+        if (!gram_tile_of<NARROW>(p, l, tl)) continue;
+        const int ti = tl.ti, tj = tl.tj;
         const bool one_tile = p.same_operand && (ti == tj);
         const uint32_t bytes = one_tile ? A_TILE_BYTES : A_TILE_BYTES + B_TILE_BYTES;
         for (int kt = 0; kt < KT; ++kt, ++it) {
@@ -398,10 +435,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t offB0 = (uint32_t)((8 * NT * wn + pg) * 128) + xo;  // + nt * 1024
 
   uint32_t it = 0;
-  for (int64_t l = slot0; l < p.ntiles_total; l += slot_stride) {
-    int ti, tj;
-    if (p.tcol_begin >= 0) gram_colrange_slot_to_tile(p.tcol_begin, l, ti, tj);
-    else if (!gram_slot_to_tile(p.T1, p.T2, p.symmetric, l, ti, tj)) continue;
+  for (int64_t l = slot0; l < slot_end; l += slot_stride) {
+    GramTile tl;
+    if (!gram_tile_of<NARROW>(p, l, tl)) continue;
+    const int ti = tl.ti, tj = tl.tj;
     const bool one_tile = p.same_operand && (ti == tj);
 
     double acc[MT][NT][2];
@@ -477,11 +514,11 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool f2 = !p.packed && p.symmetric && (p.fill & 2);            // write [j][i] (off-diagonal tiles)
     double* base;
     int64_t ldo, ib, jb;
-    if (p.packed) {  // tile k = (l - part) / nparts of this part, 128 x 128 row-major
-      base = p.out + ((l - p.part) / p.nparts) * (int64_t)(BM * BN);
-      ldo = BN;
-      ib = il0;
-      jb = jl0;
+    if (p.packed) {  // tile pk of this part, row-major; in TAIL mode the 64 x 64 sub-tile sits at (oi, oj) of its 128 x 128 parent
+      base = p.out + tl.pk * (int64_t)(tail ? GRAM_BM * GRAM_BN : BM * BN);
+      ldo = tail ? GRAM_BN : BN;
+      ib = tl.oi + il0;
+      jb = tl.oj + jl0;
     } else {
       base = p.out;
       ldo = p.ldo;
@@ -492,7 +529,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     double* const pcol = base + jb * ldo + ib;  // mirror:  pcol[(8*nt + 4*c)*ldo + 8*mt]
     const bool interior = ((int64_t)(ti + 1) * BM <= p.n1) && ((int64_t)(tj + 1) * BN <= p.n2);
     const int rel0 = diag_tile ? (jl0 - il0) : 4096;
-    const bool w1 = f1 || diag_tile, w2 = diag_tile ? true : f2;
+    // TAIL mode, sub-tile (0, 1) of a DIAGONAL parent: its mirror image is sub-tile (1, 0) of the same packed tile
+    const bool mirror_in_parent = tail && p.packed && tl.diag_parent && !diag_tile;
+    const bool f2m = f2 || mirror_in_parent;
+    const bool w1 = f1 || diag_tile, w2 = diag_tile ? true : f2m;
     // ALPHA doubles as the "uncommon parameters" switch: DotProduct power != 2, or an RBF scale beta <= 0 that cannot be
     // folded into the exponent: one general instantiation
     const bool common = (EPI == EPI_DOT) ? (p.alpha == 2) : (EPI == EPI_RBF ? (p.bmul == 1.0) : true);
@@ -504,7 +544,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else if (!common) {
       gram_epilogue<EPI, true, 0, MT, NT>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo);
     } else if (interior && !diag_tile) {
-      gram_epilogue<EPI, false, 2, MT, NT>(acc, p, i0, j0, 0, f1, f2, prow, pcol, ldo);
+      gram_epilogue<EPI, false, 2, MT, NT>(acc, p, i0, j0, 0, f1, f2m, prow, pcol, ldo);
     } else {
       gram_epilogue<EPI, true, 2, MT, NT>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo);
     }

@@ -404,9 +404,25 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   p.nparts = L.nparts;
   const bool pdl = L.pdl && !getenv("PLB200_NO_PDL");
   p.pdl = pdl ? 1 : 0;
+  p.tail_first = -1;
+  p.tail_count = 0;
+  p.T1p = p.T1;
+  p.T2p = p.T2;
   const int64_t mine = (p.ntiles_total - L.part + L.nparts - 1) / L.nparts;
   if (mine <= 0) return PL_OK;
-  const int grid = (int)(mine < g.num_sms ? mine : g.num_sms);
+  // Tile-packed shards (one GPU's share of a matrix): when the share is only a few waves of CTAs, the last PARTIAL wave costs a whole
+  // wave (config 2 on 8 GPUs: 1550 tiles = 10.47 waves of 148 -> 11). Its r tiles are then computed by a second launch of the
+  // 64 x 64 kernel as 4 r sub-tiles written into the same packed tiles (gram_tile_of, TAIL mode): ceil(4 r / SMs) quarter-cost waves.
+  int tail_r = 0;
+  if (!narrow && !small && L.packed && L.tcol_begin < 0 && !getenv("PLB200_GRAM_NO_TAIL")) {
+    const int64_t waves = mine / g.num_sms, r = mine % g.num_sms;
+    if (waves >= 1 && waves <= 48 && r > 0 && 4 * r <= 3 * (int64_t)g.num_sms) {
+      tail_r = (int)r;
+      p.ntiles_total = L.part + (mine - r) * L.nparts;  // the main launch stops before this part's last r slots
+    }
+  }
+  const int64_t main_tiles = mine - tail_r;
+  const int grid = (int)(main_tiles < g.num_sms ? main_tiles : g.num_sms);
   // Dense results of the DotProduct / IMQ / LINEAR kernels leave through the TMA-store variant (smem-staged epilogue): 9-16 % faster when
   // the contraction is shallow and the kernel is bound by writing K, still 1-2 % at d = 300. Needs an output the TMA unit can address
   // (16-byte aligned, even leading dimension). PLB200_GRAM_TMAST=0/1 overrides the rule (experiments).
@@ -424,26 +440,43 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   }
   if (L.epi != EPI_LINEAR || L.packed || L.symmetric) MAIN_KERNEL_BEGIN(st);
   cudaError_t le = cudaSuccess;
-#define GRAM_LAUNCH(NARROW_, TMAST_, SMEM_)                                                                                                   \
+#define GRAM_LAUNCH(NARROW_, TMAST_, SMEM_, GRID_, PDL_, TA_, TB_, P_)                                                                        \
   switch (L.epi) {                                                                                                                            \
-    case EPI_LINEAR: le = launch_ex(gram_kernel<EPI_LINEAR, NARROW_, TMAST_>, grid, GRAM_THREADS, SMEM_, st, pdl, tmA, tmB, tmO, p); break;   \
-    case EPI_DOT: le = launch_ex(gram_kernel<EPI_DOT, NARROW_, TMAST_>, grid, GRAM_THREADS, SMEM_, st, pdl, tmA, tmB, tmO, p); break;         \
-    case EPI_RBF: le = launch_ex(gram_kernel<EPI_RBF, NARROW_, TMAST_>, grid, GRAM_THREADS, SMEM_, st, pdl, tmA, tmB, tmO, p); break;         \
-    case EPI_IMQ: le = launch_ex(gram_kernel<EPI_IMQ, NARROW_, TMAST_>, grid, GRAM_THREADS, SMEM_, st, pdl, tmA, tmB, tmO, p); break;         \
+    case EPI_LINEAR: le = launch_ex(gram_kernel<EPI_LINEAR, NARROW_, TMAST_>, GRID_, GRAM_THREADS, SMEM_, st, PDL_, TA_, TB_, tmO, P_); break; \
+    case EPI_DOT: le = launch_ex(gram_kernel<EPI_DOT, NARROW_, TMAST_>, GRID_, GRAM_THREADS, SMEM_, st, PDL_, TA_, TB_, tmO, P_); break;       \
+    case EPI_RBF: le = launch_ex(gram_kernel<EPI_RBF, NARROW_, TMAST_>, GRID_, GRAM_THREADS, SMEM_, st, PDL_, TA_, TB_, tmO, P_); break;       \
+    case EPI_IMQ: le = launch_ex(gram_kernel<EPI_IMQ, NARROW_, TMAST_>, GRID_, GRAM_THREADS, SMEM_, st, PDL_, TA_, TB_, tmO, P_); break;       \
     default: return set_err(PL_EINVAL, "unknown epilogue %d", L.epi);                                                                        \
   }
   if (narrow) {
-    GRAM_LAUNCH(1, 0, GRAM_SMEM_BYTES)
+    GRAM_LAUNCH(1, 0, GRAM_SMEM_BYTES, grid, pdl, tmA, tmB, p)
   } else if (small) {
-    GRAM_LAUNCH(2, 0, GRAM_SMEM_BYTES)
+    GRAM_LAUNCH(2, 0, GRAM_SMEM_BYTES, grid, pdl, tmA, tmB, p)
   } else if (tmast) {
-    GRAM_LAUNCH(0, 1, GRAM_SMEM_BYTES_TMAST)
+    GRAM_LAUNCH(0, 1, GRAM_SMEM_BYTES_TMAST, grid, pdl, tmA, tmB, p)
   } else {
-    GRAM_LAUNCH(0, 0, GRAM_SMEM_BYTES)
+    GRAM_LAUNCH(0, 0, GRAM_SMEM_BYTES, grid, pdl, tmA, tmB, p)
   }
-#undef GRAM_LAUNCH
   CUDA_TRY(le);
   LAUNCH_CHECK();
+  if (tail_r) {
+    CUtensorMap tmA64, tmB64;
+    PL_TRY(make_tmap_2d(&tmA64, L.A, L.d, L.nA, L.ldA, GRAM_BK, 64));
+    PL_TRY(make_tmap_2d(&tmB64, L.B, L.d, L.nB, L.ldB, GRAM_BK, 64));
+    GramParams pt = p;
+    pt.T1 = (int)((L.nA + 63) / 64);
+    pt.T2 = (int)((L.nB + 63) / 64);
+    pt.tail_first = p.ntiles_total;  // first tail slot of this part
+    pt.tail_count = tail_r;
+    pt.tma_out = 0;
+    const bool tpdl = !getenv("PLB200_NO_PDL");  // directly behind the main launch: its prologue overlaps the main kernel's last wave
+    pt.pdl = tpdl ? 1 : 0;
+    const int tgrid = (int)(4 * (int64_t)tail_r < g.num_sms ? 4 * tail_r : g.num_sms);
+    GRAM_LAUNCH(2, 0, GRAM_SMEM_BYTES, tgrid, tpdl, tmA64, tmB64, pt)
+    CUDA_TRY(le);
+    LAUNCH_CHECK();
+  }
+#undef GRAM_LAUNCH
   if (L.epi != EPI_LINEAR || L.packed || L.symmetric) MAIN_KERNEL_END(st);
   return PL_OK;
 }

@@ -1817,3 +1817,52 @@ def test_tile_shapes_agree_bitwise(pl, monkeypatch):
                 res.append(np.asarray(pl.KernelMatrix(X, k)) if Y is None else pl.KernelMatrix(X, Y, k))
             monkeypatch.delenv("PLB200_GRAM_SMALL")
             assert np.array_equal(res[0], res[1]), (n, m, d, type(k).__name__)
+
+
+def test_packed_shard_tail_wave_subtiles(pl, orc, monkeypatch):
+    """Tile-packed shards of a few waves finish their last PARTIAL wave as 64 x 64 sub-tiles written into the same packed tiles (TAIL mode of the
+    small-tile kernel). Same bits as the plain 128 x 128 launch, for every part, with ragged edges, odd tile counts and diagonal parents (whose
+    (1, 0) sub-tile is the mirror image of (0, 1), never computed on its own); sampled tiles against the oracle."""
+    import ctypes
+
+    import torch
+
+    from plb200 import _lib
+
+    lib = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(17)
+    engaged = 0
+    for n, d, nparts in ((2700, 26, 1), (2689, 40, 1), (4000, 17, 2), (3777, 64, 2), (5400, 12, 3)):
+        X = torch.randn((n, d), device="cuda", dtype=torch.float64, generator=g) * 0.3 + 1.0
+        Xh = X.cpu().numpy()
+        for kid, ko in ((_lib.PL_KERNEL_DOT, orc.DotProduct()), (_lib.PL_KERNEL_RBF, orc.RBF(orc.Euclidean(d)))):
+            for part in range(nparts):
+                nt = int(lib.pl_gram_tile_count(n, 0, part, nparts))
+                r = nt % 148
+                engaged += int(nt >= 148 and 0 < 4 * r <= 444)
+                outs = []
+                for no_tail in ("1", None):
+                    if no_tail:
+                        monkeypatch.setenv("PLB200_GRAM_NO_TAIL", no_tail)
+                    else:
+                        monkeypatch.delenv("PLB200_GRAM_NO_TAIL")
+                    tiles = torch.full((nt, 128, 128), -3.0, device="cuda", dtype=torch.float64)
+                    _lib.check(lib.pl_gram_dev(kid, X.data_ptr(), n, d, None, 0, 0, d, 2, 0, None, 1.0, 1.0, tiles.data_ptr(), 128, _lib.PL_FILL_FULL, part, nparts, 1, st),
+                               "pl_gram_dev")
+                    torch.cuda.synchronize()
+                    outs.append(tiles.cpu().numpy())
+                assert np.array_equal(outs[0], outs[1]), (n, d, nparts, part, kid)
+                ti, tj = ctypes.c_int64(), ctypes.c_int64()
+                for k in (nt - 1, nt - 2, nt - r, max(nt - r - 1, 0), nt - (r + 1) // 2):  # tail tiles and the last main tile
+                    _lib.check(lib.pl_gram_tile_coords(n, 0, part, nparts, int(k), ctypes.byref(ti), ctypes.byref(tj)), "coords")
+                    if ti.value < 0:
+                        continue
+                    r0, r1, c0, c1 = ti.value * 128, min(ti.value * 128 + 128, n), tj.value * 128, min(tj.value * 128 + 128, n)
+                    ref = orc.kernel_matrix_cross(Xh[r0:r1], Xh[c0:c1], ko)
+                    got = outs[1][k, : r1 - r0, : c1 - c0]
+                    if ti.value == tj.value:
+                        np.fill_diagonal(ref, 1.0)
+                        assert np.array_equal(got, got.T), "packed diagonal tile: both triangles, exactly symmetric"
+                    assert relerr(got, ref) < RTOL, (n, part, k)
+    assert engaged >= 6, "the shapes above must actually take the tail path"
