@@ -55,6 +55,40 @@ class DeviceEngine:
         )
         return M, v
 
+    def normal_eq_sharded(self, A, b=None, w=None, n_energy_rows=0, w_e=1.0, w_f=1.0, intercept=False, lam=0.0):
+        """(A'WA + lam I, A'Wb) over ALL ranks' shards (pl_normal_eq_sharded_dev): SYRK -> exchange -> finish inside the library, one stream."""
+        import torch
+
+        _check_mat(A, "A")
+        R, K = A.shape
+        n = K + (1 if intercept else 0)
+        M = torch.empty((n, n), device=A.device, dtype=torch.float64)
+        v = torch.empty(n, device=A.device, dtype=torch.float64) if b is not None else None
+        _lib.check(
+            _lib.lib().pl_normal_eq_sharded_dev(A.data_ptr(), R, K, A.stride(0), None if w is None else w.data_ptr(), int(n_energy_rows), float(w_e), float(w_f),
+                                                None if b is None else b.data_ptr(), 1 if intercept else 0, float(lam), M.data_ptr(),
+                                                None if v is None else v.data_ptr(), _stream(A)),
+            "pl_normal_eq_sharded_dev",
+        )
+        return M, v
+
+    def cov_sharded(self, X, n_total, mean=None, center=True):
+        """(Q, m) over ALL ranks' rows (pl_cov_sharded_dev): one pass, the K and K x K exchanges inside the library."""
+        import torch
+
+        _check_mat(X, "X")
+        n, K = X.shape
+        C = torch.empty((K, K), device=X.device, dtype=torch.float64)
+        m = None
+        if center:
+            m = mean.clone() if mean is not None else torch.empty(K, device=X.device, dtype=torch.float64)
+        _lib.check(
+            _lib.lib().pl_cov_sharded_dev(X.data_ptr(), n, int(n_total), K, X.stride(0), None if m is None else m.data_ptr(), 1 if mean is not None else 0,
+                                          1 if center else 0, C.data_ptr(), _stream(X)),
+            "pl_cov_sharded_dev",
+        )
+        return C, m
+
     def cov_shifted(self, X, z):
         """S_z = sum (x - z)(x - z)' and rho = sum (x - z) of a row shard in ONE pass over the rows (pl_cov_shifted_dev)."""
         import torch

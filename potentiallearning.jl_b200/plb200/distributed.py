@@ -1,5 +1,9 @@
-"""Multi-GPU host logic: one process per GPU, torch.distributed (NCCL over NVLink) for the ONE exchange step each
-contraction has. The reference has no distributed code at all; sharding follows section 8(e):
+"""Multi-GPU host logic, one process per GPU. On B200s the whole step — SYRK, the ONE exchange (peer memory over NVLink, NCCL
+fallback) and the finish kernel — runs inside libplb200 (pl_normal_eq_sharded_dev / pl_cov_sharded_dev after pl_comm_init_rank; see
+csrc/multi.inl): the functions below hand over to it whenever the library owns a communicator. The explicit form that follows
+(engine partials + an all-reduce through torch.distributed) is the same sharding logic spelled out; it is what the gloo / CPU tests
+exercise with a checker engine, and what runs on GPUs when only a torch process group exists.
+The reference has no distributed code at all; sharding follows section 8(e):
 
   * normal equations / covariance: shard ROWS (whole configurations per rank), each rank produces unscaled partial
     sums with the fused SYRK kernel, ONE all-reduce of K*K (+2K+2) doubles, then the tiny finish kernel;
@@ -25,6 +29,12 @@ def shard_rows(n_rows: int, rank: int, world: int, align: int = 1):
     return min(lo_u * align, n_rows), min(hi_u * align, n_rows)
 
 
+def _library_owns_comm() -> bool:
+    from . import _lib
+
+    return _lib._inited and _lib.comm_info()["nranks"] > 1
+
+
 def _all_reduce(t, group):
     import torch.distributed as dist
 
@@ -40,6 +50,8 @@ def normal_equations_sharded(A_local, b_local=None, w_local=None, n_energy_rows_
     import torch
 
     engine = engine or DeviceEngine()
+    if isinstance(engine, DeviceEngine) and group is None and _library_owns_comm():
+        return engine.normal_eq_sharded(A_local, b_local, w_local, n_energy_rows_local, w_e, w_f, intercept, lam)
     want_vec = intercept or (b_local is not None)
     S, vec = engine.syrk_partial(A_local, w_local, n_energy_rows_local, w_e, w_f, b_local, None, want_vec)
     if vec is not None:
@@ -60,6 +72,8 @@ def covariance_sharded(X_local, n_total: int, mean=None, center=True, group=None
     (pca.m = sum(d)/length(d), pca_state.jl:35), every rank re-centres its S_z about m (delta = m - z: tiny, nothing cancels), and ONE
     all-reduce adds the shards. A persisted mean (pca.m set, pca_state.jl:34) centres directly."""
     engine = engine or DeviceEngine()
+    if isinstance(engine, DeviceEngine) and group is None and _library_owns_comm():
+        return engine.cov_sharded(X_local, n_total, mean, center)
     n_local = X_local.shape[0]
     if center and mean is None:
         prefix = min(n_local, 65536)
