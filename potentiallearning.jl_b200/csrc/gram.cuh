@@ -27,8 +27,8 @@ constexpr int GRAM_BM = 128;
 constexpr int GRAM_BN = 128;
 constexpr int GRAM_BK = 16;  // doubles per stage row: 128 bytes, the TMA 128B-swizzle span
 constexpr int GRAM_STAGES = 5;
-constexpr int GRAM_STAGES_TMAST = 3;            // operand ring of the TMA-store variant (shallow contractions: few k-steps per tile)
-constexpr int GRAM_STAGING_BYTES = 8 * 16384;   // one 32 x 64 staging tile per consumer warp
+constexpr int GRAM_STAGES_TMAST = 4;            // operand ring of the TMA-store variant
+constexpr int GRAM_STAGING_BYTES = 8 * 8192;    // HALF a 32 x 64 warp tile of staging per consumer warp (the epilogue leaves in two halves)
 constexpr int GRAM_CONSUMER_WARPS = 8;
 constexpr int GRAM_THREADS = (GRAM_CONSUMER_WARPS + 4) * 32;  // 2 DMMA warpgroups + 1 producer warpgroup (setmaxnreg needs whole warpgroups)
 constexpr int PRODUCER_REGS = 24;
@@ -36,6 +36,12 @@ constexpr int CONSUMER_REGS = 240;  // per SMSP: 2 x 240 + 24 = 504 <= 512 regis
 constexpr int GRAM_TILE_BYTES = GRAM_BM * GRAM_BK * 8;  // 16 KB per operand per stage
 constexpr int GRAM_SMEM_BYTES = GRAM_STAGES * 2 * GRAM_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int GRAM_SMEM_BYTES_TMAST = GRAM_STAGES_TMAST * 2 * GRAM_TILE_BYTES + GRAM_STAGING_BYTES + 1024 + 256;
+// RBF: table of 2^(j/256), j = 0..255, replicated 16 x (one copy per lane slot: conflict-free whatever the indices), kept in shared
+// memory by every CTA of the exp epilogue (exp2_tab below)
+constexpr int EXP_TAB_BITS = 8;
+constexpr int EXP_TAB_N = 1 << EXP_TAB_BITS;
+constexpr int EXP_TAB_BYTES = EXP_TAB_N * 16 * 8;
+constexpr int GRAM_AUG_COLS = 2;  // RBF operands carry two extra contraction columns (u_i, 1) x (1, u_j): see rbf_aug_* in prelude.cuh
 
 enum { EPI_LINEAR = 0, EPI_DOT = 1, EPI_RBF = 2, EPI_IMQ = 3 };
 
@@ -60,6 +66,9 @@ struct GramParams {
   int tcol_begin;       // >= 0: "column range" enumeration (symmetric only): tiles (ti <= tj) of tile columns
   int tma_out;          // TMAST variant: the output matrix is described by the third tensor map (dense, 16-byte aligned, even ldo)
   int pdl;              // launched as a programmatic dependent of the prelude kernel: see pdl_wait() in the kernel
+  int b_shift;          // RBF: the B operand reads its LAST k-step b_shift columns further right (the block that holds its variant of
+                        //   the augmented columns); 0 otherwise
+  const double* exp_tab;  // RBF: 2^(j/256) table in global memory, 256 doubles (replicated 16 x into shared memory by every CTA)
   int64_t tail_first;   // >= 0 (64 x 64 kernel only): TAIL mode. The last tail_count 128 x 128 tiles of this part (slots tail_first,
   int tail_count;       //   tail_first + nparts, ...) are computed as up to four 64 x 64 sub-tiles each, written into the parent tile's
   int T1p, T2p;         //   place (tile-packed output: inside the 128 x 128 packed tile). T1p / T2p: the 128-tile grid of the slots.
@@ -152,39 +161,58 @@ __device__ __noinline__ double ipow_general(double x, int a) {
   return neg ? 1.0 / r : r;
 }
 
-// exp(x) for x in [-708, 709]: n = rint(x/ln2) by the magic-number add, Cody-Waite two-constant reduction, degree-13
-// Taylor polynomial on |r| <= ln2/2 (truncation 4e-18), 2^n applied to the exponent field. Branch-free, 19 fp64
-// instructions; measured max relative error 1.4e-16 (1.2 ulp) against long double over 2e7 points in [-708, 0]
-// (tests/test_fast_exp.py re-states it). The library exp() costs ~370 SASS instructions per call site once its slow
-// paths are inlined, which made the fused RBF epilogue instruction-cache bound (profiles/r01 notes).
-// coefficients live in the constant bank so that every DFMA takes its constant as a c[][] operand (no UMOV pairs)
-__constant__ double EXP_C[18] = {
-    6755399441055744.0 /*1.5*2^52*/, 1.4426950408889634 /*log2 e*/, -6.93147180369123816490e-01 /*-ln2 hi*/,
-    -1.90821492927058770002e-10 /*-ln2 lo*/, 1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0,
-    1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
-__device__ __forceinline__ double exp_fast(double x) {
-  const double t = fma(x, EXP_C[1], EXP_C[0]);
-  const int n = __double2loint(t);
-  const double nd = t - EXP_C[0];
-  double r = fma(nd, EXP_C[2], x);
-  r = fma(nd, EXP_C[3], r);
-  double p = EXP_C[4];
-#pragma unroll
-  for (int k = 5; k < 18; ++k) p = fma(p, r, EXP_C[k]);
-  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+// 2^(y / 256) — the whole RBF epilogue. The accumulator of the RBF Gram kernel already IS
+//   y = 256 log2(e) * (-0.5 d2 / ell^2 + ln beta)        (kernels.jl:73-74 with distances.jl:59 expanded)
+// because its operands are pre-scaled by sqrt(256 log2(e)) / ell and carry the row terms -q_i/2 as two augmented contraction
+// columns (u_i, 1) x (1, u_j) (prelude.cuh, rbf_aug_kernel): no per-element argument arithmetic is left. Then
+//   N = rint(y) by the magic-number add, r = y - N (exact), j = N mod 256 -> T = 2^(j/256) from shared memory, n = N div 256,
+//   2^(y/256) = 2^n * T * e^(c r),  c = ln2 / 256,  |c r| <= 1.36e-3:  e^z - 1 = z + z^2 (b0 + b1 z + b2 z^2), the b's interpolated at
+//   Chebyshev nodes (max relative error 9.5e-18), 2^n applied to the exponent field.
+// 8 FP64-pipe instructions per element (3 DADD, 4 DFMA, 1 DMUL) instead of the 22 of the Cody-Waite + degree-13 polynomial of round 1
+// — scalar FP64 and DMMA share one pipe, so every one of them is time taken from the DMMAs. The table is replicated 16 x in shared
+// memory (entry j of lane-slot s = lane & 15 at (16 j + s) * 8: 32 KB): every half-warp reads 16 distinct bank pairs whatever the
+// indices are — a 4096-entry unreplicated table (degree 3, 7 instructions) measured 6.2 conflict wavefronts per lookup and made the
+// epilogue LSU-bound (profiles/r02b notes). Max relative error 2.2e-16 (1 ulp: half an ulp of the table entry + the final
+// rounding) against long double over 2e7 points (tests/test_fast_exp.py re-states it). Branch free; y > 0 (beta > 1) works the same
+// way. Arguments below -1022 * 256 (x < -708.4: results under 2.3e-308, denormal or zero in the reference) come out as a number
+// <= 4.5e-308 (N is clamped, below). |y| < 2^31 is assumed (|x| < 5.8e6: beyond that N is garbage, the masked table index stays
+// in bounds, and the result is some number <= 4.5e-308 or, for y = -inf / NaN, NaN).
+__constant__ double EXP2_C[5] = {6755399441055744.0 /*1.5 * 2^52*/, 0.0027076061740622863 /*c = ln2/256*/, 3.6655655969101062e-06 /*b0 c^2*/,
+                                 3.308302907918888e-09 /*b1 c^3*/, 2.239395293483284e-12 /*b2 c^4*/};
+// tab.addr = table base + 8 * (lane & 15); entry offset (N mod 256) * 128 (one LOP3 + one multiply-add).
+// Instruction diet (the epilogue of the staged kernel is bound by ISSUE slots: 2 warps x 64 elements per sub-partition and tile): the flush is
+// an integer max on N (N >= -1022 * 256 keeps the exponent field in range; everything below comes out as <= 2^-1021 = 4.5e-308 instead
+// of exactly 0 — the reference has denormals or 0 there), the exponent goes in with one shift and one multiply-add.
+constexpr int EXP2_NMIN = -1022 * EXP_TAB_N;
+struct Exp2Tab {
+  uint32_t addr;  // shared-memory address of the table + 8 * (lane & 15)
+};
+__device__ __forceinline__ double exp2_tab(const double y, const Exp2Tab tab) {
+  const double t = y + EXP2_C[0];
+  const int N = max(__double2loint(t), EXP2_NMIN);
+  const double r = y - (t - EXP2_C[0]);
+  // integer side spelled in PTX so that it stays 2 + 2 instructions (and / mad for the table address, shr / mad for the exponent field);
+  // left to itself the compiler rewrites both into shift + and + add
+  uint32_t a;
+  int hi_add;
+  asm("{\n"
+      ".reg .b32 j;\n"
+      "and.b32 j, %2, 255;\n"
+      "mad.lo.u32 %0, j, 128, %3;\n"
+      "shr.s32 j, %2, 8;\n"
+      "mul.lo.s32 %1, j, 1048576;\n"
+      "}\n"
+      : "=r"(a), "=r"(hi_add)
+      : "r"(N), "r"(tab.addr));
+  double T;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(a));
+  double q = fma(r, EXP2_C[4], EXP2_C[3]);
+  q = fma(q, r, EXP2_C[2]);
+  q = fma(q, r, EXP2_C[1]);
+  const double e = fma(T * r, q, T);
+  return __hiloint2double(__double2hiint(e) + hi_add, __double2loint(e));
 }
-// Whole-range wrapper, still branch free (a per-element branch to a slow path stops the compiler from interleaving the
-// independent exp chains of a thread, which left the FP64 pipe ~25% utilised in the epilogue): arguments below -708
-// (results under 3.3e-308, i.e. denormal or zero in the reference) flush to 0 with an INTEGER compare + selects (every
-// FP64-pipe instruction here is time taken from the DMMAs: scalar FP64 and DMMA share one pipe).
-// Arguments above 709 cannot occur for an RBF kernel (x = -0.5 d2/ell^2 + ln(beta) with d2 >= 0); they are not clamped.
-__device__ __forceinline__ double exp_clamped(double x) {
-  const double e = exp_fast(x);
-  // x <= -708.0 tested on the integer pipe: for negative doubles the magnitude grows with the unsigned bit pattern, and
-  // -708.0 is 0xC086200000000000 (NaN arguments also land here and give 0 rather than NaN; d2 is never NaN for finite input)
-  const bool tiny = (unsigned)__double2hiint(x) >= 0xC0862000u;
-  return __hiloint2double(tiny ? 0 : __double2hiint(e), tiny ? 0 : __double2loint(e));
-}
+static_assert(EXP_TAB_BITS == 8, "exp2_tab spells 255 / 8 in its PTX");
 
 // Fused epilogue of one warp tile. GENERAL = false: interior, off-diagonal tile (97% of the tiles of a large matrix):
 // no bounds or triangle logic, ~30 instructions per element. GENERAL = true: edge and diagonal tiles.
@@ -193,7 +221,9 @@ __device__ __forceinline__ double exp_clamped(double x) {
 //         positions are always written and hold 0 when their triangle was not requested (zeros(n,n) storage).
 template <int EPI, bool GENERAL, int ALPHA /* 2: DotProduct power 2 / RBF scale folded; 0: general (runtime p.alpha, p.bmul) */, int MT, int NT>
 __device__ __forceinline__ void gram_epilogue(const double (&acc)[MT][NT][2], const GramParams& p, int64_t i0, int64_t j0, int rel0, bool w1, bool w2,
-                                              double* __restrict__ prow, double* __restrict__ pcol, int64_t ldo) {
+                                              double* __restrict__ prow, double* __restrict__ pcol, int64_t ldo, const Exp2Tab tab) {
+  // per-row / per-column statistics: DotProduct 1/|x|, IMQ the quadratic forms; RBF has them inside the accumulator (augmented columns)
+  constexpr bool STATS = EPI == EPI_DOT || EPI == EPI_IMQ;
   unsigned imask = (1u << MT) - 1u;
   double sa[MT];
 #pragma unroll
@@ -203,8 +233,8 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[MT][NT][2], co
       ok = i0 + 8 * mt < p.n1;
       if (!ok) imask &= ~(1u << mt);
     }
-    const double r = (EPI != EPI_LINEAR && ok) ? __ldg(p.ra + i0 + 8 * mt) : 0.0;
-    sa[mt] = (EPI == EPI_RBF) ? fma(p.s, r, p.lnbeta) : (EPI == EPI_IMQ ? p.s * r : r);  // RBF: beta*exp(x) = exp(x + ln beta)
+    const double r = (STATS && ok) ? __ldg(p.ra + i0 + 8 * mt) : 0.0;
+    sa[mt] = EPI == EPI_IMQ ? p.s * r : r;
   }
   const double m2s = -2.0 * p.s;
   // k(x,x): beta for RBF (d2 == 0), c2^(-1/2) for IMQ, n/sqrt(n*n) = 1 for DotProduct
@@ -227,15 +257,15 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[MT][NT][2], co
         for (int c = 0; c < 2; ++c) {
           const int nt = 4 * ng + q;
           jok[q][c] = GENERAL ? (j0 + 8 * nt + 4 * c < p.n2) : true;
-          const double r = (EPI != EPI_LINEAR && jok[q][c]) ? __ldg(p.rb + j0 + 8 * nt + 4 * c) : 0.0;
+          const double r = (STATS && jok[q][c]) ? __ldg(p.rb + j0 + 8 * nt + 4 * c) : 0.0;
           double x = acc[mt][nt][c];
           if (EPI == EPI_DOT) {
             x = x * sa[mt] * r;
             if (ALPHA == 2) x = x * x;
             else if (ALPHA == 0) x = ipow_general(x, p.alpha);
           } else if (EPI == EPI_RBF) {
-            // arg = s*(q_i + q_j - 2 G_ij) = -0.5 d2 / ell^2  (kernels.jl:73-74 with distances.jl:59 expanded)
-            x = exp_clamped(fma(x, m2s, fma(p.s, r, sa[mt])));
+            // the accumulator is 256 log2(e) (-0.5 d2 / ell^2 + ln beta)  (kernels.jl:73-74 with distances.jl:59 expanded)
+            x = exp2_tab(x, tab);
             if (ALPHA == 0) x *= p.bmul;  // only for beta <= 0; for beta > 0 the scale is folded into the exponent (bmul == 1)
           } else if (EPI == EPI_IMQ) {
             // (c2 + d2/ell^2)^(-1/2)  (kernels.jl:156-164): d2/ell^2 = s*(q_i + q_j - 2 G_ij) with s = 1/ell^2
@@ -267,83 +297,100 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[MT][NT][2], co
 }
 
 // Shared-memory staged, TMA-stored epilogue of one interior off-diagonal 32 x 64 warp tile (TMAST kernel variant).
-// The fragment stores of gram_epilogue touch 8 rows x 32 B (direct) or 4 rows x 64 B (mirror) per instruction; when the contraction is
-// shallow (d <= 128: config 1's d = 26) the kernel is bound by WRITING K and those stores neither reach the HBM rate nor overlap the
-// next tile's DMMAs (measured: time = compute + stores). Here the values go to a 16 KB per-warp staging buffer in the 128B-swizzled
-// box layout (conflict-free st.shared), one lane hands 16 x 32 boxes to the TMA unit, and the warp moves on to the next tile while the
-// full-line writes drain asynchronously. The mirrored copy is staged transposed through the same buffer.
-//   direct box b (columns 16b..16b+15 of the warp tile, 32 rows): stg + 4096 b + 128 row + ((8 (col & 15)) ^ (16 (row & 7)))
-//   mirror box (ih, jh) (16 i-columns x 32 j-rows):               stg + 4096 (2 ih + jh) + 128 (j & 31) + ((8 (i & 15)) ^ (16 (j & 7)))
+// The fragment stores of gram_epilogue touch 8 rows x 32 B (direct) or 4 rows x 64 B (mirror) per instruction and the warp sits through
+// them: with the 8-instruction exponential the register epilogue of the RBF kernel was bound by the LSU, not by the FP64 pipe (ncu,
+// profiles/r02b notes); shallow contractions (d <= 128: config 1's d = 26) are bound by WRITING K outright. Here the values go to an
+// 8 KB per-warp staging buffer in the 128B-swizzled box layout (conflict-free st.shared), one lane hands 16 x 32 boxes to the TMA unit
+// (full 128-byte lines, asynchronous) and the warp moves on to the next tile while the writes drain. The warp tile leaves in two
+// halves through the same buffer (direct copy: column halves; mirrored copy, staged transposed: row halves), the values of the second
+// half being computed while the TMA unit reads the first — half the staging memory buys a fourth operand stage and the RBF table.
+//   direct half h (columns 32h .. 32h+31, 32 rows), box b = 0, 1 (16 columns each): stg + 4096 b + 128 row + ((8 (col & 15)) ^ (16 (row & 7)))
+//   mirror half ih (i-columns 16 ih .. +15), box jh = 0, 1 (32 j-rows each):          stg + 4096 jh + 128 (j & 31) + ((8 (i & 15)) ^ (16 (j & 7)))
 template <int EPI>
 __device__ __forceinline__ void gram_epilogue_staged(double (&acc)[4][8][2], const GramParams& p, const int64_t i0, const int64_t j0, const bool f1,
                                                      const bool f2, const uint32_t stg, const CUtensorMap* tmO, const int gi0w, const int gj0w,
-                                                     const int lane, const int pg, const int t) {
-  // the previous tile's stores must have finished reading the staging buffer
-  if (lane == 0) tma_store_wait_read();
-  __syncwarp();
+                                                     const int lane, const int pg, const int t, const Exp2Tab tab) {
+  constexpr bool STATS = EPI == EPI_DOT || EPI == EPI_IMQ;
   const double m2s = -2.0 * p.s;
-  // values in place (the common parameters only: DotProduct alpha = 2, RBF scale folded into the exponent)
+  // values in place (the common parameters only: DotProduct alpha = 2, RBF scale folded into the exponent), rows [8 m0, 8 m1)
+  auto values = [&](const int m0, const int m1) {
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) {
-    const double ri = (EPI != EPI_LINEAR) ? __ldg(p.ra + i0 + 8 * mt) : 0.0;
-    const double sa = (EPI == EPI_RBF) ? fma(p.s, ri, p.lnbeta) : (EPI == EPI_IMQ ? p.s * ri : ri);
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const double r = (EPI != EPI_LINEAR) ? __ldg(p.rb + j0 + 8 * nt + 4 * c) : 0.0;
-        double x = acc[mt][nt][c];
-        if (EPI == EPI_DOT) {
-          x = x * sa * r;
-          x = x * x;
-        } else if (EPI == EPI_RBF) {
-          x = exp_clamped(fma(x, m2s, fma(p.s, r, sa)));
-        } else if (EPI == EPI_IMQ) {
-          x = rsqrt(p.beta + fma(x, m2s, fma(p.s, r, sa)));
-        }
-        acc[mt][nt][c] = x;
-      }
-  }
-  if (f1) {
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+    for (int mt = 0; mt < 4; ++mt) {
+      if (mt < m0 || mt >= m1) continue;
+      const double ri = STATS ? __ldg(p.ra + i0 + 8 * mt) : 0.0;
+      const double sa = EPI == EPI_IMQ ? p.s * ri : ri;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const int col = 8 * nt + t + 4 * c;  // row = 8 mt + pg, row & 7 = pg
-          sts64(stg + (uint32_t)((col >> 4) * 4096 + (8 * mt + pg) * 128 + (((col & 15) << 3) ^ (pg << 4))), acc[mt][nt][c]);
+          const double r = STATS ? __ldg(p.rb + j0 + 8 * nt + 4 * c) : 0.0;
+          double x = acc[mt][nt][c];
+          if (EPI == EPI_DOT) {
+            x = x * sa * r;
+            x = x * x;
+          } else if (EPI == EPI_RBF) {
+            x = exp2_tab(x, tab);
+          } else if (EPI == EPI_IMQ) {
+            x = rsqrt(p.beta + fma(x, m2s, fma(p.s, r, sa)));
+          }
+          acc[mt][nt][c] = x;
         }
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-#pragma unroll
-      for (int b = 0; b < 4; ++b) tma_store_2d(tmO, stg + b * 4096, gj0w + 16 * b, gi0w);
-      tma_store_commit();
-      if (f2) tma_store_wait_read();
     }
+  };
+  // the staging buffer is free once the bulk stores issued from it have finished READING it
+  auto buffer_free = [&]() {
+    if (lane == 0) tma_store_wait_read();
     __syncwarp();
+  };
+  if (f1) {
+    values(0, 4);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      buffer_free();
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int nt = 4 * h + q;
+            const int col = 8 * nt + t + 4 * c;  // row = 8 mt + pg, row & 7 = pg
+            sts64(stg + (uint32_t)(((col >> 4) & 1) * 4096 + (8 * mt + pg) * 128 + (((col & 15) << 3) ^ (pg << 4))), acc[mt][nt][c]);
+          }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) tma_store_2d(tmO, stg + b * 4096, gj0w + 32 * h + 16 * b, gi0w);
+        tma_store_commit();
+      }
+      __syncwarp();
+    }
   }
   if (f2) {
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+    for (int ih = 0; ih < 2; ++ih) {
+      if (!f1) values(2 * ih, 2 * ih + 2);  // the second half's values are computed while the TMA unit reads the first
+      buffer_free();
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+      for (int m = 0; m < 2; ++m)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int il = 8 * mt + pg, jl = 8 * nt + t + 4 * c;  // jl & 7 = t + 4 c
-          sts64(stg + (uint32_t)((2 * (mt >> 1) + (nt >> 2)) * 4096 + (jl & 31) * 128 + (((il & 15) << 3) ^ ((t + 4 * c) << 4))), acc[mt][nt][c]);
-        }
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
+        for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int ih = 0; ih < 2; ++ih)
+          for (int c = 0; c < 2; ++c) {
+            const int mt = 2 * ih + m;
+            const int il = 8 * mt + pg, jl = 8 * nt + t + 4 * c;  // jl & 7 = t + 4 c
+            sts64(stg + (uint32_t)((nt >> 2) * 4096 + (jl & 31) * 128 + (((il & 15) << 3) ^ ((t + 4 * c) << 4))), acc[mt][nt][c]);
+          }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
 #pragma unroll
-        for (int jh = 0; jh < 2; ++jh) tma_store_2d(tmO, stg + (2 * ih + jh) * 4096, gi0w + 16 * ih, gj0w + 32 * jh);
-      tma_store_commit();
+        for (int jh = 0; jh < 2; ++jh) tma_store_2d(tmO, stg + jh * 4096, gi0w + 16 * ih, gj0w + 32 * jh);
+        tma_store_commit();
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -355,8 +402,8 @@ __device__ __forceinline__ void gram_epilogue_staged(double (&acc)[4][8][2], con
 //             KernelMatrix(F1, F2, k) against a handful of reference points): warps 8 (m) x 1, warp tile 16 x 32. A 128-wide tile
 //             would spend 128 / n2 times the DMMAs such a result needs; at n2 <= 32 the narrow tile is within 1.4 x of the HBM time of
 //             streaming the tall operand once.
-// TMAST = 1 (NARROW = 0 only): 3-stage operand ring + 8 x 16 KB staging buffers; interior off-diagonal tiles of a dense result leave
-//             through gram_epilogue_staged (tmO describes the output matrix with a 16 x 32 box). Used for shallow contractions.
+// TMAST = 1 (NARROW = 0 only): 4-stage operand ring + 8 x 8 KB staging buffers; interior off-diagonal tiles of a dense result leave
+//             through gram_epilogue_staged (tmO describes the output matrix with a 16 x 32 box).
 template <int EPI, int NARROW, int TMAST>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const GramParams p) {
@@ -370,7 +417,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + NSTAGE * 2 * GRAM_TILE_BYTES + (TMAST ? GRAM_STAGING_BYTES : 0);  // full[S] then empty[S], 8 bytes each
+  const uint32_t tab_base = smem_base + NSTAGE * 2 * GRAM_TILE_BYTES + (TMAST ? GRAM_STAGING_BYTES : 0);  // RBF: 2^(j/256) table, 16 replicas
+  const uint32_t bar_base = tab_base + (EPI == EPI_RBF ? EXP_TAB_BYTES : 0);  // full[S] then empty[S], 8 bytes each
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
 
@@ -383,6 +431,12 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(empty_bar(s), GRAM_CONSUMER_WARPS);
     }
     fence_barrier_init();
+  }
+  if (EPI == EPI_RBF) {  // the table is written once at pl_init: no dependence on the prelude kernel
+    for (int e = threadIdx.x; e < EXP_TAB_N * 8; e += GRAM_THREADS) {  // 128-bit store e covers lane slots 2 (e & 7), +1 of entry e >> 3
+      const double v = __ldg(p.exp_tab + (e >> 3));
+      asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(tab_base + 16u * e), "d"(v) : "memory");
+    }
   }
   __syncthreads();
   // Launched as a programmatic dependent of the prelude kernel (row statistics / centred copy): everything above overlaps its tail.
@@ -415,7 +469,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_arrive_expect_tx(full_bar(s), bytes);
           const uint32_t dstA = smem_base + s * 2 * GRAM_TILE_BYTES;
           tma_load_2d(dstA, &tmA, full_bar(s), kt * GRAM_BK, ti * BM);
-          if (!one_tile) tma_load_2d(dstA + GRAM_TILE_BYTES, &tmB, full_bar(s), kt * GRAM_BK, tj * BN);
+          if (!one_tile) tma_load_2d(dstA + GRAM_TILE_BYTES, &tmB, full_bar(s), kt * GRAM_BK + (kt == KT - 1 ? p.b_shift : 0), tj * BN);
         }
       }
     }
@@ -539,14 +593,14 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (TMAST && !NARROW && common && interior && !diag_tile && p.tma_out) {
       if constexpr (TMAST && !NARROW) {
         const uint32_t stg = smem_base + NSTAGE * 2 * GRAM_TILE_BYTES + warp * (GRAM_STAGING_BYTES / GRAM_CONSUMER_WARPS);
-        gram_epilogue_staged<EPI>(acc, p, i0, j0, f1, f2, stg, &tmO, ti * GRAM_BM + 32 * wm, tj * GRAM_BN + 64 * wn, lane, pg, t);
+        gram_epilogue_staged<EPI>(acc, p, i0, j0, f1, f2, stg, &tmO, ti * GRAM_BM + 32 * wm, tj * GRAM_BN + 64 * wn, lane, pg, t, Exp2Tab{tab_base + 8u * (lane & 15)});
       }
     } else if (!common) {
-      gram_epilogue<EPI, true, 0, MT, NT>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo);
+      gram_epilogue<EPI, true, 0, MT, NT>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo, Exp2Tab{tab_base + 8u * (lane & 15)});
     } else if (interior && !diag_tile) {
-      gram_epilogue<EPI, false, 2, MT, NT>(acc, p, i0, j0, 0, f1, f2m, prow, pcol, ldo);
+      gram_epilogue<EPI, false, 2, MT, NT>(acc, p, i0, j0, 0, f1, f2m, prow, pcol, ldo, Exp2Tab{tab_base + 8u * (lane & 15)});
     } else {
-      gram_epilogue<EPI, true, 2, MT, NT>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo);
+      gram_epilogue<EPI, true, 2, MT, NT>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo, Exp2Tab{tab_base + 8u * (lane & 15)});
     }
   }
   if (TMAST && lane == 0) tma_store_wait_all();  // the staging buffers must outlive the bulk stores that read them

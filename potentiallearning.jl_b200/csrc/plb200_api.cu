@@ -172,6 +172,7 @@ struct Ctx {
   uint64_t ws_gen = 0;  // bumped whenever a workspace slot is (re)allocated or freed: cached CUDA graphs hold workspace pointers
   HostStager stager;  // pinned staging ring + host threads for pageable host memory (hoststage.h)
   SyrkSchedCache sched;
+  void* exp_tab = nullptr;  // 2^(j/256) table of the RBF epilogue (gram.cuh exp2_tab), written once at context creation
   void* comm = nullptr;  // ncclComm_t of this device (pl_init_all: one per context; pl_comm_init_rank: context 0)
 };
 Ctx g_ctx[PL_MAX_DEV];
@@ -331,6 +332,7 @@ struct GramLaunch {
   double s, beta;
   int tcol_begin = -1, tcol_end = -1;  // column-range enumeration (host streaming path)
   int pdl = 0;                         // the launch directly follows the prelude kernel it depends on: programmatic dependent launch
+  int b_shift = 0;                     // RBF (augmented operands, prelude.cuh rbf_aug_kernel): the B operand's last k-step sits b_shift columns further right
 };
 
 // <<<>>> with the programmatic-dependent-launch attribute when pdl is set (the kernel then calls pdl_wait() before it touches what its
@@ -375,9 +377,13 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   const int BM = small ? 64 : GRAM_BM;
   const int BN = narrow ? 32 : (small ? 64 : GRAM_BN);
   CUtensorMap tmA, tmB;
-  PL_TRY(make_tmap_2d(&tmA, L.A, L.d, L.nA, L.ldA, GRAM_BK, BM));
-  PL_TRY(make_tmap_2d(&tmB, L.B, L.d, L.nB, L.ldB, GRAM_BK, BN));
+  PL_TRY(make_tmap_2d(&tmA, L.A, L.d + L.b_shift, L.nA, L.ldA, GRAM_BK, BM));
+  PL_TRY(make_tmap_2d(&tmB, L.B, L.d + L.b_shift, L.nB, L.ldB, GRAM_BK, BN));
   GramParams p;
+  p.b_shift = L.b_shift;
+  p.exp_tab = (const double*)g.exp_tab;
+
+  const int tab_smem = L.epi == EPI_RBF ? EXP_TAB_BYTES : 0;
   p.n1 = L.nA;
   p.n2 = L.nB;
   p.d = L.d;
@@ -426,7 +432,9 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   // Dense results of the DotProduct / IMQ / LINEAR kernels leave through the TMA-store variant (smem-staged epilogue): 9-16 % faster when
   // the contraction is shallow and the kernel is bound by writing K, still 1-2 % at d = 300. Needs an output the TMA unit can address
   // (16-byte aligned, even leading dimension). PLB200_GRAM_TMAST=0/1 overrides the rule (experiments).
-  // (not for RBF: its exp epilogue is tuned in groups of 8 interleaved chains in gram_epilogue and measured 3-6 % slower staged)
+  // Not for RBF: its epilogue is bound by instruction ISSUE (8 FP64 + ~8 integer / LDS instructions per element, two warps per
+  // sub-partition), and the staged form adds a shared-memory store and its address arithmetic per element: measured 3.70 vs 3.65 ms at
+  // config 2 (profiles/r02b_epi_probe2.json).
   bool tmast = !narrow && !small && !L.packed && L.epi != EPI_RBF && !(reinterpret_cast<uintptr_t>(L.out) & 15u) && !(L.ldo & 1);
   if (const char* e = getenv("PLB200_GRAM_TMAST")) {
     if (e[0] == '0') tmast = false;
@@ -449,20 +457,20 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
     default: return set_err(PL_EINVAL, "unknown epilogue %d", L.epi);                                                                        \
   }
   if (narrow) {
-    GRAM_LAUNCH(1, 0, GRAM_SMEM_BYTES, grid, pdl, tmA, tmB, p)
+    GRAM_LAUNCH(1, 0, GRAM_SMEM_BYTES + tab_smem, grid, pdl, tmA, tmB, p)
   } else if (small) {
-    GRAM_LAUNCH(2, 0, GRAM_SMEM_BYTES, grid, pdl, tmA, tmB, p)
+    GRAM_LAUNCH(2, 0, GRAM_SMEM_BYTES + tab_smem, grid, pdl, tmA, tmB, p)
   } else if (tmast) {
-    GRAM_LAUNCH(0, 1, GRAM_SMEM_BYTES_TMAST, grid, pdl, tmA, tmB, p)
+    GRAM_LAUNCH(0, 1, GRAM_SMEM_BYTES_TMAST + tab_smem, grid, pdl, tmA, tmB, p)
   } else {
-    GRAM_LAUNCH(0, 0, GRAM_SMEM_BYTES, grid, pdl, tmA, tmB, p)
+    GRAM_LAUNCH(0, 0, GRAM_SMEM_BYTES + tab_smem, grid, pdl, tmA, tmB, p)
   }
   CUDA_TRY(le);
   LAUNCH_CHECK();
   if (tail_r) {
     CUtensorMap tmA64, tmB64;
-    PL_TRY(make_tmap_2d(&tmA64, L.A, L.d, L.nA, L.ldA, GRAM_BK, 64));
-    PL_TRY(make_tmap_2d(&tmB64, L.B, L.d, L.nB, L.ldB, GRAM_BK, 64));
+    PL_TRY(make_tmap_2d(&tmA64, L.A, L.d + L.b_shift, L.nA, L.ldA, GRAM_BK, 64));
+    PL_TRY(make_tmap_2d(&tmB64, L.B, L.d + L.b_shift, L.nB, L.ldB, GRAM_BK, 64));
     GramParams pt = p;
     pt.T1 = (int)((L.nA + 63) / 64);
     pt.T2 = (int)((L.nB + 63) / 64);
@@ -472,7 +480,7 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
     const bool tpdl = !getenv("PLB200_NO_PDL");  // directly behind the main launch: its prologue overlaps the main kernel's last wave
     pt.pdl = tpdl ? 1 : 0;
     const int tgrid = (int)(4 * (int64_t)tail_r < g.num_sms ? 4 * tail_r : g.num_sms);
-    GRAM_LAUNCH(2, 0, GRAM_SMEM_BYTES, tgrid, tpdl, tmA64, tmB64, pt)
+    GRAM_LAUNCH(2, 0, GRAM_SMEM_BYTES + tab_smem, tgrid, tpdl, tmA64, tmB64, pt)
     CUDA_TRY(le);
     LAUNCH_CHECK();
   }
@@ -571,16 +579,88 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
     const int64_t ns = (n1 + stride - 1) / stride;
     PL_TRY(colsum(X1, ns, d, l1 * stride, (double)ns, (double*)mean, st));
   }
+  if (kernel_id == PL_KERNEL_RBF) {
+    // RBF: operands in the augmented, pre-scaled layout (prelude.cuh rbf_aug_kernel): the accumulator of the Gram kernel is the
+    // argument of 2^(./256) itself, the epilogue is exp2_tab and nothing else (gram.cuh)
+    const int KT = (int)((d + GRAM_AUG_COLS + GRAM_BK - 1) / GRAM_BK);
+    const int64_t lda = 16 * (int64_t)KT + 16;
+    const double Lc = (double)EXP_TAB_N * 1.4426950408889634074;  // 256 log2(e)
+    const double cs = sqrt(Lc) / fabs(ell);
+    const double hb = beta > 0.0 ? 0.5 * Lc * log(beta) : 0.0;  // beta <= 0 cannot be folded into the exponent: epilogue multiplies (bmul)
+    PL_TRY(ws_get(WS_XC1, (size_t)n1 * lda * 8, &xc1));
+    if (!sym) PL_TRY(ws_get(WS_XC2, (size_t)n2 * lda * 8, &xc2));
+    L.epi = EPI_RBF;
+    L.pdl = 1;
+    L.s = -0.5 / (ell * ell);
+    L.beta = beta;
+    L.d = 16 * (int64_t)KT;
+    L.b_shift = 16;
+    L.same_operand = 0;  // the two operands of a diagonal tile differ in their last k-step
+    L.ldA = L.ldB = lda;
+    auto aug = [&](int mode, const double* X, int64_t n, int64_t ldx, const double* cd, double* Xc, double* Y) -> int {
+      if (n == 0) return PL_OK;
+      const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+      switch (mode) {
+        case AUG_ID: rbf_aug_kernel<AUG_ID><<<blocks, 256, 0, st>>>(X, n, d, ldx, (const double*)mean, cd, Xc, Y, KT, cs, hb); break;
+        case AUG_DIAG: rbf_aug_kernel<AUG_DIAG><<<blocks, 256, 0, st>>>(X, n, d, ldx, (const double*)mean, cd, Xc, Y, KT, cs, hb); break;
+        case AUG_CENTER: rbf_aug_kernel<AUG_CENTER><<<blocks, 256, 0, st>>>(X, n, d, ldx, (const double*)mean, cd, Xc, Y, KT, cs, hb); break;
+        default: rbf_aug_kernel<AUG_FINISH><<<blocks, 256, 0, st>>>(X, n, d, ldx, (const double*)mean, cd, Xc, Y, KT, cs, hb); break;
+      }
+      LAUNCH_CHECK();
+      return PL_OK;
+    };
+    if (cinv_kind == PL_CINV_IDENTITY) {
+      PL_TRY(aug(AUG_ID, X1, n1, l1, nullptr, (double*)xc1, nullptr));
+      if (!sym) PL_TRY(aug(AUG_ID, X2, n2, l2, nullptr, (double*)xc2, nullptr));
+      L.A = (double*)xc1;
+    } else {
+      PL_TRY(ws_get(WS_Y1, (size_t)n1 * lda * 8, &y1));
+      if (!sym) PL_TRY(ws_get(WS_Y2, (size_t)n2 * lda * 8, &y2));
+      if (cinv_kind == PL_CINV_DIAGONAL) {
+        const double* cd;
+        int64_t ldcd;
+        PL_TRY(tma_operand(dcinv, 1, d, ldc, WS_PADC, st, &cd, &ldcd));
+        PL_TRY(aug(AUG_DIAG, X1, n1, l1, cd, (double*)xc1, (double*)y1));
+        if (!sym) PL_TRY(aug(AUG_DIAG, X2, n2, l2, cd, (double*)xc2, (double*)y2));
+      } else {
+        // Y = Xc * Cinv through the same DMMA Gram engine (Cinv symmetric: rows of Cinv are its columns), then the row terms
+        const double* cf;
+        int64_t ldcf;
+        PL_TRY(tma_operand(dcinv, d, d, d, WS_PADC, st, &cf, &ldcf));
+        for (int side = 0; side < (sym ? 1 : 2); ++side) {
+          const double* X = side ? X2 : X1;
+          const int64_t n = side ? n2 : n1, lx = side ? l2 : l1;
+          double* xc = (double*)(side ? xc2 : xc1);
+          double* y = (double*)(side ? y2 : y1);
+          PL_TRY(aug(AUG_CENTER, X, n, lx, nullptr, xc, nullptr));
+          GramLaunch Ly{};
+          Ly.epi = EPI_LINEAR;
+          Ly.A = xc; Ly.nA = n; Ly.ldA = lda;
+          Ly.B = cf; Ly.nB = d; Ly.ldB = ldcf;
+          Ly.d = d;
+          Ly.out = y; Ly.ldo = lda;
+          Ly.nparts = 1;
+          PL_TRY(launch_gram(Ly, st));
+          PL_TRY(aug(AUG_FINISH, nullptr, n, 0, nullptr, xc, y));
+        }
+      }
+      L.A = (double*)y1;
+    }
+    L.B = sym ? (double*)xc1 : (double*)xc2;
+    if (prepared) { *prepared = L; return PL_OK; }
+    return launch_gram(L, st);
+  }
+  // InverseMultiquadric: row statistics in the epilogue
   PL_TRY(ws_get(WS_XC1, (size_t)n1 * ldc * 8, &xc1));
   PL_TRY(ws_get(WS_STAT1, (size_t)n1 * 8, &s1));
   if (!sym) {
     PL_TRY(ws_get(WS_XC2, (size_t)n2 * ldc * 8, &xc2));
     PL_TRY(ws_get(WS_STAT2, (size_t)n2 * 8, &s2));
   }
-  L.epi = kernel_id == PL_KERNEL_IMQ ? EPI_IMQ : EPI_RBF;
+  L.epi = EPI_IMQ;
   L.pdl = 1;  // follows prep_rows / rowdot: barrier set-up and descriptor prefetch overlap its tail
-  L.s = kernel_id == PL_KERNEL_IMQ ? 1.0 / (ell * ell) : -0.5 / (ell * ell);
-  L.beta = beta;  // RBF: beta ; IMQ: c2
+  L.s = 1.0 / (ell * ell);
+  L.beta = beta;  // c2
   L.ra = (double*)s1;
   L.rb = sym ? (double*)s1 : (double*)s2;
   if (cinv_kind == PL_CINV_IDENTITY) {
@@ -1327,10 +1407,10 @@ int ctx_create(int idx, int device) {
   for (auto& ev : c.ev) CUDA_TRY(cudaEventCreate(&ev));
   for (auto& ev : c.chunk_ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 #define GRAM_ATTR(EPI_)                                                                                                                  \
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));                 \
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));                 \
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));                 \
-  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES_TMAST));
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES + (EPI_ == EPI_RBF ? EXP_TAB_BYTES : 0))); \
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES + (EPI_ == EPI_RBF ? EXP_TAB_BYTES : 0))); \
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES + (EPI_ == EPI_RBF ? EXP_TAB_BYTES : 0))); \
+  CUDA_TRY(cudaFuncSetAttribute(gram_kernel<EPI_, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES_TMAST + (EPI_ == EPI_RBF ? EXP_TAB_BYTES : 0)));
   GRAM_ATTR(EPI_LINEAR)
   GRAM_ATTR(EPI_DOT)
   GRAM_ATTR(EPI_RBF)
@@ -1338,6 +1418,13 @@ int ctx_create(int idx, int device) {
 #undef GRAM_ATTR
   CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(syrk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM_BYTES));
+  {
+    // correctly rounded 2^(j/256): long double exp2l carries 64 bits, the rounding to double is the only error (<= 0.5 ulp)
+    std::vector<double> tab(EXP_TAB_N);
+    for (int j = 0; j < EXP_TAB_N; ++j) tab[j] = (double)exp2l((long double)j / (long double)EXP_TAB_N);
+    CUDA_TRY(cudaMalloc(&c.exp_tab, EXP_TAB_N * 8));
+    CUDA_TRY(cudaMemcpy(c.exp_tab, tab.data(), EXP_TAB_N * 8, cudaMemcpyHostToDevice));
+  }
   c.ready = true;
   return PL_OK;
 }
@@ -1360,6 +1447,8 @@ void ctx_destroy(int idx) {
     if (ev) cudaEventDestroy(ev);
     ev = nullptr;
   }
+  if (c.exp_tab) cudaFree(c.exp_tab);
+  c.exp_tab = nullptr;
   c.stager.shutdown();
   gram_graphs_clear(idx);
   if (c.sched.ready) cudaEventDestroy(c.sched.ready);

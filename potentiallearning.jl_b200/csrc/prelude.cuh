@@ -150,6 +150,89 @@ __global__ void prep_rows_kernel(const double* __restrict__ X, int64_t n, int64_
   }
 }
 
+// ---- RBF operands in the AUGMENTED layout (consumed by gram_kernel<EPI_RBF>, gram.cuh exp2_tab) ----
+// The RBF epilogue wants y_ij = L (-0.5 d2_ij / ell^2 + ln beta), L = 256 log2(e), straight out of the accumulator. With
+//   x~ = c (x - mean), c = sqrt(L) / |ell|,   q~_i = x~_i' Cinv x~_i,   u_i = -q~_i / 2 + h,  h = L ln(beta) / 2
+// that is  y_ij = (Cinv x~_i) . x~_j + u_i * 1 + 1 * u_j : a contraction over d + 2 columns. One warp per row writes
+//   cols [0, d)               the row (x~ for Xc, y~ = Cinv x~ for Y)
+//   cols [d, 16 KT - 2)       0                                   KT = ceil((d + 2) / 16) k-steps, ld = 16 KT + 16
+//   cols 16 KT - 2, 16 KT - 1 (u, 1)                              what the A operand contracts in its last k-step
+//   cols [16 KT, 16 KT + 16)  the last 16-column block again, ending in (1, u): what the B operand reads as ITS last k-step
+//                             (GramParams::b_shift = 16), so one buffer serves as both operands of a symmetric matrix.
+// q~ is summed over the ROUNDED x~ so that identical rows give d2 = 0 up to the accumulation order. (kernels.jl:73-74, distances.jl:58-60)
+enum { AUG_ID = 0, AUG_DIAG = 1, AUG_CENTER = 2, AUG_FINISH = 3 };
+
+// tail of one row buffer: zero padding, (u, 1), and the shifted block with (1, u). `row` points at the row (ld = 16 KT + 16 doubles);
+// lanes 0..15 own the columns of the last block, lane 16 the (at most one) padding column in front of it.
+__device__ __forceinline__ void rbf_aug_tail(double* __restrict__ row, const int64_t d, const int KT, const double u, const int lane) {
+  const int64_t b0 = 16 * (int64_t)(KT - 1);
+  if (lane < 16) {
+    const int64_t col = b0 + lane;
+    const double v = col < d ? row[col] : 0.0;  // written by this warp before (__syncwarp in the caller)
+    if (col >= d) row[col] = lane == 14 ? u : (lane == 15 ? 1.0 : 0.0);
+    row[b0 + 16 + lane] = lane == 14 ? 1.0 : (lane == 15 ? u : v);
+  } else if (lane == 16 && d < b0) {
+    row[d] = 0.0;  // d == 16 (KT - 1) - 1: the only padding column outside the last block
+  }
+}
+
+template <int MODE>
+__global__ void rbf_aug_kernel(const double* __restrict__ X, int64_t n, int64_t d, int64_t ldx, const double* __restrict__ mean,
+                               const double* __restrict__ cdiag, double* __restrict__ Xc, double* __restrict__ Y, int KT, double c, double h) {
+  pdl_launch_dependents();  // the Gram kernel that follows may start its prologue now
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const int64_t ld = 16 * (int64_t)KT + 16;
+  double* const xc = Xc + row * ld;
+  double* const y = (MODE == AUG_DIAG || MODE == AUG_FINISH) ? Y + row * ld : nullptr;
+  double acc = 0.0;
+  if (MODE == AUG_FINISH) {
+    for (int64_t k = lane; k < d; k += 32) acc = fma(y[k], xc[k], acc);
+  } else {
+    const double* x = X + row * ldx;
+    const int64_t dpair = d & ~(int64_t)1;
+    for (int64_t k = 2 * lane; k < dpair; k += 64) {
+      double2 v = __ldg(reinterpret_cast<const double2*>(x + k));
+      const double2 m = __ldg(reinterpret_cast<const double2*>(mean + k));
+      v.x = (v.x - m.x) * c;
+      v.y = (v.y - m.y) * c;
+      *reinterpret_cast<double2*>(xc + k) = v;
+      if (MODE == AUG_ID) {
+        acc = fma(v.x, v.x, acc);
+        acc = fma(v.y, v.y, acc);
+      } else if (MODE == AUG_DIAG) {
+        const double2 cd = __ldg(reinterpret_cast<const double2*>(cdiag + k));
+        double2 w;
+        w.x = v.x * cd.x;
+        w.y = v.y * cd.y;
+        *reinterpret_cast<double2*>(y + k) = w;
+        acc = fma(w.x, v.x, acc);
+        acc = fma(w.y, v.y, acc);
+      }
+    }
+    if ((d & 1) && lane == 0) {
+      const int64_t k = d - 1;
+      const double v = (__ldg(x + k) - mean[k]) * c;
+      xc[k] = v;
+      if (MODE == AUG_ID) acc = fma(v, v, acc);
+      else if (MODE == AUG_DIAG) {
+        const double w = v * cdiag[k];
+        y[k] = w;
+        acc = fma(w, v, acc);
+      }
+    }
+  }
+  if constexpr (MODE != AUG_CENTER) {  // AUG_CENTER: Y = Xc Cinv by the Gram engine next, then AUG_FINISH
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    const double u = fma(-0.5, acc, h);
+    __syncwarp();
+    rbf_aug_tail(xc, d, KT, u, lane);
+    if (MODE == AUG_DIAG || MODE == AUG_FINISH) rbf_aug_tail(y, d, KT, u, lane);
+  }
+}
+
 // stat[i] = sum_k Y[i][k] * Xc[i][k]  (quadratic form x' Cinv x with Y = Xc Cinv); one warp per row
 __global__ void rowdot_kernel(const double* __restrict__ Y, const double* __restrict__ Xc, int64_t n, int64_t d, int64_t ld, double* __restrict__ stat) {
   const int lane = threadIdx.x & 31;

@@ -84,6 +84,12 @@ template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ void sts32_volatile(uint32_t addr, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
   double2 v;
   asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));

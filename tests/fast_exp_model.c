@@ -1,45 +1,53 @@
-/* CPU restatement of exp_fast / exp_clamped (csrc/gram.cuh) with the same operation order and fma contraction points,
- * so that its accuracy can be pinned without a GPU (tests/test_fast_exp.py compiles this with gcc -mfma). */
+/* CPU restatement of exp2_tab (csrc/gram.cuh), the whole RBF epilogue: 2^(y/256) with a 256-entry table of 2^(j/256), exact
+ * reduction by the magic-number add, e^z - 1 = z + z^2 (b0 + b1 z + b2 z^2) on |z| <= ln2/512, exponent-field add and the integer
+ * clamp of N — same operation order and fma contraction points, so that its accuracy can be pinned without a GPU
+ * (tests/test_fast_exp.py compiles this with gcc -mfma). The table is built as in ctx_create (plb200_api.cu): exp2l rounded to double. */
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
 
-static const double EXP_C[18] = {
-    6755399441055744.0, 1.4426950408889634, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
-    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
-    1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+#define TAB_BITS 8
+#define TAB_N (1 << TAB_BITS)
+static double TAB[TAB_N];
+static int tab_ready = 0;
+static const double EXP2_C[5] = {6755399441055744.0, 0.0027076061740622863, 3.6655655969101062e-06, 3.308302907918888e-09, 2.239395293483284e-12};
 
-static double exp_fast(double x) {
-  const double t = fma(x, EXP_C[1], EXP_C[0]);
+static void tab_init(void) {
+  if (tab_ready) return;
+  for (int j = 0; j < TAB_N; ++j) TAB[j] = (double)exp2l((long double)j / (long double)TAB_N);
+  tab_ready = 1;
+}
+
+/* 2^(y/256) */
+double exp2_tab_model(double y) {
+  tab_init();
+  const double t = y + EXP2_C[0];
   int64_t bits;
   memcpy(&bits, &t, 8);
-  const int n = (int)(bits & 0xffffffff);
-  const double nd = t - EXP_C[0];
-  double r = fma(nd, EXP_C[2], x);
-  r = fma(nd, EXP_C[3], r);
-  double p = EXP_C[4];
-  for (int k = 5; k < 18; ++k) p = fma(p, r, EXP_C[k]);
-  memcpy(&bits, &p, 8);
-  bits += ((int64_t)n) << 52;
-  memcpy(&p, &bits, 8);
-  return p;
+  int N = (int)(bits & 0xffffffff);
+  if (N < -1022 * TAB_N) N = -1022 * TAB_N; /* keeps the exponent field in range: results below 2^-1022 come out as <= 2^-1021 */
+  const double r = y - (t - EXP2_C[0]);
+  const double T = TAB[N & (TAB_N - 1)];
+  double q = fma(r, EXP2_C[4], EXP2_C[3]);
+  q = fma(q, r, EXP2_C[2]);
+  q = fma(q, r, EXP2_C[1]);
+  double e = fma(T * r, q, T);
+  memcpy(&bits, &e, 8);
+  bits += ((int64_t)(N >> TAB_BITS)) << 52;
+  memcpy(&e, &bits, 8);
+  return e;
 }
 
-double exp_clamped_model(double x) {
-  const double e = exp_fast(x);
-  uint64_t bits;
-  memcpy(&bits, &x, 8);
-  const int tiny = (uint32_t)(bits >> 32) >= 0xC0862000u; /* x <= -708.0 (or NaN with the sign bit): integer compare as in the kernel */
-  return tiny ? 0.0 : e;
-}
+/* the scale the prelude folds into the operands: y = 256 log2(e) x */
+double exp2_scale(void) { return 256.0 * 1.4426950408889634074; }
 
-/* max relative error against long double expl over n points uniformly spread on [lo, hi] */
-double exp_model_max_rel_err(double lo, double hi, int64_t n) {
+/* max relative error against long double exp2l over n points y uniformly spread on [lo, hi] (y in units of 1/256 octave) */
+double exp2_model_max_rel_err(double lo, double hi, int64_t n) {
   double worst = 0.0;
   for (int64_t i = 0; i < n; ++i) {
-    const double x = lo + (hi - lo) * ((double)i + 0.37) / (double)n;
-    const long double ref = expl((long double)x);
-    const double rel = fabs((double)(((long double)exp_clamped_model(x) - ref) / ref));
+    const double y = lo + (hi - lo) * ((double)i + 0.37) / (double)n;
+    const long double ref = exp2l((long double)y / (long double)TAB_N);
+    const double rel = fabs((double)(((long double)exp2_tab_model(y) - ref) / ref));
     if (rel > worst) worst = rel;
   }
   return worst;
