@@ -588,7 +588,7 @@ def main():
     flops_launch = flops / world  # tiles are dealt evenly; per-launch algorithmic flops of this rank
     achieved = flops_launch / (main_ms_per_step * 1e-3) / 1e12
     traffic, traffic_source = None, None
-    for name in ("r02_gram_rbf_ncu_summary.json", "r01_gram_rbf_ncu_summary.json"):
+    for name in ("r02c_gram_rbf_ncu_summary.json", "r02_gram_rbf_ncu_summary.json", "r01_gram_rbf_ncu_summary.json"):
         prof = os.path.join(ROOT, "profiles", name)
         if os.path.exists(prof):
             try:
