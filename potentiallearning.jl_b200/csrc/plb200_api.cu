@@ -573,11 +573,12 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
   const int64_t ldc = (d + 1) & ~(int64_t)1;
   PL_TRY(ws_get(WS_MEAN, (size_t)ldc * 8, &mean));
   {
-    // any shift near the centre of the data removes the cancellation: the mean of a strided sample of <= 4096 rows (a full column-mean
-    // pass costs 26 us of the 600 us an 8-GPU shard of config 2 takes). Same sample on every rank -> same shift -> same bits.
-    const int64_t stride = (n1 + 4095) / 4096;
+    // any shift near the centre of the data removes the cancellation: the mean of a strided sample of <= 512 rows, one small launch
+    // (a full column-mean pass costs 26 us of the 530 us an 8-GPU shard of config 2 takes). Same sample on every rank -> same shift -> same bits.
+    const int64_t stride = (n1 + 511) / 512;
     const int64_t ns = (n1 + stride - 1) / stride;
-    PL_TRY(colsum(X1, ns, d, l1 * stride, (double)ns, (double*)mean, st));
+    sample_mean_kernel<<<(unsigned)((d + 31) / 32), 1024, 0, st>>>(X1, ns, l1 * stride, d, (double*)mean);
+    LAUNCH_CHECK();
   }
   if (kernel_id == PL_KERNEL_RBF) {
     // RBF: operands in the augmented, pre-scaled layout (prelude.cuh rbf_aug_kernel): the accumulator of the Gram kernel is the
@@ -599,13 +600,19 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
     L.ldA = L.ldB = lda;
     auto aug = [&](int mode, const double* X, int64_t n, int64_t ldx, const double* cd, double* Xc, double* Y) -> int {
       if (n == 0) return PL_OK;
-      const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+      const int blocks = (int)((n * 32 + 255) / 256);
+      // an ordinary launch: as a programmatic dependent of sample_mean_kernel it measured no gain on plain launches and cost 30 us inside the
+      // cached CUDA graph of a tile-packed shard with its tail launch (profiles/r02c notes)
+      const bool apdl = getenv("PLB200_AUG_PDL") != nullptr;
+      const double* mn = (const double*)mean;
+      cudaError_t le;
       switch (mode) {
-        case AUG_ID: rbf_aug_kernel<AUG_ID><<<blocks, 256, 0, st>>>(X, n, d, ldx, (const double*)mean, cd, Xc, Y, KT, cs, hb); break;
-        case AUG_DIAG: rbf_aug_kernel<AUG_DIAG><<<blocks, 256, 0, st>>>(X, n, d, ldx, (const double*)mean, cd, Xc, Y, KT, cs, hb); break;
-        case AUG_CENTER: rbf_aug_kernel<AUG_CENTER><<<blocks, 256, 0, st>>>(X, n, d, ldx, (const double*)mean, cd, Xc, Y, KT, cs, hb); break;
-        default: rbf_aug_kernel<AUG_FINISH><<<blocks, 256, 0, st>>>(X, n, d, ldx, (const double*)mean, cd, Xc, Y, KT, cs, hb); break;
+        case AUG_ID: le = launch_ex(rbf_aug_kernel<AUG_ID>, blocks, 256, 0, st, apdl, X, n, d, ldx, mn, cd, Xc, Y, KT, cs, hb); break;
+        case AUG_DIAG: le = launch_ex(rbf_aug_kernel<AUG_DIAG>, blocks, 256, 0, st, apdl, X, n, d, ldx, mn, cd, Xc, Y, KT, cs, hb); break;
+        case AUG_CENTER: le = launch_ex(rbf_aug_kernel<AUG_CENTER>, blocks, 256, 0, st, apdl, X, n, d, ldx, mn, cd, Xc, Y, KT, cs, hb); break;
+        default: le = launch_ex(rbf_aug_kernel<AUG_FINISH>, blocks, 256, 0, st, apdl, X, n, d, ldx, mn, cd, Xc, Y, KT, cs, hb); break;
       }
+      CUDA_TRY(le);
       LAUNCH_CHECK();
       return PL_OK;
     };

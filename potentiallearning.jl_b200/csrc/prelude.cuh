@@ -84,6 +84,36 @@ __global__ void colsum_final_kernel(const double* __restrict__ partial, int64_t 
   }
 }
 
+// out[col] = mean over the ns sample rows 0, stride, 2 stride, ... of column col: the SHIFT of the distance kernels (any point near the
+// centre of the data removes the cancellation of the Gram form against |mean|^2; distances are translation invariant). ONE launch:
+// block = 32 columns x 32 row lanes, lane rl sums sample rows rl, rl + 32, ... with four loads in flight (the pass is latency bound: every
+// sample row is its own DRAM page), the 32 lane sums are added in fixed order — deterministic, the same on every rank. ~5 us for
+// ns <= 512 (the two-launch colsum pass over 4096 rows took 17 us of the 530 us an 8-GPU shard of config 2 takes).
+__global__ void __launch_bounds__(1024) sample_mean_kernel(const double* __restrict__ X, int64_t ns, int64_t stride_elems, int64_t d, double* __restrict__ out) {
+  pdl_launch_dependents();  // the operand kernel that follows may start its prologue; it waits (pdl_wait) before it reads the mean
+  __shared__ double sh[32][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + cl;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (c < d) {
+    int64_t r = rl;
+    for (; r + 96 < ns; r += 128) {
+      const double v0 = __ldg(X + r * stride_elems + c), v1 = __ldg(X + (r + 32) * stride_elems + c);
+      const double v2 = __ldg(X + (r + 64) * stride_elems + c), v3 = __ldg(X + (r + 96) * stride_elems + c);
+      s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+    }
+    for (; r < ns; r += 32) s0 += __ldg(X + r * stride_elems + c);
+  }
+  sh[rl][cl] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (rl == 0 && c < d) {
+    double tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) tot += sh[k][cl];
+    out[c] = tot / (double)ns;
+  }
+}
+
 enum { PREP_DOT = 0, PREP_RBF_ID = 1, PREP_RBF_DIAG = 2, PREP_CENTER_ONLY = 3 };
 
 // One warp per row.
@@ -180,6 +210,7 @@ template <int MODE>
 __global__ void rbf_aug_kernel(const double* __restrict__ X, int64_t n, int64_t d, int64_t ldx, const double* __restrict__ mean,
                                const double* __restrict__ cdiag, double* __restrict__ Xc, double* __restrict__ Y, int KT, double c, double h) {
   pdl_launch_dependents();  // the Gram kernel that follows may start its prologue now
+  pdl_wait();               // launched as a programmatic dependent of the kernel that writes `mean` (no-op otherwise)
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;

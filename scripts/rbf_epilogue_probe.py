@@ -28,6 +28,23 @@ def run(kid, n, d, fill, reps=8):
         e1.record(); torch.cuda.synchronize()
         if r >= 2: ts.append(e0.elapsed_time(e1))
     return {"ms_median": float(np.median(ts)), "ms_min": float(np.min(ts)), "checksum": float(K.sum().item())}
+def run_packed(kid, n, d, nparts, reps=8):
+    rng = np.random.default_rng(1002)
+    X = torch.as_tensor(2.0 * rng.standard_normal(d) + rng.standard_normal((n, d)) / np.sqrt(96.0), device="cuda")
+    nt = int(lib.pl_gram_tile_count(n, 0, 0, nparts))
+    K = torch.zeros((nt, 128, 128), device="cuda", dtype=torch.float64)
+    ts = []
+    for r in range(reps + 2):
+        flush.fill_(r & 1)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.pl_gram_dev(kid, X.data_ptr(), n, d, None, 0, 0, d, 2, 0, None, 1.0, 1.0, K.data_ptr(), 128, _lib.PL_FILL_FULL, 0, nparts, 1, st), "gram")
+        e1.record(); torch.cuda.synchronize()
+        if r >= 2: ts.append(e0.elapsed_time(e1))
+    return {"ms_median": float(np.median(ts)), "ms_min": float(np.min(ts)), "tiles": nt, "checksum": float(K.sum().item())}
+out["rbf_c2_packed_1part"] = run_packed(_lib.PL_KERNEL_RBF, 20000, 300, 1)
+out["rbf_c2_packed_8part"] = run_packed(_lib.PL_KERNEL_RBF, 20000, 300, 8)
+out["dot_c2_packed_1part"] = run_packed(_lib.PL_KERNEL_DOT, 20000, 300, 1)
 out["rbf_c2_U"] = run(_lib.PL_KERNEL_RBF, 20000, 300, _lib.PL_FILL_JULIA_U)
 out["rbf_c2_full"] = run(_lib.PL_KERNEL_RBF, 20000, 300, _lib.PL_FILL_FULL)
 out["rbf_n8000_d26_U"] = run(_lib.PL_KERNEL_RBF, 8000, 26, _lib.PL_FILL_JULIA_U)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One GPU's share of config 2 strong-scaled over 8 GPUs (part 0 of 8: 1551 packed tiles = 10.48 waves), timed on ONE GPU exactly as bench.py
-times a step: the effect of the tail-wave sub-tiles, the cached CUDA graph and PDL on the step. Writes gpurun_out/r02_shard_step_probe.json."""
+times a step: the effect of the tail-wave sub-tiles, the cached CUDA graph and PDL on the step. Writes gpurun_out/r02c_shard_step_probe.json."""
 import json
 import os
 import sys
@@ -51,9 +51,9 @@ for nparts in (8, 4, 2):
                 e1.synchronize()
                 ts.append(e0.elapsed_time(e1))
             row = {"nparts": nparts, "tiles": nt, "waves": round(nt / 148, 2), "tail_subtiles": tail, "cuda_graph": graph, "ms_mean": round(float(np.mean(ts)), 4),
-                   "ms_min": round(min(ts), 4), "strong_scaling_eff_vs_3.853ms": round(3.853 / (nparts * float(np.mean(ts))), 4)}
+                   "ms_min": round(min(ts), 4), "strong_scaling_eff_vs_3.652ms": round(3.652 / (nparts * float(np.mean(ts))), 4)}
             res.append(row)
             print(row, flush=True)
 os.environ.pop("PLB200_GRAM_NO_TAIL", None)
 os.environ.pop("PLB200_NO_GRAPH", None)
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", "r02_shard_step_probe.json"), "w"), indent=1)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "r02c_shard_step_probe.json"), "w"), indent=1)
