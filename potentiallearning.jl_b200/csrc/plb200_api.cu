@@ -1366,6 +1366,14 @@ int gram_sym_stream(int kernel_id, const double* d1, int64_t n1, int64_t l1, int
   PL_TRY(gram_dev_impl(kernel_id, d1, n1, l1, nullptr, n1, 0, d, alpha, cinv_kind, dc, ell, beta, dK, ldo, PL_FILL_RM_LOWER, 0, 1, 0, g.stream, &L));
   const int nch = c_hi - c_lo;
   if (nch > 12) return set_err(PL_EINVAL, "too many chunks per device");
+  // PLB200_STREAM_TRACE=1: when each range's kernel and each range's copy finished, in ms after the first launch, on stderr
+  const bool trace = getenv("PLB200_STREAM_TRACE") != nullptr;
+  cudaEvent_t tk[12] = {}, tc[12] = {};
+  if (trace)
+    for (int c = 0; c < nch; ++c) {
+      CUDA_TRY(cudaEventCreate(&tk[c]));
+      CUDA_TRY(cudaEventCreate(&tc[c]));
+    }
   for (int c = 0; c < nch; ++c) {
     if (bounds[c_lo + c + 1] > bounds[c_lo + c]) {
       L.tcol_begin = bounds[c_lo + c];
@@ -1373,6 +1381,7 @@ int gram_sym_stream(int kernel_id, const double* d1, int64_t n1, int64_t l1, int
       PL_TRY(launch_gram(L, g.stream));
     }
     CUDA_TRY(cudaEventRecord(g.chunk_ev[c], g.stream));
+    if (trace) CUDA_TRY(cudaEventRecord(tk[c], g.stream));
   }
   CUDA_TRY(cudaEventRecord(g.ev[2], g.stream));
   const bool stage_out = staging_for(K, (size_t)n1 * n1 * 4);
@@ -1386,10 +1395,24 @@ int gram_sym_stream(int kernel_id, const double* d1, int64_t n1, int64_t l1, int
       else
         CUDA_TRY(cudaMemcpy2DAsync(K + r0 * ldk, (size_t)ldk * 8, dK + r0 * ldo, (size_t)ldo * 8, (size_t)r1 * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, g.copy_stream));
     }
+    if (trace) CUDA_TRY(cudaEventRecord(tc[c], g.copy_stream));
   }
   if (stage_out) CUDA_TRY(g_stager.finish());
   CUDA_TRY(cudaEventRecord(g.ev[3], g.copy_stream));
   CUDA_TRY(cudaStreamSynchronize(g.copy_stream));
+  if (trace) {
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    fprintf(stderr, "[plb200 stream trace] range: kernel done / copy done (ms after the first launch):");
+    for (int c = 0; c < nch; ++c) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, g.ev[1], tk[c]);
+      cudaEventElapsedTime(&b, g.ev[1], tc[c]);
+      fprintf(stderr, " %d: %.2f / %.2f;", c, a, b);
+      cudaEventDestroy(tk[c]);
+      cudaEventDestroy(tc[c]);
+    }
+    fprintf(stderr, "\n");
+  }
   return finish_timing();
 }
 

@@ -239,6 +239,32 @@ def test_rbf_extreme_arguments(pl, orc):
         assert np.all(np.isfinite(K))
 
 
+def test_rbf_scale_sign_size_and_nan(pl, orc):
+    """RBF.beta is any Real in the reference (kernels.jl:51-75): beta > 1 (the exponent of the fused 2^(y/256) is positive near the
+    diagonal), beta = 1e6 / 1e-6, beta <= 0 (cannot be folded into the exponent: multiplied in afterwards), at depths whose two
+    augmented columns fit the padding (d = 9, 26), start a new k-step (d = 15, 16, 32) or sit at its end (d = 14, 30). NaN inputs
+    propagate to their row and column only."""
+    rng = np.random.default_rng(31)
+    for d in (9, 14, 15, 16, 26, 30, 32):
+        n = 140
+        X = rng.standard_normal((n, d)) * 0.5 + rng.standard_normal(d)
+        for beta in (3.0, 1e6, 1e-6, -1.5, 0.0):
+            K = np.asarray(pl.KernelMatrix(X, pl.RBF(pl.Euclidean(d), ell=1.1, beta=beta)))
+            ref = orc.symmetric(orc.kernel_matrix(X, orc.RBF(orc.Euclidean(d), ell=1.1, beta=beta), use_c=False))
+            if beta == 0.0:
+                assert np.all(K == 0.0) and np.all(ref == 0.0)
+            else:
+                assert relerr(K, ref) < RTOL, (d, beta)
+            assert np.array_equal(K, K.T) and np.all(np.diag(K) == beta)
+        Kx = pl.KernelMatrix(X[:50], X[50:], pl.RBF(pl.Euclidean(d), ell=0.9, beta=-2.0))
+        assert relerr(Kx, orc.kernel_matrix_cross(X[:50], X[50:], orc.RBF(orc.Euclidean(d), ell=0.9, beta=-2.0))) < RTOL
+    Xn = rng.standard_normal((130, 9))
+    Xn[5, 3] = np.nan
+    Kn = np.asarray(pl.KernelMatrix(Xn, pl.RBF(pl.Euclidean(9))))
+    assert np.isnan(np.delete(Kn[5], 5)).all() and np.isnan(np.delete(Kn[:, 5], 5)).all()
+    assert not np.isnan(np.delete(np.delete(Kn, 5, 0), 5, 1)).any()
+
+
 def test_gram_mean_heavy_descriptors_keep_1e10(pl, orc):
     """|x|^2 >> d2 (GlobalMean descriptors with a large common mean): the column-mean shift keeps the Gram-form distance exact."""
     rng = np.random.default_rng(5)
