@@ -250,60 +250,122 @@ def test_syrk_work_units_cover_upper_triangle_once():
     assert 4 * 3 // 2 + (4 + 1) // 2 == 8  # K = 500: 6 + 2 units (cost 8.25) instead of 9 packed units / 10 tiles
 
 
+def _smem_wavefronts(addrs):  # 8-byte accesses of one warp, 32 banks x 4 bytes: greedy packing into conflict-free wavefronts (>= 2)
+    waves = 0
+    remaining = list(addrs)
+    while remaining:
+        used, nxt = {}, []
+        for a in remaining:
+            bank = (a // 8) % 16  # pair of 4-byte banks
+            if bank in used and used[bank] != a:
+                nxt.append(a)
+            else:
+                used[bank] = a
+        waves += 1
+        remaining = nxt
+    return waves
+
+
 def test_staged_epilogue_box_layout():
-    """gram_epilogue_staged (csrc/gram.cuh): the per-warp staging buffer holds 16-column x 32-row boxes in TMA's 128B-swizzled
-    layout (16-byte chunk index XOR (row & 7)). Replays the st.shared address math of the direct and the mirrored pass and checks
-    that (a) it is a bijection onto the 16 KB buffer, (b) un-swizzling box by box gives the warp tile resp. its transpose,
-    (c) every store instruction needs the minimum of 2 (direct) / at most 4 (mirror) shared-memory wavefronts."""
+    """gram_epilogue_staged (csrc/gram.cuh): the warp tile (32 x 64) leaves in two halves through ONE 8 KB per-warp staging buffer that
+    holds two 16-column x 32-row boxes in TMA's 128B-swizzled layout (16-byte chunk index XOR (row & 7)). Direct copy: half h = columns
+    32h .. 32h+31, box (col >> 4) & 1. Mirrored copy (staged transposed): half ih = i-columns 16 ih .. +15, box jh = j-rows 32 jh .. +31.
+    Replays the st.shared address math and checks that (a) each half is a bijection onto the 8 KB buffer, (b) un-swizzling box by box
+    gives the warp tile resp. its transpose, (c) a store instruction needs the minimum of 2 (direct) / at most 4 (mirror) shared-memory wavefronts."""
     def perm(g):
         return ((g & 1) << 2) | (g >> 1)
 
-    def wavefronts(addrs):  # 8-byte accesses, 32 banks x 4 bytes
-        waves = 0
-        remaining = list(addrs)
-        while remaining:
-            used, nxt = set(), []
-            for a in remaining:
-                banks = {(a // 4) % 32, (a // 4 + 1) % 32}
-                if banks & used:
-                    nxt.append(a)
-                else:
-                    used |= banks
-            waves += 1
-            remaining = nxt
-        return waves
-
     tile = np.arange(32 * 64, dtype=np.float64).reshape(32, 64)  # value = 64 i + j
     for mirror in (False, True):
-        buf = np.full(16384 // 8, np.nan)
-        worst = 0
-        for mt in range(4):
-            for nt in range(8):
-                for c in range(2):
-                    addrs = []
-                    for lane in range(32):
-                        g, t = lane >> 2, lane & 3
-                        pg = perm(g)
-                        il, jl = 8 * mt + pg, 8 * nt + t + 4 * c
-                        if not mirror:
-                            a = (jl >> 4) * 4096 + il * 128 + (((jl & 15) << 3) ^ (pg << 4))
-                        else:
-                            a = (2 * (mt >> 1) + (nt >> 2)) * 4096 + (jl & 31) * 128 + (((il & 15) << 3) ^ ((t + 4 * c) << 4))
-                        assert np.isnan(buf[a // 8])
-                        buf[a // 8] = tile[il, jl]
-                        addrs.append(a)
-                    worst = max(worst, wavefronts(addrs))
+        for half in range(2):
+            buf = np.full(8192 // 8, np.nan)
+            worst = 0
+            for mt in range(4):
+                for nt in range(8):
+                    if (not mirror and nt // 4 != half) or (mirror and mt // 2 != half):
+                        continue
+                    for c in range(2):
+                        addrs = []
+                        for lane in range(32):
+                            g, t = lane >> 2, lane & 3
+                            pg = perm(g)
+                            il, jl = 8 * mt + pg, 8 * nt + t + 4 * c
+                            if not mirror:
+                                a = ((jl >> 4) & 1) * 4096 + il * 128 + (((jl & 15) << 3) ^ (pg << 4))
+                            else:
+                                a = (nt >> 2) * 4096 + (jl & 31) * 128 + (((il & 15) << 3) ^ ((t + 4 * c) << 4))
+                            assert np.isnan(buf[a // 8])
+                            buf[a // 8] = tile[il, jl]
+                            addrs.append(a)
+                        worst = max(worst, _smem_wavefronts(addrs))
+            assert not np.isnan(buf).any()
+            assert worst <= (4 if mirror else 2)
+            # what the TMA unit reads: box k, row r, 16-byte chunk q lives at chunk q ^ (r & 7)
+            for box in range(2):
+                got = np.empty((32, 16))
+                for r in range(32):
+                    for col in range(16):
+                        a = box * 4096 + r * 128 + ((col << 3) ^ ((r & 7) << 4))
+                        got[r, col] = buf[a // 8]
+                if not mirror:
+                    assert np.array_equal(got, tile[:, 32 * half + 16 * box:32 * half + 16 * box + 16])
+                else:
+                    assert np.array_equal(got, tile[16 * half:16 * half + 16, 32 * box:32 * box + 32].T)
+
+
+def test_exp_table_replicas_are_conflict_free():
+    """exp2_tab (csrc/gram.cuh): entry j of lane slot s = lane & 15 lives at (16 j + s) * 8 — whatever the 32 indices of a warp are, each
+    bank pair is hit exactly twice: 2 wavefronts per lookup, the minimum for 256 bytes (an unreplicated table needs ~8 for random indices)."""
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        idx = rng.integers(0, 256, size=32)
+        assert _smem_wavefronts([int((16 * j + (lane & 15)) * 8) for lane, j in enumerate(idx)]) == 2
+    flat = [_smem_wavefronts([int(j) * 8 for j in rng.integers(0, 4096, size=32)]) for _ in range(200)]
+    assert np.mean(flat) > 4  # what a 4096-entry unreplicated table costs in this model (ncu measured 6.2 CONFLICT wavefronts per lookup)
+
+
+def test_rbf_augmented_operands_give_the_exponent():
+    """rbf_aug_kernel (csrc/prelude.cuh) + the B operand's shifted last k-step (GramParams::b_shift) + exp2_tab, restated in numpy / C:
+    rows scaled by c = sqrt(256 log2 e) / ell after the shift, two augmented columns (u, 1) x (1, u) in the last two places of the last
+    16-column block, the B variant of that block stored once more behind the row. The contraction over 16 KT columns is then
+    256 log2(e) (-0.5 d2 / ell^2 + ln beta), and 2^(./256) of it is the reference's beta exp(-0.5 d2 / ell^2) (kernels.jl:73-74,
+    distances.jl:58-60) to ~1e-15 — for every depth class: columns fit the padding, start a new k-step, sit at its end."""
+    import ctypes
+    import os
+    import subprocess
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    src, lib = os.path.join(here, "fast_exp_model.c"), os.path.join(here, "..", "oracle", "_build", "libfastexp_model.so")
+    os.makedirs(os.path.dirname(lib), exist_ok=True)
+    if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-mfma", "-fPIC", "-shared", "-o", lib, src, "-lm"])
+    L = ctypes.CDLL(lib)
+    L.exp2_tab_model.restype = ctypes.c_double
+    L.exp2_tab_model.argtypes = [ctypes.c_double]
+    rng = np.random.default_rng(11)
+    Lc = 256.0 * 1.4426950408889634074
+    for d in (1, 9, 13, 14, 15, 16, 17, 26, 30, 31, 32, 300):
+        n, ell, beta = 37, 0.8 + 0.1 * (d % 5), 0.4 + 0.3 * (d % 4)
+        X = rng.standard_normal((n, d)) * 0.6 + 3.0 * rng.standard_normal(d)
+        mean = X[:: max(1, (n + 511) // 512)].mean(axis=0)
+        KT = (d + 2 + 15) // 16
+        ld = 16 * KT + 16
+        c, h = np.sqrt(Lc) / abs(ell), 0.5 * Lc * np.log(beta)
+        buf = np.full((n, ld), np.nan)
+        xs = (X - mean) * c
+        u = -0.5 * np.sum(xs * xs, axis=1) + h
+        buf[:, :d] = xs
+        buf[:, d:16 * KT - 2] = 0.0
+        buf[:, 16 * KT - 2], buf[:, 16 * KT - 1] = u, 1.0
+        b0 = 16 * (KT - 1)
+        buf[:, 16 * KT:16 * KT + 14] = buf[:, b0:b0 + 14]
+        buf[:, 16 * KT + 14], buf[:, 16 * KT + 15] = 1.0, u
         assert not np.isnan(buf).any()
-        assert worst <= (4 if mirror else 2)
-        # what the TMA unit reads: box k, row r, 16-byte chunk q lives at chunk q ^ (r & 7)
-        for box in range(4):
-            got = np.empty((32, 16))
-            for r in range(32):
-                for col in range(16):
-                    a = box * 4096 + r * 128 + ((col << 3) ^ ((r & 7) << 4))
-                    got[r, col] = buf[a // 8]
-            if not mirror:
-                assert np.array_equal(got, tile[:, 16 * box:16 * box + 16])
-            else:
-                ih, jh = box >> 1, box & 1
-                assert np.array_equal(got, tile[16 * ih:16 * ih + 16, 32 * jh:32 * jh + 32].T)
+        A = buf[:, :16 * KT]
+        B = np.concatenate([buf[:, :b0], buf[:, 16 * KT:16 * KT + 16]], axis=1)  # last k-step read 16 columns further right
+        Y = A @ B.T
+        D2 = np.sum((X[:, None, :] - X[None, :, :]) ** 2, axis=2)
+        ref = beta * np.exp(-0.5 * D2 / ell ** 2)
+        K = np.array([[L.exp2_tab_model(float(y)) for y in row] for row in Y])
+        off = ~np.eye(n, dtype=bool)  # the kernel forces the diagonal to beta exactly
+        assert np.max(np.abs(K[off] - ref[off]) / ref[off]) < 5e-13, d
