@@ -89,6 +89,9 @@ __global__ void colsum_final_kernel(const double* __restrict__ partial, int64_t 
 // block = 32 columns x 32 row lanes, lane rl sums sample rows rl, rl + 32, ... with four loads in flight (the pass is latency bound: every
 // sample row is its own DRAM page), the 32 lane sums are added in fixed order — deterministic, the same on every rank. ~5 us for
 // ns <= 512 (the two-launch colsum pass over 4096 rows took 17 us of the 530 us an 8-GPU shard of config 2 takes).
+// a NaN / Inf entry of a sampled row must not poison the SHIFT (and through it every row of the result): it counts as 0 here and
+// propagates through its own row only, as in the reference
+__device__ __forceinline__ double fin(double v) { return (__double2hiint(v) & 0x7ff00000) == 0x7ff00000 ? 0.0 : v; }
 __global__ void __launch_bounds__(1024) sample_mean_kernel(const double* __restrict__ X, int64_t ns, int64_t stride_elems, int64_t d, double* __restrict__ out) {
   pdl_launch_dependents();  // the operand kernel that follows may start its prologue; it waits (pdl_wait) before it reads the mean
   __shared__ double sh[32][33];
@@ -98,11 +101,11 @@ __global__ void __launch_bounds__(1024) sample_mean_kernel(const double* __restr
   if (c < d) {
     int64_t r = rl;
     for (; r + 96 < ns; r += 128) {
-      const double v0 = __ldg(X + r * stride_elems + c), v1 = __ldg(X + (r + 32) * stride_elems + c);
-      const double v2 = __ldg(X + (r + 64) * stride_elems + c), v3 = __ldg(X + (r + 96) * stride_elems + c);
+      const double v0 = fin(__ldg(X + r * stride_elems + c)), v1 = fin(__ldg(X + (r + 32) * stride_elems + c));
+      const double v2 = fin(__ldg(X + (r + 64) * stride_elems + c)), v3 = fin(__ldg(X + (r + 96) * stride_elems + c));
       s0 += v0; s1 += v1; s2 += v2; s3 += v3;
     }
-    for (; r < ns; r += 32) s0 += __ldg(X + r * stride_elems + c);
+    for (; r < ns; r += 32) s0 += fin(__ldg(X + r * stride_elems + c));
   }
   sh[rl][cl] = (s0 + s1) + (s2 + s3);
   __syncthreads();
