@@ -69,7 +69,7 @@ def make_features_host(n=N_CFG, d=D_CFG, seed=SEED):
 
 def workload_config(extra=None):
     cfg = {"workload": f"KernelMatrix RBF(Euclidean({D_CFG})) N={N_CFG} d={D_CFG} (BASELINE configs[1])", "flop_convention": "N(N+1)d",
-           "l2": "output 3.2 GB >> 126 MB L2; 256 MiB L2 flush written between timed steps"}
+           "l2": "output 3.2 GB >> 126 MB L2; 256 MiB L2 flush written between timed GPU steps"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -378,7 +378,7 @@ def run_reference(args):
     full_ms = N_CFG * (N_CFG + 1) * D_CFG / (value * 1e9) * 1e3
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": full_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config({"ms_per_step_note": "extrapolated from the sampled rows to the full matrix"}),
+            "config": workload_config(), "arm_notes": {"ms_per_step": "extrapolated from the sampled rows to the full matrix"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": sample + "; the reference loop is single-threaded Julia (kernels.jl:217-221), restated in C (oracle/pl_oracle.c)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -621,7 +621,10 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config({"parallelism": f"tiles round-robin over {world} GPU(s), no collective", "output": "tile-packed shards" if packed else "dense N x N storage, Symmetric uplo=:U triangle written (reference contract, kernels.jl:216-222)"}),
+            # `config` is the workload and nothing else: identical, key for key, in both arms (the driver compares them)
+            "config": workload_config(),
+            "arm_notes": {"parallelism": f"tiles round-robin over {world} GPU(s), no collective",
+                          "output": "tile-packed shards" if packed else "dense N x N storage, Symmetric uplo=:U triangle written (reference contract, kernels.jl:216-222)"},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
             "wall_s_timed_region": t_wall, "also": also}
     emit(line)

@@ -1353,6 +1353,13 @@ int gram_sym_stream(int kernel_id, const double* d1, int64_t n1, int64_t l1, int
   const int64_t ldo = (n1 + 1) & ~(int64_t)1;
   std::vector<int> bounds(nchunk_total + 1);
   for (int c = 0; c <= nchunk_total; ++c) bounds[c] = (int)(T * sqrt((double)c / nchunk_total) + 0.5);
+  if (c_lo == 0 && c_hi == nchunk_total && nchunk_total == 8 && !getenv("PLB200_STREAM_EQUAL")) {
+    // One device does all ranges: the copy is ~8 x slower than the compute, so what matters is how early it STARTS. The first range is
+    // one wave of tiles (its copy begins ~50 us after the first launch instead of after an eighth of the matrix), the next ones grow
+    // geometrically and compute stays ahead of the copy throughout (PLB200_STREAM_TRACE=1 prints the timeline).
+    static const double frac[9] = {0.0, 0.012, 0.06, 0.2, 0.4, 0.6, 0.8, 0.9, 1.0};
+    for (int c = 0; c <= 8; ++c) bounds[c] = (int)(T * sqrt(frac[c]) + 0.5);
+  }
   bounds[0] = 0;
   bounds[nchunk_total] = T;
   const int64_t row_lo = (int64_t)bounds[c_lo] * GRAM_BM;
