@@ -50,16 +50,16 @@ struct GramParams {
   int64_t d;            // contraction length
   double* out;          // dense: row-major, leading dim ldo ; packed: tile-packed (128*128 doubles per tile)
   int64_t ldo;
-  const double* ra;     // per-row statistics of the A operand rows (DOT: 1/sqrt(x.x); RBF: quadratic form q_i)
+  const double* ra;     // per-row statistics of the A operand rows (DOT: 1/sqrt(x.x); IMQ: quadratic form q_i; RBF: unused, see b_shift)
   const double* rb;     // same for B operand rows
   int symmetric;        // only tiles tj >= ti, mirrored per `fill`
   int same_operand;     // symmetric and A == B matrix: diagonal tiles load one operand tile
   int fill;             // PL_FILL_* bits (symmetric only)
   int packed;           // tile-packed output
   int alpha;            // DOT power
-  double s;             // RBF: -0.5 / ell^2 ; IMQ: 1 / ell^2
+  double s;             // IMQ: 1 / ell^2 (RBF: folded into the operands)
   double beta;          // RBF scale ; IMQ: c^2
-  double lnbeta, bmul;  // RBF: beta > 0 -> (ln beta, 1): the scale is folded into the exponent; else (0, beta)
+  double bmul;          // RBF: beta > 0 -> 1 (the scale is folded into the exponent by the prelude); else beta, multiplied in by the epilogue
   int T1, T2;           // tile rows / tile cols
   int64_t ntiles_total; // linear tile slots (symmetric: folded enumeration incl. a few invalid slots)
   int part, nparts;     // tile sharding across GPUs: slot l is ours iff l % nparts == part

@@ -399,7 +399,6 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   p.alpha = L.alpha;
   p.s = L.s;
   p.beta = L.beta;
-  p.lnbeta = (L.epi == EPI_RBF && L.beta > 0.0) ? log(L.beta) : 0.0;
   p.bmul = (L.epi == EPI_RBF && L.beta > 0.0) ? 1.0 : L.beta;
   p.T1 = (int)((L.nA + BM - 1) / BM);
   p.T2 = (int)((L.nB + BN - 1) / BN);
@@ -671,8 +670,8 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
   L.ra = (double*)s1;
   L.rb = sym ? (double*)s1 : (double*)s2;
   if (cinv_kind == PL_CINV_IDENTITY) {
-    PL_TRY(launch_prep<PREP_RBF_ID>(X1, n1, d, l1, (double*)mean, nullptr, (double*)xc1, nullptr, ldc, (double*)s1, st));
-    if (!sym) PL_TRY(launch_prep<PREP_RBF_ID>(X2, n2, d, l2, (double*)mean, nullptr, (double*)xc2, nullptr, ldc, (double*)s2, st));
+    PL_TRY(launch_prep<PREP_DIST_ID>(X1, n1, d, l1, (double*)mean, nullptr, (double*)xc1, nullptr, ldc, (double*)s1, st));
+    if (!sym) PL_TRY(launch_prep<PREP_DIST_ID>(X2, n2, d, l2, (double*)mean, nullptr, (double*)xc2, nullptr, ldc, (double*)s2, st));
     L.A = (double*)xc1; L.ldA = ldc;
     L.B = sym ? (double*)xc1 : (double*)xc2; L.ldB = ldc;
     L.same_operand = sym;
@@ -685,8 +684,8 @@ int gram_dev_impl(int kernel_id, const double* dX1, int64_t n1, int64_t ldx1, co
     const double* cd;
     int64_t ldcd;
     PL_TRY(tma_operand(dcinv, 1, d, ldc, WS_PADC, st, &cd, &ldcd));
-    PL_TRY(launch_prep<PREP_RBF_DIAG>(X1, n1, d, l1, (double*)mean, cd, (double*)xc1, (double*)y1, ldc, (double*)s1, st));
-    if (!sym) PL_TRY(launch_prep<PREP_RBF_DIAG>(X2, n2, d, l2, (double*)mean, cd, (double*)xc2, (double*)y2, ldc, (double*)s2, st));
+    PL_TRY(launch_prep<PREP_DIST_DIAG>(X1, n1, d, l1, (double*)mean, cd, (double*)xc1, (double*)y1, ldc, (double*)s1, st));
+    if (!sym) PL_TRY(launch_prep<PREP_DIST_DIAG>(X2, n2, d, l2, (double*)mean, cd, (double*)xc2, (double*)y2, ldc, (double*)s2, st));
   } else {
     // Y = Xc * Cinv through the same DMMA Gram engine (Cinv symmetric: rows of Cinv are its columns)
     const double* cf;

@@ -117,12 +117,12 @@ __global__ void __launch_bounds__(1024) sample_mean_kernel(const double* __restr
   }
 }
 
-enum { PREP_DOT = 0, PREP_RBF_ID = 1, PREP_RBF_DIAG = 2, PREP_CENTER_ONLY = 3 };
+enum { PREP_DOT = 0, PREP_DIST_ID = 1, PREP_DIST_DIAG = 2, PREP_CENTER_ONLY = 3 };
 
 // One warp per row.
 //   PREP_DOT:         stat[i] = 1/sqrt(sum_k x^2)                                  (kernels.jl:35)
-//   PREP_RBF_ID:      xc = x - mean -> Xc ; stat[i] = sum_k xc^2                   (distances.jl:59, Cinv = I)
-//   PREP_RBF_DIAG:    xc = x - mean -> Xc ; y = xc * cinv -> Y ; stat[i] = sum_k y*xc
+//   PREP_DIST_ID:     xc = x - mean -> Xc ; stat[i] = sum_k xc^2                   (distances.jl:59, Cinv = I; InverseMultiquadric — RBF has rbf_aug_kernel)
+//   PREP_DIST_DIAG:   xc = x - mean -> Xc ; y = xc * cinv -> Y ; stat[i] = sum_k y*xc
 //   PREP_CENTER_ONLY: xc = x - mean -> Xc                                          (then Y = Xc*Cinv by GEMM)
 // ldc is the leading dimension of Xc and Y.
 template <int MODE>
@@ -146,10 +146,10 @@ __global__ void prep_rows_kernel(const double* __restrict__ X, int64_t n, int64_
       v.x -= m.x;
       v.y -= m.y;
       *reinterpret_cast<double2*>(Xc + row * ldc + k) = v;
-      if (MODE == PREP_RBF_ID) {
+      if (MODE == PREP_DIST_ID) {
         acc = fma(v.x, v.x, acc);
         acc = fma(v.y, v.y, acc);
-      } else if (MODE == PREP_RBF_DIAG) {
+      } else if (MODE == PREP_DIST_DIAG) {
         const double2 c = __ldg(reinterpret_cast<const double2*>(cdiag + k));
         double2 y;
         y.x = v.x * c.x;
@@ -168,8 +168,8 @@ __global__ void prep_rows_kernel(const double* __restrict__ X, int64_t n, int64_
     } else {
       v -= mean[k];
       Xc[row * ldc + k] = v;
-      if (MODE == PREP_RBF_ID) acc = fma(v, v, acc);
-      else if (MODE == PREP_RBF_DIAG) {
+      if (MODE == PREP_DIST_ID) acc = fma(v, v, acc);
+      else if (MODE == PREP_DIST_DIAG) {
         const double y = v * cdiag[k];
         Y[row * ldc + k] = y;
         acc = fma(y, v, acc);
