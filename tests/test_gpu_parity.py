@@ -544,6 +544,45 @@ def test_device_api_tile_sharding(pl, orc):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("n", [3000, 9000])
+def test_rbf_medium_sizes_all_depth_classes(pl, n):
+    """Both tile shapes of the RBF kernel (64 x 64 below ~8600 features, 128 x 128 above) at contraction depths whose two augmented
+    columns fit the padding (d = 13, 30, 127 -> free), fill it exactly (d = 14) or open another k-step (d = 15, 16, 64), for the three
+    kinds of Cinv, `Symmetric(:U)` storage and both triangles: 150 sampled rows against numpy fp64 at the contract's 1e-10,
+    exact symmetry, exact diagonal."""
+    import torch
+
+    rng = np.random.default_rng(n)
+    rows = np.sort(rng.choice(n, size=150, replace=False))
+    for trial, d in enumerate((13, 14, 15, 16, 30, 64, 127)):
+        X = rng.standard_normal((n, d)) * 0.35 + 1.5 * rng.standard_normal(d)
+        ell, beta = 0.9 + 0.05 * trial, (0.5, 1.0, 3.0)[trial % 3]
+        kind = trial % 3
+        if kind == 0:
+            e, C = pl.Euclidean(d), np.eye(d)
+        elif kind == 1:
+            cd = rng.uniform(0.5, 2.0, size=d)
+            e, C = pl.Euclidean(pl.Diagonal(cd)), np.diag(cd)
+        else:
+            B = rng.standard_normal((d, d))
+            C = B @ B.T / d + np.eye(d)
+            e = pl.Euclidean(pl.Symmetric(C))
+        Xd = torch.as_tensor(X, device="cuda")
+        K = pl.kernel_matrix_dev(Xd, pl.RBF(e, ell=ell, beta=beta))
+        torch.cuda.synchronize()
+        assert bool(torch.equal(K, K.T)) and bool(torch.all(torch.diagonal(K) == beta)), (n, d)
+        ref = np.empty((len(rows), n))
+        for a, r in enumerate(rows):
+            U = X[r] - X
+            ref[a] = beta * np.exp(-0.5 * np.einsum("jk,jk->j", U @ C, U) / ell ** 2)
+        got = K[torch.as_tensor(rows, device="cuda")].cpu().numpy()
+        ok = ref > 1e-280
+        assert np.max(np.abs(got[ok] - ref[ok]) / ref[ok]) < 1e-10, (n, d, kind)
+        S = np.asarray(pl.KernelMatrix(X, pl.RBF(e, ell=ell, beta=beta))) if trial in (1, 5) else None  # host path, Symmetric(:U) storage
+        if S is not None:
+            assert np.array_equal(S[rows], got), "host path (streamed / staircase copy) and device-resident path agree bit for bit"
+
+
 def test_config2_full_size_properties(pl, orc):
     """BASELINE config 2: RBF(Euclidean(300)), N = 20 000, d = 300 on one GPU — checked through size-independent properties:
     exact symmetry, K[i,i] == beta, sampled rows against the restated pair loop."""
