@@ -124,6 +124,9 @@ int pl_gram_dot(const double* X, int64_t n, int64_t d, int64_t ldx, int alpha, d
 /* Symmetric RBF(Euclidean) kernel matrix.
  *   d2 = (x_i-x_j)' Cinv (x_i-x_j)  (distances.jl:58-60);  K[i,j] = beta*exp(-0.5*d2/ell^2) (kernels.jl:73-74).
  * RBF.alpha is NOT applied (the reference never applies it); K[i,i] == beta exactly.
+ * Accuracy: <= 1e-11 relative against the reference formula wherever K > 2.3e-308; entries the reference evaluates as denormal or 0
+ * (-0.5*d2/ell^2 + ln(beta) < -708.4) come out as some number <= 4.5e-308. A NaN feature vector makes its own row and column NaN and
+ * nothing else (as in the reference).
  * cinv: NULL for PL_CINV_IDENTITY, d doubles for DIAGONAL, d*d doubles for FULL. */
 int pl_gram_rbf(const double* X, int64_t n, int64_t d, int64_t ldx, int cinv_kind, const double* cinv, double ell,
                 double beta, double* K, int64_t ldk, int fill);
