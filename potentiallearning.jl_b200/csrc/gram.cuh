@@ -72,6 +72,10 @@ struct GramParams {
   int64_t tail_first;   // >= 0 (64 x 64 kernel only): TAIL mode. The last tail_count 128 x 128 tiles of this part (slots tail_first,
   int tail_count;       //   tail_first + nparts, ...) are computed as up to four 64 x 64 sub-tiles each, written into the parent tile's
   int T1p, T2p;         //   place (tile-packed output: inside the 128 x 128 packed tile). T1p / T2p: the 128-tile grid of the slots.
+#ifdef PLB_GRAM_TRACE
+  long long* trace;     // developer build (-DPLB_GRAM_TRACE, scripts/gram_trace.py): 8 int64 per CTA — globaltimer at entry, after the dependency
+                        //   wait, after the first tile's main loop, after its epilogue, at the end of the tile loop (consumer warp 0), SM id, tiles done
+#endif
   int tcol_end;         //       [tcol_begin, tcol_end), column by column — lets the host stream finished rows of the
                         //       Symmetric(:U) storage to the host while later columns are still being computed
 };
@@ -441,7 +445,21 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   // Launched as a programmatic dependent of the prelude kernel (row statistics / centred copy): everything above overlaps its tail.
   // DotProduct contracts the caller's X itself, so only the epilogue (row statistics) has to wait; the others read the prelude's output.
+#ifdef PLB_GRAM_TRACE
+  auto gtime = []() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+  long long* const tr = p.trace ? p.trace + 8 * (int64_t)blockIdx.x : nullptr;
+  if (tr && threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tr[0] = gtime();
+    tr[5] = smid;
+  }
+#endif
   if (p.pdl && EPI != EPI_DOT) pdl_wait();
+#ifdef PLB_GRAM_TRACE
+  if (tr && threadIdx.x == 0) tr[1] = gtime();
+  int tiles_done = 0;
+#endif
 
   const int KT = (int)((p.d + GRAM_BK - 1) / GRAM_BK);
   const bool tail = NARROW == 2 && p.tail_first >= 0;
@@ -555,6 +573,9 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (lane == 0) mbar_arrive(empty_bar(s));
     }
 
+#ifdef PLB_GRAM_TRACE
+    if (tr && threadIdx.x == 0 && tiles_done == 0) tr[2] = gtime();
+#endif
     // ------------------------------ fused epilogue ------------------------------
     // accumulator (mt, nt, c) of lane (g, t) is element
     //   i = 128*ti + 32*wm + 8*mt + perm(g),   j = 128*tj + 64*wn + 8*nt + perm(2t + c) = ... + t + 4c
@@ -602,6 +623,14 @@ gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else {
       gram_epilogue<EPI, true, 2, MT, NT>(acc, p, i0, j0, rel0, w1, w2, prow, pcol, ldo, Exp2Tab{tab_base + 8u * (lane & 15)});
     }
+#ifdef PLB_GRAM_TRACE
+    if (tr && threadIdx.x == 0) {
+      if (tiles_done == 0) tr[3] = gtime();
+      ++tiles_done;
+      tr[4] = gtime();
+      tr[6] = tiles_done;
+    }
+#endif
   }
   if (TMAST && lane == 0) tma_store_wait_all();  // the staging buffers must outlive the bulk stores that read them
 }

@@ -382,6 +382,15 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   GramParams p;
   p.b_shift = L.b_shift;
   p.exp_tab = (const double*)g.exp_tab;
+#ifdef PLB_GRAM_TRACE
+  p.trace = nullptr;
+  if (getenv("PLB200_GRAM_TRACE")) {  // developer build: per-CTA timeline of the MAIN launch appended to that file (scripts/gram_trace.py)
+    void* trb;
+    PL_TRY(ws_get(WS_TRACE, (size_t)g.num_sms * 8 * 8, &trb));
+    CUDA_TRY(cudaMemsetAsync(trb, 0, (size_t)g.num_sms * 8 * 8, st));
+    p.trace = (long long*)trb;
+  }
+#endif
 
   const int tab_smem = L.epi == EPI_RBF ? EXP_TAB_BYTES : 0;
   p.n1 = L.nA;
@@ -466,6 +475,22 @@ int launch_gram(const GramLaunch& L, cudaStream_t st) {
   }
   CUDA_TRY(le);
   LAUNCH_CHECK();
+#ifdef PLB_GRAM_TRACE
+  if (p.trace) {
+    std::vector<long long> h((size_t)g.num_sms * 8);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), p.trace, h.size() * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (FILE* f = fopen(getenv("PLB200_GRAM_TRACE"), "a")) {
+      fprintf(f, "launch grid %d\n", grid);
+      for (int b = 0; b < grid; ++b) {
+        fprintf(f, "%d", b);
+        for (int k = 0; k < 8; ++k) fprintf(f, " %lld", h[(size_t)b * 8 + k]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
+#endif
   if (tail_r) {
     CUtensorMap tmA64, tmB64;
     PL_TRY(make_tmap_2d(&tmA64, L.A, L.d + L.b_shift, L.nA, L.ldA, GRAM_BK, 64));
