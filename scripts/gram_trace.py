@@ -3,8 +3,15 @@ launch go. Build: nvcc ... -DPLB_GRAM_TRACE -o scripts/native/libplb200_trace.so
 import os
 import sys
 
+import subprocess
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["PLB200_LIB"] = os.path.join(ROOT, "scripts", "native", "libplb200_trace.so")
+SO = os.path.join(ROOT, "scripts", "native", "libplb200_trace.so")
+SRC = os.path.join(ROOT, "potentiallearning.jl_b200", "csrc", "plb200_api.cu")
+if not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-pthread", "-shared",
+                           "-ldl", "-lpthread", "-DPLB_GRAM_TRACE", "-o", SO, SRC])
+os.environ["PLB200_LIB"] = SO
 os.environ["PLB200_NO_GRAPH"] = "1"
 TRACE = os.path.join(ROOT, "gpurun_out", "gram_trace.txt")
 sys.path.insert(0, ROOT)

@@ -6,8 +6,14 @@ import os
 import numpy as np
 import torch
 
+import subprocess
+
 HERE = os.path.dirname(os.path.abspath(__file__))
-L = ctypes.CDLL(os.path.join(HERE, "native", "libzcprobe.so"))
+SO = os.path.join(HERE, "native", "libzcprobe.so")
+if not os.path.exists(SO):
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-shared", "-Xcompiler", "-fPIC", "-o", SO,
+                           os.path.join(HERE, "native", "zero_copy_probe.cu")])
+L = ctypes.CDLL(SO)
 L.zc_stair_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
 N = 20000
 dev = torch.device("cuda", 0)
