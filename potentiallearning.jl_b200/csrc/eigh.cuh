@@ -1,0 +1,629 @@
+// eigh.cuh — hand-written symmetric eigensolver of libplb200 (row f1 of SURVEY.md 8f): eigen(Symmetric(Q)) of
+// dimension_reduction.jl:13 (K x K covariance, K = 500 / 1000 in configs 3 / 4) and the eigendecomposition inside EllEnsemble(K)
+// (dpp.jl:26,41; config 1: N = 1000). The reference calls LAPACK (syevr) here; round 1 called cuSOLVER. This file is the
+// library-free path for matrices that live in L2 (n <= 4096):
+//
+//   1. eigh_sytrd_kernel      Householder tridiagonalisation as ONE persistent cooperative kernel: the rank-2 update of step j and
+//                             the symmetric matrix-vector product of step j+1 are one pass over the rows a CTA owns (rows dealt
+//                             cyclically), every CTA forms the next reflector redundantly from a broadcast copy of the next row,
+//                             one grid barrier per step.
+//   2. dc_*                   divide and conquer on the tridiagonal matrix (Cuppen / Gu-Eisenstat): Jacobi leaves (<= 32), per
+//                             merge: deflation, secular equation by bisection ON THE BIT PATTERN of the offset from the nearer
+//                             pole (<= 63 steps to the last bit, whatever the scale), Loewner re-computation of the update vector,
+//                             and the eigenvector update Q <- Q V as a product on the DMMA Gram engine (gram.cuh, LINEAR epilogue).
+//   3. eigh_backtransform     applies the reflectors to the eigenvectors of T (one warp per vector, reflectors streamed from L2).
+//
+// scripts/eig_proto/dc_proto.py is the numpy model of step 2 (same formulas, same order) used to validate the algorithm on the CPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace plb {
+
+constexpr int EIGH_LEAF = 32;          // largest leaf of the divide-and-conquer tree
+constexpr int EIGH_MAX_N = 4096;       // shared-memory budgets below are sized for this
+constexpr int EIGH_SYTRD_THREADS = 256;
+constexpr double EIGH_EPS = 1.1102230246251565e-16;  // LAPACK dlamch('E')
+
+struct EighMerge {
+  int lo, mid, hi;  // node [lo, hi) with children [lo, mid) and [mid, hi)
+};
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+__device__ __forceinline__ double warp_max(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+
+// block-wide sum, result broadcast to every thread; `red` holds >= 33 doubles; two __syncthreads
+__device__ __forceinline__ double block_sum(double x, double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  x = warp_sum(x);
+  __syncthreads();  // red may still be read from an earlier call
+  if (lane == 0) red[wid] = x;
+  __syncthreads();
+  double t = lane < nw ? red[lane] : 0.0;
+  return warp_sum(t);
+}
+__device__ __forceinline__ double block_max(double x, double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  x = warp_max(x);
+  __syncthreads();
+  if (lane == 0) red[wid] = x;
+  __syncthreads();
+  double t = lane < nw ? red[lane] : 0.0;
+  return warp_max(t);
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// max |a_ij| over the triangle that is read -> bits of the maximum in *out (atomicMax on the bit pattern of a non-negative double)
+__global__ void eigh_maxabs_kernel(const double* __restrict__ A, int n, int64_t lda, int lower, unsigned long long* out) {
+  double m = 0.0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < (int64_t)n * n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / n), j = (int)(e % n);
+    if (lower ? j <= i : j >= i) {
+      const double a = fabs(A[i * lda + j]);
+      m = (a > m || a != a) ? a : m;  // a NaN wins
+    }
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+// S = full symmetric copy of the triangle of A, scaled by 1 / max|a_ij|; rowbuf0 = row 0 of S (the first "next row" of the sytrd loop)
+__global__ void eigh_symmetrize_kernel(const double* __restrict__ A, int n, int64_t lda, int lower, const unsigned long long* maxbits,
+                                       double* __restrict__ S, int64_t lds, double* __restrict__ rowbuf0, double* scal) {
+  const double mx = __longlong_as_double((long long)*maxbits);
+  const double inv = (mx > 0.0 && mx < INFINITY) ? 1.0 / mx : 1.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) scal[0] = (mx > 0.0 && mx < INFINITY) ? mx : 1.0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < (int64_t)n * n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / n), j = (int)(e % n);
+    const int hi = i > j ? i : j, lo = i > j ? j : i;
+    const double a = (lower ? A[hi * lda + lo] : A[lo * lda + hi]) * inv;
+    S[i * lds + j] = a;
+    if (i == 0) rowbuf0[j] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+struct SytrdParams {
+  double* S;        // n x n full symmetric (row-major, lds); on return row j, columns > j: Householder vector j (v[j+1] = 1)
+  int64_t lds;
+  int n;
+  double* d;        // n     diagonal of T
+  double* e;        // n     off-diagonal of T (e[n-1] unused)
+  double* tau;      // n
+  double* p;        // n     A v of the current step (rows written by their owners)
+  double* pd;       // grid  partial v . (A v)
+  double* rowbuf;   // 2 x n broadcast copy of the next row, double-buffered by step parity
+  unsigned long long* bar;  // [0] arrival counter (zeroed by the host), [1] abort flag
+};
+
+// all CTAs are co-resident (cooperative launch). A barrier that is not reached within ~4 s sets the abort flag and every CTA leaves.
+__device__ __forceinline__ bool sytrd_grid_barrier(unsigned long long* bar, unsigned long long target) {
+  __shared__ int s_abort;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1ull);
+    int ab = 0;
+    const long long t0 = clock64();
+    while (ld_acquire_u64(bar) < target) {
+      if (ld_acquire_u64(bar + 1) != 0ull) { ab = 1; break; }
+      if (clock64() - t0 > 8000000000ll) { atomicExch(bar + 1, 1ull); ab = 1; break; }
+    }
+    s_abort = ab;
+  }
+  __syncthreads();
+  return s_abort == 0;
+}
+
+__global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_kernel(SytrdParams P) {
+  extern __shared__ double sm[];
+  const int n = P.n;
+  const int np = (n + 3) & ~3;
+  double* v = sm;             // v_j   (support [j+1, n), v[j+1] = 1)
+  double* w = sm + np;        // w_j
+  double* vn = sm + 2 * np;   // row j+1 after update j, then v_{j+1}
+  __shared__ double red[40];
+  __shared__ double s_tau, s_taun;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const int G = gridDim.x, b = blockIdx.x;
+  for (int c = tid; c < np; c += blockDim.x) { v[c] = 0.0; w[c] = 0.0; vn[c] = 0.0; }
+  if (tid == 0) { s_tau = 0.0; s_taun = 0.0; }
+  __syncthreads();
+  unsigned long long target = 0;
+
+  for (int j = -1; j <= n - 2; ++j) {
+    const int jn = j + 1;
+    // ---- phase a: w_j = tau p - (tau/2)(tau p.v) v from the products the row owners wrote before the barrier
+    const double* rb = P.rowbuf + (size_t)((j - 1) & 1) * n;
+    if (j >= 0) {
+      const double tau = s_tau;
+      double part = 0.0;
+      for (int g = tid; g < G; g += blockDim.x) part += __ldcg(P.pd + g);
+      const double dot = block_sum(part, red);
+      const double alpha = 0.5 * tau * tau * dot;
+      for (int c = jn + tid; c < n; c += blockDim.x) w[c] = tau * __ldcg(P.p + c) - alpha * v[c];
+    }
+    __syncthreads();
+    // ---- phase b: row jn after update j (every CTA, redundantly) -> d[jn], reflector jn
+    {
+      const double vj = v[jn], wj = w[jn];
+      double sig = 0.0;
+      for (int c = jn + tid; c < n; c += blockDim.x) {
+        double r = __ldcg(rb + c);
+        if (j >= 0) r = r - (vj * w[c] + wj * v[c]);
+        vn[c] = r;
+        if (c >= jn + 2) sig += r * r;
+      }
+      const double sigma = block_sum(sig, red);  // also makes vn visible
+      const double djn = vn[jn];
+      const double a0 = jn + 1 < n ? vn[jn + 1] : 0.0;
+      double beta = a0, taun = 0.0, scl = 0.0;
+      if (jn + 1 < n && sigma > 0.0) {
+        beta = -copysign(sqrt(a0 * a0 + sigma), a0);
+        taun = (beta - a0) / beta;
+        scl = 1.0 / (a0 - beta);
+      }
+      __syncthreads();  // everyone has read vn[jn], vn[jn+1]
+      for (int c = jn + tid; c < n; c += blockDim.x) {
+        double x = vn[c];
+        x = c >= jn + 2 ? x * scl : (c == jn + 1 ? 1.0 : 0.0);
+        vn[c] = x;
+      }
+      if (tid == 0) s_taun = taun;
+      if (b == 0 && tid == 0) {
+        P.d[jn] = djn;
+        if (jn + 1 < n) { P.e[jn] = beta; P.tau[jn] = taun; }
+      }
+      __syncthreads();
+    }
+    if (jn == n - 1) break;
+    // ---- phase c: own rows r > jn: rank-2 update with (v_j, w_j), product with v_{jn}; row jn+1 is broadcast for the next step
+    double pdw = 0.0;
+    {
+      double* rbn = P.rowbuf + (size_t)(j & 1) * n;
+      int r0 = b;  // rows r = b + G q; first q with r > jn
+      if (r0 <= jn) r0 += ((jn - r0) / G + 1) * G;
+      const int c0 = (jn + 1) & ~31;
+      for (int r = r0 + wid * G; r < n; r += nw * G) {
+        double* row = P.S + (size_t)r * P.lds;
+        const double vr = v[r], wr = w[r];
+        const bool bc = (r == jn + 1);
+        double acc = 0.0;
+        if (j >= 0) {
+          for (int c = c0 + lane; c < n; c += 32) {
+            if (c > jn) {
+              double a = __ldcg(row + c);
+              a = a - (vr * w[c] + wr * v[c]);
+              __stcg(row + c, a);
+              acc += a * vn[c];
+              if (bc) __stcg(rbn + c, a);
+            }
+          }
+        } else {
+          for (int c = c0 + lane; c < n; c += 32) {
+            if (c > jn) {
+              const double a = __ldcg(row + c);
+              acc += a * vn[c];
+              if (bc) __stcg(rbn + c, a);
+            }
+          }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          __stcg(P.p + r, acc);
+          pdw += vn[r] * acc;
+        }
+      }
+      // the owner of row jn stores reflector jn over the finished row (nobody reads S[jn][.] again)
+      if (jn % G == b) {
+        double* row = P.S + (size_t)jn * P.lds;
+        for (int c = jn + 1 + tid; c < n; c += blockDim.x) row[c] = vn[c];
+      }
+    }
+    const double pdb = block_sum(pdw, red);
+    if (tid == 0) __stcg(P.pd + b, pdb);
+    // rotate: v <- v_{jn} (w is rebuilt in phase a)
+    __syncthreads();
+    for (int c = jn + tid; c < n; c += blockDim.x) v[c] = vn[c];
+    if (tid == 0) s_tau = s_taun;
+    target += (unsigned long long)G;
+    if (!sytrd_grid_barrier(P.bar, target)) return;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// divide and conquer on T = tridiag(d, e)
+
+// leaves: cyclic Jacobi (round-robin ordering, 16 disjoint rotations per round) on the <= 32 x 32 diagonal block, torn at both ends.
+// One CTA of 256 threads per leaf. Also (every CTA, redundantly) the scale max(|d|, |e|) of T; scal[1] is written by leaf 0.
+__global__ void __launch_bounds__(256) dc_leaf_kernel(const double* __restrict__ d, const double* __restrict__ e, int n, const int2* __restrict__ leaves,
+                                                      double* __restrict__ lam, double* __restrict__ Q, int64_t ldq, double* scal) {
+  __shared__ double A[32][33];
+  __shared__ double V[32][33];
+  __shared__ double cs[16][2];
+  __shared__ int prs[16][2];
+  __shared__ double red[40];
+  const int tid = threadIdx.x;
+  const int lo = leaves[blockIdx.x].x, hi = leaves[blockIdx.x].y, m = hi - lo;
+  double mx = 0.0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    mx = fmax(mx, fabs(d[i]));
+    if (i + 1 < n) mx = fmax(mx, fabs(e[i]));
+  }
+  mx = block_max(mx, red);
+  const double scale = mx > 0.0 ? mx : 1.0;
+  const double inv = 1.0 / scale;
+  if (blockIdx.x == 0 && tid == 0) scal[1] = scale;
+  for (int t = tid; t < 32 * 32; t += blockDim.x) {
+    const int i = t >> 5, j = t & 31;
+    double a = 0.0;
+    if (i < m && j < m) {
+      if (i == j) {
+        a = d[lo + i] * inv;
+        if (i == 0 && lo > 0) a -= fabs(e[lo - 1] * inv);
+        if (i == m - 1 && hi < n) a -= fabs(e[hi - 1] * inv);
+      } else if (j == i + 1) a = e[lo + i] * inv;
+      else if (i == j + 1) a = e[lo + j] * inv;
+    }
+    A[i][j] = a;
+    V[i][j] = i == j ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int sweep = 0; sweep < 24; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int t = tid; t < 32 * 32; t += blockDim.x) {
+      const int i = t >> 5, j = t & 31;
+      const double a = A[i][j];
+      if (i == j) dg += a * a; else off += a * a;
+    }
+    off = block_sum(off, red);
+    dg = block_sum(dg, red);
+    if (off <= 1e-34 * dg || off == 0.0) break;
+    const double skip = 1e-40 * (dg + off);  // a_pq^2 below this is noise
+    for (int r = 0; r < 31; ++r) {
+      if (tid < 16) {
+        int p, q;
+        if (tid == 0) { p = r; q = 31; }
+        else { p = (r + tid) % 31; q = (r - tid + 31) % 31; }
+        if (p > q) { const int t = p; p = q; q = t; }
+        const double apq = A[p][q];
+        double c = 1.0, s = 0.0;
+        if (apq * apq > skip) {
+          const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          c = 1.0 / sqrt(t * t + 1.0);
+          s = t * c;
+        }
+        cs[tid][0] = c; cs[tid][1] = s;
+        prs[tid][0] = p; prs[tid][1] = q;
+      }
+      __syncthreads();
+      // columns: A <- A J, V <- V J
+      for (int t = tid; t < 16 * 32; t += blockDim.x) {
+        const int k = t >> 5, i = t & 31;
+        const double c = cs[k][0], s = cs[k][1];
+        if (s != 0.0) {
+          const int p = prs[k][0], q = prs[k][1];
+          const double ap = A[i][p], aq = A[i][q];
+          A[i][p] = c * ap - s * aq;
+          A[i][q] = s * ap + c * aq;
+          const double vp = V[i][p], vq = V[i][q];
+          V[i][p] = c * vp - s * vq;
+          V[i][q] = s * vp + c * vq;
+        }
+      }
+      __syncthreads();
+      // rows: A <- J' A
+      for (int t = tid; t < 16 * 32; t += blockDim.x) {
+        const int k = t >> 5, i = t & 31;
+        const double c = cs[k][0], s = cs[k][1];
+        if (s != 0.0) {
+          const int p = prs[k][0], q = prs[k][1];
+          const double ap = A[p][i], aq = A[q][i];
+          A[p][i] = c * ap - s * aq;
+          A[q][i] = s * ap + c * aq;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int t = tid; t < 32 * 32; t += blockDim.x) {
+    const int i = t >> 5, j = t & 31;
+    if (i < m && j < m) Q[(size_t)(lo + i) * ldq + lo + j] = V[i][j];
+  }
+  if (tid < m) lam[lo + tid] = A[tid][tid];
+}
+
+// per merge: z, sort, deflation (dlaed2's criteria). One CTA per merge, dynamic shared memory 2 k doubles + 2 k ints.
+// Outputs (all indexed from lo): perm[c'] = old column of new column c' (non-deflated ascending, then deflated), rot = (a, b, c, s)
+// column rotations in order, Kp = number of non-deflated, dl / wz = poles and weights of the secular equation, lam = eigenvalues in the
+// new order (the first Kp are overwritten by the secular kernel).
+struct DeflateParams {
+  const EighMerge* merges;
+  const double* e;
+  const double* scal;     // scal[1] = scale of T
+  double* lam;
+  const double* Q;
+  int64_t ldq;
+  int* perm;
+  double4* rot;
+  int* nrot;
+  int* Kp;
+  double* rho;
+  double* dl;
+  double* wz;
+};
+
+__global__ void __launch_bounds__(1024) dc_deflate_kernel(DeflateParams P) {
+  extern __shared__ double dsm[];
+  __shared__ double red[40];
+  const EighMerge mg = P.merges[blockIdx.x];
+  const int lo = mg.lo, mid = mg.mid, k = mg.hi - mg.lo, tid = threadIdx.x;
+  double* dd = dsm;
+  double* z = dsm + k;
+  int* order = (int*)(dsm + 2 * k);
+  int* outp = order + k;
+  const double beta = P.e[mid - 1] * (1.0 / P.scal[1]);  // as the leaves scale
+  const double rho = 2.0 * fabs(beta);
+  const double sgn = beta < 0.0 ? -1.0 : 1.0;
+  const double rs = 0.70710678118654752440;
+  double mx = 0.0;
+  for (int i = tid; i < k; i += blockDim.x) {
+    const double di = P.lam[lo + i];
+    const double zi = (lo + i < mid ? P.Q[(size_t)(mid - 1) * P.ldq + lo + i] : sgn * P.Q[(size_t)mid * P.ldq + lo + i]) * rs;
+    dd[i] = di;
+    z[i] = zi;
+    mx = fmax(mx, fmax(fabs(di), fabs(zi)));
+  }
+  mx = block_max(mx, red);
+  const double tol = 8.0 * EIGH_EPS * mx;
+  // rank sort (ties by index)
+  for (int i = tid; i < k; i += blockDim.x) {
+    const double di = dd[i];
+    int rk = 0;
+    for (int u = 0; u < k; ++u) {
+      const double du = dd[u];
+      rk += (du < di || (du == di && u < i)) ? 1 : 0;
+    }
+    order[rk] = i;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int nnd = 0, ndf = 0, nr = 0, pj = -1;
+    // non-deflated go to outp[0..) in ascending order, deflated to outp[k-1], outp[k-2], ... (their order is immaterial)
+    for (int t = 0; t < k; ++t) {
+      const int idx = order[t];
+      if (rho * fabs(z[idx]) <= tol) { outp[k - 1 - ndf++] = idx; continue; }
+      if (pj < 0) { pj = idx; continue; }
+      double s = z[pj], c = z[idx];
+      const double tau = hypot(c, s);
+      const double tt = dd[idx] - dd[pj];
+      c /= tau;
+      s = -s / tau;
+      if (fabs(tt * c * s) <= tol) {
+        z[idx] = tau;
+        z[pj] = 0.0;
+        P.rot[lo + nr++] = make_double4((double)pj, (double)idx, c, s);
+        const double t1 = dd[pj] * c * c + dd[idx] * s * s;
+        dd[idx] = dd[pj] * s * s + dd[idx] * c * c;
+        dd[pj] = t1;
+        outp[k - 1 - ndf++] = pj;
+        pj = idx;
+      } else {
+        outp[nnd++] = pj;
+        pj = idx;
+      }
+    }
+    if (pj >= 0) outp[nnd++] = pj;
+    P.nrot[blockIdx.x] = nr;
+    P.Kp[blockIdx.x] = nnd;
+    P.rho[blockIdx.x] = rho;
+    order[0] = nnd;  // broadcast
+  }
+  __syncthreads();
+  const int K = order[0];
+  for (int i = tid; i < k; i += blockDim.x) {
+    const int src = outp[i];
+    P.perm[lo + i] = src;
+    P.lam[lo + i] = dd[src];
+    if (i < K) { P.dl[lo + i] = dd[src]; P.wz[lo + i] = z[src]; }
+  }
+}
+
+// QB block = (QA block, rotated) with permuted columns. One CTA per row of a merge (grid.x = rows of the level, via row2merge).
+__global__ void __launch_bounds__(256) dc_permute_kernel(const EighMerge* __restrict__ merges, const int* __restrict__ row2merge, const int* __restrict__ rows,
+                                                         const double* __restrict__ QA, double* __restrict__ QB, int64_t ldq, const int* __restrict__ perm,
+                                                         const double4* __restrict__ rot, const int* __restrict__ nrot) {
+  extern __shared__ double rowv[];
+  const int i = rows[blockIdx.x];
+  const int mi = row2merge[blockIdx.x];
+  const EighMerge mg = merges[mi];
+  const int lo = mg.lo, k = mg.hi - mg.lo, tid = threadIdx.x;
+  const double* src = QA + (size_t)i * ldq + lo;
+  for (int c = tid; c < k; c += blockDim.x) rowv[c] = src[c];
+  __syncthreads();
+  const int nr = nrot[mi];
+  if (tid == 0) {
+    for (int t = 0; t < nr; ++t) {
+      const double4 r = rot[lo + t];
+      const int a = (int)r.x, b2 = (int)r.y;
+      const double x = rowv[a], y = rowv[b2];
+      rowv[a] = r.z * x + r.w * y;
+      rowv[b2] = r.z * y - r.w * x;
+    }
+  }
+  __syncthreads();
+  double* dst = QB + (size_t)i * ldq + lo;
+  for (int c = tid; c < k; c += blockDim.x) dst[c] = rowv[perm[lo + c]];
+}
+
+// secular equation: one warp per new column j of a merge. j < K: root in (dl_j, dl_{j+1}) as (origin, mu); row j of VT <- dl_i - lam_j
+// (i < K), zeros beyond; j >= K (deflated): row j of VT <- e_j.
+__global__ void __launch_bounds__(256) dc_secular_kernel(const EighMerge* __restrict__ merges, const int* __restrict__ Kp, const double* __restrict__ rhos,
+                                                         const double* __restrict__ dl, const double* __restrict__ wz, double* __restrict__ lam,
+                                                         double* __restrict__ VT, int64_t ldq) {
+  const EighMerge mg = merges[blockIdx.y];
+  const int lo = mg.lo, k = mg.hi - mg.lo;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int j = blockIdx.x * nw + wid;
+  if (j >= k) return;
+  const int K = Kp[blockIdx.y];
+  double* vrow = VT + (size_t)(lo + j) * ldq + lo;
+  if (j >= K) {
+    for (int i = lane; i < k; i += 32) vrow[i] = i == j ? 1.0 : 0.0;
+    return;
+  }
+  const double rho = rhos[blockIdx.y];
+  const double* D = dl + lo;
+  const double* W = wz + lo;
+  const bool last = (j == K - 1);
+  const double dj = D[j];
+  const double gap = last ? 0.0 : D[j + 1] - dj;
+  bool left = true;
+  double hi = 0.0;
+  if (!last) {
+    const double half = 0.5 * gap;
+    double f = 0.0;
+    for (int i = lane; i < K; i += 32) { const double wi = W[i]; f += rho * wi * wi / ((D[i] - dj) - half); }
+    f = 1.0 + warp_sum(f);
+    left = f > 0.0;
+    hi = half;
+  } else {
+    double s2 = 0.0;
+    for (int i = lane; i < K; i += 32) { const double wi = W[i]; s2 += rho * wi * wi; }
+    hi = warp_sum(s2);
+  }
+  const int o = left ? j : j + 1;
+  const double dorg = D[o];
+  const double sg = left ? 1.0 : -1.0;
+  long long lob = 0, hib = __double_as_longlong(hi);
+  while (hib - lob > 1) {
+    const long long midb = lob + ((hib - lob) >> 1);
+    const double mu = sg * __longlong_as_double(midb);
+    double g = 0.0;
+    for (int i = lane; i < K; i += 32) { const double wi = W[i]; g += rho * wi * wi / ((D[i] - dorg) - mu); }
+    g = 1.0 + warp_sum(g);
+    const bool before = left ? (g < 0.0) : (g > 0.0);
+    if (before) lob = midb; else hib = midb;
+  }
+  const double mu = sg * __longlong_as_double(hib);
+  if (lane == 0) lam[lo + j] = dorg + mu;
+  for (int i = lane; i < k; i += 32) vrow[i] = i < K ? (D[i] - dorg) - mu : 0.0;
+}
+
+// Loewner: what_i = sign(w_i) sqrt(-prod_j delta_j[i] / prod_{j != i} (dl_i - dl_j)); one thread per i < K
+__global__ void __launch_bounds__(128) dc_lowner_kernel(const EighMerge* __restrict__ merges, const int* __restrict__ Kp, const double* __restrict__ dl,
+                                                        const double* __restrict__ wz, const double* __restrict__ VT, int64_t ldq, double* __restrict__ what) {
+  const EighMerge mg = merges[blockIdx.y];
+  const int lo = mg.lo;
+  const int K = Kp[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const double* D = dl + lo;
+  const double di = D[i];
+  const double* col = VT + (size_t)lo * ldq + lo + i;
+  double p = col[(size_t)i * ldq];
+  for (int j = 0; j < K; ++j)
+    if (j != i) p *= col[(size_t)j * ldq] / (di - D[j]);
+  what[lo + i] = copysign(sqrt(fabs(p)), wz[lo + i]);
+}
+
+// eigenvectors of the rank-one update: row j of VT <- normalised what_i / delta_j[i]; one warp per j < K
+__global__ void __launch_bounds__(256) dc_vectors_kernel(const EighMerge* __restrict__ merges, const int* __restrict__ Kp, const double* __restrict__ what,
+                                                         double* __restrict__ VT, int64_t ldq) {
+  const EighMerge mg = merges[blockIdx.y];
+  const int lo = mg.lo;
+  const int K = Kp[blockIdx.y];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int j = blockIdx.x * nw + wid;
+  if (j >= K) return;
+  double* vrow = VT + (size_t)(lo + j) * ldq + lo;
+  const double* Wh = what + lo;
+  double s2 = 0.0;
+  for (int i = lane; i < K; i += 32) {
+    const double x = Wh[i] / vrow[i];
+    vrow[i] = x;
+    s2 += x * x;
+  }
+  s2 = warp_sum(s2);
+  const double inv = 1.0 / sqrt(s2);
+  for (int i = lane; i < K; i += 32) vrow[i] *= inv;
+}
+
+// final order: rank of every eigenvalue (ascending, ties by index) -> order[rank] = index; W[rank] = lam * scales
+__global__ void eigh_rank_kernel(const double* __restrict__ lam, int n, const double* __restrict__ scal, int* __restrict__ order, double* __restrict__ W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double li = lam[i];
+  int rk = 0;
+  for (int u = 0; u < n; ++u) {
+    const double lu = lam[u];
+    rk += (lu < li || (lu == li && u < i)) ? 1 : 0;
+  }
+  order[rk] = i;
+  W[rk] = li * scal[1] * scal[0];
+}
+
+// out[k][i] = Q[i][order[k]]  (32 x 32 tiles through shared memory)
+__global__ void eigh_gather_transpose_kernel(const double* __restrict__ Q, int64_t ldq, int n, const int* __restrict__ order, double* __restrict__ out,
+                                             int64_t ldo) {
+  __shared__ double t[32][33];
+  const int k0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int kk = k0 + tx;
+  const int col = kk < n ? order[kk] : 0;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r;
+    t[r][tx] = (i < n && kk < n) ? Q[(size_t)i * ldq + col] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, i = i0 + tx;
+    if (k < n && i < n) out[(size_t)k * ldo + i] = t[tx][r];
+  }
+}
+
+// rows of Z (eigenvectors of T, one per row) <- Q z with Q = H_0 H_1 ... H_{n-3}: reflectors applied last to first. One warp per
+// vector, the vector in shared memory, reflector j read from row j of S (columns > j, v[j+1] = 1 stored explicitly).
+__global__ void __launch_bounds__(256) eigh_backtransform_kernel(const double* __restrict__ S, int64_t lds, const double* __restrict__ tau, int n,
+                                                                 double* __restrict__ Z, int64_t ldz) {
+  extern __shared__ double zs[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int k = blockIdx.x * nw + wid;
+  if (k >= n) return;
+  double* z = zs + (size_t)wid * n;
+  double* zrow = Z + (size_t)k * ldz;
+  for (int c = lane; c < n; c += 32) z[c] = zrow[c];
+  __syncwarp();
+  for (int j = n - 3; j >= 0; --j) {
+    const double tj = tau[j];
+    if (tj == 0.0) continue;
+    const double* vj = S + (size_t)j * lds;
+    const int c0 = (j + 1) & ~31;
+    double dot = 0.0;
+    for (int c = c0 + lane; c < n; c += 32)
+      if (c > j) dot += __ldg(vj + c) * z[c];
+    dot = warp_sum(dot) * tj;
+    for (int c = c0 + lane; c < n; c += 32)
+      if (c > j) z[c] -= dot * __ldg(vj + c);
+    __syncwarp();
+  }
+  for (int c = lane; c < n; c += 32) zrow[c] = z[c];
+}
+
+}  // namespace plb

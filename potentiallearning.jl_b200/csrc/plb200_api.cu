@@ -23,6 +23,7 @@
 #include "hoststage.h"
 #include "prelude.cuh"
 #include "syrk.cuh"
+#include "eigh.cuh"
 
 using namespace plb;
 
@@ -130,6 +131,12 @@ enum WsSlot {
   WS_POS_C,
   WS_POS_D,
   WS_MET,
+  WS_EIGH_S,
+  WS_EIGH_QA,
+  WS_EIGH_QB,
+  WS_EIGH_VT,
+  WS_EIGH_SMALL,
+  WS_EIGH_TAB,
   WS_NSLOTS
 };
 
@@ -1248,12 +1255,188 @@ int cusolver_ready() {
   return PL_OK;
 }
 
+// ---- the library-free path (eigh.cuh): Householder tridiagonalisation in one cooperative kernel, divide and conquer with the eigenvector
+// updates on the DMMA Gram engine, back-transformation. Chosen by eigh_dev_impl for n <= PLB200_EIGH_OWN_MAX (default 2048; the matrix and
+// its three work matrices live in L2); PLB200_EIGH=cusolver / own forces one path.
+struct EighTree {
+  int n = -1;
+  std::vector<int2> leaves;
+  std::vector<std::vector<EighMerge>> levels;  // by height: children are complete before their parent
+  int kmax = 0;
+};
+EighTree g_eigh_tree;
+
+int eigh_build_node(EighTree& t, int lo, int hi) {  // returns the height
+  if (hi - lo <= EIGH_LEAF) {
+    t.leaves.push_back(make_int2(lo, hi));
+    return 0;
+  }
+  int m = (lo + hi) / 2;
+  m += (m - lo) & 1;  // even child offsets: the blocks stay 16-byte aligned for the TMA operands of the Gram engine
+  const int hl = eigh_build_node(t, lo, m), hr = eigh_build_node(t, m, hi);
+  const int h = 1 + (hl > hr ? hl : hr);
+  if ((int)t.levels.size() < h) t.levels.resize(h);
+  t.levels[h - 1].push_back(EighMerge{lo, m, hi});
+  if (hi - lo > t.kmax) t.kmax = hi - lo;
+  return h;
+}
+
+int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vectors, double* dW, cudaStream_t st) {
+  const int n = (int)n64;
+  if (n > EIGH_MAX_N) return set_err(PL_EINVAL, "the built-in eigensolver takes n <= %d", EIGH_MAX_N);
+  EighTree& T = g_eigh_tree;
+  if (T.n != n) {
+    T = EighTree();
+    T.n = n;
+    eigh_build_node(T, 0, n);
+  }
+  const int64_t ldq = (n + 3) & ~(int64_t)3;
+  const int lower = (fill & PL_FILL_RM_LOWER) ? 1 : 0;
+  void *pS, *pQA, *pQB, *pVT, *pSmall, *pTab;
+  PL_TRY(ws_get(WS_EIGH_S, (size_t)n * ldq * 8, &pS));
+  PL_TRY(ws_get(WS_EIGH_QA, (size_t)n * ldq * 8, &pQA));
+  PL_TRY(ws_get(WS_EIGH_QB, (size_t)n * ldq * 8, &pQB));
+  PL_TRY(ws_get(WS_EIGH_VT, (size_t)n * ldq * 8, &pVT));
+  // small arrays (doubles): d e tau p rowbuf(2) lam dl wz what pd(256) rot(4n) scal(8) bar(8) ; ints: perm order nrot Kp ; rho per merge
+  const size_t np8 = ((size_t)n + 7) & ~(size_t)7;
+  const size_t nmerge_max = np8;
+  const size_t small_doubles = np8 * 10 + 256 + 4 * np8 + 8 + 8 + nmerge_max;
+  const size_t small_ints = np8 * 2 + 2 * nmerge_max;
+  PL_TRY(ws_get(WS_EIGH_SMALL, small_doubles * 8 + small_ints * 4, &pSmall));
+  double* sd = (double*)pSmall;
+  double *d_d = sd, *d_e = sd + np8, *d_tau = sd + 2 * np8, *d_p = sd + 3 * np8, *d_rowbuf = sd + 4 * np8 /* 2 n, contiguous */,
+         *d_lam = sd + 6 * np8, *d_dl = sd + 7 * np8, *d_wz = sd + 8 * np8, *d_what = sd + 9 * np8, *d_pd = sd + 10 * np8;
+  double4* d_rot = (double4*)(d_pd + 256);
+  double* d_scal = (double*)(d_rot + np8);
+  unsigned long long* d_bar = (unsigned long long*)(d_scal + 8);
+  double* d_rho = (double*)(d_bar + 8);
+  int* si = (int*)(d_rho + nmerge_max);
+  int *d_perm = si, *d_order = si + np8, *d_nrot = si + 2 * np8, *d_Kp = si + 2 * np8 + nmerge_max;
+
+  // tables: leaves, then per level: merges, rows, row2merge
+  std::vector<int> tab;
+  auto push = [&](const void* src, size_t nints) {
+    const size_t at = tab.size();
+    tab.resize(at + ((nints + 3) & ~(size_t)3));
+    memcpy(tab.data() + at, src, nints * 4);
+    return at;
+  };
+  const size_t at_leaves = push(T.leaves.data(), T.leaves.size() * 2);
+  struct LevelAt { size_t merges, rows, r2m; int nrows, nm, kmax; };
+  std::vector<LevelAt> lat;
+  for (auto& lv : T.levels) {
+    std::vector<int> rows, r2m;
+    int km = 0;
+    for (size_t mi = 0; mi < lv.size(); ++mi) {
+      for (int i = lv[mi].lo; i < lv[mi].hi; ++i) { rows.push_back(i); r2m.push_back((int)mi); }
+      km = std::max(km, lv[mi].hi - lv[mi].lo);
+    }
+    LevelAt a;
+    a.merges = push(lv.data(), lv.size() * 3);
+    a.rows = push(rows.data(), rows.size());
+    a.r2m = push(r2m.data(), r2m.size());
+    a.nrows = (int)rows.size(); a.nm = (int)lv.size(); a.kmax = km;
+    lat.push_back(a);
+  }
+  PL_TRY(ws_get(WS_EIGH_TAB, tab.size() * 4, &pTab));
+  CUDA_TRY(cudaMemcpyAsync(pTab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));  // tab is a local vector
+  const int* dtab = (const int*)pTab;
+
+  double *S = (double*)pS, *QA = (double*)pQA, *QB = (double*)pQB, *VT = (double*)pVT;
+  CUDA_TRY(cudaMemsetAsync(d_bar, 0, 64, st));
+  CUDA_TRY(cudaMemsetAsync(d_pd, 0, 256 * 8, st));
+  CUDA_TRY(cudaMemsetAsync(QA, 0, (size_t)n * ldq * 8, st));
+  // d_bar[2] doubles as the max-abs accumulator
+  unsigned long long* d_max = d_bar + 2;
+  {
+    int blocks = (int)(((int64_t)n * n + 255) / 256);
+    if (blocks > g.num_sms * 8) blocks = g.num_sms * 8;
+    eigh_maxabs_kernel<<<blocks, 256, 0, st>>>(dA, n, lda, lower, d_max);
+    LAUNCH_CHECK();
+    eigh_symmetrize_kernel<<<blocks, 256, 0, st>>>(dA, n, lda, lower, d_max, S, ldq, d_rowbuf, d_scal);
+    LAUNCH_CHECK();
+  }
+  // 1. tridiagonalisation
+  {
+    SytrdParams P;
+    P.S = S; P.lds = ldq; P.n = n; P.d = d_d; P.e = d_e; P.tau = d_tau; P.p = d_p; P.pd = d_pd; P.rowbuf = d_rowbuf; P.bar = d_bar;
+    const size_t smem = (size_t)3 * ((n + 3) & ~3) * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+      CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * EIGH_MAX_N * 8));
+      CUDA_TRY(cudaFuncSetAttribute(dc_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * EIGH_MAX_N));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done = true;
+    }
+    int G = g.num_sms;
+    const int rows_per_cta = EIGH_SYTRD_THREADS / 32;
+    if (G > (n + rows_per_cta - 1) / rows_per_cta) G = (n + rows_per_cta - 1) / rows_per_cta;
+    if (G > 256) G = 256;
+    if (G < 1) G = 1;
+    void* args[] = {&P};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)eigh_sytrd_kernel, dim3(G), dim3(EIGH_SYTRD_THREADS), args, smem, st));
+    LAUNCH_CHECK();
+  }
+  // 2. divide and conquer
+  dc_leaf_kernel<<<(unsigned)T.leaves.size(), 256, 0, st>>>(d_d, d_e, n, (const int2*)(dtab + at_leaves), d_lam, QA, ldq, d_scal);
+  LAUNCH_CHECK();
+  for (auto& a : lat) {
+    const EighMerge* dm = (const EighMerge*)(dtab + a.merges);
+    DeflateParams D;
+    D.merges = dm; D.e = d_e; D.scal = d_scal; D.lam = d_lam; D.Q = QA; D.ldq = ldq; D.perm = d_perm; D.rot = d_rot; D.nrot = d_nrot; D.Kp = d_Kp;
+    D.rho = d_rho; D.dl = d_dl; D.wz = d_wz;
+    const int dthreads = a.kmax >= 1024 ? 1024 : ((a.kmax + 31) & ~31);
+    dc_deflate_kernel<<<a.nm, dthreads, (size_t)24 * a.kmax, st>>>(D);
+    LAUNCH_CHECK();
+    dc_permute_kernel<<<a.nrows, 256, (size_t)a.kmax * 8, st>>>(dm, dtab + a.r2m, dtab + a.rows, QA, QB, ldq, d_perm, d_rot, d_nrot);
+    LAUNCH_CHECK();
+    dc_secular_kernel<<<dim3((a.kmax + 7) / 8, a.nm), 256, 0, st>>>(dm, d_Kp, d_rho, d_dl, d_wz, d_lam, VT, ldq);
+    LAUNCH_CHECK();
+    dc_lowner_kernel<<<dim3((a.kmax + 127) / 128, a.nm), 128, 0, st>>>(dm, d_Kp, d_dl, d_wz, VT, ldq, d_what);
+    LAUNCH_CHECK();
+    dc_vectors_kernel<<<dim3((a.kmax + 7) / 8, a.nm), 256, 0, st>>>(dm, d_Kp, d_what, VT, ldq);
+    LAUNCH_CHECK();
+    // Q block <- (permuted Q block) V : C[i][j] = sum_l QB[i][l] VT[j][l] on the DMMA Gram engine
+    const std::vector<EighMerge>& lv = T.levels[&a - lat.data()];
+    for (const EighMerge& mg : lv) {
+      const int k = mg.hi - mg.lo;
+      const size_t off = (size_t)mg.lo * ldq + mg.lo;
+      PL_TRY(gram_dev_impl(PL_KERNEL_LINEAR, QB + off, k, ldq, VT + off, k, ldq, k, 1, 0, nullptr, 1.0, 1.0, QA + off, ldq, PL_FILL_FULL, 0, 1, 0, st));
+    }
+  }
+  // 3. order, transpose into the caller's matrix, back-transformation
+  eigh_rank_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_lam, n, d_scal, d_order, dW);
+  LAUNCH_CHECK();
+  if (want_vectors) {
+    eigh_gather_transpose_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), 256, 0, st>>>(QA, ldq, n, d_order, dA, lda);
+    LAUNCH_CHECK();
+    int nw = (int)((200 * 1024) / ((size_t)n * 8));
+    nw = nw > 8 ? 8 : (nw < 1 ? 1 : nw);
+    eigh_backtransform_kernel<<<(n + nw - 1) / nw, nw * 32, (size_t)nw * n * 8, st>>>(S, ldq, d_tau, n, dA, lda);
+    LAUNCH_CHECK();
+  }
+  unsigned long long flags[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(flags, d_bar, 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (flags[1] != 0) return set_err(PL_ECUDA, "eigensolver: a grid barrier of the tridiagonalisation timed out");
+  return PL_OK;
+}
+
 // In place: the `fill` triangle (row-major view) of dA (n x n, leading dimension lda) is read; on return row k of dA is the unit eigenvector of
 // the k-th smallest eigenvalue dW[k] (column k in Julia's column-major view). Synchronises `st` (cuSOLVER reports through a device flag).
 int eigh_dev_impl(double* dA, int64_t n, int64_t lda, int fill, int want_vectors, double* dW, cudaStream_t st) {
   PL_TRY(need_ready());
   if (n <= 0 || lda < n || !dA || !dW) return set_err(PL_EINVAL, "bad arguments");
   if (fill < 1 || fill > 3) return set_err(PL_EINVAL, "bad fill");
+  {
+    const char* mode = getenv("PLB200_EIGH");
+    const char* mx = getenv("PLB200_EIGH_OWN_MAX");
+    int64_t own_max = mx ? atoll(mx) : 2048;
+    if (own_max > EIGH_MAX_N) own_max = EIGH_MAX_N;
+    const bool force_own = mode && !strcmp(mode, "own"), force_lib = mode && !strcmp(mode, "cusolver");
+    if (force_own || (!force_lib && n <= own_max)) return eigh_own_impl(dA, n, lda, fill, want_vectors, dW, st);
+  }
   PL_TRY(cusolver_ready());
   cusolverStatus_t r = cs.SetStream(cs.h, st);
   if (r != CUSOLVER_STATUS_SUCCESS) return set_err(PL_ECUDA, "cusolverDnSetStream failed with status %d", (int)r);
