@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "plb200_api.cu")
 OUT = os.path.join(HERE, "plb200", "libplb200.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("plb200_api.cu", "gram.cuh", "syrk.cuh", "prelude.cuh", "ptx.cuh", "hoststage.h", "multi.inl")] + [
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("plb200_api.cu", "gram.cuh", "syrk.cuh", "prelude.cuh", "ptx.cuh", "hoststage.h", "multi.inl", "eigh.cuh")] + [
     os.path.join(HERE, "..", "include", "plb200.h")
 ]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-pthread", "-shared", "-ldl", "-lpthread"]

@@ -105,29 +105,39 @@ struct SytrdParams {
   double* d;        // n     diagonal of T
   double* e;        // n     off-diagonal of T (e[n-1] unused)
   double* tau;      // n
-  double* p;        // n     A v of the current step (rows written by their owners)
-  double* pd;       // grid  partial v . (A v)
+  double* p;        // 2 x n A v of the current step (rows written by their owners), double-buffered by step parity like rowbuf:
+                    //       a CTA that is already forming the next product must not overwrite what a slower CTA still reads
+  double* pd;       // 2 x 256 partial v . (A v) per CTA, same parity scheme
   double* rowbuf;   // 2 x n broadcast copy of the next row, double-buffered by step parity
-  unsigned long long* bar;  // [0] arrival counter (zeroed by the host), [1] abort flag
+  unsigned long long* bar;  // [0, grid) one slot per CTA (zeroed by the host), [256] abort flag
+  long long* prof;  // NULL, or 4 cycle counters per CTA (thread 0: staging, compute, publish, barrier) -- scripts/eigh_probe.py
 };
 
-// all CTAs are co-resident (cooperative launch). A barrier that is not reached within ~4 s sets the abort flag and every CTA leaves.
-__device__ __forceinline__ bool sytrd_grid_barrier(unsigned long long* bar, unsigned long long target) {
-  __shared__ int s_abort;
+// all CTAs are co-resident (cooperative launch). Grid barrier: fence + atomic add on one counter, thread 0 polls it. Measured against
+// the alternatives on 148 CTAs x 256 threads (scripts/native/gridbar_probe.cu, profiles/r02e_gridbar_probe.json; cycles per publish +
+// barrier + consume): this 3565, red.release counter 4001, eight sub-counters 4298, per-CTA flags 128 B apart polled by one warp of
+// every CTA 4946, slots collected by one CTA + a go word 5700, packed flags 12298. bar[0] counter (zeroed by the host), bar[1028]
+// abort flag: a barrier that is not passed within ~4 s sets it and every CTA leaves.
+constexpr int EIGH_BAR_GO = 1024, EIGH_BAR_ABORT = 1028, EIGH_BAR_WORDS = 1032;
+__device__ __forceinline__ bool sytrd_grid_barrier(unsigned long long* bar, unsigned long long step) {
+  __shared__ int s_ok;
   __syncthreads();
   if (threadIdx.x == 0) {
+    const unsigned long long want = step * gridDim.x;
     __threadfence();
     atomicAdd(bar, 1ull);
-    int ab = 0;
+    int ok = 1;
     const long long t0 = clock64();
-    while (ld_acquire_u64(bar) < target) {
-      if (ld_acquire_u64(bar + 1) != 0ull) { ab = 1; break; }
-      if (clock64() - t0 > 8000000000ll) { atomicExch(bar + 1, 1ull); ab = 1; break; }
+    for (unsigned it = 1; ld_acquire_u64(bar) < want; ++it) {
+      if ((it & 1023u) == 0) {
+        if (ld_acquire_u64(bar + EIGH_BAR_ABORT) != 0ull) { ok = 0; break; }
+        if (clock64() - t0 > 8000000000ll) { atomicExch(bar + EIGH_BAR_ABORT, 1ull); ok = 0; break; }
+      }
     }
-    s_abort = ab;
+    s_ok = ok;
   }
   __syncthreads();
-  return s_abort == 0;
+  return s_ok != 0;
 }
 
 __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_kernel(SytrdParams P) {
@@ -150,13 +160,17 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_kernel(Sytrd
     const int jn = j + 1;
     // ---- phase a: w_j = tau p - (tau/2)(tau p.v) v from the products the row owners wrote before the barrier
     const double* rb = P.rowbuf + (size_t)((j - 1) & 1) * n;
+    const double* pin = P.p + (size_t)((j - 1) & 1) * n;   // written in the previous step
+    const double* pdin = P.pd + ((j - 1) & 1) * 256;
+    double* pout = P.p + (size_t)(j & 1) * n;
+    double* pdout = P.pd + (j & 1) * 256;
     if (j >= 0) {
       const double tau = s_tau;
       double part = 0.0;
-      for (int g = tid; g < G; g += blockDim.x) part += __ldcg(P.pd + g);
+      for (int g = tid; g < G; g += blockDim.x) part += __ldcg(pdin + g);
       const double dot = block_sum(part, red);
       const double alpha = 0.5 * tau * tau * dot;
-      for (int c = jn + tid; c < n; c += blockDim.x) w[c] = tau * __ldcg(P.p + c) - alpha * v[c];
+      for (int c = jn + tid; c < n; c += blockDim.x) w[c] = tau * __ldcg(pin + c) - alpha * v[c];
     }
     __syncthreads();
     // ---- phase b: row jn after update j (every CTA, redundantly) -> d[jn], reflector jn
@@ -204,20 +218,23 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_kernel(Sytrd
         const double vr = v[r], wr = w[r];
         const bool bc = (r == jn + 1);
         double acc = 0.0;
-        if (j >= 0) {
-          for (int c = c0 + lane; c < n; c += 32) {
-            if (c > jn) {
-              double a = __ldcg(row + c);
-              a = a - (vr * w[c] + wr * v[c]);
-              __stcg(row + c, a);
-              acc += a * vn[c];
-              if (bc) __stcg(rbn + c, a);
-            }
+        // eight independent loads in flight per lane (a dependent load per element costs an L2 round trip each)
+        for (int cb = c0 + lane; cb < n; cb += 32 * 8) {
+          double av[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int c = cb + 32 * u;
+            av[u] = (c < n && c > jn) ? __ldcg(row + c) : 0.0;
           }
-        } else {
-          for (int c = c0 + lane; c < n; c += 32) {
-            if (c > jn) {
-              const double a = __ldcg(row + c);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int c = cb + 32 * u;
+            if (c < n && c > jn) {
+              double a = av[u];
+              if (j >= 0) {
+                a = a - (vr * w[c] + wr * v[c]);
+                __stcg(row + c, a);
+              }
               acc += a * vn[c];
               if (bc) __stcg(rbn + c, a);
             }
@@ -225,7 +242,7 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_kernel(Sytrd
         }
         acc = warp_sum(acc);
         if (lane == 0) {
-          __stcg(P.p + r, acc);
+          __stcg(pout + r, acc);
           pdw += vn[r] * acc;
         }
       }
@@ -236,24 +253,201 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_kernel(Sytrd
       }
     }
     const double pdb = block_sum(pdw, red);
-    if (tid == 0) __stcg(P.pd + b, pdb);
+    if (tid == 0) __stcg(pdout + b, pdb);
     // rotate: v <- v_{jn} (w is rebuilt in phase a)
     __syncthreads();
     for (int c = jn + tid; c < n; c += blockDim.x) v[c] = vn[c];
     if (tid == 0) s_tau = s_taun;
-    target += (unsigned long long)G;
+    target += 1ull;
     if (!sytrd_grid_barrier(P.bar, target)) return;
   }
+}
+
+// n <= 8 * gridDim.x: every warp owns ONE row and keeps it in REGISTERS for the whole reduction (lane l holds columns l, l+32, ...); the
+// matrix never travels again. Per step: (1) the CTA forms w = tau p - alpha v and the next row of the updated matrix element-wise in
+// shared memory from the products / broadcast row the owners published before the barrier (every element once per CTA), then the
+// scaled next reflector; (2) every warp updates its row and forms its entry of the next product in the same pass -- a BRANCH-FREE
+// unrolled loop (finished columns are updated with zeros / ignored rather than skipped: a 25-cycle DFMA latency wants independent
+// chunks in flight, and a branch per chunk serialises them: 2500 -> 600 cycles); (3) publish, grid barrier.
+// Nothing is spilled: acquire loads invalidate L1 every step, so a spilled register costs an L2 round trip per reload.
+template <int NCH, int START>
+__device__ __forceinline__ void sytrd_row_update(double (&a)[NCH], const double* __restrict__ svl, const double* __restrict__ swl,
+                                                 const double* __restrict__ svnl, double nvr, double nwr, double (&acc)[4]) {
+#pragma unroll
+  for (int m = START; m < NCH; ++m) {
+    const double an = fma(nwr, svl[32 * m], fma(nvr, swl[32 * m], a[m]));
+    a[m] = an;
+    acc[m & 3] = fma(an, svnl[32 * m], acc[m & 3]);
+  }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_reg_kernel(SytrdParams P) {
+  constexpr int NP = NCH * 32;
+  constexpr int NQ = (NP + EIGH_SYTRD_THREADS - 1) / EIGH_SYTRD_THREADS;
+  __shared__ double svb[2][NP], sw[NP], srn[NP], s_red[8], s_part[8], s_sc[2];
+  const int n = P.n;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int G = gridDim.x, b = blockIdx.x;
+  const int r = b + G * wid;  // this warp's row (>= n: no row)
+  double a[NCH];
+#pragma unroll
+  for (int m = 0; m < NCH; ++m) {
+    const int c = lane + 32 * m;
+    a[m] = (r < n && c < n) ? __ldcg(P.S + (size_t)r * P.lds + c) : 0.0;
+  }
+  for (int c = tid; c < NP; c += EIGH_SYTRD_THREADS) { svb[0][c] = 0.0; svb[1][c] = 0.0; sw[c] = 0.0; srn[c] = 0.0; }
+  __syncthreads();
+  double tau = 0.0;
+  int cur = 0;  // svb[cur] = v_j (zero outside its support), svb[cur ^ 1] <- v_{j+1}
+  unsigned long long target = 0;
+  long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = clock64();  // phase cycle counters of one warp (PLB200_EIGH_PROF)
+#define PLB_PF(i) do { if (P.prof) { const long long t_ = clock64(); pf[i] += t_ - tk; tk = t_; } } while (0)
+  for (int j = -1; j <= n - 2; ++j, cur ^= 1) {
+    const int jn = j + 1;
+    const int m0 = jn >> 5;
+    const int cbase = (jn & ~31) + tid;
+    const double* sv = svb[cur];
+    double* svn = svb[cur ^ 1];
+    // ---- (1) w_j and row jn of the updated matrix, element-wise
+    {
+      const double* rb = P.rowbuf + (size_t)((j - 1) & 1) * n;
+      const double* pin = P.p + (size_t)((j - 1) & 1) * n;
+      const double* pdin = P.pd + ((j - 1) & 1) * 256;
+      double pc[NQ], rbc[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int c = cbase + q * EIGH_SYTRD_THREADS;
+        pc[q] = (c < n && j >= 0) ? __ldcg(pin + c) : 0.0;
+        rbc[q] = c < n ? __ldcg(rb + c) : 0.0;
+      }
+      // the partial dots and p[jn] are fetched by ONE warp per CTA (every thread asking for the same few lines is 6000 requests per
+      // step on ten L2 lines) and handed on through shared memory
+      if (wid == 0) {
+        double dot = 0.0, pjn = 0.0;
+        if (j >= 0) {
+#pragma unroll
+          for (int q = 0; q < 5; ++q) dot += __ldcg(pdin + lane + 32 * q);
+          pjn = __ldcg(pin + jn);
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) {
+          const double al = 0.5 * tau * tau * dot;
+          s_sc[0] = al;
+          s_sc[1] = tau * pjn - al;  // w_j[jn]; v_j[jn] = 1
+        }
+      }
+      __syncthreads();
+      const double alpha = s_sc[0], wjn = s_sc[1];
+      PLB_PF(0);  // loads of p, row, partial dots returned
+      double sig = 0.0;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int c = cbase + q * EIGH_SYTRD_THREADS;
+        if (c >= jn && c < n) {
+          const double vc = sv[c];
+          const double wc = tau * pc[q] - alpha * vc;
+          const double rn = rbc[q] - (wc + wjn * vc);
+          sw[c] = wc;
+          srn[c] = rn;
+          if (c >= jn + 2) sig += rn * rn;
+        }
+      }
+      sig = warp_sum(sig);
+      if (lane == 0) s_red[wid] = sig;
+      PLB_PF(1);  // element-wise w and next row
+    }
+    __syncthreads();
+    PLB_PF(2);  // CTA barrier
+    const double djn = srn[jn];
+    if (jn == n - 1) {
+      if (b == 0 && tid == 0) P.d[jn] = djn;
+      break;
+    }
+    // the scalars of reflector jn (every thread) and the reflector itself, scaled, into the other buffer; the owner stores it
+    const double sigma = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) + ((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]));
+    const double a0 = srn[jn + 1];
+    double beta = a0, taun = 0.0, scl = 0.0;
+    if (sigma > 0.0) {
+      beta = -copysign(sqrt(a0 * a0 + sigma), a0);
+      taun = (beta - a0) / beta;
+      scl = 1.0 / (a0 - beta);
+    }
+    {
+      double* row = P.S + (size_t)jn * P.lds;
+      const bool owner = (jn % G == b);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int c = cbase + q * EIGH_SYTRD_THREADS;
+        if (c < NP) {
+          const double x = (c >= jn + 2 && c < n) ? srn[c] * scl : (c == jn + 1 ? 1.0 : 0.0);
+          svn[c] = x;
+          if (owner && c > jn && c < n) row[c] = x;
+        }
+      }
+      if (tid == 0 && jn >= 1) svn[jn - 1] = 0.0;  // the leading 1 of v_{j-1}; everything before it is zero already
+    }
+    __syncthreads();
+    PLB_PF(3);  // scalars + scaled reflector
+    // ---- (2) own row: rank-2 update with (v_j, w_j), entry of A v_{jn}. Finished columns (c <= jn) see v_{jn} = 0, so whatever their
+    // registers collect is never used; chunks are skipped eight at a time only.
+    double pdw = 0.0;
+    if (r > jn && r < n) {
+      const double nvr = -sv[r], nwr = -sw[r];
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      const double *svl = sv + lane, *swl = sw + lane, *svnl = svn + lane;
+      switch (m0 >> 3) {
+        case 0: sytrd_row_update<NCH, 0>(a, svl, swl, svnl, nvr, nwr, acc); break;
+        case 1: sytrd_row_update<NCH, (8 < NCH ? 8 : 0)>(a, svl, swl, svnl, nvr, nwr, acc); break;
+        case 2: sytrd_row_update<NCH, (16 < NCH ? 16 : 0)>(a, svl, swl, svnl, nvr, nwr, acc); break;
+        case 3: sytrd_row_update<NCH, (24 < NCH ? 24 : 0)>(a, svl, swl, svnl, nvr, nwr, acc); break;
+        default: sytrd_row_update<NCH, (32 < NCH ? 32 : 0)>(a, svl, swl, svnl, nvr, nwr, acc); break;
+      }
+      const double prod = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
+      pdw = svn[r] * prod;
+      if (lane == 0) __stcg(P.p + (size_t)(j & 1) * n + r, prod);
+      if (r == jn + 1) {
+        double* rbn = P.rowbuf + (size_t)(j & 1) * n;
+#pragma unroll
+        for (int m = 0; m < NCH; ++m) {
+          const int c = lane + 32 * m;
+          if (m >= m0 && c > jn && c < n) __stcg(rbn + c, a[m]);
+        }
+      }
+    }
+    if (lane == 0) s_part[wid] = pdw;
+    PLB_PF(4);  // row update, product entry, broadcast row
+    // ---- (3) partial dot and T's entries published (the grid barrier's __syncthreads orders the s_part writes)
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += s_part[q];
+      __stcg(P.pd + (j & 1) * 256 + b, t);
+      if (b == 0) { P.d[jn] = djn; P.e[jn] = beta; P.tau[jn] = taun; }
+    }
+    tau = taun;
+    target += 1ull;
+    PLB_PF(5);  // CTA barrier + publish
+    if (!sytrd_grid_barrier(P.bar, target)) return;
+    PLB_PF(6);  // grid barrier
+  }
+  if (P.prof && lane == 0 && wid == 6) {
+    for (int i = 0; i < 8; ++i) P.prof[8 * b + i] = pf[i];
+  }
+#undef PLB_PF
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
 // divide and conquer on T = tridiag(d, e)
 
 // leaves: cyclic Jacobi (round-robin ordering, 16 disjoint rotations per round) on the <= 32 x 32 diagonal block, torn at both ends.
-// One CTA of 256 threads per leaf. Also (every CTA, redundantly) the scale max(|d|, |e|) of T; scal[1] is written by leaf 0.
+// One CTA of 256 threads per leaf: thread (x, y) owns the 2 x 2 block between rotation pair x and rotation pair y and applies both
+// sides of the round in one pass from one copy of A into the other (two __syncthreads per round). Also (every CTA, redundantly) the
+// scale max(|d|, |e|) of T; scal[1] is written by leaf 0.
 __global__ void __launch_bounds__(256) dc_leaf_kernel(const double* __restrict__ d, const double* __restrict__ e, int n, const int2* __restrict__ leaves,
                                                       double* __restrict__ lam, double* __restrict__ Q, int64_t ldq, double* scal) {
-  __shared__ double A[32][33];
+  __shared__ double Ab[2][32][33];
   __shared__ double V[32][33];
   __shared__ double cs[16][2];
   __shared__ int prs[16][2];
@@ -280,15 +474,17 @@ __global__ void __launch_bounds__(256) dc_leaf_kernel(const double* __restrict__
       } else if (j == i + 1) a = e[lo + i] * inv;
       else if (i == j + 1) a = e[lo + j] * inv;
     }
-    A[i][j] = a;
+    Ab[0][i][j] = a;
     V[i][j] = i == j ? 1.0 : 0.0;
   }
   __syncthreads();
+  int cur = 0;
+  const int kx = tid >> 4, ky = tid & 15;
   for (int sweep = 0; sweep < 24; ++sweep) {
     double off = 0.0, dg = 0.0;
     for (int t = tid; t < 32 * 32; t += blockDim.x) {
       const int i = t >> 5, j = t & 31;
-      const double a = A[i][j];
+      const double a = Ab[cur][i][j];
       if (i == j) dg += a * a; else off += a * a;
     }
     off = block_sum(off, red);
@@ -299,46 +495,48 @@ __global__ void __launch_bounds__(256) dc_leaf_kernel(const double* __restrict__
       if (tid < 16) {
         int p, q;
         if (tid == 0) { p = r; q = 31; }
-        else { p = (r + tid) % 31; q = (r - tid + 31) % 31; }
+        else { p = r + tid; p = p >= 31 ? p - 31 : p; q = r - tid; q = q < 0 ? q + 31 : q; }
         if (p > q) { const int t = p; p = q; q = t; }
-        const double apq = A[p][q];
+        const double apq = Ab[cur][p][q];
         double c = 1.0, s = 0.0;
         if (apq * apq > skip) {
-          const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-          c = 1.0 / sqrt(t * t + 1.0);
+          const double zeta = Ab[cur][q][q] - Ab[cur][p][p];
+          const double t = (zeta >= 0.0 ? 2.0 : -2.0) * apq / (fabs(zeta) + sqrt(zeta * zeta + 4.0 * apq * apq));
+          c = rsqrt(t * t + 1.0);
           s = t * c;
         }
         cs[tid][0] = c; cs[tid][1] = s;
         prs[tid][0] = p; prs[tid][1] = q;
       }
       __syncthreads();
-      // columns: A <- A J, V <- V J
-      for (int t = tid; t < 16 * 32; t += blockDim.x) {
-        const int k = t >> 5, i = t & 31;
-        const double c = cs[k][0], s = cs[k][1];
-        if (s != 0.0) {
-          const int p = prs[k][0], q = prs[k][1];
-          const double ap = A[i][p], aq = A[i][q];
-          A[i][p] = c * ap - s * aq;
-          A[i][q] = s * ap + c * aq;
-          const double vp = V[i][p], vq = V[i][q];
-          V[i][p] = c * vp - s * vq;
-          V[i][q] = s * vp + c * vq;
+      {
+        // A' = J' A J on the 2 x 2 block (rows of pair kx) x (columns of pair ky)
+        const double cx = cs[kx][0], sx = cs[kx][1], cy = cs[ky][0], sy = cs[ky][1];
+        const int px = prs[kx][0], qx = prs[kx][1], py = prs[ky][0], qy = prs[ky][1];
+        const double app = Ab[cur][px][py], apq = Ab[cur][px][qy], aqp = Ab[cur][qx][py], aqq = Ab[cur][qx][qy];
+        // columns: (.,py) <- cy (.,py) - sy (.,qy) ; (.,qy) <- sy (.,py) + cy (.,qy)
+        const double bpp = cy * app - sy * apq, bpq = sy * app + cy * apq;
+        const double bqp = cy * aqp - sy * aqq, bqq = sy * aqp + cy * aqq;
+        // rows: (px,.) <- cx (px,.) - sx (qx,.) ; (qx,.) <- sx (px,.) + cx (qx,.)
+        Ab[cur ^ 1][px][py] = cx * bpp - sx * bqp;
+        Ab[cur ^ 1][px][qy] = cx * bpq - sx * bqq;
+        Ab[cur ^ 1][qx][py] = sx * bpp + cx * bqp;
+        Ab[cur ^ 1][qx][qy] = sx * bpq + cx * bqq;
+        // V <- V J: 16 pairs x 32 rows, two items per thread
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int it = tid + 256 * h;
+          const int k = it >> 5, i = it & 31;
+          const double c = cs[k][0], s2 = cs[k][1];
+          if (s2 != 0.0) {
+            const int p = prs[k][0], q = prs[k][1];
+            const double vp = V[i][p], vq = V[i][q];
+            V[i][p] = c * vp - s2 * vq;
+            V[i][q] = s2 * vp + c * vq;
+          }
         }
       }
-      __syncthreads();
-      // rows: A <- J' A
-      for (int t = tid; t < 16 * 32; t += blockDim.x) {
-        const int k = t >> 5, i = t & 31;
-        const double c = cs[k][0], s = cs[k][1];
-        if (s != 0.0) {
-          const int p = prs[k][0], q = prs[k][1];
-          const double ap = A[p][i], aq = A[q][i];
-          A[p][i] = c * ap - s * aq;
-          A[q][i] = s * ap + c * aq;
-        }
-      }
+      cur ^= 1;
       __syncthreads();
     }
   }
@@ -346,7 +544,7 @@ __global__ void __launch_bounds__(256) dc_leaf_kernel(const double* __restrict__
     const int i = t >> 5, j = t & 31;
     if (i < m && j < m) Q[(size_t)(lo + i) * ldq + lo + j] = V[i][j];
   }
-  if (tid < m) lam[lo + tid] = A[tid][tid];
+  if (tid < m) lam[lo + tid] = Ab[cur][tid][tid];
 }
 
 // per merge: z, sort, deflation (dlaed2's criteria). One CTA per merge, dynamic shared memory 2 k doubles + 2 k ints.
@@ -411,11 +609,13 @@ __global__ void __launch_bounds__(1024) dc_deflate_kernel(DeflateParams P) {
       if (rho * fabs(z[idx]) <= tol) { outp[k - 1 - ndf++] = idx; continue; }
       if (pj < 0) { pj = idx; continue; }
       double s = z[pj], c = z[idx];
-      const double tau = hypot(c, s);
       const double tt = dd[idx] - dd[pj];
-      c /= tau;
-      s = -s / tau;
-      if (fabs(tt * c * s) <= tol) {
+      const double t2 = c * c + s * s;
+      // |t c s| <= tol with c, s the normalised pair: |t z_pj z_idx| <= tol (z_pj^2 + z_idx^2) decides without sqrt or division
+      if (fabs(tt * c * s) <= tol * t2) {
+        const double tau = sqrt(t2);
+        c /= tau;
+        s = -s / tau;
         z[idx] = tau;
         z[pj] = 0.0;
         P.rot[lo + nr++] = make_double4((double)pj, (double)idx, c, s);
@@ -473,7 +673,9 @@ __global__ void __launch_bounds__(256) dc_permute_kernel(const EighMerge* __rest
 }
 
 // secular equation: one warp per new column j of a merge. j < K: root in (dl_j, dl_{j+1}) as (origin, mu); row j of VT <- dl_i - lam_j
-// (i < K), zeros beyond; j >= K (deflated): row j of VT <- e_j.
+// (i < K), zeros beyond; j >= K (deflated): row j of VT <- e_j. NCH > 0: the merge has at most 32 NCH columns and each lane keeps its
+// poles (relative to the origin) and weights in registers during the bisection; NCH = 0: any size, re-read from memory.
+template <int NCH>
 __global__ void __launch_bounds__(256) dc_secular_kernel(const EighMerge* __restrict__ merges, const int* __restrict__ Kp, const double* __restrict__ rhos,
                                                          const double* __restrict__ dl, const double* __restrict__ wz, double* __restrict__ lam,
                                                          double* __restrict__ VT, int64_t ldq) {
@@ -494,29 +696,62 @@ __global__ void __launch_bounds__(256) dc_secular_kernel(const EighMerge* __rest
   const bool last = (j == K - 1);
   const double dj = D[j];
   const double gap = last ? 0.0 : D[j + 1] - dj;
+  constexpr int NR = NCH > 0 ? NCH : 1;
+  double tr[NR], rr[NR];  // pole - origin, rho w^2 (an absent pole: weight 0, far away)
+  if (NCH > 0) {
+#pragma unroll
+    for (int m = 0; m < NR; ++m) {
+      const int i = lane + 32 * m;
+      const double wi = i < K ? W[i] : 0.0;
+      rr[m] = rho * wi * wi;
+      tr[m] = i < K ? D[i] - dj : 1e300;
+    }
+  }
   bool left = true;
   double hi = 0.0;
   if (!last) {
     const double half = 0.5 * gap;
     double f = 0.0;
-    for (int i = lane; i < K; i += 32) { const double wi = W[i]; f += rho * wi * wi / ((D[i] - dj) - half); }
+    if (NCH > 0) {
+#pragma unroll
+      for (int m = 0; m < NR; ++m) f += rr[m] / (tr[m] - half);
+    } else {
+      for (int i = lane; i < K; i += 32) { const double wi = W[i]; f += rho * wi * wi / ((D[i] - dj) - half); }
+    }
     f = 1.0 + warp_sum(f);
     left = f > 0.0;
     hi = half;
   } else {
     double s2 = 0.0;
-    for (int i = lane; i < K; i += 32) { const double wi = W[i]; s2 += rho * wi * wi; }
+    if (NCH > 0) {
+#pragma unroll
+      for (int m = 0; m < NR; ++m) s2 += rr[m];
+    } else {
+      for (int i = lane; i < K; i += 32) { const double wi = W[i]; s2 += rho * wi * wi; }
+    }
     hi = warp_sum(s2);
   }
   const int o = left ? j : j + 1;
   const double dorg = D[o];
+  if (NCH > 0 && !left) {
+#pragma unroll
+    for (int m = 0; m < NR; ++m) {
+      const int i = lane + 32 * m;
+      tr[m] = i < K ? D[i] - dorg : 1e300;
+    }
+  }
   const double sg = left ? 1.0 : -1.0;
   long long lob = 0, hib = __double_as_longlong(hi);
   while (hib - lob > 1) {
     const long long midb = lob + ((hib - lob) >> 1);
     const double mu = sg * __longlong_as_double(midb);
     double g = 0.0;
-    for (int i = lane; i < K; i += 32) { const double wi = W[i]; g += rho * wi * wi / ((D[i] - dorg) - mu); }
+    if (NCH > 0) {
+#pragma unroll
+      for (int m = 0; m < NR; ++m) g += rr[m] / (tr[m] - mu);
+    } else {
+      for (int i = lane; i < K; i += 32) { const double wi = W[i]; g += rho * wi * wi / ((D[i] - dorg) - mu); }
+    }
     g = 1.0 + warp_sum(g);
     const bool before = left ? (g < 0.0) : (g > 0.0);
     if (before) lob = midb; else hib = midb;
@@ -526,21 +761,42 @@ __global__ void __launch_bounds__(256) dc_secular_kernel(const EighMerge* __rest
   for (int i = lane; i < k; i += 32) vrow[i] = i < K ? (D[i] - dorg) - mu : 0.0;
 }
 
-// Loewner: what_i = sign(w_i) sqrt(-prod_j delta_j[i] / prod_{j != i} (dl_i - dl_j)); one thread per i < K
-__global__ void __launch_bounds__(128) dc_lowner_kernel(const EighMerge* __restrict__ merges, const int* __restrict__ Kp, const double* __restrict__ dl,
+// Loewner: what_i = sign(w_i) sqrt(-prod_j delta_j[i] / prod_{j != i} (dl_i - dl_j)). A CTA takes 32 consecutive i (lane = i: the reads of
+// delta are coalesced), its 8 warps split the product over j and multiply their parts through shared memory.
+__global__ void __launch_bounds__(256) dc_lowner_kernel(const EighMerge* __restrict__ merges, const int* __restrict__ Kp, const double* __restrict__ dl,
                                                         const double* __restrict__ wz, const double* __restrict__ VT, int64_t ldq, double* __restrict__ what) {
+  __shared__ double part[8][32];
   const EighMerge mg = merges[blockIdx.y];
   const int lo = mg.lo;
   const int K = Kp[blockIdx.y];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= K) return;
+  if (blockIdx.x * 32 >= K) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   const double* D = dl + lo;
-  const double di = D[i];
-  const double* col = VT + (size_t)lo * ldq + lo + i;
-  double p = col[(size_t)i * ldq];
-  for (int j = 0; j < K; ++j)
-    if (j != i) p *= col[(size_t)j * ldq] / (di - D[j]);
-  what[lo + i] = copysign(sqrt(fabs(p)), wz[lo + i]);
+  double p = 1.0;
+  if (i < K) {
+    const double di = D[i];
+    const double* col = VT + (size_t)lo * ldq + lo + i;
+    for (int jb = wid; jb < K; jb += 8 * 4) {
+      double num[4], den[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = jb + 8 * u;
+        num[u] = j < K ? col[(size_t)j * ldq] : 1.0;
+        den[u] = (j < K && j != i) ? di - D[j] : 1.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) p *= num[u] / den[u];
+    }
+  }
+  part[wid][lane] = p;
+  __syncthreads();
+  if (wid == 0 && i < K) {
+    double t = part[0][lane];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) t *= part[q][lane];
+    what[lo + i] = copysign(sqrt(fabs(t)), wz[lo + i]);
+  }
 }
 
 // eigenvectors of the rank-one update: row j of VT <- normalised what_i / delta_j[i]; one warp per j < K
@@ -624,6 +880,139 @@ __global__ void __launch_bounds__(256) eigh_backtransform_kernel(const double* _
     __syncwarp();
   }
   for (int c = lane; c < n; c += 32) zrow[c] = z[c];
+}
+
+// ---- blocked back-transformation (n <= 2048). Reflectors are taken R at a time, last block first: block b holds reflectors
+// jlow(b) <= j <= jtop(b) = n-3 - R b and H_jlow ... H_jtop = I - V T V' with the upper-triangular T of LAPACK's dlarft (forward,
+// columnwise). eigh_larft_kernel builds every T (one CTA per block); eigh_backtransform_wy_kernel keeps one eigenvector per warp in
+// REGISTERS (lane l holds entries l, l+32, ...), stages V block-wise in shared memory with cp.async (zero-filled up to the diagonal and
+// beyond n, double buffered) and applies z <- z - V (T (V' z)): R independent dot products and R independent updates per stage instead
+// of R dependent reflector applications.
+__device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void* src, bool take) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(take ? 8 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int R>
+__global__ void __launch_bounds__(256) eigh_larft_kernel(const double* __restrict__ S, int64_t lds, const double* __restrict__ tau, int n,
+                                                         double* __restrict__ Tf) {
+  __shared__ double G[R][R];   // G[a][b] = v_a . v_b (a < b), index = j - jlow
+  __shared__ double T[R][R];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int jtop = n - 3 - R * (int)blockIdx.x;
+  const int jlow = jtop - R + 1 > 0 ? jtop - R + 1 : 0;
+  const int nb = jtop - jlow + 1;
+  for (int pr = wid; pr < R * R; pr += 8) {
+    const int a = pr / R, b = pr % R;
+    if (a < b && b < nb) {
+      // v_a has support > jlow + a, v_b > jlow + b >= the former
+      const int jb = jlow + b;
+      const double* va = S + (size_t)(jlow + a) * lds;
+      const double* vb = S + (size_t)jb * lds;
+      double acc = 0.0;
+      for (int c = jb + 1 + lane; c < n; c += 32) acc += __ldg(va + c) * __ldg(vb + c);
+      acc = warp_sum(acc);
+      if (lane == 0) G[a][b] = acc;
+    }
+  }
+  for (int t = tid; t < R * R; t += 256) T[t / R][t % R] = 0.0;
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < nb; ++i) {
+      const double ti = tau[jlow + i];
+      T[i][i] = ti;
+      // T(0:i, i) = -tau_i T(0:i, 0:i) (V(:, 0:i)' v_i)
+      for (int a = 0; a < i; ++a) {
+        double acc = 0.0;
+        for (int b = a; b < i; ++b) acc += T[a][b] * G[b][i];
+        T[a][i] = -ti * acc;
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < R * R; t += 256) Tf[(size_t)blockIdx.x * R * R + t] = T[t / R][t % R];
+}
+
+template <int NCH, int R>
+__global__ void __launch_bounds__(256) eigh_backtransform_wy_kernel(const double* __restrict__ S, int64_t lds, const double* __restrict__ Tf, int n,
+                                                                    double* __restrict__ Z, int64_t ldz) {
+  extern __shared__ double vs[];  // 2 x R x (32 NCH)
+  __shared__ double sT[2][R * R];
+  constexpr int NP = 32 * NCH;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int k = blockIdx.x * 8 + wid;
+  double z[NCH];
+  double* zrow = Z + (size_t)(k < n ? k : 0) * ldz;
+#pragma unroll
+  for (int m = 0; m < NCH; ++m) {
+    const int c = lane + 32 * m;
+    z[m] = (k < n && c < n) ? zrow[c] : 0.0;
+  }
+  const uint32_t vs_u32 = (uint32_t)__cvta_generic_to_shared(vs);
+  auto stage = [&](int blk, int jtop, int buf) {
+    if (jtop >= 0) {
+      const int jlow = jtop - R + 1 > 0 ? jtop - R + 1 : 0;
+      const int cl = (jlow + 1) & ~31;
+      for (int q = 0; q < R; ++q) {
+        const int j = jlow + q;  // rows beyond the block (j > jtop) are zero-filled: they do nothing
+        const double* src = S + (size_t)(j <= jtop ? j : jtop) * lds;
+        const uint32_t dst = vs_u32 + (uint32_t)(((buf * R + q) * NP) * 8);
+        for (int c = cl + tid; c < NP; c += 256) cp_async8_zfill(dst + c * 8, src + (c < n ? c : 0), j <= jtop && c > j && c < n);
+      }
+      if (tid < R * R) sT[buf][tid] = Tf[(size_t)blk * R * R + tid];
+    }
+    cp_async_commit();
+  };
+  stage(0, n - 3, 0);
+  int buf = 0, blk = 0;
+  for (int jtop = n - 3; jtop >= 0; jtop -= R, buf ^= 1, ++blk) {
+    stage(blk + 1, jtop - R, buf ^ 1);  // the other buffer was consumed before the barrier that ended the previous round
+    cp_async_wait<1>();
+    __syncthreads();
+    const int jlow = jtop - R + 1 > 0 ? jtop - R + 1 : 0;
+    const int m0 = (jlow + 1) >> 5;
+    const double* vb = vs + (size_t)(buf * R) * NP + lane;
+    double y[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) y[q] = 0.0;
+#pragma unroll
+    for (int m = 0; m < NCH; ++m) {
+      if (m >= m0) {
+        const double zm = z[m];
+#pragma unroll
+        for (int q = 0; q < R; ++q) y[q] += vb[q * NP + 32 * m] * zm;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) y[q] = warp_sum(y[q]);
+    double u[R];
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+      double t = 0.0;
+#pragma unroll
+      for (int b = a; b < R; ++b) t += sT[buf][a * R + b] * y[b];
+      u[a] = t;
+    }
+#pragma unroll
+    for (int m = 0; m < NCH; ++m) {
+      if (m >= m0) {
+        double zm = z[m];
+#pragma unroll
+        for (int q = 0; q < R; ++q) zm -= vb[q * NP + 32 * m] * u[q];
+        z[m] = zm;
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  if (k < n) {
+#pragma unroll
+    for (int m = 0; m < NCH; ++m) {
+      const int c = lane + 32 * m;
+      if (c < n) zrow[c] = z[m];
+    }
+  }
 }
 
 }  // namespace plb

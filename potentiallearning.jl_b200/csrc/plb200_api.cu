@@ -1300,17 +1300,18 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
   // small arrays (doubles): d e tau p rowbuf(2) lam dl wz what pd(256) rot(4n) scal(8) bar(8) ; ints: perm order nrot Kp ; rho per merge
   const size_t np8 = ((size_t)n + 7) & ~(size_t)7;
   const size_t nmerge_max = np8;
-  const size_t small_doubles = np8 * 10 + 256 + 4 * np8 + 8 + 8 + nmerge_max;
+  const size_t small_doubles = np8 * 11 + 512 + 4 * np8 + 8 + EIGH_BAR_WORDS + nmerge_max + 8 * np8 + 64;
   const size_t small_ints = np8 * 2 + 2 * nmerge_max;
   PL_TRY(ws_get(WS_EIGH_SMALL, small_doubles * 8 + small_ints * 4, &pSmall));
   double* sd = (double*)pSmall;
-  double *d_d = sd, *d_e = sd + np8, *d_tau = sd + 2 * np8, *d_p = sd + 3 * np8, *d_rowbuf = sd + 4 * np8 /* 2 n, contiguous */,
-         *d_lam = sd + 6 * np8, *d_dl = sd + 7 * np8, *d_wz = sd + 8 * np8, *d_what = sd + 9 * np8, *d_pd = sd + 10 * np8;
-  double4* d_rot = (double4*)(d_pd + 256);
+  double *d_d = sd, *d_e = sd + np8, *d_tau = sd + 2 * np8, *d_p = sd + 3 * np8 /* 2 n */, *d_rowbuf = sd + 5 * np8 /* 2 n */,
+         *d_lam = sd + 7 * np8, *d_dl = sd + 8 * np8, *d_wz = sd + 9 * np8, *d_what = sd + 10 * np8, *d_pd = sd + 11 * np8 /* 2 x 256 */;
+  double4* d_rot = (double4*)(d_pd + 512);
   double* d_scal = (double*)(d_rot + np8);
   unsigned long long* d_bar = (unsigned long long*)(d_scal + 8);
-  double* d_rho = (double*)(d_bar + 8);
-  int* si = (int*)(d_rho + nmerge_max);
+  double* d_rho = (double*)(d_bar + EIGH_BAR_WORDS);
+  double* d_Tf = d_rho + nmerge_max;  // R x R per block of R reflectors: <= 8 n + 64 doubles
+  int* si = (int*)(d_Tf + 8 * np8 + 64);
   int *d_perm = si, *d_order = si + np8, *d_nrot = si + 2 * np8, *d_Kp = si + 2 * np8 + nmerge_max;
 
   // tables: leaves, then per level: merges, rows, row2merge
@@ -1344,11 +1345,10 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
   const int* dtab = (const int*)pTab;
 
   double *S = (double*)pS, *QA = (double*)pQA, *QB = (double*)pQB, *VT = (double*)pVT;
-  CUDA_TRY(cudaMemsetAsync(d_bar, 0, 64, st));
-  CUDA_TRY(cudaMemsetAsync(d_pd, 0, 256 * 8, st));
+  CUDA_TRY(cudaMemsetAsync(d_bar, 0, EIGH_BAR_WORDS * 8, st));
+  CUDA_TRY(cudaMemsetAsync(d_pd, 0, 512 * 8, st));
   CUDA_TRY(cudaMemsetAsync(QA, 0, (size_t)n * ldq * 8, st));
-  // d_bar[2] doubles as the max-abs accumulator
-  unsigned long long* d_max = d_bar + 2;
+  unsigned long long* d_max = d_bar + EIGH_BAR_GO + 2;  // a free word of the barrier block: the max-abs accumulator
   {
     int blocks = (int)(((int64_t)n * n + 255) / 256);
     if (blocks > g.num_sms * 8) blocks = g.num_sms * 8;
@@ -1361,22 +1361,43 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
   {
     SytrdParams P;
     P.S = S; P.lds = ldq; P.n = n; P.d = d_d; P.e = d_e; P.tau = d_tau; P.p = d_p; P.pd = d_pd; P.rowbuf = d_rowbuf; P.bar = d_bar;
+    P.prof = getenv("PLB200_EIGH_PROF") ? (long long*)d_rho : nullptr;  // over d_rho/d_Tf: written at the end of sytrd, read back below
     const size_t smem = (size_t)3 * ((n + 3) & ~3) * 8;
     static bool attr_done = false;
     if (!attr_done) {
       CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * EIGH_MAX_N * 8));
       CUDA_TRY(cudaFuncSetAttribute(dc_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * EIGH_MAX_N));
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 8 * 32 * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 16 * 32 * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 32 * 32 * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 64 * 32 * 8));
       attr_done = true;
     }
-    int G = g.num_sms;
     const int rows_per_cta = EIGH_SYTRD_THREADS / 32;
-    if (G > (n + rows_per_cta - 1) / rows_per_cta) G = (n + rows_per_cta - 1) / rows_per_cta;
-    if (G > 256) G = 256;
-    if (G < 1) G = 1;
+    int G = (n + rows_per_cta - 1) / rows_per_cta;
     void* args[] = {&P};
-    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)eigh_sytrd_kernel, dim3(G), dim3(EIGH_SYTRD_THREADS), args, smem, st));
+    const bool reg_path = G <= g.num_sms && G <= 160 && n <= 37 * 32 && !getenv("PLB200_EIGH_NO_REG");
+    if (reg_path) {  // one row per warp, register-resident
+      const void* fn = n <= 256   ? (const void*)eigh_sytrd_reg_kernel<8>
+                       : n <= 512 ? (const void*)eigh_sytrd_reg_kernel<16>
+                       : n <= 768 ? (const void*)eigh_sytrd_reg_kernel<24>
+                       : n <= 1024 ? (const void*)eigh_sytrd_reg_kernel<32>
+                                   : (const void*)eigh_sytrd_reg_kernel<37>;
+      CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(EIGH_SYTRD_THREADS), args, 0, st));
+    } else {
+      if (G > g.num_sms) G = g.num_sms;
+      CUDA_TRY(cudaLaunchCooperativeKernel((const void*)eigh_sytrd_kernel, dim3(G), dim3(EIGH_SYTRD_THREADS), args, smem, st));
+    }
     LAUNCH_CHECK();
+  }
+  if (getenv("PLB200_EIGH_PROF")) {
+    static long long prof[8 * 160];
+    CUDA_TRY(cudaMemcpyAsync(prof, d_rho, sizeof(prof), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int c : {0, 1, 73, 100})
+      fprintf(stderr, "sytrd prof cta %d warp 6: loads %lld elementwise %lld ctabar %lld rowupd %lld product %lld publish %lld gridbar %lld cycles\n", c, prof[8 * c],
+              prof[8 * c + 1], prof[8 * c + 2], prof[8 * c + 3], prof[8 * c + 4], prof[8 * c + 5], prof[8 * c + 6]);
   }
   // 2. divide and conquer
   dc_leaf_kernel<<<(unsigned)T.leaves.size(), 256, 0, st>>>(d_d, d_e, n, (const int2*)(dtab + at_leaves), d_lam, QA, ldq, d_scal);
@@ -1391,9 +1412,17 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
     LAUNCH_CHECK();
     dc_permute_kernel<<<a.nrows, 256, (size_t)a.kmax * 8, st>>>(dm, dtab + a.r2m, dtab + a.rows, QA, QB, ldq, d_perm, d_rot, d_nrot);
     LAUNCH_CHECK();
-    dc_secular_kernel<<<dim3((a.kmax + 7) / 8, a.nm), 256, 0, st>>>(dm, d_Kp, d_rho, d_dl, d_wz, d_lam, VT, ldq);
+    {
+      const dim3 sg((a.kmax + 7) / 8, a.nm);
+      if (a.kmax <= 64) dc_secular_kernel<2><<<sg, 256, 0, st>>>(dm, d_Kp, d_rho, d_dl, d_wz, d_lam, VT, ldq);
+      else if (a.kmax <= 128) dc_secular_kernel<4><<<sg, 256, 0, st>>>(dm, d_Kp, d_rho, d_dl, d_wz, d_lam, VT, ldq);
+      else if (a.kmax <= 256) dc_secular_kernel<8><<<sg, 256, 0, st>>>(dm, d_Kp, d_rho, d_dl, d_wz, d_lam, VT, ldq);
+      else if (a.kmax <= 512) dc_secular_kernel<16><<<sg, 256, 0, st>>>(dm, d_Kp, d_rho, d_dl, d_wz, d_lam, VT, ldq);
+      else if (a.kmax <= 1024) dc_secular_kernel<32><<<sg, 256, 0, st>>>(dm, d_Kp, d_rho, d_dl, d_wz, d_lam, VT, ldq);
+      else dc_secular_kernel<0><<<sg, 256, 0, st>>>(dm, d_Kp, d_rho, d_dl, d_wz, d_lam, VT, ldq);
+    }
     LAUNCH_CHECK();
-    dc_lowner_kernel<<<dim3((a.kmax + 127) / 128, a.nm), 128, 0, st>>>(dm, d_Kp, d_dl, d_wz, VT, ldq, d_what);
+    dc_lowner_kernel<<<dim3((a.kmax + 31) / 32, a.nm), 256, 0, st>>>(dm, d_Kp, d_dl, d_wz, VT, ldq, d_what);
     LAUNCH_CHECK();
     dc_vectors_kernel<<<dim3((a.kmax + 7) / 8, a.nm), 256, 0, st>>>(dm, d_Kp, d_what, VT, ldq);
     LAUNCH_CHECK();
@@ -1411,13 +1440,30 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
   if (want_vectors) {
     eigh_gather_transpose_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), 256, 0, st>>>(QA, ldq, n, d_order, dA, lda);
     LAUNCH_CHECK();
-    int nw = (int)((200 * 1024) / ((size_t)n * 8));
-    nw = nw > 8 ? 8 : (nw < 1 ? 1 : nw);
-    eigh_backtransform_kernel<<<(n + nw - 1) / nw, nw * 32, (size_t)nw * n * 8, st>>>(S, ldq, d_tau, n, dA, lda);
+    if (n <= 2048 && !getenv("PLB200_EIGH_NO_REG")) {
+      const unsigned blocks = (unsigned)((n + 7) / 8);
+      if (n >= 3) {
+#define PLB_BT(NCH, R)                                                                                                     \
+  do {                                                                                                                     \
+    eigh_larft_kernel<R><<<(unsigned)((n - 2 + R - 1) / R), 256, 0, st>>>(S, ldq, d_tau, n, d_Tf);                         \
+    LAUNCH_CHECK();                                                                                                        \
+    eigh_backtransform_wy_kernel<NCH, R><<<blocks, 256, (size_t)2 * R * NCH * 32 * 8, st>>>(S, ldq, d_Tf, n, dA, lda);     \
+  } while (0)
+        if (n <= 256) PLB_BT(8, 8);
+        else if (n <= 512) PLB_BT(16, 8);
+        else if (n <= 1024) PLB_BT(32, 8);
+        else PLB_BT(64, 4);
+#undef PLB_BT
+      }
+    } else {
+      int nw = (int)((200 * 1024) / ((size_t)n * 8));
+      nw = nw > 8 ? 8 : (nw < 1 ? 1 : nw);
+      eigh_backtransform_kernel<<<(n + nw - 1) / nw, nw * 32, (size_t)nw * n * 8, st>>>(S, ldq, d_tau, n, dA, lda);
+    }
     LAUNCH_CHECK();
   }
   unsigned long long flags[2] = {0, 0};
-  CUDA_TRY(cudaMemcpyAsync(flags, d_bar, 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(flags + 1, d_bar + EIGH_BAR_ABORT, 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   if (flags[1] != 0) return set_err(PL_ECUDA, "eigensolver: a grid barrier of the tridiagonalisation timed out");
   return PL_OK;
@@ -1432,7 +1478,7 @@ int eigh_dev_impl(double* dA, int64_t n, int64_t lda, int fill, int want_vectors
   {
     const char* mode = getenv("PLB200_EIGH");
     const char* mx = getenv("PLB200_EIGH_OWN_MAX");
-    int64_t own_max = mx ? atoll(mx) : 2048;
+    int64_t own_max = mx ? atoll(mx) : 1184;  // the register-resident tridiagonalisation (one row per warp, 148 x 8 warps)
     if (own_max > EIGH_MAX_N) own_max = EIGH_MAX_N;
     const bool force_own = mode && !strcmp(mode, "own"), force_lib = mode && !strcmp(mode, "cusolver");
     if (force_own || (!force_lib && n <= own_max)) return eigh_own_impl(dA, n, lda, fill, want_vectors, dW, st);
