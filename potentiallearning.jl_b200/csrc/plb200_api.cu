@@ -1340,23 +1340,27 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
     lat.push_back(a);
   }
   PL_TRY(ws_get(WS_EIGH_TAB, tab.size() * 4, &pTab));
-  CUDA_TRY(cudaMemcpyAsync(pTab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaStreamSynchronize(st));  // tab is a local vector
   const int* dtab = (const int*)pTab;
-
   double *S = (double*)pS, *QA = (double*)pQA, *QB = (double*)pQB, *VT = (double*)pVT;
   CUDA_TRY(cudaMemsetAsync(d_bar, 0, EIGH_BAR_WORDS * 8, st));
   CUDA_TRY(cudaMemsetAsync(d_pd, 0, 512 * 8, st));
   CUDA_TRY(cudaMemsetAsync(QA, 0, (size_t)n * ldq * 8, st));
   unsigned long long* d_max = d_bar + EIGH_BAR_GO + 2;  // a free word of the barrier block: the max-abs accumulator
+  int blocks = (int)(((int64_t)n * n + 255) / 256);
+  if (blocks > g.num_sms * 8) blocks = g.num_sms * 8;
+  eigh_maxabs_kernel<<<blocks, 256, 0, st>>>(dA, n, lda, lower, d_max);
+  LAUNCH_CHECK();
   {
-    int blocks = (int)(((int64_t)n * n + 255) / 256);
-    if (blocks > g.num_sms * 8) blocks = g.num_sms * 8;
-    eigh_maxabs_kernel<<<blocks, 256, 0, st>>>(dA, n, lda, lower, d_max);
-    LAUNCH_CHECK();
-    eigh_symmetrize_kernel<<<blocks, 256, 0, st>>>(dA, n, lda, lower, d_max, S, ldq, d_rowbuf, d_scal);
-    LAUNCH_CHECK();
+    // one synchronisation: the tables are a local vector, and a matrix with Inf / NaN entries is refused like LAPACK's chkfinite does
+    // for eigen(Symmetric) in the reference (NaN compares greater than everything in the bit-pattern maximum)
+    double mx = 0.0;
+    CUDA_TRY(cudaMemcpyAsync(pTab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(&mx, d_max, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (!(mx <= 1.79769313486231570e308)) return set_err(PL_EINVAL, "eigensolver: the matrix contains Infs or NaNs");
   }
+  eigh_symmetrize_kernel<<<blocks, 256, 0, st>>>(dA, n, lda, lower, d_max, S, ldq, d_rowbuf, d_scal);
+  LAUNCH_CHECK();
   // 1. tridiagonalisation
   {
     SytrdParams P;
