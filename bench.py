@@ -347,6 +347,33 @@ def other_configs(dev, peak_tflops, rank, world, sync):
             res["gram_dot_c1"] = {"workload": f"kDPP kernel build: KernelMatrix DotProduct N={n1} d={d1} (BASELINE configs[0]), Symmetric(:U) storage, back-to-back launches (L2-resident: 8 MB result)",
                                   "us_per_matrix": us, "algorithmic_GBps": wbytes / (us * 1e-6) / 1e9, "hbm_peak_GBps": hbm,
                                   "frac_of_hbm_copy_peak": wbytes / (us * 1e-6) / 1e9 / hbm}
+            # ---- the eigendecomposition behind EllEnsemble(K) (config 1, N = 1000) and compute_eigen (config 4, K = 1000): the
+            # built-in solver (csrc/eigh.cuh) next to cuSOLVER Xsyevd on the same kernel matrix, device-resident, vectors wanted
+            def eig_ms(mode):
+                os.environ["PLB200_EIGH"] = mode
+                ts = []
+                for rep in range(5):
+                    A = K1 + K1.T - torch.diag(torch.diagonal(K1))
+                    W = torch.empty(n1, device=dev, dtype=torch.float64)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    _lib.check(lib.pl_eigh_dev(A.data_ptr(), n1, n1, _lib.PL_FILL_FULL, 1, W.data_ptr(), stream()), "pl_eigh_dev")
+                    e1.record()
+                    e1.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                os.environ.pop("PLB200_EIGH", None)
+                return float(np.median(ts[1:])), W, A
+
+            own_ms, W_own, U_own = eig_ms("own")
+            lib_ms, W_lib, _ = eig_ms("cusolver")
+            Kfull = (K1 + K1.T - torch.diag(torch.diagonal(K1)))
+            resid = float((Kfull @ U_own.T - U_own.T * W_own[None, :]).abs().max() / W_own.abs().max())
+            orth = float((U_own @ U_own.T - torch.eye(n1, device=dev, dtype=torch.float64)).abs().max())
+            res["eigh_c1"] = {"workload": f"eigen(Symmetric(K)) of the config-1 kernel matrix (N={n1}; the same size as compute_eigen at K=1000, configs[3]): built-in "
+                                          "tridiagonalisation + divide and conquer + back-transformation, device-resident, eigenvectors wanted",
+                              "ms": own_ms, "cusolver_xsyevd_ms_same_box": lib_ms, "speedup_vs_cusolver": lib_ms / own_ms,
+                              "max_eig_diff_vs_cusolver_rel": float((W_own - W_lib).abs().max() / W_lib.abs().max()),
+                              "residual_rel": resid, "orthogonality": orth}
             del X1, K1
     except Exception as e:  # never let the side measurements take the headline line down
         import traceback

@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(256) dc_permute_kernel(const EighMerge* __rest
 }
 
 // secular equation: one warp per new column j of a merge. j < K: root in (dl_j, dl_{j+1}) as (origin, mu); row j of VT <- dl_i - lam_j
-// (i < K), zeros beyond; j >= K (deflated): row j of VT <- e_j. NCH > 0: the merge has at most 32 NCH columns and each lane keeps its
+// (i < K), zeros beyond; j >= K (deflated): row j of VT <- e_j. The root finder is a bracketed rational iteration (below). NCH > 0: the merge has at most 32 NCH columns and each lane keeps its
 // poles (relative to the origin) and weights in registers during the bisection; NCH = 0: any size, re-read from memory.
 template <int NCH>
 __global__ void __launch_bounds__(256) dc_secular_kernel(const EighMerge* __restrict__ merges, const int* __restrict__ Kp, const double* __restrict__ rhos,
@@ -752,22 +752,48 @@ __global__ void __launch_bounds__(256) dc_secular_kernel(const EighMerge* __rest
     }
   }
   const double sg = left ? 1.0 : -1.0;
+  // nu = |mu| in (0, hi]. The bracket lives on the BIT PATTERNS of nu (lob: g still has the sign it has next to the origin pole, hib:
+  // it has changed or vanished), so a bisection step halves the number of doubles left whatever their scale: <= 63 steps always
+  // terminate. Most steps are not bisections: with g and g' at nu, the model c -/+ s / nu (the origin pole exact, everything else
+  // constant) gives the next nu -- exact for one pole, quadratically convergent in general; a proposal that leaves the bracket or
+  // a run of 40 steps falls back to bisection. Converged as LAPACK's dlaed4 judges it: |g| <= 8 eps (1 + sum |terms|).
   long long lob = 0, hib = __double_as_longlong(hi);
-  while (hib - lob > 1) {
-    const long long midb = lob + ((hib - lob) >> 1);
-    const double mu = sg * __longlong_as_double(midb);
-    double g = 0.0;
+  double nu = hi;
+  for (int it = 0; it < 112; ++it) {
+    const double mu_t = sg * nu;
+    double g = 0.0, gp = 0.0, ga = 0.0;
     if (NCH > 0) {
 #pragma unroll
-      for (int m = 0; m < NR; ++m) g += rr[m] / (tr[m] - mu);
+      for (int m = 0; m < NR; ++m) {
+        const double q = 1.0 / (tr[m] - mu_t), t = rr[m] * q;
+        g += t;
+        ga += fabs(t);
+        gp = fma(t, q, gp);
+      }
     } else {
-      for (int i = lane; i < K; i += 32) { const double wi = W[i]; g += rho * wi * wi / ((D[i] - dorg) - mu); }
+      for (int i = lane; i < K; i += 32) {
+        const double wi = W[i];
+        const double q = 1.0 / ((D[i] - dorg) - mu_t), t = rho * wi * wi * q;
+        g += t;
+        ga += fabs(t);
+        gp = fma(t, q, gp);
+      }
     }
     g = 1.0 + warp_sum(g);
+    ga = 1.0 + warp_sum(ga);
+    gp = warp_sum(gp);
+    const long long bnu = __double_as_longlong(nu);
     const bool before = left ? (g < 0.0) : (g > 0.0);
-    if (before) lob = midb; else hib = midb;
+    if (before) lob = bnu > lob ? bnu : lob; else hib = bnu < hib ? bnu : hib;
+    if (fabs(g) <= 8.0 * EIGH_EPS * ga && ga < INFINITY) break;
+    if (hib - lob <= 1) { nu = __longlong_as_double(hib); break; }
+    const double den = left ? fma(gp, nu, g) : fma(gp, nu, -g);
+    const double prop = gp * nu * nu / den;
+    long long bn = (den > 0.0 && prop > 0.0 && prop < INFINITY) ? __double_as_longlong(prop) : -1;
+    if (it >= 40 || !(bn > lob && bn < hib)) bn = lob + ((hib - lob) >> 1);
+    nu = __longlong_as_double(bn);
   }
-  const double mu = sg * __longlong_as_double(hib);
+  const double mu = sg * nu;
   if (lane == 0) lam[lo + j] = dorg + mu;
   for (int i = lane; i < k; i += 32) vrow[i] = i < K ? (D[i] - dorg) - mu : 0.0;
 }
@@ -830,6 +856,52 @@ __global__ void __launch_bounds__(256) dc_vectors_kernel(const EighMerge* __rest
   s2 = warp_sum(s2);
   const double inv = 1.0 / sqrt(s2);
   for (int i = lane; i < K; i += 32) vrow[i] *= inv;
+}
+
+// Q block <- (permuted Q block) V for the SMALL merges of a level (k <= 128), all of them in one launch: C[i][j] = sum_l QB[i][l] VT[j][l].
+// One CTA per 32 x 32 tile of one merge, operands staged in shared memory (odd pitch), four results per thread. The large merges go to
+// the DMMA Gram engine, one launch each; for k <= 128 its launch costs more than the product (31 launches -> 9 at n = 1000).
+constexpr int EIGH_SMALL_GEMM_MAX = 128;
+__global__ void __launch_bounds__(256) dc_small_gemm_kernel(const EighMerge* __restrict__ merges, const double* __restrict__ QB, const double* __restrict__ VT,
+                                                            double* __restrict__ QA, int64_t ldq) {
+  extern __shared__ double gsm[];
+  const EighMerge mg = merges[blockIdx.y];
+  const int lo = mg.lo, k = mg.hi - mg.lo;
+  const int T = (k + 31) >> 5;
+  if ((int)blockIdx.x >= T * T) return;
+  const int i0 = ((int)blockIdx.x / T) * 32, j0 = ((int)blockIdx.x % T) * 32;
+  const int pitch = k | 1;
+  double* As = gsm;
+  double* Bs = gsm + 32 * pitch;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  for (int rr = ty; rr < 32; rr += 8) {
+    const bool ia = i0 + rr < k, jb = j0 + rr < k;
+    const double* qa = QB + (size_t)(lo + i0 + rr) * ldq + lo;
+    const double* vb = VT + (size_t)(lo + j0 + rr) * ldq + lo;
+    for (int l = tx; l < k; l += 32) {
+      As[rr * pitch + l] = ia ? qa[l] : 0.0;
+      Bs[rr * pitch + l] = jb ? vb[l] : 0.0;
+    }
+  }
+  __syncthreads();
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+  const double* bp = Bs + tx * pitch;
+  const double* ap = As + ty * pitch;
+#pragma unroll 4
+  for (int l = 0; l < k; ++l) {
+    const double bv = bp[l];
+    c0 = fma(ap[l], bv, c0);
+    c1 = fma(ap[8 * pitch + l], bv, c1);
+    c2 = fma(ap[16 * pitch + l], bv, c2);
+    c3 = fma(ap[24 * pitch + l], bv, c3);
+  }
+  if (j0 + tx < k) {
+    double* out = QA + (size_t)(lo + i0) * ldq + lo + j0 + tx;
+    if (i0 + ty < k) out[(size_t)ty * ldq] = c0;
+    if (i0 + ty + 8 < k) out[(size_t)(ty + 8) * ldq] = c1;
+    if (i0 + ty + 16 < k) out[(size_t)(ty + 16) * ldq] = c2;
+    if (i0 + ty + 24 < k) out[(size_t)(ty + 24) * ldq] = c3;
+  }
 }
 
 // final order: rank of every eigenvalue (ascending, ties by index) -> order[rank] = index; W[rank] = lam * scales

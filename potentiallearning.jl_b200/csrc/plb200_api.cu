@@ -1371,6 +1371,7 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
     if (!attr_done) {
       CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * EIGH_MAX_N * 8));
       CUDA_TRY(cudaFuncSetAttribute(dc_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * EIGH_MAX_N));
+      CUDA_TRY(cudaFuncSetAttribute(dc_small_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * (EIGH_SMALL_GEMM_MAX | 1) * 8));
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 8 * 32 * 8));
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 16 * 32 * 8));
@@ -1432,6 +1433,12 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
     LAUNCH_CHECK();
     // Q block <- (permuted Q block) V : C[i][j] = sum_l QB[i][l] VT[j][l] on the DMMA Gram engine
     const std::vector<EighMerge>& lv = T.levels[&a - lat.data()];
+    if (a.kmax <= EIGH_SMALL_GEMM_MAX) {  // every merge of the level in one launch
+      const int tl = (a.kmax + 31) / 32;
+      dc_small_gemm_kernel<<<dim3(tl * tl, a.nm), 256, (size_t)2 * 32 * (a.kmax | 1) * 8, st>>>(dm, QB, VT, QA, ldq);
+      LAUNCH_CHECK();
+      continue;
+    }
     for (const EighMerge& mg : lv) {
       const int k = mg.hi - mg.lo;
       const size_t off = (size_t)mg.lo * ldq + mg.lo;
