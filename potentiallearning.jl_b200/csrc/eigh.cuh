@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(256) dc_leaf_kernel(const double* __restrict__
   if (tid < m) lam[lo + tid] = Ab[cur][tid][tid];
 }
 
-// per merge: z, sort, deflation (dlaed2's criteria). One CTA per merge, dynamic shared memory 2 k doubles + 2 k ints.
+// per merge: z, sort, deflation (dlaed2's criteria). One CTA per merge.
 // Outputs (all indexed from lo): perm[c'] = old column of new column c' (non-deflated ascending, then deflated), rot = (a, b, c, s)
 // column rotations in order, Kp = number of non-deflated, dl / wz = poles and weights of the secular equation, lam = eigenvalues in the
 // new order (the first Kp are overwritten by the secular kernel).
@@ -578,21 +578,56 @@ struct DeflateParams {
   double* wz;
 };
 
+// exclusive prefix sum of one int per thread over the block (blockDim a multiple of 32, <= 1024); *total = the sum. sw: 33 ints.
+__device__ __forceinline__ int block_excl_scan(int v, int* sw, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  __syncthreads();  // sw may still be read from an earlier call
+  if (lane == 31) sw[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    int t = lane < nw ? sw[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += y;
+    }
+    sw[lane] = t;  // inclusive over warps
+  }
+  __syncthreads();
+  *total = sw[nw - 1];
+  return x - v + (wid > 0 ? sw[wid - 1] : 0);
+}
+
+// Dynamic shared memory: 48 k bytes. Everything but the chained close-pole deflations runs in parallel: the weights that vanish
+// (rho |z| <= tol) are found and compacted away by all threads, the close-pole test is evaluated for every neighbouring pair of
+// survivors with their ORIGINAL values, and one thread then walks only the runs that start at a flagged pair (inside a run the
+// rotated values feed the next test, exactly as dlaed2's sequential scan does; after a failed test the state is the original one again).
 __global__ void __launch_bounds__(1024) dc_deflate_kernel(DeflateParams P) {
   extern __shared__ double dsm[];
   __shared__ double red[40];
+  __shared__ int sw[33];
   const EighMerge mg = P.merges[blockIdx.x];
-  const int lo = mg.lo, mid = mg.mid, k = mg.hi - mg.lo, tid = threadIdx.x;
-  double* dd = dsm;
+  const int lo = mg.lo, mid = mg.mid, k = mg.hi - mg.lo, tid = threadIdx.x, nt = blockDim.x;
+  double* dd = dsm;            // original order
   double* z = dsm + k;
-  int* order = (int*)(dsm + 2 * k);
-  int* outp = order + k;
+  double* sd = dsm + 2 * k;    // ascending order
+  double* sz = dsm + 3 * k;
+  int* order = (int*)(dsm + 4 * k);  // order[t] = original index of sorted position t
+  int* surv = order + k;             // sorted positions of the weights that do not vanish
+  int* flag = surv + k;              // per survivor: 1 = the pair (s-1, s) deflates with original values; later 2 = deflated by a rotation
+  int* outp = flag + k;              // new column -> sorted position
   const double beta = P.e[mid - 1] * (1.0 / P.scal[1]);  // as the leaves scale
   const double rho = 2.0 * fabs(beta);
   const double sgn = beta < 0.0 ? -1.0 : 1.0;
   const double rs = 0.70710678118654752440;
   double mx = 0.0;
-  for (int i = tid; i < k; i += blockDim.x) {
+  for (int i = tid; i < k; i += nt) {
     const double di = P.lam[lo + i];
     const double zi = (lo + i < mid ? P.Q[(size_t)(mid - 1) * P.ldq + lo + i] : sgn * P.Q[(size_t)mid * P.ldq + lo + i]) * rs;
     dd[i] = di;
@@ -602,7 +637,7 @@ __global__ void __launch_bounds__(1024) dc_deflate_kernel(DeflateParams P) {
   mx = block_max(mx, red);
   const double tol = 8.0 * EIGH_EPS * mx;
   // rank sort (ties by index)
-  for (int i = tid; i < k; i += blockDim.x) {
+  for (int i = tid; i < k; i += nt) {
     const double di = dd[i];
     int rk = 0;
     for (int u = 0; u < k; ++u) {
@@ -610,49 +645,84 @@ __global__ void __launch_bounds__(1024) dc_deflate_kernel(DeflateParams P) {
       rk += (du < di || (du == di && u < i)) ? 1 : 0;
     }
     order[rk] = i;
+    sd[rk] = di;
+    sz[rk] = z[i];
+  }
+  __syncthreads();
+  // vanishing weights out (to the end of the new order), survivors compacted in ascending order
+  const int per = (k + nt - 1) / nt;
+  const int t0 = tid * per, t1 = t0 + per < k ? t0 + per : k;
+  int cnt = 0;
+  for (int t = t0; t < t1; ++t) cnt += (rho * fabs(sz[t]) <= tol) ? 0 : 1;
+  int ns;
+  int at = block_excl_scan(cnt, sw, &ns);
+  for (int t = t0; t < t1; ++t) {
+    if (rho * fabs(sz[t]) <= tol) outp[k - 1 - (t - at)] = t;  // at = survivors before t, so (t - at) vanishing weights precede t
+    else { surv[at] = t; ++at; }
+  }
+  __syncthreads();
+  const int nsmall = k - ns;
+  // close-pole test on the original values, every neighbouring pair of survivors
+  for (int s2 = tid; s2 < ns; s2 += nt) {
+    int f = 0;
+    if (s2 > 0) {
+      const int a = surv[s2 - 1], b2 = surv[s2];
+      const double c = sz[b2], sn = sz[a], tt = sd[b2] - sd[a];
+      f = fabs(tt * c * sn) <= tol * (c * c + sn * sn) ? 1 : 0;
+    }
+    flag[s2] = f;
   }
   __syncthreads();
   if (tid == 0) {
-    int nnd = 0, ndf = 0, nr = 0, pj = -1;
-    // non-deflated go to outp[0..) in ascending order, deflated to outp[k-1], outp[k-2], ... (their order is immaterial)
-    for (int t = 0; t < k; ++t) {
-      const int idx = order[t];
-      if (rho * fabs(z[idx]) <= tol) { outp[k - 1 - ndf++] = idx; continue; }
-      if (pj < 0) { pj = idx; continue; }
-      double s = z[pj], c = z[idx];
-      const double tt = dd[idx] - dd[pj];
-      const double t2 = c * c + s * s;
-      // |t c s| <= tol with c, s the normalised pair: |t z_pj z_idx| <= tol (z_pj^2 + z_idx^2) decides without sqrt or division
-      if (fabs(tt * c * s) <= tol * t2) {
+    int nr = 0;
+    for (int s2 = 1; s2 < ns; ++s2) {
+      if (flag[s2] != 1) continue;
+      int a = surv[s2 - 1];
+      int sa = s2 - 1;
+      for (; s2 < ns; ++s2) {  // a run: the rotated pole / weight at `a` meets the next survivor
+        const int b2 = surv[s2];
+        double c = sz[b2], sn = sz[a];
+        const double tt = sd[b2] - sd[a];
+        const double t2 = c * c + sn * sn;
+        if (!(fabs(tt * c * sn) <= tol * t2)) break;
         const double tau = sqrt(t2);
         c /= tau;
-        s = -s / tau;
-        z[idx] = tau;
-        z[pj] = 0.0;
-        P.rot[lo + nr++] = make_double4((double)pj, (double)idx, c, s);
-        const double t1 = dd[pj] * c * c + dd[idx] * s * s;
-        dd[idx] = dd[pj] * s * s + dd[idx] * c * c;
-        dd[pj] = t1;
-        outp[k - 1 - ndf++] = pj;
-        pj = idx;
-      } else {
-        outp[nnd++] = pj;
-        pj = idx;
+        sn = -sn / tau;
+        sz[b2] = tau;
+        sz[a] = 0.0;
+        P.rot[lo + nr++] = make_double4((double)order[a], (double)order[b2], c, sn);
+        const double d1 = sd[a] * c * c + sd[b2] * sn * sn;
+        sd[b2] = sd[a] * sn * sn + sd[b2] * c * c;
+        sd[a] = d1;
+        flag[sa] = 2;
+        a = b2;
+        sa = s2;
       }
+      // the pair that ended the run was tested with a rotated left member; the next pair starts from original values again
+      if (s2 < ns && flag[s2] == 1) flag[s2] = 0;
     }
-    if (pj >= 0) outp[nnd++] = pj;
     P.nrot[blockIdx.x] = nr;
-    P.Kp[blockIdx.x] = nnd;
     P.rho[blockIdx.x] = rho;
-    order[0] = nnd;  // broadcast
   }
   __syncthreads();
-  const int K = order[0];
-  for (int i = tid; i < k; i += blockDim.x) {
-    const int src = outp[i];
-    P.perm[lo + i] = src;
-    P.lam[lo + i] = dd[src];
-    if (i < K) { P.dl[lo + i] = dd[src]; P.wz[lo + i] = z[src]; }
+  // second compaction: survivors that were not rotated away stay (ascending), the rotated-away ones join the deflated end
+  const int per2 = (ns + nt - 1) / nt;
+  const int u0 = tid * per2 < ns ? tid * per2 : ns, u1 = u0 + per2 < ns ? u0 + per2 : ns;
+  int cnt2 = 0;
+  for (int u = u0; u < u1; ++u) cnt2 += flag[u] == 2 ? 0 : 1;
+  int K;
+  int at2 = block_excl_scan(cnt2, sw, &K);
+  for (int u = u0; u < u1; ++u) {
+    if (flag[u] == 2) outp[k - 1 - nsmall - (u - at2)] = surv[u];
+    else { outp[at2] = surv[u]; ++at2; }
+  }
+  if (tid == 0) P.Kp[blockIdx.x] = K;
+  __syncthreads();
+  for (int i = tid; i < k; i += nt) {
+    const int t = outp[i];
+    P.perm[lo + i] = order[t];
+    P.lam[lo + i] = sd[t];
+    if (i < K) { P.dl[lo + i] = sd[t]; P.wz[lo + i] = sz[t]; }
   }
 }
 

@@ -1370,7 +1370,7 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
     static bool attr_done = false;
     if (!attr_done) {
       CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * EIGH_MAX_N * 8));
-      CUDA_TRY(cudaFuncSetAttribute(dc_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * EIGH_MAX_N));
+      CUDA_TRY(cudaFuncSetAttribute(dc_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * EIGH_MAX_N));
       CUDA_TRY(cudaFuncSetAttribute(dc_small_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * (EIGH_SMALL_GEMM_MAX | 1) * 8));
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 8 * 32 * 8));
@@ -1413,7 +1413,7 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
     D.merges = dm; D.e = d_e; D.scal = d_scal; D.lam = d_lam; D.Q = QA; D.ldq = ldq; D.perm = d_perm; D.rot = d_rot; D.nrot = d_nrot; D.Kp = d_Kp;
     D.rho = d_rho; D.dl = d_dl; D.wz = d_wz;
     const int dthreads = a.kmax >= 1024 ? 1024 : ((a.kmax + 31) & ~31);
-    dc_deflate_kernel<<<a.nm, dthreads, (size_t)24 * a.kmax, st>>>(D);
+    dc_deflate_kernel<<<a.nm, dthreads, (size_t)48 * a.kmax, st>>>(D);
     LAUNCH_CHECK();
     dc_permute_kernel<<<a.nrows, 256, (size_t)a.kmax * 8, st>>>(dm, dtab + a.r2m, dtab + a.rows, QA, QB, ldq, d_perm, d_rot, d_nrot);
     LAUNCH_CHECK();
