@@ -271,19 +271,36 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_kernel(Sytrd
 
 // n <= 8 * gridDim.x: every warp owns ONE row and keeps it in REGISTERS for the whole reduction (lane l holds columns l, l+32, ...); the
 // matrix never travels again. Per step: (1) the CTA forms w = tau p - alpha v and the next row of the updated matrix element-wise in
-// shared memory from the products / broadcast row the owners published before the barrier (every element once per CTA), then the
-// scaled next reflector; (2) every warp updates its row and forms its entry of the next product in the same pass -- a BRANCH-FREE
+// shared memory from the products / broadcast row the owners published before the barrier (every element once per CTA); (2) every
+// warp updates its row, forms its entry of the next product and sums the norm of the next reflector in the same pass -- a BRANCH-FREE
 // unrolled loop (finished columns are updated with zeros / ignored rather than skipped: a 25-cycle DFMA latency wants independent
 // chunks in flight, and a branch per chunk serialises them: 2500 -> 600 cycles); (3) publish, grid barrier.
 // Nothing is spilled: acquire loads invalidate L1 every step, so a spilled register costs an L2 round trip per reload.
-template <int NCH, int START>
-__device__ __forceinline__ void sytrd_row_update(double (&a)[NCH], const double* __restrict__ svl, const double* __restrict__ swl,
-                                                 const double* __restrict__ svnl, double nvr, double nwr, double (&acc)[4]) {
+template <int NCH, int START, bool LIVE>
+__device__ __forceinline__ void sytrd_row_pass(double (&a)[NCH], const double* __restrict__ svl, const double* __restrict__ swl,
+                                               const double* __restrict__ srnl, double nvr, double nwr, int mq, double (&acc)[4], double (&sg)[4],
+                                               double& cap) {
 #pragma unroll
   for (int m = START; m < NCH; ++m) {
-    const double an = fma(nwr, svl[32 * m], fma(nvr, swl[32 * m], a[m]));
-    a[m] = an;
-    acc[m & 3] = fma(an, svnl[32 * m], acc[m & 3]);
+    const double rn = srnl[32 * m];
+    sg[m & 3] = fma(rn, rn, sg[m & 3]);
+    if (LIVE) {
+      const double an = fma(nwr, svl[32 * m], fma(nvr, swl[32 * m], a[m]));
+      a[m] = an;
+      acc[m & 3] = fma(an, rn, acc[m & 3]);
+      cap = m == mq ? an : cap;
+    }
+  }
+}
+template <int NCH, bool LIVE>
+__device__ __forceinline__ void sytrd_row_pass_from(int m0, double (&a)[NCH], const double* svl, const double* swl, const double* srnl, double nvr,
+                                                    double nwr, int mq, double (&acc)[4], double (&sg)[4], double& cap) {
+  switch (m0 >> 3) {  // finished chunks are skipped eight at a time only: no branch inside the unrolled pass
+    case 0: sytrd_row_pass<NCH, 0, LIVE>(a, svl, swl, srnl, nvr, nwr, mq, acc, sg, cap); break;
+    case 1: sytrd_row_pass<NCH, (8 < NCH ? 8 : 0), LIVE>(a, svl, swl, srnl, nvr, nwr, mq, acc, sg, cap); break;
+    case 2: sytrd_row_pass<NCH, (16 < NCH ? 16 : 0), LIVE>(a, svl, swl, srnl, nvr, nwr, mq, acc, sg, cap); break;
+    case 3: sytrd_row_pass<NCH, (24 < NCH ? 24 : 0), LIVE>(a, svl, swl, srnl, nvr, nwr, mq, acc, sg, cap); break;
+    default: sytrd_row_pass<NCH, (32 < NCH ? 32 : 0), LIVE>(a, svl, swl, srnl, nvr, nwr, mq, acc, sg, cap); break;
   }
 }
 
@@ -291,7 +308,9 @@ template <int NCH>
 __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_reg_kernel(SytrdParams P) {
   constexpr int NP = NCH * 32;
   constexpr int NQ = (NP + EIGH_SYTRD_THREADS - 1) / EIGH_SYTRD_THREADS;
-  __shared__ double svb[2][NP], sw[NP], srn[NP], s_red[8], s_part[8], s_sc[2];
+  // srn: row jn of the updated matrix from column jn + 2 on (zero before: columns <= jn + 1 of every earlier step were written as zero
+  // and are never touched again, so no pass needs a lower bound inside its first chunk); its entries jn and jn + 1 travel in s_sc
+  __shared__ double svb[2][NP], sw[NP], srn[NP], s_part[8], s_sc[4];
   const int n = P.n;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int G = gridDim.x, b = blockIdx.x;
@@ -346,7 +365,6 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_reg_kernel(S
       __syncthreads();
       const double alpha = s_sc[0], wjn = s_sc[1];
       PLB_PF(0);  // loads of p, row, partial dots returned
-      double sig = 0.0;
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int c = cbase + q * EIGH_SYTRD_THREADS;
@@ -355,24 +373,35 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_reg_kernel(S
           const double wc = tau * pc[q] - alpha * vc;
           const double rn = rbc[q] - (wc + wjn * vc);
           sw[c] = wc;
-          srn[c] = rn;
-          if (c >= jn + 2) sig += rn * rn;
+          srn[c] = c >= jn + 2 ? rn : 0.0;
+          if (c == jn) s_sc[2] = rn;
+          if (c == jn + 1) s_sc[3] = rn;
         }
       }
-      sig = warp_sum(sig);
-      if (lane == 0) s_red[wid] = sig;
       PLB_PF(1);  // element-wise w and next row
     }
     __syncthreads();
     PLB_PF(2);  // CTA barrier
-    const double djn = srn[jn];
+    const double djn = s_sc[2];
     if (jn == n - 1) {
       if (b == 0 && tid == 0) P.d[jn] = djn;
       break;
     }
-    // the scalars of reflector jn (every thread) and the reflector itself, scaled, into the other buffer; the owner stores it
-    const double sigma = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) + ((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]));
-    const double a0 = srn[jn + 1];
+    const double a0 = s_sc[3];
+    // ---- (2) one pass over the own row: rank-2 update with (v_j, w_j), the row's entry of A v_{jn} (unscaled: the reflector's
+    // scalars are not known yet -- they need sigma, which every warp sums in this same pass), and the entry in column jn + 1
+    const bool live = r > jn && r < n;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0}, sg[4] = {0.0, 0.0, 0.0, 0.0}, cap = 0.0;
+    const int mq = (jn + 1) >> 5;
+    if (live) sytrd_row_pass_from<NCH, true>(m0, a, sv + lane, sw + lane, srn + lane, -sv[r], -sw[r], mq, acc, sg, cap);
+    else sytrd_row_pass_from<NCH, false>(m0, a, sv + lane, sw + lane, srn + lane, 0.0, 0.0, mq, acc, sg, cap);
+    double sigma = (sg[0] + sg[1]) + (sg[2] + sg[3]), accs = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {  // two reductions, interleaved
+      sigma += __shfl_xor_sync(0xffffffffu, sigma, o);
+      accs += __shfl_xor_sync(0xffffffffu, accs, o);
+    }
+    const double acc0 = __shfl_sync(0xffffffffu, cap, (jn + 1) & 31);
     double beta = a0, taun = 0.0, scl = 0.0;
     if (sigma > 0.0) {
       // beta = -sign(a0) sqrt(x), tau = (beta - a0) / beta = 1 + |a0| / sqrt(x), 1 / (a0 - beta) = sign(a0) / (|a0| + sqrt(x)):
@@ -382,6 +411,25 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_reg_kernel(S
       taun = fma(aa, y, 1.0);
       scl = copysign(1.0 / (aa + sx), a0);
     }
+    double pdw = 0.0;
+    if (live) {
+      const double prod = fma(scl, accs, acc0);
+      const double vnr = r >= jn + 2 ? srn[r] * scl : 1.0;
+      pdw = vnr * prod;
+      if (lane == 0) __stcg(P.p + (size_t)(j & 1) * n + r, prod);
+      if (r == jn + 1) {
+        double* rbn = P.rowbuf + (size_t)(j & 1) * n;
+#pragma unroll
+        for (int m = 0; m < NCH; ++m) {
+          const int c = lane + 32 * m;
+          if (m >= m0 && c > jn && c < n) __stcg(rbn + c, a[m]);
+        }
+      }
+    }
+    if (lane == 0) s_part[wid] = pdw;
+    PLB_PF(3);  // row pass, scalars, product entry, broadcast row
+    __syncthreads();  // every warp is done with sv / sw / srn of this step
+    // ---- (3) the scaled reflector into the other buffer (the owner of row jn also stores it), T's entries, partial dot
     {
       double* row = P.S + (size_t)jn * P.lds;
       const bool owner = (jn % G == b);
@@ -394,52 +442,20 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_reg_kernel(S
           if (owner && c > jn && c < n) row[c] = x;
         }
       }
-      if (tid == 0 && jn >= 1) svn[jn - 1] = 0.0;  // the leading 1 of v_{j-1}; everything before it is zero already
-    }
-    __syncthreads();
-    PLB_PF(3);  // scalars + scaled reflector
-    // ---- (2) own row: rank-2 update with (v_j, w_j), entry of A v_{jn}. Finished columns (c <= jn) see v_{jn} = 0, so whatever their
-    // registers collect is never used; chunks are skipped eight at a time only.
-    double pdw = 0.0;
-    if (r > jn && r < n) {
-      const double nvr = -sv[r], nwr = -sw[r];
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      const double *svl = sv + lane, *swl = sw + lane, *svnl = svn + lane;
-      switch (m0 >> 3) {
-        case 0: sytrd_row_update<NCH, 0>(a, svl, swl, svnl, nvr, nwr, acc); break;
-        case 1: sytrd_row_update<NCH, (8 < NCH ? 8 : 0)>(a, svl, swl, svnl, nvr, nwr, acc); break;
-        case 2: sytrd_row_update<NCH, (16 < NCH ? 16 : 0)>(a, svl, swl, svnl, nvr, nwr, acc); break;
-        case 3: sytrd_row_update<NCH, (24 < NCH ? 24 : 0)>(a, svl, swl, svnl, nvr, nwr, acc); break;
-        default: sytrd_row_update<NCH, (32 < NCH ? 32 : 0)>(a, svl, swl, svnl, nvr, nwr, acc); break;
-      }
-      const double prod = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
-      pdw = svn[r] * prod;
-      if (lane == 0) __stcg(P.p + (size_t)(j & 1) * n + r, prod);
-      if (r == jn + 1) {
-        double* rbn = P.rowbuf + (size_t)(j & 1) * n;
+      if (tid == 0) {
+        if (jn >= 1) svn[jn - 1] = 0.0;  // the leading 1 of v_{j-1}; everything before it is zero already
+        double t = 0.0;
 #pragma unroll
-        for (int m = 0; m < NCH; ++m) {
-          const int c = lane + 32 * m;
-          if (m >= m0 && c > jn && c < n) __stcg(rbn + c, a[m]);
-        }
+        for (int q = 0; q < 8; ++q) t += s_part[q];
+        __stcg(P.pd + (j & 1) * 256 + b, t);
+        if (b == 0) { P.d[jn] = djn; P.e[jn] = beta; P.tau[jn] = taun; }
       }
-    }
-    if (lane == 0) s_part[wid] = pdw;
-    PLB_PF(4);  // row update, product entry, broadcast row
-    // ---- (3) partial dot and T's entries published (the grid barrier's __syncthreads orders the s_part writes)
-    __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) t += s_part[q];
-      __stcg(P.pd + (j & 1) * 256 + b, t);
-      if (b == 0) { P.d[jn] = djn; P.e[jn] = beta; P.tau[jn] = taun; }
     }
     tau = taun;
     target += 1ull;
-    PLB_PF(5);  // CTA barrier + publish
+    PLB_PF(4);  // reflector in place + publish
     if (!sytrd_grid_barrier(P.bar, target)) return;
-    PLB_PF(6);  // grid barrier
+    PLB_PF(5);  // grid barrier
   }
   if (P.prof && lane == 0 && wid == 6) {
     for (int i = 0; i < 8; ++i) P.prof[8 * b + i] = pf[i];
@@ -1087,20 +1103,27 @@ __global__ void __launch_bounds__(256) eigh_larft_kernel(const double* __restric
   for (int t = tid; t < R * R; t += 256) Tf[(size_t)blockIdx.x * R * R + t] = T[t / R][t % R];
 }
 
-template <int NCH, int R>
-__global__ void __launch_bounds__(256) eigh_backtransform_wy_kernel(const double* __restrict__ S, int64_t lds, const double* __restrict__ Tf, int n,
-                                                                    double* __restrict__ Z, int64_t ldz) {
+// NV eigenvectors per warp (8 per CTA of 8 / NV warps). The kernel reads one element of V from shared memory per FMA (0.62 ms at
+// n = 1000 with NV = 1); NV = 2 halves that but leaves four warps per SM with 226 registers each and measured 0.66 ms: NV = 1 ships.
+// The real fix is a DMMA form of the update (one LDS.128 per 512 FMAs), DESIGN.md section 8.
+template <int NCH, int R, int NV>
+__global__ void __launch_bounds__(256 / NV) eigh_backtransform_wy_kernel(const double* __restrict__ S, int64_t lds, const double* __restrict__ Tf, int n,
+                                                                         double* __restrict__ Z, int64_t ldz) {
   extern __shared__ double vs[];  // 2 x R x (32 NCH)
   __shared__ double sT[2][R * R];
   constexpr int NP = 32 * NCH;
+  constexpr int NT = 256 / NV;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int k = blockIdx.x * 8 + wid;
-  double z[NCH];
-  double* zrow = Z + (size_t)(k < n ? k : 0) * ldz;
+  const int k0 = blockIdx.x * 8 + wid * NV;
+  double z[NV][NCH];
 #pragma unroll
-  for (int m = 0; m < NCH; ++m) {
-    const int c = lane + 32 * m;
-    z[m] = (k < n && c < n) ? zrow[c] : 0.0;
+  for (int v = 0; v < NV; ++v) {
+    const double* zrow = Z + (size_t)(k0 + v < n ? k0 + v : 0) * ldz;
+#pragma unroll
+    for (int m = 0; m < NCH; ++m) {
+      const int c = lane + 32 * m;
+      z[v][m] = (k0 + v < n && c < n) ? zrow[c] : 0.0;
+    }
   }
   const uint32_t vs_u32 = (uint32_t)__cvta_generic_to_shared(vs);
   auto stage = [&](int blk, int jtop, int buf) {
@@ -1111,9 +1134,9 @@ __global__ void __launch_bounds__(256) eigh_backtransform_wy_kernel(const double
         const int j = jlow + q;  // rows beyond the block (j > jtop) are zero-filled: they do nothing
         const double* src = S + (size_t)(j <= jtop ? j : jtop) * lds;
         const uint32_t dst = vs_u32 + (uint32_t)(((buf * R + q) * NP) * 8);
-        for (int c = cl + tid; c < NP; c += 256) cp_async8_zfill(dst + c * 8, src + (c < n ? c : 0), j <= jtop && c > j && c < n);
+        for (int c = cl + tid; c < NP; c += NT) cp_async8_zfill(dst + c * 8, src + (c < n ? c : 0), j <= jtop && c > j && c < n);
       }
-      if (tid < R * R) sT[buf][tid] = Tf[(size_t)blk * R * R + tid];
+      for (int t = tid; t < R * R; t += NT) sT[buf][t] = Tf[(size_t)blk * R * R + t];
     }
     cp_async_commit();
   };
@@ -1126,44 +1149,59 @@ __global__ void __launch_bounds__(256) eigh_backtransform_wy_kernel(const double
     const int jlow = jtop - R + 1 > 0 ? jtop - R + 1 : 0;
     const int m0 = (jlow + 1) >> 5;
     const double* vb = vs + (size_t)(buf * R) * NP + lane;
-    double y[R];
+    double y[NV][R];
 #pragma unroll
-    for (int q = 0; q < R; ++q) y[q] = 0.0;
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int q = 0; q < R; ++q) y[v][q] = 0.0;
 #pragma unroll
     for (int m = 0; m < NCH; ++m) {
       if (m >= m0) {
-        const double zm = z[m];
 #pragma unroll
-        for (int q = 0; q < R; ++q) y[q] += vb[q * NP + 32 * m] * zm;
+        for (int q = 0; q < R; ++q) {
+          const double vq = vb[q * NP + 32 * m];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) y[v][q] = fma(vq, z[v][m], y[v][q]);
+        }
       }
     }
 #pragma unroll
-    for (int q = 0; q < R; ++q) y[q] = warp_sum(y[q]);
-    double u[R];
+    for (int v = 0; v < NV; ++v)
 #pragma unroll
-    for (int a = 0; a < R; ++a) {
-      double t = 0.0;
+      for (int q = 0; q < R; ++q) y[v][q] = warp_sum(y[v][q]);
+    double u[NV][R];
 #pragma unroll
-      for (int b = a; b < R; ++b) t += sT[buf][a * R + b] * y[b];
-      u[a] = t;
-    }
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int a = 0; a < R; ++a) {
+        double t = 0.0;
+#pragma unroll
+        for (int b = a; b < R; ++b) t += sT[buf][a * R + b] * y[v][b];
+        u[v][a] = t;
+      }
 #pragma unroll
     for (int m = 0; m < NCH; ++m) {
       if (m >= m0) {
-        double zm = z[m];
 #pragma unroll
-        for (int q = 0; q < R; ++q) zm -= vb[q * NP + 32 * m] * u[q];
-        z[m] = zm;
+        for (int q = 0; q < R; ++q) {
+          const double vq = vb[q * NP + 32 * m];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) z[v][m] = fma(-vq, u[v][q], z[v][m]);
+        }
       }
     }
     __syncthreads();
   }
   cp_async_wait<0>();
-  if (k < n) {
 #pragma unroll
-    for (int m = 0; m < NCH; ++m) {
-      const int c = lane + 32 * m;
-      if (c < n) zrow[c] = z[m];
+  for (int v = 0; v < NV; ++v) {
+    if (k0 + v < n) {
+      double* zrow = Z + (size_t)(k0 + v) * ldz;
+#pragma unroll
+      for (int m = 0; m < NCH; ++m) {
+        const int c = lane + 32 * m;
+        if (c < n) zrow[c] = z[v][m];
+      }
     }
   }
 }

@@ -1373,10 +1373,10 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
       CUDA_TRY(cudaFuncSetAttribute(dc_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * EIGH_MAX_N));
       CUDA_TRY(cudaFuncSetAttribute(dc_small_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * (EIGH_SMALL_GEMM_MAX | 1) * 8));
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 8 * 32 * 8));
-      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 16 * 32 * 8));
-      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 32 * 32 * 8));
-      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 64 * 32 * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<8, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 8 * 32 * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<16, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 16 * 32 * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<32, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 32 * 32 * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<64, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 64 * 32 * 8));
       attr_done = true;
     }
     const int rows_per_cta = EIGH_SYTRD_THREADS / 32;
@@ -1401,7 +1401,7 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
     CUDA_TRY(cudaMemcpyAsync(prof, d_rho, sizeof(prof), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int c : {0, 1, 73, 100})
-      fprintf(stderr, "sytrd prof cta %d warp 6: loads %lld elementwise %lld ctabar %lld rowupd %lld product %lld publish %lld gridbar %lld cycles\n", c, prof[8 * c],
+      fprintf(stderr, "sytrd prof cta %d warp 6: loads %lld elementwise %lld ctabar %lld rowpass %lld publish %lld gridbar %lld (%lld) cycles\n", c, prof[8 * c],
               prof[8 * c + 1], prof[8 * c + 2], prof[8 * c + 3], prof[8 * c + 4], prof[8 * c + 5], prof[8 * c + 6]);
   }
   // 2. divide and conquer
@@ -1454,16 +1454,16 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
     if (n <= 2048 && !getenv("PLB200_EIGH_NO_REG")) {
       const unsigned blocks = (unsigned)((n + 7) / 8);
       if (n >= 3) {
-#define PLB_BT(NCH, R)                                                                                                     \
-  do {                                                                                                                     \
-    eigh_larft_kernel<R><<<(unsigned)((n - 2 + R - 1) / R), 256, 0, st>>>(S, ldq, d_tau, n, d_Tf);                         \
-    LAUNCH_CHECK();                                                                                                        \
-    eigh_backtransform_wy_kernel<NCH, R><<<blocks, 256, (size_t)2 * R * NCH * 32 * 8, st>>>(S, ldq, d_Tf, n, dA, lda);     \
+#define PLB_BT(NCH, R, NV)                                                                                                          \
+  do {                                                                                                                              \
+    eigh_larft_kernel<R><<<(unsigned)((n - 2 + R - 1) / R), 256, 0, st>>>(S, ldq, d_tau, n, d_Tf);                                  \
+    LAUNCH_CHECK();                                                                                                                 \
+    eigh_backtransform_wy_kernel<NCH, R, NV><<<blocks, 256 / NV, (size_t)2 * R * NCH * 32 * 8, st>>>(S, ldq, d_Tf, n, dA, lda);     \
   } while (0)
-        if (n <= 256) PLB_BT(8, 8);
-        else if (n <= 512) PLB_BT(16, 8);
-        else if (n <= 1024) PLB_BT(32, 8);
-        else PLB_BT(64, 4);
+        if (n <= 256) PLB_BT(8, 8, 1);
+        else if (n <= 512) PLB_BT(16, 8, 1);
+        else if (n <= 1024) PLB_BT(32, 8, 1);
+        else PLB_BT(64, 4, 1);
 #undef PLB_BT
       }
     } else {
