@@ -246,13 +246,14 @@ int pl_allreduce_dev(double* dbuf, int64_t count, void* stream);
 /* ---- symmetric eigendecomposition and the L-ensemble on the device ("next" row f1 of SURVEY.md 8f) ----------- */
 /* eigen(Symmetric(Q)) (dimension_reduction.jl:13; LAPACK in the reference) and the eigendecomposition inside EllEnsemble(K)
  * (Determinantal.jl [external], reached from dpp.jl:26,41).
- * n <= 1184 (the sizes of configs 1, 3, 4: N = 1000, K = 500 / 1000): the library's OWN solver (csrc/eigh.cuh) -- Householder
- * tridiagonalisation in one cooperative kernel with the matrix in registers, divide and conquer on the tridiagonal matrix with its
- * eigenvector updates on the DMMA Gram engine, blocked back-transformation. No library call; results are bitwise reproducible.
+ * n <= 2048: the library's OWN solver (csrc/eigh.cuh) -- Householder tridiagonalisation in one cooperative kernel (n <= 1184, the
+ * sizes of configs 1, 3, 4 -- N = 1000, K = 500 / 1000: the matrix in registers, 2.6x faster than cuSOLVER; above: rows in L2, 1.2x),
+ * divide and conquer on the tridiagonal matrix with its eigenvector updates on the DMMA Gram engine, blocked back-transformation.
+ * No library call; results are bitwise reproducible.
  * Larger n: cuSOLVER's Xsyevd, loaded with dlopen at first use (PLB200_CUSOLVER overrides the search path).
  * PLB200_EIGH=own|cusolver forces one path (own: n <= 4096), PLB200_EIGH_OWN_MAX moves the switch-over.
  * Accuracy (own path, measured over random SPD / rank-deficient kernel / RBF / graded covariance / clustered / Wilkinson matrices up
- * to n = 2048): eigenvalues <= 6e-14 ||A||, residual |A U - U diag(W)| <= 7e-15 ||A||, |U'U - I| <= 3e-14.
+ * to n = 4096): eigenvalues <= 1.5e-13 ||A|| (Wilkinson, n = 4096: LAPACK-level; <= 6e-14 up to n = 2048), residual |A U - U diag(W)| <= 7e-15 ||A||, |U'U - I| <= 3e-14.
  * Errors: PL_EINVAL for a matrix with Inf / NaN entries (Julia's eigen throws there too).
  * A: symmetric n x n, only the `fill` triangle of the row-major view is read. W: n eigenvalues, ascending. V (may be NULL: values only):
  * ROW k = unit eigenvector k, i.e. Julia's column-major `eigen(...).vectors` (column k) byte for byte. Signs are the solver's. */

@@ -1,12 +1,12 @@
 // eigh.cuh — hand-written symmetric eigensolver of libplb200 (row f1 of SURVEY.md 8f): eigen(Symmetric(Q)) of
 // dimension_reduction.jl:13 (K x K covariance, K = 500 / 1000 in configs 3 / 4) and the eigendecomposition inside EllEnsemble(K)
 // (dpp.jl:26,41; config 1: N = 1000). The reference calls LAPACK (syevr) here; round 1 called cuSOLVER. This file is the
-// library-free path for matrices that live in L2 (n <= 4096):
+// library-free path for matrices that live in L2 (n <= 4096; the default routing uses it up to n = 2048):
 //
-//   1. eigh_sytrd_kernel      Householder tridiagonalisation as ONE persistent cooperative kernel: the rank-2 update of step j and
-//                             the symmetric matrix-vector product of step j+1 are one pass over the rows a CTA owns (rows dealt
-//                             cyclically), every CTA forms the next reflector redundantly from a broadcast copy of the next row,
-//                             one grid barrier per step.
+//   1. eigh_sytrd_*_kernel    Householder tridiagonalisation as ONE persistent cooperative kernel: the rank-2 update of step j and
+//                             the symmetric matrix-vector product of step j+1 are one pass over the rows a warp owns (rows dealt
+//                             cyclically; in registers for n <= 1184, through L2 above), every CTA forms the next reflector
+//                             redundantly from a broadcast copy of the next row, one grid barrier per step.
 //   2. dc_*                   divide and conquer on the tridiagonal matrix (Cuppen / Gu-Eisenstat): Jacobi leaves (<= 32), per
 //                             merge: deflation, secular equation by bisection ON THE BIT PATTERN of the offset from the nearer
 //                             pole (<= 63 steps to the last bit, whatever the scale), Loewner re-computation of the update vector,
@@ -146,129 +146,6 @@ __device__ __forceinline__ bool sytrd_grid_barrier(unsigned long long* bar, unsi
   return s_ok != 0;
 }
 
-__global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_kernel(SytrdParams P) {
-  extern __shared__ double sm[];
-  const int n = P.n;
-  const int np = (n + 3) & ~3;
-  double* v = sm;             // v_j   (support [j+1, n), v[j+1] = 1)
-  double* w = sm + np;        // w_j
-  double* vn = sm + 2 * np;   // row j+1 after update j, then v_{j+1}
-  __shared__ double red[40];
-  __shared__ double s_tau, s_taun;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-  const int G = gridDim.x, b = blockIdx.x;
-  for (int c = tid; c < np; c += blockDim.x) { v[c] = 0.0; w[c] = 0.0; vn[c] = 0.0; }
-  if (tid == 0) { s_tau = 0.0; s_taun = 0.0; }
-  __syncthreads();
-  unsigned long long target = 0;
-
-  for (int j = -1; j <= n - 2; ++j) {
-    const int jn = j + 1;
-    // ---- phase a: w_j = tau p - (tau/2)(tau p.v) v from the products the row owners wrote before the barrier
-    const double* rb = P.rowbuf + (size_t)((j - 1) & 1) * n;
-    const double* pin = P.p + (size_t)((j - 1) & 1) * n;   // written in the previous step
-    const double* pdin = P.pd + ((j - 1) & 1) * 256;
-    double* pout = P.p + (size_t)(j & 1) * n;
-    double* pdout = P.pd + (j & 1) * 256;
-    if (j >= 0) {
-      const double tau = s_tau;
-      double part = 0.0;
-      for (int g = tid; g < G; g += blockDim.x) part += __ldcg(pdin + g);
-      const double dot = block_sum(part, red);
-      const double alpha = 0.5 * tau * tau * dot;
-      for (int c = jn + tid; c < n; c += blockDim.x) w[c] = tau * __ldcg(pin + c) - alpha * v[c];
-    }
-    __syncthreads();
-    // ---- phase b: row jn after update j (every CTA, redundantly) -> d[jn], reflector jn
-    {
-      const double vj = v[jn], wj = w[jn];
-      double sig = 0.0;
-      for (int c = jn + tid; c < n; c += blockDim.x) {
-        double r = __ldcg(rb + c);
-        if (j >= 0) r = r - (vj * w[c] + wj * v[c]);
-        vn[c] = r;
-        if (c >= jn + 2) sig += r * r;
-      }
-      const double sigma = block_sum(sig, red);  // also makes vn visible
-      const double djn = vn[jn];
-      const double a0 = jn + 1 < n ? vn[jn + 1] : 0.0;
-      double beta = a0, taun = 0.0, scl = 0.0;
-      if (jn + 1 < n && sigma > 0.0) {
-        beta = -copysign(sqrt(a0 * a0 + sigma), a0);
-        taun = (beta - a0) / beta;
-        scl = 1.0 / (a0 - beta);
-      }
-      __syncthreads();  // everyone has read vn[jn], vn[jn+1]
-      for (int c = jn + tid; c < n; c += blockDim.x) {
-        double x = vn[c];
-        x = c >= jn + 2 ? x * scl : (c == jn + 1 ? 1.0 : 0.0);
-        vn[c] = x;
-      }
-      if (tid == 0) s_taun = taun;
-      if (b == 0 && tid == 0) {
-        P.d[jn] = djn;
-        if (jn + 1 < n) { P.e[jn] = beta; P.tau[jn] = taun; }
-      }
-      __syncthreads();
-    }
-    if (jn == n - 1) break;
-    // ---- phase c: own rows r > jn: rank-2 update with (v_j, w_j), product with v_{jn}; row jn+1 is broadcast for the next step
-    double pdw = 0.0;
-    {
-      double* rbn = P.rowbuf + (size_t)(j & 1) * n;
-      int r0 = b;  // rows r = b + G q; first q with r > jn
-      if (r0 <= jn) r0 += ((jn - r0) / G + 1) * G;
-      const int c0 = (jn + 1) & ~31;
-      for (int r = r0 + wid * G; r < n; r += nw * G) {
-        double* row = P.S + (size_t)r * P.lds;
-        const double vr = v[r], wr = w[r];
-        const bool bc = (r == jn + 1);
-        double acc = 0.0;
-        // eight independent loads in flight per lane (a dependent load per element costs an L2 round trip each)
-        for (int cb = c0 + lane; cb < n; cb += 32 * 8) {
-          double av[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int c = cb + 32 * u;
-            av[u] = (c < n && c > jn) ? __ldcg(row + c) : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int c = cb + 32 * u;
-            if (c < n && c > jn) {
-              double a = av[u];
-              if (j >= 0) {
-                a = a - (vr * w[c] + wr * v[c]);
-                __stcg(row + c, a);
-              }
-              acc += a * vn[c];
-              if (bc) __stcg(rbn + c, a);
-            }
-          }
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) {
-          __stcg(pout + r, acc);
-          pdw += vn[r] * acc;
-        }
-      }
-      // the owner of row jn stores reflector jn over the finished row (nobody reads S[jn][.] again)
-      if (jn % G == b) {
-        double* row = P.S + (size_t)jn * P.lds;
-        for (int c = jn + 1 + tid; c < n; c += blockDim.x) row[c] = vn[c];
-      }
-    }
-    const double pdb = block_sum(pdw, red);
-    if (tid == 0) __stcg(pdout + b, pdb);
-    // rotate: v <- v_{jn} (w is rebuilt in phase a)
-    __syncthreads();
-    for (int c = jn + tid; c < n; c += blockDim.x) v[c] = vn[c];
-    if (tid == 0) s_tau = s_taun;
-    target += 1ull;
-    if (!sytrd_grid_barrier(P.bar, target)) return;
-  }
-}
-
 // n <= 8 * gridDim.x: every warp owns ONE row and keeps it in REGISTERS for the whole reduction (lane l holds columns l, l+32, ...); the
 // matrix never travels again. Per step: (1) the CTA forms w = tau p - alpha v and the next row of the updated matrix element-wise in
 // shared memory from the products / broadcast row the owners published before the barrier (every element once per CTA); (2) every
@@ -276,14 +153,14 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_kernel(Sytrd
 // unrolled loop (finished columns are updated with zeros / ignored rather than skipped: a 25-cycle DFMA latency wants independent
 // chunks in flight, and a branch per chunk serialises them: 2500 -> 600 cycles); (3) publish, grid barrier.
 // Nothing is spilled: acquire loads invalidate L1 every step, so a spilled register costs an L2 round trip per reload.
-template <int NCH, int START, bool LIVE>
+template <int NCH, int START, bool LIVE, bool SIG = true>
 __device__ __forceinline__ void sytrd_row_pass(double (&a)[NCH], const double* __restrict__ svl, const double* __restrict__ swl,
                                                const double* __restrict__ srnl, double nvr, double nwr, int mq, double (&acc)[4], double (&sg)[4],
                                                double& cap) {
 #pragma unroll
   for (int m = START; m < NCH; ++m) {
     const double rn = srnl[32 * m];
-    sg[m & 3] = fma(rn, rn, sg[m & 3]);
+    if (SIG) sg[m & 3] = fma(rn, rn, sg[m & 3]);
     if (LIVE) {
       const double an = fma(nwr, svl[32 * m], fma(nvr, swl[32 * m], a[m]));
       a[m] = an;
@@ -461,6 +338,192 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_reg_kernel(S
     for (int i = 0; i < 8; ++i) P.prof[8 * b + i] = pf[i];
   }
 #undef PLB_PF
+}
+
+// The same step structure for 1184 < n <= 1024 NB with the rows in L2: 12 warps per CTA, a warp's rows (dealt cyclically, one per
+// warp up to n = 1776) pass through its registers one block of 32 chunks (1024 columns) at a time -- 32 independent loads in flight per
+// lane, the fused pass, predicated stores -- and the other warps of the SM hide the round trip. Shared memory holds v_j, v_{j+1}, w_j
+// and the next row (dynamic: 4 x 8 NB KB).
+constexpr int EIGH_L2_THREADS = 384;  // 12 warps = 3 per scheduler: 168 registers per thread keep the 32-chunk block and the pass without spills
+constexpr int EIGH_L2_WARPS = EIGH_L2_THREADS / 32;
+template <bool LIVE, bool SIG>
+__device__ __forceinline__ void sytrd_block_pass(int start8, double (&a)[32], const double* svl, const double* swl, const double* srnl, double nvr,
+                                                 double nwr, int mq, double (&acc)[4], double (&sg)[4], double& cap) {
+  switch (start8) {
+    case 0: sytrd_row_pass<32, 0, LIVE, SIG>(a, svl, swl, srnl, nvr, nwr, mq, acc, sg, cap); break;
+    case 1: sytrd_row_pass<32, 8, LIVE, SIG>(a, svl, swl, srnl, nvr, nwr, mq, acc, sg, cap); break;
+    case 2: sytrd_row_pass<32, 16, LIVE, SIG>(a, svl, swl, srnl, nvr, nwr, mq, acc, sg, cap); break;
+    default: sytrd_row_pass<32, 24, LIVE, SIG>(a, svl, swl, srnl, nvr, nwr, mq, acc, sg, cap); break;
+  }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(EIGH_L2_THREADS, 1) eigh_sytrd_l2_kernel(SytrdParams P) {
+  constexpr int NP = NB * 1024;
+  constexpr int NQ = (NP + EIGH_L2_THREADS - 1) / EIGH_L2_THREADS;
+  extern __shared__ double l2sm[];
+  double* svb0 = l2sm;
+  double* svb1 = l2sm + NP;
+  double* sw = l2sm + 2 * NP;
+  double* srn = l2sm + 3 * NP;
+  __shared__ double s_part[EIGH_L2_WARPS], s_sc[4];
+  const int n = P.n;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int G = gridDim.x, b = blockIdx.x;
+  for (int c = tid; c < NP; c += EIGH_L2_THREADS) { svb0[c] = 0.0; svb1[c] = 0.0; sw[c] = 0.0; srn[c] = 0.0; }
+  __syncthreads();
+  double tau = 0.0;
+  int cur = 0;
+  unsigned long long target = 0;
+  for (int j = -1; j <= n - 2; ++j, cur ^= 1) {
+    const int jn = j + 1;
+    const int m0 = jn >> 5;
+    const int cbase = (jn & ~31) + tid;
+    const double* sv = cur ? svb1 : svb0;
+    double* svn = cur ? svb0 : svb1;
+    // ---- (1) w_j and row jn of the updated matrix, element-wise
+    {
+      const double* rb = P.rowbuf + (size_t)((j - 1) & 1) * n;
+      const double* pin = P.p + (size_t)((j - 1) & 1) * n;
+      const double* pdin = P.pd + ((j - 1) & 1) * 256;
+      double pc[NQ], rbc[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int c = cbase + q * EIGH_L2_THREADS;
+        pc[q] = (c < n && j >= 0) ? __ldcg(pin + c) : 0.0;
+        rbc[q] = c < n ? __ldcg(rb + c) : 0.0;
+      }
+      if (wid == 0) {
+        double dot = 0.0, pjn = 0.0;
+        if (j >= 0) {
+#pragma unroll
+          for (int q = 0; q < 5; ++q) dot += __ldcg(pdin + lane + 32 * q);
+          pjn = __ldcg(pin + jn);
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) {
+          const double al = 0.5 * tau * tau * dot;
+          s_sc[0] = al;
+          s_sc[1] = tau * pjn - al;
+        }
+      }
+      __syncthreads();
+      const double alpha = s_sc[0], wjn = s_sc[1];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int c = cbase + q * EIGH_L2_THREADS;
+        if (c >= jn && c < n) {
+          const double vc = sv[c];
+          const double wc = tau * pc[q] - alpha * vc;
+          const double rn = rbc[q] - (wc + wjn * vc);
+          sw[c] = wc;
+          srn[c] = c >= jn + 2 ? rn : 0.0;
+          if (c == jn) s_sc[2] = rn;
+          if (c == jn + 1) s_sc[3] = rn;
+        }
+      }
+    }
+    __syncthreads();
+    const double djn = s_sc[2];
+    if (jn == n - 1) {
+      if (b == 0 && tid == 0) P.d[jn] = djn;
+      break;
+    }
+    const double a0 = s_sc[3];
+    // ---- (2) the warp's rows, block by block; the first pass of the step also sums the norm of the next reflector
+    const int mq = (jn + 1) >> 5;
+    const int kb0 = m0 >> 5;  // first block with live columns
+    double sg[4] = {0.0, 0.0, 0.0, 0.0};
+    double sigma = 0.0, beta = a0, taun = 0.0, scl = 0.0, pdw = 0.0;
+    bool have_sigma = false;
+    int r = b + G * wid;
+    if (r <= jn) r += ((jn - r) / (EIGH_L2_WARPS * G) + 1) * (EIGH_L2_WARPS * G);  // first live row of this warp
+    for (int pass = 0; r < n || !have_sigma; ++pass, r += EIGH_L2_WARPS * G) {
+      const bool live = r < n;
+      double acc[4] = {0.0, 0.0, 0.0, 0.0}, cap = 0.0;
+      const double nvr = live ? -sv[r] : 0.0, nwr = live ? -sw[r] : 0.0;
+      double* row = P.S + (size_t)(live ? r : 0) * P.lds;
+      double* rbn = P.rowbuf + (size_t)(j & 1) * n;
+      for (int kb = kb0; kb < NB; ++kb) {
+        if (kb * 1024 >= n) break;
+        const int off = kb * 1024 + lane;
+        const int rel = m0 - kb * 32;
+        const int start8 = rel <= 0 ? 0 : (rel >> 3);
+        double a[32];
+        if (live) {
+#pragma unroll
+          for (int m = 0; m < 32; ++m) {
+            const int c = off + 32 * m;
+            a[m] = c < n ? __ldcg(row + c) : 0.0;
+          }
+          if (!have_sigma) sytrd_block_pass<true, true>(start8, a, sv + off, sw + off, srn + off, nvr, nwr, mq - kb * 32, acc, sg, cap);
+          else sytrd_block_pass<true, false>(start8, a, sv + off, sw + off, srn + off, nvr, nwr, mq - kb * 32, acc, sg, cap);
+#pragma unroll
+          for (int m = 0; m < 32; ++m) {
+            const int c = off + 32 * m;
+            if (c > jn && c < n) {
+              __stcg(row + c, a[m]);
+              if (r == jn + 1) __stcg(rbn + c, a[m]);
+            }
+          }
+        } else {
+          sytrd_block_pass<false, true>(start8, a, sv + off, sw + off, srn + off, 0.0, 0.0, -1, acc, sg, cap);
+        }
+      }
+      double accs = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+      if (!have_sigma) {
+        sigma = (sg[0] + sg[1]) + (sg[2] + sg[3]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sigma += __shfl_xor_sync(0xffffffffu, sigma, o);
+          accs += __shfl_xor_sync(0xffffffffu, accs, o);
+        }
+        if (sigma > 0.0) {
+          const double x = fma(a0, a0, sigma), y = rsqrt(x), sx = x * y, aa = fabs(a0);
+          beta = -copysign(sx, a0);
+          taun = fma(aa, y, 1.0);
+          scl = copysign(1.0 / (aa + sx), a0);
+        }
+        have_sigma = true;
+      } else {
+        accs = warp_sum(accs);
+      }
+      if (live) {
+        const double acc0 = __shfl_sync(0xffffffffu, cap, (jn + 1) & 31);
+        const double prod = fma(scl, accs, acc0);
+        const double vnr = r >= jn + 2 ? srn[r] * scl : 1.0;
+        pdw += vnr * prod;
+        if (lane == 0) __stcg(P.p + (size_t)(j & 1) * n + r, prod);
+      }
+    }
+    if (lane == 0) s_part[wid] = pdw;
+    __syncthreads();
+    // ---- (3) the scaled reflector into the other buffer (the owner of row jn also stores it), T's entries, partial dot
+    {
+      double* row = P.S + (size_t)jn * P.lds;
+      const bool owner = (jn % G == b);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int c = cbase + q * EIGH_L2_THREADS;
+        if (c < NP) {
+          const double x = (c >= jn + 2 && c < n) ? srn[c] * scl : (c == jn + 1 ? 1.0 : 0.0);
+          svn[c] = x;
+          if (owner && c > jn && c < n) row[c] = x;
+        }
+      }
+      if (tid == 0) {
+        if (jn >= 1) svn[jn - 1] = 0.0;
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < EIGH_L2_WARPS; ++q) t += s_part[q];
+        __stcg(P.pd + (j & 1) * 256 + b, t);
+        if (b == 0) { P.d[jn] = djn; P.e[jn] = beta; P.tau[jn] = taun; }
+      }
+    }
+    tau = taun;
+    target += 1ull;
+    if (!sytrd_grid_barrier(P.bar, target)) return;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------

@@ -1257,7 +1257,7 @@ int cusolver_ready() {
 
 // ---- the library-free path (eigh.cuh): Householder tridiagonalisation in one cooperative kernel, divide and conquer with the eigenvector
 // updates on the DMMA Gram engine, back-transformation. Chosen by eigh_dev_impl for n <= PLB200_EIGH_OWN_MAX (default 2048; the matrix and
-// its three work matrices live in L2); PLB200_EIGH=cusolver / own forces one path.
+// its three work matrices live in L2, up to n = 1184 the matrix itself in registers); PLB200_EIGH=cusolver / own forces one path.
 struct EighTree {
   int n = -1;
   std::vector<int2> leaves;
@@ -1366,10 +1366,10 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
     SytrdParams P;
     P.S = S; P.lds = ldq; P.n = n; P.d = d_d; P.e = d_e; P.tau = d_tau; P.p = d_p; P.pd = d_pd; P.rowbuf = d_rowbuf; P.bar = d_bar;
     P.prof = getenv("PLB200_EIGH_PROF") ? (long long*)d_rho : nullptr;  // over d_rho/d_Tf: written at the end of sytrd, read back below
-    const size_t smem = (size_t)3 * ((n + 3) & ~3) * 8;
     static bool attr_done = false;
     if (!attr_done) {
-      CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * EIGH_MAX_N * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_l2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2048 * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_l2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 8));
       CUDA_TRY(cudaFuncSetAttribute(dc_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * EIGH_MAX_N));
       CUDA_TRY(cudaFuncSetAttribute(dc_small_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * (EIGH_SMALL_GEMM_MAX | 1) * 8));
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1390,9 +1390,13 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
                        : n <= 1024 ? (const void*)eigh_sytrd_reg_kernel<32>
                                    : (const void*)eigh_sytrd_reg_kernel<37>;
       CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(EIGH_SYTRD_THREADS), args, 0, st));
-    } else {
+    } else {  // rows in L2, 12 warps per CTA
+      G = (n + EIGH_L2_WARPS - 1) / EIGH_L2_WARPS;
       if (G > g.num_sms) G = g.num_sms;
-      CUDA_TRY(cudaLaunchCooperativeKernel((const void*)eigh_sytrd_kernel, dim3(G), dim3(EIGH_SYTRD_THREADS), args, smem, st));
+      if (n <= 2048)
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)eigh_sytrd_l2_kernel<2>, dim3(G), dim3(EIGH_L2_THREADS), args, (size_t)4 * 2048 * 8, st));
+      else
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)eigh_sytrd_l2_kernel<4>, dim3(G), dim3(EIGH_L2_THREADS), args, (size_t)4 * 4096 * 8, st));
     }
     LAUNCH_CHECK();
   }
@@ -1489,7 +1493,7 @@ int eigh_dev_impl(double* dA, int64_t n, int64_t lda, int fill, int want_vectors
   {
     const char* mode = getenv("PLB200_EIGH");
     const char* mx = getenv("PLB200_EIGH_OWN_MAX");
-    int64_t own_max = mx ? atoll(mx) : 1184;  // the register-resident tridiagonalisation (one row per warp, 148 x 8 warps)
+    int64_t own_max = mx ? atoll(mx) : 2048;  // <= 1184: register-resident tridiagonalisation (2.6x cuSOLVER); <= 2048: rows in L2 (1.2x)
     if (own_max > EIGH_MAX_N) own_max = EIGH_MAX_N;
     const bool force_own = mode && !strcmp(mode, "own"), force_lib = mode && !strcmp(mode, "cusolver");
     if (force_own || (!force_lib && n <= own_max)) return eigh_own_impl(dA, n, lda, fill, want_vectors, dW, st);

@@ -125,7 +125,7 @@ function pl_cov(X::Matrix{Float64}, m::Vector{Float64}, mean_given::Bool, center
     C
 end
 
-# eigen(Symmetric(Q)) on the device (the library's own solver up to n = 1184, cuSOLVER above; OPT-IN — the default keeps LAPACK like the reference): row k of the
+# eigen(Symmetric(Q)) on the device (the library's own solver up to n = 2048, cuSOLVER above; OPT-IN — the default keeps LAPACK like the reference): row k of the
 # library's V is column k of Julia's `vectors`
 function pl_eigh(A::Matrix{Float64}, uplo::Char)
     n = size(A, 1); W = zeros(n); V = zeros(n, n)

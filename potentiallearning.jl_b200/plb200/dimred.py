@@ -44,7 +44,7 @@ def compute_eigen(d, _precentered_mean=None):
 
 def eigen_symmetric(Q):
     """eigen(Symmetric(Q)) (dimension_reduction.jl:13). LAPACK on the host by default, exactly as the reference (signs and the basis of
-    degenerate clusters are solver-specific, so the default must not change solver); PLB200_EIGEN=gpu opts into pl_eigh (own solver up to n = 1184, cuSOLVER above)."""
+    degenerate clusters are solver-specific, so the default must not change solver); PLB200_EIGEN=gpu opts into pl_eigh (own solver up to n = 2048, cuSOLVER above)."""
     import os
 
     if os.environ.get("PLB200_EIGEN", "lapack") == "gpu":

@@ -3,7 +3,7 @@ built on the GPU.
 
 Hot path: `K = KernelMatrix(...)` inside the constructors (dpp.jl:25, :40). Widened: `EllEnsemble(K)`'s dense
 symmetric eigendecomposition (Determinantal.jl [external], dpp.jl:26, :41) runs on the device right behind the Gram kernel
-(pl_ell_ensemble; the library's own eigensolver up to n = 1184, cuSOLVER above); U stays device-resident, inclusion probabilities are computed there and a k-DPP draw
+(pl_ell_ensemble; the library's own eigensolver up to n = 2048, cuSOLVER above); U stays device-resident, inclusion probabilities are computed there and a k-DPP draw
 downloads only the eigenvectors it selected.
 
 What stays on the host is Determinantal.jl's sampling logic, restated so that a Python user of this mirror gets a working

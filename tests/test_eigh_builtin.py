@@ -129,8 +129,8 @@ def test_builtin_eigh_scaling_triangles_and_values_only(pl, monkeypatch):
 
 @pytest.mark.gpu
 def test_builtin_eigh_is_deterministic_and_default(pl, monkeypatch):
-    """same bits on every call (fixed reduction orders, no atomics on data); the default solver is the built-in one up to n = 1184 and
-    cuSOLVER above (PLB200_EIGH / PLB200_EIGH_OWN_MAX override), both LAPACK-accurate"""
+    """same bits on every call (fixed reduction orders, no atomics on data); the default solver is the built-in one up to n = 2048
+    (register-resident rows up to 1184, rows in L2 above) and cuSOLVER beyond (PLB200_EIGH / PLB200_EIGH_OWN_MAX override)"""
     from plb200.dpp import eigh
 
     rng = np.random.default_rng(11)
@@ -142,11 +142,27 @@ def test_builtin_eigh_is_deterministic_and_default(pl, monkeypatch):
     l3, U3 = eigh(A)
     assert np.array_equal(l1, l3) and np.array_equal(U1, U3), "n = 700 takes the built-in path by default"
     B = matrix("random_spd", 1300, rng)
-    lam, U = eigh(B)  # cuSOLVER
+    lam, U = eigh(B)  # built-in, rows in L2
     check(B, lam, U)
-    monkeypatch.setenv("PLB200_EIGH_OWN_MAX", "2048")
-    lam2, U2 = eigh(B)  # built-in, L2-resident rows
-    check(B, lam2, U2)
+    lam_o, U_o = eigh_with(monkeypatch, "own", B)
+    assert np.array_equal(lam, lam_o) and np.array_equal(U, U_o)
+    lam_c, U_c = eigh_with(monkeypatch, "cusolver", B)
+    check(B, lam_c, U_c)
+    assert np.max(np.abs(lam_c - lam)) / lam.max() < 1e-12
+    monkeypatch.delenv("PLB200_EIGH")
+    C = matrix("random_spd", 2100, rng)
+    lam, U = eigh(C)  # cuSOLVER
+    check(C, lam, U)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,kind", [(1185, "random_spd"), (1777, "rbf_kernel"), (2048, "dot_kernel"), (2049, "random_spd"), (3000, "clustered_indefinite")])
+def test_builtin_eigh_rows_in_l2(pl, monkeypatch, n, kind):
+    """the L2-resident tridiagonalisation (one and two rows per warp, both template instances) and the back-transformations above
+    n = 1024 / 2048"""
+    A = matrix(kind, n, np.random.default_rng(n))
+    lam, U = eigh_with(monkeypatch, "own", A)
+    check(A, lam, U)
 
 
 @pytest.mark.gpu
