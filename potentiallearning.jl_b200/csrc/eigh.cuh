@@ -1269,4 +1269,117 @@ __global__ void __launch_bounds__(256 / NV) eigh_backtransform_wy_kernel(const d
   }
 }
 
+// The same update on the FP64 TENSOR pipe (n <= 2048). The scalar kernel above reads one element of V from shared memory per FMA and
+// is bound by exactly that (ncu: 0.62 ms at n = 1000, FP64 pipe 12 % busy); as DMMA.8x8x4 a 16-byte read feeds 512 FMAs.
+// One CTA = 8 eigenvectors (the M of the MMA), its 8 warps own the 8-column tiles w, w+8, ... of them in registers, in the C-fragment
+// layout (lane (g, t): Z[g][8 tile + 2t], [.. + 2t + 1]). Per block of 8 reflectors (V: 8 x n, zero outside the supports, staged with
+// cp.async; T from eigh_larft_kernel<8>):
+//   Y = Z V'   : the two C registers of a tile ARE the A fragments of two MMAs if the contraction runs over the columns {8 tile + 2t}
+//                and {8 tile + 2t + 1} -- the order of a contraction is free -- and the matching B fragments V[g][8 tile + 2t (+1)]
+//                are one LDS.128; partial Y of the 8 warps are summed through shared memory in a fixed order;
+//   U = Y T'   : 12 FMAs per lane;
+//   Z -= U V   : two MMAs per tile (reflectors 0-3 and 4-7), A = -U, B = V[t (+4)][8 tile + g], C = the tile.
+template <int NT, bool DB>
+__global__ void __launch_bounds__(256) eigh_backtransform_dmma_kernel(const double* __restrict__ S, int64_t lds, const double* __restrict__ Tf, int n,
+                                                                      double* __restrict__ Z, int64_t ldz) {
+  constexpr int R = 8;
+  constexpr int NP = NT * 64;   // 8 warps x NT tiles x 8 columns
+  constexpr int PV = NP + 8;    // pitch of a staged reflector: rows alternate between the two halves of the 128-byte bank line
+  extern __shared__ double vsm[];  // (DB ? 2 : 1) x R x PV
+  __shared__ double sT[2][R * R], sYp[8][64], sY[64];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int k0 = blockIdx.x * 8;
+  const bool vrow = k0 + g < n;
+  double* zrow = Z + (size_t)(vrow ? k0 + g : 0) * ldz;
+  double z0[NT], z1[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const int c = 8 * (w + 8 * i) + 2 * t;
+    z0[i] = (vrow && c < n) ? zrow[c] : 0.0;
+    z1[i] = (vrow && c + 1 < n) ? zrow[c + 1] : 0.0;
+  }
+  const uint32_t vs_u32 = (uint32_t)__cvta_generic_to_shared(vsm);
+  auto stage = [&](int blk, int jtop, int buf) {
+    if (jtop >= 0) {
+      const int jlow = jtop - R + 1 > 0 ? jtop - R + 1 : 0;
+      const int cl = (jlow + 1) & ~7;
+      for (int q = 0; q < R; ++q) {
+        const int j = jlow + q;  // rows beyond the block (j > jtop) are zero-filled: they do nothing
+        const double* src = S + (size_t)(j <= jtop ? j : jtop) * lds;
+        const uint32_t dst = vs_u32 + (uint32_t)(((buf * R + q) * PV) * 8);
+        for (int c = cl + tid; c < NP; c += 256) cp_async8_zfill(dst + c * 8, src + (c < n ? c : 0), j <= jtop && c > j && c < n);
+      }
+      if (tid < R * R) sT[buf][tid] = Tf[(size_t)blk * R * R + tid];
+    }
+    cp_async_commit();
+  };
+  int buf = 0, blk = 0;
+  if (DB) stage(0, n - 3, 0);
+  for (int jtop = n - 3; jtop >= 0; jtop -= R, ++blk) {
+    if (DB) {
+      stage(blk + 1, jtop - R, buf ^ 1);  // the other buffer was consumed before the barrier that ended the previous round
+      cp_async_wait<1>();
+    } else {
+      stage(blk, jtop, 0);
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int jlow = jtop - R + 1 > 0 ? jtop - R + 1 : 0;
+    const int tile0 = (jlow + 1) >> 3;                 // first tile with a column inside a support
+    const int i0 = tile0 > w ? (tile0 - w + 7) >> 3 : 0;  // first own tile >= tile0
+    const double* vb = vsm + (size_t)(buf * R) * PV;
+    // ---- Y = Z V' over the own tiles (four independent accumulator pairs)
+    double ya[4] = {0.0, 0.0, 0.0, 0.0}, yb[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      if (i >= i0) {
+        const double2 bv = *reinterpret_cast<const double2*>(vb + g * PV + 8 * (w + 8 * i) + 2 * t);
+        dmma884(ya[i & 3], yb[i & 3], z0[i], bv.x);
+        dmma884(ya[i & 3], yb[i & 3], z1[i], bv.y);
+      }
+    }
+    sYp[w][g * 8 + 2 * t] = (ya[0] + ya[1]) + (ya[2] + ya[3]);
+    sYp[w][g * 8 + 2 * t + 1] = (yb[0] + yb[1]) + (yb[2] + yb[3]);
+    __syncthreads();
+    if (tid < 64) {
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc += sYp[q][tid];
+      sY[tid] = acc;
+    }
+    __syncthreads();
+    // ---- U = Y T' (upper-triangular T): this lane's A fragments of the update, negated
+    double ua = 0.0, ub = 0.0;
+#pragma unroll
+    for (int b2 = 0; b2 < R; ++b2) {
+      const double yv = sY[g * 8 + b2];
+      if (b2 >= t) ua = fma(sT[buf][t * R + b2], yv, ua);
+      if (b2 >= 4 + t) ub = fma(sT[buf][(4 + t) * R + b2], yv, ub);
+    }
+    ua = -ua;
+    ub = -ub;
+    // ---- Z -= U V
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      if (i >= i0) {
+        const int c = 8 * (w + 8 * i) + g;
+        const double b1 = vb[t * PV + c], b2 = vb[(4 + t) * PV + c];
+        dmma884(z0[i], z1[i], ua, b1);
+        dmma884(z0[i], z1[i], ub, b2);
+      }
+    }
+    __syncthreads();
+    if (DB) buf ^= 1;
+  }
+  cp_async_wait<0>();
+  if (vrow) {
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int c = 8 * (w + 8 * i) + 2 * t;
+      if (c < n) zrow[c] = z0[i];
+      if (c + 1 < n) zrow[c + 1] = z1[i];
+    }
+  }
+}
+
 }  // namespace plb

@@ -1377,6 +1377,9 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<16, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 16 * 32 * 8));
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<32, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * 32 * 32 * 8));
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_wy_kernel<64, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 64 * 32 * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_dmma_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * (16 * 64 + 8) * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_dmma_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * (8 * 64 + 8) * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_dmma_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (32 * 64 + 8) * 8));
       attr_done = true;
     }
     const int rows_per_cta = EIGH_SYTRD_THREADS / 32;
@@ -1457,7 +1460,14 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
     LAUNCH_CHECK();
     if (n <= 2048 && !getenv("PLB200_EIGH_NO_REG")) {
       const unsigned blocks = (unsigned)((n + 7) / 8);
-      if (n >= 3) {
+      if (n >= 3 && !getenv("PLB200_EIGH_SCALAR_BT")) {  // DMMA form
+        eigh_larft_kernel<8><<<(unsigned)((n - 2 + 7) / 8), 256, 0, st>>>(S, ldq, d_tau, n, d_Tf);
+        LAUNCH_CHECK();
+        if (n <= 256) eigh_backtransform_dmma_kernel<4, true><<<blocks, 256, (size_t)2 * 8 * (4 * 64 + 8) * 8, st>>>(S, ldq, d_Tf, n, dA, lda);
+        else if (n <= 512) eigh_backtransform_dmma_kernel<8, true><<<blocks, 256, (size_t)2 * 8 * (8 * 64 + 8) * 8, st>>>(S, ldq, d_Tf, n, dA, lda);
+        else if (n <= 1024) eigh_backtransform_dmma_kernel<16, true><<<blocks, 256, (size_t)2 * 8 * (16 * 64 + 8) * 8, st>>>(S, ldq, d_Tf, n, dA, lda);
+        else eigh_backtransform_dmma_kernel<32, false><<<blocks, 256, (size_t)8 * (32 * 64 + 8) * 8, st>>>(S, ldq, d_Tf, n, dA, lda);
+      } else if (n >= 3) {
 #define PLB_BT(NCH, R, NV)                                                                                                          \
   do {                                                                                                                              \
     eigh_larft_kernel<R><<<(unsigned)((n - 2 + R - 1) / R), 256, 0, st>>>(S, ldq, d_tau, n, d_Tf);                                  \
