@@ -343,7 +343,8 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_reg_kernel(S
 // The same step structure for 1184 < n <= 1024 NB with the rows in L2: 12 warps per CTA, a warp's rows (dealt cyclically, one per
 // warp up to n = 1776) pass through its registers one block of 32 chunks (1024 columns) at a time -- 32 independent loads in flight per
 // lane, the fused pass, predicated stores -- and the other warps of the SM hide the round trip. Shared memory holds v_j, v_{j+1}, w_j
-// and the next row (dynamic: 4 x 8 NB KB).
+// and the next row (dynamic: 4 x 8 NB KB). SMR (n <= 2048): the columns >= 1024 of the CTA's rows -- the part of the matrix that lives
+// longest -- stay in shared memory (<= 14 rows x 8 KB): a third of the L2 traffic, which bounds the early steps (67 MB per step at n = 2048).
 constexpr int EIGH_L2_THREADS = 384;  // 12 warps = 3 per scheduler: 168 registers per thread keep the 32-chunk block and the pass without spills
 constexpr int EIGH_L2_WARPS = EIGH_L2_THREADS / 32;
 template <bool LIVE, bool SIG>
@@ -357,7 +358,7 @@ __device__ __forceinline__ void sytrd_block_pass(int start8, double (&a)[32], co
   }
 }
 
-template <int NB>
+template <int NB, bool SMR>
 __global__ void __launch_bounds__(EIGH_L2_THREADS, 1) eigh_sytrd_l2_kernel(SytrdParams P) {
   constexpr int NP = NB * 1024;
   constexpr int NQ = (NP + EIGH_L2_THREADS - 1) / EIGH_L2_THREADS;
@@ -366,11 +367,16 @@ __global__ void __launch_bounds__(EIGH_L2_THREADS, 1) eigh_sytrd_l2_kernel(Sytrd
   double* svb1 = l2sm + NP;
   double* sw = l2sm + 2 * NP;
   double* srn = l2sm + 3 * NP;
+  double* rowsm = l2sm + 4 * NP;  // SMR: columns >= 1024 of the CTA's rows (slot (r - b) / G), 1024 doubles each
   __shared__ double s_part[EIGH_L2_WARPS], s_sc[4];
   const int n = P.n;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int G = gridDim.x, b = blockIdx.x;
   for (int c = tid; c < NP; c += EIGH_L2_THREADS) { svb0[c] = 0.0; svb1[c] = 0.0; sw[c] = 0.0; srn[c] = 0.0; }
+  if (SMR) {
+    for (int rr = b + G * wid, slot = wid; rr < n; rr += G * EIGH_L2_WARPS, slot += EIGH_L2_WARPS)
+      for (int c = lane; c < 1024; c += 32) rowsm[slot * 1024 + c] = 1024 + c < n ? __ldcg(P.S + (size_t)rr * P.lds + 1024 + c) : 0.0;
+  }
   __syncthreads();
   double tau = 0.0;
   int cur = 0;
@@ -451,19 +457,36 @@ __global__ void __launch_bounds__(EIGH_L2_THREADS, 1) eigh_sytrd_l2_kernel(Sytrd
         const int start8 = rel <= 0 ? 0 : (rel >> 3);
         double a[32];
         if (live) {
+          double* srow = rowsm + (size_t)((r - b) / G) * 1024 + lane;  // SMR, kb == 1: this row's block lives in shared memory
+          if (SMR && kb == 1) {
 #pragma unroll
-          for (int m = 0; m < 32; ++m) {
-            const int c = off + 32 * m;
-            a[m] = c < n ? __ldcg(row + c) : 0.0;
+            for (int m = 0; m < 32; ++m) a[m] = srow[32 * m];
+          } else {
+#pragma unroll
+            for (int m = 0; m < 32; ++m) {
+              const int c = off + 32 * m;
+              a[m] = c < n ? __ldcg(row + c) : 0.0;
+            }
           }
           if (!have_sigma) sytrd_block_pass<true, true>(start8, a, sv + off, sw + off, srn + off, nvr, nwr, mq - kb * 32, acc, sg, cap);
           else sytrd_block_pass<true, false>(start8, a, sv + off, sw + off, srn + off, nvr, nwr, mq - kb * 32, acc, sg, cap);
+          if (SMR && kb == 1) {
 #pragma unroll
-          for (int m = 0; m < 32; ++m) {
-            const int c = off + 32 * m;
-            if (c > jn && c < n) {
-              __stcg(row + c, a[m]);
-              if (r == jn + 1) __stcg(rbn + c, a[m]);
+            for (int m = 0; m < 32; ++m) {
+              const int c = off + 32 * m;
+              if (c > jn && c < n) {
+                srow[32 * m] = a[m];
+                if (r == jn + 1) __stcg(rbn + c, a[m]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int m = 0; m < 32; ++m) {
+              const int c = off + 32 * m;
+              if (c > jn && c < n) {
+                __stcg(row + c, a[m]);
+                if (r == jn + 1) __stcg(rbn + c, a[m]);
+              }
             }
           }
         } else {

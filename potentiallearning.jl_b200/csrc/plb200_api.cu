@@ -1368,8 +1368,9 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
     P.prof = getenv("PLB200_EIGH_PROF") ? (long long*)d_rho : nullptr;  // over d_rho/d_Tf: written at the end of sytrd, read back below
     static bool attr_done = false;
     if (!attr_done) {
-      CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_l2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2048 * 8));
-      CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_l2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_l2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4 * 2048 + 16 * 1024) * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_l2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2048 * 8));
+      CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_l2_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 8));
       CUDA_TRY(cudaFuncSetAttribute(dc_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * EIGH_MAX_N));
       CUDA_TRY(cudaFuncSetAttribute(dc_small_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * (EIGH_SMALL_GEMM_MAX | 1) * 8));
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1396,10 +1397,14 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
     } else {  // rows in L2, 12 warps per CTA
       G = (n + EIGH_L2_WARPS - 1) / EIGH_L2_WARPS;
       if (G > g.num_sms) G = g.num_sms;
-      if (n <= 2048)
-        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)eigh_sytrd_l2_kernel<2>, dim3(G), dim3(EIGH_L2_THREADS), args, (size_t)4 * 2048 * 8, st));
+      const int rows_per_cta = (n + G - 1) / G;  // <= 14 at n <= 2048
+      if (n <= 2048 && !getenv("PLB200_EIGH_NO_SMR"))
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)eigh_sytrd_l2_kernel<2, true>, dim3(G), dim3(EIGH_L2_THREADS), args,
+                                             (size_t)(4 * 2048 + rows_per_cta * 1024) * 8, st));
+      else if (n <= 2048)
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)eigh_sytrd_l2_kernel<2, false>, dim3(G), dim3(EIGH_L2_THREADS), args, (size_t)4 * 2048 * 8, st));
       else
-        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)eigh_sytrd_l2_kernel<4>, dim3(G), dim3(EIGH_L2_THREADS), args, (size_t)4 * 4096 * 8, st));
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)eigh_sytrd_l2_kernel<4, false>, dim3(G), dim3(EIGH_L2_THREADS), args, (size_t)4 * 4096 * 8, st));
     }
     LAUNCH_CHECK();
   }
