@@ -369,9 +369,14 @@ def other_configs(dev, peak_tflops, rank, world, sync):
             Kfull = (K1 + K1.T - torch.diag(torch.diagonal(K1)))
             resid = float((Kfull @ U_own.T - U_own.T * W_own[None, :]).abs().max() / W_own.abs().max())
             orth = float((U_own @ U_own.T - torch.eye(n1, device=dev, dtype=torch.float64)).abs().max())
+            Kh = Kfull.cpu().numpy()
+            t0 = time.perf_counter()
+            np.linalg.eigh(Kh)
+            lapack_ms = (time.perf_counter() - t0) * 1e3  # what the reference does here: LAPACK on the host cores
             res["eigh_c1"] = {"workload": f"eigen(Symmetric(K)) of the config-1 kernel matrix (N={n1}; the same size as compute_eigen at K=1000, configs[3]): built-in "
                                           "tridiagonalisation + divide and conquer + back-transformation, device-resident, eigenvectors wanted",
                               "ms": own_ms, "cusolver_xsyevd_ms_same_box": lib_ms, "speedup_vs_cusolver": lib_ms / own_ms,
+                              "host_lapack_eigh_ms": lapack_ms, "host_cores": os.cpu_count(),
                               "max_eig_diff_vs_cusolver_rel": float((W_own - W_lib).abs().max() / W_lib.abs().max()),
                               "residual_rel": resid, "orthogonality": orth}
             del X1, K1
