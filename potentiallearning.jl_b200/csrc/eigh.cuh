@@ -381,6 +381,8 @@ __global__ void __launch_bounds__(EIGH_L2_THREADS, 1) eigh_sytrd_l2_kernel(Sytrd
   double tau = 0.0;
   int cur = 0;
   unsigned long long target = 0;
+  long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = clock64();  // phase cycle counters of one warp (PLB200_EIGH_PROF)
+#define PLB_PF(i) do { if (P.prof) { const long long t_ = clock64(); pf[i] += t_ - tk; tk = t_; } } while (0)
   for (int j = -1; j <= n - 2; ++j, cur ^= 1) {
     const int jn = j + 1;
     const int m0 = jn >> 5;
@@ -415,6 +417,7 @@ __global__ void __launch_bounds__(EIGH_L2_THREADS, 1) eigh_sytrd_l2_kernel(Sytrd
       }
       __syncthreads();
       const double alpha = s_sc[0], wjn = s_sc[1];
+      PLB_PF(0);
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int c = cbase + q * EIGH_L2_THREADS;
@@ -429,7 +432,9 @@ __global__ void __launch_bounds__(EIGH_L2_THREADS, 1) eigh_sytrd_l2_kernel(Sytrd
         }
       }
     }
+    PLB_PF(1);
     __syncthreads();
+    PLB_PF(2);
     const double djn = s_sc[2];
     if (jn == n - 1) {
       if (b == 0 && tid == 0) P.d[jn] = djn;
@@ -520,6 +525,7 @@ __global__ void __launch_bounds__(EIGH_L2_THREADS, 1) eigh_sytrd_l2_kernel(Sytrd
       }
     }
     if (lane == 0) s_part[wid] = pdw;
+    PLB_PF(3);
     __syncthreads();
     // ---- (3) the scaled reflector into the other buffer (the owner of row jn also stores it), T's entries, partial dot
     {
@@ -545,8 +551,14 @@ __global__ void __launch_bounds__(EIGH_L2_THREADS, 1) eigh_sytrd_l2_kernel(Sytrd
     }
     tau = taun;
     target += 1ull;
+    PLB_PF(4);
     if (!sytrd_grid_barrier(P.bar, target)) return;
+    PLB_PF(5);
   }
+  if (P.prof && lane == 0 && wid == 6) {
+    for (int i = 0; i < 8; ++i) P.prof[8 * b + i] = pf[i];
+  }
+#undef PLB_PF
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
