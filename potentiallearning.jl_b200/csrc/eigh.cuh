@@ -344,7 +344,10 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_reg_kernel(S
 // warp up to n = 1776) pass through its registers one block of 32 chunks (1024 columns) at a time -- 32 independent loads in flight per
 // lane, the fused pass, predicated stores -- and the other warps of the SM hide the round trip. Shared memory holds v_j, v_{j+1}, w_j
 // and the next row (dynamic: 4 x 8 NB KB). SMR (n <= 2048): the columns >= 1024 of the CTA's rows -- the part of the matrix that lives
-// longest -- stay in shared memory (<= 14 rows x 8 KB): a third of the L2 traffic, which bounds the early steps (67 MB per step at n = 2048).
+// longest -- stay in shared memory (<= 14 rows x 8 KB): a third of the L2 traffic (67 MB per step at n = 2048 without it). Measured and
+// rejected: ALL of every row in shared memory (n <= 1536) is slower (n = 1500: 9.4 -> 10.5 ms) -- the pass then moves five 256-byte
+// shared-memory transactions per 32 columns and row (v, w, next row, row in, row out) against 128 B / clk / SM; prefetching the next
+// step's first block across the grid barrier changes nothing.
 constexpr int EIGH_L2_THREADS = 384;  // 12 warps = 3 per scheduler: 168 registers per thread keep the 32-chunk block and the pass without spills
 constexpr int EIGH_L2_WARPS = EIGH_L2_THREADS / 32;
 template <bool LIVE, bool SIG>
