@@ -1366,8 +1366,8 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
     SytrdParams P;
     P.S = S; P.lds = ldq; P.n = n; P.d = d_d; P.e = d_e; P.tau = d_tau; P.p = d_p; P.pd = d_pd; P.rowbuf = d_rowbuf; P.bar = d_bar;
     P.prof = getenv("PLB200_EIGH_PROF") ? (long long*)d_rho : nullptr;  // over d_rho/d_Tf: written at the end of sytrd, read back below
-    static bool attr_done = false;
-    if (!attr_done) {
+    static int attr_dev = -1;  // function attributes are per device: set them again when the library is re-initialised on another one
+    if (attr_dev != g.device) {
       CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_l2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4 * 2048 + 16 * 1024) * 8));
       CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_l2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2048 * 8));
       CUDA_TRY(cudaFuncSetAttribute(eigh_sytrd_l2_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 8));
@@ -1381,7 +1381,7 @@ int eigh_own_impl(double* dA, int64_t n64, int64_t lda, int fill, int want_vecto
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_dmma_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * (16 * 64 + 8) * 8));
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_dmma_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * (8 * 64 + 8) * 8));
       CUDA_TRY(cudaFuncSetAttribute(eigh_backtransform_dmma_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (32 * 64 + 8) * 8));
-      attr_done = true;
+      attr_dev = g.device;
     }
     const int rows_per_cta = EIGH_SYTRD_THREADS / 32;
     int G = (n + rows_per_cta - 1) / rows_per_cta;
