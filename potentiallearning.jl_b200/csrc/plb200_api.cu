@@ -766,6 +766,7 @@ struct SyrkSchedConfig {
   int mode;        // 0 waves, 1 streamk
   int waves;       // CTAs per SM
   double diag_cost;
+  int min_rounds;  // streamk: at least this many rounds of CTAs (experiment knob PLB200_SYRK_MIN_ROUNDS; 0 = the model decides)
 };
 
 const SyrkSchedConfig& syrk_sched_config() {
@@ -782,6 +783,8 @@ const SyrkSchedConfig& syrk_sched_config() {
     if (c.waves <= 0) c.waves = 20;  // waves: CTAs per SM; streamk: the most rounds the chunk-count search may use
     const char* dc = getenv("PLB200_SYRK_DIAG_COST");
     if (dc && atof(dc) > 0.0) c.diag_cost = atof(dc);
+    const char* mr = getenv("PLB200_SYRK_MIN_ROUNDS");
+    c.min_rounds = mr ? atoi(mr) : 0;
     return c;
   }();
   return cfg;
@@ -841,6 +844,7 @@ void build_syrk_schedule(int64_t R, int T, int nunits, int num_sms, const SyrkSc
     const int64_t nctas = noff ? noff * n + ndiag * nd : ndiag * nd;
     const int64_t rounds = (nctas + num_sms - 1) / num_sms;
     if (rounds > cfg.waves && best >= 0.0) break;
+    if (rounds < cfg.min_rounds) continue;
     const double c = noff ? std::max(1.0 / (double)n, cfg.diag_cost / (double)nd) : cfg.diag_cost / (double)nd;
     // fewer than 4 rounds leave the hardware too little to even out SM speed differences with (measured: 1 round -2.7 %, 2 rounds
     // -0.2..-1.1 %, 3 rounds -0.1..-0.9 % against 4)
