@@ -247,7 +247,7 @@ int pl_allreduce_dev(double* dbuf, int64_t count, void* stream);
 /* eigen(Symmetric(Q)) (dimension_reduction.jl:13; LAPACK in the reference) and the eigendecomposition inside EllEnsemble(K)
  * (Determinantal.jl [external], reached from dpp.jl:26,41).
  * n <= 2048: the library's OWN solver (csrc/eigh.cuh) -- Householder tridiagonalisation in one cooperative kernel (n <= 1184, the
- * sizes of configs 1, 3, 4 -- N = 1000, K = 500 / 1000: the matrix in registers, 2.6x faster than cuSOLVER; above: rows in L2, 1.2x),
+ * sizes of configs 1, 3, 4 -- N = 1000, K = 500 / 1000: the matrix in registers, 2.7x faster than cuSOLVER; above: rows in L2 / shared memory, 1.6x),
  * divide and conquer on the tridiagonal matrix with its eigenvector updates on the DMMA Gram engine, blocked back-transformation.
  * No library call; results are bitwise reproducible.
  * Larger n: cuSOLVER's Xsyevd, loaded with dlopen at first use (PLB200_CUSOLVER overrides the search path).

@@ -114,7 +114,8 @@ struct SytrdParams {
   double* p;        // 2 x n A v of the current step (rows written by their owners), double-buffered by step parity like rowbuf:
                     //       a CTA that is already forming the next product must not overwrite what a slower CTA still reads
   double* pd;       // 2 x 256 partial v . (A v) per CTA, same parity scheme
-  double* rowbuf;   // 2 x n broadcast copy of the next row, double-buffered by step parity
+  double* rowbuf;   // 2 x n the next row of the updated matrix (= its next column: every row owner publishes its element),
+                    //       double-buffered by step parity
   unsigned long long* bar;  // [0, grid) one slot per CTA (zeroed by the host), [256] abort flag
   long long* prof;  // NULL, or 4 cycle counters per CTA (thread 0: staging, compute, publish, barrier) -- scripts/eigh_probe.py
 };
@@ -293,14 +294,11 @@ __global__ void __launch_bounds__(EIGH_SYTRD_THREADS, 1) eigh_sytrd_reg_kernel(S
       const double prod = fma(scl, accs, acc0);
       const double vnr = r >= jn + 2 ? srn[r] * scl : 1.0;
       pdw = vnr * prod;
-      if (lane == 0) __stcg(P.p + (size_t)(j & 1) * n + r, prod);
-      if (r == jn + 1) {
-        double* rbn = P.rowbuf + (size_t)(j & 1) * n;
-#pragma unroll
-        for (int m = 0; m < NCH; ++m) {
-          const int c = lane + 32 * m;
-          if (m >= m0 && c > jn && c < n) __stcg(rbn + c, a[m]);
-        }
+      if (lane == 0) {
+        __stcg(P.p + (size_t)(j & 1) * n + r, prod);
+        // row jn + 1 of the updated matrix, which every CTA needs next, is column jn + 1 by symmetry: every row owner publishes
+        // its own element of it (no owner of the whole row on the critical path of the step)
+        __stcg(P.rowbuf + (size_t)(j & 1) * n + r, acc0);
       }
     }
     if (lane == 0) s_part[wid] = pdw;
@@ -484,7 +482,6 @@ __global__ void __launch_bounds__(EIGH_L2_THREADS, 1) eigh_sytrd_l2_kernel(Sytrd
               const int c = off + 32 * m;
               if (c > jn && c < n) {
                 srow[32 * m] = a[m];
-                if (r == jn + 1) __stcg(rbn + c, a[m]);
               }
             }
           } else {
@@ -493,7 +490,6 @@ __global__ void __launch_bounds__(EIGH_L2_THREADS, 1) eigh_sytrd_l2_kernel(Sytrd
               const int c = off + 32 * m;
               if (c > jn && c < n) {
                 __stcg(row + c, a[m]);
-                if (r == jn + 1) __stcg(rbn + c, a[m]);
               }
             }
           }
@@ -524,7 +520,10 @@ __global__ void __launch_bounds__(EIGH_L2_THREADS, 1) eigh_sytrd_l2_kernel(Sytrd
         const double prod = fma(scl, accs, acc0);
         const double vnr = r >= jn + 2 ? srn[r] * scl : 1.0;
         pdw += vnr * prod;
-        if (lane == 0) __stcg(P.p + (size_t)(j & 1) * n + r, prod);
+        if (lane == 0) {
+          __stcg(P.p + (size_t)(j & 1) * n + r, prod);
+          __stcg(rbn + r, acc0);  // this row's element of the next row (column jn + 1 by symmetry)
+        }
       }
     }
     if (lane == 0) s_part[wid] = pdw;

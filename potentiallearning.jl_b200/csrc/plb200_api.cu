@@ -1512,7 +1512,7 @@ int eigh_dev_impl(double* dA, int64_t n, int64_t lda, int fill, int want_vectors
   {
     const char* mode = getenv("PLB200_EIGH");
     const char* mx = getenv("PLB200_EIGH_OWN_MAX");
-    int64_t own_max = mx ? atoll(mx) : 2048;  // <= 1184: register-resident tridiagonalisation (2.6x cuSOLVER); <= 2048: rows in L2 (1.2x)
+    int64_t own_max = mx ? atoll(mx) : 2048;  // <= 1184: register-resident tridiagonalisation (2.7x cuSOLVER); <= 2048: rows in L2 (1.6x)
     if (own_max > EIGH_MAX_N) own_max = EIGH_MAX_N;
     const bool force_own = mode && !strcmp(mode, "own"), force_lib = mode && !strcmp(mode, "cusolver");
     if (force_own || (!force_lib && n <= own_max)) return eigh_own_impl(dA, n, lda, fill, want_vectors, dW, st);
