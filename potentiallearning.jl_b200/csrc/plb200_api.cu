@@ -1515,7 +1515,19 @@ int eigh_dev_impl(double* dA, int64_t n, int64_t lda, int fill, int want_vectors
     int64_t own_max = mx ? atoll(mx) : 2048;  // <= 1184: register-resident tridiagonalisation (2.7x cuSOLVER); <= 2048: rows in L2 (1.6x)
     if (own_max > EIGH_MAX_N) own_max = EIGH_MAX_N;
     const bool force_own = mode && !strcmp(mode, "own"), force_lib = mode && !strcmp(mode, "cusolver");
-    if (force_own || (!force_lib && n <= own_max)) return eigh_own_impl(dA, n, lda, fill, want_vectors, dW, st);
+    if (force_own) return eigh_own_impl(dA, n, lda, fill, want_vectors, dW, st);
+    if (!force_lib && n <= own_max) {
+      const int rc = eigh_own_impl(dA, n, lda, fill, want_vectors, dW, st);
+      // automatic routing only: a device that cannot run the cooperative kernels (launch refused, barrier timed out -- the input is
+      // untouched until the last step) hands the matrix to cuSOLVER, and says so once; bad input is reported as it is
+      if (rc == PL_OK || rc == PL_EINVAL) return rc;
+      static bool told = false;
+      if (!told) {
+        fprintf(stderr, "libplb200: built-in eigensolver failed (%s); falling back to cuSOLVER for this process\n", pl_last_error());
+        told = true;
+      }
+      cudaGetLastError();
+    }
   }
   PL_TRY(cusolver_ready());
   cusolverStatus_t r = cs.SetStream(cs.h, st);
