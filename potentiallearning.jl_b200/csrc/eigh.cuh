@@ -6,12 +6,16 @@
 //   1. eigh_sytrd_*_kernel    Householder tridiagonalisation as ONE persistent cooperative kernel: the rank-2 update of step j and
 //                             the symmetric matrix-vector product of step j+1 are one pass over the rows a warp owns (rows dealt
 //                             cyclically; in registers for n <= 1184, through L2 above), every CTA forms the next reflector
-//                             redundantly from a broadcast copy of the next row, one grid barrier per step.
+//                             redundantly from the next row of the matrix (its next column: the row owners publish their
+//                             elements), one grid barrier per step.
 //   2. dc_*                   divide and conquer on the tridiagonal matrix (Cuppen / Gu-Eisenstat): Jacobi leaves (<= 32), per
-//                             merge: deflation, secular equation by bisection ON THE BIT PATTERN of the offset from the nearer
-//                             pole (<= 63 steps to the last bit, whatever the scale), Loewner re-computation of the update vector,
-//                             and the eigenvector update Q <- Q V as a product on the DMMA Gram engine (gram.cuh, LINEAR epilogue).
-//   3. eigh_backtransform     applies the reflectors to the eigenvectors of T (one warp per vector, reflectors streamed from L2).
+//                             merge: deflation, secular equation by a bracketed rational iteration whose bracket lives ON THE BIT
+//                             PATTERN of the offset from the nearer pole (a bisection step halves the number of doubles left,
+//                             whatever the scale), Loewner re-computation of the update vector, and the eigenvector update
+//                             Q <- Q V as a product on the DMMA Gram engine (gram.cuh, LINEAR epilogue).
+//   3. eigh_backtransform_*   applies the reflectors to the eigenvectors of T, eight at a time in the compact WY form, as
+//                             DMMA.8x8x4 with the eigenvectors in registers (n <= 2048; a scalar form and a one-warp-per-vector
+//                             form remain for experiments and for larger n).
 //
 // scripts/eig_proto/dc_proto.py is the numpy model of step 2 (same formulas, same order) used to validate the algorithm on the CPU.
 #pragma once
