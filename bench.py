@@ -379,6 +379,22 @@ def other_configs(dev, peak_tflops, rank, world, sync):
                               "host_lapack_eigh_ms": lapack_ms, "host_cores": os.cpu_count(),
                               "max_eig_diff_vs_cusolver_rel": float((W_own - W_lib).abs().max() / W_lib.abs().max()),
                               "residual_rel": resid, "orthogonality": orth}
+            # ---- config 1 end to end through the public host API: kDPP(features, DotProduct) = KernelMatrix + EllEnsemble(K) + rescale! +
+            # inclusion probabilities (dpp.jl:35-44, 69), host features in, lambda / K / probabilities out; K (8 MB) travels back once
+            import plb200 as _pl
+
+            Xh = X1.cpu().numpy()
+            ts = []
+            for rep in range(4):
+                t0 = time.perf_counter()
+                ell = _pl.EllEnsemble.from_features(Xh, _pl.DotProduct())
+                _pl.rescale_(ell, 200)  # below the numerical rank of the ensemble (d(d+1)/2 = 351 for DotProduct(2) on 26 features)
+                pr = _pl.inclusion_prob(ell)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            res["kdpp_c1_e2e"] = {"workload": f"kDPP(features, DotProduct(2)) N={n1} d={d1} batch_size=200 (BASELINE configs[0]) through the host API: kernel matrix, "
+                                              "L-ensemble eigendecomposition (built-in solver), rescale!, inclusion probabilities; host arrays in and out",
+                                  "ms": float(np.median(ts[1:])), "sum_inclusion_prob": float(pr.sum()),
+                                  "host_lapack_eigh_alone_ms": lapack_ms}
             del X1, K1
     except Exception as e:  # never let the side measurements take the headline line down
         import traceback
